@@ -1,0 +1,11 @@
+"""petsyn_b200 -- B200-native (sm_100a) drop-in replacements for the 3D T1->PET generator hot path of
+jessyblues/Causality-Informed-PET-Synthesis-from-Multi-modal-Data.
+
+Host code is Python/PyTorch (device memory, streams, torch.distributed); all compute goes through the
+C ABI of ``lib/libpetsyn.so`` (``include/petsyn.h``).  No Triton, no backend dispatch, no CPU fallback.
+"""
+from . import _cabi  # noqa: F401  (fails loudly when the CUDA library has not been built)
+from . import ops  # noqa: F401
+from .unet_model import UnetGenerator3d, UnetSkipConnectionBlock3d  # noqa: F401
+
+__all__ = ["UnetGenerator3d", "UnetSkipConnectionBlock3d", "ops"]

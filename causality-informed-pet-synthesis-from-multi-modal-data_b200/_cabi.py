@@ -1,0 +1,116 @@
+"""ctypes binding of ``libpetsyn.so`` (the C ABI declared in ``include/petsyn.h``).
+
+This is the *only* place the package touches native code.  There is no CPU implementation and no
+alternative backend: if the shared library is missing the import fails loudly, and every kernel entry
+point raises when called without a CUDA device.
+
+Error convention (mirrors the reference's Python exceptions): ``PETSYN_EINVAL`` ->
+``ValueError``; every other failure -> ``RuntimeError``; the message is ``petsyn_last_error()``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libpetsyn.so")
+
+if not os.path.exists(LIB_PATH):
+    raise ImportError(
+        f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+        "(or `make -C <package>/csrc`). There is no CPU/PyTorch fallback for this package.")
+
+lib = C.CDLL(LIB_PATH)
+
+# ---------------------------------------------------------------------------------------------- constants
+OP_CONV, OP_UPCONV, OP_CONVT = 0, 1, 2
+ACT_NONE, ACT_RELU, ACT_LRELU, ACT_SILU, ACT_TANH = 0, 1, 2, 3, 4
+E_INVAL, E_CUDA, E_NOMEM = -1, -2, -3
+
+
+class ConvDesc(C.Structure):
+    """``petsyn_conv_desc`` (include/petsyn.h)."""
+    _fields_ = [
+        ("op", C.c_int32),
+        ("n", C.c_int32), ("d", C.c_int32), ("h", C.c_int32), ("w", C.c_int32),
+        ("cin", C.c_int32), ("cout", C.c_int32),
+        ("ksize", C.c_int32), ("stride", C.c_int32), ("pad", C.c_int32),
+        ("x_cstride", C.c_int32), ("x_coff", C.c_int32),
+        ("y_cstride", C.c_int32), ("y_coff", C.c_int32),
+        ("dy_cstride", C.c_int32), ("dy_coff", C.c_int32),
+        ("dx_cstride", C.c_int32), ("dx_coff", C.c_int32),
+        ("epi_act", C.c_int32),
+        ("epi_slope", C.c_float),
+    ]
+
+
+_vp, _i32, _i64, _f32, _sz = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_size_t
+
+# name -> (restype, argtypes); every symbol declared in include/petsyn.h
+SIGNATURES = {
+    "petsyn_version": (_i32, []),
+    "petsyn_last_error": (C.c_char_p, []),
+    "petsyn_conv_plan_create": (_i32, [C.POINTER(ConvDesc), C.POINTER(_vp)]),
+    "petsyn_conv_plan_destroy": (None, [_vp]),
+    "petsyn_conv_out_dims": (_i32, [_vp, C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i32)]),
+    "petsyn_conv_flops": (_i32, [_vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "petsyn_conv_packed_fprop_bytes": (_sz, [_vp]),
+    "petsyn_conv_packed_dgrad_bytes": (_sz, [_vp]),
+    "petsyn_conv_wgrad_scratch_bytes": (_sz, [_vp]),
+    "petsyn_conv_pack_weights": (_i32, [_vp, _vp, _vp, _vp, _vp]),
+    "petsyn_conv_fprop": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp]),
+    "petsyn_conv_dgrad": (_i32, [_vp, _vp, _vp, _vp, _vp]),
+    "petsyn_conv_wgrad": (_i32, [_vp, _vp, _vp, _vp, _vp, _i32, _vp]),
+    "petsyn_stem_conv_k4s2_fwd": (_i32, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
+    "petsyn_stem_conv_k4s2_wgrad": (_i32, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
+    "petsyn_head_upconv_tanh_fwd": (_i32, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
+    "petsyn_head_upconv_tanh_bwd": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
+    "petsyn_bn_stats": (_i32, [_vp, _vp, _i64, _i32, _vp]),
+    "petsyn_bn_finalize": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _f32, _f32, _i32, _vp]),
+    "petsyn_norm_act_fwd": (_i32, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp, _i32, _i32, _i32, _f32, _i64, _i32, _vp]),
+    "petsyn_norm_act_bwd_reduce": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp, _i32, _i32, _i32, _f32,
+                                          _vp, _i64, _i32, _vp]),
+    "petsyn_norm_act_bwd_apply": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp, _i32, _i32, _i32,
+                                         _f32, _vp, _vp, _vp, _vp, _i64, _i32, _vp]),
+    "petsyn_l1_loss_fwd_bwd": (_i32, [_vp, _vp, _vp, _vp, _i64, _f32, _vp]),
+    "petsyn_mse_const_fwd_bwd": (_i32, [_vp, _f32, _vp, _vp, _i64, _f32, _vp]),
+    "petsyn_adam_step": (_i32, [_vp, _vp, _vp, _vp, _i64, _f32, _f32, _f32, _f32, _i32, _vp]),
+    "petsyn_sumsq": (_i32, [_vp, _vp, _i64, _vp]),
+}
+
+for _name, (_res, _args) in SIGNATURES.items():
+    _fn = getattr(lib, _name)        # AttributeError here == the library does not export a declared symbol
+    _fn.restype = _res
+    _fn.argtypes = _args
+
+
+def last_error() -> str:
+    msg = lib.petsyn_last_error()
+    return msg.decode("utf-8", "replace") if msg else ""
+
+
+def check(rc: int, what: str = "") -> None:
+    """Translate a C return code into the reference's exception convention."""
+    if rc == 0:
+        return
+    msg = f"{what}: {last_error()}" if what else last_error()
+    if rc == E_INVAL:
+        raise ValueError(msg)
+    raise RuntimeError(msg)
+
+
+def ptr(t) -> Optional[int]:
+    """Device pointer of a torch tensor (None -> NULL)."""
+    return None if t is None else t.data_ptr()
+
+
+def stream_ptr() -> int:
+    import torch
+    return torch.cuda.current_stream().cuda_stream
+
+
+def require_cuda() -> None:
+    import torch
+    if not torch.cuda.is_available():
+        raise RuntimeError("petsyn: a CUDA device (B200, sm_100a) is required; there is no CPU fallback")

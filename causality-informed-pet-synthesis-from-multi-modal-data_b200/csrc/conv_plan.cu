@@ -1,0 +1,636 @@
+// Host side of the convolution family: turns a petsyn_conv_desc into "tap programs" (which input view / voxel offset /
+// merged kernel taps every GEMM K-block uses), packs weights accordingly, encodes TMA descriptors and launches the
+// tcgen05 kernels of igemm_kernels.cuh.
+//
+// One formalism covers every operator on the hot path.  Per spatial axis an operator is a small table of
+//   (output phase r, input phase b, voxel offset, {original kernel indices merged into this tap})
+// and the 3-D program is the outer product of the three axis tables:
+//   Conv s1            y[o]     = sum_k W[k] x[o + k - p]                      1 output view, 1 input view
+//   Conv s2            y[o]     = sum_k W[k] x[2o + k - p]                     input read through 8 stride-2 phase views
+//   Upsample x2 + Conv y[2q+r]  = sum_k W[k] x[q + floor((r + k - p)/2)]       8 output phase views; taps that hit the same
+//                                                                              source voxel are merged (27 -> 8 per phase)
+//   ConvTranspose s2   y[2q+b]  = sum_{k: b+p-k even} W[k] x[q + (b+p-k)/2]    8 output phase views
+// and the backward-data operators are the same four shapes with x and y exchanged.
+#include <algorithm>
+#include <cstring>
+#include <vector>
+
+#include "common.h"
+#include "igemm_kernels.cuh"
+
+namespace petsyn {
+
+// ------------------------------------------------------------------------------------------------ axis programs
+struct AxisTap {
+  int a_phase;           // 0/1 phase of the (stride-2) input view, 0 when the input is not phased
+  int off;               // offset in the input view's grid
+  std::vector<int> ks;   // original kernel indices along this axis that land on this tap
+};
+struct AxisProg {
+  bool a_phased = false;
+  bool out_phased = false;
+  std::vector<std::vector<AxisTap>> subs;   // [1] or [2 output phases]
+};
+
+static int floordiv(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
+
+// gather with unit stride: in = out + sign*(k - p)
+static AxisProg axis_s1(int k, int p, int sign) {
+  AxisProg a;
+  a.subs.resize(1);
+  for (int i = 0; i < k; ++i) a.subs[0].push_back({0, sign * (i - p), {i}});
+  return a;
+}
+// gather through stride-2 phase views: in = 2*out + k - p
+static AxisProg axis_s2_gather(int k, int p) {
+  AxisProg a;
+  a.a_phased = true;
+  a.subs.resize(1);
+  for (int i = 0; i < k; ++i) {
+    int e = i - p;
+    int b = ((e % 2) + 2) % 2;
+    a.subs[0].push_back({b, (e - b) / 2, {i}});
+  }
+  return a;
+}
+// scatter form (transposed / backward of stride 2): out = 2*q + b gets in[q + (b + p - k)/2] for matching parity
+static AxisProg axis_s2_scatter(int k, int p) {
+  AxisProg a;
+  a.out_phased = true;
+  a.subs.resize(2);
+  for (int b = 0; b < 2; ++b)
+    for (int i = 0; i < k; ++i)
+      if (((b + p - i) % 2) == 0) a.subs[b].push_back({0, floordiv(b + p - i, 2), {i}});
+  return a;
+}
+// nearest x2 upsample followed by a k-tap conv: out = 2q + r reads src[q + floor((r + k - p)/2)]; equal offsets merge
+static AxisProg axis_up_fwd(int k, int p) {
+  AxisProg a;
+  a.out_phased = true;
+  a.subs.resize(2);
+  for (int r = 0; r < 2; ++r)
+    for (int i = 0; i < k; ++i) {
+      int off = floordiv(r + i - p, 2);
+      bool merged = false;
+      for (auto& t : a.subs[r])
+        if (t.off == off) { t.ks.push_back(i); merged = true; }
+      if (!merged) a.subs[r].push_back({0, off, {i}});
+    }
+  return a;
+}
+// backward-data of the above: dsrc[s] = sum_r sum_taps dy_r[s - off]
+static AxisProg axis_up_bwd(int k, int p) {
+  AxisProg f = axis_up_fwd(k, p);
+  AxisProg a;
+  a.a_phased = true;
+  a.subs.resize(1);
+  for (int r = 0; r < 2; ++r)
+    for (auto& t : f.subs[r]) a.subs[0].push_back({r, -t.off, t.ks});
+  return a;
+}
+
+// ------------------------------------------------------------------------------------------------ 3-D programs
+struct TapDef {
+  int a_view, dw, dh, dd;
+  std::vector<int> src;   // flat indices (kd*k + kh)*k + kw of the original kernel taps summed into this tap
+};
+struct Program {
+  bool a_phased = false, out_phased = false;
+  std::vector<std::vector<TapDef>> subs;
+  int max_taps = 0;
+};
+
+static Program make_program(const AxisProg& ax, int k) {
+  Program P;
+  P.a_phased = ax.a_phased;
+  P.out_phased = ax.out_phased;
+  const int np = (int)ax.subs.size();
+  for (int rd = 0; rd < np; ++rd)
+    for (int rh = 0; rh < np; ++rh)
+      for (int rw = 0; rw < np; ++rw) {
+        std::vector<TapDef> taps;
+        for (auto& td : ax.subs[rd])
+          for (auto& th : ax.subs[rh])
+            for (auto& tw : ax.subs[rw]) {
+              TapDef t;
+              t.a_view = ax.a_phased ? (td.a_phase * 4 + th.a_phase * 2 + tw.a_phase) : 0;
+              t.dd = td.off; t.dh = th.off; t.dw = tw.off;
+              for (int kd : td.ks)
+                for (int kh : th.ks)
+                  for (int kw : tw.ks) t.src.push_back((kd * k + kh) * k + kw);
+              taps.push_back(t);
+            }
+        P.max_taps = std::max(P.max_taps, (int)taps.size());
+        P.subs.push_back(std::move(taps));
+      }
+  return P;
+}
+
+// ------------------------------------------------------------------------------------------------ device tables
+struct TapSrcDev {
+  int32_t nsrc;
+  int32_t src[8];
+};
+struct InvEntryDev {   // for one original tap k: where its gradient contributions live in the packed scratch
+  int32_t n;
+  int32_t sub[8];
+  int32_t tap[8];
+};
+
+__global__ void pack_weights_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out,
+                                    const TapSrcDev* __restrict__ tbl, int nsubs, int max_taps, int R, int Kc,
+                                    int kc_pad, int k3, int swap) {
+  const int64_t ldb = (int64_t)max_taps * kc_pad;
+  const int64_t total = (int64_t)nsubs * R * ldb;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % kc_pad);
+    int64_t q = i / kc_pad;
+    const int t = (int)(q % max_taps);
+    q /= max_taps;
+    const int r = (int)(q % R);
+    const int sub = (int)(q / R);
+    float acc = 0.f;
+    if (c < Kc) {
+      const TapSrcDev e = tbl[sub * max_taps + t];
+      for (int j = 0; j < e.nsrc; ++j) {
+        const int64_t idx = swap ? ((int64_t)c * R + r) * k3 + e.src[j] : ((int64_t)r * Kc + c) * k3 + e.src[j];
+        acc += w[idx];
+      }
+    }
+    out[i] = __float2bfloat16(acc);
+  }
+}
+
+// scratch [nsubs*R, max_taps*kc_pad] fp32 -> dw in PyTorch layout
+__global__ void unpack_wgrad_kernel(const float* __restrict__ scratch, float* __restrict__ dw,
+                                    const InvEntryDev* __restrict__ inv, int max_taps, int R, int Kc, int kc_pad,
+                                    int k3, int swap, int accumulate) {
+  const int64_t ldb = (int64_t)max_taps * kc_pad;
+  const int64_t total = (int64_t)R * Kc * k3;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    // iterate with c fastest so that scratch reads are coalesced
+    const int c = (int)(i % Kc);
+    int64_t q = i / Kc;
+    const int k = (int)(q % k3);
+    const int r = (int)(q / k3);
+    const InvEntryDev e = inv[k];
+    float acc = 0.f;
+    for (int j = 0; j < e.n; ++j) acc += scratch[((int64_t)e.sub[j] * R + r) * ldb + (int64_t)e.tap[j] * kc_pad + c];
+    const int64_t idx = swap ? ((int64_t)c * R + r) * k3 + k : ((int64_t)r * Kc + c) * k3 + k;
+    if (accumulate) dw[idx] += acc; else dw[idx] = acc;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ plan
+struct GemmSide {           // one gather-form GEMM (fprop or dgrad)
+  Program prog;
+  int R = 0, Kc = 0;        // output channels / reduction channels of this GEMM
+  int kc_pad = 0, kch = 64; // K-chunk (channels per pipeline stage)
+  bool swap = false;        // packed B reads W[c][r][k] instead of W[r][c][k]
+  int out_d = 0, out_h = 0, out_w = 0;   // grid of ONE output view (phase grid if out_phased)
+  int box_w = 0, box_h = 0, box_d = 0;
+  int block_n = 128;
+  IgemmTap* d_taps = nullptr;
+  TapSrcDev* d_src = nullptr;
+  std::vector<IgemmSub> subs;
+  // cached TMA descriptors, keyed by the base pointers they were built for
+  const void* key_a = nullptr; const void* key_b = nullptr; const void* key_c = nullptr;
+  IgemmParams params;
+};
+
+struct ViewSpec {           // an NDHWC tensor (channel slice) and how to derive its tensor maps
+  int C, cstride, coff;
+  int W, H, D, N;           // full (un-phased) spatial dims
+};
+
+}  // namespace petsyn
+
+struct petsyn_conv_plan {
+  petsyn_conv_desc desc;
+  int k3 = 0;
+  int od = 0, oh = 0, ow = 0;   // forward output dims
+  petsyn::ViewSpec vx, vy, vdx, vdy;
+  petsyn::GemmSide fprop, dgrad;
+  // wgrad (uses the fprop program)
+  petsyn::InvEntryDev* d_inv = nullptr;
+  int wg_box_w = 0, wg_box_h = 0, wg_box_d = 0;
+  int wg_block_n = 128, wg_ksplit = 1;
+  const void* wg_key_x = nullptr; const void* wg_key_g = nullptr; const void* wg_key_s = nullptr;
+  petsyn::WgradParams wg_params;
+};
+
+namespace petsyn {
+
+static void choose_box(int W, int H, int D, int max_rows, bool exact, int* bw, int* bh, int* bd) {
+  // maximise useful rows per tile; prefer long W runs (contiguous memory).  When `exact` the box must hold exactly
+  // max_rows voxels (wgrad: stale smem rows would pollute the reduction) and may overhang the tensor.
+  double best = -1;
+  *bw = *bh = *bd = 1;
+  for (int w = 1; w <= max_rows; ++w) {
+    if (!exact && w > W) break;
+    for (int h = 1; w * h <= max_rows; ++h) {
+      if (!exact && h > H) break;
+      for (int d = 1; w * h * d <= max_rows; ++d) {
+        if (!exact && d > D) break;
+        if (exact && w * h * d != max_rows) continue;
+        const int64_t tiles = (int64_t)((W + w - 1) / w) * ((H + h - 1) / h) * ((D + d - 1) / d);
+        const double eff = (double)W * H * D / ((double)tiles * max_rows);
+        const double score = eff + 1e-4 * w - 1e-6 * d;
+        if (score > best) { best = score; *bw = w; *bh = h; *bd = d; }
+      }
+    }
+  }
+}
+
+static int32_t upload(const void* src, size_t bytes, void** dst) {
+  PETSYN_CHECK_CUDA(cudaMalloc(dst, bytes));
+  PETSYN_CHECK_CUDA(cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice));
+  return PETSYN_OK;
+}
+
+static int32_t finish_side(GemmSide& g, int N) {
+  (void)N;
+  g.kch = 64;
+  g.kc_pad = (g.Kc + g.kch - 1) / g.kch * g.kch;
+  if (g.R >= 128) g.block_n = 128;
+  else g.block_n = (g.R + 15) / 16 * 16;
+  if (g.block_n > 64 && g.block_n < 128) g.block_n = 128;
+  choose_box(g.out_w, g.out_h, g.out_d, 128, false, &g.box_w, &g.box_h, &g.box_d);
+  std::vector<IgemmTap> taps;
+  std::vector<TapSrcDev> srcs(g.prog.subs.size() * g.prog.max_taps);
+  memset(srcs.data(), 0, srcs.size() * sizeof(TapSrcDev));
+  g.subs.clear();
+  for (size_t s = 0; s < g.prog.subs.size(); ++s) {
+    IgemmSub sub;
+    sub.c_view = g.prog.out_phased ? (int)s : 0;
+    sub.b_row = (int)s * g.R;
+    sub.tap_begin = (int)taps.size();
+    sub.tap_count = (int)g.prog.subs[s].size();
+    if (sub.tap_count > kMaxTaps) return fail(PETSYN_EINVAL, "too many taps per sub-problem (%d)", sub.tap_count);
+    for (size_t t = 0; t < g.prog.subs[s].size(); ++t) {
+      const TapDef& td = g.prog.subs[s][t];
+      taps.push_back({td.a_view, td.dw, td.dh, td.dd});
+      TapSrcDev& e = srcs[s * g.prog.max_taps + t];
+      if (td.src.size() > 8) return fail(PETSYN_EINVAL, "more than 8 merged kernel taps");
+      e.nsrc = (int)td.src.size();
+      for (size_t j = 0; j < td.src.size(); ++j) e.src[j] = td.src[j];
+    }
+    g.subs.push_back(sub);
+  }
+  int32_t rc = upload(taps.data(), taps.size() * sizeof(IgemmTap), (void**)&g.d_taps);
+  if (rc) return rc;
+  return upload(srcs.data(), srcs.size() * sizeof(TapSrcDev), (void**)&g.d_src);
+}
+
+// tensor map of (a phase of) an NDHWC bf16/fp32 view; box = (box_c, bw, bh, bd, 1)
+static int32_t view_map(CUtensorMap* out, const void* base, const ViewSpec& v, bool phased, int phase, int esz,
+                        CUtensorMapDataType dt, int box_c, int bw, int bh, int bd, int swizzle) {
+  const int step = phased ? 2 : 1;
+  const int pd = phased ? ((phase >> 2) & 1) : 0, ph = phased ? ((phase >> 1) & 1) : 0, pw = phased ? (phase & 1) : 0;
+  const uint64_t cs = (uint64_t)v.cstride * esz;
+  const uint8_t* b = reinterpret_cast<const uint8_t*>(base) + (uint64_t)v.coff * esz +
+                     (((uint64_t)pd * v.H + ph) * v.W + pw) * cs;
+  uint64_t dims[5] = {(uint64_t)v.C, (uint64_t)((v.W - pw + step - 1) / step), (uint64_t)((v.H - ph + step - 1) / step),
+                      (uint64_t)((v.D - pd + step - 1) / step), (uint64_t)v.N};
+  uint64_t strides[4] = {cs * step, cs * v.W * step, cs * v.W * v.H * step, cs * v.W * v.H * v.D};
+  uint32_t box[5] = {(uint32_t)box_c, (uint32_t)bw, (uint32_t)bh, (uint32_t)bd, 1u};
+  return encode_tmap(out, dt, 5, b, dims, strides, box, swizzle);
+}
+
+template <int BN, int OUT_MODE>
+static int32_t launch_igemm_bn(const GemmSide& g, dim3 grid, cudaStream_t st) {
+  constexpr int STAGES = (BN <= 128) ? 3 : 4;
+  using Cfg = IgemmCfg<BN, 64, STAGES, OUT_MODE>;
+  auto kern = igemm_kernel<BN, 64, STAGES, OUT_MODE>;
+  static bool attr_set = false;   // per instantiation
+  if (!attr_set) {
+    PETSYN_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    attr_set = true;
+  }
+  kern<<<grid, 128, Cfg::kSmemBytes, st>>>(g.params);
+  return check_launch("igemm_kernel");
+}
+
+static int32_t launch_igemm(const GemmSide& g, int batch, cudaStream_t st) {
+  dim3 grid;
+  grid.x = (unsigned)(g.params.tiles_w * g.params.tiles_h * g.params.tiles_d * batch);
+  grid.y = (unsigned)((g.R + g.block_n - 1) / g.block_n);
+  grid.z = (unsigned)g.subs.size();
+  switch (g.block_n) {
+    case 16: return launch_igemm_bn<16, OUT_BF16>(g, grid, st);
+    case 32: return launch_igemm_bn<32, OUT_BF16>(g, grid, st);
+    case 48: return launch_igemm_bn<48, OUT_BF16>(g, grid, st);
+    case 64: return launch_igemm_bn<64, OUT_BF16>(g, grid, st);
+    case 128: return launch_igemm_bn<128, OUT_BF16>(g, grid, st);
+    default: return fail(PETSYN_EINVAL, "unsupported BLOCK_N %d", g.block_n);
+  }
+}
+
+// (re)build the TMA descriptors of a gather-form GEMM for the given base pointers
+static int32_t bind_side(GemmSide& g, const ViewSpec& va, const ViewSpec& vc, const void* a, const void* b,
+                         const void* c, const float* bias, int act, float slope) {
+  if (g.key_a == a && g.key_b == b && g.key_c == c) {
+    g.params.bias = bias;
+    return PETSYN_OK;
+  }
+  IgemmParams& p = g.params;
+  memset(&p, 0, sizeof(p));
+  const int n_a = g.prog.a_phased ? 8 : 1;
+  const int n_c = g.prog.out_phased ? 8 : 1;
+  for (int i = 0; i < n_a; ++i) {
+    int32_t rc = view_map(&p.a_maps[i], a, va, g.prog.a_phased, i, 2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, g.kch, g.box_w,
+                          g.box_h, g.box_d, 128);
+    if (rc) return rc;
+  }
+  const int chunk_c = (g.block_n * 2) % 128 == 0 ? 64 : g.block_n;
+  const int c_swz = (g.block_n * 2) % 128 == 0 ? 128 : 0;
+  for (int i = 0; i < n_c; ++i) {
+    int32_t rc = view_map(&p.c_maps[i], c, vc, g.prog.out_phased, i, 2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, chunk_c,
+                          g.box_w, g.box_h, g.box_d, c_swz);
+    if (rc) return rc;
+  }
+  {
+    uint64_t dims[2] = {(uint64_t)g.prog.max_taps * g.kc_pad, (uint64_t)g.subs.size() * g.R};
+    uint64_t strides[1] = {dims[0] * 2};
+    uint32_t box[2] = {(uint32_t)g.kch, (uint32_t)g.block_n};
+    int32_t rc = encode_tmap(&p.b_map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, b, dims, strides, box, 128);
+    if (rc) return rc;
+  }
+  for (size_t i = 0; i < g.subs.size(); ++i) p.subs[i] = g.subs[i];
+  p.taps = g.d_taps;
+  p.bias = bias;
+  p.tiles_w = (g.out_w + g.box_w - 1) / g.box_w;
+  p.tiles_h = (g.out_h + g.box_h - 1) / g.box_h;
+  p.tiles_d = (g.out_d + g.box_d - 1) / g.box_d;
+  p.batch = va.N;
+  p.box_w = g.box_w; p.box_h = g.box_h; p.box_d = g.box_d;
+  p.a_stage_bytes = g.box_w * g.box_h * g.box_d * g.kch * 2;
+  p.kc_chunks = g.kc_pad / g.kch;
+  p.kc_pad = g.kc_pad;
+  p.rows = g.R;
+  p.epi_act = act;
+  p.epi_slope = slope;
+  g.key_a = a; g.key_b = b; g.key_c = c;
+  return PETSYN_OK;
+}
+
+static size_t packed_bytes(const GemmSide& g) {
+  return (size_t)g.subs.size() * g.R * g.prog.max_taps * g.kc_pad * 2;
+}
+
+static int32_t pack_side(const GemmSide& g, const float* w, void* out, int k3, cudaStream_t st) {
+  const int64_t total = (int64_t)packed_bytes(g) / 2;
+  const int threads = 256;
+  const int blocks = (int)std::min<int64_t>((total + threads - 1) / threads, 148 * 16);
+  pack_weights_kernel<<<blocks, threads, 0, st>>>(w, reinterpret_cast<__nv_bfloat16*>(out), g.d_src,
+                                                   (int)g.subs.size(), g.prog.max_taps, g.R, g.Kc, g.kc_pad, k3,
+                                                   g.swap ? 1 : 0);
+  return check_launch("pack_weights_kernel");
+}
+
+}  // namespace petsyn
+
+using namespace petsyn;
+
+extern "C" {
+
+int32_t petsyn_conv_plan_create(const petsyn_conv_desc* d, petsyn_conv_plan** out) {
+  PETSYN_REQUIRE(d != nullptr && out != nullptr, "null argument");
+  PETSYN_REQUIRE(d->n > 0 && d->d > 0 && d->h > 0 && d->w > 0, "non-positive tensor dims");
+  PETSYN_REQUIRE(d->cin > 0 && d->cout > 0 && d->cin % 8 == 0 && d->cout % 8 == 0,
+                 "cin (%d) and cout (%d) must be positive multiples of 8", d->cin, d->cout);
+  PETSYN_REQUIRE(d->x_cstride % 8 == 0 && d->y_cstride % 8 == 0 && d->dx_cstride % 8 == 0 && d->dy_cstride % 8 == 0 &&
+                     d->x_coff % 8 == 0 && d->y_coff % 8 == 0 && d->dx_coff % 8 == 0 && d->dy_coff % 8 == 0,
+                 "channel pitches/offsets must be multiples of 8 (16-byte TMA alignment)");
+  PETSYN_REQUIRE(d->x_coff + d->cin <= d->x_cstride && d->dx_coff + d->cin <= d->dx_cstride &&
+                     d->y_coff + d->cout <= d->y_cstride && d->dy_coff + d->cout <= d->dy_cstride,
+                 "channel slice exceeds the buffer's channel pitch");
+  auto* pl = new petsyn_conv_plan();
+  pl->desc = *d;
+  const int k = d->ksize, s = d->stride, p = d->pad;
+  AxisProg fwd, bwd;
+  int od, oh, ow;
+  if (d->op == PETSYN_OP_CONV) {
+    if (!(s == 1 || s == 2) || k < 1 || k > 4 || p < 0 || p >= k) {
+      delete pl;
+      return fail(PETSYN_EINVAL, "Conv3d: unsupported kernel/stride/pad %d/%d/%d", k, s, p);
+    }
+    if (s == 2 && ((d->d | d->h | d->w) & 1)) {
+      delete pl;
+      return fail(PETSYN_EINVAL, "stride-2 Conv3d needs even input dims, got %dx%dx%d", d->d, d->h, d->w);
+    }
+    od = (d->d + 2 * p - k) / s + 1; oh = (d->h + 2 * p - k) / s + 1; ow = (d->w + 2 * p - k) / s + 1;
+    if (s == 2 && (od * 2 != d->d || oh * 2 != d->h || ow * 2 != d->w)) {
+      delete pl;
+      return fail(PETSYN_EINVAL, "stride-2 Conv3d must halve the dims exactly (k=%d p=%d)", k, p);
+    }
+    fwd = (s == 1) ? axis_s1(k, p, +1) : axis_s2_gather(k, p);
+    bwd = (s == 1) ? axis_s1(k, p, -1) : axis_s2_scatter(k, p);
+  } else if (d->op == PETSYN_OP_UPCONV) {
+    if (!(k == 3 && s == 1 && p == 1)) {
+      delete pl;
+      return fail(PETSYN_EINVAL, "Upsample+Conv3d supports k3 s1 p1 only");
+    }
+    od = 2 * d->d; oh = 2 * d->h; ow = 2 * d->w;
+    fwd = axis_up_fwd(k, p);
+    bwd = axis_up_bwd(k, p);
+  } else if (d->op == PETSYN_OP_CONVT) {
+    if (!(k == 4 && s == 2 && p == 1)) {
+      delete pl;
+      return fail(PETSYN_EINVAL, "ConvTranspose3d supports k4 s2 p1 only");
+    }
+    od = 2 * d->d; oh = 2 * d->h; ow = 2 * d->w;
+    fwd = axis_s2_scatter(k, p);
+    bwd = axis_s2_gather(k, p);
+  } else {
+    delete pl;
+    return fail(PETSYN_EINVAL, "unknown op %d", d->op);
+  }
+  pl->k3 = k * k * k;
+  pl->od = od; pl->oh = oh; pl->ow = ow;
+  pl->vx = {d->cin, d->x_cstride, d->x_coff, d->w, d->h, d->d, d->n};
+  pl->vdx = {d->cin, d->dx_cstride, d->dx_coff, d->w, d->h, d->d, d->n};
+  pl->vy = {d->cout, d->y_cstride, d->y_coff, ow, oh, od, d->n};
+  pl->vdy = {d->cout, d->dy_cstride, d->dy_coff, ow, oh, od, d->n};
+
+  GemmSide& f = pl->fprop;
+  f.prog = make_program(fwd, k);
+  f.R = d->cout; f.Kc = d->cin;
+  f.swap = (d->op == PETSYN_OP_CONVT);
+  f.out_w = f.prog.out_phased ? ow / 2 : ow;
+  f.out_h = f.prog.out_phased ? oh / 2 : oh;
+  f.out_d = f.prog.out_phased ? od / 2 : od;
+  int32_t rc = finish_side(f, d->n);
+  GemmSide& g = pl->dgrad;
+  if (!rc) {
+    g.prog = make_program(bwd, k);
+    g.R = d->cin; g.Kc = d->cout;
+    g.swap = (d->op != PETSYN_OP_CONVT);
+    g.out_w = g.prog.out_phased ? d->w / 2 : d->w;
+    g.out_h = g.prog.out_phased ? d->h / 2 : d->h;
+    g.out_d = g.prog.out_phased ? d->d / 2 : d->d;
+    rc = finish_side(g, d->n);
+  }
+  if (!rc) {
+    // wgrad: inverse table (original tap -> packed (sub, tap) slots) from the fprop program
+    std::vector<InvEntryDev> inv(pl->k3);
+    memset(inv.data(), 0, inv.size() * sizeof(InvEntryDev));
+    for (size_t s2 = 0; s2 < f.prog.subs.size() && !rc; ++s2)
+      for (size_t t = 0; t < f.prog.subs[s2].size(); ++t)
+        for (int src : f.prog.subs[s2][t].src) {
+          InvEntryDev& e = inv[src];
+          if (e.n >= 8) { rc = fail(PETSYN_EINVAL, "tap appears in more than 8 merged slots"); break; }
+          e.sub[e.n] = (int)s2; e.tap[e.n] = (int)t; ++e.n;
+        }
+    if (!rc) rc = upload(inv.data(), inv.size() * sizeof(InvEntryDev), (void**)&pl->d_inv);
+    choose_box(f.out_w, f.out_h, f.out_d, 64, true, &pl->wg_box_w, &pl->wg_box_h, &pl->wg_box_d);
+    pl->wg_block_n = (d->cin % 128 == 0 || d->cin > 64) ? 128 : 64;
+    // split the voxel reduction so that the grid fills the machine (~2 waves of 148 SMs x 2 CTAs)
+    int64_t total_taps = 0;
+    for (auto& s2 : f.prog.subs) total_taps += (int64_t)s2.size();
+    const int64_t base_ctas = total_taps * ((d->cout + 127) / 128) * ((d->cin + pl->wg_block_n - 1) / pl->wg_block_n);
+    const int64_t nboxes = (int64_t)((f.out_w + pl->wg_box_w - 1) / pl->wg_box_w) *
+                           ((f.out_h + pl->wg_box_h - 1) / pl->wg_box_h) *
+                           ((f.out_d + pl->wg_box_d - 1) / pl->wg_box_d) * d->n;
+    int64_t ks = (148 * 4 + base_ctas - 1) / base_ctas;
+    ks = std::max<int64_t>(1, std::min<int64_t>(ks, std::max<int64_t>(1, nboxes / 8)));
+    pl->wg_ksplit = (int)ks;
+  }
+  if (rc) {
+    petsyn_conv_plan_destroy(pl);
+    return rc;
+  }
+  *out = pl;
+  return PETSYN_OK;
+}
+
+void petsyn_conv_plan_destroy(petsyn_conv_plan* pl) {
+  if (!pl) return;
+  cudaFree(pl->fprop.d_taps); cudaFree(pl->fprop.d_src);
+  cudaFree(pl->dgrad.d_taps); cudaFree(pl->dgrad.d_src);
+  cudaFree(pl->d_inv);
+  delete pl;
+}
+
+int32_t petsyn_conv_out_dims(const petsyn_conv_plan* pl, int32_t* od, int32_t* oh, int32_t* ow) {
+  PETSYN_REQUIRE(pl != nullptr, "null plan");
+  *od = pl->od; *oh = pl->oh; *ow = pl->ow;
+  return PETSYN_OK;
+}
+
+int32_t petsyn_conv_flops(const petsyn_conv_plan* pl, double* algorithmic, double* executed) {
+  PETSYN_REQUIRE(pl != nullptr, "null plan");
+  const petsyn_conv_desc& d = pl->desc;
+  const double mout = (double)d.n * pl->od * pl->oh * pl->ow;
+  const double min_ = (double)d.n * d.d * d.h * d.w;
+  if (algorithmic)
+    *algorithmic = (d.op == PETSYN_OP_CONVT) ? 2.0 * min_ * d.cin * d.cout * pl->k3 : 2.0 * mout * d.cin * d.cout * pl->k3;
+  if (executed) {
+    double taps = 0;
+    for (auto& s : pl->fprop.prog.subs) taps += (double)s.size();
+    const double vox_per_sub = (double)d.n * pl->fprop.out_d * pl->fprop.out_h * pl->fprop.out_w;
+    *executed = 2.0 * vox_per_sub * taps * d.cin * d.cout;
+  }
+  return PETSYN_OK;
+}
+
+size_t petsyn_conv_packed_fprop_bytes(const petsyn_conv_plan* pl) { return pl ? packed_bytes(pl->fprop) : 0; }
+size_t petsyn_conv_packed_dgrad_bytes(const petsyn_conv_plan* pl) { return pl ? packed_bytes(pl->dgrad) : 0; }
+size_t petsyn_conv_wgrad_scratch_bytes(const petsyn_conv_plan* pl) { return pl ? packed_bytes(pl->fprop) * 2 : 0; }
+
+int32_t petsyn_conv_pack_weights(petsyn_conv_plan* pl, const float* w, void* packed_fprop, void* packed_dgrad,
+                                 void* stream) {
+  PETSYN_REQUIRE(pl != nullptr && w != nullptr, "null argument");
+  int32_t rc = PETSYN_OK;
+  if (packed_fprop) rc = pack_side(pl->fprop, w, packed_fprop, pl->k3, as_stream(stream));
+  if (!rc && packed_dgrad) rc = pack_side(pl->dgrad, w, packed_dgrad, pl->k3, as_stream(stream));
+  return rc;
+}
+
+int32_t petsyn_conv_fprop(petsyn_conv_plan* pl, const void* x, const void* packed, const float* bias, void* y,
+                          void* stream) {
+  PETSYN_REQUIRE(pl && x && packed && y, "null argument");
+  int32_t rc = bind_side(pl->fprop, pl->vx, pl->vy, x, packed, y, bias, pl->desc.epi_act, pl->desc.epi_slope);
+  if (rc) return rc;
+  return launch_igemm(pl->fprop, pl->desc.n, as_stream(stream));
+}
+
+int32_t petsyn_conv_dgrad(petsyn_conv_plan* pl, const void* dy, const void* packed, void* dx, void* stream) {
+  PETSYN_REQUIRE(pl && dy && packed && dx, "null argument");
+  int32_t rc = bind_side(pl->dgrad, pl->vdy, pl->vdx, dy, packed, dx, nullptr, PETSYN_ACT_NONE, 0.f);
+  if (rc) return rc;
+  return launch_igemm(pl->dgrad, pl->desc.n, as_stream(stream));
+}
+
+int32_t petsyn_conv_wgrad(petsyn_conv_plan* pl, const void* x, const void* dy, void* scratch, float* dw,
+                          int32_t accumulate, void* stream) {
+  PETSYN_REQUIRE(pl && x && dy && scratch && dw, "null argument");
+  GemmSide& f = pl->fprop;
+  cudaStream_t st = as_stream(stream);
+  WgradParams& p = pl->wg_params;
+  if (!(pl->wg_key_x == x && pl->wg_key_g == dy && pl->wg_key_s == scratch)) {
+    memset(&p, 0, sizeof(p));
+    const int n_x = f.prog.a_phased ? 8 : 1;
+    const int n_g = f.prog.out_phased ? 8 : 1;
+    for (int i = 0; i < n_x; ++i) {
+      int32_t rc = view_map(&p.x_maps[i], x, pl->vx, f.prog.a_phased, i, 2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 64,
+                            pl->wg_box_w, pl->wg_box_h, pl->wg_box_d, 128);
+      if (rc) return rc;
+    }
+    for (int i = 0; i < n_g; ++i) {
+      int32_t rc = view_map(&p.g_maps[i], dy, pl->vdy, f.prog.out_phased, i, 2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 64,
+                            pl->wg_box_w, pl->wg_box_h, pl->wg_box_d, 128);
+      if (rc) return rc;
+    }
+    uint64_t dims[2] = {(uint64_t)f.prog.max_taps * f.kc_pad, (uint64_t)f.subs.size() * f.R};
+    uint64_t strides[1] = {dims[0] * 4};
+    uint32_t box[2] = {32u, 128u};
+    int32_t rc = encode_tmap(&p.d_map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, scratch, dims, strides, box, 128);
+    if (rc) return rc;
+    for (size_t i = 0; i < f.subs.size(); ++i) p.subs[i] = f.subs[i];
+    p.taps = f.d_taps;
+    p.tiles_w = (f.out_w + pl->wg_box_w - 1) / pl->wg_box_w;
+    p.tiles_h = (f.out_h + pl->wg_box_h - 1) / pl->wg_box_h;
+    p.tiles_d = (f.out_d + pl->wg_box_d - 1) / pl->wg_box_d;
+    p.batch = pl->desc.n;
+    p.box_w = pl->wg_box_w; p.box_h = pl->wg_box_h; p.box_d = pl->wg_box_d;
+    p.box_bytes = 64 * 64 * 2;
+    p.kc_pad = f.kc_pad;
+    p.ksplit = pl->wg_ksplit;
+    p.r_tiles = (f.R + 127) / 128;
+    p.c_tiles = (f.Kc + pl->wg_block_n - 1) / pl->wg_block_n;
+    pl->wg_key_x = x; pl->wg_key_g = dy; pl->wg_key_s = scratch;
+  }
+  PETSYN_CHECK_CUDA(cudaMemsetAsync(scratch, 0, petsyn_conv_wgrad_scratch_bytes(pl), st));
+  dim3 grid((unsigned)(f.prog.max_taps * p.r_tiles * p.c_tiles), (unsigned)p.ksplit, (unsigned)f.subs.size());
+  if (pl->wg_block_n == 128) {
+    constexpr int STAGES = 3;
+    constexpr int smem = STAGES * (16384 + 16384) + 1024 + 256;
+    auto kern = wgrad_kernel<128, STAGES>;
+    static bool attr_set = false;
+    if (!attr_set) {
+      PETSYN_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      attr_set = true;
+    }
+    kern<<<grid, 128, smem, st>>>(p);
+  } else {
+    constexpr int STAGES = 4;
+    constexpr int smem = STAGES * (16384 + 8192) + 1024 + 256;
+    auto kern = wgrad_kernel<64, STAGES>;
+    static bool attr_set = false;
+    if (!attr_set) {
+      PETSYN_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      attr_set = true;
+    }
+    kern<<<grid, 128, smem, st>>>(p);
+  }
+  int32_t rc = check_launch("wgrad_kernel");
+  if (rc) return rc;
+  const int64_t total = (int64_t)f.R * f.Kc * pl->k3;
+  const int blocks = (int)std::min<int64_t>((total + 255) / 256, 148 * 16);
+  unpack_wgrad_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const float*>(scratch), dw, pl->d_inv, f.prog.max_taps,
+                                               f.R, f.Kc, f.kc_pad, pl->k3, f.swap ? 1 : 0, accumulate);
+  return check_launch("unpack_wgrad_kernel");
+}
+
+}  // extern "C"

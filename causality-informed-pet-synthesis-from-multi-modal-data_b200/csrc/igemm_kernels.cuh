@@ -1,0 +1,408 @@
+// Implicit-GEMM convolution kernels for sm_100a.
+//
+//  igemm_kernel  : "gather" form used by fprop, dgrad and ConvTranspose.  One CTA computes a 128-voxel x BLOCK_N-channel
+//                  output tile.  The 128 voxels are a (box_w x box_h x box_d) brick of the output view, so for every
+//                  kernel tap the A operand is ONE 5-D TMA box load from the (possibly stride-2 phase-) view of the
+//                  input, shifted by the tap offset; out-of-bounds voxels are zero-filled by the TMA unit, which is the
+//                  convolution's zero padding.  B (packed weights, K-major) comes in by 2-D TMA.  Both land in 128B-
+//                  swizzled shared memory and feed tcgen05.mma (M=128, N=BLOCK_N, K=16 per instruction) accumulating
+//                  fp32 in TMEM.  Epilogue: tcgen05.ld -> (+bias, activation) -> bf16/fp32 -> swizzled smem -> TMA
+//                  store (clipped at the tensor edge) or TMA add-reduction (split-K).
+//  wgrad_kernel  : "reduce over voxels" form: dW'[r, tap, c] = sum_vox dy[vox, r] * x[vox + tap, c].  Both operands
+//                  are voxel-major in memory, i.e. MN-major UMMA operands; K = 64 voxels per pipeline stage.
+//
+// Warp roles (128 threads): warp 0 lane 0 = TMA producer, warp 1 lane 0 = MMA issuer (warp 1 owns the TMEM
+// allocation), then all four warps run the epilogue (warp w reads TMEM lanes 32w..32w+31).
+#pragma once
+#include <cuda_bf16.h>
+
+#include "ptx.cuh"
+
+namespace petsyn {
+
+constexpr int kMaxViews = 8;
+constexpr int kMaxSubs = 8;
+constexpr int kMaxTaps = 64;
+
+struct IgemmTap {  // one kernel tap of a sub-problem
+  int32_t a_view;  // which A tensor map (phase view) to read
+  int32_t dw, dh, dd;  // voxel offset of the A box relative to the output tile origin
+};
+
+struct IgemmSub {
+  int32_t c_view;      // which C tensor map (output phase view)
+  int32_t b_row;       // first row of this sub-problem in the packed weight matrix
+  int32_t tap_begin;   // index into the tap table
+  int32_t tap_count;
+};
+
+struct alignas(64) IgemmParams {
+  CUtensorMap a_maps[kMaxViews];
+  CUtensorMap c_maps[kMaxViews];
+  CUtensorMap b_map;
+  IgemmSub subs[kMaxSubs];
+  const IgemmTap* taps;   // device table
+  const float* bias;      // [rows] or nullptr
+  int32_t tiles_w, tiles_h, tiles_d, batch;
+  int32_t box_w, box_h, box_d;
+  int32_t a_stage_bytes;  // bytes one A box load delivers
+  int32_t kc_chunks;      // channel chunks (of KCH) per tap
+  int32_t kc_pad;         // padded reduction channels per tap in B
+  int32_t rows;           // valid output channels (for bias bounds)
+  int32_t epi_act;
+  float epi_slope;
+};
+
+enum { OUT_BF16 = 0, OUT_F32 = 1, OUT_F32_REDUCE = 2 };
+
+__device__ __forceinline__ float apply_act(float x, int act, float slope) {
+  switch (act) {
+    case PETSYN_ACT_RELU: return fmaxf(x, 0.f);
+    case PETSYN_ACT_LRELU: return x > 0.f ? x : x * slope;
+    case PETSYN_ACT_SILU: return x / (1.f + __expf(-x));
+    case PETSYN_ACT_TANH: return tanhf(x);
+    default: return x;
+  }
+}
+
+template <int KCH>
+struct SwizzleOf {
+  static constexpr int kBytes = KCH * 2;                                   // bytes per K-chunk row: 128 / 64 / 32
+  static constexpr uint32_t kLayout = (kBytes == 128) ? 2u : (kBytes == 64 ? 4u : 6u);
+  static constexpr uint32_t kSbo = 8u * kBytes;                            // 8-row core-matrix group pitch
+};
+
+template <int BLOCK_N, int KCH, int STAGES, int OUT_MODE>
+struct IgemmCfg {
+  static constexpr int kABytes = 128 * KCH * 2;
+  static constexpr int kBBytesRaw = BLOCK_N * KCH * 2;
+  static constexpr int kBBytes = (kBBytesRaw + 1023) / 1024 * 1024;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kEsz = (OUT_MODE == OUT_BF16) ? 2 : 4;
+  // epilogue staging: chunks of kChunkC channels with 128-byte (swizzled) rows when BLOCK_N allows, else one dense chunk
+  static constexpr bool kSwz = (BLOCK_N * kEsz) % 128 == 0;
+  static constexpr int kChunkC = kSwz ? 128 / kEsz : BLOCK_N;
+  static constexpr int kNChunk = BLOCK_N / kChunkC;
+  static constexpr int kRowPitch = kChunkC * kEsz;
+  static constexpr int kStagingBytes = kNChunk * 128 * kRowPitch;
+  static constexpr int kPipeBytes = STAGES * kStageBytes;
+  static constexpr int kMainBytes = kPipeBytes > kStagingBytes ? kPipeBytes : kStagingBytes;
+  static constexpr int kSmemBytes = kMainBytes + 1024 /*align slack*/ + 2048 /*barriers (256 B) + tap table*/;
+  static constexpr uint32_t kTmemCols = BLOCK_N <= 32 ? 32 : (BLOCK_N <= 64 ? 64 : (BLOCK_N <= 128 ? 128 : 256));
+};
+
+template <int BLOCK_N, int KCH, int STAGES, int OUT_MODE>
+__global__ void __launch_bounds__(128) igemm_kernel(const __grid_constant__ IgemmParams p) {
+  using Cfg = IgemmCfg<BLOCK_N, KCH, STAGES, OUT_MODE>;
+  using Sw = SwizzleOf<KCH>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* tail = smem + Cfg::kMainBytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);            // [STAGES]
+  uint64_t* empty_bar = full_bar + STAGES;                            // [STAGES]
+  uint64_t* accum_bar = empty_bar + STAGES;                           // [1]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);   // [1]
+  IgemmTap* s_taps = reinterpret_cast<IgemmTap*>(tail + 256);         // kMaxTaps x 16 B = 1024 B
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5;
+
+  const IgemmSub sub = p.subs[blockIdx.z];
+  int t = blockIdx.x;
+  const int tw = t % p.tiles_w; t /= p.tiles_w;
+  const int th = t % p.tiles_h; t /= p.tiles_h;
+  const int td = t % p.tiles_d; t /= p.tiles_d;
+  const int nb = t;
+  const int w0 = tw * p.box_w, h0 = th * p.box_h, d0 = td * p.box_d;
+  const int n0 = blockIdx.y * BLOCK_N;
+  const int nsteps = sub.tap_count * p.kc_chunks;
+
+  for (int i = tid; i < sub.tap_count; i += 128) s_taps[i] = p.taps[sub.tap_begin + i];
+
+  if (warp == 0 && ptx::elect_one()) {
+    for (int s = 0; s < STAGES; ++s) {
+      ptx::mbar_init(&full_bar[s], 1);
+      ptx::mbar_init(&empty_bar[s], 1);
+    }
+    ptx::mbar_init(accum_bar, 1);
+    ptx::fence_mbar_init();
+    ptx::prefetch_tmap(&p.b_map);
+    ptx::prefetch_tmap(&p.c_maps[sub.c_view]);
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(tmem_slot, Cfg::kTmemCols);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  ptx::tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (ptx::elect_one()) {
+      // ---------------- TMA producer ----------------
+      const uint32_t tx_bytes = uint32_t(p.a_stage_bytes) + uint32_t(Cfg::kBBytesRaw);
+      int s = 0;
+      for (int tap = 0; tap < sub.tap_count; ++tap) {
+        const IgemmTap tp = s_taps[tap];
+        const CUtensorMap* amap = &p.a_maps[tp.a_view];
+        for (int kc = 0; kc < p.kc_chunks; ++kc, ++s) {
+          const int stage = s % STAGES;
+          const uint32_t ph = (s / STAGES) & 1;
+          ptx::mbar_wait(&empty_bar[stage], ph ^ 1);
+          uint8_t* a_dst = smem + stage * Cfg::kStageBytes;
+          uint8_t* b_dst = a_dst + Cfg::kABytes;
+          ptx::mbar_expect_tx(&full_bar[stage], tx_bytes);
+          ptx::tma_load_5d(a_dst, amap, &full_bar[stage], kc * KCH, w0 + tp.dw, h0 + tp.dh, d0 + tp.dd, nb);
+          ptx::tma_load_2d(b_dst, &p.b_map, &full_bar[stage], tap * p.kc_pad + kc * KCH, sub.b_row + n0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (ptx::elect_one()) {
+      // ---------------- MMA issuer ----------------
+      constexpr uint64_t desc_base = ptx::umma_desc_base(16, Sw::kSbo, Sw::kLayout);
+      constexpr uint32_t idesc = ptx::umma_idesc_bf16(128, BLOCK_N, 0, 0);
+      for (int s = 0; s < nsteps; ++s) {
+        const int stage = s % STAGES;
+        const uint32_t ph = (s / STAGES) & 1;
+        ptx::mbar_wait(&full_bar[stage], ph);
+        ptx::tc_fence_after_sync();
+        const uint32_t a_addr = ptx::smem_u32(smem + stage * Cfg::kStageBytes);
+        const uint32_t b_addr = a_addr + Cfg::kABytes;
+#pragma unroll
+        for (int k = 0; k < KCH / 16; ++k) {
+          ptx::umma_bf16(tmem_base, ptx::umma_desc(desc_base, a_addr + k * 32), ptx::umma_desc(desc_base, b_addr + k * 32),
+                         idesc, (s | k) != 0 ? 1u : 0u);
+        }
+        ptx::umma_commit(&empty_bar[stage]);   // frees the smem slot once these MMAs have read it
+      }
+      ptx::umma_commit(accum_bar);             // accumulator complete
+    }
+  }
+  __syncwarp();
+
+  // ---------------- epilogue: TMEM -> registers -> (bias, act, convert) -> swizzled smem -> TMA store ----------------
+  ptx::mbar_wait(accum_bar, 0);
+  ptx::tc_fence_after_sync();
+  const int row = tid;  // accumulator row == TMEM lane == voxel index inside the box
+  const uint32_t lane_base = uint32_t(warp * 32) << 16;
+#pragma unroll 1
+  for (int c0 = 0; c0 < BLOCK_N; c0 += 16) {
+    uint32_t v[16];
+    ptx::tmem_ld_32x16(tmem_base + lane_base + uint32_t(c0), v);
+    ptx::tmem_ld_wait();
+    float f[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]);
+    if (p.bias != nullptr) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const int ch = n0 + c0 + i;
+        f[i] += (ch < p.rows) ? __ldg(p.bias + ch) : 0.f;
+      }
+    }
+    if (p.epi_act != PETSYN_ACT_NONE) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) f[i] = apply_act(f[i], p.epi_act, p.epi_slope);
+    }
+    const int chunk = c0 / Cfg::kChunkC;
+    const int cin = c0 % Cfg::kChunkC;
+    uint8_t* rowp = smem + chunk * (128 * Cfg::kRowPitch) + row * Cfg::kRowPitch;
+    const int j0 = (cin * Cfg::kEsz) >> 4;
+    if constexpr (OUT_MODE == OUT_BF16) {
+      uint32_t pk[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        __nv_bfloat162 b2 = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+        pk[i] = *reinterpret_cast<uint32_t*>(&b2);
+      }
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const int j = j0 + q;
+        const int js = Cfg::kSwz ? (j ^ (row & 7)) : j;
+        *reinterpret_cast<uint4*>(rowp + (js << 4)) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+      }
+    } else {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int j = j0 + q;
+        const int js = Cfg::kSwz ? (j ^ (row & 7)) : j;
+        *reinterpret_cast<float4*>(rowp + (js << 4)) = make_float4(f[4 * q], f[4 * q + 1], f[4 * q + 2], f[4 * q + 3]);
+      }
+    }
+  }
+  ptx::tc_fence_before_sync();
+  ptx::fence_proxy_async_smem();
+  __syncthreads();
+  if (warp == 1) ptx::tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  if (tid == 0) {
+    const CUtensorMap* cmap = &p.c_maps[sub.c_view];
+#pragma unroll 1
+    for (int chunk = 0; chunk < Cfg::kNChunk; ++chunk) {
+      const int ch = n0 + chunk * Cfg::kChunkC;
+      if (ch >= p.rows) break;
+      const uint8_t* src = smem + chunk * (128 * Cfg::kRowPitch);
+      if constexpr (OUT_MODE == OUT_F32_REDUCE)
+        ptx::tma_reduce_add_5d(cmap, src, ch, w0, h0, d0, nb);
+      else
+        ptx::tma_store_5d(cmap, src, ch, w0, h0, d0, nb);
+    }
+    ptx::tma_store_commit();
+    ptx::tma_store_wait_all();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// wgrad: D[r, c] (128 x BLOCK_N, fp32) = sum over voxels of G[vox, r] * X[vox + tap, c]
+// ------------------------------------------------------------------------------------------------------------
+struct alignas(64) WgradParams {
+  CUtensorMap g_maps[kMaxViews];   // dy views (per sub-problem output view); box = (64 ch, bw, bh, bd, 1)
+  CUtensorMap x_maps[kMaxViews];   // x views (per tap a_view);               box = (64 ch, bw, bh, bd, 1)
+  CUtensorMap d_map;               // fp32 [rows_total, ldb] scratch; box = (32, 128)
+  IgemmSub subs[kMaxSubs];
+  const IgemmTap* taps;
+  int32_t tiles_w, tiles_h, tiles_d, batch;   // voxel boxes (K blocks) of the sub-problem's output view
+  int32_t box_w, box_h, box_d;
+  int32_t box_bytes;               // bytes one (64 ch x box) load delivers
+  int32_t kc_pad;                  // padded Cin per tap in the scratch matrix
+  int32_t ksplit;                  // number of CTAs sharing the voxel reduction
+  int32_t r_tiles, c_tiles;
+};
+
+// grid: x = tap (within sub) * r_tiles * c_tiles flattened, y = ksplit index, z = sub
+template <int BLOCK_N, int STAGES>
+__global__ void __launch_bounds__(128) wgrad_kernel(const __grid_constant__ WgradParams p) {
+  constexpr int kGBytes = 2 * 64 * 64 * 2;            // A operand: 64 voxels x 128 r  (two 64-channel slabs)
+  constexpr int kXBytes = (BLOCK_N / 64) * 64 * 64 * 2;
+  constexpr int kStageBytes = kGBytes + kXBytes;
+  constexpr int kStagingBytes = (BLOCK_N / 32) * 128 * 128;  // fp32, 32-channel chunks with 128B rows
+  constexpr int kPipeBytes = STAGES * kStageBytes;
+  constexpr int kMainBytes = kPipeBytes > kStagingBytes ? kPipeBytes : kStagingBytes;
+  constexpr uint32_t kTmemCols = BLOCK_N <= 64 ? 64 : (BLOCK_N <= 128 ? 128 : 256);
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* tail = smem + kMainBytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* accum_bar = empty_bar + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5;
+  const IgemmSub sub = p.subs[blockIdx.z];
+  int t = blockIdx.x;
+  const int ct = t % p.c_tiles; t /= p.c_tiles;
+  const int rt = t % p.r_tiles; t /= p.r_tiles;
+  const int tap = t;
+  if (tap >= sub.tap_count) return;   // sub-problems may have fewer taps than the grid's maximum (uniform exit)
+  const IgemmTap tp = p.taps[sub.tap_begin + tap];
+  const int r0 = rt * 128, c0 = ct * BLOCK_N;
+  const int nboxes = p.tiles_w * p.tiles_h * p.tiles_d * p.batch;
+  const int per = (nboxes + p.ksplit - 1) / p.ksplit;
+  const int kb_begin = blockIdx.y * per;
+  const int kb_end = min(nboxes, kb_begin + per);
+  const int nsteps = kb_end - kb_begin;
+  if (nsteps <= 0) return;
+
+  if (warp == 0 && ptx::elect_one()) {
+    for (int s = 0; s < STAGES; ++s) {
+      ptx::mbar_init(&full_bar[s], 1);
+      ptx::mbar_init(&empty_bar[s], 1);
+    }
+    ptx::mbar_init(accum_bar, 1);
+    ptx::fence_mbar_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(tmem_slot, kTmemCols);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  ptx::tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (ptx::elect_one()) {
+      const CUtensorMap* gmap = &p.g_maps[sub.c_view];
+      const CUtensorMap* xmap = &p.x_maps[tp.a_view];
+      const uint32_t tx_bytes = uint32_t(p.box_bytes) * (2 + BLOCK_N / 64);
+      for (int s = 0; s < nsteps; ++s) {
+        int kb = kb_begin + s;
+        const int bw = kb % p.tiles_w; kb /= p.tiles_w;
+        const int bh = kb % p.tiles_h; kb /= p.tiles_h;
+        const int bd = kb % p.tiles_d; kb /= p.tiles_d;
+        const int nb = kb;
+        const int w0 = bw * p.box_w, h0 = bh * p.box_h, d0 = bd * p.box_d;
+        const int stage = s % STAGES;
+        const uint32_t ph = (s / STAGES) & 1;
+        ptx::mbar_wait(&empty_bar[stage], ph ^ 1);
+        uint8_t* g_dst = smem + stage * kStageBytes;
+        uint8_t* x_dst = g_dst + kGBytes;
+        ptx::mbar_expect_tx(&full_bar[stage], tx_bytes);
+        ptx::tma_load_5d(g_dst, gmap, &full_bar[stage], r0, w0, h0, d0, nb);
+        ptx::tma_load_5d(g_dst + 8192, gmap, &full_bar[stage], r0 + 64, w0, h0, d0, nb);
+#pragma unroll
+        for (int j = 0; j < BLOCK_N / 64; ++j)
+          ptx::tma_load_5d(x_dst + j * 8192, xmap, &full_bar[stage], c0 + j * 64, w0 + tp.dw, h0 + tp.dh, d0 + tp.dd, nb);
+      }
+    }
+  } else if (warp == 1) {
+    if (ptx::elect_one()) {
+      // MN-major, 128B swizzle: 64 contiguous channels per voxel row (128 B), 8 voxel rows per 1024 B group (SBO),
+      // next 64-channel slab 8192 B further (LBO).
+      constexpr uint64_t desc_base = ptx::umma_desc_base(8192, 1024, 2);
+      constexpr uint32_t idesc = ptx::umma_idesc_bf16(128, BLOCK_N, 1, 1);
+      for (int s = 0; s < nsteps; ++s) {
+        const int stage = s % STAGES;
+        const uint32_t ph = (s / STAGES) & 1;
+        ptx::mbar_wait(&full_bar[stage], ph);
+        ptx::tc_fence_after_sync();
+        const uint32_t g_addr = ptx::smem_u32(smem + stage * kStageBytes);
+        const uint32_t x_addr = g_addr + kGBytes;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {   // 16 voxels per MMA = two 8-row groups = 2048 B
+          ptx::umma_bf16(tmem_base, ptx::umma_desc(desc_base, g_addr + k * 2048),
+                         ptx::umma_desc(desc_base, x_addr + k * 2048), idesc, (s | k) != 0 ? 1u : 0u);
+        }
+        ptx::umma_commit(&empty_bar[stage]);
+      }
+      ptx::umma_commit(accum_bar);
+    }
+  }
+  __syncwarp();
+
+  ptx::mbar_wait(accum_bar, 0);
+  ptx::tc_fence_after_sync();
+  const int row = tid;
+  const uint32_t lane_base = uint32_t(warp * 32) << 16;
+#pragma unroll 1
+  for (int cc = 0; cc < BLOCK_N; cc += 16) {
+    uint32_t v[16];
+    ptx::tmem_ld_32x16(tmem_base + lane_base + uint32_t(cc), v);
+    ptx::tmem_ld_wait();
+    const int chunk = cc / 32;
+    uint8_t* rowp = smem + chunk * (128 * 128) + row * 128;
+    const int j0 = ((cc % 32) * 4) >> 4;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int js = (j0 + q) ^ (row & 7);
+      *reinterpret_cast<uint4*>(rowp + (js << 4)) = make_uint4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+    }
+  }
+  ptx::tc_fence_before_sync();
+  ptx::fence_proxy_async_smem();
+  __syncthreads();
+  if (warp == 1) ptx::tmem_dealloc(tmem_base, kTmemCols);
+  if (tid == 0) {
+#pragma unroll 1
+    for (int chunk = 0; chunk < BLOCK_N / 32; ++chunk) {
+      ptx::tma_reduce_add_2d(&p.d_map, smem + chunk * (128 * 128), tap * p.kc_pad + c0 + chunk * 32,
+                             sub.b_row + r0);
+    }
+    ptx::tma_store_commit();
+    ptx::tma_store_wait_all();
+  }
+}
+
+}  // namespace petsyn

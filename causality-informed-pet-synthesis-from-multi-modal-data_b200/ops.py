@@ -1,0 +1,170 @@
+"""Thin Python objects over the C ABI: one class per kernel family, tensors in, tensors out.
+
+Nothing here computes; every method forwards raw device pointers and the current CUDA stream to
+``libpetsyn.so``.  Activations are channels-last ``(N, D, H, W, C)`` bf16 tensors (possibly channel slices
+of wider buffers, described by ``cstride``/``coff``); weights are fp32 in PyTorch layout.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Tuple
+
+import torch
+
+from . import _cabi
+from ._cabi import (ACT_LRELU, ACT_NONE, ACT_RELU, ACT_SILU, ACT_TANH, OP_CONV, OP_CONVT, OP_UPCONV, check, lib, ptr,
+                    stream_ptr)
+
+__all__ = ["ConvPlan", "OP_CONV", "OP_UPCONV", "OP_CONVT", "ACT_NONE", "ACT_RELU", "ACT_LRELU", "ACT_SILU",
+           "ACT_TANH", "bn_stats", "bn_finalize", "norm_act_fwd", "norm_act_bwd", "l1_loss_fwd_bwd",
+           "mse_const_fwd_bwd", "adam_step", "sumsq", "stem_fwd", "stem_wgrad", "head_fwd", "head_bwd"]
+
+
+class ConvPlan:
+    """Conv3d / Upsample+Conv3d / ConvTranspose3d as tcgen05 implicit GEMMs (fprop, dgrad, wgrad).
+
+    Replaces ``F.conv3d`` (unet_model.py:47,60), ``nn.Upsample`` + ``F.conv3d`` (unet_model.py:59-60) and
+    ``F.conv_transpose3d`` (bmgan_model.py:57-64) together with their cuDNN backward kernels.
+    """
+
+    def __init__(self, op: int, n: int, d: int, h: int, w: int, cin: int, cout: int, ksize: int, stride: int, pad: int,
+                 x_cstride: Optional[int] = None, x_coff: int = 0, y_cstride: Optional[int] = None, y_coff: int = 0,
+                 dy_cstride: Optional[int] = None, dy_coff: int = 0, dx_cstride: Optional[int] = None,
+                 dx_coff: int = 0, act: int = ACT_NONE, slope: float = 0.2):
+        _cabi.require_cuda()
+        self.desc = _cabi.ConvDesc(op, n, d, h, w, cin, cout, ksize, stride, pad,
+                                   x_cstride or cin, x_coff, y_cstride or cout, y_coff,
+                                   dy_cstride or cout, dy_coff, dx_cstride or cin, dx_coff, act, slope)
+        handle = C.c_void_p()
+        check(lib.petsyn_conv_plan_create(C.byref(self.desc), C.byref(handle)), "conv_plan_create")
+        self._h = handle
+        od, oh, ow = C.c_int32(), C.c_int32(), C.c_int32()
+        check(lib.petsyn_conv_out_dims(self._h, C.byref(od), C.byref(oh), C.byref(ow)))
+        self.out_dims: Tuple[int, int, int] = (od.value, oh.value, ow.value)
+        fa, fe = C.c_double(), C.c_double()
+        check(lib.petsyn_conv_flops(self._h, C.byref(fa), C.byref(fe)))
+        self.flops_algorithmic, self.flops_executed = fa.value, fe.value
+        self.packed_fprop_bytes = lib.petsyn_conv_packed_fprop_bytes(self._h)
+        self.packed_dgrad_bytes = lib.petsyn_conv_packed_dgrad_bytes(self._h)
+        self.wgrad_scratch_bytes = lib.petsyn_conv_wgrad_scratch_bytes(self._h)
+        self.w_fprop: Optional[torch.Tensor] = None
+        self.w_dgrad: Optional[torch.Tensor] = None
+        self._scratch: Optional[torch.Tensor] = None
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            lib.petsyn_conv_plan_destroy(h)
+            self._h = None
+
+    # weights -------------------------------------------------------------------------------------------
+    def pack(self, w: torch.Tensor, need_dgrad: bool = True) -> None:
+        """fp32 PyTorch-layout weights -> packed bf16 GEMM operands held by the plan."""
+        assert w.is_cuda and w.dtype == torch.float32 and w.is_contiguous()
+        if self.w_fprop is None:
+            self.w_fprop = torch.empty(self.packed_fprop_bytes, dtype=torch.uint8, device=w.device)
+        if need_dgrad and self.w_dgrad is None:
+            self.w_dgrad = torch.empty(self.packed_dgrad_bytes, dtype=torch.uint8, device=w.device)
+        check(lib.petsyn_conv_pack_weights(self._h, ptr(w), ptr(self.w_fprop),
+                                           ptr(self.w_dgrad) if need_dgrad else None, stream_ptr()), "conv_pack_weights")
+
+    # kernels -------------------------------------------------------------------------------------------
+    def fprop(self, x: torch.Tensor, y: torch.Tensor, bias: Optional[torch.Tensor] = None) -> torch.Tensor:
+        check(lib.petsyn_conv_fprop(self._h, ptr(x), ptr(self.w_fprop), ptr(bias), ptr(y), stream_ptr()), "conv_fprop")
+        return y
+
+    def dgrad(self, dy: torch.Tensor, dx: torch.Tensor) -> torch.Tensor:
+        check(lib.petsyn_conv_dgrad(self._h, ptr(dy), ptr(self.w_dgrad), ptr(dx), stream_ptr()), "conv_dgrad")
+        return dx
+
+    def wgrad(self, x: torch.Tensor, dy: torch.Tensor, dw: torch.Tensor, accumulate: bool = False,
+              scratch: Optional[torch.Tensor] = None) -> torch.Tensor:
+        if scratch is None:
+            if self._scratch is None:
+                self._scratch = torch.empty(self.wgrad_scratch_bytes, dtype=torch.uint8, device=x.device)
+            scratch = self._scratch
+        assert scratch.numel() * scratch.element_size() >= self.wgrad_scratch_bytes
+        check(lib.petsyn_conv_wgrad(self._h, ptr(x), ptr(dy), ptr(scratch), ptr(dw), int(accumulate), stream_ptr()),
+              "conv_wgrad")
+        return dw
+
+
+# ------------------------------------------------------------------------------------------------ edge layers
+def stem_fwd(x: torch.Tensor, w: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+    """Conv3d(1->C, k4 s2 p1) on the fp32 network input (unet_model.py:47,62); y bf16 NDHWC."""
+    n, _, d, h, wd = x.shape
+    check(lib.petsyn_stem_conv_k4s2_fwd(ptr(x), ptr(w), ptr(y), n, d, h, wd, w.shape[0], stream_ptr()), "stem_fwd")
+    return y
+
+
+def stem_wgrad(x: torch.Tensor, dy: torch.Tensor, dw: torch.Tensor) -> torch.Tensor:
+    n, _, d, h, wd = x.shape
+    check(lib.petsyn_stem_conv_k4s2_wgrad(ptr(x), ptr(dy), ptr(dw), n, d, h, wd, dw.shape[0], stream_ptr()),
+          "stem_wgrad")
+    return dw
+
+
+def head_fwd(x: torch.Tensor, w: torch.Tensor, proj: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+    """ReLU'd skip tensor -> Upsample x2 -> Conv3d(C->1,k3,p1) -> Tanh (unet_model.py:59-64); y fp32 NCDHW."""
+    n, d, h, wd, c = x.shape
+    check(lib.petsyn_head_upconv_tanh_fwd(ptr(x), ptr(w), ptr(proj), ptr(y), n, d, h, wd, c, stream_ptr()), "head_fwd")
+    return y
+
+
+def head_bwd(x, w, y, dy, dproj, dx, dw) -> None:
+    n, d, h, wd, c = x.shape
+    check(lib.petsyn_head_upconv_tanh_bwd(ptr(x), ptr(w), ptr(y), ptr(dy), ptr(dproj), ptr(dx), ptr(dw), n, d, h, wd, c,
+                                          stream_ptr()), "head_bwd")
+
+
+# ------------------------------------------------------------------------------------------------ norm / act
+def bn_stats(z: torch.Tensor, sums: torch.Tensor, rows: int, c: int) -> None:
+    check(lib.petsyn_bn_stats(ptr(z), ptr(sums), rows, c, stream_ptr()), "bn_stats")
+
+
+def bn_finalize(sums, gamma, beta, running_mean, running_var, scale, shift, save_mean, save_rstd, rows: int, c: int,
+                eps: float, momentum: float, training: bool) -> None:
+    check(lib.petsyn_bn_finalize(ptr(sums), ptr(gamma), ptr(beta), ptr(running_mean), ptr(running_var), ptr(scale),
+                                 ptr(shift), ptr(save_mean), ptr(save_rstd), rows, c, eps, momentum, int(training),
+                                 stream_ptr()), "bn_finalize")
+
+
+def norm_act_fwd(z, scale, shift, dst1, cs1: int, co1: int, act1: int, dst2, cs2: int, co2: int, act2: int,
+                 slope: float, rows: int, c: int) -> None:
+    check(lib.petsyn_norm_act_fwd(ptr(z), ptr(scale), ptr(shift), ptr(dst1), cs1, co1, act1, ptr(dst2), cs2, co2, act2,
+                                  slope, rows, c, stream_ptr()), "norm_act_fwd")
+
+
+def norm_act_bwd(z, scale, shift, mean, rstd, gamma, g1, cs1: int, co1: int, act1: int, g2, cs2: int, co2: int,
+                 act2: int, slope: float, sums, dz, dgamma, dbeta, rows: int, c: int) -> None:
+    """Backward of norm_act_fwd: reduction pass (only when normalised) then the apply pass."""
+    if mean is not None:
+        sums.zero_()
+        check(lib.petsyn_norm_act_bwd_reduce(ptr(z), ptr(scale), ptr(shift), ptr(mean), ptr(rstd), ptr(g1), cs1, co1,
+                                             act1, ptr(g2), cs2, co2, act2, slope, ptr(sums), rows, c, stream_ptr()),
+              "norm_act_bwd_reduce")
+    check(lib.petsyn_norm_act_bwd_apply(ptr(z), ptr(scale), ptr(shift), ptr(mean), ptr(rstd), ptr(gamma), ptr(g1), cs1,
+                                        co1, act1, ptr(g2), cs2, co2, act2, slope, ptr(sums), ptr(dz), ptr(dgamma),
+                                        ptr(dbeta), rows, c, stream_ptr()), "norm_act_bwd_apply")
+
+
+# ------------------------------------------------------------------------------------------------ losses / optimiser
+def l1_loss_fwd_bwd(y: torch.Tensor, t: torch.Tensor, loss: torch.Tensor, dy: Optional[torch.Tensor],
+                    grad_scale: float = 1.0) -> None:
+    """nn.L1Loss() value (accumulated into the zeroed scalar ``loss``) and its gradient (train_unet.py:106,149)."""
+    check(lib.petsyn_l1_loss_fwd_bwd(ptr(y), ptr(t), ptr(loss), ptr(dy), y.numel(), grad_scale, stream_ptr()),
+          "l1_loss")
+
+
+def mse_const_fwd_bwd(x, target: float, loss, dx, grad_scale: float = 1.0) -> None:
+    check(lib.petsyn_mse_const_fwd_bwd(ptr(x), target, ptr(loss), ptr(dx), x.numel(), grad_scale, stream_ptr()),
+          "mse_const")
+
+
+def adam_step(p, g, m, v, lr: float, beta1: float, beta2: float, eps: float, step: int) -> None:
+    check(lib.petsyn_adam_step(ptr(p), ptr(g), ptr(m), ptr(v), p.numel(), lr, beta1, beta2, eps, step, stream_ptr()),
+          "adam_step")
+
+
+def sumsq(g: torch.Tensor, out: torch.Tensor) -> None:
+    check(lib.petsyn_sumsq(ptr(g), ptr(out), g.numel(), stream_ptr()), "sumsq")

@@ -1,0 +1,335 @@
+"""Drop-in replacement for the reference's ``unet/utils/unet_model.py`` (UnetGenerator3d and
+UnetSkipConnectionBlock3d, reference lines 5-99) running on libpetsyn's sm_100a kernels.
+
+What is kept identical to the reference (the drop-in boundary):
+  * constructor signatures and defaults, the ``assert input_nc == output_nc`` (unet_model.py:12);
+  * the module tree, hence every ``state_dict`` key/shape and the default initialisation (parameters are held by
+    ordinary ``nn.Conv3d`` / ``nn.BatchNorm3d`` containers created in the reference's order, so a seeded
+    construction draws the same weights and reference checkpoints load with ``load_state_dict``);
+  * ``forward(input)``: fp32 NCDHW in, fp32 NCDHW out, autograd-differentiable, BatchNorm train/eval semantics with
+    running-statistics updates, and the reference's in-place-activation aliasing (the skip half of every concat is
+    ``LeakyReLU(x)``, ReLU'd again by the parent).
+
+What differs: nothing is computed by the container modules.  ``UnetGenerator3d.forward`` hands the whole nest to an
+engine that runs fused CUDA kernels over channels-last bf16 activations (fp32 accumulation, fp32 master weights).
+"""
+from __future__ import annotations
+
+import functools
+from typing import Dict, List, Optional, Tuple
+
+import torch
+import torch.nn as nn
+
+from . import ops
+
+LRELU_SLOPE = 0.2   # unet_model.py:49
+
+
+class UnetSkipConnectionBlock3d(nn.Module):
+    """Parameter container mirroring unet_model.py:37-99 (same children at the same Sequential indices)."""
+
+    def __init__(self, outer_nc, inner_nc, submodule=None, outermost=False, innermost=False,
+                 norm_layer=nn.BatchNorm3d, use_dropout=False):
+        super().__init__()
+        self.outermost = outermost
+        self.innermost = innermost
+        self.outer_nc, self.inner_nc = outer_nc, inner_nc
+        norm_cls = norm_layer.func if isinstance(norm_layer, functools.partial) else norm_layer
+        use_bias = norm_cls == nn.InstanceNorm3d
+        if use_bias or norm_cls != nn.BatchNorm3d:
+            raise NotImplementedError("petsyn UnetGenerator3d implements the reference's default norm_layer=nn.BatchNorm3d")
+        if use_dropout and not (outermost or innermost):
+            raise NotImplementedError("use_dropout=True is not implemented (unused by the reference configs)")
+
+        # creation order == the reference's (downconv, downnorm, upnorm, up conv) so seeded inits coincide
+        downconv = nn.Conv3d(outer_nc, inner_nc, kernel_size=4, stride=2, padding=1, bias=False)
+        downrelu = nn.LeakyReLU(LRELU_SLOPE, True)
+        downnorm = norm_layer(inner_nc)
+        uprelu = nn.ReLU(True)
+        upnorm = norm_layer(outer_nc)
+        upsample = nn.Upsample(scale_factor=2)
+        up_in = inner_nc if innermost else inner_nc * 2
+        conv = nn.Conv3d(up_in, outer_nc, kernel_size=3, stride=1, padding=1, bias=False)
+        if outermost:
+            layers = [downconv, submodule, uprelu, upsample, conv, nn.Tanh()]
+        elif innermost:
+            layers = [downrelu, downconv, uprelu, upsample, conv, upnorm]
+        else:
+            layers = [downrelu, downconv, downnorm, submodule, uprelu, upsample, conv, upnorm]
+        self.model = nn.Sequential(*layers)
+        # handles for the engine (not registered twice: these are the same module objects)
+        self._refs = dict(downconv=downconv, downnorm=None if (outermost or innermost) else downnorm, upconv=conv,
+                          upnorm=None if outermost else upnorm, submodule=submodule)
+
+    def forward(self, x):
+        raise RuntimeError("petsyn blocks are parameter containers; call UnetGenerator3d.forward on the whole generator")
+
+
+class UnetGenerator3d(nn.Module):
+    """B200-native ``UnetGenerator3d`` (reference unet_model.py:5-32): same ctor, same keys, same forward contract."""
+
+    def __init__(self, input_nc, output_nc, num_downs, ngf=64, norm_layer=nn.BatchNorm3d, use_dropout=False):
+        super().__init__()
+        assert (input_nc == output_nc)
+        if input_nc != 1:
+            raise NotImplementedError("petsyn UnetGenerator3d implements the reference configuration input_nc == output_nc == 1")
+        blk = UnetSkipConnectionBlock3d(ngf * 8, ngf * 8, norm_layer=norm_layer, innermost=True)
+        for _ in range(num_downs - 5):
+            blk = UnetSkipConnectionBlock3d(ngf * 8, ngf * 8, blk, norm_layer=norm_layer, use_dropout=use_dropout)
+        blk = UnetSkipConnectionBlock3d(ngf * 4, ngf * 8, blk, norm_layer=norm_layer)
+        blk = UnetSkipConnectionBlock3d(ngf * 2, ngf * 4, blk, norm_layer=norm_layer)
+        if num_downs >= 5:
+            blk = UnetSkipConnectionBlock3d(ngf, ngf * 2, blk, norm_layer=norm_layer)
+            blk = UnetSkipConnectionBlock3d(output_nc, ngf, blk, outermost=True, norm_layer=norm_layer)
+        else:
+            blk = UnetSkipConnectionBlock3d(output_nc, ngf * 2, blk, outermost=True, norm_layer=norm_layer)
+        self.model = blk
+        self._engines: Dict[Tuple, "_Engine"] = {}
+
+    # ------------------------------------------------------------------------------------------------
+    def levels(self) -> List[UnetSkipConnectionBlock3d]:
+        out, b = [], self.model
+        while b is not None:
+            out.append(b)
+            b = b._refs["submodule"]
+        return out
+
+    def engine_for(self, x: torch.Tensor) -> "_Engine":
+        key = (tuple(x.shape), x.device.index)
+        eng = self._engines.get(key)
+        if eng is None:
+            eng = _Engine(self, tuple(x.shape), x.device)
+            self._engines[key] = eng
+        return eng
+
+    def forward(self, input):
+        if not input.is_cuda:
+            raise RuntimeError("petsyn UnetGenerator3d runs on CUDA (sm_100a) only; there is no CPU path")
+        if input.dim() != 5 or input.shape[1] != 1:
+            raise ValueError(f"expected input of shape [N, 1, D, H, W], got {tuple(input.shape)}")
+        x = input.contiguous().float()
+        eng = self.engine_for(x)
+        params = eng.param_list()
+        if torch.is_grad_enabled() and any(p.requires_grad for p in params):
+            return _UnetFn.apply(x, eng, *params)
+        return eng.forward(x, save=False)
+
+    def flops_per_call(self, shape) -> Tuple[float, float]:
+        """(algorithmic, executed) forward FLOPs for an input of ``shape`` (needs a CUDA device)."""
+        eng = self._engines.get((tuple(shape), torch.cuda.current_device()))
+        if eng is None:
+            raise RuntimeError("run a forward pass on this shape first")
+        return eng.flops_algorithmic, eng.flops_executed
+
+
+class _UnetFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, eng, *params):
+        ctx.eng = eng
+        return eng.forward(x, save=True)
+
+    @staticmethod
+    def backward(ctx, dy):
+        grads = ctx.eng.backward(dy.contiguous().float())
+        return (None, None, *grads)
+
+
+class _Norm:
+    """Buffers of one BatchNorm3d site."""
+
+    def __init__(self, bn: nn.BatchNorm3d, c: int, dev):
+        self.bn = bn
+        f = lambda n=c: torch.empty(n, dtype=torch.float32, device=dev)
+        self.sums = torch.zeros(2 * c, dtype=torch.float32, device=dev)
+        self.bsums = torch.zeros(2 * c, dtype=torch.float32, device=dev)
+        self.scale, self.shift, self.mean, self.rstd = f(), f(), f(), f()
+        self.dgamma, self.dbeta = f(), f()
+
+
+class _Engine:
+    """Buffers, plans and the fwd/bwd schedules for one (input shape, device)."""
+
+    def __init__(self, gen: UnetGenerator3d, shape, dev):
+        n, _, d, h, w = shape
+        self.gen = gen
+        self.shape = shape
+        self.dev = dev
+        lv = gen.levels()
+        L = len(lv)
+        self.L = L
+        if d % (1 << L) or h % (1 << L) or w % (1 << L):
+            raise ValueError(f"spatial dims {d}x{h}x{w} must be divisible by {1 << L} (one halving per level)")
+        self.lv = lv
+        bf = lambda *s: torch.empty(*s, dtype=torch.bfloat16, device=dev)
+        self.dims = [(d >> i, h >> i, w >> i) for i in range(L + 1)]          # resolution /2^i
+        self.rows = [n * a * b * c for (a, b, c) in self.dims]
+        outer = [b.outer_nc for b in lv]
+        inner = [b.inner_nc for b in lv]
+        self.outer, self.inner = outer, inner
+        for c in outer[1:] + inner:
+            if c % 8:
+                raise ValueError(f"channel widths must be multiples of 8 (got {c}); use ngf % 4 == 0")
+        # ---- activations (forward) ----
+        self.z = [bf(self.rows[i + 1], inner[i]) for i in range(L)]            # raw down-conv outputs
+        self.a = [None] + [bf(self.rows[i], outer[i]) for i in range(1, L)]    # LeakyReLU'd block inputs
+        self.cat = [None] + [bf(self.rows[i], 2 * outer[i]) for i in range(1, L)]   # [ReLU(up_i) | ReLU(x_i)]
+        self.zu = [None] + [bf(self.rows[i], outer[i]) for i in range(1, L)]   # raw up-conv outputs
+        self.r = bf(self.rows[L], inner[L - 1])                                # ReLU(innermost down output)
+        self.proj = torch.empty(self.rows[1], 32, dtype=torch.float32, device=dev)
+        self.y = torch.empty(n, 1, d, h, w, dtype=torch.float32, device=dev)
+        # ---- gradients ----
+        self.dz = [bf(self.rows[i + 1], inner[i]) for i in range(L)]
+        self.da = [None] + [bf(self.rows[i], outer[i]) for i in range(1, L)]
+        self.dcat = [None] + [bf(self.rows[i], 2 * outer[i]) for i in range(1, L)]
+        self.dzu = [None] + [bf(self.rows[i], outer[i]) for i in range(1, L)]
+        self.dr = bf(self.rows[L], inner[L - 1])
+        self.dproj = torch.empty(self.rows[1], 32, dtype=torch.float32, device=dev)
+        # ---- norms ----
+        self.dnorm: List[Optional[_Norm]] = [None] * L
+        self.unorm: List[Optional[_Norm]] = [None] * L
+        for i, b in enumerate(lv):
+            if b._refs["downnorm"] is not None:
+                self.dnorm[i] = _Norm(b._refs["downnorm"], inner[i], dev)
+            if b._refs["upnorm"] is not None:
+                self.unorm[i] = _Norm(b._refs["upnorm"], outer[i], dev)
+        # ---- conv plans ----
+        self.down: List[Optional[ops.ConvPlan]] = [None] * L
+        self.up: List[Optional[ops.ConvPlan]] = [None] * L
+        for i in range(1, L):
+            di, hi, wi = self.dims[i]
+            self.down[i] = ops.ConvPlan(ops.OP_CONV, n, di, hi, wi, outer[i], inner[i], 4, 2, 1)
+            dj, hj, wj = self.dims[i + 1]
+            if i == L - 1:   # innermost: input is r (inner channels, contiguous)
+                self.up[i] = ops.ConvPlan(ops.OP_UPCONV, n, dj, hj, wj, inner[i], outer[i], 3, 1, 1)
+            else:            # input is cat_{i+1} (2*inner_i channels); dgrad writes dcat_{i+1}
+                self.up[i] = ops.ConvPlan(ops.OP_UPCONV, n, dj, hj, wj, 2 * inner[i], outer[i], 3, 1, 1)
+        self.flops_algorithmic = sum(p.flops_algorithmic for p in self.down[1:] + self.up[1:])
+        self.flops_executed = sum(p.flops_executed for p in self.down[1:] + self.up[1:])
+        stem = 2.0 * self.rows[1] * inner[0] * 64
+        head = 2.0 * self.rows[0] * (2 * inner[0]) * 27
+        self.flops_algorithmic += stem + head
+        self.flops_executed += stem + 2.0 * self.rows[1] * (2 * inner[0]) * 27
+        self._packed_versions: Dict[int, int] = {}
+        self._grads: Optional[List[torch.Tensor]] = None
+        self._saved_x: Optional[torch.Tensor] = None
+
+    # ------------------------------------------------------------------------------------------------ parameters
+    def param_list(self) -> List[torch.Tensor]:
+        ps = []
+        for i, b in enumerate(self.lv):
+            ps.append(b._refs["downconv"].weight)
+            if self.dnorm[i] is not None:
+                ps += [self.dnorm[i].bn.weight, self.dnorm[i].bn.bias]
+            ps.append(b._refs["upconv"].weight)
+            if self.unorm[i] is not None:
+                ps += [self.unorm[i].bn.weight, self.unorm[i].bn.bias]
+        return ps
+
+    def _repack(self, need_dgrad: bool) -> None:
+        """Refresh the packed bf16 operands of every conv whose fp32 master weight changed."""
+        for i in range(1, self.L):
+            for plan, conv, dg in ((self.down[i], self.lv[i]._refs["downconv"], True),
+                                   (self.up[i], self.lv[i]._refs["upconv"], True)):
+                w = conv.weight
+                ver = (w._version, w.data_ptr(), need_dgrad and dg)
+                if self._packed_versions.get(id(plan)) != ver:
+                    plan.pack(w.detach(), need_dgrad=need_dgrad and dg)
+                    self._packed_versions[id(plan)] = ver
+
+    # ------------------------------------------------------------------------------------------------ forward
+    def _bn_forward(self, nm: _Norm, z: torch.Tensor, rows: int, c: int, training: bool) -> None:
+        bn = nm.bn
+        if training:
+            nm.sums.zero_()
+            ops.bn_stats(z, nm.sums, rows, c)
+            if bn.track_running_stats and bn.num_batches_tracked is not None:
+                bn.num_batches_tracked.add_(1)
+        momentum = 0.1 if bn.momentum is None else bn.momentum
+        ops.bn_finalize(nm.sums, bn.weight, bn.bias, bn.running_mean, bn.running_var, nm.scale, nm.shift, nm.mean,
+                        nm.rstd, rows, c, bn.eps, momentum, training)
+
+    def forward(self, x: torch.Tensor, save: bool) -> torch.Tensor:
+        L = self.L
+        training = self.gen.training
+        self._repack(need_dgrad=save)
+        lv = self.lv
+        self._saved_x = x if save else None
+        # ---- down path ----
+        ops.stem_fwd(x, lv[0]._refs["downconv"].weight.detach(), self.z[0])
+        for i in range(1, L):
+            prev = self.dnorm[i - 1]
+            c = self.outer[i]
+            if prev is not None:
+                self._bn_forward(prev, self.z[i - 1], self.rows[i], c, training)
+            ops.norm_act_fwd(self.z[i - 1], prev.scale if prev else None, prev.shift if prev else None,
+                             self.a[i], c, 0, ops.ACT_LRELU, self.cat[i], 2 * c, c, ops.ACT_RELU, LRELU_SLOPE,
+                             self.rows[i], c)
+            self.down[i].fprop(self.a[i], self.z[i])
+        # ---- innermost: ReLU(z) ----
+        ci = self.inner[L - 1]
+        ops.norm_act_fwd(self.z[L - 1], None, None, self.r, ci, 0, ops.ACT_RELU, None, 0, 0, ops.ACT_NONE, LRELU_SLOPE,
+                         self.rows[L], ci)
+        # ---- up path ----
+        for i in range(L - 1, 0, -1):
+            src = self.r if i == L - 1 else self.cat[i + 1]
+            self.up[i].fprop(src, self.zu[i])
+            nm = self.unorm[i]
+            c = self.outer[i]
+            self._bn_forward(nm, self.zu[i], self.rows[i], c, training)
+            ops.norm_act_fwd(self.zu[i], nm.scale, nm.shift, self.cat[i], 2 * c, 0, ops.ACT_RELU, None, 0, 0,
+                             ops.ACT_NONE, LRELU_SLOPE, self.rows[i], c)
+        n, _, d, h, w = self.shape
+        d1, h1, w1 = self.dims[1]
+        cat1 = self.cat[1].view(n, d1, h1, w1, 2 * self.outer[1])
+        y = self.y if save else torch.empty_like(self.y)
+        ops.head_fwd(cat1, lv[0]._refs["upconv"].weight.detach(), self.proj, y)
+        return y.clone() if save else y
+
+    # ------------------------------------------------------------------------------------------------ backward
+    def _grad_buffers(self) -> List[torch.Tensor]:
+        if self._grads is None:
+            self._grads = [torch.empty_like(p, dtype=torch.float32) for p in self.param_list()]
+        return self._grads
+
+    def backward(self, dy: torch.Tensor) -> List[torch.Tensor]:
+        L = self.L
+        lv = self.lv
+        grads = self._grad_buffers()
+        # map parameter -> grad slot
+        slot: Dict[int, torch.Tensor] = {id(p): g for p, g in zip(self.param_list(), grads)}
+        gw = lambda conv: slot[id(conv.weight)]
+        n = self.shape[0]
+        d1, h1, w1 = self.dims[1]
+        cat1 = self.cat[1].view(n, d1, h1, w1, 2 * self.outer[1])
+        ops.head_bwd(cat1, lv[0]._refs["upconv"].weight.detach(), self.y, dy, self.dproj, self.dcat[1],
+                     gw(lv[0]._refs["upconv"]))
+        # ---- up path, outer -> inner ----
+        for i in range(1, L):
+            nm = self.unorm[i]
+            c = self.outer[i]
+            ops.norm_act_bwd(self.zu[i], nm.scale, nm.shift, nm.mean, nm.rstd, nm.bn.weight, self.dcat[i], 2 * c, 0,
+                             ops.ACT_RELU, None, 0, 0, ops.ACT_NONE, LRELU_SLOPE, nm.bsums, self.dzu[i],
+                             slot[id(nm.bn.weight)], slot[id(nm.bn.bias)], self.rows[i], c)
+            src = self.r if i == L - 1 else self.cat[i + 1]
+            dsrc = self.dr if i == L - 1 else self.dcat[i + 1]
+            self.up[i].wgrad(src, self.dzu[i], gw(lv[i]._refs["upconv"]))
+            self.up[i].dgrad(self.dzu[i], dsrc)
+        # ---- innermost: through ReLU(z) ----
+        ci = self.inner[L - 1]
+        ops.norm_act_bwd(self.z[L - 1], None, None, None, None, None, self.dr, ci, 0, ops.ACT_RELU, None, 0, 0,
+                         ops.ACT_NONE, LRELU_SLOPE, None, self.dz[L - 1], None, None, self.rows[L], ci)
+        # ---- down path, inner -> outer ----
+        for i in range(L - 1, 0, -1):
+            self.down[i].wgrad(self.a[i], self.dz[i], gw(lv[i]._refs["downconv"]))
+            self.down[i].dgrad(self.dz[i], self.da[i])
+            prev = self.dnorm[i - 1]
+            c = self.outer[i]
+            ops.norm_act_bwd(self.z[i - 1], prev.scale if prev else None, prev.shift if prev else None,
+                             prev.mean if prev else None, prev.rstd if prev else None,
+                             prev.bn.weight if prev else None, self.da[i], c, 0, ops.ACT_LRELU, self.dcat[i], 2 * c, c,
+                             ops.ACT_RELU, LRELU_SLOPE, prev.bsums if prev else None, self.dz[i - 1],
+                             slot[id(prev.bn.weight)] if prev else None, slot[id(prev.bn.bias)] if prev else None,
+                             self.rows[i], c)
+        ops.stem_wgrad(self._saved_x, self.dz[0], gw(lv[0]._refs["downconv"]))
+        return [g.clone() for g in grads]

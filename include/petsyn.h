@@ -1,0 +1,193 @@
+/*
+ * libpetsyn -- C ABI of the B200-native (sm_100a) kernels behind the 3D T1->PET generator hot path.
+ *
+ * The reference (jessyblues/Causality-Informed-PET-Synthesis-from-Multi-modal-Data) is pure PyTorch and has no
+ * FFI/plugin layer of its own: its "operator interface" for this path is the set of ATen/cuDNN calls made by the
+ * nn.Module graphs in
+ *     unet/utils/unet_model.py:37-99            (Conv3d k4 s2 p1, Upsample x2 + Conv3d k3 p1, BatchNorm3d,
+ *                                                LeakyReLU/ReLU/Tanh, skip concat)
+ *     unet/utils/atten_unet_model.py:565-662    (GroupNorm + SiLU + Conv3d k3, AvgPool/nearest resampling)
+ *     bl_methods/BMGAN/bmgan_model.py:12-144    (Conv3d k3 s1/s2, ConvTranspose3d k4 s2 p1, InstanceNorm3d,
+ *                                                LeakyReLU/PReLU)
+ *     unet/scripts/train_unet.py:106,149,155    (L1 / LSGAN-MSE losses), train_unify_causal_gen.py:57-73 (KL)
+ * Every entry point below names the reference call it replaces.  A maintainer binds them from Python with ctypes
+ * (see INTEGRATION.md); the package's host layer (`_cabi.py`) is exactly such a binding.
+ *
+ * Conventions
+ *   - All functions return 0 on success or a negative PETSYN_E* code; petsyn_last_error() returns a thread-local
+ *     human-readable message for the last failure on the calling thread.
+ *   - The caller owns every buffer (inputs, outputs, workspaces); the library allocates no tensor memory.  A plan
+ *     object owns only small device-side tables (tap programs) and its cached TMA descriptors.
+ *   - All work is enqueued on the cudaStream_t passed in (as void*); no call synchronises the device.
+ *   - Activations are channels-last (N, D, H, W, C) bf16; a tensor may be a channel slice [coff, coff+C) of a wider
+ *     buffer with `cstride` channels per voxel -- this is how skip concatenation is made copy-free.
+ *   - Master weights are fp32 in PyTorch layout (Cout, Cin, kD, kH, kW); kernels consume packed bf16 copies made by
+ *     petsyn_conv_pack_weights().
+ *   - There is no CPU implementation behind this ABI.
+ */
+#ifndef PETSYN_H_
+#define PETSYN_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PETSYN_VERSION 100
+
+/* error codes */
+#define PETSYN_OK 0
+#define PETSYN_EINVAL (-1)   /* bad descriptor / unsupported shape (Python layer raises ValueError) */
+#define PETSYN_ECUDA (-2)    /* CUDA runtime/driver error (RuntimeError) */
+#define PETSYN_ENOMEM (-3)   /* workspace too small */
+
+int32_t petsyn_version(void);
+const char* petsyn_last_error(void);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Convolution family (implicit GEMM on tcgen05 tensor cores, TMA-fed, fp32 accumulation in TMEM)
+ * ---------------------------------------------------------------------------------------------------------- */
+
+/* operator kinds */
+#define PETSYN_OP_CONV 0    /* nn.Conv3d(k, stride 1|2, pad)                  unet_model.py:47, bmgan_model.py:34-51 */
+#define PETSYN_OP_UPCONV 1  /* nn.Upsample(scale_factor=2) -> nn.Conv3d(k3,p1)  unet_model.py:59-60,71-72,81-82     */
+#define PETSYN_OP_CONVT 2   /* nn.ConvTranspose3d(k4, s2, p1)                 bmgan_model.py:57-64                  */
+
+/* epilogue activations (fused after bias) */
+#define PETSYN_ACT_NONE 0
+#define PETSYN_ACT_RELU 1
+#define PETSYN_ACT_LRELU 2   /* slope given separately */
+#define PETSYN_ACT_SILU 3
+#define PETSYN_ACT_TANH 4
+
+typedef struct petsyn_conv_desc {
+  int32_t op;                 /* PETSYN_OP_* */
+  int32_t n, d, h, w;         /* dims of the stored input x (for UPCONV: before the nearest x2 upsample) */
+  int32_t cin, cout;          /* multiples of 8 (TMA 16-byte stride rule) */
+  int32_t ksize, stride, pad; /* CONV: k in {1,3,4}, stride in {1,2}; UPCONV: 3,1,1; CONVT: 4,2,1 */
+  int32_t x_cstride, x_coff;  /* channel pitch / offset of x inside its NDHWC buffer (bf16) */
+  int32_t y_cstride, y_coff;  /* same for the forward output y (bf16) */
+  int32_t dy_cstride, dy_coff;/* gradient w.r.t. y (bf16) */
+  int32_t dx_cstride, dx_coff;/* gradient w.r.t. x (bf16) */
+  int32_t epi_act;            /* PETSYN_ACT_* applied to y in the fprop epilogue (after bias) */
+  float epi_slope;            /* LeakyReLU slope */
+} petsyn_conv_desc;
+
+typedef struct petsyn_conv_plan petsyn_conv_plan;
+
+/* Validates the descriptor, chooses tiles, builds the device-side tap programs.  ValueError-class failures
+ * (PETSYN_EINVAL) mirror the reference's channel/shape checks (atten_unet_model.py:502-506,545-546). */
+int32_t petsyn_conv_plan_create(const petsyn_conv_desc* desc, petsyn_conv_plan** plan);
+void petsyn_conv_plan_destroy(petsyn_conv_plan* plan);
+
+/* Output spatial dims of the forward op. */
+int32_t petsyn_conv_out_dims(const petsyn_conv_plan* plan, int32_t* od, int32_t* oh, int32_t* ow);
+/* Direct-convolution FLOPs of one forward call (2*M*Cout*Cin*k^3) and the FLOPs the kernel executes
+ * (smaller for UPCONV, whose 27 taps collapse to 8 per output phase). */
+int32_t petsyn_conv_flops(const petsyn_conv_plan* plan, double* algorithmic, double* executed);
+
+/* Sizes (bytes) of the packed bf16 weight images and of the fp32 wgrad scratch. */
+size_t petsyn_conv_packed_fprop_bytes(const petsyn_conv_plan* plan);
+size_t petsyn_conv_packed_dgrad_bytes(const petsyn_conv_plan* plan);
+size_t petsyn_conv_wgrad_scratch_bytes(const petsyn_conv_plan* plan);
+
+/* fp32 (Cout,Cin,k,k,k) [CONVT: (Cin,Cout,k,k,k)] -> packed bf16 GEMM operands.  Either destination may be NULL. */
+int32_t petsyn_conv_pack_weights(petsyn_conv_plan* plan, const float* w, void* packed_fprop, void* packed_dgrad,
+                                 void* stream);
+
+/* y = act(conv(x, W) + bias).  Replaces F.conv3d / F.conv_transpose3d (+ the preceding F.interpolate for UPCONV).
+ * bias may be NULL (BatchNorm'd convs are bias-free, unet_model.py:42-45). */
+int32_t petsyn_conv_fprop(petsyn_conv_plan* plan, const void* x, const void* packed_fprop, const float* bias, void* y,
+                          void* stream);
+/* dx = conv_backward_input(dy, W).  Replaces cuDNN dgrad (+ the upsample's backward for UPCONV). */
+int32_t petsyn_conv_dgrad(petsyn_conv_plan* plan, const void* dy, const void* packed_dgrad, void* dx, void* stream);
+/* dw (fp32, PyTorch layout) = conv_backward_weight(x, dy); optional dbias (fp32 [cout]) = sum(dy).
+ * `scratch` must hold petsyn_conv_wgrad_scratch_bytes(); it is zeroed and reduced into by the kernel.
+ * accumulate != 0 adds into dw instead of overwriting (autograd .grad accumulation). */
+int32_t petsyn_conv_wgrad(petsyn_conv_plan* plan, const void* x, const void* dy, void* scratch, float* dw,
+                          int32_t accumulate, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Edge layers of the pix2pix U-Net that are bandwidth-bound by construction (Cin = 1 or Cout = 1)
+ * ---------------------------------------------------------------------------------------------------------- */
+
+/* First layer: Conv3d(1 -> cout, k4 s2 p1, no bias) on the fp32 NCDHW network input (unet_model.py:47,62).
+ * x fp32 [n,d,h,w]; w fp32 [cout,1,4,4,4]; y bf16 NDHWC [n,d/2,h/2,w/2,cout] raw (pre-activation). */
+int32_t petsyn_stem_conv_k4s2_fwd(const float* x, const float* w, void* y, int32_t n, int32_t d, int32_t h, int32_t w_,
+                                  int32_t cout, void* stream);
+/* dw[cout,64] (fp32) = backward-weight of the stem; dy bf16 [n,d/2,h/2,w/2,cout].  dw is overwritten. */
+int32_t petsyn_stem_conv_k4s2_wgrad(const float* x, const void* dy, float* dw, int32_t n, int32_t d, int32_t h,
+                                    int32_t w_, int32_t cout, void* stream);
+
+/* Last layer: ReLU'd skip tensor -> Upsample x2 -> Conv3d(cin -> 1, k3 p1, no bias) -> Tanh (unet_model.py:59-64).
+ * x bf16 NDHWC [n,d,h,w,cin] (already ReLU'd); w fp32 [1,cin,3,3,3]; proj fp32 scratch [n*d*h*w*32];
+ * y fp32 [n,1,2d,2h,2w]. */
+int32_t petsyn_head_upconv_tanh_fwd(const void* x, const float* w, float* proj, float* y, int32_t n, int32_t d,
+                                    int32_t h, int32_t w_, int32_t cin, void* stream);
+/* Backward of the head given dL/dy (fp32, [n,1,2d,2h,2w]) and the saved output y (for tanh').
+ * dx bf16 [n,d,h,w,cin] (gradient w.r.t. the ReLU'd input), dw fp32 [1,cin,27] overwritten. */
+int32_t petsyn_head_upconv_tanh_bwd(const void* x, const float* w, const float* y, const float* dy, float* dproj,
+                                    void* dx, float* dw, int32_t n, int32_t d, int32_t h, int32_t w_, int32_t cin,
+                                    void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Normalisation + activation + skip-concat (bandwidth-bound, vectorised, warp-shuffle reductions)
+ * ---------------------------------------------------------------------------------------------------------- */
+
+/* statistics granularity */
+#define PETSYN_NORM_BATCH 0     /* nn.BatchNorm3d: per channel over N*D*H*W        (unet_model.py:50,52)        */
+#define PETSYN_NORM_INSTANCE 1  /* nn.InstanceNorm3d: per (n, channel)             (bmgan_model.py via MONAI ADN) */
+#define PETSYN_NORM_GROUP 2     /* nn.GroupNorm: per (n, group)                    (atten_unet_model.py:593-612) */
+
+/* Per-channel partial sums of a raw conv output z (bf16 [rows, c] contiguous, rows = n*d*h*w):
+ * sums[2*c] (fp32, caller-zeroed): sum z, sum z^2 per channel (BATCH) */
+int32_t petsyn_bn_stats(const void* z, float* sums, int64_t rows, int32_t c, void* stream);
+/* mean/rstd -> fused affine (scale = gamma*rstd, shift = beta - mean*scale) and the running-stat update
+ * (momentum, unbiased variance) of nn.BatchNorm3d in training mode.  In eval mode (training == 0) scale/shift are
+ * derived from the running statistics and `sums` is ignored.  save_mean/save_rstd are kept for backward. */
+int32_t petsyn_bn_finalize(const float* sums, const float* gamma, const float* beta, float* running_mean,
+                           float* running_var, float* scale, float* shift, float* save_mean, float* save_rstd,
+                           int64_t rows, int32_t c, float eps, float momentum, int32_t training, void* stream);
+/* dst1 = act1(z*scale + shift) [, dst2 = act2(same)] written into channel slices of wider NDHWC buffers -- the
+ * copy-free form of `torch.cat([model(x), x], 1)` (unet_model.py:99) including the reference's in-place-activation
+ * aliasing (the skip half is LeakyReLU(x), then ReLU'd by the parent).  scale/shift may be NULL (no norm). */
+int32_t petsyn_norm_act_fwd(const void* z, const float* scale, const float* shift, void* dst1, int32_t dst1_cstride,
+                            int32_t dst1_coff, int32_t act1, void* dst2, int32_t dst2_cstride, int32_t dst2_coff,
+                            int32_t act2, float slope, int64_t rows, int32_t c, void* stream);
+/* Backward, pass 1: with b = z*scale+shift and g = g1*act1'(b) [+ g2*act2'(b)], accumulate per channel
+ * sums[c] += sum g, sums[c + C] += sum g*zhat (zhat = (z-mean)*rstd).  sums caller-zeroed. */
+int32_t petsyn_norm_act_bwd_reduce(const void* z, const float* scale, const float* shift, const float* mean,
+                                   const float* rstd, const void* g1, int32_t g1_cstride, int32_t g1_coff,
+                                   int32_t act1, const void* g2, int32_t g2_cstride, int32_t g2_coff, int32_t act2,
+                                   float slope, float* sums, int64_t rows, int32_t c, void* stream);
+/* Backward, pass 2: dz = gamma*rstd*(g - sum_g/rows - zhat*sum_gz/rows) (BatchNorm training backward), or
+ * dz = g when mean == NULL (no norm).  Also emits dgamma = sum g*zhat, dbeta = sum g when dgamma != NULL. */
+int32_t petsyn_norm_act_bwd_apply(const void* z, const float* scale, const float* shift, const float* mean,
+                                  const float* rstd, const float* gamma, const void* g1, int32_t g1_cstride,
+                                  int32_t g1_coff, int32_t act1, const void* g2, int32_t g2_cstride, int32_t g2_coff,
+                                  int32_t act2, float slope, const float* sums, void* dz, float* dgamma,
+                                  float* dbeta, int64_t rows, int32_t c, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Losses and optimiser
+ * ---------------------------------------------------------------------------------------------------------- */
+
+/* nn.L1Loss() forward + backward seed in one pass (train_unet.py:106,149): loss[0] += mean|y - t| (caller-zeroed),
+ * dy = grad_scale * sign(y - t) / numel. */
+int32_t petsyn_l1_loss_fwd_bwd(const float* y, const float* t, float* loss, float* dy, int64_t numel, float grad_scale,
+                               void* stream);
+/* LSGAN PatchAdversarialLoss(criterion="least_squares"): mean (x - target)^2 and its gradient. */
+int32_t petsyn_mse_const_fwd_bwd(const float* x, float target, float* loss, float* dx, int64_t numel, float grad_scale,
+                                 void* stream);
+/* torch.optim.Adam step (no amsgrad, weight_decay 0) over one flat fp32 parameter arena. step is 1-based. */
+int32_t petsyn_adam_step(float* p, const float* g, float* m, float* v, int64_t numel, float lr, float beta1,
+                         float beta2, float eps, int32_t step, void* stream);
+/* sum of squares of a flat fp32 array, accumulated into out[0] (caller-zeroed); used for gradient norms. */
+int32_t petsyn_sumsq(const float* g, float* out, int64_t numel, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PETSYN_H_ */

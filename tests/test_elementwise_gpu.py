@@ -1,0 +1,125 @@
+"""Parity of the bandwidth-bound kernels (norm/act/concat, stem, head, losses, Adam) against plain PyTorch fp32."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def rel(got, ref):
+    return ((got.float() - ref.float()).abs().max() / (ref.float().abs().max() + 1e-12)).item()
+
+
+def test_batchnorm_act_concat_fwd_bwd(petsyn):
+    ops = petsyn.ops
+    g = torch.Generator().manual_seed(3)
+    rows, c = 4096 + 37, 128
+    z = (torch.randn(rows, c, generator=g) * 1.7 + 0.3).to(DEV).to(torch.bfloat16)
+    gamma = (torch.rand(c, generator=g) + 0.5).to(DEV)
+    beta = torch.randn(c, generator=g).to(DEV)
+    rm, rv = torch.zeros(c, device=DEV), torch.ones(c, device=DEV)
+    sums = torch.zeros(2 * c, device=DEV)
+    scale, shift, mean, rstd = (torch.empty(c, device=DEV) for _ in range(4))
+    ops.bn_stats(z, sums, rows, c)
+    ops.bn_finalize(sums, gamma, beta, rm, rv, scale, shift, mean, rstd, rows, c, 1e-5, 0.1, True)
+    a = torch.empty(rows, c, dtype=torch.bfloat16, device=DEV)
+    cat = torch.zeros(rows, 2 * c, dtype=torch.bfloat16, device=DEV)
+    ops.norm_act_fwd(z, scale, shift, a, c, 0, ops.ACT_LRELU, cat, 2 * c, c, ops.ACT_RELU, 0.2, rows, c)
+    torch.cuda.synchronize()
+
+    z32 = z.float().requires_grad_(True)
+    gm, bt = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    rm2, rv2 = torch.zeros(c, device=DEV), torch.ones(c, device=DEV)
+    b = F.batch_norm(z32, rm2, rv2, gm, bt, True, 0.1, 1e-5)
+    a_ref, s_ref = F.leaky_relu(b, 0.2), F.relu(b)
+    assert rel(a, a_ref) < 1e-2 and rel(cat[:, c:], s_ref) < 1e-2
+    assert cat[:, :c].abs().max().item() == 0
+    assert rel(rm, rm2) < 1e-4 and rel(rv, rv2) < 1e-4
+
+    g1 = torch.randn(rows, c, generator=g).to(DEV).to(torch.bfloat16)
+    g2buf = torch.randn(rows, 2 * c, generator=g).to(DEV).to(torch.bfloat16)
+    (a_ref * g1.float()).sum().add((s_ref * g2buf[:, c:].float()).sum()).backward()
+    bsums = torch.zeros(2 * c, device=DEV)
+    dz = torch.empty(rows, c, dtype=torch.bfloat16, device=DEV)
+    dgamma, dbeta = torch.empty(c, device=DEV), torch.empty(c, device=DEV)
+    ops.norm_act_bwd(z, scale, shift, mean, rstd, gamma, g1, c, 0, ops.ACT_LRELU, g2buf, 2 * c, c, ops.ACT_RELU, 0.2,
+                     bsums, dz, dgamma, dbeta, rows, c)
+    torch.cuda.synchronize()
+    assert rel(dz, z32.grad) < 2e-2
+    assert rel(dgamma, gm.grad) < 2e-3 and rel(dbeta, bt.grad) < 2e-3
+
+
+def test_stem_and_head(petsyn):
+    ops = petsyn.ops
+    g = torch.Generator().manual_seed(5)
+    n, d, h, w, c = 2, 8, 12, 16, 64
+    x = torch.rand(n, 1, d, h, w, generator=g).to(DEV)
+    ws = (torch.randn(c, 1, 4, 4, 4, generator=g) / 8).to(DEV)
+    y = torch.empty(n, d // 2, h // 2, w // 2, c, dtype=torch.bfloat16, device=DEV)
+    ops.stem_fwd(x, ws, y)
+    ref = F.conv3d(x, ws, None, stride=2, padding=1)
+    assert rel(y.permute(0, 4, 1, 2, 3), ref) < 1e-2
+    dy = torch.randn(ref.shape, generator=g).to(DEV).to(torch.bfloat16)
+    ws2 = ws.clone().requires_grad_(True)
+    F.conv3d(x, ws2, None, stride=2, padding=1).backward(dy.float())
+    dw = torch.empty_like(ws)
+    ops.stem_wgrad(x, dy.permute(0, 2, 3, 4, 1).contiguous(), dw)
+    assert rel(dw, ws2.grad) < 1e-3
+
+    # head: relu'd input (bf16, NDHWC) -> up x2 -> conv3(C->1) -> tanh
+    ch = 2 * c
+    xin = torch.randn(n, d, h, w, ch, generator=g).relu().to(DEV).to(torch.bfloat16)
+    wh = (torch.randn(1, ch, 3, 3, 3, generator=g) / (ch * 27) ** 0.5 * 3).to(DEV)
+    proj = torch.empty(n * d * h * w, 32, device=DEV)
+    yo = torch.empty(n, 1, 2 * d, 2 * h, 2 * w, device=DEV)
+    ops.head_fwd(xin, wh, proj, yo)
+    x32 = xin.float().permute(0, 4, 1, 2, 3).contiguous().requires_grad_(True)
+    wh2 = wh.clone().requires_grad_(True)
+    yr = torch.tanh(F.conv3d(F.interpolate(x32, scale_factor=2, mode="nearest"), wh2, None, padding=1))
+    assert (yo - yr).abs().max().item() < 1e-4
+    go = torch.randn(yr.shape, generator=g).to(DEV)
+    yr.backward(go)
+    dproj = torch.empty_like(proj)
+    dx = torch.empty_like(xin)
+    dwh = torch.empty_like(wh)
+    ops.head_bwd(xin, wh, yo, go, dproj, dx, dwh)
+    assert rel(dx.permute(0, 4, 1, 2, 3), x32.grad) < 1e-2
+    assert rel(dwh, wh2.grad) < 1e-3
+
+
+def test_losses_and_adam(petsyn):
+    ops = petsyn.ops
+    g = torch.Generator().manual_seed(9)
+    y = torch.rand(3, 1, 8, 9, 11, generator=g).to(DEV)
+    t = torch.rand(3, 1, 8, 9, 11, generator=g).to(DEV)
+    loss = torch.zeros(1, device=DEV)
+    dy = torch.empty_like(y)
+    ops.l1_loss_fwd_bwd(y, t, loss, dy)
+    y2 = y.clone().requires_grad_(True)
+    lr = F.l1_loss(y2, t)
+    lr.backward()
+    assert abs(loss.item() - lr.item()) < 1e-6 and (dy - y2.grad).abs().max().item() < 1e-9
+
+    x = torch.randn(2, 1, 4, 6, 4, generator=g).to(DEV)
+    loss.zero_()
+    dx = torch.empty_like(x)
+    ops.mse_const_fwd_bwd(x, 1.0, loss, dx)
+    x2 = x.clone().requires_grad_(True)
+    lm = F.mse_loss(x2, torch.ones_like(x2))
+    lm.backward()
+    assert abs(loss.item() - lm.item()) < 1e-5 and (dx - x2.grad).abs().max().item() < 1e-7
+
+    p = torch.randn(10007, generator=g).to(DEV)
+    pr = p.clone().requires_grad_(True)
+    opt = torch.optim.Adam([pr], lr=5e-4, betas=(0.9, 0.999), eps=1e-8)
+    m, v = torch.zeros_like(p), torch.zeros_like(p)
+    for step in range(1, 4):
+        gr = torch.randn(10007, generator=g).to(DEV)
+        pr.grad = gr.clone()
+        opt.step()
+        ops.adam_step(p, gr, m, v, 5e-4, 0.9, 0.999, 1e-8, step)
+    assert (p - pr.detach()).abs().max().item() < 1e-6
+    out = torch.zeros(1, device=DEV)
+    ops.sumsq(p, out)
+    assert abs(out.item() - (p.double() ** 2).sum().item()) / out.item() < 1e-5

@@ -1,0 +1,113 @@
+"""Model-level parity of the CUDA UnetGenerator3d against the CPU oracle and the committed goldens.
+
+Tolerances (bf16 operands, fp32 accumulation, fp32 master weights): synthesized-PET max-abs error
+<= 3e-2 (tanh range), mean-abs <= 3e-3; loss abs error <= 2e-3; per-parameter grad-norm relative error <= 5e-2 and
+global grad-norm relative error <= 2e-2.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import unet3d as O
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+OUT_MAX, OUT_MEAN, LOSS_ABS, GN_PARAM, GN_TOTAL = 3e-2, 3e-3, 2e-3, 5e-2, 2e-2
+
+
+def synth_pair(shape, seed):
+    g = torch.Generator().manual_seed(seed)
+    n, d, h, w = shape
+    return torch.rand(n, 1, d, h, w, generator=g), torch.rand(n, 1, d, h, w, generator=g)
+
+
+def build(petsyn, ngf, seed=777):
+    torch.manual_seed(seed)
+    m = petsyn.UnetGenerator3d(1, 1, num_downs=4, ngf=ngf)
+    return m
+
+
+@pytest.mark.parametrize("name", ["unet3d_ngf32_2x32x48x32", "unet3d_ngf64_1x32x32x48"])
+def test_train_step_matches_oracle_and_golden(name, petsyn):
+    gold = np.load(os.path.join(GOLD, name + ".npz"))
+    ngf, shape, seed = int(gold["ngf"]), tuple(int(v) for v in gold["shape"]), int(gold["seed"])
+    model = build(petsyn, ngf, seed)
+    sd_cpu = {k: v.clone() for k, v in model.state_dict().items()}
+    # the seeded init must be the reference's (same RNG order): compare weight checksums with the golden
+    for k, v in sd_cpu.items():
+        if v.dtype.is_floating_point:
+            assert abs(float(v.double().abs().sum()) - float(gold["wsum/" + k])) <= 1e-6 * max(1.0, float(gold["wsum/" + k])), k
+    t1, pet = synth_pair(shape, seed)
+    loss_o, y_o, grads_o, bufs_o = O.train_step(t1, pet, sd_cpu, num_downs=4, ngf=ngf)
+    assert abs(float(loss_o) - float(gold["loss"])) < 1e-5          # oracle is pinned to the reference fixture
+
+    model = model.cuda().train()
+    y = model(t1.cuda())
+    loss = torch.nn.functional.l1_loss(y, pet.cuda())
+    loss.backward()
+    torch.cuda.synchronize()
+    yc = y.detach().cpu()
+    err = (yc - y_o).abs()
+    assert err.max().item() <= OUT_MAX and err.mean().item() <= OUT_MEAN, (err.max().item(), err.mean().item())
+    gerr = (yc.numpy() - gold["output"])
+    assert np.abs(gerr).max() <= OUT_MAX
+    assert abs(loss.item() - float(gold["loss"])) <= LOSS_ABS
+    tot, tot_ref = 0.0, 0.0
+    for k, p in model.named_parameters():
+        gn = p.grad.double().norm().item()
+        ref = float(gold["gradnorm/" + k])
+        tot += gn ** 2
+        tot_ref += ref ** 2
+        assert abs(gn - ref) <= GN_PARAM * ref + 1e-6, (k, gn, ref)
+        # direction, not just norm: cosine with the oracle gradient
+        go = grads_o[k].double().flatten()
+        cos = torch.dot(p.grad.double().cpu().flatten(), go) / (gn * go.norm().item() + 1e-30)
+        assert cos.item() > 0.995, (k, cos.item())
+    assert abs(tot ** 0.5 - tot_ref ** 0.5) <= GN_TOTAL * tot_ref ** 0.5
+    # BatchNorm running statistics follow nn.BatchNorm3d (momentum 0.1, unbiased variance)
+    sd = model.state_dict()
+    for k in gold.files:
+        if k.startswith("buffer/"):
+            ref = torch.from_numpy(gold[k])
+            got = sd[k[len("buffer/"):]].cpu()
+            assert (got - ref).abs().max().item() <= 2e-2 * (ref.abs().max().item() + 1e-3), k
+
+    # eval-mode (inference) forward with running statistics
+    model.eval()
+    with torch.no_grad():
+        ye = model(t1.cuda()).cpu().numpy()
+    assert np.abs(ye - gold["output_eval"]).max() <= 5e-2
+
+
+def test_state_dict_roundtrip_and_errors(petsyn):
+    torch.manual_seed(1)
+    m = petsyn.UnetGenerator3d(1, 1, num_downs=4, ngf=16)
+    assert list(m.state_dict().keys()) == O.state_dict_keys(1, 1, 4, 16)
+    ref_sd = O.init_state_dict(1, 1, 4, 16, seed=5)
+    m.load_state_dict(ref_sd)                       # reference-format checkpoint loads unchanged
+    with pytest.raises(AssertionError):
+        petsyn.UnetGenerator3d(1, 2, num_downs=4)  # unet_model.py:12
+    m = m.cuda()
+    with pytest.raises(ValueError):
+        m(torch.zeros(1, 1, 24, 32, 32, device="cuda"))   # 24 is not divisible by 16
+    with pytest.raises(RuntimeError):
+        m.cpu()(torch.zeros(1, 1, 32, 32, 32))             # no CPU path
+
+
+def test_full_size_cfg1_scalars(petsyn):
+    """BASELINE config 1 (ngf 64, 96x112x96, batch 1): loss / global grad-norm against the reference fixture."""
+    gold = np.load(os.path.join(GOLD, "unet3d_ngf64_1x96x112x96.npz"))
+    model = build(petsyn, 64, 777).cuda().train()
+    t1, pet = synth_pair((1, 96, 112, 96), 777)
+    y = model(t1.cuda())
+    loss = torch.nn.functional.l1_loss(y, pet.cuda())
+    loss.backward()
+    torch.cuda.synchronize()
+    assert abs(loss.item() - float(gold["loss"])) <= LOSS_ABS
+    tot = sum(p.grad.double().norm().item() ** 2 for p in model.parameters()) ** 0.5
+    assert abs(tot - float(gold["grad_norm_total"])) <= GN_TOTAL * float(gold["grad_norm_total"])
+    samp = y.detach().cpu().numpy()[:, :, ::8, ::8, ::8]
+    assert np.abs(samp - gold["output_sample"]).max() <= OUT_MAX
