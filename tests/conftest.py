@@ -9,6 +9,12 @@ if ROOT not in sys.path:
 
 
 def pytest_configure(config):
+    try:   # fp32 references must really be fp32 (cuDNN defaults to TF32 for convolutions)
+        import torch
+        torch.backends.cudnn.allow_tf32 = False
+        torch.backends.cuda.matmul.allow_tf32 = False
+    except Exception:  # pragma: no cover
+        pass
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with `-m gpu`)")
     config.addinivalue_line("markers", "reference: needs the live reference checkout at /root/reference")
 
