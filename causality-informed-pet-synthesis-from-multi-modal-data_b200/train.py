@@ -1,0 +1,158 @@
+"""Train-step orchestration for the generators (the hot loop of ``unet/scripts/train_unet.py:129-168`` restricted to
+the terms that exist offline: zero_grad -> forward -> nn.L1Loss -> backward -> Adam), plus the data-parallel gradient
+exchange that ``DistributedDataParallel`` performs implicitly in the reference (train_unet.py:41,72).
+
+Design (one process per GPU, torch.distributed for plumbing):
+  * all fp32 master parameters live in ONE flat arena, all gradients in another, laid out in the order backward
+    produces them; ``nn.Parameter.data`` / ``.grad`` are views, so ``state_dict``/checkpoints are unchanged;
+  * the arena is cut into ~32 MB buckets at parameter boundaries; as soon as backward has enqueued the last kernel
+    of a bucket, an event is recorded and ``all_reduce(AVG)`` of that bucket is launched on a side stream, so NCCL
+    (NVLink 5 / NVSwitch) overlaps the rest of backward -- the same schedule DDP's reducer runs, without autograd;
+  * Adam is one fused kernel over the whole arena.
+BatchNorm uses per-rank batch statistics exactly like the reference (no SyncBatchNorm); the reference's DDP
+``broadcast_buffers`` re-broadcast of running statistics from rank 0 is reproduced by ``sync_buffers()``.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional
+
+import torch
+import torch.distributed as dist
+
+from . import ops
+
+
+class FlatArena:
+    """Flat fp32 parameter + gradient storage with per-parameter views."""
+
+    def __init__(self, params: List[torch.nn.Parameter], device):
+        self.params = params
+        self.offsets: List[int] = []
+        off = 0
+        for p in params:
+            self.offsets.append(off)
+            off += (p.numel() + 3) // 4 * 4          # keep every view 16-byte aligned
+        self.numel = off
+        self.p = torch.zeros(off, dtype=torch.float32, device=device)
+        self.g = torch.zeros(off, dtype=torch.float32, device=device)
+        self.grad_views: Dict[int, torch.Tensor] = {}
+        for p, o in zip(params, self.offsets):
+            view = self.p[o:o + p.numel()].view_as(p)
+            view.copy_(p.data)
+            p.data = view
+            gv = self.g[o:o + p.numel()].view_as(p)
+            p.grad = gv
+            self.grad_views[id(p)] = gv
+
+
+class GradBucketer:
+    """Bucketed gradient all-reduce over a FlatArena, launched as buckets complete (device-agnostic: NCCL on CUDA
+    with a side stream, gloo on CPU for the host-logic tests)."""
+
+    def __init__(self, arena: FlatArena, bucket_mb: float = 32.0, process_group=None):
+        self.arena = arena
+        self.pg = process_group
+        self.world = dist.get_world_size(process_group) if (dist.is_available() and dist.is_initialized()) else 1
+        self.buckets: List[tuple] = []          # (start, end, id(last param))
+        limit = max(1, int(bucket_mb * (1 << 20) / 4))
+        start = 0
+        last = arena.params[-1]
+        for p, o in zip(arena.params, arena.offsets):
+            end = o + (p.numel() + 3) // 4 * 4
+            if end - start >= limit or p is last:
+                self.buckets.append((start, end, id(p)))
+                start = end
+        self._bucket_of_last = {b[2]: i for i, b in enumerate(self.buckets)}
+        self.cuda = arena.g.is_cuda
+        self.comm_stream = torch.cuda.Stream(device=arena.g.device) if (self.cuda and self.world > 1) else None
+        self._pending: List = []
+        self._avg = self.cuda          # NCCL supports ReduceOp.AVG; gloo does not
+
+    def on_ready(self, p) -> None:
+        """Call right after the kernels producing ``p.grad`` have been enqueued (gradient-production order)."""
+        i = self._bucket_of_last.get(id(p))
+        if i is None or self.world == 1:
+            return
+        start, end, _ = self.buckets[i]
+        view = self.arena.g[start:end]
+        op = dist.ReduceOp.AVG if self._avg else dist.ReduceOp.SUM
+        if self.cuda:
+            ev = torch.cuda.Event()
+            ev.record()                                # compute stream: bucket i is complete after this point
+            self.comm_stream.wait_event(ev)
+            with torch.cuda.stream(self.comm_stream):
+                work = dist.all_reduce(view, op=op, group=self.pg, async_op=True)
+        else:
+            work = dist.all_reduce(view, op=op, group=self.pg, async_op=True)
+        self._pending.append((work, view))
+
+    def wait_all(self) -> None:
+        for work, view in self._pending:
+            work.wait()                                # CUDA: the current stream waits for the collective
+            if not self._avg:
+                view.div_(self.world)
+        self._pending.clear()
+
+
+class Unet3dTrainer:
+    """Fused training step for a petsyn ``UnetGenerator3d``; data-parallel when a process group is initialised."""
+
+    def __init__(self, model, lr: float = 5e-4, betas=(0.9, 0.999), eps: float = 1e-8, bucket_mb: float = 32.0,
+                 process_group=None, example_input: Optional[torch.Tensor] = None):
+        self.model = model
+        self.lr, self.betas, self.eps = lr, betas, eps
+        self.pg = process_group
+        self.world = dist.get_world_size(process_group) if (dist.is_available() and dist.is_initialized()) else 1
+        dev = next(model.parameters()).device
+        self.dev = dev
+        if example_input is None:
+            raise ValueError("example_input (a tensor of the training shape) is required to lay out the arenas")
+        eng = model.engine_for(example_input)
+        self.eng = eng
+        order = eng.grad_order()
+        assert {id(p) for p in order} == {id(p) for p in model.parameters()}
+        self.arena = FlatArena(order, dev)
+        self.m = torch.zeros_like(self.arena.p)
+        self.v = torch.zeros_like(self.arena.p)
+        self.step_count = 0
+        self.loss = torch.zeros(1, dtype=torch.float32, device=dev)
+        self.dy = torch.empty(example_input.shape, dtype=torch.float32, device=dev)
+        eng.mark_weights_dirty()
+        self.bucketer = GradBucketer(self.arena, bucket_mb, process_group)
+        if self.world > 1:
+            self.sync_parameters()
+
+    # ------------------------------------------------------------------------------------------------ collectives
+    def sync_parameters(self) -> None:
+        """DDP construction semantics: every rank starts from rank 0's parameters and buffers."""
+        dist.broadcast(self.arena.p, src=0, group=self.pg)
+        self.sync_buffers()
+        self.eng.mark_weights_dirty()
+
+    def sync_buffers(self) -> None:
+        """DDP ``broadcast_buffers=True``: BatchNorm running statistics follow rank 0 (train_unet.py:72)."""
+        if self.world == 1:
+            return
+        for b in self.model.buffers():
+            if b.dtype.is_floating_point:
+                dist.broadcast(b, src=0, group=self.pg)
+
+    # ------------------------------------------------------------------------------------------------ step
+    def step(self, x: torch.Tensor, target: torch.Tensor, timers=None) -> torch.Tensor:
+        """One optimisation step; returns the (device) loss tensor of this rank's micro-batch."""
+        eng = self.eng
+        y = eng.forward(x, save=True, timers=timers, clone_output=False)
+        self.loss.zero_()
+        ops.l1_loss_fwd_bwd(y, target, self.loss, self.dy)
+        eng.backward(self.dy, out=self.arena.grad_views, on_ready=self.bucketer.on_ready, timers=timers)
+        self.bucketer.wait_all()
+        self.step_count += 1
+        ops.adam_step(self.arena.p, self.arena.g, self.m, self.v, self.lr, self.betas[0], self.betas[1], self.eps,
+                      self.step_count)
+        eng.mark_weights_dirty()
+        return self.loss
+
+    def grad_norm(self) -> float:
+        out = torch.zeros(1, dtype=torch.float32, device=self.dev)
+        ops.sumsq(self.arena.g, out)
+        return float(out.item()) ** 0.5

@@ -249,7 +249,7 @@ class _Engine:
         ops.bn_finalize(nm.sums, bn.weight, bn.bias, bn.running_mean, bn.running_var, nm.scale, nm.shift, nm.mean,
                         nm.rstd, rows, c, bn.eps, momentum, training)
 
-    def forward(self, x: torch.Tensor, save: bool) -> torch.Tensor:
+    def forward(self, x: torch.Tensor, save: bool, timers=None, clone_output: bool = True) -> torch.Tensor:
         L = self.L
         training = self.gen.training
         self._repack(need_dgrad=save)
@@ -265,7 +265,8 @@ class _Engine:
             ops.norm_act_fwd(self.z[i - 1], prev.scale if prev else None, prev.shift if prev else None,
                              self.a[i], c, 0, ops.ACT_LRELU, self.cat[i], 2 * c, c, ops.ACT_RELU, LRELU_SLOPE,
                              self.rows[i], c)
-            self.down[i].fprop(self.a[i], self.z[i])
+            with _timed(timers, f"down{i}.fprop"):
+                self.down[i].fprop(self.a[i], self.z[i])
         # ---- innermost: ReLU(z) ----
         ci = self.inner[L - 1]
         ops.norm_act_fwd(self.z[L - 1], None, None, self.r, ci, 0, ops.ACT_RELU, None, 0, 0, ops.ACT_NONE, LRELU_SLOPE,
@@ -273,7 +274,8 @@ class _Engine:
         # ---- up path ----
         for i in range(L - 1, 0, -1):
             src = self.r if i == L - 1 else self.cat[i + 1]
-            self.up[i].fprop(src, self.zu[i])
+            with _timed(timers, f"up{i}.fprop"):
+                self.up[i].fprop(src, self.zu[i])
             nm = self.unorm[i]
             c = self.outer[i]
             self._bn_forward(nm, self.zu[i], self.rows[i], c, training)
@@ -284,7 +286,7 @@ class _Engine:
         cat1 = self.cat[1].view(n, d1, h1, w1, 2 * self.outer[1])
         y = self.y if save else torch.empty_like(self.y)
         ops.head_fwd(cat1, lv[0]._refs["upconv"].weight.detach(), self.proj, y)
-        return y.clone() if save else y
+        return y.clone() if (save and clone_output) else y
 
     # ------------------------------------------------------------------------------------------------ backward
     def _grad_buffers(self) -> List[torch.Tensor]:
@@ -292,18 +294,45 @@ class _Engine:
             self._grads = [torch.empty_like(p, dtype=torch.float32) for p in self.param_list()]
         return self._grads
 
-    def backward(self, dy: torch.Tensor) -> List[torch.Tensor]:
+    def grad_order(self) -> List[torch.Tensor]:
+        """Parameters in the order their gradients are produced by ``backward`` (used to lay out the flat gradient
+        arena so that data-parallel buckets complete front to back)."""
+        L, lv = self.L, self.lv
+        order = [lv[0]._refs["upconv"].weight]
+        for i in range(1, L):
+            order += [self.unorm[i].bn.weight, self.unorm[i].bn.bias, lv[i]._refs["upconv"].weight]
+        for i in range(L - 1, 0, -1):
+            order.append(lv[i]._refs["downconv"].weight)
+            if self.dnorm[i - 1] is not None:
+                order += [self.dnorm[i - 1].bn.weight, self.dnorm[i - 1].bn.bias]
+        order.append(lv[0]._refs["downconv"].weight)
+        return order
+
+    def mark_weights_dirty(self) -> None:
+        """Call after updating the fp32 master weights outside autograd's version tracking (fused optimiser)."""
+        self._packed_versions.clear()
+
+    def backward(self, dy: torch.Tensor, out: Optional[Dict[int, torch.Tensor]] = None, on_ready=None,
+                 timers=None) -> List[torch.Tensor]:
+        """Backward of ``forward(save=True)``.  Gradients are written (not accumulated) into ``out[id(param)]`` when
+        given, else into engine-owned buffers whose clones are returned in ``param_list()`` order.  ``on_ready(param)``
+        is called right after the kernels producing that parameter's gradient have been enqueued."""
         L = self.L
         lv = self.lv
-        grads = self._grad_buffers()
-        # map parameter -> grad slot
-        slot: Dict[int, torch.Tensor] = {id(p): g for p, g in zip(self.param_list(), grads)}
+        if out is None:
+            grads = self._grad_buffers()
+            slot: Dict[int, torch.Tensor] = {id(p): g for p, g in zip(self.param_list(), grads)}
+        else:
+            grads = None
+            slot = out
+        ready = on_ready if on_ready is not None else (lambda p: None)
         gw = lambda conv: slot[id(conv.weight)]
         n = self.shape[0]
         d1, h1, w1 = self.dims[1]
         cat1 = self.cat[1].view(n, d1, h1, w1, 2 * self.outer[1])
         ops.head_bwd(cat1, lv[0]._refs["upconv"].weight.detach(), self.y, dy, self.dproj, self.dcat[1],
                      gw(lv[0]._refs["upconv"]))
+        ready(lv[0]._refs["upconv"].weight)
         # ---- up path, outer -> inner ----
         for i in range(1, L):
             nm = self.unorm[i]
@@ -311,18 +340,26 @@ class _Engine:
             ops.norm_act_bwd(self.zu[i], nm.scale, nm.shift, nm.mean, nm.rstd, nm.bn.weight, self.dcat[i], 2 * c, 0,
                              ops.ACT_RELU, None, 0, 0, ops.ACT_NONE, LRELU_SLOPE, nm.bsums, self.dzu[i],
                              slot[id(nm.bn.weight)], slot[id(nm.bn.bias)], self.rows[i], c)
+            ready(nm.bn.weight)
+            ready(nm.bn.bias)
             src = self.r if i == L - 1 else self.cat[i + 1]
             dsrc = self.dr if i == L - 1 else self.dcat[i + 1]
-            self.up[i].wgrad(src, self.dzu[i], gw(lv[i]._refs["upconv"]))
-            self.up[i].dgrad(self.dzu[i], dsrc)
+            with _timed(timers, f"up{i}.wgrad"):
+                self.up[i].wgrad(src, self.dzu[i], gw(lv[i]._refs["upconv"]))
+            ready(lv[i]._refs["upconv"].weight)
+            with _timed(timers, f"up{i}.dgrad"):
+                self.up[i].dgrad(self.dzu[i], dsrc)
         # ---- innermost: through ReLU(z) ----
         ci = self.inner[L - 1]
         ops.norm_act_bwd(self.z[L - 1], None, None, None, None, None, self.dr, ci, 0, ops.ACT_RELU, None, 0, 0,
                          ops.ACT_NONE, LRELU_SLOPE, None, self.dz[L - 1], None, None, self.rows[L], ci)
         # ---- down path, inner -> outer ----
         for i in range(L - 1, 0, -1):
-            self.down[i].wgrad(self.a[i], self.dz[i], gw(lv[i]._refs["downconv"]))
-            self.down[i].dgrad(self.dz[i], self.da[i])
+            with _timed(timers, f"down{i}.wgrad"):
+                self.down[i].wgrad(self.a[i], self.dz[i], gw(lv[i]._refs["downconv"]))
+            ready(lv[i]._refs["downconv"].weight)
+            with _timed(timers, f"down{i}.dgrad"):
+                self.down[i].dgrad(self.dz[i], self.da[i])
             prev = self.dnorm[i - 1]
             c = self.outer[i]
             ops.norm_act_bwd(self.z[i - 1], prev.scale if prev else None, prev.shift if prev else None,
@@ -331,5 +368,27 @@ class _Engine:
                              ops.ACT_RELU, LRELU_SLOPE, prev.bsums if prev else None, self.dz[i - 1],
                              slot[id(prev.bn.weight)] if prev else None, slot[id(prev.bn.bias)] if prev else None,
                              self.rows[i], c)
+            if prev is not None:
+                ready(prev.bn.weight)
+                ready(prev.bn.bias)
         ops.stem_wgrad(self._saved_x, self.dz[0], gw(lv[0]._refs["downconv"]))
-        return [g.clone() for g in grads]
+        ready(lv[0]._refs["downconv"].weight)
+        return [g.clone() for g in grads] if grads is not None else []
+
+
+class _timed:
+    """Optional CUDA-event bracket around one launch (bench.py's roofline leg); a no-op when ``timers`` is None."""
+
+    def __init__(self, timers, name):
+        self.timers, self.name = timers, name
+
+    def __enter__(self):
+        if self.timers is not None:
+            self.ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            self.ev[0].record()
+
+    def __exit__(self, *exc):
+        if self.timers is not None:
+            self.ev[1].record()
+            self.timers.setdefault(self.name, []).append(self.ev)
+        return False

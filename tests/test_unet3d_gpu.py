@@ -62,10 +62,12 @@ def test_train_step_matches_oracle_and_golden(name, petsyn):
         tot += gn ** 2
         tot_ref += ref ** 2
         assert abs(gn - ref) <= GN_PARAM * ref + 1e-6, (k, gn, ref)
-        # direction, not just norm: cosine with the oracle gradient
+        # direction too.  nn.L1Loss' gradient is sign(y - t)/N: a bf16-sized output error flips the sign on the
+        # ~1-2 % of voxels with |y - t| < 1e-2, so the direction bound under L1 is loose; the smooth-loss test below
+        # (test_gradient_direction_smooth_loss) is the tight one.
         go = grads_o[k].double().flatten()
         cos = torch.dot(p.grad.double().cpu().flatten(), go) / (gn * go.norm().item() + 1e-30)
-        assert cos.item() > 0.995, (k, cos.item())
+        assert cos.item() > 0.98, (k, cos.item())
     assert abs(tot ** 0.5 - tot_ref ** 0.5) <= GN_TOTAL * tot_ref ** 0.5
     # BatchNorm running statistics follow nn.BatchNorm3d (momentum 0.1, unbiased variance)
     sd = model.state_dict()
@@ -80,6 +82,31 @@ def test_train_step_matches_oracle_and_golden(name, petsyn):
     with torch.no_grad():
         ye = model(t1.cuda()).cpu().numpy()
     assert np.abs(ye - gold["output_eval"]).max() <= 5e-2
+
+
+def test_gradient_direction_smooth_loss(petsyn):
+    """Per-parameter gradient direction against the oracle under a smooth loss (0.5*mean((y-t)^2)), where bf16 output
+    noise cannot flip gradient signs: cosine >= 0.995 for every tensor, >= 0.999 globally."""
+    ngf, shape, seed = 32, (2, 32, 32, 48), 11
+    model = build(petsyn, ngf, seed)
+    sd_cpu = {k: v.clone() for k, v in model.state_dict().items()}
+    t1, pet = synth_pair(shape, seed)
+    params = {k: v.clone().requires_grad_(True) for k, v in sd_cpu.items()
+              if v.dtype.is_floating_point and "running" not in k}
+    full = dict(sd_cpu); full.update(params)
+    y_o = O.forward(t1, full, num_downs=4, ngf=ngf, training=True)
+    (0.5 * ((y_o - pet) ** 2).mean()).backward()
+    model = model.cuda().train()
+    y = model(t1.cuda())
+    (0.5 * ((y - pet.cuda()) ** 2).mean()).backward()
+    dot = na = nb = 0.0
+    for k, p in model.named_parameters():
+        a, b = p.grad.double().cpu().flatten(), params[k].grad.double().flatten()
+        cos = (torch.dot(a, b) / (a.norm() * b.norm() + 1e-30)).item()
+        assert cos > 0.995, (k, cos)
+        assert abs(a.norm().item() - b.norm().item()) <= GN_PARAM * b.norm().item() + 1e-9, k
+        dot += torch.dot(a, b).item(); na += (a ** 2).sum().item(); nb += (b ** 2).sum().item()
+    assert dot / (na * nb) ** 0.5 > 0.999
 
 
 def test_state_dict_roundtrip_and_errors(petsyn):
