@@ -185,7 +185,7 @@ def run_petsyn(args, ngf, shape, batch):
     barrier()
 
     # count our kernel launches in one step (every C-ABI call enqueues a known number of kernels)
-    launches = count_launches(trainer)
+    launches = count_launches(trainer, resident[0])
 
     # ---- timed region 1: inputs resident ----
     sampler = ClockSampler(local_rank)
@@ -281,28 +281,15 @@ def run_petsyn(args, ngf, shape, batch):
         dist.destroy_process_group()
 
 
-def count_launches(trainer) -> int:
-    """Kernels launched by one trainer.step(): counted from the schedule (each C-ABI call's kernel count is fixed)."""
-    L = trainer.eng.L
-    n = 1                                   # stem fwd
-    for i in range(1, L):
-        prev = trainer.eng.dnorm[i - 1] is not None
-        n += (2 if prev else 0) + 1 + 1     # [bn stats + finalize] + norm_act + down conv
-    n += 1                                  # innermost relu
-    n += (L - 1) * (1 + 2 + 1)              # up conv + bn stats/finalize + norm_act
-    n += 2                                  # head proj + gather
-    n += 1                                  # L1 loss
-    n += 2                                  # head bwd (scatter + bwd)
-    n += (L - 1) * (2 + 2 + 1)              # upnorm bwd (reduce+apply) + wgrad (kernel + unpack) + dgrad
-    n += 1                                  # innermost relu bwd
-    for i in range(L - 1, 0, -1):
-        prev = trainer.eng.dnorm[i - 1] is not None
-        n += 2 + 1 + (2 if prev else 1)     # wgrad (kernel + unpack) + dgrad + norm bwd
-    n += 1                                  # stem wgrad
-    n += 1                                  # adam
-    n += 2 * (L - 1)                        # weight repack (pack kernel x2 per conv pair: fprop+dgrad images) -- per conv: 2
-    n += 2 * (L - 1)
-    return n
+def count_launches(trainer, batch) -> int:
+    """Kernels of OUR library launched by one trainer.step() (petsyn_launch_count() delta)."""
+    import torch
+    from petsyn_b200 import ops
+    torch.cuda.synchronize()
+    n0 = ops.launch_count()
+    trainer.step(*batch)
+    torch.cuda.synchronize()
+    return ops.launch_count() - n0
 
 
 def main():

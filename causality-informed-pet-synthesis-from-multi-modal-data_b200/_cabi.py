@@ -42,6 +42,7 @@ class ConvDesc(C.Structure):
         ("dx_cstride", C.c_int32), ("dx_coff", C.c_int32),
         ("epi_act", C.c_int32),
         ("epi_slope", C.c_float),
+        ("y_fp32", C.c_int32),
     ]
 
 
@@ -51,6 +52,7 @@ _vp, _i32, _i64, _f32, _sz = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_si
 SIGNATURES = {
     "petsyn_version": (_i32, []),
     "petsyn_last_error": (C.c_char_p, []),
+    "petsyn_launch_count": (C.c_uint64, []),
     "petsyn_conv_plan_create": (_i32, [C.POINTER(ConvDesc), C.POINTER(_vp)]),
     "petsyn_conv_plan_destroy": (None, [_vp]),
     "petsyn_conv_out_dims": (_i32, [_vp, C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i32)]),
@@ -58,14 +60,15 @@ SIGNATURES = {
     "petsyn_conv_packed_fprop_bytes": (_sz, [_vp]),
     "petsyn_conv_packed_dgrad_bytes": (_sz, [_vp]),
     "petsyn_conv_wgrad_scratch_bytes": (_sz, [_vp]),
+    "petsyn_conv_workspace_bytes": (_sz, [_vp]),
+    "petsyn_conv_set_workspace": (_i32, [_vp, _vp, _sz]),
     "petsyn_conv_pack_weights": (_i32, [_vp, _vp, _vp, _vp, _vp]),
     "petsyn_conv_fprop": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp]),
     "petsyn_conv_dgrad": (_i32, [_vp, _vp, _vp, _vp, _vp]),
     "petsyn_conv_wgrad": (_i32, [_vp, _vp, _vp, _vp, _vp, _i32, _vp]),
-    "petsyn_stem_conv_k4s2_fwd": (_i32, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
-    "petsyn_stem_conv_k4s2_wgrad": (_i32, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
-    "petsyn_head_upconv_tanh_fwd": (_i32, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
-    "petsyn_head_upconv_tanh_bwd": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
+    "petsyn_stem_im2col_k4s2": (_i32, [_vp, _vp, _i32, _i32, _i32, _i32, _vp]),
+    "petsyn_head_gather_tanh": (_i32, [_vp, _vp, _i32, _i32, _i32, _i32, _vp]),
+    "petsyn_head_scatter_bwd": (_i32, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp]),
     "petsyn_bn_stats": (_i32, [_vp, _vp, _i64, _i32, _vp]),
     "petsyn_bn_finalize": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _f32, _f32, _i32, _vp]),
     "petsyn_norm_act_fwd": (_i32, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp, _i32, _i32, _i32, _f32, _i64, _i32, _vp]),

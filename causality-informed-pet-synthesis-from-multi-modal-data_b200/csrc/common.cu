@@ -1,9 +1,15 @@
 #include "common.h"
 
+#include <atomic>
 #include <cstring>
 #include <mutex>
 
 namespace petsyn {
+
+uint64_t launch_count();
+static std::atomic<uint64_t> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+uint64_t launch_count() { return g_launches.load(std::memory_order_relaxed); }
 
 char* last_error_buf() {
   static thread_local char buf[512] = {0};
@@ -75,4 +81,5 @@ int32_t encode_tmap(CUtensorMap* out, CUtensorMapDataType dtype, int rank, const
 extern "C" {
 int32_t petsyn_version(void) { return PETSYN_VERSION; }
 const char* petsyn_last_error(void) { return petsyn::last_error_buf(); }
+uint64_t petsyn_launch_count(void) { return petsyn::launch_count(); }
 }

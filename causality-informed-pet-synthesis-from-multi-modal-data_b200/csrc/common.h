@@ -27,7 +27,10 @@ int32_t fail(int32_t code, const char* fmt, ...);
     if (!(cond)) return ::petsyn::fail(PETSYN_EINVAL, __VA_ARGS__); \
   } while (0)
 
+void count_launch();
+
 inline int32_t check_launch(const char* what) {
+  count_launch();
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(PETSYN_ECUDA, "launch of %s failed: %s", what, cudaGetErrorString(e));
   return PETSYN_OK;

@@ -137,47 +137,127 @@ struct InvEntryDev {   // for one original tap k: where its gradient contributio
   int32_t tap[8];
 };
 
-__global__ void pack_weights_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out,
-                                    const TapSrcDev* __restrict__ tbl, int nsubs, int max_taps, int R, int Kc,
-                                    int kc_pad, int k3, int swap) {
-  const int64_t ldb = (int64_t)max_taps * kc_pad;
-  const int64_t total = (int64_t)nsubs * R * ldb;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int c = (int)(i % kc_pad);
-    int64_t q = i / kc_pad;
-    const int t = (int)(q % max_taps);
-    q /= max_taps;
-    const int r = (int)(q % R);
-    const int sub = (int)(q / R);
-    float acc = 0.f;
-    if (c < Kc) {
-      const TapSrcDev e = tbl[sub * max_taps + t];
-      for (int j = 0; j < e.nsrc; ++j) {
-        const int64_t idx = swap ? ((int64_t)c * R + r) * k3 + e.src[j] : ((int64_t)r * Kc + c) * k3 + e.src[j];
-        acc += w[idx];
+// Weight packing / gradient unpacking move W between PyTorch layout W[a][b][k] (k fastest; (a,b) = (Cout,Cin) for
+// Conv3d, (Cin,Cout) for ConvTranspose3d) and the GEMM operand layout B[(sub*rows + row)][t*kc_pad + col].
+// Both go tile-wise through shared memory (16 x 16 (a,b) pairs x all k^3 taps) so that global reads AND writes are
+// contiguous runs, and the tap count is a template parameter so that index arithmetic is constant-folded.
+constexpr int kPT = 16;
+
+struct PackImage {
+  __nv_bfloat16* out;       // nullptr: skip
+  const TapSrcDev* tbl;     // [nsubs * max_taps]
+  int32_t nsubs, max_taps;
+  int32_t rows, kc_pad;     // rows per sub-problem, padded columns per tap
+  int32_t transposed;       // 0: (row, col) = (a, b);  1: (row, col) = (b, a)
+};
+
+template <int K3>
+__global__ void __launch_bounds__(256) pack_weights_kernel(const float* __restrict__ w, int A, int B, PackImage im0,
+                                                           PackImage im1) {
+  constexpr int K3P = K3 | 1;                 // odd pitch along b
+  constexpr int ROWP = kPT * K3P + 1;         // odd pitch along a (kPT * odd is even)
+  extern __shared__ float tile[];             // [kPT][ROWP]
+  __shared__ TapSrcDev s_tbl[2][kMaxTaps];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int a0 = blockIdx.x * kPT, b0 = blockIdx.y * kPT;
+  for (int i = tid; i < im0.nsubs * im0.max_taps; i += 256)
+    if (im0.out) s_tbl[0][i] = im0.tbl[i];
+  for (int i = tid; i < im1.nsubs * im1.max_taps; i += 256)
+    if (im1.out) s_tbl[1][i] = im1.tbl[i];
+  for (int al = warp; al < kPT; al += 8) {
+    const int a = a0 + al;
+    const float* src = w + ((int64_t)a * B + b0) * K3;
+    for (int idx = lane; idx < kPT * K3; idx += 32) {
+      const int bl = idx / K3, k = idx - bl * K3;
+      tile[al * ROWP + bl * K3P + k] = (a < A && b0 + bl < B) ? __ldg(src + idx) : 0.f;
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int which = 0; which < 2; ++which) {
+    const PackImage& im = which ? im1 : im0;
+    if (im.out == nullptr) continue;
+    const int i = tid / kPT, j = tid % kPT;   // j is the fast (column) index of the image
+    const int row = im.transposed ? b0 + i : a0 + i;
+    const int col = im.transposed ? a0 + j : b0 + j;
+    if (row >= im.rows || col >= im.kc_pad) continue;
+    const float* mine = im.transposed ? tile + j * ROWP + i * K3P : tile + i * ROWP + j * K3P;
+    const int64_t ldb = (int64_t)im.max_taps * im.kc_pad;
+    for (int sub = 0; sub < im.nsubs; ++sub) {
+      __nv_bfloat16* dst = im.out + ((int64_t)sub * im.rows + row) * ldb + col;
+      for (int t = 0; t < im.max_taps; ++t) {
+        const TapSrcDev& e = s_tbl[which][sub * im.max_taps + t];
+        float acc = 0.f;
+        for (int q = 0; q < e.nsrc; ++q) acc += mine[e.src[q]];
+        dst[(int64_t)t * im.kc_pad] = __float2bfloat16(acc);
       }
     }
-    out[i] = __float2bfloat16(acc);
   }
 }
 
-// scratch [nsubs*R, max_taps*kc_pad] fp32 -> dw in PyTorch layout
-__global__ void unpack_wgrad_kernel(const float* __restrict__ scratch, float* __restrict__ dw,
-                                    const InvEntryDev* __restrict__ inv, int max_taps, int R, int Kc, int kc_pad,
-                                    int k3, int swap, int accumulate) {
+// scratch [nsubs*rows, max_taps*kc_pad] fp32 -> dw in PyTorch layout (sums the slots every original tap was merged into)
+template <int K3>
+__global__ void __launch_bounds__(256) unpack_wgrad_kernel(const float* __restrict__ scratch, float* __restrict__ dw,
+                                                           const InvEntryDev* __restrict__ inv, int A, int B, int nsubs,
+                                                           int max_taps, int rows, int kc_pad, int transposed,
+                                                           int accumulate) {
+  constexpr int kSlotPitch = kPT * (kPT + 1) + 1;
+  extern __shared__ float tile[];             // [nsubs*max_taps][kSlotPitch], element (a_off, b_off) at a_off*17 + b_off
+  __shared__ InvEntryDev s_inv[K3];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int a0 = blockIdx.x * kPT, b0 = blockIdx.y * kPT;
+  for (int i = tid; i < K3; i += 256) s_inv[i] = inv[i];
   const int64_t ldb = (int64_t)max_taps * kc_pad;
-  const int64_t total = (int64_t)R * Kc * k3;
+  {
+    const int i = tid / kPT, j = tid % kPT;
+    const int row = transposed ? b0 + i : a0 + i, col = transposed ? a0 + j : b0 + j;
+    const int a_off = transposed ? j : i, b_off = transposed ? i : j;
+    const bool ok = (a0 + a_off) < A && (b0 + b_off) < B;
+    const int nslots = nsubs * max_taps;
+    for (int s = 0; s < nslots; ++s) {
+      const int sub = s / max_taps, t = s - sub * max_taps;
+      tile[s * kSlotPitch + a_off * (kPT + 1) + b_off] =
+          ok ? __ldg(scratch + ((int64_t)sub * rows + row) * ldb + (int64_t)t * kc_pad + col) : 0.f;
+    }
+  }
+  __syncthreads();
+  for (int al = warp; al < kPT; al += 8) {
+    const int a = a0 + al;
+    if (a >= A) continue;
+    float* dst = dw + ((int64_t)a * B + b0) * K3;
+    for (int idx = lane; idx < kPT * K3; idx += 32) {
+      const int bl = idx / K3, k = idx - bl * K3;
+      if (b0 + bl >= B) continue;
+      const InvEntryDev& e = s_inv[k];
+      float acc = 0.f;
+      for (int q = 0; q < e.n; ++q) acc += tile[(e.sub[q] * max_taps + e.tap[q]) * kSlotPitch + al * (kPT + 1) + bl];
+      if (accumulate) dst[idx] += acc; else dst[idx] = acc;
+    }
+  }
+}
+
+// split-K finish: fp32 [rows, C] (contiguous) -> act(x + bias) as bf16 into a channel slice
+__global__ void __launch_bounds__(256) splitk_finish_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst,
+                                                            int64_t rows, int C, int cstride, int coff,
+                                                            const float* __restrict__ bias, int act, float slope) {
+  const int cpt = C / 8;
+  const int64_t total = rows * cpt;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    // iterate with c fastest so that scratch reads are coalesced
-    const int c = (int)(i % Kc);
-    int64_t q = i / Kc;
-    const int k = (int)(q % k3);
-    const int r = (int)(q / k3);
-    const InvEntryDev e = inv[k];
-    float acc = 0.f;
-    for (int j = 0; j < e.n; ++j) acc += scratch[((int64_t)e.sub[j] * R + r) * ldb + (int64_t)e.tap[j] * kc_pad + c];
-    const int64_t idx = swap ? ((int64_t)c * R + r) * k3 + k : ((int64_t)r * Kc + c) * k3 + k;
-    if (accumulate) dw[idx] += acc; else dw[idx] = acc;
+    const int64_t r = i / cpt;
+    const int c = (int)(i - r * cpt) * 8;
+    const float4 v0 = *reinterpret_cast<const float4*>(src + r * C + c), v1 = *reinterpret_cast<const float4*>(src + r * C + c + 4);
+    float f[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      if (bias) f[q] += __ldg(bias + c + q);
+      f[q] = apply_act(f[q], act, slope);
+    }
+    uint4 o;
+    __nv_bfloat162 b0 = __floats2bfloat162_rn(f[0], f[1]), b1 = __floats2bfloat162_rn(f[2], f[3]);
+    __nv_bfloat162 b2 = __floats2bfloat162_rn(f[4], f[5]), b3 = __floats2bfloat162_rn(f[6], f[7]);
+    o.x = *reinterpret_cast<uint32_t*>(&b0); o.y = *reinterpret_cast<uint32_t*>(&b1);
+    o.z = *reinterpret_cast<uint32_t*>(&b2); o.w = *reinterpret_cast<uint32_t*>(&b3);
+    *reinterpret_cast<uint4*>(dst + r * cstride + coff + c) = o;
   }
 }
 
@@ -190,11 +270,16 @@ struct GemmSide {           // one gather-form GEMM (fprop or dgrad)
   int out_d = 0, out_h = 0, out_w = 0;   // grid of ONE output view (phase grid if out_phased)
   int box_w = 0, box_h = 0, box_d = 0;
   int block_n = 128;
+  bool out_fp32 = false;
+  int ksplit = 1;             // >1: fp32 split-K through `workspace`, finished by splitk_finish_kernel
+  void* workspace = nullptr;
+  size_t workspace_bytes = 0;
+  int64_t out_rows_full = 0;  // voxels of the full (un-phased) output tensor
   IgemmTap* d_taps = nullptr;
   TapSrcDev* d_src = nullptr;
   std::vector<IgemmSub> subs;
   // cached TMA descriptors, keyed by the base pointers they were built for
-  const void* key_a = nullptr; const void* key_b = nullptr; const void* key_c = nullptr;
+  const void* key_a = nullptr; const void* key_b = nullptr; const void* key_c = nullptr; const void* key_w = nullptr;
   IgemmParams params;
 };
 
@@ -249,13 +334,23 @@ static int32_t upload(const void* src, size_t bytes, void** dst) {
 }
 
 static int32_t finish_side(GemmSide& g, int N) {
-  (void)N;
   g.kch = 64;
   g.kc_pad = (g.Kc + g.kch - 1) / g.kch * g.kch;
   if (g.R >= 128) g.block_n = 128;
   else g.block_n = (g.R + 15) / 16 * 16;
   if (g.block_n > 64 && g.block_n < 128) g.block_n = 128;
   choose_box(g.out_w, g.out_h, g.out_d, 128, false, &g.box_w, &g.box_h, &g.box_d);
+  {
+    // split-K when the output tiles alone cannot fill the machine (deep, small-M layers whose cost is streaming weights)
+    const int64_t tiles = (int64_t)((g.out_w + g.box_w - 1) / g.box_w) * ((g.out_h + g.box_h - 1) / g.box_h) *
+                          ((g.out_d + g.box_d - 1) / g.box_d) * N * ((g.R + g.block_n - 1) / g.block_n) *
+                          (int64_t)g.prog.subs.size();
+    int min_steps = 1 << 30;
+    for (auto& sp : g.prog.subs) min_steps = std::min<int>(min_steps, (int)sp.size() * (g.kc_pad / g.kch));
+    int ks = (int)(296 / std::max<int64_t>(tiles, 1));
+    ks = std::min(ks, std::max(1, min_steps / 8));
+    g.ksplit = (ks >= 2 && !g.out_fp32) ? ks : 1;
+  }
   std::vector<IgemmTap> taps;
   std::vector<TapSrcDev> srcs(g.prog.subs.size() * g.prog.max_taps);
   memset(srcs.data(), 0, srcs.size() * sizeof(TapSrcDev));
@@ -315,7 +410,25 @@ static int32_t launch_igemm(const GemmSide& g, int batch, cudaStream_t st) {
   dim3 grid;
   grid.x = (unsigned)(g.params.tiles_w * g.params.tiles_h * g.params.tiles_d * batch);
   grid.y = (unsigned)((g.R + g.block_n - 1) / g.block_n);
-  grid.z = (unsigned)g.subs.size();
+  grid.z = (unsigned)(g.subs.size() * g.ksplit);
+  if (g.ksplit > 1) {
+    switch (g.block_n) {
+      case 16: return launch_igemm_bn<16, OUT_F32_REDUCE>(g, grid, st);
+      case 32: return launch_igemm_bn<32, OUT_F32_REDUCE>(g, grid, st);
+      case 64: return launch_igemm_bn<64, OUT_F32_REDUCE>(g, grid, st);
+      case 128: return launch_igemm_bn<128, OUT_F32_REDUCE>(g, grid, st);
+      default: return fail(PETSYN_EINVAL, "unsupported BLOCK_N %d for split-K", g.block_n);
+    }
+  }
+  if (g.out_fp32) {
+    switch (g.block_n) {
+      case 16: return launch_igemm_bn<16, OUT_F32>(g, grid, st);
+      case 32: return launch_igemm_bn<32, OUT_F32>(g, grid, st);
+      case 64: return launch_igemm_bn<64, OUT_F32>(g, grid, st);
+      case 128: return launch_igemm_bn<128, OUT_F32>(g, grid, st);
+      default: return fail(PETSYN_EINVAL, "unsupported BLOCK_N %d for fp32 output", g.block_n);
+    }
+  }
   switch (g.block_n) {
     case 16: return launch_igemm_bn<16, OUT_BF16>(g, grid, st);
     case 32: return launch_igemm_bn<32, OUT_BF16>(g, grid, st);
@@ -326,11 +439,32 @@ static int32_t launch_igemm(const GemmSide& g, int batch, cudaStream_t st) {
   }
 }
 
+// run one gather-form GEMM: (split-K: zero the fp32 workspace, reduce into it, convert) or a direct launch
+static int32_t run_side(GemmSide& g, const ViewSpec& vc, void* c, const float* bias, int act, float slope, int batch,
+                        cudaStream_t st) {
+  if (g.ksplit > 1) {
+    const size_t bytes = (size_t)g.out_rows_full * g.R * sizeof(float);
+    if (g.workspace == nullptr || g.workspace_bytes < bytes)
+      return fail(PETSYN_ENOMEM, "split-K needs a %zu-byte workspace (petsyn_conv_set_workspace)", bytes);
+    PETSYN_CHECK_CUDA(cudaMemsetAsync(g.workspace, 0, bytes, st));
+    int32_t rc = launch_igemm(g, batch, st);
+    if (rc) return rc;
+    const int64_t total = g.out_rows_full * (g.R / 8);
+    const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>((total + 255) / 256, 148 * 8));
+    splitk_finish_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const float*>(g.workspace),
+                                                 reinterpret_cast<__nv_bfloat16*>(c), g.out_rows_full, g.R, vc.cstride,
+                                                 vc.coff, bias, act, slope);
+    return check_launch("splitk_finish_kernel");
+  }
+  return launch_igemm(g, batch, st);
+}
+
 // (re)build the TMA descriptors of a gather-form GEMM for the given base pointers
 static int32_t bind_side(GemmSide& g, const ViewSpec& va, const ViewSpec& vc, const void* a, const void* b,
                          const void* c, const float* bias, int act, float slope) {
-  if (g.key_a == a && g.key_b == b && g.key_c == c) {
-    g.params.bias = bias;
+  const bool split = g.ksplit > 1;
+  if (g.key_a == a && g.key_b == b && g.key_c == c && g.key_w == g.workspace) {
+    g.params.bias = split ? nullptr : bias;
     return PETSYN_OK;
   }
   IgemmParams& p = g.params;
@@ -342,10 +476,17 @@ static int32_t bind_side(GemmSide& g, const ViewSpec& va, const ViewSpec& vc, co
                           g.box_h, g.box_d, 128);
     if (rc) return rc;
   }
-  const int chunk_c = (g.block_n * 2) % 128 == 0 ? 64 : g.block_n;
-  const int c_swz = (g.block_n * 2) % 128 == 0 ? 128 : 0;
+  const bool c_f32 = g.out_fp32 || split;
+  const int c_esz = c_f32 ? 4 : 2;
+  const bool c_swizzled = (g.block_n * c_esz) % 128 == 0;
+  ViewSpec vws = vc;               // split-K accumulates into a dense fp32 image of the output tensor
+  vws.cstride = g.R; vws.coff = 0;
+  if (split && g.workspace == nullptr) return fail(PETSYN_ENOMEM, "split-K workspace not set (petsyn_conv_set_workspace)");
+  const int chunk_c = c_swizzled ? 128 / c_esz : g.block_n;
+  const int c_swz = c_swizzled ? 128 : 0;
   for (int i = 0; i < n_c; ++i) {
-    int32_t rc = view_map(&p.c_maps[i], c, vc, g.prog.out_phased, i, 2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, chunk_c,
+    int32_t rc = view_map(&p.c_maps[i], split ? g.workspace : c, split ? vws : vc, g.prog.out_phased, i, c_esz,
+                          c_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, chunk_c,
                           g.box_w, g.box_h, g.box_d, c_swz);
     if (rc) return rc;
   }
@@ -358,7 +499,8 @@ static int32_t bind_side(GemmSide& g, const ViewSpec& va, const ViewSpec& vc, co
   }
   for (size_t i = 0; i < g.subs.size(); ++i) p.subs[i] = g.subs[i];
   p.taps = g.d_taps;
-  p.bias = bias;
+  p.bias = split ? nullptr : bias;
+  p.ksplit = g.ksplit;
   p.tiles_w = (g.out_w + g.box_w - 1) / g.box_w;
   p.tiles_h = (g.out_h + g.box_h - 1) / g.box_h;
   p.tiles_d = (g.out_d + g.box_d - 1) / g.box_d;
@@ -368,9 +510,9 @@ static int32_t bind_side(GemmSide& g, const ViewSpec& va, const ViewSpec& vc, co
   p.kc_chunks = g.kc_pad / g.kch;
   p.kc_pad = g.kc_pad;
   p.rows = g.R;
-  p.epi_act = act;
+  p.epi_act = split ? PETSYN_ACT_NONE : act;
   p.epi_slope = slope;
-  g.key_a = a; g.key_b = b; g.key_c = c;
+  g.key_a = a; g.key_b = b; g.key_c = c; g.key_w = g.workspace;
   return PETSYN_OK;
 }
 
@@ -378,14 +520,44 @@ static size_t packed_bytes(const GemmSide& g) {
   return (size_t)g.subs.size() * g.R * g.prog.max_taps * g.kc_pad * 2;
 }
 
-static int32_t pack_side(const GemmSide& g, const float* w, void* out, int k3, cudaStream_t st) {
-  const int64_t total = (int64_t)packed_bytes(g) / 2;
-  const int threads = 256;
-  const int blocks = (int)std::min<int64_t>((total + threads - 1) / threads, 148 * 16);
-  pack_weights_kernel<<<blocks, threads, 0, st>>>(w, reinterpret_cast<__nv_bfloat16*>(out), g.d_src,
-                                                   (int)g.subs.size(), g.prog.max_taps, g.R, g.Kc, g.kc_pad, k3,
-                                                   g.swap ? 1 : 0);
+static PackImage make_image(const GemmSide& g, void* out, bool transposed) {
+  PackImage im;
+  im.out = reinterpret_cast<__nv_bfloat16*>(out);
+  im.tbl = g.d_src;
+  im.nsubs = (int)g.subs.size();
+  im.max_taps = g.prog.max_taps;
+  im.rows = g.R;
+  im.kc_pad = g.kc_pad;
+  im.transposed = transposed ? 1 : 0;
+  return im;
+}
+
+template <int K3>
+static int32_t launch_pack(const float* w, int A, int B, const PackImage& i0, const PackImage& i1, dim3 grid,
+                           cudaStream_t st) {
+  constexpr size_t smem = (size_t)kPT * (kPT * (K3 | 1) + 1) * sizeof(float);
+  static bool attr = false;
+  if (!attr) {
+    PETSYN_CHECK_CUDA(cudaFuncSetAttribute(pack_weights_kernel<K3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = true;
+  }
+  pack_weights_kernel<K3><<<grid, 256, smem, st>>>(w, A, B, i0, i1);
   return check_launch("pack_weights_kernel");
+}
+
+template <int K3>
+static int32_t launch_unpack(const float* scratch, float* dw, const InvEntryDev* inv, int A, int B, const GemmSide& f,
+                             bool transposed, int accumulate, cudaStream_t st) {
+  const size_t smem = (size_t)f.subs.size() * f.prog.max_taps * (kPT * (kPT + 1) + 1) * sizeof(float);
+  static size_t smem_set = 0;
+  if (smem > smem_set) {
+    PETSYN_CHECK_CUDA(cudaFuncSetAttribute(unpack_wgrad_kernel<K3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    smem_set = smem;
+  }
+  dim3 grid((unsigned)((A + kPT - 1) / kPT), (unsigned)((B + kPT - 1) / kPT));
+  unpack_wgrad_kernel<K3><<<grid, 256, smem, st>>>(scratch, dw, inv, A, B, (int)f.subs.size(), f.prog.max_taps, f.R,
+                                                   f.kc_pad, transposed ? 1 : 0, accumulate);
+  return check_launch("unpack_wgrad_kernel");
 }
 
 }  // namespace petsyn
@@ -457,9 +629,11 @@ int32_t petsyn_conv_plan_create(const petsyn_conv_desc* d, petsyn_conv_plan** ou
   f.prog = make_program(fwd, k);
   f.R = d->cout; f.Kc = d->cin;
   f.swap = (d->op == PETSYN_OP_CONVT);
+  f.out_fp32 = d->y_fp32 != 0;
   f.out_w = f.prog.out_phased ? ow / 2 : ow;
   f.out_h = f.prog.out_phased ? oh / 2 : oh;
   f.out_d = f.prog.out_phased ? od / 2 : od;
+  f.out_rows_full = (int64_t)d->n * od * oh * ow;
   int32_t rc = finish_side(f, d->n);
   GemmSide& g = pl->dgrad;
   if (!rc) {
@@ -469,6 +643,7 @@ int32_t petsyn_conv_plan_create(const petsyn_conv_desc* d, petsyn_conv_plan** ou
     g.out_w = g.prog.out_phased ? d->w / 2 : d->w;
     g.out_h = g.prog.out_phased ? d->h / 2 : d->h;
     g.out_d = g.prog.out_phased ? d->d / 2 : d->d;
+    g.out_rows_full = (int64_t)d->n * d->d * d->h * d->w;
     rc = finish_side(g, d->n);
   }
   if (!rc) {
@@ -538,12 +713,50 @@ size_t petsyn_conv_packed_fprop_bytes(const petsyn_conv_plan* pl) { return pl ? 
 size_t petsyn_conv_packed_dgrad_bytes(const petsyn_conv_plan* pl) { return pl ? packed_bytes(pl->dgrad) : 0; }
 size_t petsyn_conv_wgrad_scratch_bytes(const petsyn_conv_plan* pl) { return pl ? packed_bytes(pl->fprop) * 2 : 0; }
 
+size_t petsyn_conv_workspace_bytes(const petsyn_conv_plan* pl) {
+  if (!pl) return 0;
+  size_t b = 0;
+  for (const GemmSide* g : {&pl->fprop, &pl->dgrad})
+    if (g->ksplit > 1) b = std::max(b, (size_t)g->out_rows_full * g->R * sizeof(float));
+  return b;
+}
+
+int32_t petsyn_conv_set_workspace(petsyn_conv_plan* pl, void* workspace, size_t bytes) {
+  PETSYN_REQUIRE(pl != nullptr, "null plan");
+  PETSYN_REQUIRE(bytes >= petsyn_conv_workspace_bytes(pl), "workspace too small (%zu < %zu)", bytes,
+                 petsyn_conv_workspace_bytes(pl));
+  for (GemmSide* g : {&pl->fprop, &pl->dgrad}) {
+    g->workspace = workspace;
+    g->workspace_bytes = bytes;
+  }
+  return PETSYN_OK;
+}
+
 int32_t petsyn_conv_pack_weights(petsyn_conv_plan* pl, const float* w, void* packed_fprop, void* packed_dgrad,
                                  void* stream) {
   PETSYN_REQUIRE(pl != nullptr && w != nullptr, "null argument");
-  int32_t rc = PETSYN_OK;
-  if (packed_fprop) rc = pack_side(pl->fprop, w, packed_fprop, pl->k3, as_stream(stream));
-  if (!rc && packed_dgrad) rc = pack_side(pl->dgrad, w, packed_dgrad, pl->k3, as_stream(stream));
+  // W[a][b][k]: (a, b) = (cout, cin) for Conv/UpConv, (cin, cout) for ConvTranspose.  An image whose rows are W's dim 1
+  // is "transposed".
+  const bool convt = pl->desc.op == PETSYN_OP_CONVT;
+  const int A = convt ? pl->desc.cin : pl->desc.cout, B = convt ? pl->desc.cout : pl->desc.cin;
+  PackImage i0 = make_image(pl->fprop, packed_fprop, /*transposed=*/convt);
+  PackImage i1 = make_image(pl->dgrad, packed_dgrad, /*transposed=*/!convt);
+  // the tile grid must also cover the zero padding of the column dimension of either image
+  int amax = A, bmax = B;
+  for (const PackImage* im : {&i0, &i1}) {
+    if (!im->out) continue;
+    if (im->transposed) amax = std::max(amax, im->kc_pad); else bmax = std::max(bmax, im->kc_pad);
+  }
+  dim3 grid((unsigned)((amax + kPT - 1) / kPT), (unsigned)((bmax + kPT - 1) / kPT));
+  cudaStream_t st = as_stream(stream);
+  int32_t rc;
+  switch (pl->k3) {
+    case 1: rc = launch_pack<1>(w, A, B, i0, i1, grid, st); break;
+    case 8: rc = launch_pack<8>(w, A, B, i0, i1, grid, st); break;
+    case 27: rc = launch_pack<27>(w, A, B, i0, i1, grid, st); break;
+    case 64: rc = launch_pack<64>(w, A, B, i0, i1, grid, st); break;
+    default: rc = fail(PETSYN_EINVAL, "unsupported kernel volume %d", pl->k3);
+  }
   return rc;
 }
 
@@ -552,14 +765,14 @@ int32_t petsyn_conv_fprop(petsyn_conv_plan* pl, const void* x, const void* packe
   PETSYN_REQUIRE(pl && x && packed && y, "null argument");
   int32_t rc = bind_side(pl->fprop, pl->vx, pl->vy, x, packed, y, bias, pl->desc.epi_act, pl->desc.epi_slope);
   if (rc) return rc;
-  return launch_igemm(pl->fprop, pl->desc.n, as_stream(stream));
+  return run_side(pl->fprop, pl->vy, y, bias, pl->desc.epi_act, pl->desc.epi_slope, pl->desc.n, as_stream(stream));
 }
 
 int32_t petsyn_conv_dgrad(petsyn_conv_plan* pl, const void* dy, const void* packed, void* dx, void* stream) {
   PETSYN_REQUIRE(pl && dy && packed && dx, "null argument");
   int32_t rc = bind_side(pl->dgrad, pl->vdy, pl->vdx, dy, packed, dx, nullptr, PETSYN_ACT_NONE, 0.f);
   if (rc) return rc;
-  return launch_igemm(pl->dgrad, pl->desc.n, as_stream(stream));
+  return run_side(pl->dgrad, pl->vdx, dx, nullptr, PETSYN_ACT_NONE, 0.f, pl->desc.n, as_stream(stream));
 }
 
 int32_t petsyn_conv_wgrad(petsyn_conv_plan* pl, const void* x, const void* dy, void* scratch, float* dw,
@@ -626,11 +839,18 @@ int32_t petsyn_conv_wgrad(petsyn_conv_plan* pl, const void* x, const void* dy, v
   }
   int32_t rc = check_launch("wgrad_kernel");
   if (rc) return rc;
-  const int64_t total = (int64_t)f.R * f.Kc * pl->k3;
-  const int blocks = (int)std::min<int64_t>((total + 255) / 256, 148 * 16);
-  unpack_wgrad_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const float*>(scratch), dw, pl->d_inv, f.prog.max_taps,
-                                               f.R, f.Kc, f.kc_pad, pl->k3, f.swap ? 1 : 0, accumulate);
-  return check_launch("unpack_wgrad_kernel");
+  {
+    const bool convt = pl->desc.op == PETSYN_OP_CONVT;
+    const int A = convt ? pl->desc.cin : pl->desc.cout, B = convt ? pl->desc.cout : pl->desc.cin;
+    const float* sc = reinterpret_cast<const float*>(scratch);
+    switch (pl->k3) {
+      case 1: return launch_unpack<1>(sc, dw, pl->d_inv, A, B, f, convt, accumulate, st);
+      case 8: return launch_unpack<8>(sc, dw, pl->d_inv, A, B, f, convt, accumulate, st);
+      case 27: return launch_unpack<27>(sc, dw, pl->d_inv, A, B, f, convt, accumulate, st);
+      case 64: return launch_unpack<64>(sc, dw, pl->d_inv, A, B, f, convt, accumulate, st);
+      default: return fail(PETSYN_EINVAL, "unsupported kernel volume %d", pl->k3);
+    }
+  }
 }
 
 }  // extern "C"

@@ -51,6 +51,7 @@ struct alignas(64) IgemmParams {
   int32_t rows;           // valid output channels (for bias bounds)
   int32_t epi_act;
   float epi_slope;
+  int32_t ksplit;         // CTAs sharing one output tile's K loop (split-K; >1 only with OUT_F32_REDUCE)
 };
 
 enum { OUT_BF16 = 0, OUT_F32 = 1, OUT_F32_REDUCE = 2 };
@@ -107,7 +108,8 @@ __global__ void __launch_bounds__(128) igemm_kernel(const __grid_constant__ Igem
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
 
-  const IgemmSub sub = p.subs[blockIdx.z];
+  const IgemmSub sub = p.subs[blockIdx.z / p.ksplit];
+  const int split = blockIdx.z % p.ksplit;
   int t = blockIdx.x;
   const int tw = t % p.tiles_w; t /= p.tiles_w;
   const int th = t % p.tiles_h; t /= p.tiles_h;
@@ -115,7 +117,12 @@ __global__ void __launch_bounds__(128) igemm_kernel(const __grid_constant__ Igem
   const int nb = t;
   const int w0 = tw * p.box_w, h0 = th * p.box_h, d0 = td * p.box_d;
   const int n0 = blockIdx.y * BLOCK_N;
-  const int nsteps = sub.tap_count * p.kc_chunks;
+  const int total_steps = sub.tap_count * p.kc_chunks;
+  const int per_split = (total_steps + p.ksplit - 1) / p.ksplit;
+  const int s_begin = split * per_split;
+  const int s_end = min(total_steps, s_begin + per_split);
+  const int nsteps = s_end - s_begin;
+  if (nsteps <= 0) return;   // uniform across the CTA; nothing to add to the split-K sum
 
   for (int i = tid; i < sub.tap_count; i += 128) s_taps[i] = p.taps[sub.tap_begin + i];
 
@@ -142,20 +149,18 @@ __global__ void __launch_bounds__(128) igemm_kernel(const __grid_constant__ Igem
     if (ptx::elect_one()) {
       // ---------------- TMA producer ----------------
       const uint32_t tx_bytes = uint32_t(p.a_stage_bytes) + uint32_t(Cfg::kBBytesRaw);
-      int s = 0;
-      for (int tap = 0; tap < sub.tap_count; ++tap) {
+      int tap = s_begin / p.kc_chunks, kc = s_begin - tap * p.kc_chunks;
+      for (int s = 0; s < nsteps; ++s) {
         const IgemmTap tp = s_taps[tap];
-        const CUtensorMap* amap = &p.a_maps[tp.a_view];
-        for (int kc = 0; kc < p.kc_chunks; ++kc, ++s) {
-          const int stage = s % STAGES;
-          const uint32_t ph = (s / STAGES) & 1;
-          ptx::mbar_wait(&empty_bar[stage], ph ^ 1);
-          uint8_t* a_dst = smem + stage * Cfg::kStageBytes;
-          uint8_t* b_dst = a_dst + Cfg::kABytes;
-          ptx::mbar_expect_tx(&full_bar[stage], tx_bytes);
-          ptx::tma_load_5d(a_dst, amap, &full_bar[stage], kc * KCH, w0 + tp.dw, h0 + tp.dh, d0 + tp.dd, nb);
-          ptx::tma_load_2d(b_dst, &p.b_map, &full_bar[stage], tap * p.kc_pad + kc * KCH, sub.b_row + n0);
-        }
+        const int stage = s % STAGES;
+        const uint32_t ph = (s / STAGES) & 1;
+        ptx::mbar_wait(&empty_bar[stage], ph ^ 1);
+        uint8_t* a_dst = smem + stage * Cfg::kStageBytes;
+        uint8_t* b_dst = a_dst + Cfg::kABytes;
+        ptx::mbar_expect_tx(&full_bar[stage], tx_bytes);
+        ptx::tma_load_5d(a_dst, &p.a_maps[tp.a_view], &full_bar[stage], kc * KCH, w0 + tp.dw, h0 + tp.dh, d0 + tp.dd, nb);
+        ptx::tma_load_2d(b_dst, &p.b_map, &full_bar[stage], tap * p.kc_pad + kc * KCH, sub.b_row + n0);
+        if (++kc == p.kc_chunks) { kc = 0; ++tap; }
       }
     }
   } else if (warp == 1) {

@@ -17,7 +17,7 @@ from ._cabi import (ACT_LRELU, ACT_NONE, ACT_RELU, ACT_SILU, ACT_TANH, OP_CONV, 
 
 __all__ = ["ConvPlan", "OP_CONV", "OP_UPCONV", "OP_CONVT", "ACT_NONE", "ACT_RELU", "ACT_LRELU", "ACT_SILU",
            "ACT_TANH", "bn_stats", "bn_finalize", "norm_act_fwd", "norm_act_bwd", "l1_loss_fwd_bwd",
-           "mse_const_fwd_bwd", "adam_step", "sumsq", "stem_fwd", "stem_wgrad", "head_fwd", "head_bwd"]
+           "mse_const_fwd_bwd", "adam_step", "sumsq", "StemConv", "HeadConv"]
 
 
 class ConvPlan:
@@ -30,11 +30,11 @@ class ConvPlan:
     def __init__(self, op: int, n: int, d: int, h: int, w: int, cin: int, cout: int, ksize: int, stride: int, pad: int,
                  x_cstride: Optional[int] = None, x_coff: int = 0, y_cstride: Optional[int] = None, y_coff: int = 0,
                  dy_cstride: Optional[int] = None, dy_coff: int = 0, dx_cstride: Optional[int] = None,
-                 dx_coff: int = 0, act: int = ACT_NONE, slope: float = 0.2):
+                 dx_coff: int = 0, act: int = ACT_NONE, slope: float = 0.2, y_fp32: bool = False):
         _cabi.require_cuda()
         self.desc = _cabi.ConvDesc(op, n, d, h, w, cin, cout, ksize, stride, pad,
                                    x_cstride or cin, x_coff, y_cstride or cout, y_coff,
-                                   dy_cstride or cout, dy_coff, dx_cstride or cin, dx_coff, act, slope)
+                                   dy_cstride or cout, dy_coff, dx_cstride or cin, dx_coff, act, slope, int(y_fp32))
         handle = C.c_void_p()
         check(lib.petsyn_conv_plan_create(C.byref(self.desc), C.byref(handle)), "conv_plan_create")
         self._h = handle
@@ -47,6 +47,11 @@ class ConvPlan:
         self.packed_fprop_bytes = lib.petsyn_conv_packed_fprop_bytes(self._h)
         self.packed_dgrad_bytes = lib.petsyn_conv_packed_dgrad_bytes(self._h)
         self.wgrad_scratch_bytes = lib.petsyn_conv_wgrad_scratch_bytes(self._h)
+        ws = lib.petsyn_conv_workspace_bytes(self._h)
+        self.workspace: Optional[torch.Tensor] = None
+        if ws:
+            self.workspace = torch.empty(ws, dtype=torch.uint8, device=torch.device("cuda", torch.cuda.current_device()))
+            check(lib.petsyn_conv_set_workspace(self._h, ptr(self.workspace), ws), "conv_set_workspace")
         self.w_fprop: Optional[torch.Tensor] = None
         self.w_dgrad: Optional[torch.Tensor] = None
         self._scratch: Optional[torch.Tensor] = None
@@ -90,31 +95,71 @@ class ConvPlan:
 
 
 # ------------------------------------------------------------------------------------------------ edge layers
-def stem_fwd(x: torch.Tensor, w: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
-    """Conv3d(1->C, k4 s2 p1) on the fp32 network input (unet_model.py:47,62); y bf16 NDHWC."""
-    n, _, d, h, wd = x.shape
-    check(lib.petsyn_stem_conv_k4s2_fwd(ptr(x), ptr(w), ptr(y), n, d, h, wd, w.shape[0], stream_ptr()), "stem_fwd")
-    return y
+class StemConv:
+    """Conv3d(1 -> C, k4 s2 p1, no bias) on the fp32 NCDHW network input (unet_model.py:47,62).
+
+    im2col of the single-channel volume (``petsyn_stem_im2col_k4s2``) turns it into a K = 64 GEMM that runs on the
+    tcgen05 conv kernel (k = 1); the patches are kept for the weight gradient.
+    """
+
+    def __init__(self, n: int, d: int, h: int, w: int, cout: int, device):
+        self.n, self.d, self.h, self.w, self.cout = n, d, h, w, cout
+        self.rows = n * (d // 2) * (h // 2) * (w // 2)
+        self.patches = torch.empty(self.rows, 64, dtype=torch.bfloat16, device=device)
+        self.plan = ConvPlan(OP_CONV, n, d // 2, h // 2, w // 2, 64, cout, 1, 1, 0)
+
+    def pack(self, w: torch.Tensor) -> None:
+        self.plan.pack(w.view(self.cout, 64, 1, 1, 1), need_dgrad=False)
+
+    def fprop(self, x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+        check(lib.petsyn_stem_im2col_k4s2(ptr(x), ptr(self.patches), self.n, self.d, self.h, self.w, stream_ptr()),
+              "stem_im2col")
+        return self.plan.fprop(self.patches, y)
+
+    def wgrad(self, dy: torch.Tensor, dw: torch.Tensor) -> torch.Tensor:
+        """dw [C,1,4,4,4] from the patches of the last fprop."""
+        return self.plan.wgrad(self.patches, dy, dw)
 
 
-def stem_wgrad(x: torch.Tensor, dy: torch.Tensor, dw: torch.Tensor) -> torch.Tensor:
-    n, _, d, h, wd = x.shape
-    check(lib.petsyn_stem_conv_k4s2_wgrad(ptr(x), ptr(dy), ptr(dw), n, d, h, wd, dw.shape[0], stream_ptr()),
-          "stem_wgrad")
-    return dw
+class HeadConv:
+    """ReLU'd skip tensor -> Upsample x2 -> Conv3d(C -> 1, k3 p1, no bias) -> Tanh (unet_model.py:59-64).
 
+    fwd: proj[s, k] = <x[s, :], W[k, :]> (k = 1 conv, cout = 32, fp32 out, tensor cores) then a 27-term gather + tanh.
+    bwd: scatter of dy*(1 - y^2) into dproj (bf16, 64 wide) then dx = dproj @ W (k = 1 conv) and dW = wgrad of the proj.
+    """
 
-def head_fwd(x: torch.Tensor, w: torch.Tensor, proj: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
-    """ReLU'd skip tensor -> Upsample x2 -> Conv3d(C->1,k3,p1) -> Tanh (unet_model.py:59-64); y fp32 NCDHW."""
-    n, d, h, wd, c = x.shape
-    check(lib.petsyn_head_upconv_tanh_fwd(ptr(x), ptr(w), ptr(proj), ptr(y), n, d, h, wd, c, stream_ptr()), "head_fwd")
-    return y
+    def __init__(self, n: int, d: int, h: int, w: int, cin: int, device):
+        self.n, self.d, self.h, self.w, self.cin = n, d, h, w, cin
+        self.rows = n * d * h * w
+        self.proj = torch.empty(self.rows, 32, dtype=torch.float32, device=device)
+        self.dproj = torch.zeros(self.rows, 64, dtype=torch.bfloat16, device=device)
+        self.plan_proj = ConvPlan(OP_CONV, n, d, h, w, cin, 32, 1, 1, 0, dy_cstride=64, y_fp32=True)
+        self.plan_dx = ConvPlan(OP_CONV, n, d, h, w, 64, cin, 1, 1, 0)
+        self.w_proj = torch.zeros(32, cin, 1, 1, 1, dtype=torch.float32, device=device)
+        self.w_dx = torch.zeros(cin, 64, 1, 1, 1, dtype=torch.float32, device=device)
+        self.dw_proj = torch.empty(32, cin, 1, 1, 1, dtype=torch.float32, device=device)
 
+    def pack(self, w: torch.Tensor, need_bwd: bool = True) -> None:
+        """w: [1, C, 3, 3, 3] fp32."""
+        wk = w.view(self.cin, 27)
+        self.w_proj.view(32, self.cin)[:27].copy_(wk.t())
+        self.plan_proj.pack(self.w_proj, need_dgrad=False)
+        if need_bwd:
+            self.w_dx.view(self.cin, 64)[:, :27].copy_(wk)
+            self.plan_dx.pack(self.w_dx, need_dgrad=False)
 
-def head_bwd(x, w, y, dy, dproj, dx, dw) -> None:
-    n, d, h, wd, c = x.shape
-    check(lib.petsyn_head_upconv_tanh_bwd(ptr(x), ptr(w), ptr(y), ptr(dy), ptr(dproj), ptr(dx), ptr(dw), n, d, h, wd, c,
-                                          stream_ptr()), "head_bwd")
+    def fprop(self, x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+        self.plan_proj.fprop(x, self.proj)
+        check(lib.petsyn_head_gather_tanh(ptr(self.proj), ptr(y), self.n, self.d, self.h, self.w, stream_ptr()),
+              "head_gather_tanh")
+        return y
+
+    def backward(self, x: torch.Tensor, y: torch.Tensor, dy: torch.Tensor, dx: torch.Tensor, dw: torch.Tensor) -> None:
+        check(lib.petsyn_head_scatter_bwd(ptr(y), ptr(dy), ptr(self.dproj), self.n, self.d, self.h, self.w,
+                                          stream_ptr()), "head_scatter_bwd")
+        self.plan_dx.fprop(self.dproj, dx)
+        self.plan_proj.wgrad(x, self.dproj, self.dw_proj)
+        dw.view(self.cin, 27).copy_(self.dw_proj.view(32, self.cin)[:27].t())
 
 
 # ------------------------------------------------------------------------------------------------ norm / act
@@ -164,6 +209,11 @@ def mse_const_fwd_bwd(x, target: float, loss, dx, grad_scale: float = 1.0) -> No
 def adam_step(p, g, m, v, lr: float, beta1: float, beta2: float, eps: float, step: int) -> None:
     check(lib.petsyn_adam_step(ptr(p), ptr(g), ptr(m), ptr(v), p.numel(), lr, beta1, beta2, eps, step, stream_ptr()),
           "adam_step")
+
+
+def launch_count() -> int:
+    """Kernels launched by libpetsyn so far in this process."""
+    return int(lib.petsyn_launch_count())
 
 
 def sumsq(g: torch.Tensor, out: torch.Tensor) -> None:

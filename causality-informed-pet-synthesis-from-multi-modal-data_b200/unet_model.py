@@ -176,7 +176,6 @@ class _Engine:
         self.cat = [None] + [bf(self.rows[i], 2 * outer[i]) for i in range(1, L)]   # [ReLU(up_i) | ReLU(x_i)]
         self.zu = [None] + [bf(self.rows[i], outer[i]) for i in range(1, L)]   # raw up-conv outputs
         self.r = bf(self.rows[L], inner[L - 1])                                # ReLU(innermost down output)
-        self.proj = torch.empty(self.rows[1], 32, dtype=torch.float32, device=dev)
         self.y = torch.empty(n, 1, d, h, w, dtype=torch.float32, device=dev)
         # ---- gradients ----
         self.dz = [bf(self.rows[i + 1], inner[i]) for i in range(L)]
@@ -184,7 +183,6 @@ class _Engine:
         self.dcat = [None] + [bf(self.rows[i], 2 * outer[i]) for i in range(1, L)]
         self.dzu = [None] + [bf(self.rows[i], outer[i]) for i in range(1, L)]
         self.dr = bf(self.rows[L], inner[L - 1])
-        self.dproj = torch.empty(self.rows[1], 32, dtype=torch.float32, device=dev)
         # ---- norms ----
         self.dnorm: List[Optional[_Norm]] = [None] * L
         self.unorm: List[Optional[_Norm]] = [None] * L
@@ -194,6 +192,9 @@ class _Engine:
             if b._refs["upnorm"] is not None:
                 self.unorm[i] = _Norm(b._refs["upnorm"], outer[i], dev)
         # ---- conv plans ----
+        d1, h1, w1 = self.dims[1]
+        self.stem = ops.StemConv(n, d, h, w, inner[0], dev)
+        self.head = ops.HeadConv(n, d1, h1, w1, 2 * inner[0], dev)
         self.down: List[Optional[ops.ConvPlan]] = [None] * L
         self.up: List[Optional[ops.ConvPlan]] = [None] * L
         for i in range(1, L):
@@ -228,14 +229,17 @@ class _Engine:
 
     def _repack(self, need_dgrad: bool) -> None:
         """Refresh the packed bf16 operands of every conv whose fp32 master weight changed."""
+        jobs = [(self.stem, self.lv[0]._refs["downconv"], lambda w: self.stem.pack(w)),
+                (self.head, self.lv[0]._refs["upconv"], lambda w: self.head.pack(w, need_bwd=need_dgrad))]
         for i in range(1, self.L):
-            for plan, conv, dg in ((self.down[i], self.lv[i]._refs["downconv"], True),
-                                   (self.up[i], self.lv[i]._refs["upconv"], True)):
-                w = conv.weight
-                ver = (w._version, w.data_ptr(), need_dgrad and dg)
-                if self._packed_versions.get(id(plan)) != ver:
-                    plan.pack(w.detach(), need_dgrad=need_dgrad and dg)
-                    self._packed_versions[id(plan)] = ver
+            for plan, conv in ((self.down[i], self.lv[i]._refs["downconv"]), (self.up[i], self.lv[i]._refs["upconv"])):
+                jobs.append((plan, conv, lambda w, plan=plan: plan.pack(w, need_dgrad=need_dgrad)))
+        for obj, conv, fn in jobs:
+            w = conv.weight
+            ver = (w._version, w.data_ptr(), need_dgrad)
+            if self._packed_versions.get(id(obj)) != ver:
+                fn(w.detach())
+                self._packed_versions[id(obj)] = ver
 
     # ------------------------------------------------------------------------------------------------ forward
     def _bn_forward(self, nm: _Norm, z: torch.Tensor, rows: int, c: int, training: bool) -> None:
@@ -256,7 +260,7 @@ class _Engine:
         lv = self.lv
         self._saved_x = x if save else None
         # ---- down path ----
-        ops.stem_fwd(x, lv[0]._refs["downconv"].weight.detach(), self.z[0])
+        self.stem.fprop(x, self.z[0])
         for i in range(1, L):
             prev = self.dnorm[i - 1]
             c = self.outer[i]
@@ -285,7 +289,7 @@ class _Engine:
         d1, h1, w1 = self.dims[1]
         cat1 = self.cat[1].view(n, d1, h1, w1, 2 * self.outer[1])
         y = self.y if save else torch.empty_like(self.y)
-        ops.head_fwd(cat1, lv[0]._refs["upconv"].weight.detach(), self.proj, y)
+        self.head.fprop(cat1, y)
         return y.clone() if (save and clone_output) else y
 
     # ------------------------------------------------------------------------------------------------ backward
@@ -330,8 +334,7 @@ class _Engine:
         n = self.shape[0]
         d1, h1, w1 = self.dims[1]
         cat1 = self.cat[1].view(n, d1, h1, w1, 2 * self.outer[1])
-        ops.head_bwd(cat1, lv[0]._refs["upconv"].weight.detach(), self.y, dy, self.dproj, self.dcat[1],
-                     gw(lv[0]._refs["upconv"]))
+        self.head.backward(cat1, self.y, dy, self.dcat[1], gw(lv[0]._refs["upconv"]))
         ready(lv[0]._refs["upconv"].weight)
         # ---- up path, outer -> inner ----
         for i in range(1, L):
@@ -371,7 +374,7 @@ class _Engine:
             if prev is not None:
                 ready(prev.bn.weight)
                 ready(prev.bn.bias)
-        ops.stem_wgrad(self._saved_x, self.dz[0], gw(lv[0]._refs["downconv"]))
+        self.stem.wgrad(self.dz[0], gw(lv[0]._refs["downconv"]))
         ready(lv[0]._refs["downconv"].weight)
         return [g.clone() for g in grads] if grads is not None else []
 

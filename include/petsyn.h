@@ -45,6 +45,8 @@ extern "C" {
 
 int32_t petsyn_version(void);
 const char* petsyn_last_error(void);
+/* Number of CUDA kernels this library has launched in the calling process (monotonic; for benchmarks' bookkeeping). */
+uint64_t petsyn_launch_count(void);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Convolution family (implicit GEMM on tcgen05 tensor cores, TMA-fed, fp32 accumulation in TMEM)
@@ -73,6 +75,7 @@ typedef struct petsyn_conv_desc {
   int32_t dx_cstride, dx_coff;/* gradient w.r.t. x (bf16) */
   int32_t epi_act;            /* PETSYN_ACT_* applied to y in the fprop epilogue (after bias) */
   float epi_slope;            /* LeakyReLU slope */
+  int32_t y_fp32;             /* != 0: the forward output y is fp32 instead of bf16 (pitches still in elements) */
 } petsyn_conv_desc;
 
 typedef struct petsyn_conv_plan petsyn_conv_plan;
@@ -93,6 +96,12 @@ size_t petsyn_conv_packed_fprop_bytes(const petsyn_conv_plan* plan);
 size_t petsyn_conv_packed_dgrad_bytes(const petsyn_conv_plan* plan);
 size_t petsyn_conv_wgrad_scratch_bytes(const petsyn_conv_plan* plan);
 
+/* Deep layers with few output voxels (M = 252 at the U-Net bottleneck) split their K loop over several CTAs that
+ * add-reduce fp32 partial tiles (TMA reduction) into a caller-owned workspace; 0 bytes when no split is planned.
+ * The workspace (shared by fprop and dgrad, which never overlap on one stream) must be set before the first call. */
+size_t petsyn_conv_workspace_bytes(const petsyn_conv_plan* plan);
+int32_t petsyn_conv_set_workspace(petsyn_conv_plan* plan, void* workspace, size_t bytes);
+
 /* fp32 (Cout,Cin,k,k,k) [CONVT: (Cin,Cout,k,k,k)] -> packed bf16 GEMM operands.  Either destination may be NULL. */
 int32_t petsyn_conv_pack_weights(petsyn_conv_plan* plan, const float* w, void* packed_fprop, void* packed_dgrad,
                                  void* stream);
@@ -110,27 +119,25 @@ int32_t petsyn_conv_wgrad(petsyn_conv_plan* plan, const void* x, const void* dy,
                           int32_t accumulate, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
- * Edge layers of the pix2pix U-Net that are bandwidth-bound by construction (Cin = 1 or Cout = 1)
+ * Edge layers of the pix2pix U-Net (Cin = 1 / Cout = 1): small layout kernels that turn them into 1x1x1 GEMMs for the
+ * conv family above, so that they too run on the tensor cores.
  * ---------------------------------------------------------------------------------------------------------- */
 
-/* First layer: Conv3d(1 -> cout, k4 s2 p1, no bias) on the fp32 NCDHW network input (unet_model.py:47,62).
- * x fp32 [n,d,h,w]; w fp32 [cout,1,4,4,4]; y bf16 NDHWC [n,d/2,h/2,w/2,cout] raw (pre-activation). */
-int32_t petsyn_stem_conv_k4s2_fwd(const float* x, const float* w, void* y, int32_t n, int32_t d, int32_t h, int32_t w_,
-                                  int32_t cout, void* stream);
-/* dw[cout,64] (fp32) = backward-weight of the stem; dy bf16 [n,d/2,h/2,w/2,cout].  dw is overwritten. */
-int32_t petsyn_stem_conv_k4s2_wgrad(const float* x, const void* dy, float* dw, int32_t n, int32_t d, int32_t h,
-                                    int32_t w_, int32_t cout, void* stream);
+/* First layer, Conv3d(1 -> C, k4 s2 p1) on the fp32 NCDHW network input (unet_model.py:47,62): explicit im2col of the
+ * single-channel volume.  x fp32 [n,d,h,w] -> patches bf16 [n*(d/2)*(h/2)*(w/2), 64] (tap = (kd*4+kh)*4+kw, zero
+ * padded at the borders).  The conv itself is then petsyn_conv_fprop with k=1, cin=64, and its weight gradient
+ * petsyn_conv_wgrad on the same patches. */
+int32_t petsyn_stem_im2col_k4s2(const float* x, void* patches, int32_t n, int32_t d, int32_t h, int32_t w, void* stream);
 
-/* Last layer: ReLU'd skip tensor -> Upsample x2 -> Conv3d(cin -> 1, k3 p1, no bias) -> Tanh (unet_model.py:59-64).
- * x bf16 NDHWC [n,d,h,w,cin] (already ReLU'd); w fp32 [1,cin,3,3,3]; proj fp32 scratch [n*d*h*w*32];
- * y fp32 [n,1,2d,2h,2w]. */
-int32_t petsyn_head_upconv_tanh_fwd(const void* x, const float* w, float* proj, float* y, int32_t n, int32_t d,
-                                    int32_t h, int32_t w_, int32_t cin, void* stream);
-/* Backward of the head given dL/dy (fp32, [n,1,2d,2h,2w]) and the saved output y (for tanh').
- * dx bf16 [n,d,h,w,cin] (gradient w.r.t. the ReLU'd input), dw fp32 [1,cin,27] overwritten. */
-int32_t petsyn_head_upconv_tanh_bwd(const void* x, const float* w, const float* y, const float* dy, float* dproj,
-                                    void* dx, float* dw, int32_t n, int32_t d, int32_t h, int32_t w_, int32_t cin,
-                                    void* stream);
+/* Last layer, Upsample x2 -> Conv3d(C -> 1, k3 p1) -> Tanh (unet_model.py:59-64).  The 27-tap conv on the upsampled
+ * grid is computed as a per-SOURCE-voxel projection proj[s][k] = <x[s,:], W[k,:]> (a k=1 conv with cout=32, fp32
+ * output, done by petsyn_conv_fprop) followed by this 27-term gather: y[o] = tanh(sum_k proj[(o+k-1)>>1][k]).
+ * proj fp32 [n*d*h*w, 32]; y fp32 [n,1,2d,2h,2w]. */
+int32_t petsyn_head_gather_tanh(const float* proj, float* y, int32_t n, int32_t d, int32_t h, int32_t w, void* stream);
+/* Backward of the gather: dproj[s][k] = sum_{o: (o+k-1)>>1 == s} dy[o]*(1 - y[o]^2), written as bf16 rows of 64
+ * (columns 27..63 zero) so that it feeds petsyn_conv_fprop / petsyn_conv_wgrad directly. */
+int32_t petsyn_head_scatter_bwd(const float* y, const float* dy, void* dproj, int32_t n, int32_t d, int32_t h,
+                                int32_t w, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Normalisation + activation + skip-concat (bandwidth-bound, vectorised, warp-shuffle reductions)

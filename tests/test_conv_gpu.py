@@ -48,6 +48,8 @@ CASES = [
     ("upconv", 2, 3, 5, 4, 64, 128, 3, 1, 1),
     ("convt", 1, 4, 6, 8, 64, 64, 4, 2, 1),
     ("convt", 1, 3, 4, 3, 128, 128, 4, 2, 1),
+    ("conv", 1, 6, 8, 6, 256, 256, 4, 2, 1),       # bottleneck-like: few voxels, long K -> split-K fprop
+    ("upconv", 1, 3, 4, 3, 256, 256, 3, 1, 1),     # split-K dgrad (64 taps x 4 chunks, 36 voxels)
 ]
 
 

@@ -85,25 +85,35 @@ def test_train_step_matches_oracle_and_golden(name, petsyn):
 
 
 def test_gradient_direction_smooth_loss(petsyn):
-    """Per-parameter gradient direction against the oracle under a smooth loss (0.5*mean((y-t)^2)), where bf16 output
-    noise cannot flip gradient signs: cosine >= 0.995 for every tensor, >= 0.999 globally."""
+    """Per-parameter gradient direction against the fp32 oracle under a smooth loss (0.5*mean((y-t)^2)), calibrated
+    with a PEER as SURVEY 8d prescribes: the same oracle graph run by PyTorch on the GPU under bf16 autocast (cuDNN).
+    Accept when our angular error (1 - cos) is <= 2x the peer's, or below 5e-3 outright; global cosine >= 0.999."""
     ngf, shape, seed = 32, (2, 32, 32, 48), 11
     model = build(petsyn, ngf, seed)
     sd_cpu = {k: v.clone() for k, v in model.state_dict().items()}
     t1, pet = synth_pair(shape, seed)
-    params = {k: v.clone().requires_grad_(True) for k, v in sd_cpu.items()
-              if v.dtype.is_floating_point and "running" not in k}
-    full = dict(sd_cpu); full.update(params)
-    y_o = O.forward(t1, full, num_downs=4, ngf=ngf, training=True)
-    (0.5 * ((y_o - pet) ** 2).mean()).backward()
+
+    def oracle_grads(device, autocast):
+        params = {k: v.clone().to(device).requires_grad_(True) for k, v in sd_cpu.items()
+                  if v.dtype.is_floating_point and "running" not in k}
+        full = {k: v.to(device) for k, v in sd_cpu.items()}
+        full.update(params)
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
+            y_ = O.forward(t1.to(device), full, num_downs=4, ngf=ngf, training=True)
+        (0.5 * ((y_.float() - pet.to(device)) ** 2).mean()).backward()
+        return {k: v.grad.double().cpu().flatten() for k, v in params.items()}
+
+    ref = oracle_grads("cpu", False)
+    peer = oracle_grads("cuda", True)
     model = model.cuda().train()
     y = model(t1.cuda())
     (0.5 * ((y - pet.cuda()) ** 2).mean()).backward()
+    cosf = lambda a, b: (torch.dot(a, b) / (a.norm() * b.norm() + 1e-30)).item()
     dot = na = nb = 0.0
     for k, p in model.named_parameters():
-        a, b = p.grad.double().cpu().flatten(), params[k].grad.double().flatten()
-        cos = (torch.dot(a, b) / (a.norm() * b.norm() + 1e-30)).item()
-        assert cos > 0.995, (k, cos)
+        a, b = p.grad.double().cpu().flatten(), ref[k]
+        ours, theirs = 1.0 - cosf(a, b), 1.0 - cosf(peer[k], b)
+        assert ours <= max(5e-3, 2.0 * theirs), (k, ours, theirs)
         assert abs(a.norm().item() - b.norm().item()) <= GN_PARAM * b.norm().item() + 1e-9, k
         dot += torch.dot(a, b).item(); na += (a ** 2).sum().item(); nb += (b ** 2).sum().item()
     assert dot / (na * nb) ** 0.5 > 0.999
