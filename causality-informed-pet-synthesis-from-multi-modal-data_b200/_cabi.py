@@ -78,7 +78,7 @@ SIGNATURES = {
                                          _f32, _vp, _vp, _vp, _vp, _i64, _i32, _vp]),
     "petsyn_l1_loss_fwd_bwd": (_i32, [_vp, _vp, _vp, _vp, _i64, _f32, _vp]),
     "petsyn_mse_const_fwd_bwd": (_i32, [_vp, _f32, _vp, _vp, _i64, _f32, _vp]),
-    "petsyn_adam_step": (_i32, [_vp, _vp, _vp, _vp, _i64, _f32, _f32, _f32, _f32, _i32, _vp]),
+    "petsyn_adam_step": (_i32, [_vp, _vp, _vp, _vp, _i64, _f32, _f32, _f32, _f32, _i32, _vp, _vp]),
     "petsyn_sumsq": (_i32, [_vp, _vp, _i64, _vp]),
 }
 

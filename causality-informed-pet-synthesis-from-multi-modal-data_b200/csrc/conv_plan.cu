@@ -139,98 +139,94 @@ struct InvEntryDev {   // for one original tap k: where its gradient contributio
 
 // Weight packing / gradient unpacking move W between PyTorch layout W[a][b][k] (k fastest; (a,b) = (Cout,Cin) for
 // Conv3d, (Cin,Cout) for ConvTranspose3d) and the GEMM operand layout B[(sub*rows + row)][t*kc_pad + col].
-// Both go tile-wise through shared memory (16 x 16 (a,b) pairs x all k^3 taps) so that global reads AND writes are
-// contiguous runs, and the tap count is a template parameter so that index arithmetic is constant-folded.
-constexpr int kPT = 16;
-
+// Both go tile-wise through shared memory -- TA x TB (a,b) pairs x all k^3 taps, 256 pairs per block -- shaped so that
+// the image's column index is the long tile edge (64): global reads AND writes are then 128-byte runs.  The tap count
+// is a template parameter so that all index arithmetic is constant-folded.
 struct PackImage {
-  __nv_bfloat16* out;       // nullptr: skip
+  __nv_bfloat16* out;
   const TapSrcDev* tbl;     // [nsubs * max_taps]
   int32_t nsubs, max_taps;
   int32_t rows, kc_pad;     // rows per sub-problem, padded columns per tap
-  int32_t transposed;       // 0: (row, col) = (a, b);  1: (row, col) = (b, a)
 };
 
-template <int K3>
-__global__ void __launch_bounds__(256) pack_weights_kernel(const float* __restrict__ w, int A, int B, PackImage im0,
-                                                           PackImage im1) {
-  constexpr int K3P = K3 | 1;                 // odd pitch along b
-  constexpr int ROWP = kPT * K3P + 1;         // odd pitch along a (kPT * odd is even)
-  extern __shared__ float tile[];             // [kPT][ROWP]
-  __shared__ TapSrcDev s_tbl[2][kMaxTaps];
+// TRANSPOSED = false: (row, col) = (a, b), tile 4 x 64;  true: (row, col) = (b, a), tile 64 x 4
+template <int K3, bool TRANSPOSED>
+__global__ void __launch_bounds__(256) pack_weights_kernel(const float* __restrict__ w, int A, int B, PackImage im) {
+  constexpr int TA = TRANSPOSED ? 64 : 4, TB = TRANSPOSED ? 4 : 64;
+  constexpr int K3P = K3 | 1;                        // odd pitch along b
+  constexpr int ROWP = (TB * K3P) | 1;               // odd pitch along a
+  extern __shared__ float tile[];                    // [TA][ROWP]
+  __shared__ TapSrcDev s_tbl[kMaxTaps];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int a0 = blockIdx.x * kPT, b0 = blockIdx.y * kPT;
-  for (int i = tid; i < im0.nsubs * im0.max_taps; i += 256)
-    if (im0.out) s_tbl[0][i] = im0.tbl[i];
-  for (int i = tid; i < im1.nsubs * im1.max_taps; i += 256)
-    if (im1.out) s_tbl[1][i] = im1.tbl[i];
-  for (int al = warp; al < kPT; al += 8) {
+  const int a0 = blockIdx.x * TA, b0 = blockIdx.y * TB;
+  for (int i = tid; i < im.nsubs * im.max_taps; i += 256) s_tbl[i] = im.tbl[i];
+  for (int al = warp; al < TA; al += 8) {
     const int a = a0 + al;
     const float* src = w + ((int64_t)a * B + b0) * K3;
-    for (int idx = lane; idx < kPT * K3; idx += 32) {
+    for (int idx = lane; idx < TB * K3; idx += 32) {
       const int bl = idx / K3, k = idx - bl * K3;
       tile[al * ROWP + bl * K3P + k] = (a < A && b0 + bl < B) ? __ldg(src + idx) : 0.f;
     }
   }
   __syncthreads();
-#pragma unroll
-  for (int which = 0; which < 2; ++which) {
-    const PackImage& im = which ? im1 : im0;
-    if (im.out == nullptr) continue;
-    const int i = tid / kPT, j = tid % kPT;   // j is the fast (column) index of the image
-    const int row = im.transposed ? b0 + i : a0 + i;
-    const int col = im.transposed ? a0 + j : b0 + j;
-    if (row >= im.rows || col >= im.kc_pad) continue;
-    const float* mine = im.transposed ? tile + j * ROWP + i * K3P : tile + i * ROWP + j * K3P;
-    const int64_t ldb = (int64_t)im.max_taps * im.kc_pad;
-    for (int sub = 0; sub < im.nsubs; ++sub) {
-      __nv_bfloat16* dst = im.out + ((int64_t)sub * im.rows + row) * ldb + col;
-      for (int t = 0; t < im.max_taps; ++t) {
-        const TapSrcDev& e = s_tbl[which][sub * im.max_taps + t];
-        float acc = 0.f;
-        for (int q = 0; q < e.nsrc; ++q) acc += mine[e.src[q]];
-        dst[(int64_t)t * im.kc_pad] = __float2bfloat16(acc);
-      }
+  // thread <-> one (row, col) of the tile; col is the fast index (64 consecutive columns per row)
+  const int ci = tid & 63, ri = tid >> 6;
+  const int row = TRANSPOSED ? b0 + ri : a0 + ri;
+  const int col = TRANSPOSED ? a0 + ci : b0 + ci;
+  if (row >= im.rows || col >= im.kc_pad) return;
+  const float* mine = TRANSPOSED ? tile + ci * ROWP + ri * K3P : tile + ri * ROWP + ci * K3P;
+  const int64_t ldb = (int64_t)im.max_taps * im.kc_pad;
+  for (int sub = 0; sub < im.nsubs; ++sub) {
+    __nv_bfloat16* dst = im.out + ((int64_t)sub * im.rows + row) * ldb + col;
+    const TapSrcDev* tb = s_tbl + sub * im.max_taps;
+#pragma unroll 4
+    for (int t = 0; t < im.max_taps; ++t) {
+      const int n = tb[t].nsrc;
+      float acc = 0.f;
+      for (int q = 0; q < n; ++q) acc += mine[tb[t].src[q]];
+      dst[(int64_t)t * im.kc_pad] = __float2bfloat16(acc);
     }
   }
 }
 
 // scratch [nsubs*rows, max_taps*kc_pad] fp32 -> dw in PyTorch layout (sums the slots every original tap was merged into)
-template <int K3>
+template <int K3, bool TRANSPOSED>
 __global__ void __launch_bounds__(256) unpack_wgrad_kernel(const float* __restrict__ scratch, float* __restrict__ dw,
                                                            const InvEntryDev* __restrict__ inv, int A, int B, int nsubs,
-                                                           int max_taps, int rows, int kc_pad, int transposed,
-                                                           int accumulate) {
-  constexpr int kSlotPitch = kPT * (kPT + 1) + 1;
-  extern __shared__ float tile[];             // [nsubs*max_taps][kSlotPitch], element (a_off, b_off) at a_off*17 + b_off
+                                                           int max_taps, int rows, int kc_pad, int accumulate) {
+  constexpr int TA = TRANSPOSED ? 64 : 4, TB = TRANSPOSED ? 4 : 64;
+  constexpr int kAP = TB + 1;                        // pitch along a inside a slot
+  constexpr int kSlotPitch = (TA * kAP) | 1;
+  extern __shared__ float tile[];                    // [nsubs*max_taps][kSlotPitch], element (a_off, b_off) at a_off*kAP + b_off
   __shared__ InvEntryDev s_inv[K3];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int a0 = blockIdx.x * kPT, b0 = blockIdx.y * kPT;
+  const int a0 = blockIdx.x * TA, b0 = blockIdx.y * TB;
   for (int i = tid; i < K3; i += 256) s_inv[i] = inv[i];
   const int64_t ldb = (int64_t)max_taps * kc_pad;
   {
-    const int i = tid / kPT, j = tid % kPT;
-    const int row = transposed ? b0 + i : a0 + i, col = transposed ? a0 + j : b0 + j;
-    const int a_off = transposed ? j : i, b_off = transposed ? i : j;
+    const int ci = tid & 63, ri = tid >> 6;
+    const int row = TRANSPOSED ? b0 + ri : a0 + ri, col = TRANSPOSED ? a0 + ci : b0 + ci;
+    const int a_off = TRANSPOSED ? ci : ri, b_off = TRANSPOSED ? ri : ci;
     const bool ok = (a0 + a_off) < A && (b0 + b_off) < B;
-    const int nslots = nsubs * max_taps;
-    for (int s = 0; s < nslots; ++s) {
-      const int sub = s / max_taps, t = s - sub * max_taps;
-      tile[s * kSlotPitch + a_off * (kPT + 1) + b_off] =
-          ok ? __ldg(scratch + ((int64_t)sub * rows + row) * ldb + (int64_t)t * kc_pad + col) : 0.f;
+    float* dst = tile + a_off * kAP + b_off;
+    for (int sub = 0; sub < nsubs; ++sub) {
+      const float* src = scratch + ((int64_t)sub * rows + row) * ldb + col;
+#pragma unroll 8
+      for (int t = 0; t < max_taps; ++t)
+        dst[(sub * max_taps + t) * kSlotPitch] = ok ? __ldg(src + (int64_t)t * kc_pad) : 0.f;
     }
   }
   __syncthreads();
-  for (int al = warp; al < kPT; al += 8) {
+  for (int al = warp; al < TA; al += 8) {
     const int a = a0 + al;
     if (a >= A) continue;
     float* dst = dw + ((int64_t)a * B + b0) * K3;
-    for (int idx = lane; idx < kPT * K3; idx += 32) {
+    for (int idx = lane; idx < TB * K3; idx += 32) {
       const int bl = idx / K3, k = idx - bl * K3;
       if (b0 + bl >= B) continue;
       const InvEntryDev& e = s_inv[k];
       float acc = 0.f;
-      for (int q = 0; q < e.n; ++q) acc += tile[(e.sub[q] * max_taps + e.tap[q]) * kSlotPitch + al * (kPT + 1) + bl];
+      for (int q = 0; q < e.n; ++q) acc += tile[(e.sub[q] * max_taps + e.tap[q]) * kSlotPitch + al * kAP + bl];
       if (accumulate) dst[idx] += acc; else dst[idx] = acc;
     }
   }
@@ -520,7 +516,7 @@ static size_t packed_bytes(const GemmSide& g) {
   return (size_t)g.subs.size() * g.R * g.prog.max_taps * g.kc_pad * 2;
 }
 
-static PackImage make_image(const GemmSide& g, void* out, bool transposed) {
+static PackImage make_image(const GemmSide& g, void* out) {
   PackImage im;
   im.out = reinterpret_cast<__nv_bfloat16*>(out);
   im.tbl = g.d_src;
@@ -528,36 +524,69 @@ static PackImage make_image(const GemmSide& g, void* out, bool transposed) {
   im.max_taps = g.prog.max_taps;
   im.rows = g.R;
   im.kc_pad = g.kc_pad;
-  im.transposed = transposed ? 1 : 0;
   return im;
 }
 
-template <int K3>
-static int32_t launch_pack(const float* w, int A, int B, const PackImage& i0, const PackImage& i1, dim3 grid,
-                           cudaStream_t st) {
-  constexpr size_t smem = (size_t)kPT * (kPT * (K3 | 1) + 1) * sizeof(float);
+template <int K3, bool T>
+static int32_t launch_pack_t(const float* w, int A, int B, const PackImage& im, cudaStream_t st) {
+  constexpr int TA = T ? 64 : 4, TB = T ? 4 : 64;
+  constexpr size_t smem = (size_t)TA * ((TB * (K3 | 1)) | 1) * sizeof(float);
   static bool attr = false;
   if (!attr) {
-    PETSYN_CHECK_CUDA(cudaFuncSetAttribute(pack_weights_kernel<K3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PETSYN_CHECK_CUDA(cudaFuncSetAttribute(pack_weights_kernel<K3, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr = true;
   }
-  pack_weights_kernel<K3><<<grid, 256, smem, st>>>(w, A, B, i0, i1);
+  // the tile grid also covers the zero padding of the image's column dimension
+  const int amax = T ? std::max(A, im.kc_pad) : A, bmax = T ? B : std::max(B, im.kc_pad);
+  dim3 grid((unsigned)((amax + TA - 1) / TA), (unsigned)((bmax + TB - 1) / TB));
+  pack_weights_kernel<K3, T><<<grid, 256, smem, st>>>(w, A, B, im);
   return check_launch("pack_weights_kernel");
 }
 
-template <int K3>
-static int32_t launch_unpack(const float* scratch, float* dw, const InvEntryDev* inv, int A, int B, const GemmSide& f,
-                             bool transposed, int accumulate, cudaStream_t st) {
-  const size_t smem = (size_t)f.subs.size() * f.prog.max_taps * (kPT * (kPT + 1) + 1) * sizeof(float);
+static int32_t launch_pack(int k3, bool transposed, const float* w, int A, int B, const PackImage& im, cudaStream_t st) {
+#define PETSYN_PACK_CASE(K)                                                        \
+  case K: return transposed ? launch_pack_t<K, true>(w, A, B, im, st) : launch_pack_t<K, false>(w, A, B, im, st);
+  switch (k3) {
+    PETSYN_PACK_CASE(1)
+    PETSYN_PACK_CASE(8)
+    PETSYN_PACK_CASE(27)
+    PETSYN_PACK_CASE(64)
+    default: return fail(PETSYN_EINVAL, "unsupported kernel volume %d", k3);
+  }
+#undef PETSYN_PACK_CASE
+}
+
+template <int K3, bool T>
+static int32_t launch_unpack_t(const float* scratch, float* dw, const InvEntryDev* inv, int A, int B, const GemmSide& f,
+                               int accumulate, cudaStream_t st) {
+  constexpr int TA = T ? 64 : 4, TB = T ? 4 : 64;
+  const size_t smem = (size_t)f.subs.size() * f.prog.max_taps * ((TA * (TB + 1)) | 1) * sizeof(float);
   static size_t smem_set = 0;
   if (smem > smem_set) {
-    PETSYN_CHECK_CUDA(cudaFuncSetAttribute(unpack_wgrad_kernel<K3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PETSYN_CHECK_CUDA(
+        cudaFuncSetAttribute(unpack_wgrad_kernel<K3, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     smem_set = smem;
   }
-  dim3 grid((unsigned)((A + kPT - 1) / kPT), (unsigned)((B + kPT - 1) / kPT));
-  unpack_wgrad_kernel<K3><<<grid, 256, smem, st>>>(scratch, dw, inv, A, B, (int)f.subs.size(), f.prog.max_taps, f.R,
-                                                   f.kc_pad, transposed ? 1 : 0, accumulate);
+  dim3 grid((unsigned)((A + TA - 1) / TA), (unsigned)((B + TB - 1) / TB));
+  unpack_wgrad_kernel<K3, T><<<grid, 256, smem, st>>>(scratch, dw, inv, A, B, (int)f.subs.size(), f.prog.max_taps, f.R,
+                                                      f.kc_pad, accumulate);
   return check_launch("unpack_wgrad_kernel");
+}
+
+static int32_t launch_unpack(int k3, bool transposed, const float* scratch, float* dw, const InvEntryDev* inv, int A,
+                             int B, const GemmSide& f, int accumulate, cudaStream_t st) {
+#define PETSYN_UNPACK_CASE(K)                                                                       \
+  case K:                                                                                           \
+    return transposed ? launch_unpack_t<K, true>(scratch, dw, inv, A, B, f, accumulate, st)         \
+                      : launch_unpack_t<K, false>(scratch, dw, inv, A, B, f, accumulate, st);
+  switch (k3) {
+    PETSYN_UNPACK_CASE(1)
+    PETSYN_UNPACK_CASE(8)
+    PETSYN_UNPACK_CASE(27)
+    PETSYN_UNPACK_CASE(64)
+    default: return fail(PETSYN_EINVAL, "unsupported kernel volume %d", k3);
+  }
+#undef PETSYN_UNPACK_CASE
 }
 
 }  // namespace petsyn
@@ -739,24 +768,10 @@ int32_t petsyn_conv_pack_weights(petsyn_conv_plan* pl, const float* w, void* pac
   // is "transposed".
   const bool convt = pl->desc.op == PETSYN_OP_CONVT;
   const int A = convt ? pl->desc.cin : pl->desc.cout, B = convt ? pl->desc.cout : pl->desc.cin;
-  PackImage i0 = make_image(pl->fprop, packed_fprop, /*transposed=*/convt);
-  PackImage i1 = make_image(pl->dgrad, packed_dgrad, /*transposed=*/!convt);
-  // the tile grid must also cover the zero padding of the column dimension of either image
-  int amax = A, bmax = B;
-  for (const PackImage* im : {&i0, &i1}) {
-    if (!im->out) continue;
-    if (im->transposed) amax = std::max(amax, im->kc_pad); else bmax = std::max(bmax, im->kc_pad);
-  }
-  dim3 grid((unsigned)((amax + kPT - 1) / kPT), (unsigned)((bmax + kPT - 1) / kPT));
   cudaStream_t st = as_stream(stream);
-  int32_t rc;
-  switch (pl->k3) {
-    case 1: rc = launch_pack<1>(w, A, B, i0, i1, grid, st); break;
-    case 8: rc = launch_pack<8>(w, A, B, i0, i1, grid, st); break;
-    case 27: rc = launch_pack<27>(w, A, B, i0, i1, grid, st); break;
-    case 64: rc = launch_pack<64>(w, A, B, i0, i1, grid, st); break;
-    default: rc = fail(PETSYN_EINVAL, "unsupported kernel volume %d", pl->k3);
-  }
+  int32_t rc = PETSYN_OK;
+  if (packed_fprop) rc = launch_pack(pl->k3, /*transposed=*/convt, w, A, B, make_image(pl->fprop, packed_fprop), st);
+  if (!rc && packed_dgrad) rc = launch_pack(pl->k3, /*transposed=*/!convt, w, A, B, make_image(pl->dgrad, packed_dgrad), st);
   return rc;
 }
 
@@ -842,14 +857,7 @@ int32_t petsyn_conv_wgrad(petsyn_conv_plan* pl, const void* x, const void* dy, v
   {
     const bool convt = pl->desc.op == PETSYN_OP_CONVT;
     const int A = convt ? pl->desc.cin : pl->desc.cout, B = convt ? pl->desc.cout : pl->desc.cin;
-    const float* sc = reinterpret_cast<const float*>(scratch);
-    switch (pl->k3) {
-      case 1: return launch_unpack<1>(sc, dw, pl->d_inv, A, B, f, convt, accumulate, st);
-      case 8: return launch_unpack<8>(sc, dw, pl->d_inv, A, B, f, convt, accumulate, st);
-      case 27: return launch_unpack<27>(sc, dw, pl->d_inv, A, B, f, convt, accumulate, st);
-      case 64: return launch_unpack<64>(sc, dw, pl->d_inv, A, B, f, convt, accumulate, st);
-      default: return fail(PETSYN_EINVAL, "unsupported kernel volume %d", pl->k3);
-    }
+    return launch_unpack(pl->k3, convt, reinterpret_cast<const float*>(scratch), dw, pl->d_inv, A, B, f, accumulate, st);
   }
 }
 

@@ -60,6 +60,8 @@ __device__ __forceinline__ float act_grad(float b, int act, float slope) {
   }
 }
 
+constexpr int kRowUnroll = 4;   // independent 16-byte loads in flight per thread
+
 // Thread layout shared by the row-streaming kernels: cpt = C/8 threads span the channels, blockDim/cpt rows in flight.
 struct RowIter {
   int cpt, rpp, tx, ty;
@@ -101,13 +103,21 @@ __global__ void __launch_bounds__(256) bn_stats_kernel(const __nv_bfloat16* __re
 #pragma unroll
   for (int i = 0; i < 8; ++i) acc[0][i] = acc[1][i] = 0.f;
   if (it.active) {
-    for (int64_t r = (int64_t)blockIdx.x * it.rpp + it.ty; r < rows; r += (int64_t)gridDim.x * it.rpp) {
-      const F8 x = load8(z + r * C + it.tx * 8);
+    const int64_t stride = (int64_t)gridDim.x * it.rpp;
+    for (int64_t r = (int64_t)blockIdx.x * it.rpp + it.ty; r < rows; r += kRowUnroll * stride) {
+      F8 x[kRowUnroll];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        acc[0][i] += x.v[i];
-        acc[1][i] += x.v[i] * x.v[i];
-      }
+      for (int u = 0; u < kRowUnroll; ++u)
+        if (r + u * stride < rows) x[u] = load8(z + (r + u * stride) * C + it.tx * 8);
+#pragma unroll
+      for (int u = 0; u < kRowUnroll; ++u)
+        if (r + u * stride < rows) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            acc[0][i] += x[u].v[i];
+            acc[1][i] += x[u].v[i] * x[u].v[i];
+          }
+        }
     }
   }
   block_reduce_channels<2>(it, acc, smem_f, sums, C);
@@ -155,17 +165,26 @@ __global__ void __launch_bounds__(256) norm_act_fwd_kernel(const __nv_bfloat16* 
 #pragma unroll
   for (int i = 0; i < 8; ++i) { sc.v[i] = 1.f; sh.v[i] = 0.f; }
   if (scale) { sc = load8f(scale + it.tx * 8); sh = load8f(shift + it.tx * 8); }
-  for (int64_t r = (int64_t)blockIdx.x * it.rpp + it.ty; r < rows; r += (int64_t)gridDim.x * it.rpp) {
-    const F8 x = load8(z + r * C + it.tx * 8);
-    F8 o1, o2;
+  const int64_t stride = (int64_t)gridDim.x * it.rpp;
+  for (int64_t r0 = (int64_t)blockIdx.x * it.rpp + it.ty; r0 < rows; r0 += kRowUnroll * stride) {
+    F8 xs[kRowUnroll];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const float b = x.v[i] * sc.v[i] + sh.v[i];
-      o1.v[i] = act_fwd(b, act1, slope);
-      o2.v[i] = act_fwd(b, act2, slope);
+    for (int u = 0; u < kRowUnroll; ++u)
+      if (r0 + u * stride < rows) xs[u] = load8(z + (r0 + u * stride) * C + it.tx * 8);
+#pragma unroll
+    for (int u = 0; u < kRowUnroll; ++u) {
+      const int64_t r = r0 + u * stride;
+      if (r >= rows) break;
+      F8 o1, o2;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float b = xs[u].v[i] * sc.v[i] + sh.v[i];
+        o1.v[i] = act_fwd(b, act1, slope);
+        o2.v[i] = act_fwd(b, act2, slope);
+      }
+      store8(dst1 + r * cs1 + co1 + it.tx * 8, o1);
+      if (dst2) store8(dst2 + r * cs2 + co2 + it.tx * 8, o2);
     }
-    store8(dst1 + r * cs1 + co1 + it.tx * 8, o1);
-    if (dst2) store8(dst2 + r * cs2 + co2 + it.tx * 8, o2);
   }
 }
 
@@ -186,18 +205,29 @@ __global__ void __launch_bounds__(256) norm_act_bwd_reduce_kernel(
     for (int i = 0; i < 8; ++i) { sc.v[i] = 1.f; sh.v[i] = 0.f; mu.v[i] = 0.f; rs.v[i] = 1.f; }
     if (scale) { sc = load8f(scale + it.tx * 8); sh = load8f(shift + it.tx * 8); }
     if (mean) { mu = load8f(mean + it.tx * 8); rs = load8f(rstd + it.tx * 8); }
-    for (int64_t r = (int64_t)blockIdx.x * it.rpp + it.ty; r < rows; r += (int64_t)gridDim.x * it.rpp) {
-      const F8 x = load8(z + r * C + it.tx * 8);
-      const F8 a = load8(g1 + r * cs1 + co1 + it.tx * 8);
-      F8 b2;
-      if (g2) b2 = load8(g2 + r * cs2 + co2 + it.tx * 8);
+    const int64_t stride = (int64_t)gridDim.x * it.rpp;
+    for (int64_t r0 = (int64_t)blockIdx.x * it.rpp + it.ty; r0 < rows; r0 += 2 * stride) {
+      F8 xs[2], as[2], bs[2];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float b = x.v[i] * sc.v[i] + sh.v[i];
-        float g = a.v[i] * act_grad(b, act1, slope);
-        if (g2) g += b2.v[i] * act_grad(b, act2, slope);
-        acc[0][i] += g;
-        acc[1][i] += g * (x.v[i] - mu.v[i]) * rs.v[i];
+      for (int u = 0; u < 2; ++u) {
+        const int64_t r = r0 + u * stride;
+        if (r < rows) {
+          xs[u] = load8(z + r * C + it.tx * 8);
+          as[u] = load8(g1 + r * cs1 + co1 + it.tx * 8);
+          if (g2) bs[u] = load8(g2 + r * cs2 + co2 + it.tx * 8);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        if (r0 + u * stride >= rows) break;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float b = xs[u].v[i] * sc.v[i] + sh.v[i];
+          float g = as[u].v[i] * act_grad(b, act1, slope);
+          if (g2) g += bs[u].v[i] * act_grad(b, act2, slope);
+          acc[0][i] += g;
+          acc[1][i] += g * (xs[u].v[i] - mu.v[i]) * rs.v[i];
+        }
       }
     }
   }
@@ -235,21 +265,33 @@ __global__ void __launch_bounds__(256) norm_act_bwd_apply_kernel(
       k2.v[i] = s1.v[i] * inv;
     }
   }
-  for (int64_t r = (int64_t)blockIdx.x * it.rpp + it.ty; r < rows; r += (int64_t)gridDim.x * it.rpp) {
-    const F8 x = load8(z + r * C + it.tx * 8);
-    const F8 a = load8(g1 + r * cs1 + co1 + it.tx * 8);
-    F8 b2;
-    if (g2) b2 = load8(g2 + r * cs2 + co2 + it.tx * 8);
-    F8 o;
+  const int64_t stride = (int64_t)gridDim.x * it.rpp;
+  for (int64_t r0 = (int64_t)blockIdx.x * it.rpp + it.ty; r0 < rows; r0 += 2 * stride) {
+    F8 xs[2], as[2], bs[2];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const float b = x.v[i] * sc.v[i] + sh.v[i];
-      float g = a.v[i] * act_grad(b, act1, slope);
-      if (g2) g += b2.v[i] * act_grad(b, act2, slope);
-      const float zh = (x.v[i] - mu.v[i]) * rs.v[i];
-      o.v[i] = k0.v[i] * (g - k1.v[i] - zh * k2.v[i]);
+    for (int u = 0; u < 2; ++u) {
+      const int64_t r = r0 + u * stride;
+      if (r < rows) {
+        xs[u] = load8(z + r * C + it.tx * 8);
+        as[u] = load8(g1 + r * cs1 + co1 + it.tx * 8);
+        if (g2) bs[u] = load8(g2 + r * cs2 + co2 + it.tx * 8);
+      }
     }
-    store8(dz + r * C + it.tx * 8, o);
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int64_t r = r0 + u * stride;
+      if (r >= rows) break;
+      F8 o;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float b = xs[u].v[i] * sc.v[i] + sh.v[i];
+        float g = as[u].v[i] * act_grad(b, act1, slope);
+        if (g2) g += bs[u].v[i] * act_grad(b, act2, slope);
+        const float zh = (xs[u].v[i] - mu.v[i]) * rs.v[i];
+        o.v[i] = k0.v[i] * (g - k1.v[i] - zh * k2.v[i]);
+      }
+      store8(dz + r * C + it.tx * 8, o);
+    }
   }
 }
 
@@ -309,18 +351,39 @@ __global__ void __launch_bounds__(256) mse_const_kernel(const float* __restrict_
   if (threadIdx.x == 0) atomicAdd(loss, s * inv_n);
 }
 
+// step_dev (optional): device-resident 1-based step counter, so that a CUDA graph of the training step stays valid as
+// the bias corrections change from step to step.
 __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g,
                                                    float* __restrict__ m, float* __restrict__ v, int64_t n, float lr,
-                                                   float b1, float b2, float eps, float bc1, float bc2_sqrt) {
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    const float gi = g[i];
-    const float mi = b1 * m[i] + (1.f - b1) * gi;
-    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
-    m[i] = mi;
-    v[i] = vi;
-    const float denom = sqrtf(vi) / bc2_sqrt + eps;
-    p[i] -= (lr / bc1) * (mi / denom);
+                                                   float b1, float b2, float eps, int step,
+                                                   const int32_t* __restrict__ step_dev) {
+  const float t = (float)(step_dev ? *step_dev : step);
+  const float bc1 = 1.f - powf(b1, t);
+  const float bc2_sqrt = sqrtf(1.f - powf(b2, t));
+  const float step_size = lr / bc1;
+  const int64_t n4 = n >> 2;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    const float4 gi = reinterpret_cast<const float4*>(g)[i];
+    float4 mi = reinterpret_cast<float4*>(m)[i], vi = reinterpret_cast<float4*>(v)[i], pi = reinterpret_cast<float4*>(p)[i];
+#define PETSYN_ADAM1(c)                                        \
+    mi.c = b1 * mi.c + (1.f - b1) * gi.c;                      \
+    vi.c = b2 * vi.c + (1.f - b2) * gi.c * gi.c;               \
+    pi.c -= step_size * (mi.c / (sqrtf(vi.c) / bc2_sqrt + eps));
+    PETSYN_ADAM1(x) PETSYN_ADAM1(y) PETSYN_ADAM1(z) PETSYN_ADAM1(w)
+#undef PETSYN_ADAM1
+    reinterpret_cast<float4*>(m)[i] = mi;
+    reinterpret_cast<float4*>(v)[i] = vi;
+    reinterpret_cast<float4*>(p)[i] = pi;
   }
+  if (blockIdx.x == 0)
+    for (int64_t i = n4 * 4 + threadIdx.x; i < n; i += blockDim.x) {
+      const float gi = g[i];
+      const float mi = b1 * m[i] + (1.f - b1) * gi;
+      const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+      m[i] = mi;
+      v[i] = vi;
+      p[i] -= step_size * (mi / (sqrtf(vi) / bc2_sqrt + eps));
+    }
 }
 
 __global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g, float* __restrict__ out, int64_t n) {
@@ -431,13 +494,13 @@ int32_t petsyn_mse_const_fwd_bwd(const float* x, float target, float* loss, floa
 }
 
 int32_t petsyn_adam_step(float* p, const float* g, float* m, float* v, int64_t numel, float lr, float beta1,
-                         float beta2, float eps, int32_t step, void* stream) {
+                         float beta2, float eps, int32_t step, const int32_t* step_dev, void* stream) {
   PETSYN_REQUIRE(p && g && m && v, "null argument");
-  PETSYN_REQUIRE(step >= 1, "Adam step is 1-based");
-  const float bc1 = 1.f - powf(beta1, (float)step);
-  const float bc2s = sqrtf(1.f - powf(beta2, (float)step));
-  const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>((numel + 255) / 256, 148 * 16));
-  adam_kernel<<<blocks, 256, 0, as_stream(stream)>>>(p, g, m, v, numel, lr, beta1, beta2, eps, bc1, bc2s);
+  PETSYN_REQUIRE(step_dev != nullptr || step >= 1, "Adam step is 1-based");
+  PETSYN_REQUIRE((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
+                  reinterpret_cast<uintptr_t>(v)) % 16 == 0, "Adam arenas must be 16-byte aligned");
+  const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>((numel / 4 + 255) / 256, 148 * 16));
+  adam_kernel<<<blocks, 256, 0, as_stream(stream)>>>(p, g, m, v, numel, lr, beta1, beta2, eps, step, step_dev);
   return check_launch("adam_kernel");
 }
 

@@ -206,9 +206,11 @@ def mse_const_fwd_bwd(x, target: float, loss, dx, grad_scale: float = 1.0) -> No
           "mse_const")
 
 
-def adam_step(p, g, m, v, lr: float, beta1: float, beta2: float, eps: float, step: int) -> None:
-    check(lib.petsyn_adam_step(ptr(p), ptr(g), ptr(m), ptr(v), p.numel(), lr, beta1, beta2, eps, step, stream_ptr()),
-          "adam_step")
+def adam_step(p, g, m, v, lr: float, beta1: float, beta2: float, eps: float, step: int,
+              step_dev: Optional[torch.Tensor] = None) -> None:
+    """torch.optim.Adam update; ``step_dev`` (int32 device scalar) overrides ``step`` for graph-captured loops."""
+    check(lib.petsyn_adam_step(ptr(p), ptr(g), ptr(m), ptr(v), p.numel(), lr, beta1, beta2, eps, step, ptr(step_dev),
+                               stream_ptr()), "adam_step")
 
 
 def launch_count() -> int:

@@ -115,6 +115,9 @@ class Unet3dTrainer:
         self.m = torch.zeros_like(self.arena.p)
         self.v = torch.zeros_like(self.arena.p)
         self.step_count = 0
+        self.step_dev = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.graph = None
+        self.static_x = self.static_t = None
         self.loss = torch.zeros(1, dtype=torch.float32, device=dev)
         self.dy = torch.empty(example_input.shape, dtype=torch.float32, device=dev)
         eng.mark_weights_dirty()
@@ -138,19 +141,57 @@ class Unet3dTrainer:
                 dist.broadcast(b, src=0, group=self.pg)
 
     # ------------------------------------------------------------------------------------------------ step
-    def step(self, x: torch.Tensor, target: torch.Tensor, timers=None) -> torch.Tensor:
-        """One optimisation step; returns the (device) loss tensor of this rank's micro-batch."""
+    def _step_impl(self, x: torch.Tensor, target: torch.Tensor, timers=None) -> torch.Tensor:
         eng = self.eng
         y = eng.forward(x, save=True, timers=timers, clone_output=False)
         self.loss.zero_()
         ops.l1_loss_fwd_bwd(y, target, self.loss, self.dy)
         eng.backward(self.dy, out=self.arena.grad_views, on_ready=self.bucketer.on_ready, timers=timers)
         self.bucketer.wait_all()
-        self.step_count += 1
-        ops.adam_step(self.arena.p, self.arena.g, self.m, self.v, self.lr, self.betas[0], self.betas[1], self.eps,
-                      self.step_count)
+        self.step_dev.add_(1)
+        ops.adam_step(self.arena.p, self.arena.g, self.m, self.v, self.lr, self.betas[0], self.betas[1], self.eps, 0,
+                      step_dev=self.step_dev)
         eng.mark_weights_dirty()
         return self.loss
+
+    def step(self, x: torch.Tensor, target: torch.Tensor, timers=None) -> torch.Tensor:
+        """One optimisation step (zero_grad -> fwd -> L1 -> bwd -> [all-reduce] -> Adam); returns the device loss
+        tensor of this rank's micro-batch.  Replays the captured CUDA graph when ``capture()`` has been called."""
+        self.step_count += 1
+        if self.graph is not None and timers is None:
+            if x.data_ptr() != self.static_x.data_ptr():
+                self.static_x.copy_(x, non_blocking=True)
+            if target.data_ptr() != self.static_t.data_ptr():
+                self.static_t.copy_(target, non_blocking=True)
+            self.graph.replay()
+            return self.loss
+        return self._step_impl(x, target, timers)
+
+    def capture(self, warmup: int = 3) -> None:
+        """Capture the whole training step into one CUDA graph (the step is ~100 short kernels; launching them one by
+        one from Python costs more host time than the GPU needs to run them).  Parameters, optimiser state and
+        BatchNorm buffers are restored after the warm-up steps that capture requires, so capture() has no side effect
+        on training state.  Feed ``static_x`` / ``static_t`` directly to skip the device-to-device input copy."""
+        snap = [t.clone() for t in (self.arena.p, self.m, self.v, self.step_dev)]
+        bufs = [b.clone() for b in self.model.buffers()]
+        count = self.step_count
+        self.static_x = torch.zeros(self.dy.shape, dtype=torch.float32, device=self.dev)
+        self.static_t = torch.zeros(self.dy.shape, dtype=torch.float32, device=self.dev)
+        side = torch.cuda.Stream(device=self.dev)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                self._step_impl(self.static_x, self.static_t)
+        torch.cuda.current_stream().wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            self._step_impl(self.static_x, self.static_t)
+        for dst, src in zip((self.arena.p, self.m, self.v, self.step_dev), snap):
+            dst.copy_(src)
+        for dst, src in zip(self.model.buffers(), bufs):
+            dst.copy_(src)
+        self.step_count = count
+        self.graph = graph
 
     def grad_norm(self) -> float:
         out = torch.zeros(1, dtype=torch.float32, device=self.dev)

@@ -188,9 +188,10 @@ int32_t petsyn_l1_loss_fwd_bwd(const float* y, const float* t, float* loss, floa
 /* LSGAN PatchAdversarialLoss(criterion="least_squares"): mean (x - target)^2 and its gradient. */
 int32_t petsyn_mse_const_fwd_bwd(const float* x, float target, float* loss, float* dx, int64_t numel, float grad_scale,
                                  void* stream);
-/* torch.optim.Adam step (no amsgrad, weight_decay 0) over one flat fp32 parameter arena. step is 1-based. */
+/* torch.optim.Adam step (no amsgrad, weight_decay 0) over one flat fp32 parameter arena.  The 1-based step number is
+ * `step`, or -- when step_dev != NULL -- read from device memory (so a captured CUDA graph of the step stays valid). */
 int32_t petsyn_adam_step(float* p, const float* g, float* m, float* v, int64_t numel, float lr, float beta1,
-                         float beta2, float eps, int32_t step, void* stream);
+                         float beta2, float eps, int32_t step, const int32_t* step_dev, void* stream);
 /* sum of squares of a flat fp32 array, accumulated into out[0] (caller-zeroed); used for gradient norms. */
 int32_t petsyn_sumsq(const float* g, float* out, int64_t numel, void* stream);
 

@@ -116,12 +116,15 @@ def test_losses_and_adam(petsyn):
     pr = p.clone().requires_grad_(True)
     opt = torch.optim.Adam([pr], lr=5e-4, betas=(0.9, 0.999), eps=1e-8)
     m, v = torch.zeros_like(p), torch.zeros_like(p)
+    p2, m2, v2 = p.clone(), torch.zeros_like(p), torch.zeros_like(p)
     for step in range(1, 4):
         gr = torch.randn(10007, generator=g).to(DEV)
         pr.grad = gr.clone()
         opt.step()
         ops.adam_step(p, gr, m, v, 5e-4, 0.9, 0.999, 1e-8, step)
+        ops.adam_step(p2, gr, m2, v2, 5e-4, 0.9, 0.999, 1e-8, 0, step_dev=torch.tensor([step], dtype=torch.int32, device=DEV))
     assert (p - pr.detach()).abs().max().item() < 1e-6
+    assert torch.equal(p, p2)
     out = torch.zeros(1, device=DEV)
     ops.sumsq(p, out)
     assert abs(out.item() - (p.double() ** 2).sum().item()) / out.item() < 1e-5

@@ -148,3 +148,43 @@ def test_full_size_cfg1_scalars(petsyn):
     assert abs(tot - float(gold["grad_norm_total"])) <= GN_TOTAL * float(gold["grad_norm_total"])
     samp = y.detach().cpu().numpy()[:, :, ::8, ::8, ::8]
     assert np.abs(samp - gold["output_sample"]).max() <= OUT_MAX
+
+
+def test_trainer_eager_and_graph_match_autograd_adam(petsyn):
+    """The fused train step (flat arenas + fused Adam), eager and CUDA-graph replayed, follows the same trajectory as
+    the autograd path driven by torch.optim.Adam (train_unet.py:149-168 with L1 only)."""
+    from petsyn_b200.train import Unet3dTrainer
+    ngf, shape, seed, steps = 32, (1, 32, 32, 32), 3, 3
+    batches = [synth_pair(shape, 100 + i) for i in range(steps)]
+
+    def run(mode):
+        model = build(petsyn, ngf, seed).cuda().train()
+        losses = []
+        if mode == "autograd":
+            opt = torch.optim.Adam(model.parameters(), lr=5e-4)
+            for t1, pet in batches:
+                opt.zero_grad()
+                loss = torch.nn.functional.l1_loss(model(t1.cuda()), pet.cuda())
+                loss.backward()
+                opt.step()
+                losses.append(loss.item())
+        else:
+            tr = Unet3dTrainer(model, lr=5e-4, example_input=batches[0][0].cuda())
+            if mode == "graph":
+                tr.capture()
+            for t1, pet in batches:
+                losses.append(tr.step(t1.cuda(), pet.cuda()).item())
+        return losses, {k: v.detach().float().cpu().clone() for k, v in model.state_dict().items()}
+
+    la, sa = run("autograd")
+    le, se = run("eager")
+    lg, sg = run("graph")
+    for a, b, c in zip(la, le, lg):
+        assert abs(a - b) < 2e-3 and abs(a - c) < 2e-3, (la, le, lg)
+    for k in sa:
+        ref = sa[k]
+        scale = ref.abs().max().item() + 1e-6
+        # Adam's first steps move every weight by ~lr regardless of gradient scale, so compare against lr-sized motion
+        assert (se[k] - ref).abs().max().item() <= 2e-3 * scale + 2.5e-3, k
+        assert (sg[k] - se[k]).abs().max().item() <= 2e-3 * scale + 2.5e-3, k
+    assert int(sg["model.model.1.model.2.num_batches_tracked"]) == steps   # capture() restored the BN counters
