@@ -149,23 +149,32 @@ struct PackImage {
   int32_t rows, kc_pad;     // rows per sub-problem, padded columns per tap
 };
 
-// TRANSPOSED = false: (row, col) = (a, b), tile 4 x 64;  true: (row, col) = (b, a), tile 64 x 4
-template <int K3, bool TRANSPOSED>
+// TRANSPOSED = false: (row, col) = (a, b), tile 4 x 64;  true: (row, col) = (b, a), tile 64 x 4.
+// NS = merged source taps per slot (1: plain convs, 8: Upsample+Conv); short slots are padded with a pointer to a
+// zero element so that the inner sum is a fixed, fully unrolled chain of independent shared-memory loads.
+template <int K3, bool TRANSPOSED, int NS>
 __global__ void __launch_bounds__(256) pack_weights_kernel(const float* __restrict__ w, int A, int B, PackImage im) {
   constexpr int TA = TRANSPOSED ? 64 : 4, TB = TRANSPOSED ? 4 : 64;
-  constexpr int K3P = K3 | 1;                        // odd pitch along b
+  constexpr int K3P = (K3 & 1) ? K3 + 2 : K3 + 1;    // odd pitch along b with at least one spare (zero) element
   constexpr int ROWP = (TB * K3P) | 1;               // odd pitch along a
   extern __shared__ float tile[];                    // [TA][ROWP]
-  __shared__ TapSrcDev s_tbl[kMaxTaps];
+  __shared__ int16_t s_src[kMaxTaps][NS];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int a0 = blockIdx.x * TA, b0 = blockIdx.y * TB;
-  for (int i = tid; i < im.nsubs * im.max_taps; i += 256) s_tbl[i] = im.tbl[i];
+  const int nslots = im.nsubs * im.max_taps;
+  for (int i = tid; i < nslots * NS; i += 256) {
+    const TapSrcDev& e = im.tbl[i / NS];
+    const int q = i % NS;
+    s_src[i / NS][q] = (int16_t)(q < e.nsrc ? e.src[q] : K3);   // K3 = index of the spare zero element
+  }
+  for (int i = tid; i < TA * ROWP; i += 256) tile[i] = 0.f;
+  __syncthreads();
   for (int al = warp; al < TA; al += 8) {
     const int a = a0 + al;
     const float* src = w + ((int64_t)a * B + b0) * K3;
     for (int idx = lane; idx < TB * K3; idx += 32) {
       const int bl = idx / K3, k = idx - bl * K3;
-      tile[al * ROWP + bl * K3P + k] = (a < A && b0 + bl < B) ? __ldg(src + idx) : 0.f;
+      if (a < A && b0 + bl < B) tile[al * ROWP + bl * K3P + k] = __ldg(src + idx);
     }
   }
   __syncthreads();
@@ -178,30 +187,36 @@ __global__ void __launch_bounds__(256) pack_weights_kernel(const float* __restri
   const int64_t ldb = (int64_t)im.max_taps * im.kc_pad;
   for (int sub = 0; sub < im.nsubs; ++sub) {
     __nv_bfloat16* dst = im.out + ((int64_t)sub * im.rows + row) * ldb + col;
-    const TapSrcDev* tb = s_tbl + sub * im.max_taps;
+    const int16_t(*ss)[NS] = s_src + sub * im.max_taps;
 #pragma unroll 4
     for (int t = 0; t < im.max_taps; ++t) {
-      const int n = tb[t].nsrc;
       float acc = 0.f;
-      for (int q = 0; q < n; ++q) acc += mine[tb[t].src[q]];
+#pragma unroll
+      for (int q = 0; q < NS; ++q) acc += mine[ss[t][q]];
       dst[(int64_t)t * im.kc_pad] = __float2bfloat16(acc);
     }
   }
 }
 
 // scratch [nsubs*rows, max_taps*kc_pad] fp32 -> dw in PyTorch layout (sums the slots every original tap was merged into)
-template <int K3, bool TRANSPOSED>
+template <int K3, bool TRANSPOSED, int NS>
 __global__ void __launch_bounds__(256) unpack_wgrad_kernel(const float* __restrict__ scratch, float* __restrict__ dw,
                                                            const InvEntryDev* __restrict__ inv, int A, int B, int nsubs,
                                                            int max_taps, int rows, int kc_pad, int accumulate) {
   constexpr int TA = TRANSPOSED ? 64 : 4, TB = TRANSPOSED ? 4 : 64;
   constexpr int kAP = TB + 1;                        // pitch along a inside a slot
   constexpr int kSlotPitch = (TA * kAP) | 1;
-  extern __shared__ float tile[];                    // [nsubs*max_taps][kSlotPitch], element (a_off, b_off) at a_off*kAP + b_off
-  __shared__ InvEntryDev s_inv[K3];
+  extern __shared__ float tile[];                    // [nslots + 1][kSlotPitch]; the extra slot is all zeros
+  __shared__ int16_t s_slot[K3][NS];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int a0 = blockIdx.x * TA, b0 = blockIdx.y * TB;
-  for (int i = tid; i < K3; i += 256) s_inv[i] = inv[i];
+  const int nslots = nsubs * max_taps;
+  for (int i = tid; i < K3 * NS; i += 256) {
+    const InvEntryDev& e = inv[i / NS];
+    const int q = i % NS;
+    s_slot[i / NS][q] = (int16_t)(q < e.n ? e.sub[q] * max_taps + e.tap[q] : nslots);
+  }
+  for (int i = tid; i < kSlotPitch; i += 256) tile[nslots * kSlotPitch + i] = 0.f;
   const int64_t ldb = (int64_t)max_taps * kc_pad;
   {
     const int ci = tid & 63, ri = tid >> 6;
@@ -221,12 +236,14 @@ __global__ void __launch_bounds__(256) unpack_wgrad_kernel(const float* __restri
     const int a = a0 + al;
     if (a >= A) continue;
     float* dst = dw + ((int64_t)a * B + b0) * K3;
+    const float* trow = tile + al * kAP;
+#pragma unroll 2
     for (int idx = lane; idx < TB * K3; idx += 32) {
       const int bl = idx / K3, k = idx - bl * K3;
       if (b0 + bl >= B) continue;
-      const InvEntryDev& e = s_inv[k];
       float acc = 0.f;
-      for (int q = 0; q < e.n; ++q) acc += tile[(e.sub[q] * max_taps + e.tap[q]) * kSlotPitch + al * kAP + bl];
+#pragma unroll
+      for (int q = 0; q < NS; ++q) acc += trow[s_slot[k][q] * kSlotPitch + bl];
       if (accumulate) dst[idx] += acc; else dst[idx] = acc;
     }
   }
@@ -294,6 +311,7 @@ struct petsyn_conv_plan {
   petsyn::GemmSide fprop, dgrad;
   // wgrad (uses the fprop program)
   petsyn::InvEntryDev* d_inv = nullptr;
+  int inv_max = 1;              // max number of packed slots one original tap contributes to
   int wg_box_w = 0, wg_box_h = 0, wg_box_d = 0;
   int wg_block_n = 128, wg_ksplit = 1;
   const void* wg_key_x = nullptr; const void* wg_key_g = nullptr; const void* wg_key_s = nullptr;
@@ -527,66 +545,75 @@ static PackImage make_image(const GemmSide& g, void* out) {
   return im;
 }
 
-template <int K3, bool T>
+static int max_nsrc(const GemmSide& g) {
+  size_t m = 1;
+  for (auto& sp : g.prog.subs)
+    for (auto& t : sp) m = std::max(m, t.src.size());
+  return (int)m;
+}
+
+template <int K3, bool T, int NS>
 static int32_t launch_pack_t(const float* w, int A, int B, const PackImage& im, cudaStream_t st) {
   constexpr int TA = T ? 64 : 4, TB = T ? 4 : 64;
-  constexpr size_t smem = (size_t)TA * ((TB * (K3 | 1)) | 1) * sizeof(float);
+  constexpr int K3P = (K3 & 1) ? K3 + 2 : K3 + 1;
+  constexpr size_t smem = (size_t)TA * ((TB * K3P) | 1) * sizeof(float);
   static bool attr = false;
   if (!attr) {
-    PETSYN_CHECK_CUDA(cudaFuncSetAttribute(pack_weights_kernel<K3, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PETSYN_CHECK_CUDA(
+        cudaFuncSetAttribute(pack_weights_kernel<K3, T, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr = true;
   }
   // the tile grid also covers the zero padding of the image's column dimension
   const int amax = T ? std::max(A, im.kc_pad) : A, bmax = T ? B : std::max(B, im.kc_pad);
   dim3 grid((unsigned)((amax + TA - 1) / TA), (unsigned)((bmax + TB - 1) / TB));
-  pack_weights_kernel<K3, T><<<grid, 256, smem, st>>>(w, A, B, im);
+  pack_weights_kernel<K3, T, NS><<<grid, 256, smem, st>>>(w, A, B, im);
   return check_launch("pack_weights_kernel");
 }
 
-static int32_t launch_pack(int k3, bool transposed, const float* w, int A, int B, const PackImage& im, cudaStream_t st) {
-#define PETSYN_PACK_CASE(K)                                                        \
-  case K: return transposed ? launch_pack_t<K, true>(w, A, B, im, st) : launch_pack_t<K, false>(w, A, B, im, st);
-  switch (k3) {
-    PETSYN_PACK_CASE(1)
-    PETSYN_PACK_CASE(8)
-    PETSYN_PACK_CASE(27)
-    PETSYN_PACK_CASE(64)
-    default: return fail(PETSYN_EINVAL, "unsupported kernel volume %d", k3);
-  }
+static int32_t launch_pack(int k3, bool transposed, int ns, const float* w, int A, int B, const PackImage& im,
+                           cudaStream_t st) {
+#define PETSYN_PACK_CASE(K, NS)                                                           \
+  if (k3 == K && ns <= NS)                                                                \
+    return transposed ? launch_pack_t<K, true, NS>(w, A, B, im, st) : launch_pack_t<K, false, NS>(w, A, B, im, st);
+  PETSYN_PACK_CASE(1, 1)
+  PETSYN_PACK_CASE(8, 1)
+  PETSYN_PACK_CASE(27, 1)
+  PETSYN_PACK_CASE(27, 8)
+  PETSYN_PACK_CASE(64, 1)
 #undef PETSYN_PACK_CASE
+  return fail(PETSYN_EINVAL, "unsupported kernel volume %d / merge factor %d", k3, ns);
 }
 
-template <int K3, bool T>
+template <int K3, bool T, int NS>
 static int32_t launch_unpack_t(const float* scratch, float* dw, const InvEntryDev* inv, int A, int B, const GemmSide& f,
                                int accumulate, cudaStream_t st) {
   constexpr int TA = T ? 64 : 4, TB = T ? 4 : 64;
-  const size_t smem = (size_t)f.subs.size() * f.prog.max_taps * ((TA * (TB + 1)) | 1) * sizeof(float);
+  const size_t smem = ((size_t)f.subs.size() * f.prog.max_taps + 1) * ((TA * (TB + 1)) | 1) * sizeof(float);
   static size_t smem_set = 0;
   if (smem > smem_set) {
     PETSYN_CHECK_CUDA(
-        cudaFuncSetAttribute(unpack_wgrad_kernel<K3, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        cudaFuncSetAttribute(unpack_wgrad_kernel<K3, T, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     smem_set = smem;
   }
   dim3 grid((unsigned)((A + TA - 1) / TA), (unsigned)((B + TB - 1) / TB));
-  unpack_wgrad_kernel<K3, T><<<grid, 256, smem, st>>>(scratch, dw, inv, A, B, (int)f.subs.size(), f.prog.max_taps, f.R,
-                                                      f.kc_pad, accumulate);
+  unpack_wgrad_kernel<K3, T, NS><<<grid, 256, smem, st>>>(scratch, dw, inv, A, B, (int)f.subs.size(), f.prog.max_taps,
+                                                          f.R, f.kc_pad, accumulate);
   return check_launch("unpack_wgrad_kernel");
 }
 
-static int32_t launch_unpack(int k3, bool transposed, const float* scratch, float* dw, const InvEntryDev* inv, int A,
-                             int B, const GemmSide& f, int accumulate, cudaStream_t st) {
-#define PETSYN_UNPACK_CASE(K)                                                                       \
-  case K:                                                                                           \
-    return transposed ? launch_unpack_t<K, true>(scratch, dw, inv, A, B, f, accumulate, st)         \
-                      : launch_unpack_t<K, false>(scratch, dw, inv, A, B, f, accumulate, st);
-  switch (k3) {
-    PETSYN_UNPACK_CASE(1)
-    PETSYN_UNPACK_CASE(8)
-    PETSYN_UNPACK_CASE(27)
-    PETSYN_UNPACK_CASE(64)
-    default: return fail(PETSYN_EINVAL, "unsupported kernel volume %d", k3);
-  }
+static int32_t launch_unpack(int k3, bool transposed, int ns, const float* scratch, float* dw, const InvEntryDev* inv,
+                             int A, int B, const GemmSide& f, int accumulate, cudaStream_t st) {
+#define PETSYN_UNPACK_CASE(K, NS)                                                                          \
+  if (k3 == K && ns <= NS)                                                                                 \
+    return transposed ? launch_unpack_t<K, true, NS>(scratch, dw, inv, A, B, f, accumulate, st)            \
+                      : launch_unpack_t<K, false, NS>(scratch, dw, inv, A, B, f, accumulate, st);
+  PETSYN_UNPACK_CASE(1, 1)
+  PETSYN_UNPACK_CASE(8, 1)
+  PETSYN_UNPACK_CASE(27, 1)
+  PETSYN_UNPACK_CASE(27, 8)
+  PETSYN_UNPACK_CASE(64, 1)
 #undef PETSYN_UNPACK_CASE
+  return fail(PETSYN_EINVAL, "unsupported kernel volume %d / merge factor %d", k3, ns);
 }
 
 }  // namespace petsyn
@@ -685,6 +712,7 @@ int32_t petsyn_conv_plan_create(const petsyn_conv_desc* d, petsyn_conv_plan** ou
           InvEntryDev& e = inv[src];
           if (e.n >= 8) { rc = fail(PETSYN_EINVAL, "tap appears in more than 8 merged slots"); break; }
           e.sub[e.n] = (int)s2; e.tap[e.n] = (int)t; ++e.n;
+          pl->inv_max = std::max(pl->inv_max, e.n);
         }
     if (!rc) rc = upload(inv.data(), inv.size() * sizeof(InvEntryDev), (void**)&pl->d_inv);
     choose_box(f.out_w, f.out_h, f.out_d, 64, true, &pl->wg_box_w, &pl->wg_box_h, &pl->wg_box_d);
@@ -770,8 +798,10 @@ int32_t petsyn_conv_pack_weights(petsyn_conv_plan* pl, const float* w, void* pac
   const int A = convt ? pl->desc.cin : pl->desc.cout, B = convt ? pl->desc.cout : pl->desc.cin;
   cudaStream_t st = as_stream(stream);
   int32_t rc = PETSYN_OK;
-  if (packed_fprop) rc = launch_pack(pl->k3, /*transposed=*/convt, w, A, B, make_image(pl->fprop, packed_fprop), st);
-  if (!rc && packed_dgrad) rc = launch_pack(pl->k3, /*transposed=*/!convt, w, A, B, make_image(pl->dgrad, packed_dgrad), st);
+  if (packed_fprop)
+    rc = launch_pack(pl->k3, /*transposed=*/convt, max_nsrc(pl->fprop), w, A, B, make_image(pl->fprop, packed_fprop), st);
+  if (!rc && packed_dgrad)
+    rc = launch_pack(pl->k3, /*transposed=*/!convt, max_nsrc(pl->dgrad), w, A, B, make_image(pl->dgrad, packed_dgrad), st);
   return rc;
 }
 
@@ -857,7 +887,8 @@ int32_t petsyn_conv_wgrad(petsyn_conv_plan* pl, const void* x, const void* dy, v
   {
     const bool convt = pl->desc.op == PETSYN_OP_CONVT;
     const int A = convt ? pl->desc.cin : pl->desc.cout, B = convt ? pl->desc.cout : pl->desc.cin;
-    return launch_unpack(pl->k3, convt, reinterpret_cast<const float*>(scratch), dw, pl->d_inv, A, B, f, accumulate, st);
+    return launch_unpack(pl->k3, convt, pl->inv_max, reinterpret_cast<const float*>(scratch), dw, pl->d_inv, A, B, f,
+                         accumulate, st);
   }
 }
 

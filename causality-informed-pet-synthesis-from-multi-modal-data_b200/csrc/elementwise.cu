@@ -60,7 +60,7 @@ __device__ __forceinline__ float act_grad(float b, int act, float slope) {
   }
 }
 
-constexpr int kRowUnroll = 4;   // independent 16-byte loads in flight per thread
+constexpr int kRowUnroll = 2;   // independent 16-byte loads in flight per thread
 
 // Thread layout shared by the row-streaming kernels: cpt = C/8 threads span the channels, blockDim/cpt rows in flight.
 struct RowIter {

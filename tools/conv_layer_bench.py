@@ -1,0 +1,84 @@
+#!/usr/bin/env python
+"""Time one convolution layer of the hot path in isolation (CUDA events, L2 flushed between launches).
+
+    python tools/conv_layer_bench.py --layer up1 [--pass fprop|dgrad|wgrad|all] [--iters 20] [--once]
+
+Layers are the UnetGenerator3d(1,1,4) convs at 96x112x96, batch 1.  ``--once`` runs each pass a few
+times without timing -- the form used under ``ncu --set full`` (profiles/).
+"""
+import argparse
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+import petsyn  # noqa: E402
+
+ops = petsyn.ops
+LAYERS = {
+    # name: (op, n, d, h, w, cin, cout, k, s, p)   -- dims of the stored input
+    "down1": (ops.OP_CONV, 1, 48, 56, 48, 128, 256, 4, 2, 1),
+    "down2": (ops.OP_CONV, 1, 24, 28, 24, 256, 512, 4, 2, 1),
+    "down3": (ops.OP_CONV, 1, 12, 14, 12, 512, 512, 4, 2, 1),
+    "up3": (ops.OP_UPCONV, 1, 6, 7, 6, 512, 512, 3, 1, 1),
+    "up2": (ops.OP_UPCONV, 1, 12, 14, 12, 1024, 256, 3, 1, 1),
+    "up1": (ops.OP_UPCONV, 1, 24, 28, 24, 512, 128, 3, 1, 1),
+}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--layer", default="up1", choices=sorted(LAYERS))
+    ap.add_argument("--pass", dest="which", default="all", choices=["fprop", "dgrad", "wgrad", "all"])
+    ap.add_argument("--iters", type=int, default=20)
+    ap.add_argument("--batch", type=int, default=1)
+    ap.add_argument("--once", action="store_true")
+    args = ap.parse_args()
+    op, n, d, h, w, cin, cout, k, s, p = LAYERS[args.layer]
+    n = args.batch
+    dev = torch.device("cuda:0")
+    plan = ops.ConvPlan(op, n, d, h, w, cin, cout, k, s, p)
+    g = torch.Generator().manual_seed(0)
+    wt = (torch.randn(cout, cin, k, k, k, generator=g) / (cin * k ** 3) ** 0.5).to(dev)
+    plan.pack(wt)
+    x = torch.randn(n, d, h, w, cin, generator=g).to(dev).to(torch.bfloat16)
+    od, oh, ow = plan.out_dims
+    y = torch.empty(n, od, oh, ow, cout, dtype=torch.bfloat16, device=dev)
+    dy = torch.randn(n, od, oh, ow, cout, generator=g).to(dev).to(torch.bfloat16)
+    dx = torch.empty_like(x)
+    dw = torch.empty_like(wt)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
+    passes = {"fprop": lambda: plan.fprop(x, y), "dgrad": lambda: plan.dgrad(dy, dx),
+              "wgrad": lambda: plan.wgrad(x, dy, dw)}
+    todo = list(passes) if args.which == "all" else [args.which]
+    out = {"layer": args.layer, "batch": n, "flops_algorithmic": plan.flops_algorithmic,
+           "flops_executed": plan.flops_executed}
+    for name in todo:
+        fn = passes[name]
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        if args.once:
+            continue
+        ts = []
+        for _ in range(args.iters):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        ts.sort()
+        med = ts[len(ts) // 2]
+        out[name] = {"ms_median": med, "ms_min": ts[0], "tflops_executed": plan.flops_executed / med / 1e9,
+                     "tflops_algorithmic": plan.flops_algorithmic / med / 1e9}
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()
