@@ -206,8 +206,8 @@ def run_petsyn(args, ngf, shape, batch):
     final_loss = float(loss.item())
 
     # ---- timed region 2: end-to-end from pinned host memory, loss read back every step ----
-    x_dev = trainer.static_x if trainer.graph is not None else torch.empty_like(resident[0][0])
-    t_dev = trainer.static_t if trainer.graph is not None else torch.empty_like(resident[0][1])
+    x_dev = trainer.static_x if trainer.graphs is not None else torch.empty_like(resident[0][0])
+    t_dev = trainer.static_t if trainer.graphs is not None else torch.empty_like(resident[0][1])
     loss_host = torch.zeros(1, dtype=torch.float32).pin_memory()
     barrier()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -260,7 +260,7 @@ def run_petsyn(args, ngf, shape, batch):
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": args.workload, "model": f"UnetGenerator3d(1,1,num_downs=4,ngf={ngf})",
                        "volume": list(shape), "per_gpu_batch": batch, "global_batch": batch * world,
-                       "parallelism": f"dp{world}", "optimizer": "Adam(lr=5e-4)", "loss": "L1", "cuda_graph": trainer.graph is not None,
+                       "parallelism": f"dp{world}", "optimizer": "Adam(lr=5e-4)", "loss": "L1", "cuda_graph": trainer.graphs is not None,
                        "l2": "per-step working set (weights+packed operands+activations > 1 GB) exceeds the 126 MB L2; "
                              "inputs rotate over 4 distinct batches; no explicit flush"},
             "e2e": {"value": e2e_s, "unit": UNIT, "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": 4,

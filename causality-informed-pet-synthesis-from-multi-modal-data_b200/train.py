@@ -116,7 +116,8 @@ class Unet3dTrainer:
         self.v = torch.zeros_like(self.arena.p)
         self.step_count = 0
         self.step_dev = torch.zeros(1, dtype=torch.int32, device=dev)
-        self.graph = None
+        self.graphs = None
+        self.opt_graph = None
         self.static_x = self.static_t = None
         self.loss = torch.zeros(1, dtype=torch.float32, device=dev)
         self.dy = torch.empty(example_input.shape, dtype=torch.float32, device=dev)
@@ -141,37 +142,57 @@ class Unet3dTrainer:
                 dist.broadcast(b, src=0, group=self.pg)
 
     # ------------------------------------------------------------------------------------------------ step
-    def _step_impl(self, x: torch.Tensor, target: torch.Tensor, timers=None) -> torch.Tensor:
-        eng = self.eng
-        y = eng.forward(x, save=True, timers=timers, clone_output=False)
+    def _forward_and_loss(self, x: torch.Tensor, target: torch.Tensor, timers=None) -> None:
+        y = self.eng.forward(x, save=True, timers=timers, clone_output=False)
         self.loss.zero_()
         ops.l1_loss_fwd_bwd(y, target, self.loss, self.dy)
-        eng.backward(self.dy, out=self.arena.grad_views, on_ready=self.bucketer.on_ready, timers=timers)
-        self.bucketer.wait_all()
+
+    def _optimizer(self) -> None:
         self.step_dev.add_(1)
         ops.adam_step(self.arena.p, self.arena.g, self.m, self.v, self.lr, self.betas[0], self.betas[1], self.eps, 0,
                       step_dev=self.step_dev)
-        eng.mark_weights_dirty()
+        self.eng.mark_weights_dirty()
+
+    def _step_impl(self, x: torch.Tensor, target: torch.Tensor, timers=None) -> torch.Tensor:
+        self._forward_and_loss(x, target, timers)
+        self.eng.backward(self.dy, out=self.arena.grad_views, on_ready=self.bucketer.on_ready, timers=timers)
+        self.bucketer.wait_all()
+        self._optimizer()
         return self.loss
 
     def step(self, x: torch.Tensor, target: torch.Tensor, timers=None) -> torch.Tensor:
         """One optimisation step (zero_grad -> fwd -> L1 -> bwd -> [all-reduce] -> Adam); returns the device loss
-        tensor of this rank's micro-batch.  Replays the captured CUDA graph when ``capture()`` has been called."""
+        tensor of this rank's micro-batch.  Replays the captured CUDA graph(s) when ``capture()`` has been called."""
         self.step_count += 1
-        if self.graph is not None and timers is None:
-            if x.data_ptr() != self.static_x.data_ptr():
-                self.static_x.copy_(x, non_blocking=True)
-            if target.data_ptr() != self.static_t.data_ptr():
-                self.static_t.copy_(target, non_blocking=True)
-            self.graph.replay()
-            return self.loss
-        return self._step_impl(x, target, timers)
+        if self.graphs is None or timers is not None:
+            return self._step_impl(x, target, timers)
+        if x.data_ptr() != self.static_x.data_ptr():
+            self.static_x.copy_(x, non_blocking=True)
+        if target.data_ptr() != self.static_t.data_ptr():
+            self.static_t.copy_(target, non_blocking=True)
+        for graph, last_param in self.graphs:
+            graph.replay()
+            if last_param is not None:
+                self.bucketer.on_ready(last_param)       # eager NCCL launch between graph segments
+        if self.world > 1:
+            self.bucketer.wait_all()
+            self.opt_graph.replay()
+        return self.loss
+
+    @property
+    def graph(self):
+        return self.graphs
 
     def capture(self, warmup: int = 3) -> None:
-        """Capture the whole training step into one CUDA graph (the step is ~100 short kernels; launching them one by
-        one from Python costs more host time than the GPU needs to run them).  Parameters, optimiser state and
-        BatchNorm buffers are restored after the warm-up steps that capture requires, so capture() has no side effect
-        on training state.  Feed ``static_x`` / ``static_t`` directly to skip the device-to-device input copy."""
+        """Capture the training step into CUDA graphs (the step is ~100 short kernels; launching them one by one from
+        Python costs more host time than the GPU needs to run them).
+
+        Single GPU: one graph for the whole step.  Data parallel: the collectives stay outside the graphs -- the step
+        is cut at every gradient-bucket boundary into [fwd + loss + backward-until-bucket-0] [..until bucket 1] ...
+        [Adam]; after each segment the bucket's NCCL all-reduce is launched on the side stream, overlapping the next
+        segment.  Parameters, optimiser state and BatchNorm buffers are restored after the warm-up steps capture
+        needs, so capture() has no side effect on training state.  Write inputs into ``static_x`` / ``static_t`` to
+        skip the device-to-device input copy."""
         snap = [t.clone() for t in (self.arena.p, self.m, self.v, self.step_dev)]
         bufs = [b.clone() for b in self.model.buffers()]
         count = self.step_count
@@ -183,15 +204,40 @@ class Unet3dTrainer:
             for _ in range(warmup):
                 self._step_impl(self.static_x, self.static_t)
         torch.cuda.current_stream().wait_stream(side)
-        graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph):
-            self._step_impl(self.static_x, self.static_t)
+        torch.cuda.synchronize(self.dev)
+        graphs = []
+        pool = torch.cuda.graph_pool_handle()
+        if self.world == 1:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, pool=pool):
+                self._step_impl(self.static_x, self.static_t)
+            graphs.append((g, None))
+            self.opt_graph = None
+        else:
+            closers = set(self.bucketer._bucket_of_last)
+            it = self.eng.backward_iter(self.dy, self.arena.grad_views)
+            g = torch.cuda.CUDAGraph()
+            ctx = torch.cuda.graph(g, pool=pool)
+            ctx.__enter__()
+            self._forward_and_loss(self.static_x, self.static_t)
+            for prm in it:
+                if id(prm) in closers:
+                    ctx.__exit__(None, None, None)
+                    graphs.append((g, prm))
+                    g = torch.cuda.CUDAGraph()
+                    ctx = torch.cuda.graph(g, pool=pool)
+                    ctx.__enter__()
+            # the last parameter always closes the last bucket, so the open capture only holds trailing kernels (none)
+            self._optimizer()
+            ctx.__exit__(None, None, None)
+            self.opt_graph = g
         for dst, src in zip((self.arena.p, self.m, self.v, self.step_dev), snap):
             dst.copy_(src)
         for dst, src in zip(self.model.buffers(), bufs):
             dst.copy_(src)
         self.step_count = count
-        self.graph = graph
+        self.eng.mark_weights_dirty()
+        self.graphs = graphs
 
     def grad_norm(self) -> float:
         out = torch.zeros(1, dtype=torch.float32, device=self.dev)

@@ -321,21 +321,29 @@ class _Engine:
         """Backward of ``forward(save=True)``.  Gradients are written (not accumulated) into ``out[id(param)]`` when
         given, else into engine-owned buffers whose clones are returned in ``param_list()`` order.  ``on_ready(param)``
         is called right after the kernels producing that parameter's gradient have been enqueued."""
-        L = self.L
-        lv = self.lv
         if out is None:
             grads = self._grad_buffers()
             slot: Dict[int, torch.Tensor] = {id(p): g for p, g in zip(self.param_list(), grads)}
         else:
             grads = None
             slot = out
-        ready = on_ready if on_ready is not None else (lambda p: None)
+        for p in self.backward_iter(dy, slot, timers):
+            if on_ready is not None:
+                on_ready(p)
+        return [g.clone() for g in grads] if grads is not None else []
+
+    def backward_iter(self, dy: torch.Tensor, slot: Dict[int, torch.Tensor], timers=None):
+        """Generator form of backward: enqueues kernels and yields each parameter as soon as the kernels producing
+        its gradient (into ``slot[id(param)]``) have been enqueued.  The trainer uses the yield points to cut the
+        backward pass into CUDA-graph segments with a bucket all-reduce launched between them."""
+        L = self.L
+        lv = self.lv
         gw = lambda conv: slot[id(conv.weight)]
         n = self.shape[0]
         d1, h1, w1 = self.dims[1]
         cat1 = self.cat[1].view(n, d1, h1, w1, 2 * self.outer[1])
         self.head.backward(cat1, self.y, dy, self.dcat[1], gw(lv[0]._refs["upconv"]))
-        ready(lv[0]._refs["upconv"].weight)
+        yield lv[0]._refs["upconv"].weight
         # ---- up path, outer -> inner ----
         for i in range(1, L):
             nm = self.unorm[i]
@@ -343,13 +351,13 @@ class _Engine:
             ops.norm_act_bwd(self.zu[i], nm.scale, nm.shift, nm.mean, nm.rstd, nm.bn.weight, self.dcat[i], 2 * c, 0,
                              ops.ACT_RELU, None, 0, 0, ops.ACT_NONE, LRELU_SLOPE, nm.bsums, self.dzu[i],
                              slot[id(nm.bn.weight)], slot[id(nm.bn.bias)], self.rows[i], c)
-            ready(nm.bn.weight)
-            ready(nm.bn.bias)
+            yield nm.bn.weight
+            yield nm.bn.bias
             src = self.r if i == L - 1 else self.cat[i + 1]
             dsrc = self.dr if i == L - 1 else self.dcat[i + 1]
             with _timed(timers, f"up{i}.wgrad"):
                 self.up[i].wgrad(src, self.dzu[i], gw(lv[i]._refs["upconv"]))
-            ready(lv[i]._refs["upconv"].weight)
+            yield lv[i]._refs["upconv"].weight
             with _timed(timers, f"up{i}.dgrad"):
                 self.up[i].dgrad(self.dzu[i], dsrc)
         # ---- innermost: through ReLU(z) ----
@@ -360,7 +368,7 @@ class _Engine:
         for i in range(L - 1, 0, -1):
             with _timed(timers, f"down{i}.wgrad"):
                 self.down[i].wgrad(self.a[i], self.dz[i], gw(lv[i]._refs["downconv"]))
-            ready(lv[i]._refs["downconv"].weight)
+            yield lv[i]._refs["downconv"].weight
             with _timed(timers, f"down{i}.dgrad"):
                 self.down[i].dgrad(self.dz[i], self.da[i])
             prev = self.dnorm[i - 1]
@@ -372,11 +380,10 @@ class _Engine:
                              slot[id(prev.bn.weight)] if prev else None, slot[id(prev.bn.bias)] if prev else None,
                              self.rows[i], c)
             if prev is not None:
-                ready(prev.bn.weight)
-                ready(prev.bn.bias)
+                yield prev.bn.weight
+                yield prev.bn.bias
         self.stem.wgrad(self.dz[0], gw(lv[0]._refs["downconv"]))
-        ready(lv[0]._refs["downconv"].weight)
-        return [g.clone() for g in grads] if grads is not None else []
+        yield lv[0]._refs["downconv"].weight
 
 
 class _timed:
