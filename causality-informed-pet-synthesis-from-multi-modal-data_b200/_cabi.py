@@ -46,6 +46,20 @@ class ConvDesc(C.Structure):
     ]
 
 
+class NormActDesc(C.Structure):
+    """``petsyn_normact_desc`` (include/petsyn.h)."""
+    _fields_ = [
+        ("z", C.c_void_p), ("rows", C.c_int64), ("c", C.c_int32), ("nsamples", C.c_int32),
+        ("per_sample_stats", C.c_int32),
+        ("scale", C.c_void_p), ("shift", C.c_void_p), ("mean", C.c_void_p), ("rstd", C.c_void_p), ("gamma", C.c_void_p),
+        ("t1", C.c_void_p), ("t1_cstride", C.c_int32), ("t1_coff", C.c_int32), ("act1", C.c_int32),
+        ("t2", C.c_void_p), ("t2_cstride", C.c_int32), ("t2_coff", C.c_int32), ("act2", C.c_int32),
+        ("slope", C.c_float),
+        ("res", C.c_void_p), ("res_cstride", C.c_int32), ("res_coff", C.c_int32), ("res_accumulate", C.c_int32),
+        ("sums", C.c_void_p), ("dz", C.c_void_p), ("dgamma", C.c_void_p), ("dbeta", C.c_void_p),
+    ]
+
+
 _vp, _i32, _i64, _f32, _sz = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_size_t
 
 # name -> (restype, argtypes); every symbol declared in include/petsyn.h
@@ -65,7 +79,19 @@ SIGNATURES = {
     "petsyn_conv_pack_weights": (_i32, [_vp, _vp, _vp, _vp, _vp]),
     "petsyn_conv_fprop": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp]),
     "petsyn_conv_dgrad": (_i32, [_vp, _vp, _vp, _vp, _vp]),
+    "petsyn_conv_dgrad_accumulate": (_i32, [_vp, _vp, _vp, _vp, _vp]),
     "petsyn_conv_wgrad": (_i32, [_vp, _vp, _vp, _vp, _vp, _i32, _vp]),
+    "petsyn_stem_col2im_k4s2": (_i32, [_vp, _vp, _i32, _i32, _i32, _i32, _vp]),
+    "petsyn_concat_latent": (_i32, [_vp, _vp, _vp, _i64, _i32, _i32, _i32, _vp]),
+    "petsyn_take_channel0": (_i32, [_vp, _vp, _i64, _i32, _vp]),
+    "petsyn_put_channel0_grad": (_i32, [_vp, _vp, _vp, _i64, _i32, _i32, _vp]),
+    "petsyn_norm_stats": (_i32, [_vp, _vp, _i64, _i32, _i32, _vp]),
+    "petsyn_norm_finalize": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _f32, _f32, _i32,
+                                    _vp]),
+    "petsyn_normact_fwd": (_i32, [C.POINTER(NormActDesc), _vp]),
+    "petsyn_normact_bwd": (_i32, [C.POINTER(NormActDesc), _vp]),
+    "petsyn_add_slice": (_i32, [_vp, _i32, _i32, _vp, _i32, _i32, _i64, _i32, _i32, _vp]),
+    "petsyn_colsum": (_i32, [_vp, _i32, _i32, _vp, _i64, _i32, _vp]),
     "petsyn_stem_im2col_k4s2": (_i32, [_vp, _vp, _i32, _i32, _i32, _i32, _vp]),
     "petsyn_head_gather_tanh": (_i32, [_vp, _vp, _i32, _i32, _i32, _i32, _vp]),
     "petsyn_head_scatter_bwd": (_i32, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp]),

@@ -252,7 +252,8 @@ __global__ void __launch_bounds__(256) unpack_wgrad_kernel(const float* __restri
 // split-K finish: fp32 [rows, C] (contiguous) -> act(x + bias) as bf16 into a channel slice
 __global__ void __launch_bounds__(256) splitk_finish_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst,
                                                             int64_t rows, int C, int cstride, int coff,
-                                                            const float* __restrict__ bias, int act, float slope) {
+                                                            const float* __restrict__ bias, int act, float slope,
+                                                            int accumulate) {
   const int cpt = C / 8;
   const int64_t total = rows * cpt;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -264,6 +265,16 @@ __global__ void __launch_bounds__(256) splitk_finish_kernel(const float* __restr
     for (int q = 0; q < 8; ++q) {
       if (bias) f[q] += __ldg(bias + c + q);
       f[q] = apply_act(f[q], act, slope);
+    }
+    if (accumulate) {
+      const uint4 old = *reinterpret_cast<const uint4*>(dst + r * cstride + coff + c);
+      const __nv_bfloat162* ob = reinterpret_cast<const __nv_bfloat162*>(&old);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float2 of = __bfloat1622float2(ob[q]);
+        f[2 * q] += of.x;
+        f[2 * q + 1] += of.y;
+      }
     }
     uint4 o;
     __nv_bfloat162 b0 = __floats2bfloat162_rn(f[0], f[1]), b1 = __floats2bfloat162_rn(f[2], f[3]);
@@ -284,6 +295,7 @@ struct GemmSide {           // one gather-form GEMM (fprop or dgrad)
   int box_w = 0, box_h = 0, box_d = 0;
   int block_n = 128;
   bool out_fp32 = false;
+  bool accumulate = false;    // add into the destination (bf16 TMA reduction) instead of overwriting
   int ksplit = 1;             // >1: fp32 split-K through `workspace`, finished by splitk_finish_kernel
   void* workspace = nullptr;
   size_t workspace_bytes = 0;
@@ -425,6 +437,15 @@ static int32_t launch_igemm(const GemmSide& g, int batch, cudaStream_t st) {
   grid.x = (unsigned)(g.params.tiles_w * g.params.tiles_h * g.params.tiles_d * batch);
   grid.y = (unsigned)((g.R + g.block_n - 1) / g.block_n);
   grid.z = (unsigned)(g.subs.size() * g.ksplit);
+  if (g.accumulate && g.ksplit == 1) {
+    switch (g.block_n) {
+      case 16: return launch_igemm_bn<16, OUT_BF16_REDUCE>(g, grid, st);
+      case 32: return launch_igemm_bn<32, OUT_BF16_REDUCE>(g, grid, st);
+      case 64: return launch_igemm_bn<64, OUT_BF16_REDUCE>(g, grid, st);
+      case 128: return launch_igemm_bn<128, OUT_BF16_REDUCE>(g, grid, st);
+      default: return fail(PETSYN_EINVAL, "unsupported BLOCK_N %d for accumulating output", g.block_n);
+    }
+  }
   if (g.ksplit > 1) {
     switch (g.block_n) {
       case 16: return launch_igemm_bn<16, OUT_F32_REDUCE>(g, grid, st);
@@ -467,7 +488,7 @@ static int32_t run_side(GemmSide& g, const ViewSpec& vc, void* c, const float* b
     const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>((total + 255) / 256, 148 * 8));
     splitk_finish_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const float*>(g.workspace),
                                                  reinterpret_cast<__nv_bfloat16*>(c), g.out_rows_full, g.R, vc.cstride,
-                                                 vc.coff, bias, act, slope);
+                                                 vc.coff, bias, act, slope, g.accumulate ? 1 : 0);
     return check_launch("splitk_finish_kernel");
   }
   return launch_igemm(g, batch, st);
@@ -818,6 +839,15 @@ int32_t petsyn_conv_dgrad(petsyn_conv_plan* pl, const void* dy, const void* pack
   int32_t rc = bind_side(pl->dgrad, pl->vdy, pl->vdx, dy, packed, dx, nullptr, PETSYN_ACT_NONE, 0.f);
   if (rc) return rc;
   return run_side(pl->dgrad, pl->vdx, dx, nullptr, PETSYN_ACT_NONE, 0.f, pl->desc.n, as_stream(stream));
+}
+
+int32_t petsyn_conv_dgrad_accumulate(petsyn_conv_plan* pl, const void* dy, const void* packed, void* dx, void* stream) {
+  PETSYN_REQUIRE(pl && dy && packed && dx, "null argument");
+  pl->dgrad.accumulate = true;
+  int32_t rc = bind_side(pl->dgrad, pl->vdy, pl->vdx, dy, packed, dx, nullptr, PETSYN_ACT_NONE, 0.f);
+  if (!rc) rc = run_side(pl->dgrad, pl->vdx, dx, nullptr, PETSYN_ACT_NONE, 0.f, pl->desc.n, as_stream(stream));
+  pl->dgrad.accumulate = false;
+  return rc;
 }
 
 int32_t petsyn_conv_wgrad(petsyn_conv_plan* pl, const void* x, const void* dy, void* scratch, float* dw,

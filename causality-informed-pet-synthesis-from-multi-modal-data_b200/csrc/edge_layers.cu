@@ -40,6 +40,39 @@ __global__ void __launch_bounds__(256) stem_im2col_kernel(const float* __restric
   }
 }
 
+// dx[i] = sum over (o, tap) with 2o + k - 1 == i of dpatches[o][tap]: two (o, k) pairs per axis -> 8 terms
+__global__ void __launch_bounds__(256) stem_col2im_kernel(const __nv_bfloat16* __restrict__ dp, float* __restrict__ dx,
+                                                          int N, int D, int H, int W) {
+  const int OD = D / 2, OH = H / 2, OW = W / 2;
+  const int64_t total = (int64_t)N * D * H * W;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t q = i;
+    const int iw = (int)(q % W); q /= W;
+    const int ih = (int)(q % H); q /= H;
+    const int id = (int)(q % D); q /= D;
+    const int n = (int)q;
+    float acc = 0.f;
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+      const int kd = ((id + 1) & 1) + 2 * a, od = (id + 1 - kd) / 2;     // 2*od + kd - 1 == id
+      if (od < 0 || od >= OD) continue;
+#pragma unroll
+      for (int b = 0; b < 2; ++b) {
+        const int kh = ((ih + 1) & 1) + 2 * b, oh = (ih + 1 - kh) / 2;
+        if (oh < 0 || oh >= OH) continue;
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          const int kw = ((iw + 1) & 1) + 2 * c, ow = (iw + 1 - kw) / 2;
+          if (ow < 0 || ow >= OW) continue;
+          const int64_t o = (((int64_t)n * OD + od) * OH + oh) * OW + ow;
+          acc += __bfloat162float(dp[o * 64 + (kd * 4 + kh) * 4 + kw]);
+        }
+      }
+    }
+    dx[i] = acc;
+  }
+}
+
 // y[o] = tanh( sum_k proj[src(o,k)][k] ), src = (o + k - 1) >> 1 on each axis, zero outside the upsampled volume
 __global__ void __launch_bounds__(256) head_gather_tanh_kernel(const float* __restrict__ proj, float* __restrict__ y,
                                                                int N, int D, int H, int W) {
@@ -127,6 +160,38 @@ __global__ void __launch_bounds__(256) head_scatter_bwd_kernel(const float* __re
   }
 }
 
+// ---- one-channel heads / tails of the BMGAN networks -------------------------------------------------------------
+// generator input: cat([t1, z.view(N,8,1,1,1).expand(...)], 1) (bmgan_model.py:76-79) as NDHWC bf16 padded to cpad
+__global__ void __launch_bounds__(256) concat_latent_kernel(const float* __restrict__ x, const float* __restrict__ zvec,
+                                                            __nv_bfloat16* __restrict__ out, int64_t rows_per_sample,
+                                                            int64_t rows, int nz, int cpad) {
+  for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < rows; r += (int64_t)gridDim.x * blockDim.x) {
+    const int n = (int)(r / rows_per_sample);
+    __nv_bfloat16* o = out + r * cpad;
+    o[0] = __float2bfloat16(x[r]);
+    for (int j = 0; j < nz; ++j) o[1 + j] = __float2bfloat16(zvec[n * nz + j]);
+    for (int j = 1 + nz; j < cpad; ++j) o[j] = __float2bfloat16(0.f);
+  }
+}
+// y[r] = src[r, 0]   (channel 0 of a padded fp32 conv output -> contiguous N,1,D,H,W)
+__global__ void __launch_bounds__(256) take_channel0_kernel(const float* __restrict__ src, float* __restrict__ y,
+                                                            int64_t rows, int cpad) {
+  for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < rows; r += (int64_t)gridDim.x * blockDim.x)
+    y[r] = src[r * cpad];
+}
+// dz[r, 0] = dy[r] * (tanh_out ? 1 - y[r]^2 : 1); dz[r, 1:] = 0   (bf16, padded)
+__global__ void __launch_bounds__(256) put_channel0_grad_kernel(const float* __restrict__ y, const float* __restrict__ dy,
+                                                                __nv_bfloat16* __restrict__ dz, int64_t rows, int cpad,
+                                                                int tanh_out) {
+  for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < rows; r += (int64_t)gridDim.x * blockDim.x) {
+    float g = dy[r];
+    if (tanh_out) { const float v = y[r]; g *= 1.f - v * v; }
+    __nv_bfloat16* o = dz + r * cpad;
+    o[0] = __float2bfloat16(g);
+    for (int j = 1; j < cpad; ++j) o[j] = __float2bfloat16(0.f);
+  }
+}
+
 }  // namespace petsyn
 
 using namespace petsyn;
@@ -141,6 +206,44 @@ int32_t petsyn_stem_im2col_k4s2(const float* x, void* patches, int32_t n, int32_
   const int blocks = (int)std::min<int64_t>((total + 255) / 256, 148 * 32);
   stem_im2col_kernel<<<blocks, 256, 0, as_stream(stream)>>>(x, reinterpret_cast<__nv_bfloat16*>(patches), n, d, h, w);
   return check_launch("stem_im2col_kernel");
+}
+
+int32_t petsyn_stem_col2im_k4s2(const void* dpatches, float* dx, int32_t n, int32_t d, int32_t h, int32_t w,
+                                void* stream) {
+  PETSYN_REQUIRE(dpatches && dx, "null argument");
+  PETSYN_REQUIRE(n > 0 && d > 0 && h > 0 && w > 0 && (d % 2 | h % 2 | w % 2) == 0, "stem: dims must be positive and even");
+  const int64_t total = (int64_t)n * d * h * w;
+  const int blocks = (int)std::min<int64_t>((total + 255) / 256, 148 * 32);
+  stem_col2im_kernel<<<blocks, 256, 0, as_stream(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(dpatches), dx, n, d, h,
+                                                            w);
+  return check_launch("stem_col2im_kernel");
+}
+
+int32_t petsyn_concat_latent(const float* x, const float* zvec, void* out, int64_t rows_per_sample, int32_t n,
+                             int32_t nz, int32_t cpad, void* stream) {
+  PETSYN_REQUIRE(x && zvec && out, "null argument");
+  PETSYN_REQUIRE(n > 0 && rows_per_sample > 0 && nz >= 0 && 1 + nz <= cpad && cpad % 8 == 0, "bad channel layout");
+  const int64_t rows = rows_per_sample * n;
+  const int blocks = (int)std::min<int64_t>((rows + 255) / 256, 148 * 16);
+  concat_latent_kernel<<<blocks, 256, 0, as_stream(stream)>>>(x, zvec, reinterpret_cast<__nv_bfloat16*>(out),
+                                                              rows_per_sample, rows, nz, cpad);
+  return check_launch("concat_latent_kernel");
+}
+
+int32_t petsyn_take_channel0(const float* src, float* y, int64_t rows, int32_t cpad, void* stream) {
+  PETSYN_REQUIRE(src && y && rows > 0 && cpad > 0, "bad argument");
+  const int blocks = (int)std::min<int64_t>((rows + 255) / 256, 148 * 16);
+  take_channel0_kernel<<<blocks, 256, 0, as_stream(stream)>>>(src, y, rows, cpad);
+  return check_launch("take_channel0_kernel");
+}
+
+int32_t petsyn_put_channel0_grad(const float* y, const float* dy, void* dz, int64_t rows, int32_t cpad,
+                                 int32_t tanh_out, void* stream) {
+  PETSYN_REQUIRE(dy && dz && rows > 0 && cpad > 0 && (!tanh_out || y), "bad argument");
+  const int blocks = (int)std::min<int64_t>((rows + 255) / 256, 148 * 16);
+  put_channel0_grad_kernel<<<blocks, 256, 0, as_stream(stream)>>>(y, dy, reinterpret_cast<__nv_bfloat16*>(dz), rows, cpad,
+                                                                  tanh_out);
+  return check_launch("put_channel0_grad_kernel");
 }
 
 int32_t petsyn_head_gather_tanh(const float* proj, float* y, int32_t n, int32_t d, int32_t h, int32_t w, void* stream) {

@@ -54,7 +54,7 @@ struct alignas(64) IgemmParams {
   int32_t ksplit;         // CTAs sharing one output tile's K loop (split-K; >1 only with OUT_F32_REDUCE)
 };
 
-enum { OUT_BF16 = 0, OUT_F32 = 1, OUT_F32_REDUCE = 2 };
+enum { OUT_BF16 = 0, OUT_F32 = 1, OUT_F32_REDUCE = 2, OUT_BF16_REDUCE = 3 };
 
 __device__ __forceinline__ float apply_act(float x, int act, float slope) {
   switch (act) {
@@ -79,7 +79,7 @@ struct IgemmCfg {
   static constexpr int kBBytesRaw = BLOCK_N * KCH * 2;
   static constexpr int kBBytes = (kBBytesRaw + 1023) / 1024 * 1024;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kEsz = (OUT_MODE == OUT_BF16) ? 2 : 4;
+  static constexpr int kEsz = (OUT_MODE == OUT_BF16 || OUT_MODE == OUT_BF16_REDUCE) ? 2 : 4;
   // epilogue staging: chunks of kChunkC channels with 128-byte (swizzled) rows when BLOCK_N allows, else one dense chunk
   static constexpr bool kSwz = (BLOCK_N * kEsz) % 128 == 0;
   static constexpr int kChunkC = kSwz ? 128 / kEsz : BLOCK_N;
@@ -215,7 +215,7 @@ __global__ void __launch_bounds__(128) igemm_kernel(const __grid_constant__ Igem
     const int cin = c0 % Cfg::kChunkC;
     uint8_t* rowp = smem + chunk * (128 * Cfg::kRowPitch) + row * Cfg::kRowPitch;
     const int j0 = (cin * Cfg::kEsz) >> 4;
-    if constexpr (OUT_MODE == OUT_BF16) {
+    if constexpr (OUT_MODE == OUT_BF16 || OUT_MODE == OUT_BF16_REDUCE) {
       uint32_t pk[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
@@ -248,7 +248,7 @@ __global__ void __launch_bounds__(128) igemm_kernel(const __grid_constant__ Igem
       const int ch = n0 + chunk * Cfg::kChunkC;
       if (ch >= p.rows) break;
       const uint8_t* src = smem + chunk * (128 * Cfg::kRowPitch);
-      if constexpr (OUT_MODE == OUT_F32_REDUCE)
+      if constexpr (OUT_MODE == OUT_F32_REDUCE || OUT_MODE == OUT_BF16_REDUCE)
         ptx::tma_reduce_add_5d(cmap, src, ch, w0, h0, d0, nb);
       else
         ptx::tma_store_5d(cmap, src, ch, w0, h0, d0, nb);

@@ -1,0 +1,441 @@
+// Generalised normalisation + activation kernels (descriptor API): batch / instance / group statistics, residual add
+// and gradient fan-out.  Used by the BMGAN blocks (Conv -> InstanceNorm3d -> LeakyReLU, ResidualUnit sums, dense
+// concatenation; bmgan_model.py:12-70) and the PatchGAN discriminator (BatchNorm3d).
+//
+// Same access pattern as elementwise.cu: activations are NDHWC bf16, a thread owns 8 consecutive channels (16 bytes),
+// a warp covers consecutive channels of consecutive voxels; blockIdx.y is the sample (statistics group) index.
+#include <cuda_bf16.h>
+
+#include <algorithm>
+
+#include "common.h"
+
+namespace petsyn {
+namespace nx {
+
+struct F8 {
+  float v[8];
+};
+__device__ __forceinline__ F8 load8(const __nv_bfloat16* p) {
+  const uint4 raw = *reinterpret_cast<const uint4*>(p);
+  const __nv_bfloat162* b2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
+  F8 r;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 f = __bfloat1622float2(b2[i]);
+    r.v[2 * i] = f.x;
+    r.v[2 * i + 1] = f.y;
+  }
+  return r;
+}
+__device__ __forceinline__ void store8(__nv_bfloat16* p, const F8& r) {
+  uint4 o;
+  __nv_bfloat162 b0 = __floats2bfloat162_rn(r.v[0], r.v[1]), b1 = __floats2bfloat162_rn(r.v[2], r.v[3]);
+  __nv_bfloat162 b2 = __floats2bfloat162_rn(r.v[4], r.v[5]), b3 = __floats2bfloat162_rn(r.v[6], r.v[7]);
+  o.x = *reinterpret_cast<uint32_t*>(&b0); o.y = *reinterpret_cast<uint32_t*>(&b1);
+  o.z = *reinterpret_cast<uint32_t*>(&b2); o.w = *reinterpret_cast<uint32_t*>(&b3);
+  *reinterpret_cast<uint4*>(p) = o;
+}
+__device__ __forceinline__ F8 load8f(const float* p) {
+  const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+  F8 r;
+  r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w; r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+  return r;
+}
+__device__ __forceinline__ F8 splat(float x) {
+  F8 r;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) r.v[i] = x;
+  return r;
+}
+
+__device__ __forceinline__ float act_fwd(float b, int act, float slope) {
+  switch (act) {
+    case PETSYN_ACT_RELU: return fmaxf(b, 0.f);
+    case PETSYN_ACT_LRELU: return b > 0.f ? b : b * slope;
+    case PETSYN_ACT_SILU: return b / (1.f + __expf(-b));
+    case PETSYN_ACT_TANH: return tanhf(b);
+    default: return b;
+  }
+}
+__device__ __forceinline__ float act_grad(float b, int act, float slope) {
+  switch (act) {
+    case PETSYN_ACT_RELU: return b > 0.f ? 1.f : 0.f;
+    case PETSYN_ACT_LRELU: return b > 0.f ? 1.f : slope;
+    case PETSYN_ACT_SILU: { const float s = 1.f / (1.f + __expf(-b)); return s * (1.f + b * (1.f - s)); }
+    case PETSYN_ACT_TANH: { const float t = tanhf(b); return 1.f - t * t; }
+    default: return 1.f;
+  }
+}
+
+struct RowIter {
+  int cpt, rpp, tx, ty;
+  bool active;
+  __device__ RowIter(int C) {
+    cpt = C / 8;
+    rpp = blockDim.x / cpt;
+    tx = threadIdx.x % cpt;
+    ty = threadIdx.x / cpt;
+    active = ty < rpp;
+  }
+};
+
+template <int NV>
+__device__ __forceinline__ void block_reduce_channels(const RowIter& it, float (&acc)[NV][8], float* smem, float* out,
+                                                      int C) {
+  if (it.active) {
+#pragma unroll
+    for (int v = 0; v < NV; ++v)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) smem[(it.ty * NV + v) * C + it.tx * 8 + i] = acc[v][i];
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < NV * C; e += blockDim.x) {
+    float s = 0.f;
+    for (int r = 0; r < it.rpp; ++r) s += smem[r * NV * C + e];
+    atomicAdd(out + e, s);
+  }
+}
+
+// sums[sample][0:C] += sum z, sums[sample][C:2C] += sum z^2
+__global__ void __launch_bounds__(256) stats_kernel(const __nv_bfloat16* __restrict__ z, float* __restrict__ sums,
+                                                    int64_t rows, int C) {
+  extern __shared__ float smem_f[];
+  RowIter it(C);
+  z += (int64_t)blockIdx.y * rows * C;
+  sums += (int64_t)blockIdx.y * 2 * C;
+  float acc[2][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[0][i] = acc[1][i] = 0.f;
+  if (it.active) {
+    const int64_t stride = (int64_t)gridDim.x * it.rpp;
+    for (int64_t r = (int64_t)blockIdx.x * it.rpp + it.ty; r < rows; r += 2 * stride) {
+      F8 x0 = load8(z + r * C + it.tx * 8), x1 = splat(0.f);
+      if (r + stride < rows) x1 = load8(z + (r + stride) * C + it.tx * 8);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        acc[0][i] += x0.v[i] + x1.v[i];
+        acc[1][i] += x0.v[i] * x0.v[i] + x1.v[i] * x1.v[i];
+      }
+    }
+  }
+  block_reduce_channels<2>(it, acc, smem_f, sums, C);
+}
+
+// One thread per (sample, channel).  group_size channels share their statistics (GroupNorm); group_size == 1 is
+// Batch (nsamples == 1) / Instance (nsamples == N) normalisation.
+__global__ void finalize_kernel(const float* __restrict__ sums, const float* __restrict__ gamma,
+                                const float* __restrict__ beta, float* __restrict__ running_mean,
+                                float* __restrict__ running_var, float* __restrict__ scale, float* __restrict__ shift,
+                                float* __restrict__ save_mean, float* __restrict__ save_rstd, int64_t rows, int C,
+                                int nsamples, int group_size, float eps, float momentum, int training) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nsamples * C) return;
+  const int s = i / C, c = i % C;
+  double mean, var;
+  if (training || running_mean == nullptr) {
+    const float* sm = sums + (int64_t)s * 2 * C;
+    const int g0 = c / group_size * group_size;
+    double a = 0, b = 0;
+    for (int j = 0; j < group_size; ++j) { a += sm[g0 + j]; b += sm[C + g0 + j]; }
+    const double cnt = (double)rows * group_size;
+    mean = a / cnt;
+    var = b / cnt - mean * mean;
+    if (var < 0) var = 0;
+    if (running_mean != nullptr && nsamples == 1 && group_size == 1) {
+      const double unbiased = rows > 1 ? var * (double)rows / (double)(rows - 1) : var;
+      running_mean[c] = (float)((1.0 - momentum) * running_mean[c] + momentum * mean);
+      running_var[c] = (float)((1.0 - momentum) * running_var[c] + momentum * unbiased);
+    }
+  } else {
+    mean = running_mean[c];
+    var = running_var[c];
+  }
+  const double rstd = 1.0 / sqrt(var + (double)eps);
+  const float g = gamma ? gamma[c] : 1.f, b = beta ? beta[c] : 0.f;
+  scale[i] = (float)(g * rstd);
+  shift[i] = (float)(b - mean * g * rstd);
+  if (save_mean) save_mean[i] = (float)mean;
+  if (save_rstd) save_rstd[i] = (float)rstd;
+}
+
+struct Dev {   // device copy of petsyn_normact_desc with typed pointers
+  const __nv_bfloat16* z;
+  int64_t rows;
+  int C, per_sample;
+  const float *scale, *shift, *mean, *rstd, *gamma;
+  __nv_bfloat16* t1; int cs1, co1, act1;
+  __nv_bfloat16* t2; int cs2, co2, act2;
+  float slope;
+  __nv_bfloat16* res; int csr, cor, res_acc;
+  float* sums;
+  __nv_bfloat16* dz;
+  float *dgamma, *dbeta;
+};
+
+__global__ void __launch_bounds__(256) fwd_kernel(const Dev d) {
+  RowIter it(d.C);
+  if (!it.active) return;
+  const int s = blockIdx.y;
+  const int64_t base = (int64_t)s * d.rows;
+  const int so = d.per_sample ? s * d.C : 0;
+  F8 sc = splat(1.f), sh = splat(0.f);
+  if (d.scale) { sc = load8f(d.scale + so + it.tx * 8); sh = load8f(d.shift + so + it.tx * 8); }
+  const int64_t stride = (int64_t)gridDim.x * it.rpp;
+  for (int64_t r0 = (int64_t)blockIdx.x * it.rpp + it.ty; r0 < d.rows; r0 += stride) {
+    const int64_t r = base + r0;
+    const F8 x = load8(d.z + r * d.C + it.tx * 8);
+    F8 rs = splat(0.f);
+    if (d.res) rs = load8(d.res + r * d.csr + d.cor + it.tx * 8);
+    F8 o1, o2;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float b = x.v[i] * sc.v[i] + sh.v[i];
+      o1.v[i] = act_fwd(b, d.act1, d.slope) + rs.v[i];
+      o2.v[i] = act_fwd(b, d.act2, d.slope) + rs.v[i];
+    }
+    store8(d.t1 + r * d.cs1 + d.co1 + it.tx * 8, o1);
+    if (d.t2) store8(d.t2 + r * d.cs2 + d.co2 + it.tx * 8, o2);
+  }
+}
+
+__global__ void __launch_bounds__(256) bwd_reduce_kernel(const Dev d) {
+  extern __shared__ float smem_f[];
+  RowIter it(d.C);
+  const int s = blockIdx.y;
+  const int64_t base = (int64_t)s * d.rows;
+  const int so = d.per_sample ? s * d.C : 0;
+  float acc[2][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[0][i] = acc[1][i] = 0.f;
+  if (it.active) {
+    F8 sc = splat(1.f), sh = splat(0.f);
+    if (d.scale) { sc = load8f(d.scale + so + it.tx * 8); sh = load8f(d.shift + so + it.tx * 8); }
+    const F8 mu = load8f(d.mean + so + it.tx * 8), rs = load8f(d.rstd + so + it.tx * 8);
+    const int64_t stride = (int64_t)gridDim.x * it.rpp;
+    for (int64_t r0 = (int64_t)blockIdx.x * it.rpp + it.ty; r0 < d.rows; r0 += stride) {
+      const int64_t r = base + r0;
+      const F8 x = load8(d.z + r * d.C + it.tx * 8);
+      const F8 a = load8(d.t1 + r * d.cs1 + d.co1 + it.tx * 8);
+      F8 b2 = splat(0.f);
+      if (d.t2) b2 = load8(d.t2 + r * d.cs2 + d.co2 + it.tx * 8);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float b = x.v[i] * sc.v[i] + sh.v[i];
+        float g = a.v[i] * act_grad(b, d.act1, d.slope);
+        if (d.t2) g += b2.v[i] * act_grad(b, d.act2, d.slope);
+        acc[0][i] += g;
+        acc[1][i] += g * (x.v[i] - mu.v[i]) * rs.v[i];
+      }
+    }
+  }
+  block_reduce_channels<2>(it, acc, smem_f, d.sums + (d.per_sample ? (int64_t)s * 2 * d.C : 0), d.C);
+}
+
+__global__ void __launch_bounds__(256) bwd_apply_kernel(const Dev d) {
+  RowIter it(d.C);
+  if (blockIdx.x == 0 && blockIdx.y == 0 && d.dgamma != nullptr) {
+    for (int c = threadIdx.x; c < d.C; c += blockDim.x) {
+      d.dbeta[c] = d.sums[c];
+      d.dgamma[c] = d.sums[d.C + c];
+    }
+  }
+  if (!it.active) return;
+  const int s = blockIdx.y;
+  const int64_t base = (int64_t)s * d.rows;
+  const int so = d.per_sample ? s * d.C : 0;
+  F8 sc = splat(1.f), sh = splat(0.f), mu = splat(0.f), rs = splat(1.f), k0 = splat(1.f), k1 = splat(0.f), k2 = splat(0.f);
+  if (d.scale) { sc = load8f(d.scale + so + it.tx * 8); sh = load8f(d.shift + so + it.tx * 8); }
+  if (d.mean) {
+    mu = load8f(d.mean + so + it.tx * 8);
+    rs = load8f(d.rstd + so + it.tx * 8);
+    const F8 ga = d.gamma ? load8f(d.gamma + it.tx * 8) : splat(1.f);
+    const float* sm = d.sums + (d.per_sample ? (int64_t)s * 2 * d.C : 0);
+    const F8 s0 = load8f(sm + it.tx * 8), s1 = load8f(sm + d.C + it.tx * 8);
+    const float inv = 1.f / (float)d.rows;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      k0.v[i] = ga.v[i] * rs.v[i];
+      k1.v[i] = s0.v[i] * inv;
+      k2.v[i] = s1.v[i] * inv;
+    }
+  }
+  const int64_t stride = (int64_t)gridDim.x * it.rpp;
+  for (int64_t r0 = (int64_t)blockIdx.x * it.rpp + it.ty; r0 < d.rows; r0 += stride) {
+    const int64_t r = base + r0;
+    const F8 x = load8(d.z + r * d.C + it.tx * 8);
+    const F8 a = load8(d.t1 + r * d.cs1 + d.co1 + it.tx * 8);
+    F8 b2 = splat(0.f);
+    if (d.t2) b2 = load8(d.t2 + r * d.cs2 + d.co2 + it.tx * 8);
+    F8 o, dr;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float b = x.v[i] * sc.v[i] + sh.v[i];
+      float g = a.v[i] * act_grad(b, d.act1, d.slope);
+      if (d.t2) g += b2.v[i] * act_grad(b, d.act2, d.slope);
+      const float zh = (x.v[i] - mu.v[i]) * rs.v[i];
+      o.v[i] = k0.v[i] * (g - k1.v[i] - zh * k2.v[i]);
+      dr.v[i] = a.v[i] + b2.v[i];
+    }
+    store8(d.dz + r * d.C + it.tx * 8, o);
+    if (d.res) {
+      __nv_bfloat16* p = d.res + r * d.csr + d.cor + it.tx * 8;
+      if (d.res_acc) {
+        const F8 old = load8(p);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) dr.v[i] += old.v[i];
+      }
+      store8(p, dr);
+    }
+  }
+}
+
+// dst[r, coff:coff+C] (+)= src[r, soff:soff+C]   (gradient fan-in for tensors with several consumers)
+__global__ void __launch_bounds__(256) add_slice_kernel(const __nv_bfloat16* __restrict__ src, int css, int cos,
+                                                        __nv_bfloat16* __restrict__ dst, int csd, int cod, int64_t rows,
+                                                        int C, int accumulate) {
+  RowIter it(C);
+  if (!it.active) return;
+  const int64_t stride = (int64_t)gridDim.x * it.rpp;
+  for (int64_t r = (int64_t)blockIdx.x * it.rpp + it.ty; r < rows; r += stride) {
+    F8 x = load8(src + r * css + cos + it.tx * 8);
+    __nv_bfloat16* p = dst + r * csd + cod + it.tx * 8;
+    if (accumulate) {
+      const F8 old = load8(p);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) x.v[i] += old.v[i];
+    }
+    store8(p, x);
+  }
+}
+
+// out[c] = sum_r x[r, coff + c]  (bias gradient), fp32, caller-zeroed
+__global__ void __launch_bounds__(256) colsum_kernel(const __nv_bfloat16* __restrict__ x, int cs, int co,
+                                                     float* __restrict__ out, int64_t rows, int C) {
+  extern __shared__ float smem_f[];
+  RowIter it(C);
+  float acc[1][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[0][i] = 0.f;
+  if (it.active) {
+    const int64_t stride = (int64_t)gridDim.x * it.rpp;
+    for (int64_t r = (int64_t)blockIdx.x * it.rpp + it.ty; r < rows; r += stride) {
+      const F8 v = load8(x + r * cs + co + it.tx * 8);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[0][i] += v.v[i];
+    }
+  }
+  block_reduce_channels<1>(it, acc, smem_f, out, C);
+}
+
+static int row_blocks(int64_t rows, int C, int nsamples) {
+  const int rpp = 256 / (C / 8);
+  const int64_t want = (rows + rpp - 1) / rpp;
+  return (int)std::max<int64_t>(1, std::min<int64_t>(want, std::max(1, 148 * 8 / nsamples)));
+}
+
+static int32_t to_dev(const petsyn_normact_desc* d, Dev* o) {
+  PETSYN_REQUIRE(d != nullptr, "null descriptor");
+  PETSYN_REQUIRE(d->z != nullptr && d->rows > 0 && d->nsamples >= 1, "bad tensor");
+  PETSYN_REQUIRE(d->c % 8 == 0 && d->c >= 8 && d->c <= 2048, "channels must be a multiple of 8 in [8, 2048]");
+  PETSYN_REQUIRE((d->t1_cstride | d->t1_coff | d->t2_cstride | d->t2_coff | d->res_cstride | d->res_coff) % 8 == 0,
+                 "channel pitches/offsets must be multiples of 8");
+  o->z = reinterpret_cast<const __nv_bfloat16*>(d->z);
+  o->rows = d->rows; o->C = d->c; o->per_sample = d->per_sample_stats;
+  o->scale = d->scale; o->shift = d->shift; o->mean = d->mean; o->rstd = d->rstd; o->gamma = d->gamma;
+  o->t1 = reinterpret_cast<__nv_bfloat16*>(d->t1); o->cs1 = d->t1_cstride; o->co1 = d->t1_coff; o->act1 = d->act1;
+  o->t2 = reinterpret_cast<__nv_bfloat16*>(d->t2); o->cs2 = d->t2_cstride; o->co2 = d->t2_coff; o->act2 = d->act2;
+  o->slope = d->slope;
+  o->res = reinterpret_cast<__nv_bfloat16*>(d->res); o->csr = d->res_cstride; o->cor = d->res_coff;
+  o->res_acc = d->res_accumulate;
+  o->sums = d->sums;
+  o->dz = reinterpret_cast<__nv_bfloat16*>(d->dz);
+  o->dgamma = d->dgamma; o->dbeta = d->dbeta;
+  return PETSYN_OK;
+}
+
+}  // namespace nx
+}  // namespace petsyn
+
+using namespace petsyn;
+using namespace petsyn::nx;
+
+extern "C" {
+
+int32_t petsyn_norm_stats(const void* z, float* sums, int64_t rows, int32_t c, int32_t nsamples, void* stream) {
+  PETSYN_REQUIRE(z && sums && rows > 0 && nsamples >= 1, "bad argument");
+  PETSYN_REQUIRE(c % 8 == 0 && c >= 8 && c <= 2048, "channels must be a multiple of 8 in [8, 2048]");
+  const int rpp = 256 / (c / 8);
+  const size_t smem = (size_t)rpp * 2 * c * sizeof(float);
+  dim3 grid((unsigned)row_blocks(rows, c, nsamples), (unsigned)nsamples);
+  stats_kernel<<<grid, 256, smem, as_stream(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(z), sums, rows, c);
+  return check_launch("stats_kernel");
+}
+
+int32_t petsyn_norm_finalize(const float* sums, const float* gamma, const float* beta, float* running_mean,
+                             float* running_var, float* scale, float* shift, float* save_mean, float* save_rstd,
+                             int64_t rows, int32_t c, int32_t nsamples, int32_t group_size, float eps, float momentum,
+                             int32_t training, void* stream) {
+  PETSYN_REQUIRE(scale && shift && nsamples >= 1 && group_size >= 1 && c % group_size == 0, "bad argument");
+  PETSYN_REQUIRE(training || running_mean != nullptr || sums != nullptr, "missing statistics");
+  const int total = nsamples * c;
+  finalize_kernel<<<(total + 127) / 128, 128, 0, as_stream(stream)>>>(sums, gamma, beta, running_mean, running_var, scale,
+                                                                      shift, save_mean, save_rstd, rows, c, nsamples,
+                                                                      group_size, eps, momentum, training);
+  return check_launch("finalize_kernel");
+}
+
+int32_t petsyn_normact_fwd(const petsyn_normact_desc* desc, void* stream) {
+  Dev d;
+  int32_t rc = to_dev(desc, &d);
+  if (rc) return rc;
+  PETSYN_REQUIRE(d.t1 != nullptr, "missing destination");
+  dim3 grid((unsigned)row_blocks(d.rows, d.C, desc->nsamples), (unsigned)desc->nsamples);
+  fwd_kernel<<<grid, 256, 0, as_stream(stream)>>>(d);
+  return check_launch("normact fwd_kernel");
+}
+
+int32_t petsyn_normact_bwd(const petsyn_normact_desc* desc, void* stream) {
+  Dev d;
+  int32_t rc = to_dev(desc, &d);
+  if (rc) return rc;
+  PETSYN_REQUIRE(d.t1 != nullptr && d.dz != nullptr, "missing gradient source / destination");
+  PETSYN_REQUIRE(d.mean == nullptr || d.sums != nullptr, "normalised backward needs the sums workspace");
+  cudaStream_t st = as_stream(stream);
+  dim3 grid((unsigned)row_blocks(d.rows, d.C, desc->nsamples), (unsigned)desc->nsamples);
+  if (d.mean != nullptr) {
+    const int nst = d.per_sample ? desc->nsamples : 1;
+    PETSYN_CHECK_CUDA(cudaMemsetAsync(d.sums, 0, (size_t)nst * 2 * d.C * sizeof(float), st));
+    const int rpp = 256 / (d.C / 8);
+    const size_t smem = (size_t)rpp * 2 * d.C * sizeof(float);
+    bwd_reduce_kernel<<<grid, 256, smem, st>>>(d);
+    rc = check_launch("normact bwd_reduce_kernel");
+    if (rc) return rc;
+  }
+  bwd_apply_kernel<<<grid, 256, 0, st>>>(d);
+  return check_launch("normact bwd_apply_kernel");
+}
+
+int32_t petsyn_add_slice(const void* src, int32_t src_cstride, int32_t src_coff, void* dst, int32_t dst_cstride,
+                         int32_t dst_coff, int64_t rows, int32_t c, int32_t accumulate, void* stream) {
+  PETSYN_REQUIRE(src && dst && rows > 0, "bad argument");
+  PETSYN_REQUIRE(c % 8 == 0 && c >= 8 && c <= 2048 && (src_cstride | src_coff | dst_cstride | dst_coff) % 8 == 0,
+                 "channels, pitches and offsets must be multiples of 8");
+  add_slice_kernel<<<row_blocks(rows, c, 1), 256, 0, as_stream(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(src), src_cstride, src_coff, reinterpret_cast<__nv_bfloat16*>(dst),
+      dst_cstride, dst_coff, rows, c, accumulate);
+  return check_launch("add_slice_kernel");
+}
+
+int32_t petsyn_colsum(const void* x, int32_t cstride, int32_t coff, float* out, int64_t rows, int32_t c, void* stream) {
+  PETSYN_REQUIRE(x && out && rows > 0, "bad argument");
+  PETSYN_REQUIRE(c % 8 == 0 && c >= 8 && c <= 2048 && (cstride | coff) % 8 == 0, "channels must be a multiple of 8");
+  cudaStream_t st = as_stream(stream);
+  PETSYN_CHECK_CUDA(cudaMemsetAsync(out, 0, (size_t)c * sizeof(float), st));
+  const int rpp = 256 / (c / 8);
+  colsum_kernel<<<row_blocks(rows, c, 1), 256, (size_t)rpp * c * sizeof(float), st>>>(
+      reinterpret_cast<const __nv_bfloat16*>(x), cstride, coff, out, rows, c);
+  return check_launch("colsum_kernel");
+}
+
+}  // extern "C"

@@ -1,0 +1,304 @@
+"""A small static-graph executor for networks made of (Conv3d | ConvTranspose3d) -> (Instance|Batch)Norm -> activation
+blocks with residual sums and dense channel concatenation -- the BMGAN generator/discriminator
+(``bl_methods/BMGAN/bmgan_model.py:12-144``).
+
+Tensors are channels-last bf16 buffers; an op reads/writes *channel slices* of buffers, so ``torch.cat`` is never
+executed: producers write straight into the concat buffer of their consumer(s).  Backward is the reverse op list;
+which gradient writes overwrite and which accumulate is decided once, statically, when the tape is finalised (the first
+writer of a gradient region in backward order overwrites, later ones add -- through the conv kernels' TMA add-reduce
+epilogue or the norm kernels' read-modify-write).  Every FLOP goes through ``ops`` (libpetsyn).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _cabi, ops
+from ._cabi import check, lib, ptr, stream_ptr
+
+
+class Buf:
+    """Channels-last bf16 activation buffer [n*d*h*w, c] (+ lazily allocated gradient of the same shape)."""
+
+    def __init__(self, n: int, d: int, h: int, w: int, c: int, device, name: str = ""):
+        self.n, self.d, self.h, self.w, self.c = n, d, h, w, c
+        self.rows = n * d * h * w
+        self.name = name
+        self.t = torch.zeros(self.rows, c, dtype=torch.bfloat16, device=device)
+        self._g: Optional[torch.Tensor] = None
+
+    @property
+    def g(self) -> torch.Tensor:
+        if self._g is None:
+            self._g = torch.zeros_like(self.t)
+        return self._g
+
+    def sl(self, off: int = 0, c: Optional[int] = None) -> "Sl":
+        return Sl(self, off, self.c - off if c is None else c)
+
+
+class Sl:
+    """Channel slice [off, off+c) of a buffer."""
+
+    def __init__(self, buf: Buf, off: int, c: int):
+        assert 0 <= off and off + c <= buf.c, (off, c, buf.c)
+        self.buf, self.off, self.c = buf, off, c
+
+
+class Op:
+    def fwd(self, training: bool) -> None: ...
+    def bwd(self) -> None: ...
+    def grad_writes(self) -> List[Tuple[str, Sl]]:
+        """Gradient regions this op writes in backward, in the order it writes them."""
+        return []
+
+    def repack(self) -> None: ...
+
+
+class ConvOp(Op):
+    """z = conv(x) [+ bias] [-> activation]: raw output into its own contiguous buffer (bf16) or an fp32 tensor.
+
+    Channel counts that are not multiples of 8 (the 9-channel BMGAN input, 1-channel outputs) are zero-padded in a
+    staging copy of the weights; the padded activations' extra channels are zeros.
+    """
+
+    def __init__(self, x: Sl, weight: torch.nn.Parameter, bias: Optional[torch.nn.Parameter], ksize: int, stride: int,
+                 pad: int, op: int = ops.OP_CONV, act: int = ops.ACT_NONE, slope: float = 0.2, y_fp32: bool = False,
+                 use_bias: bool = True, need_dx: bool = True, need_dw: bool = True, name: str = ""):
+        self.x, self.weight, self.bias = x, weight, bias
+        self.name = name
+        self.opcode = op
+        b = x.buf
+        dev = b.t.device
+        if op == ops.OP_CONVT:
+            cin_w, cout_w = weight.shape[0], weight.shape[1]
+        else:
+            cout_w, cin_w = weight.shape[0], weight.shape[1]
+        self.cin_w, self.cout_w = cin_w, cout_w
+        self.cin, self.cout = x.c, (cout_w + 7) // 8 * 8
+        if cout_w < 8:
+            self.cout = 16                     # one-channel heads: smallest UMMA N with an unswizzled 32-byte row
+        assert cin_w <= self.cin, (cin_w, self.cin)
+        self.padded = (self.cin != cin_w) or (self.cout != cout_w)
+        self.use_bias = use_bias and bias is not None
+        self.need_dx, self.need_dw = need_dx, need_dw
+        self.plan = ops.ConvPlan(op, b.n, b.d, b.h, b.w, self.cin, self.cout, ksize, stride, pad,
+                                 x_cstride=b.c, x_coff=x.off, dx_cstride=b.c, dx_coff=x.off, act=act, slope=slope,
+                                 y_fp32=y_fp32)
+        od, oh, ow = self.plan.out_dims
+        self.y_fp32 = y_fp32
+        if y_fp32:
+            self.z = None
+            self.zf = torch.zeros(b.n * od * oh * ow, self.cout, dtype=torch.float32, device=dev)
+            self.zg = torch.zeros(b.n * od * oh * ow, self.cout, dtype=torch.bfloat16, device=dev)   # grad w.r.t. zf
+        else:
+            self.z = Buf(b.n, od, oh, ow, self.cout, dev, name + ".z")
+        k3 = ksize ** 3
+        if self.padded:
+            shape = (self.cin, self.cout) if op == ops.OP_CONVT else (self.cout, self.cin)
+            self.w_stage = torch.zeros(*shape, ksize, ksize, ksize, dtype=torch.float32, device=dev)
+            self.dw_stage = torch.zeros_like(self.w_stage)
+        self.bias_stage = None
+        if self.use_bias and self.cout != cout_w:
+            self.bias_stage = torch.zeros(self.cout, dtype=torch.float32, device=dev)
+        self.dbias_stage = torch.zeros(self.cout, dtype=torch.float32, device=dev) if bias is not None else None
+        self.acc_dx = False
+        self._ver = None
+        self.grad_w: Optional[torch.Tensor] = None     # set by the owner: where dW / dbias go
+        self.grad_b: Optional[torch.Tensor] = None
+        self.flops = self.plan.flops_algorithmic
+
+    # -------------------------------------------------------------------------------------------------
+    def repack(self, force: bool = False) -> None:
+        w = self.weight
+        ver = (w._version, w.data_ptr(), self.need_dx)
+        if not force and ver == self._ver:
+            return
+        src = w.detach()
+        if self.padded:
+            if self.opcode == ops.OP_CONVT:
+                self.w_stage[:self.cin_w, :self.cout_w].copy_(src)
+            else:
+                self.w_stage[:self.cout_w, :self.cin_w].copy_(src)
+            src = self.w_stage
+        self.plan.pack(src, need_dgrad=self.need_dx)
+        if self.bias_stage is not None:
+            self.bias_stage[:self.cout_w].copy_(self.bias.detach())
+        self._ver = ver
+
+    def out(self) -> torch.Tensor:
+        return self.zf if self.y_fp32 else self.z.t
+
+    def dout(self) -> torch.Tensor:
+        return self.zg if self.y_fp32 else self.z.g
+
+    def fwd(self, training: bool) -> None:
+        bias = None
+        if self.use_bias:
+            bias = self.bias_stage if self.bias_stage is not None else self.bias.detach()
+        self.plan.fprop(self.x.buf.t, self.out(), bias)
+
+    def grad_writes(self):
+        return [("dx", self.x)] if self.need_dx else []
+
+    def bwd(self) -> None:
+        dz = self.dout()
+        if self.need_dw:
+            if self.padded:
+                self.plan.wgrad(self.x.buf.t, dz, self.dw_stage)
+                if self.opcode == ops.OP_CONVT:
+                    self.grad_w.copy_(self.dw_stage[:self.cin_w, :self.cout_w])
+                else:
+                    self.grad_w.copy_(self.dw_stage[:self.cout_w, :self.cin_w])
+            else:
+                self.plan.wgrad(self.x.buf.t, dz, self.grad_w)
+            if self.bias is not None:
+                if self.use_bias:
+                    check(lib.petsyn_colsum(ptr(dz), self.cout, 0, ptr(self.dbias_stage), dz.shape[0], self.cout,
+                                            stream_ptr()), "colsum")
+                    self.grad_b.copy_(self.dbias_stage[:self.cout_w])
+                else:
+                    self.grad_b.zero_()     # a bias in front of a non-affine InstanceNorm has exactly zero gradient
+        if self.need_dx:
+            if self.acc_dx:
+                check(lib.petsyn_conv_dgrad_accumulate(self.plan._h, ptr(dz), ptr(self.plan.w_dgrad), ptr(self.x.buf.g),
+                                                       stream_ptr()), "conv_dgrad_accumulate")
+            else:
+                self.plan.dgrad(dz, self.x.buf.g)
+
+
+class NormActOp(Op):
+    """dst_i = act(norm(z)) [+ res] for one or two destinations (channel slices)."""
+
+    def __init__(self, z: Buf, kind: str, act: int, dsts: Sequence[Sl], res: Optional[Sl] = None, slope: float = 0.2,
+                 bn: Optional[torch.nn.BatchNorm3d] = None, eps: float = 1e-5, name: str = ""):
+        assert kind in ("instance", "batch", "none") and 1 <= len(dsts) <= 2
+        self.z, self.kind, self.act, self.dsts, self.res, self.slope, self.bn, self.eps = z, kind, act, list(dsts), res, \
+            slope, bn, eps
+        self.name = name
+        dev = z.t.device
+        self.ns = z.n if kind == "instance" else 1
+        self.rows = z.rows // self.ns
+        c = z.c
+        if kind != "none":
+            f = lambda m=1: torch.zeros(self.ns * c * m, dtype=torch.float32, device=dev)
+            self.sums, self.bsums = f(2), f(2)
+            self.scale, self.shift, self.mean, self.rstd = f(), f(), f(), f()
+        self.acc_res = False
+        self.grad_gamma: Optional[torch.Tensor] = None
+        self.grad_beta: Optional[torch.Tensor] = None
+        self.need_dz = True
+
+    def _desc(self, backward: bool) -> _cabi.NormActDesc:
+        z = self.z
+        d = _cabi.NormActDesc()
+        d.z, d.rows, d.c, d.nsamples = ptr(z.t), self.rows, z.c, self.ns
+        d.per_sample_stats = 1 if self.kind == "instance" else 0
+        if self.kind != "none":
+            d.scale, d.shift = ptr(self.scale), ptr(self.shift)
+            if backward:
+                d.mean, d.rstd = ptr(self.mean), ptr(self.rstd)
+                d.sums = ptr(self.bsums)
+                if self.bn is not None and self.bn.weight is not None:
+                    d.gamma = ptr(self.bn.weight)
+        src = (lambda s: s.buf.g) if backward else (lambda s: s.buf.t)
+        s1 = self.dsts[0]
+        d.t1, d.t1_cstride, d.t1_coff, d.act1 = ptr(src(s1)), s1.buf.c, s1.off, self.act
+        if len(self.dsts) > 1:
+            s2 = self.dsts[1]
+            d.t2, d.t2_cstride, d.t2_coff, d.act2 = ptr(src(s2)), s2.buf.c, s2.off, self.act
+        d.slope = self.slope
+        if self.res is not None:
+            d.res, d.res_cstride, d.res_coff = ptr(src(self.res)), self.res.buf.c, self.res.off
+            d.res_accumulate = int(self.acc_res)
+        if backward:
+            d.dz = ptr(z.g)
+            if self.grad_gamma is not None:
+                d.dgamma, d.dbeta = ptr(self.grad_gamma), ptr(self.grad_beta)
+        return d
+
+    def fwd(self, training: bool) -> None:
+        z = self.z
+        if self.kind == "instance":
+            self.sums.zero_()
+            check(lib.petsyn_norm_stats(ptr(z.t), ptr(self.sums), self.rows, z.c, z.n, stream_ptr()), "norm_stats")
+            check(lib.petsyn_norm_finalize(ptr(self.sums), None, None, None, None, ptr(self.scale), ptr(self.shift),
+                                           ptr(self.mean), ptr(self.rstd), self.rows, z.c, z.n, 1, self.eps, 0.0, 1,
+                                           stream_ptr()), "norm_finalize")
+        elif self.kind == "batch":
+            bn = self.bn
+            if training:
+                self.sums.zero_()
+                check(lib.petsyn_norm_stats(ptr(z.t), ptr(self.sums), z.rows, z.c, 1, stream_ptr()), "norm_stats")
+                if bn.num_batches_tracked is not None:
+                    bn.num_batches_tracked.add_(1)
+            mom = 0.1 if bn.momentum is None else bn.momentum
+            check(lib.petsyn_norm_finalize(ptr(self.sums), ptr(bn.weight), ptr(bn.bias), ptr(bn.running_mean),
+                                           ptr(bn.running_var), ptr(self.scale), ptr(self.shift), ptr(self.mean),
+                                           ptr(self.rstd), z.rows, z.c, 1, 1, bn.eps, mom, int(training), stream_ptr()),
+                  "norm_finalize")
+        d = self._desc(False)
+        check(lib.petsyn_normact_fwd(C.byref(d), stream_ptr()), "normact_fwd")
+
+    def grad_writes(self):
+        w = [("dz", self.z.sl())]
+        if self.res is not None:
+            w.append(("dres", self.res))
+        return w
+
+    def bwd(self) -> None:
+        d = self._desc(True)
+        check(lib.petsyn_normact_bwd(C.byref(d), stream_ptr()), "normact_bwd")
+
+
+class Tape:
+    """Ordered op list with static gradient write/accumulate analysis."""
+
+    def __init__(self):
+        self.ops: List[Op] = []
+        self._final = False
+
+    def add(self, op: Op) -> Op:
+        self.ops.append(op)
+        return op
+
+    def finalize(self) -> None:
+        """Walk backward order once: the first writer of a gradient region overwrites, later writers accumulate.  A
+        region may only be accumulated into if an earlier write covers it entirely."""
+        init: Dict[int, List[Tuple[int, int]]] = {}
+        for op in reversed(self.ops):
+            for key, s in op.grad_writes():
+                ranges = init.setdefault(id(s.buf), [])
+                lo, hi = s.off, s.off + s.c
+                covered = any(a <= lo and hi <= b for a, b in ranges)
+                overlap = any(a < hi and lo < b for a, b in ranges)
+                if overlap and not covered:
+                    raise RuntimeError(f"gradient region {s.buf.name}[{lo}:{hi}] partially overlaps an earlier write")
+                if key == "dx":
+                    op.acc_dx = covered
+                elif key == "dres":
+                    op.acc_res = covered
+                elif key == "dz" and covered:
+                    raise RuntimeError("raw conv outputs have a single consumer")
+                if not covered:
+                    ranges.append((lo, hi))
+        self._final = True
+
+    def repack(self) -> None:
+        for op in self.ops:
+            op.repack()
+
+    def forward(self, training: bool) -> None:
+        assert self._final
+        self.repack()
+        for op in self.ops:
+            op.fwd(training)
+
+    def backward(self) -> None:
+        for op in reversed(self.ops):
+            op.bwd()
+
+    def flops(self) -> float:
+        return sum(getattr(op, "flops", 0.0) for op in self.ops)

@@ -112,6 +112,10 @@ int32_t petsyn_conv_fprop(petsyn_conv_plan* plan, const void* x, const void* pac
                           void* stream);
 /* dx = conv_backward_input(dy, W).  Replaces cuDNN dgrad (+ the upsample's backward for UPCONV). */
 int32_t petsyn_conv_dgrad(petsyn_conv_plan* plan, const void* dy, const void* packed_dgrad, void* dx, void* stream);
+/* dx += conv_backward_input(dy, W): gradient fan-in for tensors with several consumers (dense concatenation and
+ * residual sums in bmgan_model.py:12-23).  The tile epilogue add-reduces through the TMA unit (bf16). */
+int32_t petsyn_conv_dgrad_accumulate(petsyn_conv_plan* plan, const void* dy, const void* packed_dgrad, void* dx,
+                                     void* stream);
 /* dw (fp32, PyTorch layout) = conv_backward_weight(x, dy); optional dbias (fp32 [cout]) = sum(dy).
  * `scratch` must hold petsyn_conv_wgrad_scratch_bytes(); it is zeroed and reduced into by the kernel.
  * accumulate != 0 adds into dw instead of overwriting (autograd .grad accumulation). */
@@ -128,6 +132,21 @@ int32_t petsyn_conv_wgrad(petsyn_conv_plan* plan, const void* x, const void* dy,
  * padded at the borders).  The conv itself is then petsyn_conv_fprop with k=1, cin=64, and its weight gradient
  * petsyn_conv_wgrad on the same patches. */
 int32_t petsyn_stem_im2col_k4s2(const float* x, void* patches, int32_t n, int32_t d, int32_t h, int32_t w, void* stream);
+
+/* Backward-data of the first layer (needed when a generator's output feeds the PatchGAN discriminator, whose first
+ * conv is exactly this stem): dpatches bf16 [n*(d/2)*(h/2)*(w/2), 64] -> dx fp32 [n,d,h,w] (col2im, gather form). */
+int32_t petsyn_stem_col2im_k4s2(const void* dpatches, float* dx, int32_t n, int32_t d, int32_t h, int32_t w, void* stream);
+
+/* BMGAN generator input: cat([t1, z.view(N,nz,1,1,1).expand(...)], 1) (bmgan_model.py:76-79) written as NDHWC bf16
+ * with the 1+nz channels zero-padded to cpad.  x fp32 [n, rows_per_sample]; zvec fp32 [n, nz]. */
+int32_t petsyn_concat_latent(const float* x, const float* zvec, void* out, int64_t rows_per_sample, int32_t n,
+                             int32_t nz, int32_t cpad, void* stream);
+/* One-channel heads (generator output conv, PatchGAN final conv) run with Cout padded to cpad:
+ * y[r] = src[r, 0] (fp32), and the matching gradient packer dz[r, 0] = dy[r] * (tanh_out ? 1 - y[r]^2 : 1), rest 0
+ * (bf16) -- the Tanh of bmgan_model.py:69 is applied in the conv epilogue, its derivative here. */
+int32_t petsyn_take_channel0(const float* src, float* y, int64_t rows, int32_t cpad, void* stream);
+int32_t petsyn_put_channel0_grad(const float* y, const float* dy, void* dz, int64_t rows, int32_t cpad,
+                                 int32_t tanh_out, void* stream);
 
 /* Last layer, Upsample x2 -> Conv3d(C -> 1, k3 p1) -> Tanh (unet_model.py:59-64).  The 27-tap conv on the upsampled
  * grid is computed as a per-SOURCE-voxel projection proj[s][k] = <x[s,:], W[k,:]> (a k=1 conv with cout=32, fp32
@@ -176,6 +195,54 @@ int32_t petsyn_norm_act_bwd_apply(const void* z, const float* scale, const float
                                   int32_t g1_coff, int32_t act1, const void* g2, int32_t g2_cstride, int32_t g2_coff,
                                   int32_t act2, float slope, const float* sums, void* dz, float* dgamma,
                                   float* dbeta, int64_t rows, int32_t c, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Generalised normalisation + activation (descriptor API): batch / instance / group statistics, residual add,
+ * gradient fan-out.  Conv -> InstanceNorm3d -> LeakyReLU, ResidualUnit sums and dense concatenation of BMGAN
+ * (bmgan_model.py:12-70 through MONAI's Convolution/ADN/ResidualUnit/ConvDenseBlock), PatchGAN BatchNorm3d.
+ * ---------------------------------------------------------------------------------------------------------- */
+typedef struct petsyn_normact_desc {
+  const void* z;             /* raw conv output, bf16 [nsamples*rows, c], contiguous */
+  int64_t rows;              /* voxels per statistics group (per sample for instance/group norm, all for batch norm) */
+  int32_t c;
+  int32_t nsamples;          /* 1 for batch statistics */
+  int32_t per_sample_stats;  /* 1: scale/shift/mean/rstd/sums are [nsamples][c]; 0: [c] */
+  const float* scale;        /* fused affine from petsyn_norm_finalize; NULL = no normalisation */
+  const float* shift;
+  const float* mean;         /* saved statistics (backward only); NULL = no normalisation */
+  const float* rstd;
+  const float* gamma;        /* [c] or NULL */
+  void* t1;                  /* fwd: destination 1 (bf16 channel slice); bwd: gradient w.r.t. destination 1 */
+  int32_t t1_cstride, t1_coff, act1;
+  void* t2;                  /* optional second destination / gradient source */
+  int32_t t2_cstride, t2_coff, act2;
+  float slope;               /* LeakyReLU slope */
+  void* res;                 /* fwd: residual input, out = act(norm(z)) + res; bwd: gradient w.r.t. res (output) */
+  int32_t res_cstride, res_coff;
+  int32_t res_accumulate;    /* bwd: add into res instead of overwriting */
+  float* sums;               /* bwd workspace [nsamples|1][2c] */
+  void* dz;                  /* bwd: gradient w.r.t. z, bf16 contiguous */
+  float* dgamma;             /* optional outputs (batch statistics with affine) */
+  float* dbeta;
+} petsyn_normact_desc;
+
+/* sums[sample][0:c] = sum z, sums[sample][c:2c] = sum z^2 (fp32, caller-zeroed). */
+int32_t petsyn_norm_stats(const void* z, float* sums, int64_t rows, int32_t c, int32_t nsamples, void* stream);
+/* Statistics -> fused affine scale/shift per (sample, channel).  group_size channels share statistics (GroupNorm,
+ * atten_unet_model.py:593-612); group_size 1 with nsamples == N is InstanceNorm3d, with nsamples == 1 BatchNorm3d
+ * (running statistics updated in training mode, used in eval mode). */
+int32_t petsyn_norm_finalize(const float* sums, const float* gamma, const float* beta, float* running_mean,
+                             float* running_var, float* scale, float* shift, float* save_mean, float* save_rstd,
+                             int64_t rows, int32_t c, int32_t nsamples, int32_t group_size, float eps, float momentum,
+                             int32_t training, void* stream);
+int32_t petsyn_normact_fwd(const petsyn_normact_desc* desc, void* stream);
+/* Reduction pass (only when normalised) + apply pass: dz, optional d(res), dgamma, dbeta. */
+int32_t petsyn_normact_bwd(const petsyn_normact_desc* desc, void* stream);
+/* dst[:, dst_coff:+c] (+)= src[:, src_coff:+c] on bf16 channel slices. */
+int32_t petsyn_add_slice(const void* src, int32_t src_cstride, int32_t src_coff, void* dst, int32_t dst_cstride,
+                         int32_t dst_coff, int64_t rows, int32_t c, int32_t accumulate, void* stream);
+/* out[c] = sum over rows of x[:, coff + c] (bias gradient); out fp32, overwritten. */
+int32_t petsyn_colsum(const void* x, int32_t cstride, int32_t coff, float* out, int64_t rows, int32_t c, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Losses and optimiser

@@ -1,0 +1,129 @@
+"""Model-level parity of the CUDA BMGAN generator / discriminator against the CPU oracle and the committed golden
+(generated from the reference's own bmgan_model.py over the MONAI stubs).
+
+Tolerances (bf16 operands, fp32 accumulation): synthesized-PET max-abs <= 6e-2 / mean-abs <= 6e-3 (the dense U-Net
+stacks ~60 conv+InstanceNorm layers, twice the depth of the pix2pix U-Net, and InstanceNorm over the 12-voxel bottleneck
+of this small test volume amplifies rounding); losses <= 1 % relative; global grad-norm <= 5 %; per-tensor grad-norms
+<= 15 % for tensors carrying > 0.1 % of the gradient energy.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import bmgan as OB
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+SMALL = dict(input_conv_channel=64, output_conv_channel=64, down_channels=[64, 128, 128, 128], middle_channels=[128],
+             up_channels=[128, 128, 128, 128, 64])
+
+
+def synth(shape, seed):
+    g = torch.Generator().manual_seed(seed)
+    n, d, h, w = shape
+    return (torch.rand(n, 1, d, h, w, generator=g), torch.rand(n, 1, d, h, w, generator=g) * 2 - 1,
+            torch.randn(n, 8, generator=g))
+
+
+def test_generator_step_matches_oracle_and_golden(petsyn):
+    gold = np.load(os.path.join(GOLD, "bmgan_small_2x64x96x64.npz"))
+    shape, seed = tuple(int(v) for v in gold["shape"]), int(gold["seed"])
+    torch.manual_seed(seed)
+    gen = petsyn.dense_unet_generator(**SMALL).train()
+    disc = petsyn.patch_discriminator().train()
+    for k, v in list(gen.state_dict().items()) + [("D." + k, v) for k, v in disc.state_dict().items()]:
+        if v.dtype.is_floating_point:
+            ref = float(gold["wsum/" + k])
+            assert abs(float(v.double().abs().sum()) - ref) <= 1e-6 * max(1.0, ref), k
+    # oracle with the same weights (CPU, fp32)
+    og, od = OB.DenseUnetGenerator(**SMALL).train(), OB.PatchDiscriminatorWrapper().train()
+    og.load_state_dict(gen.state_dict())
+    od.load_state_dict(disc.state_dict())
+    t1, pet, z = synth(shape, seed)
+    lo, ao, l1o, fo = OB.generator_step(og, od, t1, pet, z)
+    lo.backward()
+    assert abs(lo.item() - float(gold["g_loss"])) < 1e-4 * abs(float(gold["g_loss"]))     # oracle pinned to the fixture
+
+    gen, disc = gen.cuda(), disc.cuda()
+    for p in disc.parameters():
+        p.requires_grad_(False)                                   # train_bmgan.py:141-143
+    fake = gen(t1.cuda(), z.cuda())
+    logits = disc(fake.contiguous().float())[-1]
+    adv = ((logits - 1.0) ** 2).mean()
+    l1 = (fake - pet.cuda()).abs().mean()
+    loss = adv + 20.0 * l1
+    loss.backward()
+    torch.cuda.synchronize()
+    err = (fake.detach().cpu() - fo.detach()).abs()
+    print("fake err max/mean", err.max().item(), err.mean().item(), "loss", loss.item(), lo.item(), adv.item(), ao.item())
+    assert err.max().item() <= 6e-2 and err.mean().item() <= 6e-3
+    assert np.abs(fake.detach().cpu().numpy()[:, :, ::2, ::2, ::2] - gold["fake_sample"]).max() <= 6e-2
+    assert abs(loss.item() - float(gold["g_loss"])) <= 1e-2 * float(gold["g_loss"])
+    assert abs(adv.item() - float(gold["g_adv"])) <= 2e-2 * float(gold["g_adv"])
+    tot = tot_ref = 0.0
+    ref_norms = {k: float(gold["gradnorm/" + k]) for k, _ in gen.named_parameters()}
+    energy = sum(v * v for v in ref_norms.values())
+    worst = 0.0
+    for k, p in gen.named_parameters():
+        gn, ref = p.grad.double().norm().item(), ref_norms[k]
+        tot += gn * gn
+        tot_ref += ref * ref
+        if ref * ref > 1e-3 * energy:
+            worst = max(worst, abs(gn - ref) / ref)
+            assert abs(gn - ref) <= 0.15 * ref, (k, gn, ref)
+        elif k.endswith("bias") and ref < 1e-6:
+            assert gn < 1e-4, (k, gn)                              # biases in front of InstanceNorm: exactly zero grad
+    print("global grad-norm", tot ** 0.5, tot_ref ** 0.5, "worst per-tensor rel", worst)
+    assert abs(tot ** 0.5 - tot_ref ** 0.5) <= 5e-2 * tot_ref ** 0.5
+    # gradient direction on the largest tensors
+    og_grads = dict(og.named_parameters())
+    for k in sorted(ref_norms, key=ref_norms.get, reverse=True)[:6]:
+        a = dict(gen.named_parameters())[k].grad.double().cpu().flatten()
+        b = og_grads[k].grad.double().flatten()
+        cos = (torch.dot(a, b) / (a.norm() * b.norm() + 1e-30)).item()
+        assert cos > 0.97, (k, cos)
+
+
+def test_discriminator_phase_matches_oracle_and_golden(petsyn):
+    gold = np.load(os.path.join(GOLD, "bmgan_small_2x64x96x64.npz"))
+    shape, seed = tuple(int(v) for v in gold["shape"]), int(gold["seed"])
+    torch.manual_seed(seed)
+    petsyn.dense_unet_generator(**SMALL)                          # consume the RNG exactly like the fixture script
+    disc = petsyn.patch_discriminator().train()
+    od = OB.PatchDiscriminatorWrapper().train()
+    od.load_state_dict(disc.state_dict())
+    g = torch.Generator().manual_seed(5)
+    fake = torch.rand(shape[0], 1, *shape[1:], generator=g) * 2 - 1
+    real = torch.rand(shape[0], 1, *shape[1:], generator=g) * 2 - 1
+    dl = OB.discriminator_step(od, fake, real)
+    disc = disc.cuda()
+    lf = ((disc(fake.cuda())[-1]) ** 2).mean()
+    lf.backward()
+    lr = ((disc(real.cuda())[-1] - 1.0) ** 2).mean()
+    lr.backward()
+    torch.cuda.synchronize()
+    assert abs(0.5 * (lf + lr).item() - dl.item()) <= 2e-2 * abs(dl.item()) + 1e-3
+    for (k, p), (_, q) in zip(disc.named_parameters(), od.named_parameters()):
+        a, b = p.grad.double().cpu().flatten(), q.grad.double().flatten()
+        assert abs(a.norm().item() - b.norm().item()) <= 0.1 * b.norm().item() + 1e-6, (k, a.norm().item(), b.norm().item())
+        if b.norm().item() > 1e-6:
+            cos = (torch.dot(a, b) / (a.norm() * b.norm())).item()
+            assert cos > 0.98, (k, cos)
+    sd, so = disc.state_dict(), od.state_dict()
+    for k in so:
+        if "running" in k:
+            assert (sd[k].cpu() - so[k]).abs().max().item() <= 2e-2 * (so[k].abs().max().item() + 1e-2), k
+        if k.endswith("num_batches_tracked"):
+            assert int(sd[k]) == int(so[k]) == 2
+
+
+def test_bmgan_contracts(petsyn):
+    g = petsyn.dense_unet_generator(**SMALL).cuda()
+    with pytest.raises(ValueError):
+        g(torch.zeros(1, 1, 48, 64, 64, device="cuda"), torch.zeros(1, 8, device="cuda"))     # 48 % 32 != 0
+    with pytest.raises(ValueError):
+        g(torch.zeros(1, 1, 64, 64, 64, device="cuda"), torch.zeros(1, 4, device="cuda"))     # wrong latent size
+    with pytest.raises(RuntimeError):
+        petsyn.patch_discriminator()(torch.zeros(1, 1, 32, 32, 32))                           # no CPU path
