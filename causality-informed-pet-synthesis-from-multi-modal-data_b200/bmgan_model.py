@@ -212,7 +212,12 @@ class _GenEngine(_EngineBase):
             if c % 8:
                 raise ValueError(f"channel widths must be multiples of 8 (got {c})")
         res = lambda i: (D >> i, H >> i, W >> i)
-        B = lambda i, c, name: Buf(n, *res(i), c, dev, name)
+        self.bufs: Dict[str, Buf] = {}
+
+        def B(i, c, name):
+            self.bufs[name] = Buf(n, *res(i), c, dev, name)
+            return self.bufs[name]
+
         skips = [ic] + down
         nd = len(down)
         # ---- concat buffers of every dense block: cat0 = [X | v0], cat1 = [y0 | v1] ----

@@ -1,10 +1,11 @@
 """Model-level parity of the CUDA BMGAN generator / discriminator against the CPU oracle and the committed golden
 (generated from the reference's own bmgan_model.py over the MONAI stubs).
 
-Tolerances (bf16 operands, fp32 accumulation): synthesized-PET max-abs <= 6e-2 / mean-abs <= 6e-3 (the dense U-Net
-stacks ~60 conv+InstanceNorm layers, twice the depth of the pix2pix U-Net, and InstanceNorm over the 12-voxel bottleneck
-of this small test volume amplifies rounding); losses <= 1 % relative; global grad-norm <= 5 %; per-tensor grad-norms
-<= 15 % for tensors carrying > 0.1 % of the gradient energy.
+Tolerances are PEER-CALIBRATED as SURVEY 8d prescribes: the dense U-Net stacks ~60 conv + InstanceNorm layers, so bf16
+rounding noise (bf16 activations, bf16 weights, fp32 accumulation) compounds to a few percent of the activation scale for
+ANY bf16 implementation.  The peer is the oracle graph itself run by PyTorch/cuDNN on the same GPU under bf16 autocast;
+we require our error against the fp32 CPU oracle to be <= 2x the peer's (plus a small floor): synthesized-PET max-abs /
+mean-abs, loss, global and per-tensor gradient norms, gradient direction.
 """
 import os
 
@@ -46,6 +47,16 @@ def test_generator_step_matches_oracle_and_golden(petsyn):
     lo.backward()
     assert abs(lo.item() - float(gold["g_loss"])) < 1e-4 * abs(float(gold["g_loss"]))     # oracle pinned to the fixture
 
+    # ---- peer: the same graph under bf16 autocast on the GPU ----
+    import copy
+    pg, pd = copy.deepcopy(og).cuda(), copy.deepcopy(od).cuda()
+    pg.zero_grad()
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        lp, ap, l1p, fp = OB.generator_step(pg, pd, t1.cuda(), pet.cuda(), z.cuda())
+    lp.float().backward()
+    peer_err = (fp.detach().float().cpu() - fo.detach()).abs()
+    peer_norm = {k: p.grad.double().norm().item() for k, p in pg.named_parameters()}
+
     gen, disc = gen.cuda(), disc.cuda()
     for p in disc.parameters():
         p.requires_grad_(False)                                   # train_bmgan.py:141-143
@@ -57,33 +68,42 @@ def test_generator_step_matches_oracle_and_golden(petsyn):
     loss.backward()
     torch.cuda.synchronize()
     err = (fake.detach().cpu() - fo.detach()).abs()
-    print("fake err max/mean", err.max().item(), err.mean().item(), "loss", loss.item(), lo.item(), adv.item(), ao.item())
-    assert err.max().item() <= 6e-2 and err.mean().item() <= 6e-3
-    assert np.abs(fake.detach().cpu().numpy()[:, :, ::2, ::2, ::2] - gold["fake_sample"]).max() <= 6e-2
-    assert abs(loss.item() - float(gold["g_loss"])) <= 1e-2 * float(gold["g_loss"])
-    assert abs(adv.item() - float(gold["g_adv"])) <= 2e-2 * float(gold["g_adv"])
-    tot = tot_ref = 0.0
+    print("fake err max/mean ours", err.max().item(), err.mean().item(), "peer", peer_err.max().item(),
+          peer_err.mean().item(), "| loss ours/oracle/peer", loss.item(), lo.item(), lp.item())
+    assert err.max().item() <= 2.0 * peer_err.max().item() + 1e-2
+    assert err.mean().item() <= 2.0 * peer_err.mean().item() + 1e-3
+    gs = np.abs(fake.detach().cpu().numpy()[:, :, ::2, ::2, ::2] - gold["fake_sample"])
+    assert gs.max() <= 2.0 * peer_err.max().item() + 1e-2
+    gl = float(gold["g_loss"])
+    assert abs(loss.item() - gl) <= max(2.0 * abs(lp.item() - gl), 5e-3 * gl)
+    assert abs(adv.item() - float(gold["g_adv"])) <= max(2.0 * abs(ap.item() - float(gold["g_adv"])), 1e-2 * float(gold["g_adv"]))
+    tot = tot_ref = tot_peer = 0.0
     ref_norms = {k: float(gold["gradnorm/" + k]) for k, _ in gen.named_parameters()}
     energy = sum(v * v for v in ref_norms.values())
-    worst = 0.0
+    worst = worst_peer = 0.0
     for k, p in gen.named_parameters():
         gn, ref = p.grad.double().norm().item(), ref_norms[k]
         tot += gn * gn
         tot_ref += ref * ref
+        tot_peer += peer_norm[k] ** 2
         if ref * ref > 1e-3 * energy:
-            worst = max(worst, abs(gn - ref) / ref)
-            assert abs(gn - ref) <= 0.15 * ref, (k, gn, ref)
+            rel, rel_peer = abs(gn - ref) / ref, abs(peer_norm[k] - ref) / ref
+            worst, worst_peer = max(worst, rel), max(worst_peer, rel_peer)
+            assert rel <= max(2.0 * rel_peer, 0.05), (k, gn, ref, peer_norm[k])
         elif k.endswith("bias") and ref < 1e-6:
             assert gn < 1e-4, (k, gn)                              # biases in front of InstanceNorm: exactly zero grad
-    print("global grad-norm", tot ** 0.5, tot_ref ** 0.5, "worst per-tensor rel", worst)
-    assert abs(tot ** 0.5 - tot_ref ** 0.5) <= 5e-2 * tot_ref ** 0.5
+    print("global grad-norm ours/oracle/peer", tot ** 0.5, tot_ref ** 0.5, tot_peer ** 0.5, "worst per-tensor rel", worst,
+          "peer", worst_peer)
+    assert abs(tot ** 0.5 - tot_ref ** 0.5) <= max(2.0 * abs(tot_peer ** 0.5 - tot_ref ** 0.5), 2e-2 * tot_ref ** 0.5)
     # gradient direction on the largest tensors
-    og_grads = dict(og.named_parameters())
+    og_grads, pg_grads = dict(og.named_parameters()), dict(pg.named_parameters())
     for k in sorted(ref_norms, key=ref_norms.get, reverse=True)[:6]:
         a = dict(gen.named_parameters())[k].grad.double().cpu().flatten()
         b = og_grads[k].grad.double().flatten()
+        c = pg_grads[k].grad.double().cpu().flatten()
         cos = (torch.dot(a, b) / (a.norm() * b.norm() + 1e-30)).item()
-        assert cos > 0.97, (k, cos)
+        cos_peer = (torch.dot(c, b) / (c.norm() * b.norm() + 1e-30)).item()
+        assert 1.0 - cos <= max(2.0 * (1.0 - cos_peer), 5e-3), (k, cos, cos_peer)
 
 
 def test_discriminator_phase_matches_oracle_and_golden(petsyn):
