@@ -35,6 +35,15 @@ WORKLOADS = {
     "unet3d_train_cfg1": (64, (96, 112, 96), 1),
     "unet3d_train_s2_b2": (64, (96, 128, 96), 2),
     "unet3d_train_small": (32, (32, 32, 32), 1),
+    # BASELINE configs[2]: BMGAN generator + discriminator adversarial step, per-GPU batch 1 (train_bmgan.py:315);
+    # first field = generator config name
+    "bmgan_adv_step_s2": ("full", (96, 128, 96), 1),
+    "bmgan_adv_step_small": ("small", (64, 96, 64), 1),
+}
+BMGAN_CFG = {
+    "full": {},
+    "small": dict(input_conv_channel=64, output_conv_channel=64, down_channels=[64, 128, 128, 128],
+                  middle_channels=[128], up_channels=[128, 128, 128, 128, 64]),
 }
 METRIC = "3D T1->PET training-step throughput (fwd + L1 + bwd + Adam)"
 UNIT = "volumes/s"
@@ -286,6 +295,186 @@ def run_petsyn(args, ngf, shape, batch):
         dist.destroy_process_group()
 
 
+# ---------------------------------------------------------------------------------------------- BMGAN arms
+def bmgan_batch(shape, seed, batch):
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    d, h, w = shape
+    return (torch.rand(batch, 1, d, h, w, generator=g), torch.rand(batch, 1, d, h, w, generator=g) * 2 - 1,
+            torch.randn(batch, 8, generator=g))
+
+
+def cpu_bmgan_steps(cfg_name, shape, batch, steps, warmup, budget_s=150.0):
+    """Oracle port of the BMGAN adversarial step (G phase + D phase as written) on the host cores."""
+    import torch
+    from oracle import bmgan as OB
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    torch.manual_seed(777)
+    gen, disc = OB.DenseUnetGenerator(**BMGAN_CFG[cfg_name]).train(), OB.PatchDiscriminatorWrapper().train()
+    opt = torch.optim.Adam(gen.parameters(), lr=2e-4)
+
+    def one(shape_):
+        t1, pet, z = bmgan_batch(shape_, 777, batch)
+        t0 = time.perf_counter()
+        loss, _, _, fake = OB.generator_step(gen, disc, t1, pet, z)
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        with torch.no_grad():
+            fake = gen(t1, z)
+        OB.discriminator_step(disc, fake, pet)
+        return time.perf_counter() - t0
+
+    d, h, w = shape
+    small = (32, 64, 32)
+    t_small = one(small)
+    frac_small = (small[0] * small[1] * small[2]) / (d * h * w)
+    use, frac = shape, 1.0
+    if t_small / frac_small * (steps + warmup) > budget_s:
+        use, frac = small, frac_small
+    for _ in range(warmup):
+        one(use)
+    ts = [one(use) for _ in range(steps)]
+    total = sum(ts)
+    sample = (f"{steps} timed + {warmup} warm-up BMGAN adversarial steps (G phase + D phase) of the oracle port (PyTorch "
+              f"fp32 CPU, {cores} threads) on {'the full' if frac == 1.0 else f'a {use[0]}x{use[1]}x{use[2]} crop ({frac:.4f} of the)'} "
+              f"{d}x{h}x{w} volume, batch {batch}; volumes/s scaled by voxel fraction")
+    return batch * frac * steps / total, sample, cores, total / steps * 1e3
+
+
+def run_petsyn_bmgan(args, cfg_name, shape, batch):
+    import torch
+    import torch.distributed as dist
+
+    import petsyn
+    from petsyn_b200 import ops
+    from petsyn_b200.train import BmganTrainer
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    torch.manual_seed(777)
+    gen = petsyn.dense_unet_generator(**BMGAN_CFG[cfg_name]).to(dev).train()
+    disc = petsyn.patch_discriminator().to(dev).train()
+    pool = 3
+    host = [bmgan_batch(shape, 777 + 1000 * rank + i, batch) for i in range(pool)]
+    pinned = [tuple(t.pin_memory() for t in b) for b in host]
+    resident = [tuple(t.to(dev) for t in b) for b in host]
+    trainer = BmganTrainer(gen, disc, lr=2e-4, example_input=resident[0][0])
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(2):
+        trainer.step(*resident[i % pool])
+    torch.cuda.synchronize()
+    n0 = ops.launch_count()
+    trainer.step(*resident[0])
+    torch.cuda.synchronize()
+    launches = ops.launch_count() - n0
+    if not args.no_graph and world == 1:
+        trainer.capture()
+    for i in range(max(args.warmup, 3)):
+        trainer.step(*resident[i % pool])
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        losses = trainer.step(*resident[i % pool])
+    e1.record()
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    final = [float(l.item()) for l in losses]
+    stat = trainer.static if trainer.graph is not None else tuple(torch.empty_like(t) for t in resident[0])
+    loss_host = torch.zeros(4, dtype=torch.float32).pin_memory()
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for i in range(args.steps):
+        for dst, src in zip(stat, pinned[i % pool]):
+            dst.copy_(src, non_blocking=True)
+        ls = trainer.step(*stat)
+        for j, l in enumerate(ls):
+            loss_host[j:j + 1].copy_(l, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+    f1.record()
+    barrier()
+    ms_e2e = f0.elapsed_time(f1)
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms_total, ms_e2e], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total, ms_e2e = t.tolist()
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak_tf = float(peaks.get("bf16_tflops_sustained", 1400.0))
+        d, h, w = shape
+        gf, df = trainer.geng.flops_algorithmic, trainer.deng.flops_algorithmic
+        # algorithmic FLOPs of the step: G fwd+bwd (3x) + G fwd again (1x); D: 3 fwd + dgrad-only bwd (1x) + 2 full bwd (2x each)
+        step_flops = 4.0 * gf + (3.0 + 1.0 + 4.0) * df
+        ms = ms_total / args.steps
+        ach = step_flops / (ms * 1e-3) / 1e12
+        line = {
+            "metric": "BMGAN adversarial-step throughput (G phase + D phase, train_bmgan.py:141-200 without LPIPS/encoder)",
+            "value": world * batch * args.steps / (ms_total * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": args.workload, "model": f"dense_unet_generator({cfg_name}) + patch_discriminator()",
+                       "volume": list(shape), "per_gpu_batch": batch, "global_batch": batch * world,
+                       "parallelism": f"dp{world}", "optimizer": "Adam(lr=2e-4) on G; D as written (never stepped)",
+                       "loss": "LSGAN + 20*L1", "cuda_graph": trainer.graph is not None,
+                       "l2": "per-step working set (> 5 GB) exceeds the 126 MB L2; inputs rotate over 3 batches"},
+            "e2e": {"value": world * batch * args.steps / (ms_e2e * 1e-3), "unit": UNIT,
+                    "h2d_bytes_per_step": 2 * batch * d * h * w * 4 + batch * 32, "d2h_bytes_per_step": 16,
+                    "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": launches * args.steps, "clocks": clocks,
+            "roofline": {"bound": "tensor", "kernel": "all convolution kernels of the step (igemm/wgrad); whole-step "
+                         "algorithmic conv FLOPs / step time", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s",
+                         "frac": ach / peak_tf, "traffic": None,
+                         "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback",
+                         "generator_fwd_gflop": gf / 1e9, "discriminator_fwd_gflop": df / 1e9},
+            "final_losses": {"adv": final[0], "l1": final[1], "d_fake": final[2], "d_real": final[3]},
+        }
+        if not args.no_cpu_baseline and world == 1:
+            v, sample, cores, _ = cpu_bmgan_steps(cfg_name, shape, batch, 1, 0, budget_s=30.0)
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def run_reference_bmgan(args, cfg_name, shape, batch):
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    vol_s, sample, cores, ms = cpu_bmgan_steps(cfg_name, shape, batch, args.steps, args.warmup)
+    print(json.dumps({
+        "impl": "reference", "metric": "BMGAN adversarial-step throughput (G phase + D phase, train_bmgan.py:141-200 "
+        "without LPIPS/encoder)", "value": vol_s, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.workload, "model": f"dense_unet_generator({cfg_name}) + patch_discriminator()",
+                   "volume": list(shape), "per_gpu_batch": batch},
+        "cpu_baseline": {"value": vol_s, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": vol_s, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}),
+        flush=True)
+
+
 def count_launches(trainer, batch) -> int:
     """Kernels of OUR library launched by one trainer.step() (petsyn_launch_count() delta)."""
     import torch
@@ -309,7 +498,9 @@ def main():
     ap.add_argument("--no-graph", action="store_true", help="launch kernels eagerly instead of replaying a CUDA graph")
     args = ap.parse_args()
     ngf, shape, batch = WORKLOADS[args.workload]
-    if args.impl == "reference":
+    if args.workload.startswith("bmgan"):
+        (run_reference_bmgan if args.impl == "reference" else run_petsyn_bmgan)(args, ngf, shape, batch)
+    elif args.impl == "reference":
         run_reference(args, ngf, shape, batch)
     else:
         run_petsyn(args, ngf, shape, batch)

@@ -308,12 +308,29 @@ class _GenEngine(_EngineBase):
               "take_channel0")
         return self.y
 
-    def backward(self, dy: torch.Tensor, need_dx: bool = False, out: Optional[Dict[int, torch.Tensor]] = None):
+    def backward(self, dy: torch.Tensor, need_dx: bool = False, out: Optional[Dict[int, torch.Tensor]] = None,
+                 on_ready=None):
         grads = self.grad_slots(out)
         check(lib.petsyn_put_channel0_grad(ptr(self.y), ptr(dy), ptr(self.head.zg), dy.numel(), self.head.cout, 1,
                                            stream_ptr()), "put_channel0_grad")
-        self.tape.backward()
+        cb = None
+        if on_ready is not None:
+            by_op: Dict[int, List[nn.Parameter]] = {}
+            for op, _, p in self._bind:
+                by_op.setdefault(id(op), []).append(p)
+            cb = lambda op: [on_ready(p) for p in by_op.get(id(op), [])]
+        self.tape.backward(cb)
         return None, ([g.clone() for g in grads] if out is None else [])
+
+    def grad_order(self) -> List[nn.Parameter]:
+        """Parameters in the order backward produces their gradients (reverse op order)."""
+        order, seen = [], set()
+        for op in reversed(self.tape.ops):
+            for o, _, p in self._bind:
+                if o is op and id(p) not in seen:
+                    seen.add(id(p))
+                    order.append(p)
+        return order
 
 
 # ------------------------------------------------------------------------------------------------ discriminator
@@ -383,6 +400,7 @@ class _StemOp(graph.Op):
         self.dpatches = torch.zeros_like(self.stem.patches)
         self.dbias = torch.zeros(conv.out_channels, dtype=torch.float32, device=dev)
         self.grad_w = self.grad_b = None
+        self.acc_dw = False
         self.flops = 2.0 * self.z.rows * conv.out_channels * 64
         self._ver = None
 
@@ -402,10 +420,13 @@ class _StemOp(graph.Op):
     def bwd(self) -> None:
         eng, st = self.eng, self.stem
         if eng.need_dw:
-            st.plan.wgrad(st.patches, self.z.g, self.grad_w)
+            st.plan.wgrad(st.patches, self.z.g, self.grad_w, accumulate=self.acc_dw)
             check(lib.petsyn_colsum(ptr(self.z.g), self.z.c, 0, ptr(self.dbias), self.z.rows, self.z.c, stream_ptr()),
                   "colsum")
-            self.grad_b.copy_(self.dbias)
+            if self.acc_dw:
+                self.grad_b.add_(self.dbias)
+            else:
+                self.grad_b.copy_(self.dbias)
         if eng.need_dx:
             st.plan.dgrad(self.z.g, self.dpatches)
             check(lib.petsyn_stem_col2im_k4s2(ptr(self.dpatches), ptr(eng.dx), st.n, st.d, st.h, st.w, stream_ptr()),
@@ -446,11 +467,15 @@ class _DiscEngine(_EngineBase):
         self.logits = torch.zeros(n, 1, od, oh, ow, dtype=torch.float32, device=dev)
         self._finish()
 
-    def set_mode(self, need_dx: bool, need_dw: bool) -> None:
-        """G phase: frozen weights, gradient w.r.t. the input; D phase: weight gradients only."""
+    def set_mode(self, need_dx: bool, need_dw: bool, accumulate: bool = False) -> None:
+        """G phase: frozen weights, gradient w.r.t. the input; D phase: weight gradients only (``accumulate`` for the
+        second of the two backward calls of train_bmgan.py:191-196)."""
         self.need_dx, self.need_dw = need_dx, need_dw
         for cv in self.convs:
             cv.need_dw = need_dw
+        for op in self.tape.ops:
+            if hasattr(op, "acc_dw"):
+                op.acc_dw = accumulate
 
     def forward(self, x: torch.Tensor, _unused=None) -> torch.Tensor:
         self.x = x
@@ -459,10 +484,12 @@ class _DiscEngine(_EngineBase):
                                        stream_ptr()), "take_channel0")
         return self.logits
 
-    def backward(self, dlogits: torch.Tensor, need_dx: bool = True, out: Optional[Dict[int, torch.Tensor]] = None):
+    def backward(self, dlogits: torch.Tensor, need_dx: bool = True, out: Optional[Dict[int, torch.Tensor]] = None,
+                 need_dw: Optional[bool] = None, accumulate: bool = False):
         self.need_dx = need_dx
-        need_dw = any(p.requires_grad for p in self.params)
-        self.set_mode(need_dx, need_dw)
+        if need_dw is None:
+            need_dw = any(p.requires_grad for p in self.params)
+        self.set_mode(need_dx, need_dw, accumulate)
         grads = self.grad_slots(out)
         check(lib.petsyn_put_channel0_grad(None, ptr(dlogits), ptr(self.head.zg), dlogits.numel(), self.head.cout, 0,
                                            stream_ptr()), "put_channel0_grad")

@@ -105,6 +105,7 @@ class ConvOp(Op):
             self.bias_stage = torch.zeros(self.cout, dtype=torch.float32, device=dev)
         self.dbias_stage = torch.zeros(self.cout, dtype=torch.float32, device=dev) if bias is not None else None
         self.acc_dx = False
+        self.acc_dw = False      # add into grad_w / grad_b instead of overwriting (several backward calls per step)
         self._ver = None
         self.grad_w: Optional[torch.Tensor] = None     # set by the owner: where dW / dbias go
         self.grad_b: Optional[torch.Tensor] = None
@@ -148,18 +149,23 @@ class ConvOp(Op):
         if self.need_dw:
             if self.padded:
                 self.plan.wgrad(self.x.buf.t, dz, self.dw_stage)
-                if self.opcode == ops.OP_CONVT:
-                    self.grad_w.copy_(self.dw_stage[:self.cin_w, :self.cout_w])
+                part = self.dw_stage[:self.cin_w, :self.cout_w] if self.opcode == ops.OP_CONVT else \
+                    self.dw_stage[:self.cout_w, :self.cin_w]
+                if self.acc_dw:
+                    self.grad_w.add_(part)
                 else:
-                    self.grad_w.copy_(self.dw_stage[:self.cout_w, :self.cin_w])
+                    self.grad_w.copy_(part)
             else:
-                self.plan.wgrad(self.x.buf.t, dz, self.grad_w)
+                self.plan.wgrad(self.x.buf.t, dz, self.grad_w, accumulate=self.acc_dw)
             if self.bias is not None:
                 if self.use_bias:
                     check(lib.petsyn_colsum(ptr(dz), self.cout, 0, ptr(self.dbias_stage), dz.shape[0], self.cout,
                                             stream_ptr()), "colsum")
-                    self.grad_b.copy_(self.dbias_stage[:self.cout_w])
-                else:
+                    if self.acc_dw:
+                        self.grad_b.add_(self.dbias_stage[:self.cout_w])
+                    else:
+                        self.grad_b.copy_(self.dbias_stage[:self.cout_w])
+                elif not self.acc_dw:
                     self.grad_b.zero_()     # a bias in front of a non-affine InstanceNorm has exactly zero gradient
         if self.need_dx:
             if self.acc_dx:
@@ -189,7 +195,8 @@ class NormActOp(Op):
         self.acc_res = False
         self.grad_gamma: Optional[torch.Tensor] = None
         self.grad_beta: Optional[torch.Tensor] = None
-        self.need_dz = True
+        self.acc_dw = False
+        self._tmp_gb: Optional[torch.Tensor] = None
 
     def _desc(self, backward: bool) -> _cabi.NormActDesc:
         z = self.z
@@ -216,7 +223,12 @@ class NormActOp(Op):
         if backward:
             d.dz = ptr(z.g)
             if self.grad_gamma is not None:
-                d.dgamma, d.dbeta = ptr(self.grad_gamma), ptr(self.grad_beta)
+                if self.acc_dw:
+                    if self._tmp_gb is None:
+                        self._tmp_gb = torch.zeros(2, z.c, dtype=torch.float32, device=z.t.device)
+                    d.dgamma, d.dbeta = ptr(self._tmp_gb[0]), ptr(self._tmp_gb[1])
+                else:
+                    d.dgamma, d.dbeta = ptr(self.grad_gamma), ptr(self.grad_beta)
         return d
 
     def fwd(self, training: bool) -> None:
@@ -251,6 +263,9 @@ class NormActOp(Op):
     def bwd(self) -> None:
         d = self._desc(True)
         check(lib.petsyn_normact_bwd(C.byref(d), stream_ptr()), "normact_bwd")
+        if self.acc_dw and self.grad_gamma is not None:
+            self.grad_gamma.add_(self._tmp_gb[0])
+            self.grad_beta.add_(self._tmp_gb[1])
 
 
 class Tape:
@@ -296,9 +311,11 @@ class Tape:
         for op in self.ops:
             op.fwd(training)
 
-    def backward(self) -> None:
+    def backward(self, on_op_done=None) -> None:
         for op in reversed(self.ops):
             op.bwd()
+            if on_op_done is not None:
+                on_op_done(op)
 
     def flops(self) -> float:
         return sum(getattr(op, "flops", 0.0) for op in self.ops)

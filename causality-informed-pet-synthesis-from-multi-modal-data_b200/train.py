@@ -243,3 +243,136 @@ class Unet3dTrainer:
         out = torch.zeros(1, dtype=torch.float32, device=self.dev)
         ops.sumsq(self.arena.g, out)
         return float(out.item()) ** 0.5
+
+
+class BmganTrainer:
+    """One BMGAN "adversarial step" as written in ``bl_methods/BMGAN/train_bmgan.py:141-200``, minus the
+    parts that cannot exist offline (LPIPS needs downloaded weights) and the encoder phase (not built yet):
+
+      G phase (:141-161)  fake = G(t1, z); loss = LSGAN(D(fake), real) + lamda_l1 * L1(fake, pet); D frozen;
+                          backward through D (data gradient only) into G; [bucketed all-reduce]; Adam on G.
+      D phase (:183-200)  G forward again (weights just changed; the reference recomputes under no_grad), then
+                          LSGAN(D(fake), fake) and LSGAN(D(real), real): two backward calls whose weight gradients
+                          accumulate.  The reference never calls ``d_optimizer.step()``: reproduced
+                          "as written" -- D stays at its initialisation; set ``step_discriminator=True`` for the
+                          evidently intended behaviour.
+    Per-GPU batch 1 (train_bmgan.py:315); data parallel exactly like Unet3dTrainer (flat arenas, bucketed all-reduce of
+    G's gradients overlapped with backward, per-rank normalisation statistics).
+    """
+
+    def __init__(self, gen, disc, lr: float = 2e-4, betas=(0.9, 0.999), eps: float = 1e-8, lamda_l1: float = 20.0,
+                 bucket_mb: float = 64.0, process_group=None, example_input: Optional[torch.Tensor] = None,
+                 step_discriminator: bool = False):
+        if example_input is None:
+            raise ValueError("example_input (a tensor of the training shape) is required to lay out the arenas")
+        self.gen, self.disc = gen, disc
+        self.lr, self.betas, self.eps, self.lamda_l1 = lr, betas, eps, lamda_l1
+        self.step_discriminator = step_discriminator
+        self.pg = process_group
+        self.world = dist.get_world_size(process_group) if (dist.is_available() and dist.is_initialized()) else 1
+        dev = example_input.device
+        self.dev = dev
+        self.geng = gen.engine_for(example_input)
+        self.deng = disc.engine_for(example_input)
+        self.garena = FlatArena(self.geng.grad_order(), dev)
+        self.darena = FlatArena(list(self.deng.params), dev)
+        self.gm, self.gv = torch.zeros_like(self.garena.p), torch.zeros_like(self.garena.p)
+        self.dm, self.dv = torch.zeros_like(self.darena.p), torch.zeros_like(self.darena.p)
+        self.step_dev = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.step_count = 0
+        f = lambda: torch.zeros(1, dtype=torch.float32, device=dev)
+        self.loss_adv, self.loss_l1, self.loss_d_fake, self.loss_d_real = f(), f(), f(), f()
+        self.dy = torch.zeros(example_input.shape, dtype=torch.float32, device=dev)
+        self.dlogits = torch.zeros_like(self.deng.logits)
+        self.bucketer = GradBucketer(self.garena, bucket_mb, process_group)
+        self.graph = None
+        self.static = None
+        if self.world > 1:
+            dist.broadcast(self.garena.p, src=0, group=self.pg)
+            dist.broadcast(self.darena.p, src=0, group=self.pg)
+            for b in list(gen.buffers()) + list(disc.buffers()):
+                if b.dtype.is_floating_point:
+                    dist.broadcast(b, src=0, group=self.pg)
+        self._dirty()
+
+    def _dirty(self) -> None:
+        for op in self.geng.tape.ops:
+            if hasattr(op, "_ver"):
+                op._ver = None
+
+    def _step_impl(self, t1: torch.Tensor, pet: torch.Tensor, z: torch.Tensor) -> None:
+        geng, deng = self.geng, self.deng
+        # ---------------- G phase ----------------
+        fake = geng.forward(t1, z)
+        logits = deng.forward(fake)
+        self.loss_adv.zero_()
+        ops.mse_const_fwd_bwd(logits, 1.0, self.loss_adv, self.dlogits)
+        dfake, _ = deng.backward(self.dlogits, need_dx=True, out=self.darena.grad_views, need_dw=False)
+        self.loss_l1.zero_()
+        ops.l1_loss_fwd_bwd(fake, pet, self.loss_l1, self.dy, grad_scale=self.lamda_l1)
+        self.dy.add_(dfake)
+        geng.backward(self.dy, out=self.garena.grad_views, on_ready=self.bucketer.on_ready)
+        self.bucketer.wait_all()
+        self.step_dev.add_(1)
+        ops.adam_step(self.garena.p, self.garena.g, self.gm, self.gv, self.lr, self.betas[0], self.betas[1], self.eps, 0,
+                      step_dev=self.step_dev)
+        self._dirty()
+        # ---------------- D phase ----------------
+        fake = geng.forward(t1, z)                                   # recomputed with the updated generator
+        logits = deng.forward(fake)
+        self.loss_d_fake.zero_()
+        ops.mse_const_fwd_bwd(logits, 0.0, self.loss_d_fake, self.dlogits)
+        deng.backward(self.dlogits, need_dx=False, out=self.darena.grad_views, need_dw=True,
+                      accumulate=not self.step_discriminator)
+        logits = deng.forward(pet)
+        self.loss_d_real.zero_()
+        ops.mse_const_fwd_bwd(logits, 1.0, self.loss_d_real, self.dlogits)
+        deng.backward(self.dlogits, need_dx=False, out=self.darena.grad_views, need_dw=True, accumulate=True)
+        if self.step_discriminator:
+            if self.world > 1:
+                dist.all_reduce(self.darena.g, op=dist.ReduceOp.AVG, group=self.pg)
+            ops.adam_step(self.darena.p, self.darena.g, self.dm, self.dv, self.lr, self.betas[0], self.betas[1], self.eps,
+                          0, step_dev=self.step_dev)
+            for op in self.deng.tape.ops:
+                if hasattr(op, "_ver"):
+                    op._ver = None
+
+    def step(self, t1: torch.Tensor, pet: torch.Tensor, z: torch.Tensor):
+        """Returns the device tensors (adv, l1, d_fake, d_real) of this rank's micro-batch."""
+        self.step_count += 1
+        if self.graph is not None:
+            for dst, src in zip(self.static, (t1, pet, z)):
+                if dst.data_ptr() != src.data_ptr():
+                    dst.copy_(src, non_blocking=True)
+            self.graph.replay()
+        else:
+            self._step_impl(t1, pet, z)
+        return self.loss_adv, self.loss_l1, self.loss_d_fake, self.loss_d_real
+
+    def capture(self, warmup: int = 2) -> None:
+        """Single-GPU only: the whole adversarial step as one CUDA graph (state is restored after the warm-up)."""
+        if self.world > 1:
+            raise RuntimeError("BmganTrainer.capture supports world_size 1; data-parallel runs launch eagerly")
+        snap = [t.clone() for t in (self.garena.p, self.gm, self.gv, self.darena.p, self.darena.g, self.dm, self.dv,
+                                    self.step_dev)]
+        bufs = [b.clone() for b in list(self.gen.buffers()) + list(self.disc.buffers())]
+        n = self.dy.shape[0]
+        self.static = (torch.zeros_like(self.dy), torch.zeros_like(self.dy),
+                       torch.zeros(n, self.gen.cfg["input_channel"] - 1, dtype=torch.float32, device=self.dev))
+        side = torch.cuda.Stream(device=self.dev)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                self._step_impl(*self.static)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize(self.dev)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self._step_impl(*self.static)
+        for dst, src in zip((self.garena.p, self.gm, self.gv, self.darena.p, self.darena.g, self.dm, self.dv,
+                             self.step_dev), snap):
+            dst.copy_(src)
+        for dst, src in zip(list(self.gen.buffers()) + list(self.disc.buffers()), bufs):
+            dst.copy_(src)
+        self._dirty()
+        self.graph = g
