@@ -25,7 +25,7 @@ lib = C.CDLL(LIB_PATH)
 
 # ---------------------------------------------------------------------------------------------- constants
 OP_CONV, OP_UPCONV, OP_CONVT = 0, 1, 2
-ACT_NONE, ACT_RELU, ACT_LRELU, ACT_SILU, ACT_TANH = 0, 1, 2, 3, 4
+ACT_NONE, ACT_RELU, ACT_LRELU, ACT_SILU, ACT_TANH, ACT_PRELU = 0, 1, 2, 3, 4, 5
 E_INVAL, E_CUDA, E_NOMEM = -1, -2, -3
 
 
@@ -57,6 +57,7 @@ class NormActDesc(C.Structure):
         ("slope", C.c_float),
         ("res", C.c_void_p), ("res_cstride", C.c_int32), ("res_coff", C.c_int32), ("res_accumulate", C.c_int32),
         ("sums", C.c_void_p), ("dz", C.c_void_p), ("dgamma", C.c_void_p), ("dbeta", C.c_void_p),
+        ("slope_dev", C.c_void_p), ("dslope", C.c_void_p),
     ]
 
 
@@ -104,6 +105,7 @@ SIGNATURES = {
                                          _f32, _vp, _vp, _vp, _vp, _i64, _i32, _vp]),
     "petsyn_l1_loss_fwd_bwd": (_i32, [_vp, _vp, _vp, _vp, _i64, _f32, _vp]),
     "petsyn_mse_const_fwd_bwd": (_i32, [_vp, _f32, _vp, _vp, _i64, _f32, _vp]),
+    "petsyn_kl_fwd_bwd": (_i32, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _f32, _vp]),
     "petsyn_adam_step": (_i32, [_vp, _vp, _vp, _vp, _i64, _f32, _f32, _f32, _f32, _i32, _vp, _vp]),
     "petsyn_sumsq": (_i32, [_vp, _vp, _i64, _vp]),
 }

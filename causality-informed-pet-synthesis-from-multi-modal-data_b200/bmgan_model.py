@@ -498,3 +498,190 @@ class _DiscEngine(_EngineBase):
         if out is not None:
             return dx, []
         return dx, [g.clone() if need_dw else None for g in grads]
+
+
+# ------------------------------------------------------------------------------------------------ encoder
+class _ResidualUnitS2(_Container):
+    """MONAI ``ResidualUnit(3, cin, c, strides=2, padding=1)``: ``conv.unit0`` (k3 s2) and ``conv.unit1`` (k3 s1), each
+    Conv -> InstanceNorm -> PReLU; ``residual`` = Conv3d(cin, c, 3, 2, 1)."""
+
+    def __init__(self, cin, c):
+        super().__init__()
+        self.conv = nn.Sequential()
+        for su, (a, s) in enumerate(((cin, 2), (c, 1))):
+            unit = nn.Sequential()
+            unit.add_module("conv", nn.Conv3d(a, c, 3, stride=s, padding=1, bias=True))
+            adn = nn.Sequential()
+            adn.add_module("N", nn.InstanceNorm3d(c))
+            adn.add_module("A", nn.PReLU())
+            unit.add_module("adn", adn)
+            self.conv.add_module(f"unit{su:d}", unit)
+        self.residual = nn.Conv3d(cin, c, 3, 2, 1, bias=True)
+
+
+class ResNet_encoder(nn.Module):
+    """B200-native ``ResNet_encoder`` (bmgan_model.py:103-130): PET volume -> (mu, logvar) in R^8.  Like the reference
+    (``nn.Linear(128*8, 8)``, :119) it accepts only volumes that six stride-2 stages reduce to 2x2x2."""
+
+    def __init__(self, input_layer_channel=32, channels=[64, 128, 128, 128, 128, 128]):
+        super().__init__()
+        self.input_layer = nn.Sequential(nn.Conv3d(1, input_layer_channel, 3, padding=1),
+                                         nn.InstanceNorm3d(input_layer_channel), nn.ReLU())
+        self.resblocks = nn.ModuleList([])
+        cur = input_layer_channel
+        for c in channels:
+            self.resblocks.append(_ResidualUnitS2(cur, c))
+            cur = c
+        self.linear1 = nn.Linear(128 * 8, 8)
+        self.linear2 = nn.Linear(128 * 8, 8)
+        self._engines: Dict[Tuple, "_EncEngine"] = {}
+
+    def engine_for(self, x: torch.Tensor) -> "_EncEngine":
+        key = (tuple(x.shape), x.device.index)
+        eng = self._engines.get(key)
+        if eng is None:
+            eng = _EncEngine(self, tuple(x.shape), x.device)
+            self._engines[key] = eng
+        return eng
+
+    def forward(self, x: torch.Tensor):
+        if not x.is_cuda:
+            raise RuntimeError("petsyn ResNet_encoder runs on CUDA (sm_100a) only; there is no CPU path")
+        if x.dim() != 5 or x.shape[1] != 1:
+            raise ValueError(f"expected x of shape [N, 1, D, H, W], got {tuple(x.shape)}")
+        x = x.contiguous().float()
+        eng = self.engine_for(x)
+        if torch.is_grad_enabled() and any(p.requires_grad for p in eng.params):
+            out = _EncFn.apply(eng, x, *eng.params)
+        else:
+            out = eng.forward(x).clone()
+        return out[:, :8], out[:, 8:16]
+
+
+class _EncFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, eng, x, *params):
+        ctx.eng = eng
+        return eng.forward(x).clone()
+
+    @staticmethod
+    def backward(ctx, dout):
+        grads = ctx.eng.backward(dout.contiguous().float())
+        return (None, None, *grads)
+
+
+class _LinearHeads(graph.Op):
+    """linear1 / linear2 on nn.Flatten() of the NCDHW feature map = ONE k=1 conv on the channels-last buffer with the
+    weight columns permuted from (c, voxel) to (voxel, c) order; fp32 output [N, 16] = [mu | logvar]."""
+
+    def __init__(self, feat: Buf, lin1: nn.Linear, lin2: nn.Linear, dev):
+        self.lin = (lin1, lin2)
+        n, c = feat.n, feat.c
+        self.vox = feat.rows // n
+        self.c = c
+        flat = feat.alias(n, 1, 1, 1, self.vox * c, "enc.flat")
+        self.flat = flat
+        self.plan = ops.ConvPlan(ops.OP_CONV, n, 1, 1, 1, self.vox * c, 16, 1, 1, 0, y_fp32=True)
+        self.w = torch.zeros(16, self.vox * c, 1, 1, 1, dtype=torch.float32, device=dev)
+        self.dw = torch.zeros_like(self.w)
+        self.b = torch.zeros(16, dtype=torch.float32, device=dev)
+        self.out = torch.zeros(n, 16, dtype=torch.float32, device=dev)
+        self.dout = torch.zeros(n, 16, dtype=torch.bfloat16, device=dev)
+        self.db = torch.zeros(16, dtype=torch.float32, device=dev)
+        self.grad = {}          # id(param) -> tensor, bound by the engine
+        self.acc_dw = False
+        self.flops = 2.0 * n * self.vox * c * 16
+        self._ver = None
+
+    def repack(self) -> None:
+        l1, l2 = self.lin
+        ver = (l1.weight._version, l1.weight.data_ptr(), l2.weight._version, l1.bias._version, l2.bias._version)
+        if ver == self._ver:
+            return
+        for i, l in enumerate(self.lin):      # Flatten order is (c, voxel); the buffer is (voxel, c)
+            self.w[8 * i:8 * i + 8, :, 0, 0, 0].copy_(
+                l.weight.detach().view(8, self.c, self.vox).permute(0, 2, 1).reshape(8, -1))
+            self.b[8 * i:8 * i + 8].copy_(l.bias.detach())
+        self.plan.pack(self.w, need_dgrad=True)
+        self._ver = ver
+
+    def fwd(self, training: bool) -> None:
+        self.plan.fprop(self.flat.t, self.out, self.b)
+
+    def grad_writes(self):
+        return [("dx", self.flat.sl())]
+
+    def bwd(self) -> None:
+        self.plan.wgrad(self.flat.t, self.dout, self.dw)
+        check(lib.petsyn_colsum(ptr(self.dout), 16, 0, ptr(self.db), self.dout.shape[0], 16, stream_ptr()), "colsum")
+        for i, l in enumerate(self.lin):
+            gw = self.dw[8 * i:8 * i + 8, :, 0, 0, 0].view(8, self.vox, self.c).permute(0, 2, 1).reshape(8, -1)
+            if self.acc_dw:
+                self.grad[id(l.weight)].add_(gw)
+                self.grad[id(l.bias)].add_(self.db[8 * i:8 * i + 8])
+            else:
+                self.grad[id(l.weight)].copy_(gw)
+                self.grad[id(l.bias)].copy_(self.db[8 * i:8 * i + 8])
+        self.plan.dgrad(self.dout, self.flat.g)
+
+
+class _EncEngine(_EngineBase):
+    CPAD_IN = 16
+
+    def __init__(self, enc: ResNet_encoder, shape, dev):
+        super().__init__(enc, dev)
+        n, _, D, H, W = shape
+        self.shape = shape
+        t = self.tape
+        self.inp = Buf(n, D, H, W, self.CPAD_IN, dev, "enc.in")
+        c0 = self._conv(self.inp.sl(), enc.input_layer[0], ksize=3, stride=1, pad=1, use_bias=False, need_dx=False,
+                        name="enc.conv_in")
+        a = Buf(n, D, H, W, c0.z.c, dev, "enc.a0")
+        t.add(NormActOp(c0.z, "instance", ops.ACT_RELU, [a.sl()]))
+        self.prelu_ops: List[Tuple[NormActOp, nn.Parameter]] = []
+        for i, ru in enumerate(enc.resblocks):
+            u0, u1 = ru.conv.unit0, ru.conv.unit1
+            cv0 = self._conv(a.sl(), u0.conv, ksize=3, stride=2, pad=1, use_bias=False, name=f"enc.{i}.u0")
+            zc = cv0.z
+            h0 = Buf(zc.n, zc.d, zc.h, zc.w, zc.c, dev, f"enc.{i}.h0")
+            n0 = NormActOp(zc, "instance", ops.ACT_PRELU, [h0.sl()], slope_param=u0.adn.A.weight)
+            t.add(n0)
+            cvr = self._conv(a.sl(), ru.residual, ksize=3, stride=2, pad=1, use_bias=True, name=f"enc.{i}.res")
+            cv1 = self._conv(h0.sl(), u1.conv, ksize=3, stride=1, pad=1, use_bias=False, name=f"enc.{i}.u1")
+            a = Buf(zc.n, zc.d, zc.h, zc.w, zc.c, dev, f"enc.{i}.out")
+            n1 = NormActOp(cv1.z, "instance", ops.ACT_PRELU, [a.sl()], res=cvr.z.sl(), slope_param=u1.adn.A.weight)
+            t.add(n1)
+            for nm, prm in ((n0, u0.adn.A.weight), (n1, u1.adn.A.weight)):
+                self._bind.append((nm, "grad_slope", prm))
+        if (a.d, a.h, a.w) != (2, 2, 2) or a.c != 128:
+            raise ValueError(f"ResNet_encoder needs an input that reduces to 128 x 2x2x2 (got {a.c} x {a.d}x{a.h}x{a.w}); "
+                             "the reference hard-codes nn.Linear(128*8, 8)")
+        self.heads = _LinearHeads(a, enc.linear1, enc.linear2, dev)
+        t.add(self.heads)
+        for l in (enc.linear1, enc.linear2):
+            self._bind += [(self.heads, "_w", l.weight), (self.heads, "_b", l.bias)]
+        self._finish()
+
+    def grad_slots(self, out=None):
+        grads = super().grad_slots(out)
+        self.heads.grad = {id(p): g for p, g in zip(self.params, grads)}
+        return grads
+
+    def set_accumulate(self, acc: bool) -> None:
+        for op in self.tape.ops:
+            if hasattr(op, "acc_dw"):
+                op.acc_dw = acc
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        n, _, D, H, W = self.shape
+        check(lib.petsyn_concat_latent(ptr(x), ptr(x), ptr(self.inp.t), D * H * W, n, 0, self.CPAD_IN, stream_ptr()),
+              "concat_latent")
+        self.tape.forward(self.module.training)
+        return self.heads.out
+
+    def backward(self, dout: torch.Tensor, out: Optional[Dict[int, torch.Tensor]] = None, accumulate: bool = False):
+        grads = self.grad_slots(out)
+        self.set_accumulate(accumulate)
+        self.heads.dout.copy_(dout)
+        self.tape.backward()
+        return [g.clone() for g in grads] if out is None else []

@@ -664,14 +664,15 @@ int32_t petsyn_conv_plan_create(const petsyn_conv_desc* d, petsyn_conv_plan** ou
       delete pl;
       return fail(PETSYN_EINVAL, "Conv3d: unsupported kernel/stride/pad %d/%d/%d", k, s, p);
     }
-    if (s == 2 && ((d->d | d->h | d->w) & 1)) {
-      delete pl;
-      return fail(PETSYN_EINVAL, "stride-2 Conv3d needs even input dims, got %dx%dx%d", d->d, d->h, d->w);
-    }
     od = (d->d + 2 * p - k) / s + 1; oh = (d->h + 2 * p - k) / s + 1; ow = (d->w + 2 * p - k) / s + 1;
-    if (s == 2 && (od * 2 != d->d || oh * 2 != d->h || ow * 2 != d->w)) {
+    if (od < 1 || oh < 1 || ow < 1) {
       delete pl;
-      return fail(PETSYN_EINVAL, "stride-2 Conv3d must halve the dims exactly (k=%d p=%d)", k, p);
+      return fail(PETSYN_EINVAL, "Conv3d: empty output for input %dx%dx%d (k=%d s=%d p=%d)", d->d, d->h, d->w, k, s, p);
+    }
+    if (s == 2 && (od != (d->d + 1) / 2 || oh != (d->h + 1) / 2 || ow != (d->w + 1) / 2)) {
+      delete pl;
+      return fail(PETSYN_EINVAL, "stride-2 Conv3d must map n -> ceil(n/2) (k=%d p=%d on %dx%dx%d)", k, p, d->d, d->h,
+                  d->w);
     }
     fwd = (s == 1) ? axis_s1(k, p, +1) : axis_s2_gather(k, p);
     bwd = (s == 1) ? axis_s1(k, p, -1) : axis_s2_scatter(k, p);
@@ -717,9 +718,9 @@ int32_t petsyn_conv_plan_create(const petsyn_conv_desc* d, petsyn_conv_plan** ou
     g.prog = make_program(bwd, k);
     g.R = d->cin; g.Kc = d->cout;
     g.swap = (d->op != PETSYN_OP_CONVT);
-    g.out_w = g.prog.out_phased ? d->w / 2 : d->w;
-    g.out_h = g.prog.out_phased ? d->h / 2 : d->h;
-    g.out_d = g.prog.out_phased ? d->d / 2 : d->d;
+    g.out_w = g.prog.out_phased ? (d->w + 1) / 2 : d->w;      // phase 0 of an odd extent has one more element
+    g.out_h = g.prog.out_phased ? (d->h + 1) / 2 : d->h;
+    g.out_d = g.prog.out_phased ? (d->d + 1) / 2 : d->d;
     g.out_rows_full = (int64_t)d->n * d->d * d->h * d->w;
     rc = finish_side(g, d->n);
   }

@@ -386,6 +386,23 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
     }
 }
 
+// one block; n*dim is tiny (batch x 8 latent dims)
+__global__ void __launch_bounds__(256) kl_kernel(const float* __restrict__ mu, const float* __restrict__ lv,
+                                                 float* __restrict__ loss, float* __restrict__ dmu,
+                                                 float* __restrict__ dlv, int n, int dim, int pitch, float gscale) {
+  __shared__ float red[8];
+  float acc = 0.f;
+  for (int i = threadIdx.x; i < n * dim; i += blockDim.x) {
+    const int r = i / dim, c = i % dim;
+    const float m = mu[r * pitch + c], l = lv[r * pitch + c], e = __expf(l);
+    acc += -0.5f * (1.f + l - m * m - e);
+    if (dmu) dmu[r * pitch + c] = gscale * m / (float)n;
+    if (dlv) dlv[r * pitch + c] = gscale * (-0.5f) * (1.f - e) / (float)n;
+  }
+  const float s = block_sum(acc, red);
+  if (threadIdx.x == 0) atomicAdd(loss, s / (float)n);
+}
+
 __global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g, float* __restrict__ out, int64_t n) {
   __shared__ float red[8];
   float acc = 0.f;
@@ -491,6 +508,13 @@ int32_t petsyn_mse_const_fwd_bwd(const float* x, float target, float* loss, floa
   mse_const_kernel<<<blocks, 256, 0, as_stream(stream)>>>(x, target, loss, dx, numel, 1.f / (float)numel,
                                                           grad_scale / (float)numel);
   return check_launch("mse_const_kernel");
+}
+
+int32_t petsyn_kl_fwd_bwd(const float* mu, const float* logvar, float* loss, float* dmu, float* dlogvar, int32_t n,
+                          int32_t dim, int32_t pitch, float grad_scale, void* stream) {
+  PETSYN_REQUIRE(mu && logvar && loss && n > 0 && dim > 0 && pitch >= dim, "bad argument");
+  kl_kernel<<<1, 256, 0, as_stream(stream)>>>(mu, logvar, loss, dmu, dlogvar, n, dim, pitch, grad_scale);
+  return check_launch("kl_kernel");
 }
 
 int32_t petsyn_adam_step(float* p, const float* g, float* m, float* v, int64_t numel, float lr, float beta1,

@@ -52,7 +52,8 @@ __device__ __forceinline__ F8 splat(float x) {
 __device__ __forceinline__ float act_fwd(float b, int act, float slope) {
   switch (act) {
     case PETSYN_ACT_RELU: return fmaxf(b, 0.f);
-    case PETSYN_ACT_LRELU: return b > 0.f ? b : b * slope;
+    case PETSYN_ACT_LRELU:
+    case PETSYN_ACT_PRELU: return b > 0.f ? b : b * slope;
     case PETSYN_ACT_SILU: return b / (1.f + __expf(-b));
     case PETSYN_ACT_TANH: return tanhf(b);
     default: return b;
@@ -61,7 +62,8 @@ __device__ __forceinline__ float act_fwd(float b, int act, float slope) {
 __device__ __forceinline__ float act_grad(float b, int act, float slope) {
   switch (act) {
     case PETSYN_ACT_RELU: return b > 0.f ? 1.f : 0.f;
-    case PETSYN_ACT_LRELU: return b > 0.f ? 1.f : slope;
+    case PETSYN_ACT_LRELU:
+    case PETSYN_ACT_PRELU: return b > 0.f ? 1.f : slope;
     case PETSYN_ACT_SILU: { const float s = 1.f / (1.f + __expf(-b)); return s * (1.f + b * (1.f - s)); }
     case PETSYN_ACT_TANH: { const float t = tanhf(b); return 1.f - t * t; }
     default: return 1.f;
@@ -171,6 +173,8 @@ struct Dev {   // device copy of petsyn_normact_desc with typed pointers
   float* sums;
   __nv_bfloat16* dz;
   float *dgamma, *dbeta;
+  const float* slope_dev;
+  float* dslope;
 };
 
 __global__ void __launch_bounds__(256) fwd_kernel(const Dev d) {
@@ -181,6 +185,7 @@ __global__ void __launch_bounds__(256) fwd_kernel(const Dev d) {
   const int so = d.per_sample ? s * d.C : 0;
   F8 sc = splat(1.f), sh = splat(0.f);
   if (d.scale) { sc = load8f(d.scale + so + it.tx * 8); sh = load8f(d.shift + so + it.tx * 8); }
+  const float slope = d.slope_dev ? __ldg(d.slope_dev) : d.slope;
   const int64_t stride = (int64_t)gridDim.x * it.rpp;
   for (int64_t r0 = (int64_t)blockIdx.x * it.rpp + it.ty; r0 < d.rows; r0 += stride) {
     const int64_t r = base + r0;
@@ -191,8 +196,8 @@ __global__ void __launch_bounds__(256) fwd_kernel(const Dev d) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const float b = x.v[i] * sc.v[i] + sh.v[i];
-      o1.v[i] = act_fwd(b, d.act1, d.slope) + rs.v[i];
-      o2.v[i] = act_fwd(b, d.act2, d.slope) + rs.v[i];
+      o1.v[i] = act_fwd(b, d.act1, slope) + rs.v[i];
+      o2.v[i] = act_fwd(b, d.act2, slope) + rs.v[i];
     }
     store8(d.t1 + r * d.cs1 + d.co1 + it.tx * 8, o1);
     if (d.t2) store8(d.t2 + r * d.cs2 + d.co2 + it.tx * 8, o2);
@@ -206,6 +211,8 @@ __global__ void __launch_bounds__(256) bwd_reduce_kernel(const Dev d) {
   const int64_t base = (int64_t)s * d.rows;
   const int so = d.per_sample ? s * d.C : 0;
   float acc[2][8];
+  float dsl = 0.f;
+  const float slope = d.slope_dev ? __ldg(d.slope_dev) : d.slope;
 #pragma unroll
   for (int i = 0; i < 8; ++i) acc[0][i] = acc[1][i] = 0.f;
   if (it.active) {
@@ -222,12 +229,17 @@ __global__ void __launch_bounds__(256) bwd_reduce_kernel(const Dev d) {
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const float b = x.v[i] * sc.v[i] + sh.v[i];
-        float g = a.v[i] * act_grad(b, d.act1, d.slope);
-        if (d.t2) g += b2.v[i] * act_grad(b, d.act2, d.slope);
+        float g = a.v[i] * act_grad(b, d.act1, slope);
+        if (d.t2) g += b2.v[i] * act_grad(b, d.act2, slope);
         acc[0][i] += g;
         acc[1][i] += g * (x.v[i] - mu.v[i]) * rs.v[i];
+        if (d.dslope != nullptr && b < 0.f) dsl += (a.v[i] + (d.t2 ? b2.v[i] : 0.f)) * b;   // d PReLU / d slope = min(b, 0)
       }
     }
+  }
+  if (d.dslope != nullptr) {
+    for (int o = 16; o > 0; o >>= 1) dsl += __shfl_xor_sync(0xffffffffu, dsl, o);
+    if ((threadIdx.x & 31) == 0 && dsl != 0.f) atomicAdd(d.dslope, dsl);
   }
   block_reduce_channels<2>(it, acc, smem_f, d.sums + (d.per_sample ? (int64_t)s * 2 * d.C : 0), d.C);
 }
@@ -260,6 +272,7 @@ __global__ void __launch_bounds__(256) bwd_apply_kernel(const Dev d) {
       k2.v[i] = s1.v[i] * inv;
     }
   }
+  const float slope = d.slope_dev ? __ldg(d.slope_dev) : d.slope;
   const int64_t stride = (int64_t)gridDim.x * it.rpp;
   for (int64_t r0 = (int64_t)blockIdx.x * it.rpp + it.ty; r0 < d.rows; r0 += stride) {
     const int64_t r = base + r0;
@@ -271,8 +284,8 @@ __global__ void __launch_bounds__(256) bwd_apply_kernel(const Dev d) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const float b = x.v[i] * sc.v[i] + sh.v[i];
-      float g = a.v[i] * act_grad(b, d.act1, d.slope);
-      if (d.t2) g += b2.v[i] * act_grad(b, d.act2, d.slope);
+      float g = a.v[i] * act_grad(b, d.act1, slope);
+      if (d.t2) g += b2.v[i] * act_grad(b, d.act2, slope);
       const float zh = (x.v[i] - mu.v[i]) * rs.v[i];
       o.v[i] = k0.v[i] * (g - k1.v[i] - zh * k2.v[i]);
       dr.v[i] = a.v[i] + b2.v[i];
@@ -351,6 +364,7 @@ static int32_t to_dev(const petsyn_normact_desc* d, Dev* o) {
   o->sums = d->sums;
   o->dz = reinterpret_cast<__nv_bfloat16*>(d->dz);
   o->dgamma = d->dgamma; o->dbeta = d->dbeta;
+  o->slope_dev = d->slope_dev; o->dslope = d->dslope;
   return PETSYN_OK;
 }
 

@@ -35,6 +35,15 @@ class Buf:
             self._g = torch.zeros_like(self.t)
         return self._g
 
+    def alias(self, n: int, d: int, h: int, w: int, c: int, name: str = "") -> "Buf":
+        """Same storage (values and gradients) seen with another shape, e.g. [N*8, 128] as [N, 1024] for nn.Flatten."""
+        assert n * d * h * w * c == self.rows * self.c
+        o = object.__new__(Buf)
+        o.n, o.d, o.h, o.w, o.c, o.rows, o.name = n, d, h, w, c, n * d * h * w, name or self.name
+        o.t = self.t.view(o.rows, c)
+        o._g = self.g.view(o.rows, c)
+        return o
+
     def sl(self, off: int = 0, c: Optional[int] = None) -> "Sl":
         return Sl(self, off, self.c - off if c is None else c)
 
@@ -179,8 +188,11 @@ class NormActOp(Op):
     """dst_i = act(norm(z)) [+ res] for one or two destinations (channel slices)."""
 
     def __init__(self, z: Buf, kind: str, act: int, dsts: Sequence[Sl], res: Optional[Sl] = None, slope: float = 0.2,
-                 bn: Optional[torch.nn.BatchNorm3d] = None, eps: float = 1e-5, name: str = ""):
+                 bn: Optional[torch.nn.BatchNorm3d] = None, eps: float = 1e-5, name: str = "",
+                 slope_param: Optional[torch.nn.Parameter] = None):
         assert kind in ("instance", "batch", "none") and 1 <= len(dsts) <= 2
+        self.slope_param = slope_param          # nn.PReLU weight (one element): slope read from device memory
+        self.grad_slope: Optional[torch.Tensor] = None
         self.z, self.kind, self.act, self.dsts, self.res, self.slope, self.bn, self.eps = z, kind, act, list(dsts), res, \
             slope, bn, eps
         self.name = name
@@ -217,6 +229,10 @@ class NormActOp(Op):
             s2 = self.dsts[1]
             d.t2, d.t2_cstride, d.t2_coff, d.act2 = ptr(src(s2)), s2.buf.c, s2.off, self.act
         d.slope = self.slope
+        if self.slope_param is not None:
+            d.slope_dev = ptr(self.slope_param)
+            if backward and self.grad_slope is not None:
+                d.dslope = ptr(self.grad_slope)
         if self.res is not None:
             d.res, d.res_cstride, d.res_coff = ptr(src(self.res)), self.res.buf.c, self.res.off
             d.res_accumulate = int(self.acc_res)
@@ -261,6 +277,8 @@ class NormActOp(Op):
         return w
 
     def bwd(self) -> None:
+        if self.grad_slope is not None and not self.acc_dw:
+            self.grad_slope.zero_()
         d = self._desc(True)
         check(lib.petsyn_normact_bwd(C.byref(d), stream_ptr()), "normact_bwd")
         if self.acc_dw and self.grad_gamma is not None:

@@ -12,11 +12,11 @@ from typing import Optional, Tuple
 import torch
 
 from . import _cabi
-from ._cabi import (ACT_LRELU, ACT_NONE, ACT_RELU, ACT_SILU, ACT_TANH, OP_CONV, OP_CONVT, OP_UPCONV, check, lib, ptr,
+from ._cabi import (ACT_LRELU, ACT_NONE, ACT_PRELU, ACT_RELU, ACT_SILU, ACT_TANH, OP_CONV, OP_CONVT, OP_UPCONV, check, lib, ptr,
                     stream_ptr)
 
 __all__ = ["ConvPlan", "OP_CONV", "OP_UPCONV", "OP_CONVT", "ACT_NONE", "ACT_RELU", "ACT_LRELU", "ACT_SILU",
-           "ACT_TANH", "bn_stats", "bn_finalize", "norm_act_fwd", "norm_act_bwd", "l1_loss_fwd_bwd",
+           "ACT_TANH", "ACT_PRELU", "kl_fwd_bwd", "bn_stats", "bn_finalize", "norm_act_fwd", "norm_act_bwd", "l1_loss_fwd_bwd",
            "mse_const_fwd_bwd", "adam_step", "sumsq", "StemConv", "HeadConv"]
 
 
@@ -204,6 +204,12 @@ def l1_loss_fwd_bwd(y: torch.Tensor, t: torch.Tensor, loss: torch.Tensor, dy: Op
 def mse_const_fwd_bwd(x, target: float, loss, dx, grad_scale: float = 1.0) -> None:
     check(lib.petsyn_mse_const_fwd_bwd(ptr(x), target, ptr(loss), ptr(dx), x.numel(), grad_scale, stream_ptr()),
           "mse_const")
+
+
+def kl_fwd_bwd(mu, logvar, loss, dmu, dlogvar, n: int, dim: int, pitch: int, grad_scale: float = 1.0) -> None:
+    """kl_divergence(...).mean() of train_bmgan.py:33-40,174-176 and its gradient."""
+    check(lib.petsyn_kl_fwd_bwd(ptr(mu), ptr(logvar), ptr(loss), ptr(dmu), ptr(dlogvar), n, dim, pitch, grad_scale,
+                                stream_ptr()), "kl_fwd_bwd")
 
 
 def adam_step(p, g, m, v, lr: float, beta1: float, beta2: float, eps: float, step: int,

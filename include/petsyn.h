@@ -63,6 +63,7 @@ uint64_t petsyn_launch_count(void);
 #define PETSYN_ACT_LRELU 2   /* slope given separately */
 #define PETSYN_ACT_SILU 3
 #define PETSYN_ACT_TANH 4
+#define PETSYN_ACT_PRELU 5   /* nn.PReLU() with one learnable slope read from device memory (normact descriptor only) */
 
 typedef struct petsyn_conv_desc {
   int32_t op;                 /* PETSYN_OP_* */
@@ -224,6 +225,8 @@ typedef struct petsyn_normact_desc {
   void* dz;                  /* bwd: gradient w.r.t. z, bf16 contiguous */
   float* dgamma;             /* optional outputs (batch statistics with affine) */
   float* dbeta;
+  const float* slope_dev;    /* PETSYN_ACT_PRELU: device scalar holding the slope (MONAI ResidualUnit act="PRELU") */
+  float* dslope;             /* bwd: d(loss)/d(slope) accumulated into this device scalar (caller-zeroed) */
 } petsyn_normact_desc;
 
 /* sums[sample][0:c] = sum z, sums[sample][c:2c] = sum z^2 (fp32, caller-zeroed). */
@@ -255,6 +258,10 @@ int32_t petsyn_l1_loss_fwd_bwd(const float* y, const float* t, float* loss, floa
 /* LSGAN PatchAdversarialLoss(criterion="least_squares"): mean (x - target)^2 and its gradient. */
 int32_t petsyn_mse_const_fwd_bwd(const float* x, float target, float* loss, float* dx, int64_t numel, float grad_scale,
                                  void* stream);
+/* kl_divergence of train_bmgan.py:33-40 averaged over the batch (:176): loss[0] += mean_n( -0.5 * sum_j(1 + lv - mu^2 -
+ * exp(lv)) ) (caller-zeroed); dmu / dlv = gradient * grad_scale.  mu, lv fp32 with row pitch `pitch` (>= dim). */
+int32_t petsyn_kl_fwd_bwd(const float* mu, const float* logvar, float* loss, float* dmu, float* dlogvar, int32_t n,
+                          int32_t dim, int32_t pitch, float grad_scale, void* stream);
 /* torch.optim.Adam step (no amsgrad, weight_decay 0) over one flat fp32 parameter arena.  The 1-based step number is
  * `step`, or -- when step_dev != NULL -- read from device memory (so a captured CUDA graph of the step stays valid). */
 int32_t petsyn_adam_step(float* p, const float* g, float* m, float* v, int64_t numel, float lr, float beta1,

@@ -147,3 +147,61 @@ def test_bmgan_contracts(petsyn):
         g(torch.zeros(1, 1, 64, 64, 64, device="cuda"), torch.zeros(1, 4, device="cuda"))     # wrong latent size
     with pytest.raises(RuntimeError):
         petsyn.patch_discriminator()(torch.zeros(1, 1, 32, 32, 32))                           # no CPU path
+
+
+def test_encoder_kl_matches_oracle(petsyn):
+    """ResNet_encoder (bmgan_model.py:103-130) + kl_divergence (train_bmgan.py:33-40,174-176) against the fp32 oracle,
+    peer-calibrated like the generator test.  72x96x80 exercises odd extents under stride 2 (9 -> 5 -> 3 -> 2)."""
+    import copy
+    torch.manual_seed(21)
+    enc = petsyn.ResNet_encoder().train()
+    oe = OB.ResNetEncoder().train()
+    oe.load_state_dict(enc.state_dict())
+    g = torch.Generator().manual_seed(2)
+    x = torch.rand(2, 1, 72, 96, 80, generator=g) * 2 - 1
+    mu_o, lv_o = oe(x)
+    loss_o = OB.kl_divergence(mu_o, lv_o).mean()
+    loss_o.backward()
+    pe = copy.deepcopy(oe).cuda()
+    pe.zero_grad()
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        mu_p, lv_p = pe(x.cuda())
+    OB.kl_divergence(mu_p.float(), lv_p.float()).mean().backward()
+
+    enc = enc.cuda()
+    mu, lv = enc(x.cuda())
+    loss = (-0.5 * torch.sum(1 + lv - mu.pow(2) - lv.exp(), dim=-1)).mean()
+    loss.backward()
+    torch.cuda.synchronize()
+    e_ours = max((mu.detach().cpu() - mu_o.detach()).abs().max().item(), (lv.detach().cpu() - lv_o.detach()).abs().max().item())
+    e_peer = max((mu_p.detach().float().cpu() - mu_o.detach()).abs().max().item(),
+                 (lv_p.detach().float().cpu() - lv_o.detach()).abs().max().item())
+    print("encoder out err ours/peer", e_ours, e_peer, "loss", loss.item(), loss_o.item())
+    assert e_ours <= 2.0 * e_peer + 5e-3
+    assert abs(loss.item() - loss_o.item()) <= 2.0 * abs(OB.kl_divergence(mu_p.float(), lv_p.float()).mean().item() - loss_o.item()) + 1e-3
+    po, pp = dict(oe.named_parameters()), dict(pe.named_parameters())
+    tot = tot_o = tot_p = 0.0
+    for k, p in enc.named_parameters():
+        a, b, c = p.grad.double().cpu().flatten(), po[k].grad.double().flatten(), pp[k].grad.double().cpu().flatten()
+        tot += (a ** 2).sum().item(); tot_o += (b ** 2).sum().item(); tot_p += (c ** 2).sum().item()
+        if b.norm().item() > 1e-3 * 1.0:
+            rel, rel_p = abs(a.norm() - b.norm()).item() / b.norm().item(), abs(c.norm() - b.norm()).item() / b.norm().item()
+            assert rel <= max(2.0 * rel_p, 0.05), (k, a.norm().item(), b.norm().item(), c.norm().item())
+            cos = (torch.dot(a, b) / (a.norm() * b.norm())).item()
+            cos_p = (torch.dot(c, b) / (c.norm() * b.norm())).item()
+            assert 1 - cos <= max(2.0 * (1 - cos_p), 1e-2), (k, cos, cos_p)
+    print("encoder grad-norm ours/oracle/peer", tot ** 0.5, tot_o ** 0.5, tot_p ** 0.5)
+    assert abs(tot ** 0.5 - tot_o ** 0.5) <= max(2.0 * abs(tot_p ** 0.5 - tot_o ** 0.5), 2e-2 * tot_o ** 0.5)
+    # fused KL kernel == the formula
+    ops = petsyn.ops
+    out = torch.stack([mu.detach(), lv.detach()], 0).reshape(2, -1)    # any fp32 [n, 8] pair
+    m, l = mu.detach().contiguous(), lv.detach().contiguous()
+    lossk = torch.zeros(1, device="cuda"); dm, dl = torch.empty_like(m), torch.empty_like(l)
+    ops.kl_fwd_bwd(m, l, lossk, dm, dl, m.shape[0], 8, 8)
+    m2, l2 = m.clone().requires_grad_(True), l.clone().requires_grad_(True)
+    ref = (-0.5 * torch.sum(1 + l2 - m2.pow(2) - l2.exp(), dim=-1)).mean()
+    ref.backward()
+    assert abs(lossk.item() - ref.item()) < 1e-4 * abs(ref.item()) + 1e-5
+    assert (dm - m2.grad).abs().max().item() < 1e-5 and (dl - l2.grad).abs().max().item() < 1e-5
+    with pytest.raises(ValueError):
+        enc(torch.zeros(1, 1, 32, 32, 32, device="cuda"))            # does not reduce to 2x2x2

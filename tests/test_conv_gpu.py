@@ -48,6 +48,7 @@ CASES = [
     ("upconv", 2, 3, 5, 4, 64, 128, 3, 1, 1),
     ("convt", 1, 4, 6, 8, 64, 64, 4, 2, 1),
     ("convt", 1, 3, 4, 3, 128, 128, 4, 2, 1),
+    ("conv", 2, 3, 4, 3, 128, 128, 3, 2, 1),       # odd extents with stride 2 (ResNet_encoder: 3 -> 2)
     ("conv", 1, 6, 8, 6, 256, 256, 4, 2, 1),       # bottleneck-like: few voxels, long K -> split-K fprop
     ("upconv", 1, 3, 4, 3, 256, 256, 3, 1, 1),     # split-K dgrad (64 taps x 4 chunks, 36 voxels)
 ]
@@ -116,6 +117,6 @@ def test_conv_bad_config_raises(petsyn):
     with pytest.raises(ValueError):
         ops.ConvPlan(ops.OP_CONV, 1, 8, 8, 8, 60, 64, 3, 1, 1)       # cin not a multiple of 8
     with pytest.raises(ValueError):
-        ops.ConvPlan(ops.OP_CONV, 1, 7, 8, 8, 64, 64, 4, 2, 1)       # odd dim with stride 2
+        ops.ConvPlan(ops.OP_CONV, 1, 8, 8, 8, 64, 64, 3, 1, 3)       # padding >= kernel size
     with pytest.raises(ValueError):
         ops.ConvPlan(ops.OP_CONVT, 1, 8, 8, 8, 64, 64, 3, 1, 1)      # unsupported transposed config
