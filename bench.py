@@ -323,8 +323,8 @@ def cpu_bmgan_steps(cfg_name, shape, batch, steps, warmup, budget_s=150.0):
         opt.step()
         with torch.no_grad():
             fake = gen(t1, z)
-        OB.discriminator_step(disc, fake, pet)
-        return time.perf_counter() - t0
+        OB.discriminator_step(disc, fake, pet)   # (the encoder phase needs the full 96x128x96 volume and is < 3 % of
+        return time.perf_counter() - t0          #  the step's FLOPs; it is left out of the cropped CPU sample)
 
     d, h, w = shape
     small = (32, 64, 32)
@@ -361,11 +361,12 @@ def run_petsyn_bmgan(args, cfg_name, shape, batch):
     torch.manual_seed(777)
     gen = petsyn.dense_unet_generator(**BMGAN_CFG[cfg_name]).to(dev).train()
     disc = petsyn.patch_discriminator().to(dev).train()
+    enc = petsyn.ResNet_encoder().to(dev).train() if cfg_name == "full" else None   # needs a volume that reduces to 2x2x2
     pool = 3
     host = [bmgan_batch(shape, 777 + 1000 * rank + i, batch) for i in range(pool)]
     pinned = [tuple(t.pin_memory() for t in b) for b in host]
     resident = [tuple(t.to(dev) for t in b) for b in host]
-    trainer = BmganTrainer(gen, disc, lr=2e-4, example_input=resident[0][0])
+    trainer = BmganTrainer(gen, disc, lr=2e-4, example_input=resident[0][0], enc=enc)
 
     def barrier():
         if world > 1:
@@ -425,16 +426,18 @@ def run_petsyn_bmgan(args, cfg_name, shape, batch):
         peak_tf = float(peaks.get("bf16_tflops_sustained", 1400.0))
         d, h, w = shape
         gf, df = trainer.geng.flops_algorithmic, trainer.deng.flops_algorithmic
-        # algorithmic FLOPs of the step: G fwd+bwd (3x) + G fwd again (1x); D: 3 fwd + dgrad-only bwd (1x) + 2 full bwd (2x each)
-        step_flops = 4.0 * gf + (3.0 + 1.0 + 4.0) * df
+        # algorithmic FLOPs of the step: G fwd+bwd (3x) + one more G fwd per later phase; D: 3 fwd + dgrad-only bwd (1x)
+        # + 2 full bwd (2x each); E: 2 x (fwd + bwd)
+        ef = trainer.eeng.flops_algorithmic if enc is not None else 0.0
+        step_flops = (3.0 + (2.0 if enc is not None else 1.0)) * gf + (3.0 + 1.0 + 4.0) * df + 6.0 * ef
         ms = ms_total / args.steps
         ach = step_flops / (ms * 1e-3) / 1e12
         line = {
-            "metric": "BMGAN adversarial-step throughput (G phase + D phase, train_bmgan.py:141-200 without LPIPS/encoder)",
+            "metric": "BMGAN adversarial-step throughput (G, E, D phases of train_bmgan.py:141-200, LPIPS dropped)",
             "value": world * batch * args.steps / (ms_total * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": args.workload, "model": f"dense_unet_generator({cfg_name}) + patch_discriminator()",
+            "config": {"workload": args.workload, "model": f"dense_unet_generator({cfg_name}) + patch_discriminator()" + (" + ResNet_encoder()" if enc is not None else ""),
                        "volume": list(shape), "per_gpu_batch": batch, "global_batch": batch * world,
                        "parallelism": f"dp{world}", "optimizer": "Adam(lr=2e-4) on G; D as written (never stepped)",
                        "loss": "LSGAN + 20*L1", "cuda_graph": trainer.graph is not None,

@@ -247,11 +247,13 @@ class Unet3dTrainer:
 
 class BmganTrainer:
     """One BMGAN "adversarial step" as written in ``bl_methods/BMGAN/train_bmgan.py:141-200``, minus the
-    parts that cannot exist offline (LPIPS needs downloaded weights) and the encoder phase (not built yet):
+    part that cannot exist offline (LPIPS needs downloaded weights):
 
       G phase (:141-161)  fake = G(t1, z); loss = LSGAN(D(fake), real) + lamda_l1 * L1(fake, pet); D frozen;
                           backward through D (data gradient only) into G; [bucketed all-reduce]; Adam on G.
-      D phase (:183-200)  G forward again (weights just changed; the reference recomputes under no_grad), then
+      E phase (:163-180)  (when an encoder is given) G forward again under no_grad, mu/logvar = E(real), E(fake);
+                          loss = mean(KL(real) + KL(fake)); Adam on E.
+      D phase (:183-200)  G forward a third time (the reference recomputes it in every phase), then
                           LSGAN(D(fake), fake) and LSGAN(D(real), real): two backward calls whose weight gradients
                           accumulate.  The reference never calls ``d_optimizer.step()``: reproduced
                           "as written" -- D stays at its initialisation; set ``step_discriminator=True`` for the
@@ -262,7 +264,7 @@ class BmganTrainer:
 
     def __init__(self, gen, disc, lr: float = 2e-4, betas=(0.9, 0.999), eps: float = 1e-8, lamda_l1: float = 20.0,
                  bucket_mb: float = 64.0, process_group=None, example_input: Optional[torch.Tensor] = None,
-                 step_discriminator: bool = False):
+                 step_discriminator: bool = False, enc=None):
         if example_input is None:
             raise ValueError("example_input (a tensor of the training shape) is required to lay out the arenas")
         self.gen, self.disc = gen, disc
@@ -278,6 +280,13 @@ class BmganTrainer:
         self.darena = FlatArena(list(self.deng.params), dev)
         self.gm, self.gv = torch.zeros_like(self.garena.p), torch.zeros_like(self.garena.p)
         self.dm, self.dv = torch.zeros_like(self.darena.p), torch.zeros_like(self.darena.p)
+        self.enc = enc
+        if enc is not None:
+            self.eeng = enc.engine_for(example_input)
+            self.earena = FlatArena(list(self.eeng.params), dev)
+            self.em, self.ev = torch.zeros_like(self.earena.p), torch.zeros_like(self.earena.p)
+            self.loss_kl = torch.zeros(1, dtype=torch.float32, device=dev)
+            self.dlatent = torch.zeros(example_input.shape[0], 16, dtype=torch.float32, device=dev)
         self.step_dev = torch.zeros(1, dtype=torch.int32, device=dev)
         self.step_count = 0
         f = lambda: torch.zeros(1, dtype=torch.float32, device=dev)
@@ -290,6 +299,8 @@ class BmganTrainer:
         if self.world > 1:
             dist.broadcast(self.garena.p, src=0, group=self.pg)
             dist.broadcast(self.darena.p, src=0, group=self.pg)
+            if enc is not None:
+                dist.broadcast(self.earena.p, src=0, group=self.pg)
             for b in list(gen.buffers()) + list(disc.buffers()):
                 if b.dtype.is_floating_point:
                     dist.broadcast(b, src=0, group=self.pg)
@@ -317,8 +328,25 @@ class BmganTrainer:
         ops.adam_step(self.garena.p, self.garena.g, self.gm, self.gv, self.lr, self.betas[0], self.betas[1], self.eps, 0,
                       step_dev=self.step_dev)
         self._dirty()
+        # ---------------- E phase ----------------
+        if self.enc is not None:
+            eeng = self.eeng
+            fake = geng.forward(t1, z)                               # train_bmgan.py:168-169 (no_grad recompute)
+            self.loss_kl.zero_()
+            n = t1.shape[0]
+            for i, vol in enumerate((pet, fake)):
+                lat = eeng.forward(vol)                              # [n, 16] = [mu | logvar]
+                ops.kl_fwd_bwd(lat, lat[:, 8:], self.loss_kl, self.dlatent, self.dlatent[:, 8:], n, 8, 16)
+                eeng.backward(self.dlatent, out=self.earena.grad_views, accumulate=(i == 1))
+            if self.world > 1:
+                dist.all_reduce(self.earena.g, op=dist.ReduceOp.AVG, group=self.pg)
+            ops.adam_step(self.earena.p, self.earena.g, self.em, self.ev, self.lr, self.betas[0], self.betas[1], self.eps,
+                          0, step_dev=self.step_dev)
+            for op in eeng.tape.ops:
+                if hasattr(op, "_ver"):
+                    op._ver = None
         # ---------------- D phase ----------------
-        fake = geng.forward(t1, z)                                   # recomputed with the updated generator
+        fake = geng.forward(t1, z)                                   # recomputed again, as the reference does
         logits = deng.forward(fake)
         self.loss_d_fake.zero_()
         ops.mse_const_fwd_bwd(logits, 0.0, self.loss_d_fake, self.dlogits)
@@ -353,8 +381,10 @@ class BmganTrainer:
         """Single-GPU only: the whole adversarial step as one CUDA graph (state is restored after the warm-up)."""
         if self.world > 1:
             raise RuntimeError("BmganTrainer.capture supports world_size 1; data-parallel runs launch eagerly")
-        snap = [t.clone() for t in (self.garena.p, self.gm, self.gv, self.darena.p, self.darena.g, self.dm, self.dv,
-                                    self.step_dev)]
+        state = [self.garena.p, self.gm, self.gv, self.darena.p, self.darena.g, self.dm, self.dv, self.step_dev]
+        if self.enc is not None:
+            state += [self.earena.p, self.em, self.ev]
+        snap = [t.clone() for t in state]
         bufs = [b.clone() for b in list(self.gen.buffers()) + list(self.disc.buffers())]
         n = self.dy.shape[0]
         self.static = (torch.zeros_like(self.dy), torch.zeros_like(self.dy),
@@ -369,10 +399,13 @@ class BmganTrainer:
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
             self._step_impl(*self.static)
-        for dst, src in zip((self.garena.p, self.gm, self.gv, self.darena.p, self.darena.g, self.dm, self.dv,
-                             self.step_dev), snap):
+        for dst, src in zip(state, snap):
             dst.copy_(src)
         for dst, src in zip(list(self.gen.buffers()) + list(self.disc.buffers()), bufs):
             dst.copy_(src)
         self._dirty()
+        if self.enc is not None:
+            for op in self.eeng.tape.ops:
+                if hasattr(op, "_ver"):
+                    op._ver = None
         self.graph = g
