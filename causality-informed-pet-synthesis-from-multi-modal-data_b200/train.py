@@ -403,9 +403,14 @@ class BmganTrainer:
             dst.copy_(src)
         for dst, src in zip(list(self.gen.buffers()) + list(self.disc.buffers()), bufs):
             dst.copy_(src)
+        # The captured step starts with a generator forward that does NOT repack (its weights were packed by the last
+        # forward of the previous step); after restoring the pre-warm-up weights the packed images must be refreshed
+        # eagerly once, or the first replay would run on the warm-up's weights.
         self._dirty()
+        self.geng.tape.repack()
         if self.enc is not None:
             for op in self.eeng.tape.ops:
                 if hasattr(op, "_ver"):
                     op._ver = None
+            self.eeng.tape.repack()
         self.graph = g

@@ -247,7 +247,7 @@ def test_bmgan_trainer_step(petsyn):
         # 12-voxel InstanceNorm bottleneck is ill-conditioned: the statistics' atomic reduction order flips bf16 ulps and
         # the network amplifies them (two identical forwards differ by up to 0.5 in the last feature maps, for the cuDNN
         # peer as well), so only a loose bound is meaningful here; L1 averages 393 k voxels and is tight.
-        assert abs(losses[0][0] - adv_ref) <= 0.4 * abs(adv_ref) and abs(losses[0][1] - l1_ref) <= 5e-3
+        assert abs(losses[0][0] - adv_ref) <= 0.25 * abs(adv_ref) and abs(losses[0][1] - l1_ref) <= 2e-3
         assert all(np.isfinite(v) for row in losses for v in row)
         assert tr.step_count == 3 and int(tr.step_dev.item()) == 3        # capture() restored the optimiser state
         for k, v in d0.items():                                          # D is never stepped
@@ -255,4 +255,4 @@ def test_bmgan_trainer_step(petsyn):
         assert tr.darena.g.abs().sum().item() > 0                        # ... but its gradients accumulate
     for a, b in zip(results[0], results[1]):
         for x, y in zip(a, b):
-            assert abs(x - y) <= 0.4 * abs(x) + 2e-2, (results[0], results[1])
+            assert abs(x - y) <= 0.5 * abs(x) + 2e-2, (results[0], results[1])
