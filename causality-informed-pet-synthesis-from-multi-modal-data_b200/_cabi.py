@@ -57,6 +57,7 @@ class NormActDesc(C.Structure):
         ("slope", C.c_float),
         ("res", C.c_void_p), ("res_cstride", C.c_int32), ("res_coff", C.c_int32), ("res_accumulate", C.c_int32),
         ("sums", C.c_void_p), ("dz", C.c_void_p), ("dgamma", C.c_void_p), ("dbeta", C.c_void_p),
+        ("group_size", C.c_int32), ("dz_accumulate", C.c_int32), ("affine_accumulate", C.c_int32),
         ("slope_dev", C.c_void_p), ("dslope", C.c_void_p),
     ]
 
@@ -105,6 +106,15 @@ SIGNATURES = {
                                          _f32, _vp, _vp, _vp, _vp, _i64, _i32, _vp]),
     "petsyn_l1_loss_fwd_bwd": (_i32, [_vp, _vp, _vp, _vp, _i64, _f32, _vp]),
     "petsyn_mse_const_fwd_bwd": (_i32, [_vp, _f32, _vp, _vp, _i64, _f32, _vp]),
+    "petsyn_resample2": (_i32, [_vp, _i32, _i32, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _f32, _i32, _vp]),
+    "petsyn_layernorm_fwd": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _f32, _vp]),
+    "petsyn_layernorm_bwd": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _vp]),
+    "petsyn_geglu_fwd": (_i32, [_vp, _vp, _i64, _i32, _vp]),
+    "petsyn_geglu_bwd": (_i32, [_vp, _vp, _vp, _i64, _i32, _vp]),
+    "petsyn_attention_fwd": (_i32, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _f32, _vp]),
+    "petsyn_attention_bwd": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _f32, _vp]),
+    "petsyn_covariate_bias_fwd": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i64, _vp]),
+    "petsyn_covariate_bias_bwd": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i64, _vp]),
     "petsyn_kl_fwd_bwd": (_i32, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _f32, _vp]),
     "petsyn_adam_step": (_i32, [_vp, _vp, _vp, _vp, _i64, _f32, _f32, _f32, _f32, _i32, _vp, _vp]),
     "petsyn_sumsq": (_i32, [_vp, _vp, _i64, _vp]),

@@ -1,0 +1,510 @@
+"""Drop-in replacement for the reference's covariate-conditioned generator ``AttenUNet``
+(``unet/utils/atten_unet_model.py:1575-1860``) running on libpetsyn's sm_100a kernels.
+
+Kept identical to the reference: the constructor signature and its ``ValueError`` checks, the module tree (``conv_in``,
+``down_blocks.{i}.resnets/attentions/downsampler``, ``middle_block.resnet_1/attention/resnet_2``,
+``up_blocks.{i}.resnets/attentions/upsampler``, ``out``; MONAI's ``Convolution(conv_only=True)`` child name ``conv``,
+``MLPBlock``'s ``linear1/linear2``) and therefore every ``state_dict`` key and shape (416 tensors for
+``unet/config/training.json``), the ``zero_module`` initialisation, ``forward(x, context)`` on fp32 NCDHW tensors, autograd.
+
+Implemented configuration family: ``resblock_updown=True``, ``with_conditioning=True`` (attention levels use
+cross-attention transformer blocks), one transformer layer, 32 channels per head -- i.e. ``training.json``.  Other
+combinations raise ``NotImplementedError`` (class embeddings are broken in the reference itself).
+
+Execution: a static op tape (``graph.py``).  GroupNorm+SiLU, residual sums and skip concatenation are fused
+bandwidth kernels over channels-last bf16 buffers; every Conv3d (3^3, 1^3, the nearest-x2 + 3^3 of the up-sampling
+ResnetBlocks) and every Linear of the transformer runs on the tcgen05 implicit-GEMM kernel; self-attention is a
+flash-style kernel (no L x L score tensor); cross-attention over the length-1 covariate context is computed as what it
+is mathematically -- a per-sample bias ``to_out(to_v(context))`` added to every token -- with exact zero
+gradients for ``attn2.to_q``, ``attn2.to_k`` and ``norm2``.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+import torch.nn as nn
+
+from . import graph, ops
+from ._cabi import check, lib, ptr, stream_ptr
+from .bmgan_model import _EngineBase
+from .graph import (AttentionOp, Buf, ConvOp, CovariateBiasOp, GegluOp, LayerNormOp, NormActOp, ResampleOp, Sl, Tape)
+
+
+def zero_module(module: nn.Module) -> nn.Module:
+    for p in module.parameters():
+        p.detach().zero_()
+    return module
+
+
+class _Container(nn.Module):
+    def forward(self, *a, **k):
+        raise RuntimeError("petsyn AttenUNet blocks are parameter containers; call AttenUNet.forward")
+
+
+class _Convolution(nn.Sequential):
+    """MONAI ``Convolution(conv_only=True)``: one child named ``conv``."""
+
+    def __init__(self, cin: int, cout: int, k: int):
+        super().__init__()
+        self.add_module("conv", nn.Conv3d(cin, cout, k, stride=1, padding=(k - 1) // 2, bias=True))
+
+
+class ResnetBlock(_Container):
+    def __init__(self, in_channels: int, out_channels: Optional[int] = None, up: bool = False, down: bool = False,
+                 norm_num_groups: int = 32, norm_eps: float = 1e-6):
+        super().__init__()
+        self.channels = in_channels
+        self.out_channels = out_channels or in_channels
+        self.up, self.down = up, down
+        self.norm1 = nn.GroupNorm(norm_num_groups, in_channels, eps=norm_eps, affine=True)
+        self.nonlinearity = nn.SiLU()
+        self.conv1 = _Convolution(in_channels, self.out_channels, 3)
+        self.upsample = self.downsample = None
+        if up:
+            self.upsample = nn.Upsample(scale_factor=2.0, mode="nearest")
+        elif down:
+            self.downsample = nn.AvgPool3d(kernel_size=2, stride=2)
+        self.norm2 = nn.GroupNorm(norm_num_groups, self.out_channels, eps=norm_eps, affine=True)
+        self.conv2 = zero_module(_Convolution(self.out_channels, self.out_channels, 3))
+        self.skip_connection = (nn.Identity() if self.out_channels == in_channels
+                                else _Convolution(in_channels, self.out_channels, 1))
+
+
+class CrossAttention(_Container):
+    def __init__(self, query_dim: int, cross_attention_dim: Optional[int], heads: int, head_channels: int):
+        super().__init__()
+        inner = heads * head_channels
+        cross_attention_dim = cross_attention_dim if cross_attention_dim is not None else query_dim
+        self.num_heads = heads
+        self.to_q = nn.Linear(query_dim, inner, bias=False)
+        self.to_k = nn.Linear(cross_attention_dim, inner, bias=False)
+        self.to_v = nn.Linear(cross_attention_dim, inner, bias=False)
+        self.to_out = nn.Sequential(nn.Linear(inner, query_dim), nn.Dropout(0.0))
+
+
+class _MLPBlock(_Container):
+    """MONAI ``MLPBlock(act="GEGLU")``."""
+
+    def __init__(self, hidden: int, mlp_dim: int):
+        super().__init__()
+        self.linear1 = nn.Linear(hidden, mlp_dim * 2)
+        self.linear2 = nn.Linear(mlp_dim, hidden)
+        self.drop1, self.drop2 = nn.Dropout(0.0), nn.Dropout(0.0)
+
+
+class BasicTransformerBlock(_Container):
+    def __init__(self, channels: int, heads: int, head_channels: int, cross_attention_dim: Optional[int]):
+        super().__init__()
+        self.attn1 = CrossAttention(channels, None, heads, head_channels)
+        self.ff = _MLPBlock(channels, channels * 4)
+        self.attn2 = CrossAttention(channels, cross_attention_dim, heads, head_channels)
+        self.norm1, self.norm2, self.norm3 = nn.LayerNorm(channels), nn.LayerNorm(channels), nn.LayerNorm(channels)
+
+
+class SpatialTransformer(_Container):
+    def __init__(self, in_channels: int, heads: int, head_channels: int, num_layers: int, norm_num_groups: int,
+                 norm_eps: float, cross_attention_dim: Optional[int]):
+        super().__init__()
+        inner = heads * head_channels
+        self.norm = nn.GroupNorm(norm_num_groups, in_channels, eps=norm_eps, affine=True)
+        self.proj_in = _Convolution(in_channels, inner, 1)
+        self.transformer_blocks = nn.ModuleList(
+            [BasicTransformerBlock(inner, heads, head_channels, cross_attention_dim) for _ in range(num_layers)])
+        self.proj_out = zero_module(_Convolution(inner, in_channels, 1))
+
+
+class _DownBlock(_Container):
+    def __init__(self, cin, cout, nres, groups, eps, add_downsample, attn: Optional[dict]):
+        super().__init__()
+        resnets = [ResnetBlock(cin if i == 0 else cout, cout, norm_num_groups=groups, norm_eps=eps) for i in range(nres)]
+        if attn is not None:      # the reference's CrossAttn blocks register `attentions` before `resnets`
+            self.attentions = nn.ModuleList([SpatialTransformer(cout, **attn) for _ in range(nres)])
+        self.resnets = nn.ModuleList(resnets)
+        self.downsampler = (ResnetBlock(cout, cout, down=True, norm_num_groups=groups, norm_eps=eps)
+                            if add_downsample else None)
+
+
+class _MidBlock(_Container):
+    def __init__(self, c, groups, eps, attn: dict):
+        super().__init__()
+        self.resnet_1 = ResnetBlock(c, c, norm_num_groups=groups, norm_eps=eps)
+        self.attention = SpatialTransformer(c, **attn)
+        self.resnet_2 = ResnetBlock(c, c, norm_num_groups=groups, norm_eps=eps)
+
+
+class _UpBlock(_Container):
+    def __init__(self, cin, prev, cout, nres, groups, eps, add_upsample, attn: Optional[dict]):
+        super().__init__()
+        resnets = []
+        for i in range(nres):
+            skip_c = cin if i == nres - 1 else cout
+            in_c = prev if i == 0 else cout
+            resnets.append(ResnetBlock(in_c + skip_c, cout, norm_num_groups=groups, norm_eps=eps))
+        if attn is not None:
+            self.attentions = nn.ModuleList([SpatialTransformer(cout, **attn) for _ in range(nres)])
+        self.resnets = nn.ModuleList(resnets)
+        self.upsampler = (ResnetBlock(cout, cout, up=True, norm_num_groups=groups, norm_eps=eps)
+                          if add_upsample else None)
+
+
+def _rep(v, n):
+    return list(v) if isinstance(v, (list, tuple)) else [v] * n
+
+
+class AttenUNet(nn.Module):
+    """B200-native ``AttenUNet`` (reference atten_unet_model.py:1575-1860): same ctor, keys and forward contract."""
+
+    def __init__(self, spatial_dims: int, in_channels: int, out_channels: int,
+                 num_res_blocks: Sequence[int] | int = (2, 2, 2, 2), num_channels: Sequence[int] = (32, 64, 64, 64),
+                 attention_levels: Sequence[bool] = (False, False, True, True), norm_num_groups: int = 32,
+                 norm_eps: float = 1e-6, resblock_updown: bool = False, num_head_channels: int | Sequence[int] = 8,
+                 with_conditioning: bool = False, transformer_num_layers: int = 1,
+                 cross_attention_dim: int | None = None, num_class_embeds: int | None = None,
+                 upcast_attention: bool = False, use_flash_attention: bool = False,
+                 dropout_cattn: float = 0.0) -> None:
+        super().__init__()
+        # the reference's own argument checks (atten_unet_model.py:1623-1666)
+        if with_conditioning is True and cross_attention_dim is None:
+            raise ValueError("AttenUNet expects dimension of the cross-attention conditioning (cross_attention_dim) "
+                             "when using with_conditioning.")
+        if cross_attention_dim is not None and with_conditioning is False:
+            raise ValueError("AttenUNet expects with_conditioning=True when specifying the cross_attention_dim.")
+        if dropout_cattn > 1.0 or dropout_cattn < 0.0:
+            raise ValueError("Dropout cannot be negative or >1.0!")
+        if any((c % norm_num_groups) != 0 for c in num_channels):
+            raise ValueError("AttenUNet expects all num_channels being multiple of norm_num_groups")
+        if len(num_channels) != len(attention_levels):
+            raise ValueError("AttenUNet expects num_channels being same size of attention_levels")
+        n = len(num_channels)
+        num_head_channels = _rep(num_head_channels, n)
+        if len(num_head_channels) != n:
+            raise ValueError("num_head_channels should have the same length as attention_levels.")
+        num_res_blocks = _rep(num_res_blocks, n)
+        if len(num_res_blocks) != n:
+            raise ValueError("`num_res_blocks` should be a single integer or a tuple of integers with the same length "
+                             "as `num_channels`.")
+        if spatial_dims != 3 or in_channels != 1 or out_channels != 1:
+            raise NotImplementedError("petsyn AttenUNet implements the reference use: 3-D, one channel in, one out")
+        if not (resblock_updown and with_conditioning) or transformer_num_layers != 1 or num_class_embeds is not None \
+                or dropout_cattn != 0.0:
+            raise NotImplementedError("petsyn AttenUNet implements the training.json family: resblock_updown=True, "
+                                      "with_conditioning=True, transformer_num_layers=1, no class embeddings/dropout")
+        for lvl, a in enumerate(attention_levels):
+            if a and num_head_channels[lvl] != 32:
+                raise NotImplementedError("attention levels need num_head_channels == 32 (the attention kernel's head size)")
+        self.cfg = dict(num_channels=list(num_channels), num_res_blocks=num_res_blocks,
+                        attention_levels=list(attention_levels), num_head_channels=num_head_channels,
+                        norm_num_groups=norm_num_groups, norm_eps=norm_eps, cross_attention_dim=cross_attention_dim)
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.block_out_channels = num_channels
+        self.with_conditioning = with_conditioning
+        ch, g, e = list(num_channels), norm_num_groups, norm_eps
+
+        def attn_kw(lvl):
+            if not attention_levels[lvl]:
+                return None
+            return dict(heads=ch[lvl] // num_head_channels[lvl], head_channels=num_head_channels[lvl],
+                        num_layers=transformer_num_layers, norm_num_groups=g, norm_eps=e,
+                        cross_attention_dim=cross_attention_dim)
+
+        self.conv_in = _Convolution(in_channels, ch[0], 3)
+        self.down_blocks = nn.ModuleList([])
+        out_c = ch[0]
+        for i in range(n):
+            in_c, out_c = out_c, ch[i]
+            self.down_blocks.append(_DownBlock(in_c, out_c, num_res_blocks[i], g, e, i != n - 1, attn_kw(i)))
+        mid_attn = dict(heads=ch[-1] // num_head_channels[-1], head_channels=num_head_channels[-1],
+                        num_layers=transformer_num_layers, norm_num_groups=g, norm_eps=e,
+                        cross_attention_dim=cross_attention_dim)
+        if num_head_channels[-1] != 32:
+            raise NotImplementedError("the middle block's attention needs num_head_channels[-1] == 32")
+        self.middle_block = _MidBlock(ch[-1], g, e, mid_attn)
+        self.up_blocks = nn.ModuleList([])
+        rch = list(reversed(ch))
+        out_c = rch[0]
+        for i in range(n):
+            prev, out_c = out_c, rch[i]
+            in_c = rch[min(i + 1, n - 1)]
+            lvl = n - 1 - i
+            self.up_blocks.append(_UpBlock(in_c, prev, out_c, num_res_blocks[lvl] + 1, g, e, i != n - 1, attn_kw(lvl)))
+        self.out = nn.Sequential(nn.GroupNorm(g, ch[0], eps=e, affine=True), nn.SiLU(),
+                                 zero_module(_Convolution(ch[0], out_channels, 3)))
+        self._engines: Dict[Tuple, "_AttenEngine"] = {}
+
+    def engine_for(self, x: torch.Tensor) -> "_AttenEngine":
+        key = (tuple(x.shape), x.device.index)
+        eng = self._engines.get(key)
+        if eng is None:
+            eng = _AttenEngine(self, tuple(x.shape), x.device)
+            self._engines[key] = eng
+        return eng
+
+    def forward(self, x: torch.Tensor, context: torch.Tensor | None = None, class_labels: torch.Tensor | None = None,
+                down_block_additional_residuals=None, mid_block_additional_residual=None) -> torch.Tensor:
+        if class_labels is not None or down_block_additional_residuals is not None \
+                or mid_block_additional_residual is not None:
+            raise NotImplementedError("class labels / additional residuals are not used by the reference scripts")
+        if context is None:
+            raise ValueError("AttenUNet(with_conditioning=True) needs the covariate context tensor")
+        if not x.is_cuda:
+            raise RuntimeError("petsyn AttenUNet runs on CUDA (sm_100a) only; there is no CPU path")
+        if x.dim() != 5 or x.shape[1] != 1:
+            raise ValueError(f"expected x of shape [N, 1, D, H, W], got {tuple(x.shape)}")
+        x = x.contiguous().float()
+        ctx = context.reshape(x.shape[0], -1).contiguous().float()        # [N, 1, C] or [N, C] (:110-112) -> [N, C]
+        if ctx.shape[1] != self.cfg["cross_attention_dim"]:
+            raise ValueError(f"context has {ctx.shape[1]} covariates, expected {self.cfg['cross_attention_dim']} "
+                             "(context length must be 1)")
+        eng = self.engine_for(x)
+        if torch.is_grad_enabled() and any(p.requires_grad for p in eng.params):
+            return _AttenFn.apply(eng, x, ctx, *eng.params)
+        return eng.forward(x, ctx).clone()
+
+
+class _AttenFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx_, eng, x, context, *params):
+        ctx_.eng = eng
+        return eng.forward(x, context).clone()
+
+    @staticmethod
+    def backward(ctx_, dy):
+        grads = ctx_.eng.backward(dy.contiguous().float())
+        return (None, None, None, *grads)
+
+
+class _ZeroGrad(graph.Op):
+    """Parameters the forward never uses mathematically (attn2.to_q / to_k / norm2 with a length-1 context): zero grads."""
+
+    def __init__(self):
+        self.slots: List[torch.Tensor] = []
+
+    def bwd(self) -> None:
+        for s in self.slots:
+            s.zero_()
+
+
+class _AttenEngine(_EngineBase):
+    CPAD = 16
+
+    def __init__(self, net: AttenUNet, shape, dev):
+        super().__init__(net, dev)
+        n, _, D, H, W = shape
+        cfg = net.cfg
+        ch = cfg["num_channels"]
+        nl = len(ch)
+        if D % (1 << (nl - 1)) or H % (1 << (nl - 1)) or W % (1 << (nl - 1)):
+            raise ValueError(f"spatial dims {D}x{H}x{W} must be divisible by {1 << (nl - 1)}")
+        for c in ch:
+            if c % 8:
+                raise ValueError(f"channel widths must be multiples of 8 (got {c})")
+        self.shape, self.n = shape, n
+        self.context: Optional[torch.Tensor] = None
+        self.zero = _ZeroGrad()
+        self._zero_params: List[nn.Parameter] = []
+        t = self.tape
+        dims = lambda lvl: (D >> lvl, H >> lvl, W >> lvl)
+        B = lambda lvl, c, name: Buf(n, *dims(lvl), c, dev, name)
+        nres = cfg["num_res_blocks"]
+        # ---- plan the skip list and the up path's concat buffers (cat([h, skip]) is never executed) ----
+        skip_c, skip_lvl = [ch[0]], [0]
+        for i in range(nl):
+            for _ in range(nres[i]):
+                skip_c.append(ch[i]); skip_lvl.append(i)
+            if i != nl - 1:
+                skip_c.append(ch[i]); skip_lvl.append(i + 1)
+        cats: List[List[Buf]] = []
+        slot: Dict[int, Sl] = {}
+        k = len(skip_c) - 1
+        h_c = ch[-1]
+        for i in range(nl):
+            lvl = nl - 1 - i
+            row = []
+            for j in range(nres[lvl] + 1):
+                assert skip_lvl[k] == lvl
+                cb = B(lvl, h_c + skip_c[k], f"up{i}.{j}.cat")
+                slot[k] = cb.sl(h_c, skip_c[k])
+                row.append(cb)
+                h_c = ch[lvl]
+                k -= 1
+            cats.append(row)
+        assert k == -1
+        # ---- stem ----
+        self.inp = B(0, self.CPAD, "input")
+        c_in = self._conv(self.inp.sl(), net.conv_in.conv, ksize=3, stride=1, pad=1, need_dx=False, name="conv_in")
+        h = B(0, ch[0], "h0")
+        t.add(NormActOp(c_in.z, "none", ops.ACT_NONE, [h.sl(), slot[0]]))
+        sk = 1
+        # ---- down path ----
+        for i, blk in enumerate(net.down_blocks):
+            for j, rb in enumerate(blk.resnets):
+                has_attn = cfg["attention_levels"][i]
+                if has_attn:
+                    h = self._resnet(rb, h, i, [None], f"down{i}.{j}")
+                    h = self._transformer(blk.attentions[j], h, i, [None, slot[sk]], f"down{i}.{j}.attn")
+                else:
+                    h = self._resnet(rb, h, i, [None, slot[sk]], f"down{i}.{j}")
+                sk += 1
+            if blk.downsampler is not None:
+                h = self._resnet(blk.downsampler, h, i, [None, slot[sk]], f"down{i}.ds", down=True)
+                sk += 1
+        # ---- middle ----
+        mb = net.middle_block
+        h = self._resnet(mb.resnet_1, h, nl - 1, [None], "mid.r1")
+        h = self._transformer(mb.attention, h, nl - 1, [None], "mid.attn")
+        h = self._resnet(mb.resnet_2, h, nl - 1, [cats[0][0].sl(0, ch[-1])], "mid.r2", standalone=False)
+        # ---- up path ----
+        for i, blk in enumerate(net.up_blocks):
+            lvl = nl - 1 - i
+            for j, rb in enumerate(blk.resnets):
+                last_in_block = j == len(blk.resnets) - 1
+                nxt: Optional[Sl] = None
+                if not last_in_block:
+                    nxt = cats[i][j + 1].sl(0, ch[lvl])
+                has_attn = cfg["attention_levels"][lvl]
+                last_of_all = last_in_block and blk.upsampler is None
+                if has_attn:
+                    h = self._resnet(rb, cats[i][j], lvl, [None], f"up{i}.{j}")
+                    h = self._transformer(blk.attentions[j], h, lvl, [nxt] if nxt is not None else [None],
+                                          f"up{i}.{j}.attn", standalone=nxt is None)
+                else:
+                    h = self._resnet(rb, cats[i][j], lvl, [nxt] if nxt is not None else [None], f"up{i}.{j}",
+                                     standalone=nxt is None)
+            if blk.upsampler is not None:
+                h = self._resnet(blk.upsampler, h, lvl, [cats[i + 1][0].sl(0, ch[lvl])], f"up{i}.us", up=True,
+                                 standalone=False)
+        # ---- head ----
+        a = B(0, ch[0], "out.a")
+        gn = NormActOp(h, "group", ops.ACT_SILU, [a.sl()], gn=net.out[0])
+        t.add(gn)
+        self._bind += [(gn, "grad_gamma", net.out[0].weight), (gn, "grad_beta", net.out[0].bias)]
+        self.head = self._conv(a.sl(), net.out[2].conv, ksize=3, stride=1, pad=1, y_fp32=True, name="out.conv")
+        t.add(self.zero)
+        self.y = torch.zeros(n, 1, D, H, W, dtype=torch.float32, device=dev)
+        self._finish()
+        for p in self._zero_params:
+            if all(p is not q for q in self.params):
+                self.params.append(p)
+
+    # ------------------------------------------------------------------------------------------------ builders
+    def _gn_act(self, z: Buf, gn: nn.GroupNorm, act: int, dst: Buf) -> NormActOp:
+        op = NormActOp(z, "group", act, [dst.sl()], gn=gn)
+        self.tape.add(op)
+        self._bind += [(op, "grad_gamma", gn.weight), (op, "grad_beta", gn.bias)]
+        return op
+
+    def _resnet(self, rb: ResnetBlock, x: Buf, lvl: int, dsts: List[Optional[Sl]], name: str, up: bool = False,
+                down: bool = False, standalone: bool = True) -> Optional[Buf]:
+        """ResnetBlock.forward (atten_unet_model.py:641-662).  ``dsts``: None entries mean "a fresh standalone buffer"
+        (returned); Sl entries are concat-buffer slots that receive a copy of the output."""
+        t, dev, n = self.tape, self.dev, self.n
+        cin, cout = rb.channels, rb.out_channels
+        assert x.c == cin, (name, x.c, cin)
+        a1 = Buf(n, x.d, x.h, x.w, cin, dev, name + ".a1")
+        self._gn_act(x, rb.norm1, ops.ACT_SILU, a1)
+        if down:
+            a1p = Buf(n, x.d // 2, x.h // 2, x.w // 2, cin, dev, name + ".a1p")
+            xs = Buf(n, x.d // 2, x.h // 2, x.w // 2, cin, dev, name + ".xs")
+            t.add(ResampleOp(a1.sl(), a1p.sl(), up=False))
+            t.add(ResampleOp(x.sl(), xs.sl(), up=False))
+            c1 = self._conv(a1p.sl(), rb.conv1.conv, ksize=3, stride=1, pad=1, name=name + ".conv1")
+        elif up:
+            xs = Buf(n, 2 * x.d, 2 * x.h, 2 * x.w, cin, dev, name + ".xs")
+            t.add(ResampleOp(x.sl(), xs.sl(), up=True))
+            c1 = self._conv(a1.sl(), rb.conv1.conv, ksize=3, stride=1, pad=1, op=ops.OP_UPCONV, name=name + ".conv1")
+        else:
+            xs = x
+            c1 = self._conv(a1.sl(), rb.conv1.conv, ksize=3, stride=1, pad=1, name=name + ".conv1")
+        a2 = Buf(n, c1.z.d, c1.z.h, c1.z.w, cout, dev, name + ".a2")
+        self._gn_act(c1.z, rb.norm2, ops.ACT_SILU, a2)
+        c2 = self._conv(a2.sl(), rb.conv2.conv, ksize=3, stride=1, pad=1, name=name + ".conv2")
+        if isinstance(rb.skip_connection, nn.Identity):
+            res = xs.sl()
+        else:
+            cs = self._conv(xs.sl(), rb.skip_connection.conv, ksize=1, stride=1, pad=0, name=name + ".skip")
+            res = cs.z.sl()
+        return self._emit(c2.z, res, dsts, name)
+
+    def _emit(self, z: Buf, res: Sl, dsts: List[Optional[Sl]], name: str) -> Optional[Buf]:
+        """out = z + res written to up to two destinations; returns the standalone buffer if one was requested."""
+        out = None
+        real: List[Sl] = []
+        for d in dsts:
+            if d is None:
+                out = Buf(z.n, z.d, z.h, z.w, z.c, self.dev, name + ".out")
+                real.append(out.sl())
+            else:
+                real.append(d)
+        self.tape.add(NormActOp(z, "none", ops.ACT_NONE, real, res=res))
+        return out
+
+    def _linear(self, x: Sl, lin: nn.Linear, name: str, out: Optional[Sl] = None) -> ConvOp:
+        return self._conv(x, lin, ksize=1, stride=1, pad=0, name=name, out=out)
+
+    def _transformer(self, st: SpatialTransformer, x: Buf, lvl: int, dsts: List[Optional[Sl]], name: str,
+                     standalone: bool = True) -> Optional[Buf]:
+        """SpatialTransformer.forward (atten_unet_model.py:315-343) with one BasicTransformerBlock (:225-235)."""
+        t, dev, n = self.tape, self.dev, self.n
+        c = x.c
+        L = x.d * x.h * x.w
+        blk: BasicTransformerBlock = st.transformer_blocks[0]
+        heads = blk.attn1.num_heads
+        T = lambda ch_, nm: Buf(n, x.d, x.h, x.w, ch_, dev, f"{name}.{nm}")
+        g = T(c, "gn")
+        self._gn_act(x, st.norm, ops.ACT_NONE, g)
+        t0 = self._conv(g.sl(), st.proj_in.conv, ksize=1, stride=1, pad=0, name=name + ".proj_in").z
+        inner = t0.c
+        n1 = T(inner, "n1")
+        ln1 = LayerNormOp(t0, n1, blk.norm1)
+        t.add(ln1)
+        self._bind += [(ln1, "grad_gamma", blk.norm1.weight), (ln1, "grad_beta", blk.norm1.bias)]
+        qkv = T(3 * inner, "qkv")
+        for idx, lin in enumerate((blk.attn1.to_q, blk.attn1.to_k, blk.attn1.to_v)):
+            self._linear(n1.sl(), lin, f"{name}.qkv{idx}", out=qkv.sl(idx * inner, inner))
+        o = T(inner, "o")
+        t.add(AttentionOp(qkv, o, heads, L))
+        p = self._linear(o.sl(), blk.attn1.to_out[0], name + ".to_out").z
+        t1 = T(inner, "t1")
+        t.add(NormActOp(p, "none", ops.ACT_NONE, [t1.sl()], res=t0.sl()))
+        cb = CovariateBiasOp(t1, self, blk.attn2.to_v, blk.attn2.to_out[0], L)
+        t.add(cb)
+        self._bind += [(cb, "grad_wv", blk.attn2.to_v.weight), (cb, "grad_wo", blk.attn2.to_out[0].weight),
+                       (cb, "grad_bo", blk.attn2.to_out[0].bias)]
+        self._zero_params += [blk.attn2.to_q.weight, blk.attn2.to_k.weight, blk.norm2.weight, blk.norm2.bias]
+        n3 = T(inner, "n3")
+        ln3 = LayerNormOp(t1, n3, blk.norm3)
+        t.add(ln3)
+        self._bind += [(ln3, "grad_gamma", blk.norm3.weight), (ln3, "grad_beta", blk.norm3.bias)]
+        hh = self._linear(n3.sl(), blk.ff.linear1, name + ".ff1").z
+        gg = T(hh.c // 2, "geglu")
+        t.add(GegluOp(hh, gg))
+        f2 = self._linear(gg.sl(), blk.ff.linear2, name + ".ff2").z
+        t3 = T(inner, "t3")
+        t.add(NormActOp(f2, "none", ops.ACT_NONE, [t3.sl()], res=t1.sl()))
+        po = self._conv(t3.sl(), st.proj_out.conv, ksize=1, stride=1, pad=0, name=name + ".proj_out").z
+        return self._emit(po, x.sl(), dsts, name)
+
+    # ------------------------------------------------------------------------------------------------ run
+    def grad_slots(self, out=None):
+        grads = super().grad_slots(out)
+        by_id = {id(p): g for p, g in zip(self.params, grads)}
+        self.zero.slots = [by_id[id(p)] for p in self._zero_params]
+        return grads
+
+    def forward(self, x: torch.Tensor, context: torch.Tensor) -> torch.Tensor:
+        n, _, D, H, W = self.shape
+        self.context = context
+        check(lib.petsyn_concat_latent(ptr(x), ptr(x), ptr(self.inp.t), D * H * W, n, 0, self.CPAD, stream_ptr()),
+              "concat_latent")
+        self.tape.forward(self.module.training)
+        check(lib.petsyn_take_channel0(ptr(self.head.zf), ptr(self.y), self.y.numel(), self.head.cout, stream_ptr()),
+              "take_channel0")
+        return self.y
+
+    def backward(self, dy: torch.Tensor, out: Optional[Dict[int, torch.Tensor]] = None, on_ready=None):
+        grads = self.grad_slots(out)
+        check(lib.petsyn_put_channel0_grad(None, ptr(dy), ptr(self.head.zg), dy.numel(), self.head.cout, 0,
+                                           stream_ptr()), "put_channel0_grad")
+        self.tape.backward()
+        return [g.clone() for g in grads] if out is None else []

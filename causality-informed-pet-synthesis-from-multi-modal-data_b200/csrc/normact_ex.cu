@@ -175,6 +175,8 @@ struct Dev {   // device copy of petsyn_normact_desc with typed pointers
   float *dgamma, *dbeta;
   const float* slope_dev;
   float* dslope;
+  const float *ka, *kb;   // per (sample, channel) backward constants of the affine/group path (nullptr: plain path)
+  int dz_acc;
 };
 
 __global__ void __launch_bounds__(256) fwd_kernel(const Dev d) {
@@ -246,7 +248,7 @@ __global__ void __launch_bounds__(256) bwd_reduce_kernel(const Dev d) {
 
 __global__ void __launch_bounds__(256) bwd_apply_kernel(const Dev d) {
   RowIter it(d.C);
-  if (blockIdx.x == 0 && blockIdx.y == 0 && d.dgamma != nullptr) {
+  if (blockIdx.x == 0 && blockIdx.y == 0 && d.dgamma != nullptr && d.ka == nullptr) {
     for (int c = threadIdx.x; c < d.C; c += blockDim.x) {
       d.dbeta[c] = d.sums[c];
       d.dgamma[c] = d.sums[d.C + c];
@@ -268,8 +270,12 @@ __global__ void __launch_bounds__(256) bwd_apply_kernel(const Dev d) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       k0.v[i] = ga.v[i] * rs.v[i];
-      k1.v[i] = s0.v[i] * inv;
-      k2.v[i] = s1.v[i] * inv;
+      k1.v[i] = k0.v[i] * s0.v[i] * inv;      // dz = k0*g - k1 - zhat*k2
+      k2.v[i] = k0.v[i] * s1.v[i] * inv;
+    }
+    if (d.ka != nullptr) {                     // group statistics and/or per-sample affine: constants precomputed
+      k1 = load8f(d.ka + so + it.tx * 8);
+      k2 = load8f(d.kb + so + it.tx * 8);
     }
   }
   const float slope = d.slope_dev ? __ldg(d.slope_dev) : d.slope;
@@ -287,8 +293,13 @@ __global__ void __launch_bounds__(256) bwd_apply_kernel(const Dev d) {
       float g = a.v[i] * act_grad(b, d.act1, slope);
       if (d.t2) g += b2.v[i] * act_grad(b, d.act2, slope);
       const float zh = (x.v[i] - mu.v[i]) * rs.v[i];
-      o.v[i] = k0.v[i] * (g - k1.v[i] - zh * k2.v[i]);
+      o.v[i] = k0.v[i] * g - k1.v[i] - zh * k2.v[i];
       dr.v[i] = a.v[i] + b2.v[i];
+    }
+    if (d.dz_acc) {
+      const F8 old = load8(d.dz + r * d.C + it.tx * 8);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o.v[i] += old.v[i];
     }
     store8(d.dz + r * d.C + it.tx * 8, o);
     if (d.res) {
@@ -300,6 +311,38 @@ __global__ void __launch_bounds__(256) bwd_apply_kernel(const Dev d) {
       }
       store8(p, dr);
     }
+  }
+}
+
+// GroupNorm / per-sample affine backward constants.  With S0 = sum g, S1 = sum g*zhat per (sample, channel):
+//   ka[s,c] = rstd[s,c] * sum_{c' in group(c)} gamma[c'] S0[s,c'] / (rows * group_size),  kb likewise with S1;
+//   dgamma[c] = sum_s S1[s,c], dbeta[c] = sum_s S0[s,c].
+__global__ void group_combine_kernel(const float* __restrict__ sums, const float* __restrict__ gamma,
+                                     const float* __restrict__ rstd, float* __restrict__ ka, float* __restrict__ kb,
+                                     float* __restrict__ dgamma, float* __restrict__ dbeta, int64_t rows, int C,
+                                     int nsamples, int group_size, int accumulate) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < nsamples * C) {
+    const int s = i / C, c = i % C;
+    const float* sm = sums + (int64_t)s * 2 * C;
+    const int g0 = c / group_size * group_size;
+    float a = 0.f, b = 0.f;
+    for (int j = 0; j < group_size; ++j) {
+      const float ga = gamma ? gamma[g0 + j] : 1.f;
+      a += ga * sm[g0 + j];
+      b += ga * sm[C + g0 + j];
+    }
+    const float inv = 1.f / ((float)rows * (float)group_size);
+    ka[i] = rstd[i] * a * inv;
+    kb[i] = rstd[i] * b * inv;
+  }
+  if (i < C && dgamma != nullptr) {
+    float a = 0.f, b = 0.f;
+    for (int s = 0; s < nsamples; ++s) {
+      a += sums[(int64_t)s * 2 * C + C + i];
+      b += sums[(int64_t)s * 2 * C + i];
+    }
+    if (accumulate) { dgamma[i] += a; dbeta[i] += b; } else { dgamma[i] = a; dbeta[i] = b; }
   }
 }
 
@@ -365,6 +408,8 @@ static int32_t to_dev(const petsyn_normact_desc* d, Dev* o) {
   o->dz = reinterpret_cast<__nv_bfloat16*>(d->dz);
   o->dgamma = d->dgamma; o->dbeta = d->dbeta;
   o->slope_dev = d->slope_dev; o->dslope = d->dslope;
+  o->ka = o->kb = nullptr;
+  o->dz_acc = d->dz_accumulate;
   return PETSYN_OK;
 }
 
@@ -425,6 +470,19 @@ int32_t petsyn_normact_bwd(const petsyn_normact_desc* desc, void* stream) {
     bwd_reduce_kernel<<<grid, 256, smem, st>>>(d);
     rc = check_launch("normact bwd_reduce_kernel");
     if (rc) return rc;
+    const int gs = desc->group_size > 1 ? desc->group_size : 1;
+    if (d.per_sample && (gs > 1 || d.gamma != nullptr)) {
+      // the sums workspace holds [S0|S1] for every sample followed by ka and kb: 4 * nsamples * C floats
+      float* ka = d.sums + (size_t)nst * 2 * d.C;
+      float* kb = ka + (size_t)nst * d.C;
+      const int total = nst * d.C;
+      group_combine_kernel<<<(total + 127) / 128, 128, 0, st>>>(d.sums, d.gamma, d.rstd, ka, kb, d.dgamma, d.dbeta, d.rows,
+                                                                d.C, nst, gs, desc->affine_accumulate);
+      rc = check_launch("group_combine_kernel");
+      if (rc) return rc;
+      d.ka = ka;
+      d.kb = kb;
+    }
   }
   bwd_apply_kernel<<<grid, 256, 0, st>>>(d);
   return check_launch("normact bwd_apply_kernel");

@@ -1,0 +1,584 @@
+// Kernels for the covariate-conditioned generator (AttenUNet, unet/utils/atten_unet_model.py): 2x resampling inside
+// the up/down ResnetBlocks (:646-654), and the token-stream ops of the level-3 SpatialTransformer (:65-343): LayerNorm,
+// self-attention over L = D/8*H/8*W/8 tokens (head dim 32), GEGLU, and the covariate injection that cross-attention
+// over a length-1 context reduces to.  All SIMT: these are bandwidth/latency-bound ops on tensors of a
+// few MB; the GEMMs around them (proj_in/out, to_q/k/v, to_out, MLP linears) run on the tcgen05 conv kernel as k=1
+// convolutions.
+#include <cuda_bf16.h>
+
+#include <algorithm>
+
+#include "common.h"
+
+namespace petsyn {
+namespace tk {
+
+__device__ __forceinline__ float bf(const __nv_bfloat16 v) { return __bfloat162float(v); }
+
+// ------------------------------------------------------------------------------------------------ resampling
+// dst[n, od, oh, ow, :] (+)= scale * sum_{2x2x2} src[n, 2od+a, 2oh+b, 2ow+c, :]   (AvgPool3d(2,2): scale = 1/8)
+__global__ void __launch_bounds__(256) resample_down_kernel(const __nv_bfloat16* __restrict__ src, int css, int cos,
+                                                            __nv_bfloat16* __restrict__ dst, int csd, int cod, int N,
+                                                            int OD, int OH, int OW, int C, float scale, int accumulate) {
+  const int cpt = C / 8;
+  const int64_t total = (int64_t)N * OD * OH * OW * cpt;
+  const int ID = 2 * OD, IH = 2 * OH, IW = 2 * OW;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int cg = (int)(i % cpt);
+    int64_t q = i / cpt;
+    const int ow = (int)(q % OW); q /= OW;
+    const int oh = (int)(q % OH); q /= OH;
+    const int od = (int)(q % OD); q /= OD;
+    const int n = (int)q;
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      const int id = 2 * od + (t >> 2), ih = 2 * oh + ((t >> 1) & 1), iw = 2 * ow + (t & 1);
+      const int64_t r = (((int64_t)n * ID + id) * IH + ih) * IW + iw;
+      const uint4 raw = *reinterpret_cast<const uint4*>(src + r * css + cos + cg * 8);
+      const __nv_bfloat162* b2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = __bfloat1622float2(b2[j]);
+        acc[2 * j] += f.x;
+        acc[2 * j + 1] += f.y;
+      }
+    }
+    const int64_t ro = (((int64_t)n * OD + od) * OH + oh) * OW + ow;
+    __nv_bfloat16* p = dst + ro * csd + cod + cg * 8;
+    if (accumulate) {
+      const uint4 raw = *reinterpret_cast<const uint4*>(p);
+      const __nv_bfloat162* b2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = __bfloat1622float2(b2[j]);
+        acc[2 * j] = acc[2 * j] * scale + f.x;
+        acc[2 * j + 1] = acc[2 * j + 1] * scale + f.y;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] *= scale;
+    }
+    uint4 o;
+    __nv_bfloat162 b0 = __floats2bfloat162_rn(acc[0], acc[1]), b1 = __floats2bfloat162_rn(acc[2], acc[3]);
+    __nv_bfloat162 b2o = __floats2bfloat162_rn(acc[4], acc[5]), b3 = __floats2bfloat162_rn(acc[6], acc[7]);
+    o.x = *reinterpret_cast<uint32_t*>(&b0); o.y = *reinterpret_cast<uint32_t*>(&b1);
+    o.z = *reinterpret_cast<uint32_t*>(&b2o); o.w = *reinterpret_cast<uint32_t*>(&b3);
+    *reinterpret_cast<uint4*>(p) = o;
+  }
+}
+
+// dst[n, od, oh, ow, :] (+)= scale * src[n, od/2, oh/2, ow/2, :]   (nearest x2 upsampling: scale = 1)
+__global__ void __launch_bounds__(256) resample_up_kernel(const __nv_bfloat16* __restrict__ src, int css, int cos,
+                                                          __nv_bfloat16* __restrict__ dst, int csd, int cod, int N,
+                                                          int OD, int OH, int OW, int C, float scale, int accumulate) {
+  const int cpt = C / 8;
+  const int64_t total = (int64_t)N * OD * OH * OW * cpt;
+  const int ID = OD / 2, IH = OH / 2, IW = OW / 2;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int cg = (int)(i % cpt);
+    int64_t q = i / cpt;
+    const int ow = (int)(q % OW); q /= OW;
+    const int oh = (int)(q % OH); q /= OH;
+    const int od = (int)(q % OD); q /= OD;
+    const int n = (int)q;
+    const int64_t r = (((int64_t)n * ID + (od >> 1)) * IH + (oh >> 1)) * IW + (ow >> 1);
+    const uint4 raw = *reinterpret_cast<const uint4*>(src + r * css + cos + cg * 8);
+    const __nv_bfloat162* b2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = __bfloat1622float2(b2[j]);
+      acc[2 * j] = f.x * scale;
+      acc[2 * j + 1] = f.y * scale;
+    }
+    const int64_t ro = (((int64_t)n * OD + od) * OH + oh) * OW + ow;
+    __nv_bfloat16* p = dst + ro * csd + cod + cg * 8;
+    if (accumulate) {
+      const uint4 rawd = *reinterpret_cast<const uint4*>(p);
+      const __nv_bfloat162* d2 = reinterpret_cast<const __nv_bfloat162*>(&rawd);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = __bfloat1622float2(d2[j]);
+        acc[2 * j] += f.x;
+        acc[2 * j + 1] += f.y;
+      }
+    }
+    uint4 o;
+    __nv_bfloat162 b0 = __floats2bfloat162_rn(acc[0], acc[1]), b1 = __floats2bfloat162_rn(acc[2], acc[3]);
+    __nv_bfloat162 b2o = __floats2bfloat162_rn(acc[4], acc[5]), b3 = __floats2bfloat162_rn(acc[6], acc[7]);
+    o.x = *reinterpret_cast<uint32_t*>(&b0); o.y = *reinterpret_cast<uint32_t*>(&b1);
+    o.z = *reinterpret_cast<uint32_t*>(&b2o); o.w = *reinterpret_cast<uint32_t*>(&b3);
+    *reinterpret_cast<uint4*>(p) = o;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ LayerNorm (warp per row)
+// x, y: bf16 [rows, C] contiguous, C <= 1024 and C % 32 == 0
+__global__ void __launch_bounds__(256) layernorm_fwd_kernel(const __nv_bfloat16* __restrict__ x,
+                                                            const float* __restrict__ gamma,
+                                                            const float* __restrict__ beta,
+                                                            __nv_bfloat16* __restrict__ y, float* __restrict__ mean,
+                                                            float* __restrict__ rstd, int64_t rows, int C, float eps) {
+  const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  const int per = C / 32;
+  for (int64_t r = (int64_t)blockIdx.x * wpb + (threadIdx.x >> 5); r < rows; r += (int64_t)gridDim.x * wpb) {
+    float v[32];
+    float s = 0.f;
+    for (int j = 0; j < per; ++j) { v[j] = bf(x[r * C + j * 32 + lane]); s += v[j]; }
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mu = s / (float)C;
+    float q = 0.f;
+    for (int j = 0; j < per; ++j) { const float d = v[j] - mu; q += d * d; }
+    for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    const float rs = rsqrtf(q / (float)C + eps);
+    for (int j = 0; j < per; ++j) {
+      const int c = j * 32 + lane;
+      y[r * C + c] = __float2bfloat16((v[j] - mu) * rs * gamma[c] + beta[c]);
+    }
+    if (lane == 0) { mean[r] = mu; rstd[r] = rs; }
+  }
+}
+
+// dx (+)= rstd * (g*gamma - mean(g*gamma) - xhat * mean(g*gamma*xhat)); dgamma += sum g*xhat, dbeta += sum g (fp32 atomics)
+__global__ void __launch_bounds__(256) layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ x,
+                                                            const __nv_bfloat16* __restrict__ dy,
+                                                            const float* __restrict__ gamma,
+                                                            const float* __restrict__ mean,
+                                                            const float* __restrict__ rstd,
+                                                            __nv_bfloat16* __restrict__ dx, float* __restrict__ dgamma,
+                                                            float* __restrict__ dbeta, int64_t rows, int C,
+                                                            int accumulate) {
+  extern __shared__ float sm[];   // [2][C] block partials of dgamma / dbeta
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sm[i] = 0.f;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  const int per = C / 32;
+  float pg[32], pb[32];
+  for (int j = 0; j < per; ++j) pg[j] = pb[j] = 0.f;
+  for (int64_t r = (int64_t)blockIdx.x * wpb + (threadIdx.x >> 5); r < rows; r += (int64_t)gridDim.x * wpb) {
+    const float mu = mean[r], rs = rstd[r];
+    float xh[32], gg[32];
+    float s0 = 0.f, s1 = 0.f;
+    for (int j = 0; j < per; ++j) {
+      const int c = j * 32 + lane;
+      const float g = bf(dy[r * C + c]);
+      xh[j] = (bf(x[r * C + c]) - mu) * rs;
+      gg[j] = g * gamma[c];
+      s0 += gg[j];
+      s1 += gg[j] * xh[j];
+      pg[j] += g * xh[j];
+      pb[j] += g;
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+      s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+      s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+    }
+    s0 /= (float)C; s1 /= (float)C;
+    for (int j = 0; j < per; ++j) {
+      const int c = j * 32 + lane;
+      float v = rs * (gg[j] - s0 - xh[j] * s1);
+      if (accumulate) v += bf(dx[r * C + c]);
+      dx[r * C + c] = __float2bfloat16(v);
+    }
+  }
+  for (int j = 0; j < per; ++j) {
+    atomicAdd(&sm[j * 32 + lane], pg[j]);
+    atomicAdd(&sm[C + j * 32 + lane], pb[j]);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < C; i += blockDim.x) {
+    atomicAdd(dgamma + i, sm[i]);
+    atomicAdd(dbeta + i, sm[C + i]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ GEGLU
+__device__ __forceinline__ float gelu_f(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752f)); }
+__device__ __forceinline__ float gelu_grad(float x) {
+  return 0.5f * (1.f + erff(x * 0.70710678118654752f)) + x * 0.3989422804014327f * __expf(-0.5f * x * x);
+}
+// h: [rows, 2F] = (x | gate); out [rows, F] = x * gelu(gate)     (MONAI MLPBlock act="GEGLU")
+__global__ void __launch_bounds__(256) geglu_fwd_kernel(const __nv_bfloat16* __restrict__ h,
+                                                        __nv_bfloat16* __restrict__ out, int64_t rows, int F) {
+  const int64_t total = rows * F;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / F;
+    const int c = (int)(i - r * F);
+    out[i] = __float2bfloat16(bf(h[r * 2 * F + c]) * gelu_f(bf(h[r * 2 * F + F + c])));
+  }
+}
+__global__ void __launch_bounds__(256) geglu_bwd_kernel(const __nv_bfloat16* __restrict__ h,
+                                                        const __nv_bfloat16* __restrict__ dout,
+                                                        __nv_bfloat16* __restrict__ dh, int64_t rows, int F) {
+  const int64_t total = rows * F;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / F;
+    const int c = (int)(i - r * F);
+    const float x = bf(h[r * 2 * F + c]), g = bf(h[r * 2 * F + F + c]), d = bf(dout[i]);
+    dh[r * 2 * F + c] = __float2bfloat16(d * gelu_f(g));
+    dh[r * 2 * F + F + c] = __float2bfloat16(d * x * gelu_grad(g));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ self-attention, head dim 32
+// qkv: bf16 [N*L, 3*H*32] = (q | k | v), heads contiguous inside each third.  One thread = one query row; keys/values
+// are staged in shared memory 64 at a time; online softmax in fp32.  lse[n, h, t] saved for backward.
+constexpr int kHD = 32, kKT = 64;
+
+__global__ void __launch_bounds__(128) attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out,
+                                                       float* __restrict__ lse, int L, int H, float scale) {
+  __shared__ float sk[kKT][kHD + 1], sv[kKT][kHD + 1];
+  const int n = blockIdx.z, h = blockIdx.y;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int ld = 3 * H * kHD;
+  const __nv_bfloat16* base = qkv + (int64_t)n * L * ld;
+  float q[kHD], acc[kHD];
+  const bool valid = t < L;
+#pragma unroll
+  for (int d = 0; d < kHD; ++d) { q[d] = valid ? bf(base[(int64_t)t * ld + h * kHD + d]) * scale : 0.f; acc[d] = 0.f; }
+  float m = -INFINITY, l = 0.f;
+  for (int k0 = 0; k0 < L; k0 += kKT) {
+    __syncthreads();
+    for (int e = threadIdx.x; e < kKT * kHD; e += blockDim.x) {
+      const int kk = e / kHD, d = e % kHD;
+      const bool ok = k0 + kk < L;
+      sk[kk][d] = ok ? bf(base[(int64_t)(k0 + kk) * ld + H * kHD + h * kHD + d]) : 0.f;
+      sv[kk][d] = ok ? bf(base[(int64_t)(k0 + kk) * ld + 2 * H * kHD + h * kHD + d]) : 0.f;
+    }
+    __syncthreads();
+    const int kn = min(kKT, L - k0);
+    for (int kk = 0; kk < kn; ++kk) {
+      float s = 0.f;
+#pragma unroll
+      for (int d = 0; d < kHD; ++d) s += q[d] * sk[kk][d];
+      const float mn = fmaxf(m, s);
+      const float corr = __expf(m - mn), p = __expf(s - mn);
+      l = l * corr + p;
+#pragma unroll
+      for (int d = 0; d < kHD; ++d) acc[d] = acc[d] * corr + p * sv[kk][d];
+      m = mn;
+    }
+  }
+  if (valid) {
+    const float inv = 1.f / l;
+#pragma unroll
+    for (int d = 0; d < kHD; ++d) out[((int64_t)n * L + t) * (H * kHD) + h * kHD + d] = __float2bfloat16(acc[d] * inv);
+    lse[((int64_t)n * H + h) * L + t] = m + __logf(l);
+  }
+}
+
+// delta[n,h,t] = sum_d dO * O
+__global__ void __launch_bounds__(256) attn_delta_kernel(const __nv_bfloat16* __restrict__ o,
+                                                         const __nv_bfloat16* __restrict__ dout,
+                                                         float* __restrict__ delta, int N, int L, int H) {
+  const int64_t total = (int64_t)N * H * L;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int t = (int)(i % L);
+    const int h = (int)((i / L) % H);
+    const int n = (int)(i / ((int64_t)L * H));
+    const int64_t off = ((int64_t)n * L + t) * (H * kHD) + h * kHD;
+    float s = 0.f;
+#pragma unroll
+    for (int d = 0; d < kHD; ++d) s += bf(o[off + d]) * bf(dout[off + d]);
+    delta[i] = s;
+  }
+}
+
+// dQ: thread per query, loop over keys.  dS = P * (dP - delta), dQ = scale * dS K
+__global__ void __launch_bounds__(128) attn_bwd_dq_kernel(const __nv_bfloat16* __restrict__ qkv,
+                                                          const __nv_bfloat16* __restrict__ dout,
+                                                          const float* __restrict__ lse, const float* __restrict__ delta,
+                                                          __nv_bfloat16* __restrict__ dqkv, int L, int H, float scale) {
+  __shared__ float sk[kKT][kHD + 1], sv[kKT][kHD + 1];
+  const int n = blockIdx.z, h = blockIdx.y;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int ld = 3 * H * kHD;
+  const __nv_bfloat16* base = qkv + (int64_t)n * L * ld;
+  const bool valid = t < L;
+  float q[kHD], go[kHD], dq[kHD];
+  const int64_t orow = ((int64_t)n * L + (valid ? t : 0)) * (H * kHD) + h * kHD;
+#pragma unroll
+  for (int d = 0; d < kHD; ++d) {
+    q[d] = valid ? bf(base[(int64_t)t * ld + h * kHD + d]) * scale : 0.f;
+    go[d] = valid ? bf(dout[orow + d]) : 0.f;
+    dq[d] = 0.f;
+  }
+  const float ls = valid ? lse[((int64_t)n * H + h) * L + t] : 0.f;
+  const float dl = valid ? delta[((int64_t)n * H + h) * L + t] : 0.f;
+  for (int k0 = 0; k0 < L; k0 += kKT) {
+    __syncthreads();
+    for (int e = threadIdx.x; e < kKT * kHD; e += blockDim.x) {
+      const int kk = e / kHD, d = e % kHD;
+      const bool ok = k0 + kk < L;
+      sk[kk][d] = ok ? bf(base[(int64_t)(k0 + kk) * ld + H * kHD + h * kHD + d]) : 0.f;
+      sv[kk][d] = ok ? bf(base[(int64_t)(k0 + kk) * ld + 2 * H * kHD + h * kHD + d]) : 0.f;
+    }
+    __syncthreads();
+    const int kn = min(kKT, L - k0);
+    for (int kk = 0; kk < kn; ++kk) {
+      float s = 0.f, dp = 0.f;
+#pragma unroll
+      for (int d = 0; d < kHD; ++d) { s += q[d] * sk[kk][d]; dp += go[d] * sv[kk][d]; }
+      const float ds = __expf(s - ls) * (dp - dl);
+#pragma unroll
+      for (int d = 0; d < kHD; ++d) dq[d] += ds * sk[kk][d];
+    }
+  }
+  if (valid) {
+#pragma unroll
+    for (int d = 0; d < kHD; ++d) dqkv[((int64_t)n * L + t) * ld + h * kHD + d] = __float2bfloat16(dq[d] * scale);
+  }
+}
+
+// dK, dV: thread per key, loop over queries.  dV = P^T dO, dK = scale * dS^T Q
+__global__ void __launch_bounds__(128) attn_bwd_dkv_kernel(const __nv_bfloat16* __restrict__ qkv,
+                                                           const __nv_bfloat16* __restrict__ dout,
+                                                           const float* __restrict__ lse, const float* __restrict__ delta,
+                                                           __nv_bfloat16* __restrict__ dqkv, int L, int H, float scale) {
+  __shared__ float sq[kKT][kHD + 1], sg[kKT][kHD + 1];
+  __shared__ float sl[kKT], sd[kKT];
+  const int n = blockIdx.z, h = blockIdx.y;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;   // key index
+  const int ld = 3 * H * kHD;
+  const __nv_bfloat16* base = qkv + (int64_t)n * L * ld;
+  const bool valid = t < L;
+  float k[kHD], v[kHD], dk[kHD], dv[kHD];
+#pragma unroll
+  for (int d = 0; d < kHD; ++d) {
+    k[d] = valid ? bf(base[(int64_t)t * ld + H * kHD + h * kHD + d]) : 0.f;
+    v[d] = valid ? bf(base[(int64_t)t * ld + 2 * H * kHD + h * kHD + d]) : 0.f;
+    dk[d] = dv[d] = 0.f;
+  }
+  for (int q0 = 0; q0 < L; q0 += kKT) {
+    __syncthreads();
+    for (int e = threadIdx.x; e < kKT * kHD; e += blockDim.x) {
+      const int qq = e / kHD, d = e % kHD;
+      const bool ok = q0 + qq < L;
+      sq[qq][d] = ok ? bf(base[(int64_t)(q0 + qq) * ld + h * kHD + d]) * scale : 0.f;
+      sg[qq][d] = ok ? bf(dout[((int64_t)n * L + q0 + qq) * (H * kHD) + h * kHD + d]) : 0.f;
+    }
+    for (int e = threadIdx.x; e < kKT; e += blockDim.x) {
+      const bool ok = q0 + e < L;
+      sl[e] = ok ? lse[((int64_t)n * H + h) * L + q0 + e] : 0.f;
+      sd[e] = ok ? delta[((int64_t)n * H + h) * L + q0 + e] : 0.f;
+    }
+    __syncthreads();
+    const int qn = min(kKT, L - q0);
+    for (int qq = 0; qq < qn; ++qq) {
+      float s = 0.f, dp = 0.f;
+#pragma unroll
+      for (int d = 0; d < kHD; ++d) { s += sq[qq][d] * k[d]; dp += sg[qq][d] * v[d]; }
+      const float p = __expf(s - sl[qq]);
+      const float ds = p * (dp - sd[qq]);
+#pragma unroll
+      for (int d = 0; d < kHD; ++d) { dv[d] += p * sg[qq][d]; dk[d] += ds * sq[qq][d]; }
+    }
+  }
+  if (valid) {
+#pragma unroll
+    for (int d = 0; d < kHD; ++d) {
+      dqkv[((int64_t)n * L + t) * ld + H * kHD + h * kHD + d] = __float2bfloat16(dk[d]);   // sq already carries `scale`
+      dqkv[((int64_t)n * L + t) * ld + 2 * H * kHD + h * kHD + d] = __float2bfloat16(dv[d]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ covariate injection
+// Cross-attention over a length-1 context: softmax over one key == 1, so attn2(x, ctx) = to_out(to_v(ctx)) for every
+// token (atten_unet_model.py:156-175).  bias[n, :] = Wo (Wv ctx[n]) + bo, then t[n, l, :] += bias[n, :].
+__global__ void __launch_bounds__(128) covariate_bias_kernel(const float* __restrict__ ctx, const float* __restrict__ wv,
+                                                             const float* __restrict__ wo, const float* __restrict__ bo,
+                                                             float* __restrict__ vbuf, float* __restrict__ bias, int N,
+                                                             int Cctx, int C) {
+  extern __shared__ float sv[];   // [C]
+  const int n = blockIdx.x;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float s = 0.f;
+    for (int j = 0; j < Cctx; ++j) s += wv[c * Cctx + j] * ctx[n * Cctx + j];
+    sv[c] = s;
+    vbuf[n * C + c] = s;
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float s = bo[c];
+    for (int j = 0; j < C; ++j) s += wo[c * C + j] * sv[j];
+    bias[n * C + c] = s;
+  }
+}
+__global__ void __launch_bounds__(256) add_sample_bias_kernel(__nv_bfloat16* __restrict__ t, const float* __restrict__ bias,
+                                                              int64_t rows_per_sample, int64_t rows, int C) {
+  const int64_t total = rows * C;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / C;
+    const int c = (int)(i - r * C);
+    t[i] = __float2bfloat16(bf(t[i]) + bias[(r / rows_per_sample) * C + c]);
+  }
+}
+// dbias[n, c] = sum over the sample's rows of dt[., c]
+__global__ void __launch_bounds__(256) sample_colsum_kernel(const __nv_bfloat16* __restrict__ dt, float* __restrict__ out,
+                                                            int64_t rows_per_sample, int C) {
+  const int n = blockIdx.y;
+  const int c = threadIdx.x % C;
+  const int rl = threadIdx.x / C, rpp = blockDim.x / C;
+  float acc = 0.f;
+  if (rl < rpp)
+    for (int64_t r = (int64_t)blockIdx.x * rpp + rl; r < rows_per_sample; r += (int64_t)gridDim.x * rpp)
+      acc += bf(dt[((int64_t)n * rows_per_sample + r) * C + c]);
+  if (rl < rpp) atomicAdd(out + n * C + c, acc);
+}
+// gradients of the tiny linears: dbo = sum_n dbias; dWo = sum_n dbias (x) v; dv = Wo^T dbias; dWv = sum_n dv (x) ctx
+__global__ void __launch_bounds__(128) covariate_bias_bwd_kernel(const float* __restrict__ ctx, const float* __restrict__ wo,
+                                                                 const float* __restrict__ vbuf,
+                                                                 const float* __restrict__ dbias, float* __restrict__ dwv,
+                                                                 float* __restrict__ dwo, float* __restrict__ dbo, int N,
+                                                                 int Cctx, int C) {
+  extern __shared__ float sdv[];  // [N][C]
+  for (int e = threadIdx.x; e < N * C; e += blockDim.x) {
+    const int n = e / C, j = e % C;
+    float s = 0.f;
+    for (int c = 0; c < C; ++c) s += wo[c * C + j] * dbias[n * C + c];
+    sdv[e] = s;
+  }
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float s = 0.f;
+    for (int n = 0; n < N; ++n) s += dbias[n * C + c];
+    dbo[c] = s;
+  }
+  for (int e = threadIdx.x; e < C * C; e += blockDim.x) {
+    const int c = e / C, j = e % C;
+    float s = 0.f;
+    for (int n = 0; n < N; ++n) s += dbias[n * C + c] * vbuf[n * C + j];
+    dwo[e] = s;
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < C * Cctx; e += blockDim.x) {
+    const int c = e / Cctx, j = e % Cctx;
+    float s = 0.f;
+    for (int n = 0; n < N; ++n) s += sdv[n * C + c] * ctx[n * Cctx + j];
+    dwv[e] = s;
+  }
+}
+
+static int blocks_for(int64_t total, int per_block = 256, int cap = 148 * 16) {
+  return (int)std::max<int64_t>(1, std::min<int64_t>((total + per_block - 1) / per_block, cap));
+}
+
+}  // namespace tk
+}  // namespace petsyn
+
+using namespace petsyn;
+using namespace petsyn::tk;
+#define BFP(p) reinterpret_cast<__nv_bfloat16*>(p)
+#define CBFP(p) reinterpret_cast<const __nv_bfloat16*>(p)
+
+extern "C" {
+
+int32_t petsyn_resample2(const void* src, int32_t src_cstride, int32_t src_coff, void* dst, int32_t dst_cstride,
+                         int32_t dst_coff, int32_t n, int32_t od, int32_t oh, int32_t ow, int32_t c, int32_t up,
+                         float scale, int32_t accumulate, void* stream) {
+  PETSYN_REQUIRE(src && dst && n > 0 && od > 0 && oh > 0 && ow > 0, "bad argument");
+  PETSYN_REQUIRE(c % 8 == 0 && (src_cstride | src_coff | dst_cstride | dst_coff) % 8 == 0,
+                 "channels, pitches and offsets must be multiples of 8");
+  PETSYN_REQUIRE(!up || ((od | oh | ow) & 1) == 0, "upsampled dims must be even");
+  const int64_t total = (int64_t)n * od * oh * ow * (c / 8);
+  if (up)
+    resample_up_kernel<<<blocks_for(total), 256, 0, as_stream(stream)>>>(CBFP(src), src_cstride, src_coff, BFP(dst),
+                                                                         dst_cstride, dst_coff, n, od, oh, ow, c, scale,
+                                                                         accumulate);
+  else
+    resample_down_kernel<<<blocks_for(total), 256, 0, as_stream(stream)>>>(CBFP(src), src_cstride, src_coff, BFP(dst),
+                                                                           dst_cstride, dst_coff, n, od, oh, ow, c, scale,
+                                                                           accumulate);
+  return check_launch("resample kernel");
+}
+
+int32_t petsyn_layernorm_fwd(const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd,
+                             int64_t rows, int32_t c, float eps, void* stream) {
+  PETSYN_REQUIRE(x && gamma && beta && y && mean && rstd && rows > 0, "bad argument");
+  PETSYN_REQUIRE(c % 32 == 0 && c <= 1024, "LayerNorm width must be a multiple of 32, at most 1024");
+  layernorm_fwd_kernel<<<blocks_for(rows, 8), 256, 0, as_stream(stream)>>>(CBFP(x), gamma, beta, BFP(y), mean, rstd, rows,
+                                                                           c, eps);
+  return check_launch("layernorm_fwd_kernel");
+}
+
+int32_t petsyn_layernorm_bwd(const void* x, const void* dy, const float* gamma, const float* mean, const float* rstd,
+                             void* dx, float* dgamma, float* dbeta, int64_t rows, int32_t c, int32_t accumulate_dx,
+                             void* stream) {
+  PETSYN_REQUIRE(x && dy && gamma && mean && rstd && dx && dgamma && dbeta && rows > 0, "bad argument");
+  PETSYN_REQUIRE(c % 32 == 0 && c <= 1024, "LayerNorm width must be a multiple of 32, at most 1024");
+  cudaStream_t st = as_stream(stream);
+  PETSYN_CHECK_CUDA(cudaMemsetAsync(dgamma, 0, c * sizeof(float), st));
+  PETSYN_CHECK_CUDA(cudaMemsetAsync(dbeta, 0, c * sizeof(float), st));
+  layernorm_bwd_kernel<<<blocks_for(rows, 8, 148 * 4), 256, 2 * c * sizeof(float), st>>>(
+      CBFP(x), CBFP(dy), gamma, mean, rstd, BFP(dx), dgamma, dbeta, rows, c, accumulate_dx);
+  return check_launch("layernorm_bwd_kernel");
+}
+
+int32_t petsyn_geglu_fwd(const void* h, void* out, int64_t rows, int32_t f, void* stream) {
+  PETSYN_REQUIRE(h && out && rows > 0 && f > 0, "bad argument");
+  geglu_fwd_kernel<<<blocks_for(rows * f), 256, 0, as_stream(stream)>>>(CBFP(h), BFP(out), rows, f);
+  return check_launch("geglu_fwd_kernel");
+}
+
+int32_t petsyn_geglu_bwd(const void* h, const void* dout, void* dh, int64_t rows, int32_t f, void* stream) {
+  PETSYN_REQUIRE(h && dout && dh && rows > 0 && f > 0, "bad argument");
+  geglu_bwd_kernel<<<blocks_for(rows * f), 256, 0, as_stream(stream)>>>(CBFP(h), CBFP(dout), BFP(dh), rows, f);
+  return check_launch("geglu_bwd_kernel");
+}
+
+int32_t petsyn_attention_fwd(const void* qkv, void* out, float* lse, int32_t n, int32_t l, int32_t heads,
+                             int32_t head_dim, float scale, void* stream) {
+  PETSYN_REQUIRE(qkv && out && lse && n > 0 && l > 0 && heads > 0, "bad argument");
+  PETSYN_REQUIRE(head_dim == kHD, "attention kernels are specialised for head_dim 32 (num_head_channels=32)");
+  dim3 grid((unsigned)((l + 127) / 128), (unsigned)heads, (unsigned)n);
+  attn_fwd_kernel<<<grid, 128, 0, as_stream(stream)>>>(CBFP(qkv), BFP(out), lse, l, heads, scale);
+  return check_launch("attn_fwd_kernel");
+}
+
+int32_t petsyn_attention_bwd(const void* qkv, const void* out, const void* dout, const float* lse, float* delta,
+                             void* dqkv, int32_t n, int32_t l, int32_t heads, int32_t head_dim, float scale,
+                             void* stream) {
+  PETSYN_REQUIRE(qkv && out && dout && lse && delta && dqkv && n > 0 && l > 0 && heads > 0, "bad argument");
+  PETSYN_REQUIRE(head_dim == kHD, "attention kernels are specialised for head_dim 32 (num_head_channels=32)");
+  cudaStream_t st = as_stream(stream);
+  attn_delta_kernel<<<blocks_for((int64_t)n * heads * l), 256, 0, st>>>(CBFP(out), CBFP(dout), delta, n, l, heads);
+  int32_t rc = check_launch("attn_delta_kernel");
+  if (rc) return rc;
+  dim3 grid((unsigned)((l + 127) / 128), (unsigned)heads, (unsigned)n);
+  attn_bwd_dq_kernel<<<grid, 128, 0, st>>>(CBFP(qkv), CBFP(dout), lse, delta, BFP(dqkv), l, heads, scale);
+  rc = check_launch("attn_bwd_dq_kernel");
+  if (rc) return rc;
+  attn_bwd_dkv_kernel<<<grid, 128, 0, st>>>(CBFP(qkv), CBFP(dout), lse, delta, BFP(dqkv), l, heads, scale);
+  return check_launch("attn_bwd_dkv_kernel");
+}
+
+int32_t petsyn_covariate_bias_fwd(const float* ctx, const float* wv, const float* wo, const float* bo, float* vbuf,
+                                  float* bias, void* tokens, int32_t n, int32_t cctx, int32_t c,
+                                  int64_t rows_per_sample, void* stream) {
+  PETSYN_REQUIRE(ctx && wv && wo && bo && vbuf && bias && tokens && n > 0 && cctx > 0 && c > 0, "bad argument");
+  cudaStream_t st = as_stream(stream);
+  covariate_bias_kernel<<<n, 128, c * sizeof(float), st>>>(ctx, wv, wo, bo, vbuf, bias, n, cctx, c);
+  int32_t rc = check_launch("covariate_bias_kernel");
+  if (rc) return rc;
+  add_sample_bias_kernel<<<blocks_for(rows_per_sample * n * c), 256, 0, st>>>(BFP(tokens), bias, rows_per_sample,
+                                                                            rows_per_sample * n, c);
+  return check_launch("add_sample_bias_kernel");
+}
+
+int32_t petsyn_covariate_bias_bwd(const float* ctx, const float* wo, const float* vbuf, const void* dtokens,
+                                  float* dbias, float* dwv, float* dwo, float* dbo, int32_t n, int32_t cctx, int32_t c,
+                                  int64_t rows_per_sample, void* stream) {
+  PETSYN_REQUIRE(ctx && wo && vbuf && dtokens && dbias && dwv && dwo && dbo && n > 0, "bad argument");
+  PETSYN_REQUIRE(c <= 256 && 256 % c == 0 && (size_t)n * c * sizeof(float) <= 48 * 1024, "unsupported width/batch");
+  cudaStream_t st = as_stream(stream);
+  PETSYN_CHECK_CUDA(cudaMemsetAsync(dbias, 0, (size_t)n * c * sizeof(float), st));
+  dim3 grid((unsigned)std::min<int64_t>(64, (rows_per_sample + 1) / 2), (unsigned)n);
+  sample_colsum_kernel<<<grid, 256, 0, st>>>(CBFP(dtokens), dbias, rows_per_sample, c);
+  int32_t rc = check_launch("sample_colsum_kernel");
+  if (rc) return rc;
+  covariate_bias_bwd_kernel<<<1, 128, (size_t)n * c * sizeof(float), st>>>(ctx, wo, vbuf, dbias, dwv, dwo, dbo, n, cctx, c);
+  return check_launch("covariate_bias_bwd_kernel");
+}
+
+}  // extern "C"

@@ -75,8 +75,10 @@ class ConvOp(Op):
 
     def __init__(self, x: Sl, weight: torch.nn.Parameter, bias: Optional[torch.nn.Parameter], ksize: int, stride: int,
                  pad: int, op: int = ops.OP_CONV, act: int = ops.ACT_NONE, slope: float = 0.2, y_fp32: bool = False,
-                 use_bias: bool = True, need_dx: bool = True, need_dw: bool = True, name: str = ""):
+                 use_bias: bool = True, need_dx: bool = True, need_dw: bool = True, name: str = "",
+                 out: Optional["Sl"] = None):
         self.x, self.weight, self.bias = x, weight, bias
+        self.out_sl = out                      # write into a channel slice of an existing buffer instead of an own one
         self.name = name
         self.opcode = op
         b = x.buf
@@ -93,12 +95,19 @@ class ConvOp(Op):
         self.padded = (self.cin != cin_w) or (self.cout != cout_w)
         self.use_bias = use_bias and bias is not None
         self.need_dx, self.need_dw = need_dx, need_dw
+        ykw = {}
+        if out is not None:
+            assert out.c == self.cout and not y_fp32
+            ykw = dict(y_cstride=out.buf.c, y_coff=out.off, dy_cstride=out.buf.c, dy_coff=out.off)
         self.plan = ops.ConvPlan(op, b.n, b.d, b.h, b.w, self.cin, self.cout, ksize, stride, pad,
                                  x_cstride=b.c, x_coff=x.off, dx_cstride=b.c, dx_coff=x.off, act=act, slope=slope,
-                                 y_fp32=y_fp32)
+                                 y_fp32=y_fp32, **ykw)
         od, oh, ow = self.plan.out_dims
         self.y_fp32 = y_fp32
-        if y_fp32:
+        if out is not None:
+            assert (out.buf.n, out.buf.d, out.buf.h, out.buf.w) == (b.n, od, oh, ow)
+            self.z = None
+        elif y_fp32:
             self.z = None
             self.zf = torch.zeros(b.n * od * oh * ow, self.cout, dtype=torch.float32, device=dev)
             self.zg = torch.zeros(b.n * od * oh * ow, self.cout, dtype=torch.bfloat16, device=dev)   # grad w.r.t. zf
@@ -139,9 +148,13 @@ class ConvOp(Op):
         self._ver = ver
 
     def out(self) -> torch.Tensor:
+        if self.out_sl is not None:
+            return self.out_sl.buf.t
         return self.zf if self.y_fp32 else self.z.t
 
     def dout(self) -> torch.Tensor:
+        if self.out_sl is not None:
+            return self.out_sl.buf.g
         return self.zg if self.y_fp32 else self.z.g
 
     def fwd(self, training: bool) -> None:
@@ -168,7 +181,8 @@ class ConvOp(Op):
                 self.plan.wgrad(self.x.buf.t, dz, self.grad_w, accumulate=self.acc_dw)
             if self.bias is not None:
                 if self.use_bias:
-                    check(lib.petsyn_colsum(ptr(dz), self.cout, 0, ptr(self.dbias_stage), dz.shape[0], self.cout,
+                    cs, co = (self.out_sl.buf.c, self.out_sl.off) if self.out_sl is not None else (self.cout, 0)
+                    check(lib.petsyn_colsum(ptr(dz), cs, co, ptr(self.dbias_stage), dz.shape[0], self.cout,
                                             stream_ptr()), "colsum")
                     if self.acc_dw:
                         self.grad_b.add_(self.dbias_stage[:self.cout_w])
@@ -189,20 +203,22 @@ class NormActOp(Op):
 
     def __init__(self, z: Buf, kind: str, act: int, dsts: Sequence[Sl], res: Optional[Sl] = None, slope: float = 0.2,
                  bn: Optional[torch.nn.BatchNorm3d] = None, eps: float = 1e-5, name: str = "",
-                 slope_param: Optional[torch.nn.Parameter] = None):
-        assert kind in ("instance", "batch", "none") and 1 <= len(dsts) <= 2
+                 slope_param: Optional[torch.nn.Parameter] = None, gn: Optional[torch.nn.GroupNorm] = None):
+        assert kind in ("instance", "batch", "group", "none") and 1 <= len(dsts) <= 2
+        self.gn = gn                            # nn.GroupNorm (kind == "group"): affine, num_groups, eps
+        self.acc_dz = False
         self.slope_param = slope_param          # nn.PReLU weight (one element): slope read from device memory
         self.grad_slope: Optional[torch.Tensor] = None
         self.z, self.kind, self.act, self.dsts, self.res, self.slope, self.bn, self.eps = z, kind, act, list(dsts), res, \
             slope, bn, eps
         self.name = name
         dev = z.t.device
-        self.ns = z.n if kind == "instance" else 1
+        self.ns = z.n if kind in ("instance", "group") else 1
         self.rows = z.rows // self.ns
         c = z.c
         if kind != "none":
             f = lambda m=1: torch.zeros(self.ns * c * m, dtype=torch.float32, device=dev)
-            self.sums, self.bsums = f(2), f(2)
+            self.sums, self.bsums = f(2), f(4)
             self.scale, self.shift, self.mean, self.rstd = f(), f(), f(), f()
         self.acc_res = False
         self.grad_gamma: Optional[torch.Tensor] = None
@@ -214,7 +230,12 @@ class NormActOp(Op):
         z = self.z
         d = _cabi.NormActDesc()
         d.z, d.rows, d.c, d.nsamples = ptr(z.t), self.rows, z.c, self.ns
-        d.per_sample_stats = 1 if self.kind == "instance" else 0
+        d.per_sample_stats = 1 if self.kind in ("instance", "group") else 0
+        if self.kind == "group":
+            d.group_size = z.c // self.gn.num_groups
+            if backward:
+                d.gamma = ptr(self.gn.weight)
+        d.dz_accumulate = int(self.acc_dz)
         if self.kind != "none":
             d.scale, d.shift = ptr(self.scale), ptr(self.shift)
             if backward:
@@ -255,6 +276,13 @@ class NormActOp(Op):
             check(lib.petsyn_norm_finalize(ptr(self.sums), None, None, None, None, ptr(self.scale), ptr(self.shift),
                                            ptr(self.mean), ptr(self.rstd), self.rows, z.c, z.n, 1, self.eps, 0.0, 1,
                                            stream_ptr()), "norm_finalize")
+        elif self.kind == "group":
+            gn = self.gn
+            self.sums.zero_()
+            check(lib.petsyn_norm_stats(ptr(z.t), ptr(self.sums), self.rows, z.c, z.n, stream_ptr()), "norm_stats")
+            check(lib.petsyn_norm_finalize(ptr(self.sums), ptr(gn.weight), ptr(gn.bias), None, None, ptr(self.scale),
+                                           ptr(self.shift), ptr(self.mean), ptr(self.rstd), self.rows, z.c, z.n,
+                                           z.c // gn.num_groups, gn.eps, 0.0, 1, stream_ptr()), "norm_finalize")
         elif self.kind == "batch":
             bn = self.bn
             if training:
@@ -286,6 +314,127 @@ class NormActOp(Op):
             self.grad_beta.add_(self._tmp_gb[1])
 
 
+class ResampleOp(Op):
+    """dst = AvgPool3d(2,2)(src) (up=False) or nearest x2 upsampling (up=True) of a whole buffer."""
+
+    def __init__(self, src: Sl, dst: Sl, up: bool):
+        self.src, self.dst, self.up = src, dst, up
+        self.acc_dx = False
+
+    def _run(self, a: torch.Tensor, sa: Sl, b: torch.Tensor, sb: Sl, up: bool, scale: float, acc: bool) -> None:
+        ob = sb.buf
+        check(lib.petsyn_resample2(ptr(a), sa.buf.c, sa.off, ptr(b), ob.c, sb.off, ob.n, ob.d, ob.h, ob.w, sb.c, int(up),
+                                   scale, int(acc), stream_ptr()), "resample2")
+
+    def fwd(self, training: bool) -> None:
+        self._run(self.src.buf.t, self.src, self.dst.buf.t, self.dst, self.up, 1.0 if self.up else 0.125, False)
+
+    def grad_writes(self):
+        return [("dx", self.src)]
+
+    def bwd(self) -> None:      # transpose of the forward map
+        self._run(self.dst.buf.g, self.dst, self.src.buf.g, self.src, not self.up, 1.0 if self.up else 0.125, self.acc_dx)
+
+
+class LayerNormOp(Op):
+    """y = nn.LayerNorm(c)(x) on a token stream (whole buffers)."""
+
+    def __init__(self, x: Buf, y: Buf, ln: torch.nn.LayerNorm):
+        self.x, self.y, self.ln = x, y, ln
+        dev = x.t.device
+        self.mean = torch.zeros(x.rows, dtype=torch.float32, device=dev)
+        self.rstd = torch.zeros(x.rows, dtype=torch.float32, device=dev)
+        self.grad_gamma = self.grad_beta = None
+        self.acc_dx = False
+
+    def fwd(self, training: bool) -> None:
+        check(lib.petsyn_layernorm_fwd(ptr(self.x.t), ptr(self.ln.weight), ptr(self.ln.bias), ptr(self.y.t),
+                                       ptr(self.mean), ptr(self.rstd), self.x.rows, self.x.c, self.ln.eps, stream_ptr()),
+              "layernorm_fwd")
+
+    def grad_writes(self):
+        return [("dx", self.x.sl())]
+
+    def bwd(self) -> None:
+        check(lib.petsyn_layernorm_bwd(ptr(self.x.t), ptr(self.y.g), ptr(self.ln.weight), ptr(self.mean), ptr(self.rstd),
+                                       ptr(self.x.g), ptr(self.grad_gamma), ptr(self.grad_beta), self.x.rows, self.x.c,
+                                       int(self.acc_dx), stream_ptr()), "layernorm_bwd")
+
+
+class GegluOp(Op):
+    """out = x * gelu(gate) with h = (x | gate) (MONAI MLPBlock act="GEGLU")."""
+    can_accumulate = False
+
+    def __init__(self, h: Buf, out: Buf):
+        assert h.c == 2 * out.c
+        self.h, self.o = h, out
+
+    def fwd(self, training: bool) -> None:
+        check(lib.petsyn_geglu_fwd(ptr(self.h.t), ptr(self.o.t), self.h.rows, self.o.c, stream_ptr()), "geglu_fwd")
+
+    def grad_writes(self):
+        return [("dx", self.h.sl())]
+
+    def bwd(self) -> None:
+        check(lib.petsyn_geglu_bwd(ptr(self.h.t), ptr(self.o.g), ptr(self.h.g), self.h.rows, self.o.c, stream_ptr()),
+              "geglu_bwd")
+
+
+class AttentionOp(Op):
+    """o = softmax(scale * q k^T) v per (sample, head); qkv = (q | k | v) columns of one buffer."""
+    can_accumulate = False
+
+    def __init__(self, qkv: Buf, out: Buf, heads: int, tokens_per_sample: int):
+        self.qkv, self.o, self.heads, self.L = qkv, out, heads, tokens_per_sample
+        self.n = qkv.rows // tokens_per_sample
+        self.hd = out.c // heads
+        dev = qkv.t.device
+        self.lse = torch.zeros(self.n * heads * self.L, dtype=torch.float32, device=dev)
+        self.delta = torch.zeros_like(self.lse)
+        self.scale = 1.0 / (self.hd ** 0.5)
+        self.flops = 4.0 * self.n * heads * self.L * self.L * self.hd
+
+    def fwd(self, training: bool) -> None:
+        check(lib.petsyn_attention_fwd(ptr(self.qkv.t), ptr(self.o.t), ptr(self.lse), self.n, self.L, self.heads, self.hd,
+                                       self.scale, stream_ptr()), "attention_fwd")
+
+    def grad_writes(self):
+        return [("dx", self.qkv.sl())]
+
+    def bwd(self) -> None:
+        check(lib.petsyn_attention_bwd(ptr(self.qkv.t), ptr(self.o.t), ptr(self.o.g), ptr(self.lse), ptr(self.delta),
+                                       ptr(self.qkv.g), self.n, self.L, self.heads, self.hd, self.scale, stream_ptr()),
+              "attention_bwd")
+
+
+class CovariateBiasOp(Op):
+    """tokens += to_out(to_v(context)) broadcast over the tokens of each sample: what cross-attention over a length-1
+    context computes (atten_unet_model.py:156-175).  In place; the gradient w.r.t. the tokens passes
+    through unchanged, to_q / to_k receive exactly zero gradient."""
+
+    def __init__(self, tokens: Buf, owner, to_v: torch.nn.Linear, to_out: torch.nn.Linear, tokens_per_sample: int):
+        self.t, self.owner, self.to_v, self.to_out, self.L = tokens, owner, to_v, to_out, tokens_per_sample
+        self.n = tokens.rows // tokens_per_sample
+        dev = tokens.t.device
+        c = tokens.c
+        self.vbuf = torch.zeros(self.n, c, dtype=torch.float32, device=dev)
+        self.bias = torch.zeros(self.n, c, dtype=torch.float32, device=dev)
+        self.dbias = torch.zeros(self.n, c, dtype=torch.float32, device=dev)
+        self.grad_wv = self.grad_wo = self.grad_bo = None
+
+    def fwd(self, training: bool) -> None:
+        ctx = self.owner.context
+        check(lib.petsyn_covariate_bias_fwd(ptr(ctx), ptr(self.to_v.weight), ptr(self.to_out.weight),
+                                            ptr(self.to_out.bias), ptr(self.vbuf), ptr(self.bias), ptr(self.t.t), self.n,
+                                            ctx.shape[1], self.t.c, self.L, stream_ptr()), "covariate_bias_fwd")
+
+    def bwd(self) -> None:
+        ctx = self.owner.context
+        check(lib.petsyn_covariate_bias_bwd(ptr(ctx), ptr(self.to_out.weight), ptr(self.vbuf), ptr(self.t.g),
+                                            ptr(self.dbias), ptr(self.grad_wv), ptr(self.grad_wo), ptr(self.grad_bo),
+                                            self.n, ctx.shape[1], self.t.c, self.L, stream_ptr()), "covariate_bias_bwd")
+
+
 class Tape:
     """Ordered op list with static gradient write/accumulate analysis."""
 
@@ -309,12 +458,14 @@ class Tape:
                 overlap = any(a < hi and lo < b for a, b in ranges)
                 if overlap and not covered:
                     raise RuntimeError(f"gradient region {s.buf.name}[{lo}:{hi}] partially overlaps an earlier write")
+                if covered and not getattr(op, "can_accumulate", True):
+                    raise RuntimeError(f"{type(op).__name__} cannot accumulate into an already written gradient region")
                 if key == "dx":
                     op.acc_dx = covered
                 elif key == "dres":
                     op.acc_res = covered
-                elif key == "dz" and covered:
-                    raise RuntimeError("raw conv outputs have a single consumer")
+                elif key == "dz":
+                    op.acc_dz = covered
                 if not covered:
                     ranges.append((lo, hi))
         self._final = True

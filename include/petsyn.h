@@ -225,6 +225,10 @@ typedef struct petsyn_normact_desc {
   void* dz;                  /* bwd: gradient w.r.t. z, bf16 contiguous */
   float* dgamma;             /* optional outputs (batch statistics with affine) */
   float* dbeta;
+  int32_t group_size;        /* channels sharing statistics (GroupNorm); 0/1 = per channel.  With group_size > 1 or a
+                              * per-sample affine the `sums` workspace must hold 4*nsamples*c floats */
+  int32_t dz_accumulate;     /* bwd: add into dz (the normalised tensor has other consumers, e.g. a ResnetBlock skip) */
+  int32_t affine_accumulate; /* bwd: add into dgamma/dbeta (group/per-sample-affine path) */
   const float* slope_dev;    /* PETSYN_ACT_PRELU: device scalar holding the slope (MONAI ResidualUnit act="PRELU") */
   float* dslope;             /* bwd: d(loss)/d(slope) accumulated into this device scalar (caller-zeroed) */
 } petsyn_normact_desc;
@@ -246,6 +250,48 @@ int32_t petsyn_add_slice(const void* src, int32_t src_cstride, int32_t src_coff,
                          int32_t dst_coff, int64_t rows, int32_t c, int32_t accumulate, void* stream);
 /* out[c] = sum over rows of x[:, coff + c] (bias gradient); out fp32, overwritten. */
 int32_t petsyn_colsum(const void* x, int32_t cstride, int32_t coff, float* out, int64_t rows, int32_t c, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Covariate-conditioned generator (AttenUNet, unet/utils/atten_unet_model.py): resampling inside the up/down
+ * ResnetBlocks and the token-stream ops of the level-3 SpatialTransformer.  The linear layers around them are k=1
+ * convolutions of the conv family.
+ * ---------------------------------------------------------------------------------------------------------- */
+
+/* up == 0: dst[o] (+)= scale * sum of the 2x2x2 src block (AvgPool3d(2,2) with scale 1/8, atten_unet_model.py:498,
+ * 652-654; also the backward of nearest upsampling with scale 1).  up == 1: dst[o] (+)= scale * src[o/2] (nearest x2,
+ * :535, 646-651; also the backward of average pooling with scale 1/8).  (od, oh, ow) are dst's dims. */
+int32_t petsyn_resample2(const void* src, int32_t src_cstride, int32_t src_coff, void* dst, int32_t dst_cstride,
+                         int32_t dst_coff, int32_t n, int32_t od, int32_t oh, int32_t ow, int32_t c, int32_t up,
+                         float scale, int32_t accumulate, void* stream);
+/* nn.LayerNorm(c) over the channel dim of a token stream [rows, c] (bf16), atten_unet_model.py:221-223. */
+int32_t petsyn_layernorm_fwd(const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd,
+                             int64_t rows, int32_t c, float eps, void* stream);
+int32_t petsyn_layernorm_bwd(const void* x, const void* dy, const float* gamma, const float* mean, const float* rstd,
+                             void* dx, float* dgamma, float* dbeta, int64_t rows, int32_t c, int32_t accumulate_dx,
+                             void* stream);
+/* MONAI MLPBlock(act="GEGLU") gate: h [rows, 2f] = (x | gate) -> x * gelu(gate) (exact erf GELU), :211. */
+int32_t petsyn_geglu_fwd(const void* h, void* out, int64_t rows, int32_t f, void* stream);
+int32_t petsyn_geglu_bwd(const void* h, const void* dout, void* dh, int64_t rows, int32_t f, void* stream);
+/* softmax(scale * Q K^T) V per (sample, head) without materialising the L x L scores (the reference's baddbmm ->
+ * softmax -> bmm, :137-154).  qkv bf16 [n*l, 3*heads*head_dim] = (q | k | v); out bf16 [n*l, heads*head_dim];
+ * lse fp32 [n, heads, l] saved for backward.  head_dim must be 32 (num_head_channels = 32 in training.json). */
+int32_t petsyn_attention_fwd(const void* qkv, void* out, float* lse, int32_t n, int32_t l, int32_t heads,
+                             int32_t head_dim, float scale, void* stream);
+int32_t petsyn_attention_bwd(const void* qkv, const void* out, const void* dout, const float* lse, float* delta,
+                             void* dqkv, int32_t n, int32_t l, int32_t heads, int32_t head_dim, float scale,
+                             void* stream);
+/* Covariate injection: cross-attention over a length-1 context collapses to a per-sample bias
+ * to_out(to_v(context)) broadcast over all tokens (:156-175).  ctx fp32 [n, cctx]; wv [c, cctx];
+ * wo [c, c]; bo [c]; vbuf/bias fp32 [n, c] scratch (kept for backward); tokens bf16 [n*rows_per_sample, c] updated
+ * in place. */
+int32_t petsyn_covariate_bias_fwd(const float* ctx, const float* wv, const float* wo, const float* bo, float* vbuf,
+                                  float* bias, void* tokens, int32_t n, int32_t cctx, int32_t c,
+                                  int64_t rows_per_sample, void* stream);
+/* dbias = per-sample column sums of dtokens; dwv, dwo, dbo = gradients of to_v.weight, to_out.weight, to_out.bias
+ * (to_q / to_k receive exactly zero gradient). */
+int32_t petsyn_covariate_bias_bwd(const float* ctx, const float* wo, const float* vbuf, const void* dtokens,
+                                  float* dbias, float* dwv, float* dwo, float* dbo, int32_t n, int32_t cctx, int32_t c,
+                                  int64_t rows_per_sample, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Losses and optimiser

@@ -1,0 +1,150 @@
+"""Oracle (CPU, fp32) for the covariate-conditioned generator ``AttenUNet`` (TEST INFRASTRUCTURE ONLY).
+
+Functional restatement of ``unet/utils/atten_unet_model.py`` driven by the reference's state-dict keys:
+``ResnetBlock`` :565-662, ``Downsample``/``Upsample`` :464-562 (``resblock_updown`` form), ``DownBlock`` /
+``CrossAttnDownBlock`` :665-967, ``CrossAttnMidBlock`` :1037-1100, ``UpBlock`` / ``CrossAttnUpBlock`` :1103-1409,
+``SpatialTransformer`` :238-343, ``BasicTransformerBlock`` :178-235, ``CrossAttention`` :65-175, ``AttenUNet.forward``
+:1792-1860.  The two MONAI pieces the file imports are restated per upstream: ``Convolution(conv_only=True)`` =
+``nn.Conv3d`` child named ``conv``; ``MLPBlock(act="GEGLU")`` = linear1 -> chunk -> x*gelu(gate) -> linear2.
+Pinned by ``tests/test_oracle_cpu.py::test_atten_unet_oracle_matches_live_reference`` (the reference class imported
+unmodified over a stub ``monai``) and ``tests/golden/atten_unet_*.npz``.
+"""
+from __future__ import annotations
+
+import zlib
+from typing import Dict, List, Sequence
+
+import torch
+import torch.nn.functional as F
+
+TRAINING_JSON = dict(  # unet/config/training.json:8-38 (atten_unet_def) + cross_attention_dim injected at train_unet.py:64-68
+    spatial_dims=3, in_channels=1, out_channels=1, num_channels=[16, 32, 64, 128], num_res_blocks=2,
+    attention_levels=[False, False, False, True], norm_num_groups=16, norm_eps=1e-6, resblock_updown=True,
+    num_head_channels=[0, 0, 0, 32], with_conditioning=True, transformer_num_layers=1, upcast_attention=False,
+    use_flash_attention=False, cross_attention_dim=5)
+
+
+def randomize_(named_tensors, seed: int = 0) -> None:
+    """Deterministic, construction-order-independent re-draw of every parameter (by NAME), so that the reference, the
+    oracle and the CUDA modules can be given identical weights -- and so that the reference's ``zero_module`` tensors
+    (conv2 / proj_out / out conv, atten_unet_model.py:56-62,303,616,1779), which make the default-initialised network
+    output exactly 0, are non-zero."""
+    with torch.no_grad():
+        for name, p in named_tensors:
+            g = torch.Generator().manual_seed(seed * 1000003 + zlib.crc32(name.encode()))
+            r = torch.randn(p.shape, generator=g)
+            if p.dim() >= 2:
+                fan_in = p[0].numel()
+                p.copy_(r / fan_in ** 0.5)
+            elif "norm" in name and name.endswith("weight") or name.endswith("out.0.weight"):
+                p.copy_(1.0 + 0.1 * r)
+            else:
+                p.copy_(0.1 * r)
+
+
+def _gn(sd, pre, x, groups, eps):
+    return F.group_norm(x, groups, sd[pre + "weight"], sd[pre + "bias"], eps)
+
+
+def _conv(sd, pre, x, pad):
+    return F.conv3d(x, sd[pre + "conv.weight"], sd[pre + "conv.bias"], padding=pad)
+
+
+def resnet(sd, pre, x, groups, eps, up=False, down=False):
+    """ResnetBlock.forward (:641-662)."""
+    h = F.silu(_gn(sd, pre + "norm1.", x, groups, eps))
+    if up:
+        x, h = (F.interpolate(t, scale_factor=2.0, mode="nearest") for t in (x, h))
+    elif down:
+        x, h = (F.avg_pool3d(t, 2, 2) for t in (x, h))
+    h = _conv(sd, pre + "conv1.", h, 1)
+    h = F.silu(_gn(sd, pre + "norm2.", h, groups, eps))
+    h = _conv(sd, pre + "conv2.", h, 1)
+    if pre + "skip_connection.conv.weight" in sd:
+        x = _conv(sd, pre + "skip_connection.", x, 0)
+    return x + h
+
+
+def cross_attention(sd, pre, x, ctx, heads):
+    """CrossAttention.forward (:156-175) with the naive baddbmm/softmax/bmm attention (:137-154)."""
+    q = F.linear(x, sd[pre + "to_q.weight"])
+    k = F.linear(ctx, sd[pre + "to_k.weight"])
+    v = F.linear(ctx, sd[pre + "to_v.weight"])
+
+    def split(t):
+        b, l, d = t.shape
+        return t.reshape(b, l, heads, d // heads).permute(0, 2, 1, 3).reshape(b * heads, l, d // heads)
+
+    q, k, v = split(q), split(k), split(v)
+    scale = 1.0 / (q.shape[-1] ** 0.5)
+    probs = (torch.bmm(q, k.transpose(1, 2)) * scale).softmax(-1)
+    o = torch.bmm(probs, v)
+    bh, l, d = o.shape
+    o = o.reshape(bh // heads, heads, l, d).permute(0, 2, 1, 3).reshape(bh // heads, l, d * heads)
+    return F.linear(o, sd[pre + "to_out.0.weight"], sd[pre + "to_out.0.bias"])
+
+
+def transformer(sd, pre, x, ctx, groups, eps, heads):
+    """SpatialTransformer.forward (:315-343) with one BasicTransformerBlock (:225-235)."""
+    n, c, d, h, w = x.shape
+    res = x
+    t = _conv(sd, pre + "proj_in.", _gn(sd, pre + "norm.", x, groups, eps), 0)
+    t = t.permute(0, 2, 3, 4, 1).reshape(n, d * h * w, -1)
+    b = pre + "transformer_blocks.0."
+    ln = lambda name, v: F.layer_norm(v, (v.shape[-1],), sd[b + name + ".weight"], sd[b + name + ".bias"])
+    t = cross_attention(sd, b + "attn1.", ln("norm1", t), ln("norm1", t), heads) + t
+    t = cross_attention(sd, b + "attn2.", ln("norm2", t), ctx, heads) + t
+    y = F.linear(ln("norm3", t), sd[b + "ff.linear1.weight"], sd[b + "ff.linear1.bias"])
+    a, gate = y.chunk(2, dim=-1)
+    t = F.linear(a * F.gelu(gate), sd[b + "ff.linear2.weight"], sd[b + "ff.linear2.bias"]) + t
+    t = t.reshape(n, d, h, w, -1).permute(0, 4, 1, 2, 3).contiguous()
+    return _conv(sd, pre + "proj_out.", t, 0) + res
+
+
+def forward(x: torch.Tensor, context: torch.Tensor, sd: Dict[str, torch.Tensor], cfg=TRAINING_JSON) -> torch.Tensor:
+    """AttenUNet.forward (:1792-1860) for the resblock_updown / with_conditioning configuration."""
+    ch: Sequence[int] = cfg["num_channels"]
+    nres = cfg["num_res_blocks"]
+    nres = [nres] * len(ch) if isinstance(nres, int) else list(nres)
+    att = cfg["attention_levels"]
+    hc = cfg["num_head_channels"]
+    hc = [hc] * len(ch) if isinstance(hc, int) else list(hc)
+    groups, eps = cfg["norm_num_groups"], cfg["norm_eps"]
+    assert cfg["resblock_updown"] and cfg["with_conditioning"]
+    if context.dim() < 3:
+        context = context.unsqueeze(1)                                            # :110-112
+    heads = lambda lvl: ch[lvl] // hc[lvl]
+    h = _conv(sd, "conv_in.", x, 1)
+    skips: List[torch.Tensor] = [h]
+    for i in range(len(ch)):
+        for j in range(nres[i]):
+            h = resnet(sd, f"down_blocks.{i}.resnets.{j}.", h, groups, eps)
+            if att[i]:
+                h = transformer(sd, f"down_blocks.{i}.attentions.{j}.", h, context, groups, eps, heads(i))
+            skips.append(h)
+        if i != len(ch) - 1:
+            h = resnet(sd, f"down_blocks.{i}.downsampler.", h, groups, eps, down=True)
+            skips.append(h)
+    h = resnet(sd, "middle_block.resnet_1.", h, groups, eps)
+    h = transformer(sd, "middle_block.attention.", h, context, groups, eps, heads(len(ch) - 1))
+    h = resnet(sd, "middle_block.resnet_2.", h, groups, eps)
+    for i in range(len(ch)):
+        lvl = len(ch) - 1 - i
+        for j in range(nres[lvl] + 1):
+            h = torch.cat([h, skips.pop()], 1)
+            h = resnet(sd, f"up_blocks.{i}.resnets.{j}.", h, groups, eps)
+            if att[lvl]:
+                h = transformer(sd, f"up_blocks.{i}.attentions.{j}.", h, context, groups, eps, heads(lvl))
+        if i != len(ch) - 1:
+            h = resnet(sd, f"up_blocks.{i}.upsampler.", h, groups, eps, up=True)
+    h = F.silu(F.group_norm(h, groups, sd["out.0.weight"], sd["out.0.bias"], eps))
+    return F.conv3d(h, sd["out.2.conv.weight"], sd["out.2.conv.bias"], padding=1)
+
+
+def train_step(x, context, target, sd, cfg=TRAINING_JSON):
+    """fwd -> nn.L1Loss -> bwd (train_unet.py:147-149,167 with the perceptual/adversarial terms dropped)."""
+    params = {k: v.detach().clone().requires_grad_(True) for k, v in sd.items()}
+    y = forward(x, context, params, cfg)
+    loss = (y - target).abs().mean()
+    loss.backward()
+    return loss.detach(), y.detach(), {k: p.grad if p.grad is not None else torch.zeros_like(p) for k, p in params.items()}

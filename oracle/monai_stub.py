@@ -194,3 +194,43 @@ def install() -> None:
     nets = mod("monai_diffusion.generative.networks.nets")
     md.generative, gen.networks, nets_pkg.nets = gen, nets_pkg, nets
     nets.PatchDiscriminator = PatchDiscriminator
+
+
+# ------------------------------------------------------------------------------------------------ AttenUNet imports
+class MLPBlock(nn.Module):
+    """Upstream ``monai.networks.blocks.MLPBlock(hidden, mlp_dim, act="GEGLU")`` (atten_unet_model.py:40,211):
+    linear1: hidden -> 2*mlp_dim; x, gate = chunk(2, -1); x * gelu(gate) (exact erf GELU); linear2: mlp_dim -> hidden."""
+
+    def __init__(self, hidden_size, mlp_dim, dropout_rate=0.0, act="GELU", dropout_mode="vit"):
+        super().__init__()
+        assert act == "GEGLU"
+        self.linear1 = nn.Linear(hidden_size, mlp_dim * 2)
+        self.linear2 = nn.Linear(mlp_dim, hidden_size)
+        self.drop1, self.drop2 = nn.Dropout(dropout_rate), nn.Dropout(dropout_rate)
+
+    def forward(self, x):
+        x, gate = self.linear1(x).chunk(2, dim=-1)
+        return self.drop2(self.linear2(self.drop1(x * nn.functional.gelu(gate))))
+
+
+class _PoolFactory:
+    """``monai.networks.layers.factories.Pool``: ``Pool[Pool.AVG, 3]`` is ``nn.AvgPool3d`` (atten_unet_model.py:41,498)."""
+    AVG = "avg"
+
+    def __getitem__(self, key):
+        return nn.AvgPool3d
+
+
+def install_atten() -> None:
+    """Stub ``monai`` so that ``unet/utils/atten_unet_model.py`` imports unmodified (it uses Convolution with
+    conv_only=True, MLPBlock(GEGLU), Pool and ensure_tuple_rep; :40-42)."""
+    install()
+    blocks = sys.modules["monai.networks.blocks"]
+    blocks.MLPBlock = MLPBlock
+    for name in ("monai.networks.layers", "monai.networks.layers.factories", "monai.utils"):
+        if name not in sys.modules:
+            m = types.ModuleType(name)
+            m.__path__ = []
+            sys.modules[name] = m
+    sys.modules["monai.networks.layers.factories"].Pool = _PoolFactory()
+    sys.modules["monai.utils"].ensure_tuple_rep = lambda v, n: tuple(v) if isinstance(v, (list, tuple)) else (v,) * n

@@ -1,0 +1,86 @@
+"""Model-level parity of the CUDA AttenUNet (covariate-conditioned generator, BASELINE config 2's model) against the fp32
+CPU oracle and the committed golden (generated from the reference class over the monai stub), peer-calibrated against
+the same graph under PyTorch bf16 autocast on the GPU: error <= 2x the peer's (plus a small floor)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import atten_unet as OA
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def synth(shape, seed):
+    g = torch.Generator().manual_seed(seed)
+    n, d, h, w = shape
+    return (torch.rand(n, 1, d, h, w, generator=g), torch.rand(n, 1, 5, generator=g),
+            torch.rand(n, 1, d, h, w, generator=g))
+
+
+def test_train_step_matches_oracle_and_golden(petsyn):
+    gold = np.load(os.path.join(GOLD, "atten_unet_2x32x48x32.npz"))
+    shape, seed = tuple(int(v) for v in gold["shape"]), int(gold["seed"])
+    model = petsyn.AttenUNet(**OA.TRAINING_JSON).train()
+    OA.randomize_(model.named_parameters(), seed=seed)
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    for k, v in sd.items():
+        ref = float(gold["wsum/" + k])
+        assert abs(float(v.double().abs().sum()) - ref) <= 1e-6 * max(1.0, ref), k
+    x, ctx, tgt = synth(shape, seed)
+    loss_o, y_o, grads_o = OA.train_step(x, ctx, tgt, sd)
+    assert abs(float(loss_o) - float(gold["loss"])) < 1e-6 and np.abs(y_o.numpy() - gold["output"]).max() < 1e-5
+    # peer
+    pp = {k: v.detach().clone().cuda().requires_grad_(True) for k, v in sd.items()}
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        y_p = OA.forward(x.cuda(), ctx.cuda(), pp)
+    (y_p.float() - tgt.cuda()).abs().mean().backward()
+    peer_err = (y_p.detach().float().cpu() - y_o).abs()
+
+    model = model.cuda()
+    y = model(x.cuda(), ctx.cuda())
+    loss = torch.nn.functional.l1_loss(y, tgt.cuda())
+    loss.backward()
+    torch.cuda.synchronize()
+    err = (y.detach().cpu() - y_o).abs()
+    print("out err ours max/mean", err.max().item(), err.mean().item(), "peer", peer_err.max().item(), peer_err.mean().item(),
+          "loss", loss.item(), float(loss_o))
+    assert err.max().item() <= 2.0 * peer_err.max().item() + 5e-3
+    assert err.mean().item() <= 2.0 * peer_err.mean().item() + 5e-4
+    assert abs(loss.item() - float(gold["loss"])) <= 2e-3
+    tot = tot_o = tot_p = 0.0
+    zero_keys = [k for k in sd if ".attn2.to_q." in k or ".attn2.to_k." in k or ".transformer_blocks.0.norm2." in k]
+    assert len(zero_keys) == 6 * 4
+    for k, p in model.named_parameters():
+        a, b = p.grad.double().cpu().flatten(), grads_o[k].double().flatten()
+        c = (pp[k].grad if pp[k].grad is not None else torch.zeros_like(pp[k])).double().cpu().flatten()
+        tot += (a ** 2).sum().item(); tot_o += (b ** 2).sum().item(); tot_p += (c ** 2).sum().item()
+        if k in zero_keys:
+            assert a.abs().max().item() == 0.0 and b.abs().max().item() < 1e-12, k
+            continue
+        if b.norm().item() > 1e-2 * float(gold["grad_norm_total"]):
+            rel, rel_p = abs(a.norm() - b.norm()).item() / b.norm().item(), abs(c.norm() - b.norm()).item() / b.norm().item()
+            assert rel <= max(2.0 * rel_p, 0.05), (k, a.norm().item(), b.norm().item(), c.norm().item())
+            cos = (torch.dot(a, b) / (a.norm() * b.norm())).item()
+            cos_p = (torch.dot(c, b) / (c.norm() * b.norm())).item()
+            assert 1 - cos <= max(2.0 * (1 - cos_p), 2e-2), (k, cos, cos_p)
+    print("grad-norm ours/oracle/peer", tot ** 0.5, tot_o ** 0.5, tot_p ** 0.5)
+    assert abs(tot ** 0.5 - tot_o ** 0.5) <= max(2.0 * abs(tot_p ** 0.5 - tot_o ** 0.5), 2e-2 * tot_o ** 0.5)
+
+
+def test_contracts(petsyn):
+    cfg = dict(OA.TRAINING_JSON)
+    with pytest.raises(ValueError):
+        petsyn.AttenUNet(**{**cfg, "cross_attention_dim": None})                      # atten_unet_model.py:1623-1627
+    with pytest.raises(ValueError):
+        petsyn.AttenUNet(**{**cfg, "num_channels": [16, 32, 64, 100]})                # not a multiple of the group count
+    m = petsyn.AttenUNet(**cfg).cuda()
+    assert len(m.state_dict()) == 416 and sum(p.numel() for p in m.parameters()) == 12562945
+    y = m(torch.rand(1, 1, 16, 16, 16, device="cuda"), torch.rand(1, 5, device="cuda"))   # 2-D context (:110-112)
+    assert float(y.abs().max()) == 0.0                                                 # zero_module init
+    with pytest.raises(ValueError):
+        m(torch.rand(1, 1, 12, 16, 16, device="cuda"), torch.rand(1, 1, 5, device="cuda"))    # 12 % 8 != 0
+    with pytest.raises(ValueError):
+        m(torch.rand(1, 1, 16, 16, 16, device="cuda"), torch.rand(1, 1, 6, device="cuda"))    # wrong covariate count
