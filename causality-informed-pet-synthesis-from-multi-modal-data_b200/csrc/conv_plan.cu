@@ -441,6 +441,7 @@ static int32_t launch_igemm(const GemmSide& g, int batch, cudaStream_t st) {
     switch (g.block_n) {
       case 16: return launch_igemm_bn<16, OUT_BF16_REDUCE>(g, grid, st);
       case 32: return launch_igemm_bn<32, OUT_BF16_REDUCE>(g, grid, st);
+      case 48: return launch_igemm_bn<48, OUT_BF16_REDUCE>(g, grid, st);
       case 64: return launch_igemm_bn<64, OUT_BF16_REDUCE>(g, grid, st);
       case 128: return launch_igemm_bn<128, OUT_BF16_REDUCE>(g, grid, st);
       default: return fail(PETSYN_EINVAL, "unsupported BLOCK_N %d for accumulating output", g.block_n);
@@ -450,6 +451,7 @@ static int32_t launch_igemm(const GemmSide& g, int batch, cudaStream_t st) {
     switch (g.block_n) {
       case 16: return launch_igemm_bn<16, OUT_F32_REDUCE>(g, grid, st);
       case 32: return launch_igemm_bn<32, OUT_F32_REDUCE>(g, grid, st);
+      case 48: return launch_igemm_bn<48, OUT_F32_REDUCE>(g, grid, st);
       case 64: return launch_igemm_bn<64, OUT_F32_REDUCE>(g, grid, st);
       case 128: return launch_igemm_bn<128, OUT_F32_REDUCE>(g, grid, st);
       default: return fail(PETSYN_EINVAL, "unsupported BLOCK_N %d for split-K", g.block_n);
@@ -459,6 +461,7 @@ static int32_t launch_igemm(const GemmSide& g, int batch, cudaStream_t st) {
     switch (g.block_n) {
       case 16: return launch_igemm_bn<16, OUT_F32>(g, grid, st);
       case 32: return launch_igemm_bn<32, OUT_F32>(g, grid, st);
+      case 48: return launch_igemm_bn<48, OUT_F32>(g, grid, st);
       case 64: return launch_igemm_bn<64, OUT_F32>(g, grid, st);
       case 128: return launch_igemm_bn<128, OUT_F32>(g, grid, st);
       default: return fail(PETSYN_EINVAL, "unsupported BLOCK_N %d for fp32 output", g.block_n);
