@@ -506,5 +506,8 @@ class _AttenEngine(_EngineBase):
         grads = self.grad_slots(out)
         check(lib.petsyn_put_channel0_grad(None, ptr(dy), ptr(self.head.zg), dy.numel(), self.head.cout, 0,
                                            stream_ptr()), "put_channel0_grad")
-        self.tape.backward()
+        self.run_backward(on_ready)
+        if on_ready is not None:
+            for p in self._zero_params:
+                on_ready(p)
         return [g.clone() for g in grads] if out is None else []

@@ -182,6 +182,36 @@ class _EngineBase:
         self.tape.finalize()
         self.flops_algorithmic = self.tape.flops()
 
+    def grad_order(self) -> List[nn.Parameter]:
+        """Parameters in the order backward produces their gradients (reverse op order), then any parameter no op
+        produces a gradient for."""
+        order, seen = [], set()
+        for op in reversed(self.tape.ops):
+            for o, _, p in self._bind:
+                if o is op and id(p) not in seen:
+                    seen.add(id(p))
+                    order.append(p)
+        for p in self.params:
+            if id(p) not in seen:
+                seen.add(id(p))
+                order.append(p)
+        return order
+
+    def run_backward(self, on_ready=None) -> None:
+        """Tape backward; ``on_ready(param)`` fires right after the op producing that parameter's gradient."""
+        cb = None
+        if on_ready is not None:
+            by_op: Dict[int, List[nn.Parameter]] = {}
+            for op, _, p in self._bind:
+                by_op.setdefault(id(op), []).append(p)
+            cb = lambda op: [on_ready(p) for p in by_op.get(id(op), [])]
+        self.tape.backward(cb)
+
+    def mark_weights_dirty(self) -> None:
+        for op in self.tape.ops:
+            if hasattr(op, "_ver"):
+                op._ver = None
+
     def grad_slots(self, out: Optional[Dict[int, torch.Tensor]] = None) -> List[torch.Tensor]:
         """Bind every op's gradient destination; ``out`` maps id(param) -> tensor (flat-arena views), else the engine
         owns the buffers."""

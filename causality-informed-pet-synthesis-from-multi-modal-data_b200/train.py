@@ -414,3 +414,83 @@ class BmganTrainer:
                     op._ver = None
             self.eeng.tape.repack()
         self.graph = g
+
+
+class AttenUNetTrainer:
+    """Fused training step for the covariate-conditioned generator (``train_unet.py:136-168`` with the offline-available
+    terms: zero_grad -> unet(t1, condition) -> nn.L1Loss -> backward -> Adam), data-parallel like Unet3dTrainer.
+    Single GPU: the whole step replays as one CUDA graph after ``capture()``."""
+
+    def __init__(self, model, lr: float = 5e-4, betas=(0.9, 0.999), eps: float = 1e-8, bucket_mb: float = 32.0,
+                 process_group=None, example_input: Optional[torch.Tensor] = None):
+        if example_input is None:
+            raise ValueError("example_input (a tensor of the training shape) is required to lay out the arenas")
+        self.model = model
+        self.lr, self.betas, self.eps = lr, betas, eps
+        self.pg = process_group
+        self.world = dist.get_world_size(process_group) if (dist.is_available() and dist.is_initialized()) else 1
+        dev = example_input.device
+        self.dev = dev
+        self.eng = model.engine_for(example_input)
+        order = self.eng.grad_order()
+        assert {id(p) for p in order} == {id(p) for p in model.parameters()}
+        self.arena = FlatArena(order, dev)
+        self.m, self.v = torch.zeros_like(self.arena.p), torch.zeros_like(self.arena.p)
+        self.step_dev = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.step_count = 0
+        self.loss = torch.zeros(1, dtype=torch.float32, device=dev)
+        self.dy = torch.zeros(example_input.shape, dtype=torch.float32, device=dev)
+        self.bucketer = GradBucketer(self.arena, bucket_mb, process_group)
+        self.graph = None
+        self.static = None
+        if self.world > 1:
+            dist.broadcast(self.arena.p, src=0, group=self.pg)
+        self.eng.mark_weights_dirty()
+
+    def _step_impl(self, x: torch.Tensor, context: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
+        eng = self.eng
+        y = eng.forward(x, context)
+        self.loss.zero_()
+        ops.l1_loss_fwd_bwd(y, target, self.loss, self.dy)
+        eng.backward(self.dy, out=self.arena.grad_views, on_ready=self.bucketer.on_ready)
+        self.bucketer.wait_all()
+        self.step_dev.add_(1)
+        ops.adam_step(self.arena.p, self.arena.g, self.m, self.v, self.lr, self.betas[0], self.betas[1], self.eps, 0,
+                      step_dev=self.step_dev)
+        eng.mark_weights_dirty()
+        return self.loss
+
+    def step(self, x: torch.Tensor, context: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
+        self.step_count += 1
+        ctx = context.reshape(x.shape[0], -1)
+        if self.graph is None:
+            return self._step_impl(x, ctx.contiguous().float(), target)
+        for dst, src in zip(self.static, (x, ctx, target)):
+            if dst.data_ptr() != src.data_ptr():
+                dst.copy_(src, non_blocking=True)
+        self.graph.replay()
+        return self.loss
+
+    def capture(self, warmup: int = 2) -> None:
+        if self.world > 1:
+            raise RuntimeError("AttenUNetTrainer.capture supports world_size 1; data-parallel runs launch eagerly")
+        state = [self.arena.p, self.m, self.v, self.step_dev]
+        snap = [t.clone() for t in state]
+        n = self.dy.shape[0]
+        cdim = self.model.cfg["cross_attention_dim"]
+        self.static = (torch.zeros_like(self.dy), torch.zeros(n, cdim, dtype=torch.float32, device=self.dev),
+                       torch.zeros_like(self.dy))
+        side = torch.cuda.Stream(device=self.dev)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                self._step_impl(*self.static)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize(self.dev)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self._step_impl(*self.static)
+        for dst, src in zip(state, snap):
+            dst.copy_(src)
+        self.eng.mark_weights_dirty()        # the captured step begins with the repack, so no eager refresh is needed
+        self.graph = g
