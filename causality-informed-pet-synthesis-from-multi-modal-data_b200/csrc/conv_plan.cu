@@ -249,6 +249,26 @@ __global__ void __launch_bounds__(256) unpack_wgrad_kernel(const float* __restri
   }
 }
 
+// small-channel wgrad scratch T[(sub*m_tiles + mt)*128 + tap_local*Cin + ci][co] -> dw[co][ci][k]
+__global__ void __launch_bounds__(256) unpack_wgrad_small_kernel(const float* __restrict__ scratch,
+                                                                 float* __restrict__ dw,
+                                                                 const InvEntryDev* __restrict__ inv, int Cout, int Cin,
+                                                                 int k3, int npad, int tpm, int m_tiles, int accumulate) {
+  const int total = Cout * Cin * k3;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int k = i % k3;
+    const int ci = (i / k3) % Cin;
+    const int co = i / (k3 * Cin);
+    const InvEntryDev e = inv[k];
+    float acc = 0.f;
+    for (int q = 0; q < e.n; ++q) {
+      const int mt = e.tap[q] / tpm, tl = e.tap[q] - mt * tpm;
+      acc += scratch[((int64_t)(e.sub[q] * m_tiles + mt) * 128 + tl * Cin + ci) * npad + co];
+    }
+    if (accumulate) dw[i] += acc; else dw[i] = acc;
+  }
+}
+
 // split-K finish: fp32 [rows, C] (contiguous) -> act(x + bias) as bf16 into a channel slice
 __global__ void __launch_bounds__(256) splitk_finish_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst,
                                                             int64_t rows, int C, int cstride, int coff,
@@ -326,6 +346,9 @@ struct petsyn_conv_plan {
   int inv_max = 1;              // max number of packed slots one original tap contributes to
   int wg_box_w = 0, wg_box_h = 0, wg_box_d = 0;
   int wg_block_n = 128, wg_ksplit = 1;
+  bool wg_small = false;        // small-channel path: taps folded into the MMA M dimension (wgrad_small_kernel)
+  int wg_tpm = 1, wg_mtiles = 1, wg_npad = 16;
+  petsyn::WgradSmallParams wgs_params;
   const void* wg_key_x = nullptr; const void* wg_key_g = nullptr; const void* wg_key_s = nullptr;
   petsyn::WgradParams wg_params;
 };
@@ -752,6 +775,16 @@ int32_t petsyn_conv_plan_create(const petsyn_conv_desc* d, petsyn_conv_plan** ou
     int64_t ks = (148 * 4 + base_ctas - 1) / base_ctas;
     ks = std::max<int64_t>(1, std::min<int64_t>(ks, std::max<int64_t>(1, nboxes / 8)));
     pl->wg_ksplit = (int)ks;
+    if (d->op != PETSYN_OP_CONVT && d->cin % 16 == 0 && d->cin <= 64 && d->cout <= 64) {
+      pl->wg_small = true;
+      pl->wg_tpm = 128 / d->cin;
+      pl->wg_mtiles = (f.prog.max_taps + pl->wg_tpm - 1) / pl->wg_tpm;
+      pl->wg_npad = (d->cout + 15) / 16 * 16;
+      const int64_t ctas = (int64_t)pl->wg_mtiles * (int64_t)f.prog.subs.size();
+      int64_t ks2 = (148 * 3 + ctas - 1) / ctas;
+      ks2 = std::max<int64_t>(1, std::min<int64_t>(ks2, std::max<int64_t>(1, nboxes / 8)));
+      pl->wg_ksplit = (int)ks2;
+    }
   }
   if (rc) {
     petsyn_conv_plan_destroy(pl);
@@ -793,7 +826,11 @@ int32_t petsyn_conv_flops(const petsyn_conv_plan* pl, double* algorithmic, doubl
 
 size_t petsyn_conv_packed_fprop_bytes(const petsyn_conv_plan* pl) { return pl ? packed_bytes(pl->fprop) : 0; }
 size_t petsyn_conv_packed_dgrad_bytes(const petsyn_conv_plan* pl) { return pl ? packed_bytes(pl->dgrad) : 0; }
-size_t petsyn_conv_wgrad_scratch_bytes(const petsyn_conv_plan* pl) { return pl ? packed_bytes(pl->fprop) * 2 : 0; }
+size_t petsyn_conv_wgrad_scratch_bytes(const petsyn_conv_plan* pl) {
+  if (!pl) return 0;
+  if (pl->wg_small) return (size_t)pl->fprop.subs.size() * pl->wg_mtiles * 128 * pl->wg_npad * sizeof(float);
+  return packed_bytes(pl->fprop) * 2;
+}
 
 size_t petsyn_conv_workspace_bytes(const petsyn_conv_plan* pl) {
   if (!pl) return 0;
@@ -859,6 +896,58 @@ int32_t petsyn_conv_wgrad(petsyn_conv_plan* pl, const void* x, const void* dy, v
   PETSYN_REQUIRE(pl && x && dy && scratch && dw, "null argument");
   GemmSide& f = pl->fprop;
   cudaStream_t st = as_stream(stream);
+  if (pl->wg_small) {
+    WgradSmallParams& q = pl->wgs_params;
+    if (!(pl->wg_key_x == x && pl->wg_key_g == dy && pl->wg_key_s == scratch)) {
+      memset(&q, 0, sizeof(q));
+      const int n_x = f.prog.a_phased ? 8 : 1;
+      const int n_g = f.prog.out_phased ? 8 : 1;
+      for (int i = 0; i < n_x; ++i) {
+        int32_t rc = view_map(&q.x_maps[i], x, pl->vx, f.prog.a_phased, i, 2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 16,
+                              pl->wg_box_w, pl->wg_box_h, pl->wg_box_d, 32);
+        if (rc) return rc;
+      }
+      for (int i = 0; i < n_g; ++i) {
+        int32_t rc = view_map(&q.g_maps[i], dy, pl->vdy, f.prog.out_phased, i, 2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 16,
+                              pl->wg_box_w, pl->wg_box_h, pl->wg_box_d, 32);
+        if (rc) return rc;
+      }
+      uint64_t dims[2] = {(uint64_t)pl->wg_npad, (uint64_t)f.subs.size() * pl->wg_mtiles * 128};
+      uint64_t strides[1] = {dims[0] * 4};
+      uint32_t box[2] = {(uint32_t)pl->wg_npad, 128u};
+      int32_t rc = encode_tmap(&q.d_map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, scratch, dims, strides, box, 0);
+      if (rc) return rc;
+      for (size_t i = 0; i < f.subs.size(); ++i) q.subs[i] = f.subs[i];
+      q.taps = f.d_taps;
+      q.tiles_w = (f.out_w + pl->wg_box_w - 1) / pl->wg_box_w;
+      q.tiles_h = (f.out_h + pl->wg_box_h - 1) / pl->wg_box_h;
+      q.tiles_d = (f.out_d + pl->wg_box_d - 1) / pl->wg_box_d;
+      q.batch = pl->desc.n;
+      q.box_w = pl->wg_box_w; q.box_h = pl->wg_box_h; q.box_d = pl->wg_box_d;
+      q.cin = pl->desc.cin; q.cin_atoms = pl->desc.cin / 16;
+      q.n_atoms = pl->wg_npad / 16;
+      q.tpm = pl->wg_tpm; q.m_tiles = pl->wg_mtiles; q.ksplit = pl->wg_ksplit;
+      pl->wg_key_x = x; pl->wg_key_g = dy; pl->wg_key_s = scratch;
+    }
+    PETSYN_CHECK_CUDA(cudaMemsetAsync(scratch, 0, petsyn_conv_wgrad_scratch_bytes(pl), st));
+    constexpr int STAGES = 4;
+    constexpr int smem = STAGES * (12 * 2048) + 1024 + 256;
+    auto kern = wgrad_small_kernel<STAGES>;
+    static bool attr_set = false;
+    if (!attr_set) {
+      PETSYN_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      attr_set = true;
+    }
+    dim3 grid((unsigned)pl->wg_mtiles, (unsigned)pl->wg_ksplit, (unsigned)f.subs.size());
+    kern<<<grid, 128, smem, st>>>(q);
+    int32_t rc = check_launch("wgrad_small_kernel");
+    if (rc) return rc;
+    const int total = pl->desc.cout * pl->desc.cin * pl->k3;
+    unpack_wgrad_small_kernel<<<std::min((total + 255) / 256, 148 * 8), 256, 0, st>>>(
+        reinterpret_cast<const float*>(scratch), dw, pl->d_inv, pl->desc.cout, pl->desc.cin, pl->k3, pl->wg_npad, pl->wg_tpm,
+        pl->wg_mtiles, accumulate);
+    return check_launch("unpack_wgrad_small_kernel");
+  }
   WgradParams& p = pl->wg_params;
   if (!(pl->wg_key_x == x && pl->wg_key_g == dy && pl->wg_key_s == scratch)) {
     memset(&p, 0, sizeof(p));

@@ -410,4 +410,151 @@ __global__ void __launch_bounds__(128) wgrad_kernel(const __grid_constant__ Wgra
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// wgrad for SMALL channel counts (Cin, Cout <= 64, multiples of 16): the AttenUNet full-resolution layers.
+// With 16..64 channels a (Cout x Cin) weight-gradient tile would fill 1/32..1/2 of a 128 x 64 MMA.  Instead the kernel
+// taps are folded into the MMA's M dimension:   D[(tap, ci), co] = sum_vox X_tap[vox, ci] * dY[vox, co]
+// A operand = TPM = 128/Cin shifted boxes of x side by side (16-channel MN-major atoms, 32-byte swizzle),
+// B operand = dy (Cout/16 atoms).  One K step = 64 voxels; split over `ksplit` CTAs; fp32 tiles are TMA-add-reduced into
+// a scratch laid out [(sub, m_tile) * 128 + tap_local * Cin + ci][co].
+// ------------------------------------------------------------------------------------------------------------
+struct alignas(64) WgradSmallParams {
+  CUtensorMap g_maps[kMaxViews];   // dy views; box = (16 ch, bw, bh, bd, 1), 32B swizzle
+  CUtensorMap x_maps[kMaxViews];   // x views;  box = (16 ch, bw, bh, bd, 1), 32B swizzle
+  CUtensorMap d_map;               // fp32 [rows_total, npad] scratch; box = (npad, 128), no swizzle
+  IgemmSub subs[kMaxSubs];
+  const IgemmTap* taps;
+  int32_t tiles_w, tiles_h, tiles_d, batch;
+  int32_t box_w, box_h, box_d;
+  int32_t cin, cin_atoms;          // Cin, Cin/16
+  int32_t n_atoms;                 // Cout/16 (padded)
+  int32_t tpm;                     // taps per M tile
+  int32_t m_tiles;                 // M tiles per sub-problem (grid.x)
+  int32_t ksplit;
+};
+
+template <int STAGES>
+__global__ void __launch_bounds__(128) wgrad_small_kernel(const __grid_constant__ WgradSmallParams p) {
+  constexpr int kAtom = 64 * 32;                 // one [64 voxels x 16 channels] box: 2 KB
+  constexpr int kABytes = 8 * kAtom;             // 128 M rows = 8 atoms
+  constexpr int kBBytes = 4 * kAtom;             // up to N = 64
+  constexpr int kStageBytes = kABytes + kBBytes;
+  constexpr int kStagingBytes = 128 * 64 * 4;    // fp32 [128][<=64]
+  constexpr int kPipeBytes = STAGES * kStageBytes;
+  constexpr int kMainBytes = kPipeBytes > kStagingBytes ? kPipeBytes : kStagingBytes;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* tail = smem + kMainBytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* accum_bar = empty_bar + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5;
+  const IgemmSub sub = p.subs[blockIdx.z];
+  const int mt = blockIdx.x;
+  const int tap0 = mt * p.tpm;
+  const int ntaps = min(p.tpm, sub.tap_count - tap0);
+  if (ntaps <= 0) return;
+  const int nboxes = p.tiles_w * p.tiles_h * p.tiles_d * p.batch;
+  const int per = (nboxes + p.ksplit - 1) / p.ksplit;
+  const int kb_begin = blockIdx.y * per;
+  const int nsteps = min(nboxes, kb_begin + per) - kb_begin;
+  if (nsteps <= 0) return;
+  const int npad = p.n_atoms * 16;
+
+  if (warp == 0 && ptx::elect_one()) {
+    for (int s = 0; s < STAGES; ++s) {
+      ptx::mbar_init(&full_bar[s], 1);
+      ptx::mbar_init(&empty_bar[s], 1);
+    }
+    ptx::mbar_init(accum_bar, 1);
+    ptx::fence_mbar_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(tmem_slot, 64);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  ptx::tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (ptx::elect_one()) {
+      const CUtensorMap* gmap = &p.g_maps[sub.c_view];
+      const uint32_t tx_bytes = uint32_t(kAtom) * uint32_t(ntaps * p.cin_atoms + p.n_atoms);
+      for (int s = 0; s < nsteps; ++s) {
+        int kb = kb_begin + s;
+        const int bw = kb % p.tiles_w; kb /= p.tiles_w;
+        const int bh = kb % p.tiles_h; kb /= p.tiles_h;
+        const int bd = kb % p.tiles_d; kb /= p.tiles_d;
+        const int nb = kb;
+        const int w0 = bw * p.box_w, h0 = bh * p.box_h, d0 = bd * p.box_d;
+        const int stage = s % STAGES;
+        const uint32_t ph = (s / STAGES) & 1;
+        ptx::mbar_wait(&empty_bar[stage], ph ^ 1);
+        uint8_t* a_dst = smem + stage * kStageBytes;
+        uint8_t* b_dst = a_dst + kABytes;
+        ptx::mbar_expect_tx(&full_bar[stage], tx_bytes);
+        for (int t = 0; t < ntaps; ++t) {
+          const IgemmTap tp = p.taps[sub.tap_begin + tap0 + t];
+          for (int c = 0; c < p.cin_atoms; ++c)
+            ptx::tma_load_5d(a_dst + (t * p.cin_atoms + c) * kAtom, &p.x_maps[tp.a_view], &full_bar[stage], c * 16,
+                             w0 + tp.dw, h0 + tp.dh, d0 + tp.dd, nb);
+        }
+        for (int c = 0; c < p.n_atoms; ++c)
+          ptx::tma_load_5d(b_dst + c * kAtom, gmap, &full_bar[stage], c * 16, w0, h0, d0, nb);
+      }
+    }
+  } else if (warp == 1) {
+    if (ptx::elect_one()) {
+      // MN-major, 32B swizzle: 16 contiguous channels per voxel row (32 B), 8 voxel rows per 256 B group (SBO),
+      // next 16-channel atom 2048 B further (LBO)
+      constexpr uint64_t desc_base = ptx::umma_desc_base(kAtom, 256, 6);
+      const uint32_t idesc = ptx::umma_idesc_bf16(128, uint32_t(npad), 1, 1);
+      for (int s = 0; s < nsteps; ++s) {
+        const int stage = s % STAGES;
+        const uint32_t ph = (s / STAGES) & 1;
+        ptx::mbar_wait(&full_bar[stage], ph);
+        ptx::tc_fence_after_sync();
+        const uint32_t a_addr = ptx::smem_u32(smem + stage * kStageBytes);
+        const uint32_t b_addr = a_addr + kABytes;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {   // 16 voxels per MMA = two 8-row groups = 512 B
+          ptx::umma_bf16(tmem_base, ptx::umma_desc(desc_base, a_addr + k * 512), ptx::umma_desc(desc_base, b_addr + k * 512),
+                         idesc, (s | k) != 0 ? 1u : 0u);
+        }
+        ptx::umma_commit(&empty_bar[stage]);
+      }
+      ptx::umma_commit(accum_bar);
+    }
+  }
+  __syncwarp();
+
+  ptx::mbar_wait(accum_bar, 0);
+  ptx::tc_fence_after_sync();
+  const int row = tid;
+  const uint32_t lane_base = uint32_t(warp * 32) << 16;
+  float* stg = reinterpret_cast<float*>(smem);
+  for (int cc = 0; cc < npad; cc += 16) {
+    uint32_t v[16];
+    ptx::tmem_ld_32x16(tmem_base + lane_base + uint32_t(cc), v);
+    ptx::tmem_ld_wait();
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      *reinterpret_cast<uint4*>(stg + row * npad + cc + 4 * q) = make_uint4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+  }
+  ptx::tc_fence_before_sync();
+  ptx::fence_proxy_async_smem();
+  __syncthreads();
+  if (warp == 1) ptx::tmem_dealloc(tmem_base, 64);
+  if (tid == 0) {
+    ptx::tma_reduce_add_2d(&p.d_map, smem, 0, (int(blockIdx.z) * p.m_tiles + mt) * 128);
+    ptx::tma_store_commit();
+    ptx::tma_store_wait_all();
+  }
+}
+
 }  // namespace petsyn

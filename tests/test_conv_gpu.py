@@ -48,6 +48,11 @@ CASES = [
     ("upconv", 2, 3, 5, 4, 64, 128, 3, 1, 1),
     ("convt", 1, 4, 6, 8, 64, 64, 4, 2, 1),
     ("convt", 1, 3, 4, 3, 128, 128, 4, 2, 1),
+    ("conv", 2, 8, 12, 16, 16, 16, 3, 1, 1),       # AttenUNet full-resolution layers: small-channel wgrad (8 taps per M tile)
+    ("conv", 1, 8, 8, 12, 32, 48, 3, 1, 1),        # 4 taps per M tile, N = 48
+    ("conv", 1, 8, 8, 8, 48, 16, 3, 1, 1),         # 2 taps per M tile with 32 idle rows
+    ("conv", 1, 4, 8, 8, 16, 32, 1, 1, 0),         # 1x1 skip connection
+    ("upconv", 1, 4, 6, 8, 32, 32, 3, 1, 1),       # up-sampling ResnetBlock conv1 (8 phases x 8 merged taps)
     ("conv", 2, 3, 4, 3, 128, 128, 3, 2, 1),       # odd extents with stride 2 (ResNet_encoder: 3 -> 2)
     ("conv", 1, 6, 8, 6, 256, 256, 4, 2, 1),       # bottleneck-like: few voxels, long K -> split-K fprop
     ("upconv", 1, 3, 4, 3, 256, 256, 3, 1, 1),     # split-K dgrad (64 taps x 4 chunks, 36 voxels)
