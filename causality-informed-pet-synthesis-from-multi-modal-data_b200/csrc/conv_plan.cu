@@ -17,6 +17,7 @@
 
 #include "common.h"
 #include "igemm_kernels.cuh"
+#include "slab_kernels.cuh"
 
 namespace petsyn {
 
@@ -326,6 +327,10 @@ struct GemmSide {           // one gather-form GEMM (fprop or dgrad)
   // cached TMA descriptors, keyed by the base pointers they were built for
   const void* key_a = nullptr; const void* key_b = nullptr; const void* key_c = nullptr; const void* key_w = nullptr;
   IgemmParams params;
+  // small-channel slab path (slab_kernels.cuh): k3 s1 p1, 16..64 channels, many voxels
+  bool slab = false;
+  int slab_grid = 0, slab_smem = 0;
+  SlabParams sparams;
 };
 
 struct ViewSpec {           // an NDHWC tensor (channel slice) and how to derive its tensor maps
@@ -351,6 +356,9 @@ struct petsyn_conv_plan {
   petsyn::WgradSmallParams wgs_params;
   const void* wg_key_x = nullptr; const void* wg_key_g = nullptr; const void* wg_key_s = nullptr;
   petsyn::WgradParams wg_params;
+  bool wg_slab = false;         // slab path (slab_wgrad_kernel): k3 s1 p1, Cin <= 48, many voxels
+  int wg_slab_grid = 0, wg_slab_smem = 0;
+  petsyn::SlabWgradParams wgl_params;
 };
 
 namespace petsyn {
@@ -382,7 +390,24 @@ static int32_t upload(const void* src, size_t bytes, void** dst) {
   return PETSYN_OK;
 }
 
-static int32_t finish_side(GemmSide& g, int N) {
+// persistent-CTA work split of the slab kernels: columns of (tile_w x tile_h) tiles cut into depth chunks
+static void slab_split(int W, int H, int D, int N, int tile_w, int tile_h, int ctas, int* dchunk, int* nchunks, int* items) {
+  const int cols = ((W + tile_w - 1) / tile_w) * ((H + tile_h - 1) / tile_h) * N;
+  double best = -1;
+  *dchunk = D; *nchunks = 1;
+  for (int dc = std::min(D, 4); dc <= D; ++dc) {
+    const int nc = (D + dc - 1) / dc;
+    const int it = cols * nc;
+    const int waves = (it + ctas - 1) / ctas;
+    // longest CTA processes `waves` items of (dc + 2) slab loads and dc tiles each
+    const double cost = (double)waves * (dc + 0.35 * 2.0);
+    const double score = (double)cols * D / ((double)ctas * cost);
+    if (score > best) { best = score; *dchunk = dc; *nchunks = nc; }
+  }
+  *items = cols * *nchunks;
+}
+
+static int32_t finish_side(GemmSide& g, int N, bool allow_slab = false) {
   g.kch = 64;
   g.kc_pad = (g.Kc + g.kch - 1) / g.kch * g.kch;
   if (g.R >= 128) g.block_n = 128;
@@ -421,9 +446,96 @@ static int32_t finish_side(GemmSide& g, int N) {
     }
     g.subs.push_back(sub);
   }
+  if (allow_slab && !g.out_fp32 && g.Kc % 16 == 0 && g.Kc <= 64 && g.R % 16 == 0 && g.R <= 64 &&
+      slab_smem_bytes(27, g.Kc / 16, g.R, ((g.Kc / 16) * kSlabWp * kSlabHp * 32 + 1023) / 1024 * 1024, 4) <= 224 * 1024 &&
+      (int64_t)g.out_w * g.out_h * g.out_d * N >= 128 * 148) {
+    g.slab = true;
+    g.ksplit = 1;
+    g.block_n = g.R;
+  }
   int32_t rc = upload(taps.data(), taps.size() * sizeof(IgemmTap), (void**)&g.d_taps);
   if (rc) return rc;
   return upload(srcs.data(), srcs.size() * sizeof(TapSrcDev), (void**)&g.d_src);
+}
+
+static int32_t view_map(CUtensorMap* out, const void* base, const ViewSpec& v, bool phased, int phase, int esz,
+                        CUtensorMapDataType dt, int box_c, int bw, int bh, int bd, int swizzle);
+
+// tensor map of an NDHWC bf16 view for the slab kernels: dims (16 ch, W, atoms, H, D*N) so that one box load lands as
+// [h][atom][w][16 ch] in shared memory (32B swizzle)
+static int32_t slab_view_map(CUtensorMap* out, const void* base, const ViewSpec& v, int atoms, int box_w, int box_h) {
+  const uint64_t cs = (uint64_t)v.cstride * 2;
+  const uint8_t* b = reinterpret_cast<const uint8_t*>(base) + (uint64_t)v.coff * 2;
+  uint64_t dims[5] = {16, (uint64_t)v.W, (uint64_t)atoms, (uint64_t)v.H, (uint64_t)v.D * v.N};
+  uint64_t strides[4] = {cs, 32, cs * v.W, cs * v.W * v.H};
+  uint32_t box[5] = {16u, (uint32_t)box_w, (uint32_t)atoms, (uint32_t)box_h, 1u};
+  return encode_tmap(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, b, dims, strides, box, 32);
+}
+
+static int32_t bind_slab(GemmSide& g, const ViewSpec& va, const ViewSpec& vc, const void* a, const void* b, const void* c,
+                         const float* bias, int act, float slope) {
+  SlabParams& p = g.sparams;
+  p.bias = bias; p.epi_act = act; p.epi_slope = slope;
+  p.reduce = g.accumulate ? 1 : 0;
+  if (g.key_a == a && g.key_b == b && g.key_c == c) return PETSYN_OK;
+  const int atoms = g.Kc / 16;
+  int32_t rc = slab_view_map(&p.a_map, a, va, atoms, kSlabWp, kSlabHp);
+  if (rc) return rc;
+  {
+    uint64_t dims[2] = {(uint64_t)g.prog.max_taps * g.kc_pad, (uint64_t)g.subs.size() * g.R};
+    uint64_t strides[1] = {dims[0] * 2};
+    uint32_t box[2] = {16u, (uint32_t)g.R};
+    rc = encode_tmap(&p.b_map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, b, dims, strides, box, 32);
+    if (rc) return rc;
+  }
+  rc = view_map(&p.c_map, c, vc, false, 0, 2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, g.R, kSlabW, kSlabH, 1, 0);
+  if (rc) return rc;
+  if (g.prog.subs.size() != 1 || g.prog.subs[0].size() != 27) return fail(PETSYN_EINVAL, "slab path needs one 27-tap program");
+  for (int t = 0; t < 27; ++t) {
+    const TapDef& td = g.prog.subs[0][t];
+    if (td.dd != g.prog.subs[0][t / 9 * 9].dd) return fail(PETSYN_EINVAL, "slab path: taps are not grouped by depth offset");
+    p.tap_off[t] = (((td.dh + 1) * atoms) * (kSlabWp * 32) + (td.dw + 1) * 32) >> 4;
+    p.tap_slab[t / 9] = td.dd + 1;
+  }
+  p.ntaps = g.subs[0].tap_count; p.atoms = atoms; p.kc_pad = g.kc_pad; p.b_row = g.subs[0].b_row;
+  p.block_n = g.R; p.rows = g.R;
+  p.W = va.W; p.H = va.H; p.D = va.D; p.batch = va.N;
+  p.tiles_w = (va.W + kSlabW - 1) / kSlabW;
+  p.tiles_h = (va.H + kSlabH - 1) / kSlabH;
+  p.slab_tx = atoms * kSlabWp * kSlabHp * 32;
+  p.slab_bytes = (p.slab_tx + 1023) / 1024 * 1024;
+  // ring depth and CTAs per SM from the shared-memory budget
+  const int fixed = slab_smem_bytes(p.ntaps, atoms, g.R, p.slab_bytes, 0);
+  const int ring = (fixed + 8 * p.slab_bytes <= 110 * 1024) ? 8 : 4;
+  p.ring = ring;
+  g.slab_smem = fixed + ring * p.slab_bytes;
+  int occ = std::max(1, std::min(3, (227 * 1024) / (g.slab_smem + 1024)));
+  const int ctas = 148 * occ;
+  slab_split(va.W, va.H, va.D, va.N, kSlabW, kSlabH, ctas, &p.dchunk, &p.nchunks, &p.items);
+  g.slab_grid = std::min(ctas, p.items);
+  g.key_a = a; g.key_b = b; g.key_c = c;
+  return PETSYN_OK;
+}
+
+template <int ATOMS>
+static int32_t launch_slab(const GemmSide& g, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    PETSYN_CHECK_CUDA(cudaFuncSetAttribute(slab_conv_kernel<ATOMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+    attr_set = true;
+  }
+  slab_conv_kernel<ATOMS><<<g.slab_grid, 192, g.slab_smem, st>>>(g.sparams);
+  return check_launch("slab_conv_kernel");
+}
+
+static int32_t run_slab(GemmSide& g, cudaStream_t st) {
+  switch (g.Kc / 16) {
+    case 1: return launch_slab<1>(g, st);
+    case 2: return launch_slab<2>(g, st);
+    case 3: return launch_slab<3>(g, st);
+    case 4: return launch_slab<4>(g, st);
+    default: return fail(PETSYN_EINVAL, "slab path: unsupported channel count %d", g.Kc);
+  }
 }
 
 // tensor map of (a phase of) an NDHWC bf16/fp32 view; box = (box_c, bw, bh, bd, 1)
@@ -738,7 +850,8 @@ int32_t petsyn_conv_plan_create(const petsyn_conv_desc* d, petsyn_conv_plan** ou
   f.out_h = f.prog.out_phased ? oh / 2 : oh;
   f.out_d = f.prog.out_phased ? od / 2 : od;
   f.out_rows_full = (int64_t)d->n * od * oh * ow;
-  int32_t rc = finish_side(f, d->n);
+  const bool slab_ok = d->op == PETSYN_OP_CONV && k == 3 && s == 1 && p == 1;
+  int32_t rc = finish_side(f, d->n, slab_ok);
   GemmSide& g = pl->dgrad;
   if (!rc) {
     g.prog = make_program(bwd, k);
@@ -748,7 +861,7 @@ int32_t petsyn_conv_plan_create(const petsyn_conv_desc* d, petsyn_conv_plan** ou
     g.out_h = g.prog.out_phased ? (d->h + 1) / 2 : d->h;
     g.out_d = g.prog.out_phased ? (d->d + 1) / 2 : d->d;
     g.out_rows_full = (int64_t)d->n * d->d * d->h * d->w;
-    rc = finish_side(g, d->n);
+    rc = finish_side(g, d->n, slab_ok);
   }
   if (!rc) {
     // wgrad: inverse table (original tap -> packed (sub, tap) slots) from the fprop program
@@ -784,6 +897,11 @@ int32_t petsyn_conv_plan_create(const petsyn_conv_desc* d, petsyn_conv_plan** ou
       int64_t ks2 = (148 * 3 + ctas - 1) / ctas;
       ks2 = std::max<int64_t>(1, std::min<int64_t>(ks2, std::max<int64_t>(1, nboxes / 8)));
       pl->wg_ksplit = (int)ks2;
+    }
+    if (slab_ok && d->cin % 16 == 0 && d->cin <= 48 && d->cout % 16 == 0 && d->cout <= 64 &&
+        (int64_t)d->w * d->h * d->d * d->n >= 256 * 148) {
+      pl->wg_slab = true;
+      pl->wg_small = false;
     }
   }
   if (rc) {
@@ -828,6 +946,7 @@ size_t petsyn_conv_packed_fprop_bytes(const petsyn_conv_plan* pl) { return pl ? 
 size_t petsyn_conv_packed_dgrad_bytes(const petsyn_conv_plan* pl) { return pl ? packed_bytes(pl->dgrad) : 0; }
 size_t petsyn_conv_wgrad_scratch_bytes(const petsyn_conv_plan* pl) {
   if (!pl) return 0;
+  if (pl->wg_slab) return (size_t)(pl->desc.cout / 16) * 3 * 48 * (3 * (pl->desc.cin / 16) * 16) * sizeof(float);
   if (pl->wg_small) return (size_t)pl->fprop.subs.size() * pl->wg_mtiles * 128 * pl->wg_npad * sizeof(float);
   return packed_bytes(pl->fprop) * 2;
 }
@@ -870,6 +989,10 @@ int32_t petsyn_conv_pack_weights(petsyn_conv_plan* pl, const float* w, void* pac
 int32_t petsyn_conv_fprop(petsyn_conv_plan* pl, const void* x, const void* packed, const float* bias, void* y,
                           void* stream) {
   PETSYN_REQUIRE(pl && x && packed && y, "null argument");
+  if (pl->fprop.slab) {
+    int32_t rs = bind_slab(pl->fprop, pl->vx, pl->vy, x, packed, y, bias, pl->desc.epi_act, pl->desc.epi_slope);
+    return rs ? rs : run_slab(pl->fprop, as_stream(stream));
+  }
   int32_t rc = bind_side(pl->fprop, pl->vx, pl->vy, x, packed, y, bias, pl->desc.epi_act, pl->desc.epi_slope);
   if (rc) return rc;
   return run_side(pl->fprop, pl->vy, y, bias, pl->desc.epi_act, pl->desc.epi_slope, pl->desc.n, as_stream(stream));
@@ -877,6 +1000,10 @@ int32_t petsyn_conv_fprop(petsyn_conv_plan* pl, const void* x, const void* packe
 
 int32_t petsyn_conv_dgrad(petsyn_conv_plan* pl, const void* dy, const void* packed, void* dx, void* stream) {
   PETSYN_REQUIRE(pl && dy && packed && dx, "null argument");
+  if (pl->dgrad.slab) {
+    int32_t rs = bind_slab(pl->dgrad, pl->vdy, pl->vdx, dy, packed, dx, nullptr, PETSYN_ACT_NONE, 0.f);
+    return rs ? rs : run_slab(pl->dgrad, as_stream(stream));
+  }
   int32_t rc = bind_side(pl->dgrad, pl->vdy, pl->vdx, dy, packed, dx, nullptr, PETSYN_ACT_NONE, 0.f);
   if (rc) return rc;
   return run_side(pl->dgrad, pl->vdx, dx, nullptr, PETSYN_ACT_NONE, 0.f, pl->desc.n, as_stream(stream));
@@ -885,6 +1012,12 @@ int32_t petsyn_conv_dgrad(petsyn_conv_plan* pl, const void* dy, const void* pack
 int32_t petsyn_conv_dgrad_accumulate(petsyn_conv_plan* pl, const void* dy, const void* packed, void* dx, void* stream) {
   PETSYN_REQUIRE(pl && dy && packed && dx, "null argument");
   pl->dgrad.accumulate = true;
+  if (pl->dgrad.slab) {
+    int32_t rs = bind_slab(pl->dgrad, pl->vdy, pl->vdx, dy, packed, dx, nullptr, PETSYN_ACT_NONE, 0.f);
+    if (!rs) rs = run_slab(pl->dgrad, as_stream(stream));
+    pl->dgrad.accumulate = false;
+    return rs;
+  }
   int32_t rc = bind_side(pl->dgrad, pl->vdy, pl->vdx, dy, packed, dx, nullptr, PETSYN_ACT_NONE, 0.f);
   if (!rc) rc = run_side(pl->dgrad, pl->vdx, dx, nullptr, PETSYN_ACT_NONE, 0.f, pl->desc.n, as_stream(stream));
   pl->dgrad.accumulate = false;
@@ -896,6 +1029,56 @@ int32_t petsyn_conv_wgrad(petsyn_conv_plan* pl, const void* x, const void* dy, v
   PETSYN_REQUIRE(pl && x && dy && scratch && dw, "null argument");
   GemmSide& f = pl->fprop;
   cudaStream_t st = as_stream(stream);
+  if (pl->wg_slab) {
+    SlabWgradParams& q = pl->wgl_params;
+    const int atoms = pl->desc.cin / 16, co_atoms = pl->desc.cout / 16;
+    const int ncols = 3 * atoms * 16;
+    if (!(pl->wg_key_x == x && pl->wg_key_g == dy && pl->wg_key_s == scratch)) {
+      memset(&q, 0, sizeof(q));
+      int32_t rc = slab_view_map(&q.x_map, x, pl->vx, atoms, kWgW, kWgH + 2);
+      if (rc) return rc;
+      {
+        const ViewSpec& v = pl->vdy;
+        const uint64_t cs = (uint64_t)v.cstride * 2;
+        const uint8_t* b = reinterpret_cast<const uint8_t*>(dy) + (uint64_t)v.coff * 2;
+        uint64_t dims[4] = {(uint64_t)v.C, (uint64_t)v.W, (uint64_t)v.H, (uint64_t)v.D * v.N};
+        uint64_t strides[3] = {cs, cs * v.W, cs * v.W * v.H};
+        uint32_t box[4] = {16u, (uint32_t)(kWgW + 2), (uint32_t)kWgH, 1u};
+        rc = encode_tmap(&q.g_map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, b, dims, strides, box, 32);
+        if (rc) return rc;
+      }
+      q.scratch = reinterpret_cast<float*>(scratch);
+      q.atoms = atoms; q.co_atoms = co_atoms;
+      q.W = pl->desc.w; q.H = pl->desc.h; q.D = pl->desc.d; q.batch = pl->desc.n;
+      q.tiles_w = (q.W + kWgW - 1) / kWgW;
+      q.tiles_h = (q.H + kWgH - 1) / kWgH;
+      q.xslab_tx = atoms * kWgW * (kWgH + 2) * 32;
+      q.xslab_bytes = (q.xslab_tx + 1023) / 1024 * 1024;
+      q.gslab_tx = (kWgW + 2) * kWgH * 32;
+      q.gslab_bytes = (q.gslab_tx + 7 * 32 + 1023) / 1024 * 1024;   // M atoms 3..7 read past the last row: keep it in bounds
+      q.acc_stride = ncols;
+      q.tmem_cols = 3 * ncols <= 256 ? 256 : 512;
+      q.gring = 4;
+      const int cap = (q.tmem_cols == 256 ? 110 : 200) * 1024;
+      q.xring = slab_wgrad_smem_bytes(q.xslab_bytes, q.gslab_bytes, ncols, 8, q.gring) <= cap ? 8 : 4;
+      pl->wg_slab_smem = slab_wgrad_smem_bytes(q.xslab_bytes, q.gslab_bytes, ncols, q.xring, q.gring);
+      const int occ = q.tmem_cols == 256 ? std::max(1, std::min(2, (227 * 1024) / (pl->wg_slab_smem + 1024))) : 1;
+      const int ctas = std::max(1, 148 * occ / co_atoms);
+      slab_split(q.W, q.H, q.D, q.batch, kWgW, kWgH, ctas, &q.dchunk, &q.nchunks, &q.items);
+      pl->wg_slab_grid = std::min(ctas, q.items);
+      PETSYN_CHECK_CUDA(cudaFuncSetAttribute(slab_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+      pl->wg_key_x = x; pl->wg_key_g = dy; pl->wg_key_s = scratch;
+    }
+    PETSYN_CHECK_CUDA(cudaMemsetAsync(scratch, 0, petsyn_conv_wgrad_scratch_bytes(pl), st));
+    dim3 grid((unsigned)pl->wg_slab_grid, (unsigned)co_atoms);
+    slab_wgrad_kernel<<<grid, 192, pl->wg_slab_smem, st>>>(q);
+    int32_t rc = check_launch("slab_wgrad_kernel");
+    if (rc) return rc;
+    const int total = pl->desc.cout * pl->desc.cin * 27;
+    slab_wgrad_unpack_kernel<<<std::min((total + 255) / 256, 148 * 8), 256, 0, st>>>(
+        reinterpret_cast<const float*>(scratch), dw, pl->desc.cout, pl->desc.cin, atoms, accumulate);
+    return check_launch("slab_wgrad_unpack_kernel");
+  }
   if (pl->wg_small) {
     WgradSmallParams& q = pl->wgs_params;
     if (!(pl->wg_key_x == x && pl->wg_key_g == dy && pl->wg_key_s == scratch)) {

@@ -56,6 +56,11 @@ CASES = [
     ("conv", 2, 3, 4, 3, 128, 128, 3, 2, 1),       # odd extents with stride 2 (ResNet_encoder: 3 -> 2)
     ("conv", 1, 6, 8, 6, 256, 256, 4, 2, 1),       # bottleneck-like: few voxels, long K -> split-K fprop
     ("upconv", 1, 3, 4, 3, 256, 256, 3, 1, 1),     # split-K dgrad (64 taps x 4 chunks, 36 voxels)
+    # slab kernels (persistent depth sweep, taps as shifted views of smem-resident halo slabs): need >= 19k / 38k voxels
+    ("conv", 2, 16, 32, 48, 16, 16, 3, 1, 1),      # 1 channel atom, exact tiles, 2 samples (depth halo must not leak)
+    ("conv", 1, 24, 40, 40, 48, 32, 3, 1, 1),      # 3 atoms in, ragged tiles in w and h
+    ("conv", 1, 20, 32, 64, 32, 48, 3, 1, 1),      # N = 48; dgrad runs 48 -> 32
+    ("conv", 3, 7, 48, 40, 16, 64, 3, 1, 1),       # short depth, 3 samples, N = 64
 ]
 
 

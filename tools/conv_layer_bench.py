@@ -27,6 +27,14 @@ LAYERS = {
     "up3": (ops.OP_UPCONV, 1, 6, 7, 6, 512, 512, 3, 1, 1),
     "up2": (ops.OP_UPCONV, 1, 12, 14, 12, 1024, 256, 3, 1, 1),
     "up1": (ops.OP_UPCONV, 1, 24, 28, 24, 512, 128, 3, 1, 1),
+    # AttenUNet (training.json) full- and half-resolution layers at 96x128x96, batch 2
+    "a16_16": (ops.OP_CONV, 2, 96, 128, 96, 16, 16, 3, 1, 1),
+    "a32_32": (ops.OP_CONV, 2, 96, 128, 96, 32, 32, 3, 1, 1),
+    "a48_16": (ops.OP_CONV, 2, 96, 128, 96, 48, 16, 3, 1, 1),
+    "a32_16": (ops.OP_CONV, 2, 96, 128, 96, 32, 16, 3, 1, 1),
+    "h32_32": (ops.OP_CONV, 2, 48, 64, 48, 32, 32, 3, 1, 1),
+    "h64_32": (ops.OP_CONV, 2, 48, 64, 48, 64, 32, 3, 1, 1),
+    "h64_64": (ops.OP_CONV, 2, 48, 64, 48, 64, 64, 3, 1, 1),
 }
 
 
@@ -35,11 +43,11 @@ def main():
     ap.add_argument("--layer", default="up1", choices=sorted(LAYERS))
     ap.add_argument("--pass", dest="which", default="all", choices=["fprop", "dgrad", "wgrad", "all"])
     ap.add_argument("--iters", type=int, default=20)
-    ap.add_argument("--batch", type=int, default=1)
+    ap.add_argument("--batch", type=int, default=0)
     ap.add_argument("--once", action="store_true")
     args = ap.parse_args()
     op, n, d, h, w, cin, cout, k, s, p = LAYERS[args.layer]
-    n = args.batch
+    n = args.batch or n
     dev = torch.device("cuda:0")
     plan = ops.ConvPlan(op, n, d, h, w, cin, cout, k, s, p)
     g = torch.Generator().manual_seed(0)
@@ -75,8 +83,9 @@ def main():
             ts.append(e0.elapsed_time(e1))
         ts.sort()
         med = ts[len(ts) // 2]
+        io_bytes = 2.0 * n * d * h * w * cin + 2.0 * n * od * oh * ow * cout     # bf16 read-once + write-once
         out[name] = {"ms_median": med, "ms_min": ts[0], "tflops_executed": plan.flops_executed / med / 1e9,
-                     "tflops_algorithmic": plan.flops_algorithmic / med / 1e9}
+                     "tflops_algorithmic": plan.flops_algorithmic / med / 1e9, "hbm_gbs_min": io_bytes / med / 1e6}
     print(json.dumps(out))
 
 
