@@ -1,9 +1,8 @@
 // Kernels for the covariate-conditioned generator (AttenUNet, unet/utils/atten_unet_model.py): 2x resampling inside
 // the up/down ResnetBlocks (:646-654), and the token-stream ops of the level-3 SpatialTransformer (:65-343): LayerNorm,
-// self-attention over L = D/8*H/8*W/8 tokens (head dim 32), GEGLU, and the covariate injection that cross-attention
-// over a length-1 context reduces to.  All SIMT: these are bandwidth/latency-bound ops on tensors of a
-// few MB; the GEMMs around them (proj_in/out, to_q/k/v, to_out, MLP linears) run on the tcgen05 conv kernel as k=1
-// convolutions.
+// GEGLU, and the covariate injection that cross-attention over a length-1 context reduces to.  All SIMT:
+// these are bandwidth/latency-bound ops on tensors of a few MB; the GEMMs around them (proj_in/out, to_q/k/v, to_out,
+// MLP linears) run on the tcgen05 conv kernel as k=1 convolutions and self-attention lives in attention_mma.cu.
 #include <cuda_bf16.h>
 
 #include <algorithm>
@@ -221,169 +220,6 @@ __global__ void __launch_bounds__(256) geglu_bwd_kernel(const __nv_bfloat16* __r
   }
 }
 
-// ------------------------------------------------------------------------------------------------ self-attention, head dim 32
-// qkv: bf16 [N*L, 3*H*32] = (q | k | v), heads contiguous inside each third.  One thread = one query row; keys/values
-// are staged in shared memory 64 at a time; online softmax in fp32.  lse[n, h, t] saved for backward.
-constexpr int kHD = 32, kKT = 64;
-
-__global__ void __launch_bounds__(128) attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out,
-                                                       float* __restrict__ lse, int L, int H, float scale) {
-  __shared__ float sk[kKT][kHD + 1], sv[kKT][kHD + 1];
-  const int n = blockIdx.z, h = blockIdx.y;
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  const int ld = 3 * H * kHD;
-  const __nv_bfloat16* base = qkv + (int64_t)n * L * ld;
-  float q[kHD], acc[kHD];
-  const bool valid = t < L;
-#pragma unroll
-  for (int d = 0; d < kHD; ++d) { q[d] = valid ? bf(base[(int64_t)t * ld + h * kHD + d]) * scale : 0.f; acc[d] = 0.f; }
-  float m = -INFINITY, l = 0.f;
-  for (int k0 = 0; k0 < L; k0 += kKT) {
-    __syncthreads();
-    for (int e = threadIdx.x; e < kKT * kHD; e += blockDim.x) {
-      const int kk = e / kHD, d = e % kHD;
-      const bool ok = k0 + kk < L;
-      sk[kk][d] = ok ? bf(base[(int64_t)(k0 + kk) * ld + H * kHD + h * kHD + d]) : 0.f;
-      sv[kk][d] = ok ? bf(base[(int64_t)(k0 + kk) * ld + 2 * H * kHD + h * kHD + d]) : 0.f;
-    }
-    __syncthreads();
-    const int kn = min(kKT, L - k0);
-    for (int kk = 0; kk < kn; ++kk) {
-      float s = 0.f;
-#pragma unroll
-      for (int d = 0; d < kHD; ++d) s += q[d] * sk[kk][d];
-      const float mn = fmaxf(m, s);
-      const float corr = __expf(m - mn), p = __expf(s - mn);
-      l = l * corr + p;
-#pragma unroll
-      for (int d = 0; d < kHD; ++d) acc[d] = acc[d] * corr + p * sv[kk][d];
-      m = mn;
-    }
-  }
-  if (valid) {
-    const float inv = 1.f / l;
-#pragma unroll
-    for (int d = 0; d < kHD; ++d) out[((int64_t)n * L + t) * (H * kHD) + h * kHD + d] = __float2bfloat16(acc[d] * inv);
-    lse[((int64_t)n * H + h) * L + t] = m + __logf(l);
-  }
-}
-
-// delta[n,h,t] = sum_d dO * O
-__global__ void __launch_bounds__(256) attn_delta_kernel(const __nv_bfloat16* __restrict__ o,
-                                                         const __nv_bfloat16* __restrict__ dout,
-                                                         float* __restrict__ delta, int N, int L, int H) {
-  const int64_t total = (int64_t)N * H * L;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int t = (int)(i % L);
-    const int h = (int)((i / L) % H);
-    const int n = (int)(i / ((int64_t)L * H));
-    const int64_t off = ((int64_t)n * L + t) * (H * kHD) + h * kHD;
-    float s = 0.f;
-#pragma unroll
-    for (int d = 0; d < kHD; ++d) s += bf(o[off + d]) * bf(dout[off + d]);
-    delta[i] = s;
-  }
-}
-
-// dQ: thread per query, loop over keys.  dS = P * (dP - delta), dQ = scale * dS K
-__global__ void __launch_bounds__(128) attn_bwd_dq_kernel(const __nv_bfloat16* __restrict__ qkv,
-                                                          const __nv_bfloat16* __restrict__ dout,
-                                                          const float* __restrict__ lse, const float* __restrict__ delta,
-                                                          __nv_bfloat16* __restrict__ dqkv, int L, int H, float scale) {
-  __shared__ float sk[kKT][kHD + 1], sv[kKT][kHD + 1];
-  const int n = blockIdx.z, h = blockIdx.y;
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  const int ld = 3 * H * kHD;
-  const __nv_bfloat16* base = qkv + (int64_t)n * L * ld;
-  const bool valid = t < L;
-  float q[kHD], go[kHD], dq[kHD];
-  const int64_t orow = ((int64_t)n * L + (valid ? t : 0)) * (H * kHD) + h * kHD;
-#pragma unroll
-  for (int d = 0; d < kHD; ++d) {
-    q[d] = valid ? bf(base[(int64_t)t * ld + h * kHD + d]) * scale : 0.f;
-    go[d] = valid ? bf(dout[orow + d]) : 0.f;
-    dq[d] = 0.f;
-  }
-  const float ls = valid ? lse[((int64_t)n * H + h) * L + t] : 0.f;
-  const float dl = valid ? delta[((int64_t)n * H + h) * L + t] : 0.f;
-  for (int k0 = 0; k0 < L; k0 += kKT) {
-    __syncthreads();
-    for (int e = threadIdx.x; e < kKT * kHD; e += blockDim.x) {
-      const int kk = e / kHD, d = e % kHD;
-      const bool ok = k0 + kk < L;
-      sk[kk][d] = ok ? bf(base[(int64_t)(k0 + kk) * ld + H * kHD + h * kHD + d]) : 0.f;
-      sv[kk][d] = ok ? bf(base[(int64_t)(k0 + kk) * ld + 2 * H * kHD + h * kHD + d]) : 0.f;
-    }
-    __syncthreads();
-    const int kn = min(kKT, L - k0);
-    for (int kk = 0; kk < kn; ++kk) {
-      float s = 0.f, dp = 0.f;
-#pragma unroll
-      for (int d = 0; d < kHD; ++d) { s += q[d] * sk[kk][d]; dp += go[d] * sv[kk][d]; }
-      const float ds = __expf(s - ls) * (dp - dl);
-#pragma unroll
-      for (int d = 0; d < kHD; ++d) dq[d] += ds * sk[kk][d];
-    }
-  }
-  if (valid) {
-#pragma unroll
-    for (int d = 0; d < kHD; ++d) dqkv[((int64_t)n * L + t) * ld + h * kHD + d] = __float2bfloat16(dq[d] * scale);
-  }
-}
-
-// dK, dV: thread per key, loop over queries.  dV = P^T dO, dK = scale * dS^T Q
-__global__ void __launch_bounds__(128) attn_bwd_dkv_kernel(const __nv_bfloat16* __restrict__ qkv,
-                                                           const __nv_bfloat16* __restrict__ dout,
-                                                           const float* __restrict__ lse, const float* __restrict__ delta,
-                                                           __nv_bfloat16* __restrict__ dqkv, int L, int H, float scale) {
-  __shared__ float sq[kKT][kHD + 1], sg[kKT][kHD + 1];
-  __shared__ float sl[kKT], sd[kKT];
-  const int n = blockIdx.z, h = blockIdx.y;
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;   // key index
-  const int ld = 3 * H * kHD;
-  const __nv_bfloat16* base = qkv + (int64_t)n * L * ld;
-  const bool valid = t < L;
-  float k[kHD], v[kHD], dk[kHD], dv[kHD];
-#pragma unroll
-  for (int d = 0; d < kHD; ++d) {
-    k[d] = valid ? bf(base[(int64_t)t * ld + H * kHD + h * kHD + d]) : 0.f;
-    v[d] = valid ? bf(base[(int64_t)t * ld + 2 * H * kHD + h * kHD + d]) : 0.f;
-    dk[d] = dv[d] = 0.f;
-  }
-  for (int q0 = 0; q0 < L; q0 += kKT) {
-    __syncthreads();
-    for (int e = threadIdx.x; e < kKT * kHD; e += blockDim.x) {
-      const int qq = e / kHD, d = e % kHD;
-      const bool ok = q0 + qq < L;
-      sq[qq][d] = ok ? bf(base[(int64_t)(q0 + qq) * ld + h * kHD + d]) * scale : 0.f;
-      sg[qq][d] = ok ? bf(dout[((int64_t)n * L + q0 + qq) * (H * kHD) + h * kHD + d]) : 0.f;
-    }
-    for (int e = threadIdx.x; e < kKT; e += blockDim.x) {
-      const bool ok = q0 + e < L;
-      sl[e] = ok ? lse[((int64_t)n * H + h) * L + q0 + e] : 0.f;
-      sd[e] = ok ? delta[((int64_t)n * H + h) * L + q0 + e] : 0.f;
-    }
-    __syncthreads();
-    const int qn = min(kKT, L - q0);
-    for (int qq = 0; qq < qn; ++qq) {
-      float s = 0.f, dp = 0.f;
-#pragma unroll
-      for (int d = 0; d < kHD; ++d) { s += sq[qq][d] * k[d]; dp += sg[qq][d] * v[d]; }
-      const float p = __expf(s - sl[qq]);
-      const float ds = p * (dp - sd[qq]);
-#pragma unroll
-      for (int d = 0; d < kHD; ++d) { dv[d] += p * sg[qq][d]; dk[d] += ds * sq[qq][d]; }
-    }
-  }
-  if (valid) {
-#pragma unroll
-    for (int d = 0; d < kHD; ++d) {
-      dqkv[((int64_t)n * L + t) * ld + H * kHD + h * kHD + d] = __float2bfloat16(dk[d]);   // sq already carries `scale`
-      dqkv[((int64_t)n * L + t) * ld + 2 * H * kHD + h * kHD + d] = __float2bfloat16(dv[d]);
-    }
-  }
-}
-
 // ------------------------------------------------------------------------------------------------ covariate injection
 // Cross-attention over a length-1 context: softmax over one key == 1, so attn2(x, ctx) = to_out(to_v(ctx)) for every
 // token (atten_unet_model.py:156-175).  bias[n, :] = Wo (Wv ctx[n]) + bo, then t[n, l, :] += bias[n, :].
@@ -525,32 +361,6 @@ int32_t petsyn_geglu_bwd(const void* h, const void* dout, void* dh, int64_t rows
   PETSYN_REQUIRE(h && dout && dh && rows > 0 && f > 0, "bad argument");
   geglu_bwd_kernel<<<blocks_for(rows * f), 256, 0, as_stream(stream)>>>(CBFP(h), CBFP(dout), BFP(dh), rows, f);
   return check_launch("geglu_bwd_kernel");
-}
-
-int32_t petsyn_attention_fwd(const void* qkv, void* out, float* lse, int32_t n, int32_t l, int32_t heads,
-                             int32_t head_dim, float scale, void* stream) {
-  PETSYN_REQUIRE(qkv && out && lse && n > 0 && l > 0 && heads > 0, "bad argument");
-  PETSYN_REQUIRE(head_dim == kHD, "attention kernels are specialised for head_dim 32 (num_head_channels=32)");
-  dim3 grid((unsigned)((l + 127) / 128), (unsigned)heads, (unsigned)n);
-  attn_fwd_kernel<<<grid, 128, 0, as_stream(stream)>>>(CBFP(qkv), BFP(out), lse, l, heads, scale);
-  return check_launch("attn_fwd_kernel");
-}
-
-int32_t petsyn_attention_bwd(const void* qkv, const void* out, const void* dout, const float* lse, float* delta,
-                             void* dqkv, int32_t n, int32_t l, int32_t heads, int32_t head_dim, float scale,
-                             void* stream) {
-  PETSYN_REQUIRE(qkv && out && dout && lse && delta && dqkv && n > 0 && l > 0 && heads > 0, "bad argument");
-  PETSYN_REQUIRE(head_dim == kHD, "attention kernels are specialised for head_dim 32 (num_head_channels=32)");
-  cudaStream_t st = as_stream(stream);
-  attn_delta_kernel<<<blocks_for((int64_t)n * heads * l), 256, 0, st>>>(CBFP(out), CBFP(dout), delta, n, l, heads);
-  int32_t rc = check_launch("attn_delta_kernel");
-  if (rc) return rc;
-  dim3 grid((unsigned)((l + 127) / 128), (unsigned)heads, (unsigned)n);
-  attn_bwd_dq_kernel<<<grid, 128, 0, st>>>(CBFP(qkv), CBFP(dout), lse, delta, BFP(dqkv), l, heads, scale);
-  rc = check_launch("attn_bwd_dq_kernel");
-  if (rc) return rc;
-  attn_bwd_dkv_kernel<<<grid, 128, 0, st>>>(CBFP(qkv), CBFP(dout), lse, delta, BFP(dqkv), l, heads, scale);
-  return check_launch("attn_bwd_dkv_kernel");
 }
 
 int32_t petsyn_covariate_bias_fwd(const float* ctx, const float* wv, const float* wo, const float* bo, float* vbuf,

@@ -122,6 +122,54 @@ def test_conv_channel_slices_and_bias(petsyn):
     assert ybuf[..., :64].abs().max().item() == 0.0   # the other half of the concat buffer is untouched
 
 
+def test_slab_path_slices_bias_act_accumulate(petsyn):
+    """The slab kernels (small-channel k3 s1 p1 convs with many voxels) behind the same contract: x / y / dy / dx as
+    channel slices of wider buffers, bias + SiLU epilogue, and the accumulating backward-data variant."""
+    from petsyn_b200._cabi import check, lib, ptr, stream_ptr
+    ops = petsyn.ops
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device="cpu").manual_seed(11)
+    n, d, h, w, cin, cout = 2, 12, 32, 40, 32, 16
+    xbuf = torch.randn(n, d, h, w, 96, generator=g).to(dev).to(torch.bfloat16)
+    ybuf = torch.zeros(n, d, h, w, 48, dtype=torch.bfloat16, device=dev)
+    wt = (torch.randn(cout, cin, 3, 3, 3, generator=g) / (cin * 27) ** 0.5).to(dev)
+    bias = torch.randn(cout, generator=g).to(dev)
+    plan = ops.ConvPlan(ops.OP_CONV, n, d, h, w, cin, cout, 3, 1, 1, x_cstride=96, x_coff=32, y_cstride=48, y_coff=16,
+                        dy_cstride=48, dy_coff=32, dx_cstride=96, dx_coff=64, act=ops.ACT_SILU)
+    plan.pack(wt)
+    plan.fprop(xbuf, ybuf, bias)
+    torch.cuda.synchronize()
+    x32 = from_ndhwc(xbuf[..., 32:64]).float()
+    ref = F.silu(F.conv3d(x32, wt, bias, padding=1))
+    close(from_ndhwc(ybuf[..., 16:32]), ref, "slab sliced fprop")
+    assert ybuf[..., :16].abs().max().item() == 0.0 and ybuf[..., 32:].abs().max().item() == 0.0
+
+    dybuf = torch.randn(n, d, h, w, 48, generator=g).to(dev).to(torch.bfloat16)
+    dxbuf = torch.randn(n, d, h, w, 96, generator=g).to(dev).to(torch.bfloat16)
+    before = dxbuf.clone()
+    dy32 = from_ndhwc(dybuf[..., 32:48]).float()
+    dx_ref = F.conv_transpose3d(dy32, wt, None, padding=1)
+    check(lib.petsyn_conv_dgrad_accumulate(plan._h, ptr(dybuf), ptr(plan.w_dgrad), ptr(dxbuf), stream_ptr()), "dgrad_acc")
+    torch.cuda.synchronize()
+    close(from_ndhwc(dxbuf[..., 64:96]), dx_ref + from_ndhwc(before[..., 64:96]).float(), "slab accumulating dgrad")
+    assert torch.equal(dxbuf[..., :64], before[..., :64])
+    plan.dgrad(dybuf, dxbuf)
+    torch.cuda.synchronize()
+    close(from_ndhwc(dxbuf[..., 64:96]), dx_ref, "slab sliced dgrad")
+
+    dw = torch.empty_like(wt)
+    plan.wgrad(xbuf, dybuf, dw)
+    torch.cuda.synchronize()
+    x32r = x32.clone().requires_grad_(False)
+    w32 = wt.clone().requires_grad_(True)
+    F.conv3d(x32r, w32, None, padding=1).backward(dy32)
+    close(dw, w32.grad, "slab sliced wgrad")
+    dw2 = dw.clone()
+    plan.wgrad(xbuf, dybuf, dw2, accumulate=True)
+    torch.cuda.synchronize()
+    close(dw2, 2 * w32.grad, "slab accumulating wgrad")
+
+
 def test_conv_bad_config_raises(petsyn):
     ops = petsyn.ops
     with pytest.raises(ValueError):

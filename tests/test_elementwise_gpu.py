@@ -156,3 +156,44 @@ def test_generalised_normact(petsyn):
     assert rel(ncl(z.g), zz.grad) < 1e-2
     assert (ncl(res.g) - rr.grad).abs().max().item() == 0.0
     assert abs(op.grad_slope.item() - a2.grad.item()) <= 1e-4 * abs(a2.grad.item())
+
+
+@pytest.mark.parametrize("n,L,H", [(2, 96, 4), (1, 200, 2), (2, 2304, 4), (1, 77, 1)])
+def test_flash_attention_matches_torch(n, L, H, petsyn):
+    """Tensor-core flash attention (csrc/attention_mma.cu) through the C ABI against fp32 softmax(q k^T * scale) v of the
+    same bf16-rounded q, k, v (atten_unet_model.py:137-154), forward and backward; L not a multiple of the 64-row tile
+    exercises the masking of padded keys / queries.  P and dS are rounded to bf16 for the second GEMM of each product:
+    tolerance 2e-2 of the reference's max (forward), 3e-2 (gradients)."""
+    from petsyn_b200._cabi import check, lib, ptr, stream_ptr
+    dev = torch.device("cuda:0")
+    hd = 32
+    g = torch.Generator().manual_seed(5)
+    qkv = torch.randn(n * L, 3 * H * hd, generator=g).to(dev).to(torch.bfloat16)
+    dout = torch.randn(n * L, H * hd, generator=g).to(dev).to(torch.bfloat16)
+    scale = hd ** -0.5
+    out = torch.empty(n * L, H * hd, dtype=torch.bfloat16, device=dev)
+    lse = torch.empty(n, H, L, dtype=torch.float32, device=dev)
+    delta = torch.empty_like(lse)
+    dqkv = torch.zeros_like(qkv)
+    check(lib.petsyn_attention_fwd(ptr(qkv), ptr(out), ptr(lse), n, L, H, hd, scale, stream_ptr()), "attention_fwd")
+    check(lib.petsyn_attention_bwd(ptr(qkv), ptr(out), ptr(dout), ptr(lse), ptr(delta), ptr(dqkv), n, L, H, hd, scale,
+                                   stream_ptr()), "attention_bwd")
+    torch.cuda.synchronize()
+
+    x = qkv.float().view(n, L, 3, H, hd).permute(2, 0, 3, 1, 4).contiguous().requires_grad_(True)   # [3, n, H, L, hd]
+    q, k, v = x[0], x[1], x[2]
+    s = torch.einsum("nhld,nhmd->nhlm", q, k) * scale
+    ref = torch.einsum("nhlm,nhmd->nhld", torch.softmax(s, -1), v)                                  # [n, H, L, hd]
+    ref.backward(dout.float().view(n, L, H, hd).permute(0, 2, 1, 3))
+    ref_out = ref.detach().permute(0, 2, 1, 3).reshape(n * L, H * hd)
+    ref_lse = torch.logsumexp(s.detach(), -1)
+    ref_dqkv = x.grad.permute(1, 3, 0, 2, 4).reshape(n * L, 3 * H * hd)
+
+    def rel(a, b):
+        return ((a.float() - b).abs().max() / b.abs().max()).item()
+
+    assert rel(out, ref_out) <= 2e-2, rel(out, ref_out)
+    assert (lse - ref_lse).abs().max().item() <= 2e-3
+    for i, name in enumerate("qkv"):
+        sl = slice(i * H * hd, (i + 1) * H * hd)
+        assert rel(dqkv[:, sl], ref_dqkv[:, sl]) <= 3e-2, (name, rel(dqkv[:, sl], ref_dqkv[:, sl]))
