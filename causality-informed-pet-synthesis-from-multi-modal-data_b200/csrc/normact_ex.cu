@@ -28,6 +28,18 @@ __device__ __forceinline__ F8 load8(const __nv_bfloat16* p) {
   }
   return r;
 }
+__device__ __forceinline__ uint4 load_raw(const __nv_bfloat16* p) { return *reinterpret_cast<const uint4*>(p); }
+__device__ __forceinline__ F8 unpack8(const uint4& raw) {
+  const __nv_bfloat162* b2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
+  F8 r;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 f = __bfloat1622float2(b2[i]);
+    r.v[2 * i] = f.x;
+    r.v[2 * i + 1] = f.y;
+  }
+  return r;
+}
 __device__ __forceinline__ void store8(__nv_bfloat16* p, const F8& r) {
   uint4 o;
   __nv_bfloat162 b0 = __floats2bfloat162_rn(r.v[0], r.v[1]), b1 = __floats2bfloat162_rn(r.v[2], r.v[3]);
@@ -54,7 +66,7 @@ __device__ __forceinline__ float act_fwd(float b, int act, float slope) {
     case PETSYN_ACT_RELU: return fmaxf(b, 0.f);
     case PETSYN_ACT_LRELU:
     case PETSYN_ACT_PRELU: return b > 0.f ? b : b * slope;
-    case PETSYN_ACT_SILU: return b / (1.f + __expf(-b));
+    case PETSYN_ACT_SILU: return __fdividef(b, 1.f + __expf(-b));
     case PETSYN_ACT_TANH: return tanhf(b);
     default: return b;
   }
@@ -64,7 +76,7 @@ __device__ __forceinline__ float act_grad(float b, int act, float slope) {
     case PETSYN_ACT_RELU: return b > 0.f ? 1.f : 0.f;
     case PETSYN_ACT_LRELU:
     case PETSYN_ACT_PRELU: return b > 0.f ? 1.f : slope;
-    case PETSYN_ACT_SILU: { const float s = 1.f / (1.f + __expf(-b)); return s * (1.f + b * (1.f - s)); }
+    case PETSYN_ACT_SILU: { const float s = __fdividef(1.f, 1.f + __expf(-b)); return s * (1.f + b * (1.f - s)); }
     case PETSYN_ACT_TANH: { const float t = tanhf(b); return 1.f - t * t; }
     default: return 1.f;
   }
@@ -179,7 +191,10 @@ struct Dev {   // device copy of petsyn_normact_desc with typed pointers
   int dz_acc;
 };
 
-__global__ void __launch_bounds__(256) fwd_kernel(const Dev d) {
+// ACT < 0: activation codes read from the descriptor at run time (rare combinations); ACT >= 0: act1 == act2 == ACT
+// known at compile time (the common case), so the inner loop carries no switch.
+template <int ACT>
+__global__ void __launch_bounds__(256, 3) fwd_kernel(const Dev d) {
   RowIter it(d.C);
   if (!it.active) return;
   const int s = blockIdx.y;
@@ -188,56 +203,91 @@ __global__ void __launch_bounds__(256) fwd_kernel(const Dev d) {
   F8 sc = splat(1.f), sh = splat(0.f);
   if (d.scale) { sc = load8f(d.scale + so + it.tx * 8); sh = load8f(d.shift + so + it.tx * 8); }
   const float slope = d.slope_dev ? __ldg(d.slope_dev) : d.slope;
+  const int a1 = ACT >= 0 ? ACT : d.act1, a2 = ACT >= 0 ? ACT : d.act2;
   const int64_t stride = (int64_t)gridDim.x * it.rpp;
-  for (int64_t r0 = (int64_t)blockIdx.x * it.rpp + it.ty; r0 < d.rows; r0 += stride) {
-    const int64_t r = base + r0;
-    const F8 x = load8(d.z + r * d.C + it.tx * 8);
-    F8 rs = splat(0.f);
-    if (d.res) rs = load8(d.res + r * d.csr + d.cor + it.tx * 8);
-    F8 o1, o2;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const float b = x.v[i] * sc.v[i] + sh.v[i];
-      o1.v[i] = act_fwd(b, d.act1, slope) + rs.v[i];
-      o2.v[i] = act_fwd(b, d.act2, slope) + rs.v[i];
+  for (int64_t r0 = (int64_t)blockIdx.x * it.rpp + it.ty; r0 < d.rows; r0 += 2 * stride) {
+    const int64_t ra = base + r0, rb = ra + stride;
+    const bool two = r0 + stride < d.rows;
+    const F8 xa = load8(d.z + ra * d.C + it.tx * 8);
+    F8 xb = splat(0.f), rsa = splat(0.f), rsb = splat(0.f);
+    if (two) xb = load8(d.z + rb * d.C + it.tx * 8);
+    if (d.res) {
+      rsa = load8(d.res + ra * d.csr + d.cor + it.tx * 8);
+      if (two) rsb = load8(d.res + rb * d.csr + d.cor + it.tx * 8);
     }
-    store8(d.t1 + r * d.cs1 + d.co1 + it.tx * 8, o1);
-    if (d.t2) store8(d.t2 + r * d.cs2 + d.co2 + it.tx * 8, o2);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      if (h == 1 && !two) break;
+      const F8& x = h ? xb : xa;
+      const F8& rs = h ? rsb : rsa;
+      const int64_t r = h ? rb : ra;
+      F8 o1, o2;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float b = x.v[i] * sc.v[i] + sh.v[i];
+        o1.v[i] = act_fwd(b, a1, slope) + rs.v[i];
+        o2.v[i] = (ACT >= 0) ? o1.v[i] : act_fwd(b, a2, slope) + rs.v[i];
+      }
+      store8(d.t1 + r * d.cs1 + d.co1 + it.tx * 8, o1);
+      if (d.t2) store8(d.t2 + r * d.cs2 + d.co2 + it.tx * 8, o2);
+    }
   }
 }
 
-__global__ void __launch_bounds__(256) bwd_reduce_kernel(const Dev d) {
+template <int ACT>
+__global__ void __launch_bounds__(256, 2) bwd_reduce_kernel(const Dev d) {
   extern __shared__ float smem_f[];
   RowIter it(d.C);
   const int s = blockIdx.y;
   const int64_t base = (int64_t)s * d.rows;
   const int so = d.per_sample ? s * d.C : 0;
-  float acc[2][8];
+  float acc[2][8];   // sum g, sum g * x  (turned into sum g * zhat after the loop)
   float dsl = 0.f;
   const float slope = d.slope_dev ? __ldg(d.slope_dev) : d.slope;
+  const int a1 = ACT >= 0 ? ACT : d.act1, a2 = ACT >= 0 ? ACT : d.act2;
 #pragma unroll
   for (int i = 0; i < 8; ++i) acc[0][i] = acc[1][i] = 0.f;
   if (it.active) {
     F8 sc = splat(1.f), sh = splat(0.f);
     if (d.scale) { sc = load8f(d.scale + so + it.tx * 8); sh = load8f(d.shift + so + it.tx * 8); }
-    const F8 mu = load8f(d.mean + so + it.tx * 8), rs = load8f(d.rstd + so + it.tx * 8);
     const int64_t stride = (int64_t)gridDim.x * it.rpp;
-    for (int64_t r0 = (int64_t)blockIdx.x * it.rpp + it.ty; r0 < d.rows; r0 += stride) {
-      const int64_t r = base + r0;
-      const F8 x = load8(d.z + r * d.C + it.tx * 8);
-      const F8 a = load8(d.t1 + r * d.cs1 + d.co1 + it.tx * 8);
-      F8 b2 = splat(0.f);
-      if (d.t2) b2 = load8(d.t2 + r * d.cs2 + d.co2 + it.tx * 8);
+    const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+    for (int64_t r0 = (int64_t)blockIdx.x * it.rpp + it.ty; r0 < d.rows; r0 += 2 * stride) {
+      const int64_t ra = base + r0, rb = ra + stride;
+      const bool two = r0 + stride < d.rows;
+      uint4 xr[2], ar[2], br[2];
+      xr[0] = load_raw(d.z + ra * d.C + it.tx * 8);
+      ar[0] = load_raw(d.t1 + ra * d.cs1 + d.co1 + it.tx * 8);
+      br[0] = br[1] = xr[1] = ar[1] = zero;
+      if (d.t2) br[0] = load_raw(d.t2 + ra * d.cs2 + d.co2 + it.tx * 8);
+      if (two) {
+        xr[1] = load_raw(d.z + rb * d.C + it.tx * 8);
+        ar[1] = load_raw(d.t1 + rb * d.cs1 + d.co1 + it.tx * 8);
+        if (d.t2) br[1] = load_raw(d.t2 + rb * d.cs2 + d.co2 + it.tx * 8);
+      }
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float b = x.v[i] * sc.v[i] + sh.v[i];
-        float g = a.v[i] * act_grad(b, d.act1, slope);
-        if (d.t2) g += b2.v[i] * act_grad(b, d.act2, slope);
-        acc[0][i] += g;
-        acc[1][i] += g * (x.v[i] - mu.v[i]) * rs.v[i];
-        if (d.dslope != nullptr && b < 0.f) dsl += (a.v[i] + (d.t2 ? b2.v[i] : 0.f)) * b;   // d PReLU / d slope = min(b, 0)
+      for (int h = 0; h < 2; ++h) {
+        if (h == 1 && !two) break;
+        const F8 x = unpack8(xr[h]), av = unpack8(ar[h]), bv = unpack8(br[h]);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float b = x.v[i] * sc.v[i] + sh.v[i];
+          float g;
+          if (ACT >= 0) {
+            g = (av.v[i] + bv.v[i]) * act_grad(b, a1, slope);
+          } else {
+            g = av.v[i] * act_grad(b, a1, slope);
+            if (d.t2) g += bv.v[i] * act_grad(b, a2, slope);
+          }
+          acc[0][i] += g;
+          acc[1][i] += g * x.v[i];
+          if (d.dslope != nullptr && b < 0.f) dsl += (av.v[i] + bv.v[i]) * b;   // d PReLU / d slope = min(b, 0)
+        }
       }
     }
+    const F8 mu = load8f(d.mean + so + it.tx * 8), rs = load8f(d.rstd + so + it.tx * 8);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[1][i] = (acc[1][i] - mu.v[i] * acc[0][i]) * rs.v[i];   // sum g * (x - mu) * rstd
   }
   if (d.dslope != nullptr) {
     for (int o = 16; o > 0; o >>= 1) dsl += __shfl_xor_sync(0xffffffffu, dsl, o);
@@ -246,7 +296,8 @@ __global__ void __launch_bounds__(256) bwd_reduce_kernel(const Dev d) {
   block_reduce_channels<2>(it, acc, smem_f, d.sums + (d.per_sample ? (int64_t)s * 2 * d.C : 0), d.C);
 }
 
-__global__ void __launch_bounds__(256) bwd_apply_kernel(const Dev d) {
+template <int ACT>
+__global__ void __launch_bounds__(256, 2) bwd_apply_kernel(const Dev d) {
   RowIter it(d.C);
   if (blockIdx.x == 0 && blockIdx.y == 0 && d.dgamma != nullptr && d.ka == nullptr) {
     for (int c = threadIdx.x; c < d.C; c += blockDim.x) {
@@ -258,58 +309,86 @@ __global__ void __launch_bounds__(256) bwd_apply_kernel(const Dev d) {
   const int s = blockIdx.y;
   const int64_t base = (int64_t)s * d.rows;
   const int so = d.per_sample ? s * d.C : 0;
-  F8 sc = splat(1.f), sh = splat(0.f), mu = splat(0.f), rs = splat(1.f), k0 = splat(1.f), k1 = splat(0.f), k2 = splat(0.f);
+  // dz = k0*g - k1 - zhat*k2 with zhat = (x - mu)*rstd   ==   k0*g - kA - x*kB,  kA = k1 - mu*rstd*k2, kB = rstd*k2
+  F8 sc = splat(1.f), sh = splat(0.f), k0 = splat(1.f), kA = splat(0.f), kB = splat(0.f);
   if (d.scale) { sc = load8f(d.scale + so + it.tx * 8); sh = load8f(d.shift + so + it.tx * 8); }
   if (d.mean) {
-    mu = load8f(d.mean + so + it.tx * 8);
-    rs = load8f(d.rstd + so + it.tx * 8);
+    const F8 mu = load8f(d.mean + so + it.tx * 8), rs = load8f(d.rstd + so + it.tx * 8);
     const F8 ga = d.gamma ? load8f(d.gamma + it.tx * 8) : splat(1.f);
-    const float* sm = d.sums + (d.per_sample ? (int64_t)s * 2 * d.C : 0);
-    const F8 s0 = load8f(sm + it.tx * 8), s1 = load8f(sm + d.C + it.tx * 8);
-    const float inv = 1.f / (float)d.rows;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      k0.v[i] = ga.v[i] * rs.v[i];
-      k1.v[i] = k0.v[i] * s0.v[i] * inv;      // dz = k0*g - k1 - zhat*k2
-      k2.v[i] = k0.v[i] * s1.v[i] * inv;
-    }
+    F8 k1, k2;
     if (d.ka != nullptr) {                     // group statistics and/or per-sample affine: constants precomputed
       k1 = load8f(d.ka + so + it.tx * 8);
       k2 = load8f(d.kb + so + it.tx * 8);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) k0.v[i] = ga.v[i] * rs.v[i];
+    } else {
+      const float* sm = d.sums + (d.per_sample ? (int64_t)s * 2 * d.C : 0);
+      const F8 s0 = load8f(sm + it.tx * 8), s1 = load8f(sm + d.C + it.tx * 8);
+      const float inv = 1.f / (float)d.rows;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        k0.v[i] = ga.v[i] * rs.v[i];
+        k1.v[i] = k0.v[i] * s0.v[i] * inv;
+        k2.v[i] = k0.v[i] * s1.v[i] * inv;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      kB.v[i] = rs.v[i] * k2.v[i];
+      kA.v[i] = k1.v[i] - mu.v[i] * kB.v[i];
     }
   }
   const float slope = d.slope_dev ? __ldg(d.slope_dev) : d.slope;
+  const int a1 = ACT >= 0 ? ACT : d.act1, a2 = ACT >= 0 ? ACT : d.act2;
   const int64_t stride = (int64_t)gridDim.x * it.rpp;
-  for (int64_t r0 = (int64_t)blockIdx.x * it.rpp + it.ty; r0 < d.rows; r0 += stride) {
-    const int64_t r = base + r0;
-    const F8 x = load8(d.z + r * d.C + it.tx * 8);
-    const F8 a = load8(d.t1 + r * d.cs1 + d.co1 + it.tx * 8);
-    F8 b2 = splat(0.f);
-    if (d.t2) b2 = load8(d.t2 + r * d.cs2 + d.co2 + it.tx * 8);
-    F8 o, dr;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const float b = x.v[i] * sc.v[i] + sh.v[i];
-      float g = a.v[i] * act_grad(b, d.act1, slope);
-      if (d.t2) g += b2.v[i] * act_grad(b, d.act2, slope);
-      const float zh = (x.v[i] - mu.v[i]) * rs.v[i];
-      o.v[i] = k0.v[i] * g - k1.v[i] - zh * k2.v[i];
-      dr.v[i] = a.v[i] + b2.v[i];
+  const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+  for (int64_t r0 = (int64_t)blockIdx.x * it.rpp + it.ty; r0 < d.rows; r0 += 2 * stride) {
+    const int64_t ra = base + r0, rb = ra + stride;
+    const bool two = r0 + stride < d.rows;
+    uint4 xr[2], ar[2], br[2];
+    xr[0] = load_raw(d.z + ra * d.C + it.tx * 8);
+    ar[0] = load_raw(d.t1 + ra * d.cs1 + d.co1 + it.tx * 8);
+    br[0] = br[1] = xr[1] = ar[1] = zero;
+    if (d.t2) br[0] = load_raw(d.t2 + ra * d.cs2 + d.co2 + it.tx * 8);
+    if (two) {
+      xr[1] = load_raw(d.z + rb * d.C + it.tx * 8);
+      ar[1] = load_raw(d.t1 + rb * d.cs1 + d.co1 + it.tx * 8);
+      if (d.t2) br[1] = load_raw(d.t2 + rb * d.cs2 + d.co2 + it.tx * 8);
     }
-    if (d.dz_acc) {
-      const F8 old = load8(d.dz + r * d.C + it.tx * 8);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) o.v[i] += old.v[i];
-    }
-    store8(d.dz + r * d.C + it.tx * 8, o);
-    if (d.res) {
-      __nv_bfloat16* p = d.res + r * d.csr + d.cor + it.tx * 8;
-      if (d.res_acc) {
-        const F8 old = load8(p);
+    for (int h = 0; h < 2; ++h) {
+      if (h == 1 && !two) break;
+      const int64_t r = h ? rb : ra;
+      const F8 x = unpack8(xr[h]), av = unpack8(ar[h]), bv = unpack8(br[h]);
+      F8 o, dr;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) dr.v[i] += old.v[i];
+      for (int i = 0; i < 8; ++i) {
+        const float b = x.v[i] * sc.v[i] + sh.v[i];
+        float g;
+        if (ACT >= 0) {
+          g = (av.v[i] + bv.v[i]) * act_grad(b, a1, slope);
+        } else {
+          g = av.v[i] * act_grad(b, a1, slope);
+          if (d.t2) g += bv.v[i] * act_grad(b, a2, slope);
+        }
+        o.v[i] = k0.v[i] * g - kA.v[i] - x.v[i] * kB.v[i];
+        dr.v[i] = av.v[i] + bv.v[i];
       }
-      store8(p, dr);
+      if (d.dz_acc) {
+        const F8 old = load8(d.dz + r * d.C + it.tx * 8);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o.v[i] += old.v[i];
+      }
+      store8(d.dz + r * d.C + it.tx * 8, o);
+      if (d.res) {
+        __nv_bfloat16* p = d.res + r * d.csr + d.cor + it.tx * 8;
+        if (d.res_acc) {
+          const F8 old = load8(p);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) dr.v[i] += old.v[i];
+        }
+        store8(p, dr);
+      }
     }
   }
 }
@@ -419,6 +498,19 @@ static int32_t to_dev(const petsyn_normact_desc* d, Dev* o) {
 using namespace petsyn;
 using namespace petsyn::nx;
 
+// compile-time activation when both destinations share it (always true for the module mirrors), run-time otherwise
+#define PETSYN_NX_DISPATCH(KERNEL, GRID, SMEM, ST, D)                                         \
+  do {                                                                                        \
+    const int _a = ((D).t2 == nullptr || (D).act1 == (D).act2) ? (D).act1 : -1;               \
+    switch (_a) {                                                                             \
+      case PETSYN_ACT_NONE: KERNEL<PETSYN_ACT_NONE><<<GRID, 256, SMEM, ST>>>(D); break;       \
+      case PETSYN_ACT_RELU: KERNEL<PETSYN_ACT_RELU><<<GRID, 256, SMEM, ST>>>(D); break;       \
+      case PETSYN_ACT_LRELU: KERNEL<PETSYN_ACT_LRELU><<<GRID, 256, SMEM, ST>>>(D); break;     \
+      case PETSYN_ACT_SILU: KERNEL<PETSYN_ACT_SILU><<<GRID, 256, SMEM, ST>>>(D); break;       \
+      default: KERNEL<-1><<<GRID, 256, SMEM, ST>>>(D); break;                                 \
+    }                                                                                         \
+  } while (0)
+
 extern "C" {
 
 int32_t petsyn_norm_stats(const void* z, float* sums, int64_t rows, int32_t c, int32_t nsamples, void* stream) {
@@ -450,7 +542,7 @@ int32_t petsyn_normact_fwd(const petsyn_normact_desc* desc, void* stream) {
   if (rc) return rc;
   PETSYN_REQUIRE(d.t1 != nullptr, "missing destination");
   dim3 grid((unsigned)row_blocks(d.rows, d.C, desc->nsamples), (unsigned)desc->nsamples);
-  fwd_kernel<<<grid, 256, 0, as_stream(stream)>>>(d);
+  PETSYN_NX_DISPATCH(fwd_kernel, grid, 0, as_stream(stream), d);
   return check_launch("normact fwd_kernel");
 }
 
@@ -467,7 +559,7 @@ int32_t petsyn_normact_bwd(const petsyn_normact_desc* desc, void* stream) {
     PETSYN_CHECK_CUDA(cudaMemsetAsync(d.sums, 0, (size_t)nst * 2 * d.C * sizeof(float), st));
     const int rpp = 256 / (d.C / 8);
     const size_t smem = (size_t)rpp * 2 * d.C * sizeof(float);
-    bwd_reduce_kernel<<<grid, 256, smem, st>>>(d);
+    PETSYN_NX_DISPATCH(bwd_reduce_kernel, grid, smem, st, d);
     rc = check_launch("normact bwd_reduce_kernel");
     if (rc) return rc;
     const int gs = desc->group_size > 1 ? desc->group_size : 1;
@@ -484,7 +576,7 @@ int32_t petsyn_normact_bwd(const petsyn_normact_desc* desc, void* stream) {
       d.kb = kb;
     }
   }
-  bwd_apply_kernel<<<grid, 256, 0, st>>>(d);
+  PETSYN_NX_DISPATCH(bwd_apply_kernel, grid, 0, st, d);
   return check_launch("normact bwd_apply_kernel");
 }
 
