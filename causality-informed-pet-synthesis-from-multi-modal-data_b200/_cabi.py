@@ -79,6 +79,10 @@ SIGNATURES = {
     "petsyn_conv_workspace_bytes": (_sz, [_vp]),
     "petsyn_conv_set_workspace": (_i32, [_vp, _vp, _sz]),
     "petsyn_conv_pack_weights": (_i32, [_vp, _vp, _vp, _vp, _vp]),
+    "petsyn_pack_batch_create": (_i32, [_i32, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp),
+                                        C.POINTER(_vp)]),
+    "petsyn_pack_batch_run": (_i32, [_vp, _vp]),
+    "petsyn_pack_batch_destroy": (None, [_vp]),
     "petsyn_conv_fprop": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp]),
     "petsyn_conv_dgrad": (_i32, [_vp, _vp, _vp, _vp, _vp]),
     "petsyn_conv_dgrad_accumulate": (_i32, [_vp, _vp, _vp, _vp, _vp]),

@@ -154,14 +154,14 @@ struct PackImage {
 // NS = merged source taps per slot (1: plain convs, 8: Upsample+Conv); short slots are padded with a pointer to a
 // zero element so that the inner sum is a fixed, fully unrolled chain of independent shared-memory loads.
 template <int K3, bool TRANSPOSED, int NS>
-__global__ void __launch_bounds__(256) pack_weights_kernel(const float* __restrict__ w, int A, int B, PackImage im) {
+__device__ __forceinline__ void pack_tile(const float* __restrict__ w, int A, int B, const PackImage& im, int bx, int by) {
   constexpr int TA = TRANSPOSED ? 64 : 4, TB = TRANSPOSED ? 4 : 64;
   constexpr int K3P = (K3 & 1) ? K3 + 2 : K3 + 1;    // odd pitch along b with at least one spare (zero) element
   constexpr int ROWP = (TB * K3P) | 1;               // odd pitch along a
   extern __shared__ float tile[];                    // [TA][ROWP]
   __shared__ int16_t s_src[kMaxTaps][NS];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int a0 = blockIdx.x * TA, b0 = blockIdx.y * TB;
+  const int a0 = bx * TA, b0 = by * TB;
   const int nslots = im.nsubs * im.max_taps;
   for (int i = tid; i < nslots * NS; i += 256) {
     const TapSrcDev& e = im.tbl[i / NS];
@@ -197,6 +197,33 @@ __global__ void __launch_bounds__(256) pack_weights_kernel(const float* __restri
       dst[(int64_t)t * im.kc_pad] = __float2bfloat16(acc);
     }
   }
+}
+
+template <int K3, bool TRANSPOSED, int NS>
+__global__ void __launch_bounds__(256) pack_weights_kernel(const float* __restrict__ w, int A, int B, PackImage im) {
+  pack_tile<K3, TRANSPOSED, NS>(w, A, B, im, blockIdx.x, blockIdx.y);
+}
+
+// Batched form: one launch packs every weight tensor of a network that shares (K3, TRANSPOSED, NS); a block finds its
+// job by binary search over the jobs' first-tile indices.
+struct PackJob {
+  const float* w;
+  int32_t A, B;
+  PackImage im;
+  int32_t tile_begin, tiles_x;
+};
+
+template <int K3, bool TRANSPOSED, int NS>
+__global__ void __launch_bounds__(256) pack_weights_multi_kernel(const PackJob* __restrict__ jobs, int njobs) {
+  int lo = 0, hi = njobs - 1;
+  const int b = blockIdx.x;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (jobs[mid].tile_begin <= b) lo = mid; else hi = mid - 1;
+  }
+  const PackJob& j = jobs[lo];
+  const int local = b - j.tile_begin;
+  pack_tile<K3, TRANSPOSED, NS>(j.w, j.A, j.B, j.im, local % j.tiles_x, local / j.tiles_x);
 }
 
 // scratch [nsubs*rows, max_taps*kc_pad] fp32 -> dw in PyTorch layout (sums the slots every original tap was merged into)
@@ -339,6 +366,12 @@ struct ViewSpec {           // an NDHWC tensor (channel slice) and how to derive
 };
 
 }  // namespace petsyn
+
+struct petsyn_pack_batch {
+  petsyn::PackJob* d_jobs[16] = {nullptr};
+  int njobs[16] = {0};
+  int tiles[16] = {0};
+};
 
 struct petsyn_conv_plan {
   petsyn_conv_desc desc;
@@ -743,6 +776,49 @@ static int32_t launch_pack(int k3, bool transposed, int ns, const float* w, int 
   return fail(PETSYN_EINVAL, "unsupported kernel volume %d / merge factor %d", k3, ns);
 }
 
+// ---- batched packing: jobs grouped by kernel instantiation
+struct PackClass { int k3; bool transposed; int ns; };
+static const PackClass kPackClasses[] = {{1, false, 1}, {1, true, 1}, {8, false, 1}, {8, true, 1}, {27, false, 1},
+                                          {27, true, 1}, {27, false, 8}, {27, true, 8}, {64, false, 1}, {64, true, 1}};
+constexpr int kNumPackClasses = sizeof(kPackClasses) / sizeof(kPackClasses[0]);
+
+static int pack_class_of(int k3, bool transposed, int ns) {
+  for (int i = 0; i < kNumPackClasses; ++i)
+    if (kPackClasses[i].k3 == k3 && kPackClasses[i].transposed == transposed && ns <= kPackClasses[i].ns) return i;
+  return -1;
+}
+
+template <int K3, bool T, int NS>
+static int32_t launch_pack_multi_t(const PackJob* jobs, int njobs, int tiles, cudaStream_t st) {
+  constexpr int TA = T ? 64 : 4, TB = T ? 4 : 64;
+  constexpr int K3P = (K3 & 1) ? K3 + 2 : K3 + 1;
+  constexpr size_t smem = (size_t)TA * ((TB * K3P) | 1) * sizeof(float);
+  static bool attr = false;
+  if (!attr) {
+    PETSYN_CHECK_CUDA(cudaFuncSetAttribute(pack_weights_multi_kernel<K3, T, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)smem));
+    attr = true;
+  }
+  pack_weights_multi_kernel<K3, T, NS><<<tiles, 256, smem, st>>>(jobs, njobs);
+  return check_launch("pack_weights_multi_kernel");
+}
+
+static int32_t launch_pack_multi(int cls, const PackJob* jobs, int njobs, int tiles, cudaStream_t st) {
+  switch (cls) {
+    case 0: return launch_pack_multi_t<1, false, 1>(jobs, njobs, tiles, st);
+    case 1: return launch_pack_multi_t<1, true, 1>(jobs, njobs, tiles, st);
+    case 2: return launch_pack_multi_t<8, false, 1>(jobs, njobs, tiles, st);
+    case 3: return launch_pack_multi_t<8, true, 1>(jobs, njobs, tiles, st);
+    case 4: return launch_pack_multi_t<27, false, 1>(jobs, njobs, tiles, st);
+    case 5: return launch_pack_multi_t<27, true, 1>(jobs, njobs, tiles, st);
+    case 6: return launch_pack_multi_t<27, false, 8>(jobs, njobs, tiles, st);
+    case 7: return launch_pack_multi_t<27, true, 8>(jobs, njobs, tiles, st);
+    case 8: return launch_pack_multi_t<64, false, 1>(jobs, njobs, tiles, st);
+    case 9: return launch_pack_multi_t<64, true, 1>(jobs, njobs, tiles, st);
+    default: return fail(PETSYN_EINVAL, "bad pack class %d", cls);
+  }
+}
+
 template <int K3, bool T, int NS>
 static int32_t launch_unpack_t(const float* scratch, float* dw, const InvEntryDev* inv, int A, int B, const GemmSide& f,
                                int accumulate, cudaStream_t st) {
@@ -984,6 +1060,65 @@ int32_t petsyn_conv_pack_weights(petsyn_conv_plan* pl, const float* w, void* pac
   if (!rc && packed_dgrad)
     rc = launch_pack(pl->k3, /*transposed=*/!convt, max_nsrc(pl->dgrad), w, A, B, make_image(pl->dgrad, packed_dgrad), st);
   return rc;
+}
+
+int32_t petsyn_pack_batch_create(int32_t n, petsyn_conv_plan* const* plans, const float* const* weights,
+                                 void* const* packed_fprop, void* const* packed_dgrad, petsyn_pack_batch** out) {
+  PETSYN_REQUIRE(n > 0 && plans && weights && packed_fprop && packed_dgrad && out, "bad argument");
+  std::vector<PackJob> jobs[kNumPackClasses];
+  int tiles[kNumPackClasses] = {0};
+  auto add = [&](const petsyn_conv_plan* pl, const GemmSide& g, bool transposed, const float* w, void* dst) -> int32_t {
+    const bool convt = pl->desc.op == PETSYN_OP_CONVT;
+    const int A = convt ? pl->desc.cin : pl->desc.cout, B = convt ? pl->desc.cout : pl->desc.cin;
+    const int cls = pack_class_of(pl->k3, transposed, max_nsrc(g));
+    if (cls < 0) return fail(PETSYN_EINVAL, "unsupported kernel volume %d / merge factor %d", pl->k3, max_nsrc(g));
+    const int TA = transposed ? 64 : 4, TB = transposed ? 4 : 64;
+    PackJob j;
+    j.w = w; j.A = A; j.B = B;
+    j.im = make_image(g, dst);
+    const int amax = transposed ? std::max(A, j.im.kc_pad) : A, bmax = transposed ? B : std::max(B, j.im.kc_pad);
+    j.tiles_x = (amax + TA - 1) / TA;
+    const int ty = (bmax + TB - 1) / TB;
+    j.tile_begin = tiles[cls];
+    tiles[cls] += j.tiles_x * ty;
+    jobs[cls].push_back(j);
+    return PETSYN_OK;
+  };
+  for (int i = 0; i < n; ++i) {
+    const petsyn_conv_plan* pl = plans[i];
+    PETSYN_REQUIRE(pl && weights[i], "null plan / weight in batch entry %d", i);
+    const bool convt = pl->desc.op == PETSYN_OP_CONVT;
+    int32_t rc = PETSYN_OK;
+    if (packed_fprop[i]) rc = add(pl, pl->fprop, convt, weights[i], packed_fprop[i]);
+    if (!rc && packed_dgrad[i]) rc = add(pl, pl->dgrad, !convt, weights[i], packed_dgrad[i]);
+    if (rc) return rc;
+  }
+  auto* b = new petsyn_pack_batch();
+  for (int c = 0; c < kNumPackClasses; ++c) {
+    if (jobs[c].empty()) continue;
+    b->njobs[c] = (int)jobs[c].size();
+    b->tiles[c] = tiles[c];
+    int32_t rc = upload(jobs[c].data(), jobs[c].size() * sizeof(PackJob), (void**)&b->d_jobs[c]);
+    if (rc) { petsyn_pack_batch_destroy(b); return rc; }
+  }
+  *out = b;
+  return PETSYN_OK;
+}
+
+int32_t petsyn_pack_batch_run(petsyn_pack_batch* b, void* stream) {
+  PETSYN_REQUIRE(b != nullptr, "null batch");
+  for (int c = 0; c < kNumPackClasses; ++c) {
+    if (b->njobs[c] == 0) continue;
+    int32_t rc = launch_pack_multi(c, b->d_jobs[c], b->njobs[c], b->tiles[c], as_stream(stream));
+    if (rc) return rc;
+  }
+  return PETSYN_OK;
+}
+
+void petsyn_pack_batch_destroy(petsyn_pack_batch* b) {
+  if (!b) return;
+  for (int c = 0; c < 16; ++c) cudaFree(b->d_jobs[c]);
+  delete b;
 }
 
 int32_t petsyn_conv_fprop(petsyn_conv_plan* pl, const void* x, const void* packed, const float* bias, void* y,

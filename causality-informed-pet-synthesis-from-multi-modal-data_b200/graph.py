@@ -130,6 +130,32 @@ class ConvOp(Op):
         self.flops = self.plan.flops_algorithmic
 
     # -------------------------------------------------------------------------------------------------
+    # batched packing (Tape.repack): staleness check, operand allocation, staging of zero-padded weights
+    def stale(self) -> bool:
+        w = self.weight
+        return (w._version, w.data_ptr(), self.need_dx) != self._ver
+
+    def pack_source(self) -> torch.Tensor:
+        return self.w_stage if self.padded else self.weight.detach()
+
+    def alloc_packed(self) -> None:
+        p, dev = self.plan, self.weight.device
+        if p.w_fprop is None:
+            p.w_fprop = torch.empty(p.packed_fprop_bytes, dtype=torch.uint8, device=dev)
+        if self.need_dx and p.w_dgrad is None:
+            p.w_dgrad = torch.empty(p.packed_dgrad_bytes, dtype=torch.uint8, device=dev)
+
+    def stage_padded(self) -> None:
+        w = self.weight
+        if self.padded:
+            if self.opcode == ops.OP_CONVT:
+                self.w_stage[:self.cin_w, :self.cout_w].copy_(w.detach())
+            else:
+                self.w_stage[:self.cout_w, :self.cin_w].copy_(w.detach())
+        if self.bias_stage is not None:
+            self.bias_stage[:self.cout_w].copy_(self.bias.detach())
+        self._ver = (w._version, w.data_ptr(), self.need_dx)
+
     def repack(self, force: bool = False) -> None:
         w = self.weight
         ver = (w._version, w.data_ptr(), self.need_dx)
@@ -471,8 +497,33 @@ class Tape:
         self._final = True
 
     def repack(self) -> None:
+        """Refresh the packed bf16 weight images of every conv whose parameter changed.  All of them go through ONE
+        batched pack (``petsyn_pack_batch_*``: a launch per kernel-volume class, not per tensor); the batch is rebuilt
+        when a weight tensor moves (``.to()``, flat-arena adoption)."""
+        convs = [op for op in self.ops if isinstance(op, ConvOp)]
         for op in self.ops:
-            op.repack()
+            if not isinstance(op, ConvOp):
+                op.repack()
+        stale = [op for op in convs if op.stale()]
+        if not stale:
+            return
+        key = tuple((op.weight.data_ptr(), op.need_dx) for op in convs)
+        if getattr(self, "_pack_key", None) != key:
+            if getattr(self, "_pack_batch", None):
+                lib.petsyn_pack_batch_destroy(self._pack_batch)
+            n = len(convs)
+            arr = lambda vals: (C.c_void_p * n)(*vals)
+            for op in convs:
+                op.alloc_packed()
+            handle = C.c_void_p()
+            check(lib.petsyn_pack_batch_create(
+                n, arr([op.plan._h.value for op in convs]), arr([ptr(op.pack_source()) for op in convs]),
+                arr([ptr(op.plan.w_fprop) for op in convs]),
+                arr([ptr(op.plan.w_dgrad) if op.need_dx else None for op in convs]), C.byref(handle)), "pack_batch_create")
+            self._pack_batch, self._pack_key = handle, key
+        for op in convs:
+            op.stage_padded()
+        check(lib.petsyn_pack_batch_run(self._pack_batch, stream_ptr()), "pack_batch_run")
 
     def forward(self, training: bool) -> None:
         assert self._final

@@ -107,6 +107,16 @@ int32_t petsyn_conv_set_workspace(petsyn_conv_plan* plan, void* workspace, size_
 int32_t petsyn_conv_pack_weights(petsyn_conv_plan* plan, const float* w, void* packed_fprop, void* packed_dgrad,
                                  void* stream);
 
+/* Batched weight packing: every weight tensor of a network in a handful of launches (one per kernel-volume / layout
+ * class) instead of one launch per tensor.  Entry i packs weights[i] for plans[i] into packed_fprop[i] and, when not
+ * NULL, packed_dgrad[i].  All pointers are captured at creation and must stay valid (flat parameter arenas).
+ * No reference counterpart: the reference re-reads nn.Parameter storage through cuDNN every step. */
+typedef struct petsyn_pack_batch petsyn_pack_batch;
+int32_t petsyn_pack_batch_create(int32_t n, petsyn_conv_plan* const* plans, const float* const* weights,
+                                 void* const* packed_fprop, void* const* packed_dgrad, petsyn_pack_batch** out);
+int32_t petsyn_pack_batch_run(petsyn_pack_batch* batch, void* stream);
+void petsyn_pack_batch_destroy(petsyn_pack_batch* batch);
+
 /* y = act(conv(x, W) + bias).  Replaces F.conv3d / F.conv_transpose3d (+ the preceding F.interpolate for UPCONV).
  * bias may be NULL (BatchNorm'd convs are bias-free, unet_model.py:42-45). */
 int32_t petsyn_conv_fprop(petsyn_conv_plan* plan, const void* x, const void* packed_fprop, const float* bias, void* y,
