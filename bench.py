@@ -5,15 +5,17 @@
 
 One process per GPU (torchrun sets RANK/LOCAL_RANK/WORLD_SIZE for N > 1).  Rank 0 prints ONE JSON line.
 
-Workload at N = 1 (``config.workload``): ``unet3d_train_cfg1`` = BASELINE.json configs[0]'s model and volume
-(UnetGenerator3d(1,1,num_downs=4), 96x112x96, per-GPU batch 1) run as a full training step
-(zero_grad -> fwd -> L1 -> bwd -> [bucketed all-reduce] -> Adam).  configs[1] (the covariate-conditioned AttenUNet)
-is not built yet in this round, so the metric is quoted on the generator that is.
+Default workload (``config.workload``): ``atten_unet_train_cfg2`` = BASELINE.json configs[1], the covariate-conditioned
+generator (AttenUNet(**unet/config/training.json atten_unet_def, cross_attention_dim=5)) at the reference's crop
+96x128x96 and per-GPU batch 2 (train_unet.py:111,319), run as a full training step
+(zero_grad -> fwd -> L1 -> bwd -> [bucketed all-reduce] -> Adam).  Other workloads (``--workload``): configs[0]
+(``unet3d_train_cfg1``: UnetGenerator3d at 96x112x96, batch 1) and configs[2] (``bmgan_adv_step_s2``).
 
   value        volumes/s with inputs resident in HBM, timed with CUDA events, max over ranks
-  e2e          same step driven from pinned HOST buffers (H2D of t1+pet every step) with the loss read back (D2H)
-  roofline     dominant kernel (tcgen05 implicit-GEMM conv, layer up1 fprop): algorithmic FLOPs / CUDA-event time
-  cpu_baseline the oracle port of the reference (PyTorch fp32 on the host cores) on the same workload
+  e2e          same step driven from pinned HOST buffers (H2D of t1 + covariates + pet every step), loss read back (D2H)
+  roofline     dominant kernel of the step, timed live with CUDA events in extra eager steps: the slab convolution
+               kernel on the full-resolution 16 -> 16 channel layers (HBM-bound: AI 216 F/B < ridge)
+  cpu_baseline the oracle port of the reference (PyTorch fp32 on the host cores) on a bounded sample of the workload
 """
 from __future__ import annotations
 
@@ -486,6 +488,32 @@ def run_reference_bmgan(args, cfg_name, shape, batch):
 ATTEN_METRIC = "covariate-conditioned 3D T1->PET generator (AttenUNet) training-step throughput (fwd + L1 + bwd + Adam)"
 
 
+# unet/config/training.json:8-38 (atten_unet_def) + cross_attention_dim injected at train_unet.py:64-68
+ATTEN_CFG = dict(spatial_dims=3, in_channels=1, out_channels=1, num_channels=[16, 32, 64, 128], num_res_blocks=2,
+                 attention_levels=[False, False, False, True], norm_num_groups=16, norm_eps=1e-6, resblock_updown=True,
+                 num_head_channels=[0, 0, 0, 32], with_conditioning=True, transformer_num_layers=1,
+                 upcast_attention=False, use_flash_attention=False, cross_attention_dim=5)
+
+
+def redraw_parameters_(named_tensors, seed=0):
+    """Seeded re-draw of every parameter by NAME: the reference zero-initialises conv2 / proj_out / out
+    (atten_unet_model.py:56-62,303,616,1779), which makes a freshly constructed network output exactly 0
+    -- a benchmark on that network would time a degenerate backward.  Same recipe as the parity tests use."""
+    import zlib
+
+    import torch
+    with torch.no_grad():
+        for name, p in named_tensors:
+            g = torch.Generator().manual_seed(seed * 1000003 + zlib.crc32(name.encode()))
+            r = torch.randn(p.shape, generator=g)
+            if p.dim() >= 2:
+                p.copy_(r / p[0].numel() ** 0.5)
+            elif "norm" in name and name.endswith("weight") or name.endswith("out.0.weight"):
+                p.copy_(1.0 + 0.1 * r)
+            else:
+                p.copy_(0.1 * r)
+
+
 def atten_batch(shape, seed, batch):
     import torch
     g = torch.Generator().manual_seed(seed)
@@ -502,8 +530,8 @@ def cpu_atten_steps(shape, batch, steps, warmup, budget_s=150.0):
     torch.set_num_threads(cores)
     # parameter shapes come from the oracle's own key walk: build them from a throw-away CUDA-free module mirror
     import petsyn
-    sd = {k: v.detach().clone() for k, v in petsyn.AttenUNet(**OA.TRAINING_JSON).state_dict().items()}
-    OA.randomize_(sd.items(), seed=777)
+    sd = {k: v.detach().clone() for k, v in petsyn.AttenUNet(**ATTEN_CFG).state_dict().items()}
+    redraw_parameters_(sd.items(), seed=777)
 
     def one(shape_):
         x, ctx, tgt = atten_batch(shape_, 777, batch)
@@ -537,7 +565,7 @@ def run_petsyn_atten(args, shape, batch):
     import torch.distributed as dist
 
     import petsyn
-    from oracle import atten_unet as OA   # only for the deterministic re-draw of the zero-initialised tensors
+    from petsyn_b200 import graph as G
     from petsyn_b200 import ops
     from petsyn_b200.train import AttenUNetTrainer
 
@@ -548,8 +576,8 @@ def run_petsyn_atten(args, shape, batch):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    model = petsyn.AttenUNet(**OA.TRAINING_JSON)
-    OA.randomize_(model.named_parameters(), seed=777)       # default init has zero_module tensors => output == 0
+    model = petsyn.AttenUNet(**ATTEN_CFG)
+    redraw_parameters_(model.named_parameters(), seed=777)   # default init has zero_module tensors => output == 0
     model = model.to(dev).train()
     pool = 3
     host = [atten_batch(shape, 777 + 1000 * rank + i, batch) for i in range(pool)]
@@ -601,6 +629,26 @@ def run_petsyn_atten(args, shape, batch):
     barrier()
     ms_e2e = f0.elapsed_time(f1)
     clocks = sampler.stop() if rank == 0 else None
+
+    # ---- roofline leg: CUDA-event brackets around every op of a few extra EAGER steps (same kernels as the graph) ----
+    tape = trainer.eng.tape
+    tape.timers = {}
+    saved_graph, trainer.graph = trainer.graph, None
+    for i in range(4):
+        trainer.step(*resident[i % pool])
+    torch.cuda.synchronize()
+    trainer.graph = saved_graph
+    timers, tape.timers = tape.timers, None
+    op_ms = {k: statistics.mean(a.elapsed_time(b) for a, b in v[1:]) for k, v in timers.items()}   # first step = warm-up
+    by_kind = {}
+    for (idx, which), ms_ in op_ms.items():
+        key = f"{type(tape.ops[idx]).__name__}.{which}"
+        by_kind[key] = by_kind.get(key, 0.0) + ms_
+    # the dominant kernel: slab_conv_kernel on the full-resolution 16 -> 16 layers (one launch = one fprop)
+    dom = [i for i, op in enumerate(tape.ops) if isinstance(op, G.ConvOp) and op.plan.kernel_path[0] == 1
+           and op.cin == 16 and op.cout == 16 and op.x.buf.rows == batch * shape[0] * shape[1] * shape[2]]
+    dom_ms = statistics.mean(op_ms[(i, "fwd")] for i in dom) if dom else None
+
     t = torch.tensor([ms_total, ms_e2e], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -612,10 +660,24 @@ def run_petsyn_atten(args, shape, batch):
         except Exception:
             pass
         peak_tf = float(peaks.get("bf16_tflops_sustained", 1400.0))
+        peak_bw = float(peaks.get("hbm_gbs", 6459.0))
         d, h, w = shape
         fwd = trainer.eng.flops_algorithmic
         ms = ms_total / args.steps
         ach = 3.0 * fwd / (ms * 1e-3) / 1e12
+        vox = batch * d * h * w
+        dom_bytes = vox * 16 * 2 * 2                      # bf16 read-once of x + write-once of y, 16 channels each
+        dom_flops = 2.0 * vox * 16 * 16 * 27
+        roof = {"bound": "hbm", "kernel": "slab_conv_kernel<1> (Conv3d 16->16 k3 s1 p1 at 96x128x96, batch 2: the "
+                f"{len(dom)} full-resolution ResnetBlock convs; fprop launches timed)", "achieved": None, "peak": peak_bw,
+                "unit": "GB/s", "frac": None, "traffic": 110.9e6,
+                "traffic_source": "profiles/r1_slab_conv_ncu_full_summary.csv (dram read + write bytes of one launch)",
+                "algorithmic_bytes_per_launch": dom_bytes, "algorithmic_flops_per_launch": dom_flops,
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6459 GB/s"}
+        if dom_ms:
+            roof.update(achieved=dom_bytes / (dom_ms * 1e-3) / 1e9, launch_ms=dom_ms,
+                        tensor_tflops=dom_flops / (dom_ms * 1e-3) / 1e12)
+            roof["frac"] = roof["achieved"] / peak_bw
         line = {
             "metric": ATTEN_METRIC, "value": world * batch * args.steps / (ms_total * 1e-3), "unit": UNIT,
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms,
@@ -629,11 +691,10 @@ def run_petsyn_atten(args, shape, batch):
                     "h2d_bytes_per_step": 2 * batch * d * h * w * 4 + batch * 20, "d2h_bytes_per_step": 4,
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches * args.steps, "clocks": clocks,
-            "roofline": {"bound": "hbm", "kernel": "whole step (small-channel convs are HBM/smem-bound by construction, "
-                         "SURVEY 8a A3); achieved = 3 x forward algorithmic conv+attention FLOPs / step time, reported "
-                         "against the tensor peak for reference", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s",
-                         "frac": ach / peak_tf, "traffic": None, "forward_gflop": fwd / 1e9,
-                         "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback"},
+            "roofline": roof,
+            "step_breakdown": {"per_op_class_ms": {k: round(v, 4) for k, v in sorted(by_kind.items(), key=lambda kv: -kv[1])},
+                               "model_tflops_algorithmic": ach, "forward_gflop": fwd / 1e9,
+                               "model_frac_of_tensor_peak": ach / peak_tf},
             "final_loss": final,
         }
         if not args.no_cpu_baseline and world == 1:
@@ -675,10 +736,10 @@ def count_launches(trainer, batch) -> int:
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="petsyn", choices=["petsyn", "reference"])
-    ap.add_argument("--workload", default="unet3d_train_cfg1", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="atten_unet_train_cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch kernels eagerly instead of replaying a CUDA graph")
     args = ap.parse_args()

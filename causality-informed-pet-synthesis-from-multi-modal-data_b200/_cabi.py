@@ -73,6 +73,7 @@ SIGNATURES = {
     "petsyn_conv_plan_destroy": (None, [_vp]),
     "petsyn_conv_out_dims": (_i32, [_vp, C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i32)]),
     "petsyn_conv_flops": (_i32, [_vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "petsyn_conv_kernel_path": (_i32, [_vp, _i32]),
     "petsyn_conv_packed_fprop_bytes": (_sz, [_vp]),
     "petsyn_conv_packed_dgrad_bytes": (_sz, [_vp]),
     "petsyn_conv_wgrad_scratch_bytes": (_sz, [_vp]),

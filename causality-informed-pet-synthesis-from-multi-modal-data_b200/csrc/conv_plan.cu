@@ -1018,6 +1018,16 @@ int32_t petsyn_conv_flops(const petsyn_conv_plan* pl, double* algorithmic, doubl
   return PETSYN_OK;
 }
 
+int32_t petsyn_conv_kernel_path(const petsyn_conv_plan* pl, int32_t pass) {
+  if (!pl) return -1;
+  switch (pass) {
+    case 0: return pl->fprop.slab ? 1 : 0;
+    case 1: return pl->dgrad.slab ? 1 : 0;
+    case 2: return pl->wg_slab ? 1 : (pl->wg_small ? 2 : 0);
+    default: return -1;
+  }
+}
+
 size_t petsyn_conv_packed_fprop_bytes(const petsyn_conv_plan* pl) { return pl ? packed_bytes(pl->fprop) : 0; }
 size_t petsyn_conv_packed_dgrad_bytes(const petsyn_conv_plan* pl) { return pl ? packed_bytes(pl->dgrad) : 0; }
 size_t petsyn_conv_wgrad_scratch_bytes(const petsyn_conv_plan* pl) {

@@ -525,15 +525,34 @@ class Tape:
             op.stage_padded()
         check(lib.petsyn_pack_batch_run(self._pack_batch, stream_ptr()), "pack_batch_run")
 
+    # ``timers``: None, or a dict that receives {(op index, "fwd"|"bwd"): [(start, end) CUDA events, ...]} -- eager
+    # profiling runs only (bench.py's roofline leg); events are recorded on the current stream around each op
+    timers: Optional[Dict] = None
+
+    def _timed(self, idx: int, which: str, fn) -> None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        self.timers.setdefault((idx, which), []).append((e0, e1))
+
     def forward(self, training: bool) -> None:
         assert self._final
         self.repack()
+        if self.timers is not None:
+            for i, op in enumerate(self.ops):
+                self._timed(i, "fwd", lambda: op.fwd(training))
+            return
         for op in self.ops:
             op.fwd(training)
 
     def backward(self, on_op_done=None) -> None:
-        for op in reversed(self.ops):
-            op.bwd()
+        for i in range(len(self.ops) - 1, -1, -1):
+            op = self.ops[i]
+            if self.timers is not None:
+                self._timed(i, "bwd", op.bwd)
+            else:
+                op.bwd()
             if on_op_done is not None:
                 on_op_done(op)
 

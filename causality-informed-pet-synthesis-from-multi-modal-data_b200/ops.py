@@ -44,6 +44,8 @@ class ConvPlan:
         fa, fe = C.c_double(), C.c_double()
         check(lib.petsyn_conv_flops(self._h, C.byref(fa), C.byref(fe)))
         self.flops_algorithmic, self.flops_executed = fa.value, fe.value
+        # kernel family per pass (0 gather-form igemm, 1 slab, 2 small-channel wgrad): reporting only
+        self.kernel_path = tuple(lib.petsyn_conv_kernel_path(self._h, i) for i in range(3))
         self.packed_fprop_bytes = lib.petsyn_conv_packed_fprop_bytes(self._h)
         self.packed_dgrad_bytes = lib.petsyn_conv_packed_dgrad_bytes(self._h)
         self.wgrad_scratch_bytes = lib.petsyn_conv_wgrad_scratch_bytes(self._h)

@@ -97,6 +97,11 @@ size_t petsyn_conv_packed_fprop_bytes(const petsyn_conv_plan* plan);
 size_t petsyn_conv_packed_dgrad_bytes(const petsyn_conv_plan* plan);
 size_t petsyn_conv_wgrad_scratch_bytes(const petsyn_conv_plan* plan);
 
+/* Which kernel family a pass of this plan runs on (for profiling / reporting): pass 0 = fprop, 1 = dgrad, 2 = wgrad.
+ * Returns 0 = gather-form tcgen05 implicit GEMM (igemm_kernel / wgrad_kernel), 1 = slab kernels (smem-resident halo
+ * slabs, small channel counts), 2 = wgrad_small_kernel; -1 on a bad argument. */
+int32_t petsyn_conv_kernel_path(const petsyn_conv_plan* plan, int32_t pass);
+
 /* Deep layers with few output voxels (M = 252 at the U-Net bottleneck) split their K loop over several CTAs that
  * add-reduce fp32 partial tiles (TMA reduction) into a caller-owned workspace; 0 bytes when no split is planned.
  * The workspace (shared by fprop and dgrad, which never overlap on one stream) must be set before the first call. */
