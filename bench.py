@@ -597,7 +597,7 @@ def run_petsyn_atten(args, shape, batch):
     trainer.step(*resident[0])
     torch.cuda.synchronize()
     launches = ops.launch_count() - n0
-    if not args.no_graph and world == 1:
+    if not args.no_graph:
         trainer.capture()
     for i in range(max(args.warmup, 3)):
         trainer.step(*resident[i % pool])

@@ -442,22 +442,28 @@ class AttenUNetTrainer:
         self.dy = torch.zeros(example_input.shape, dtype=torch.float32, device=dev)
         self.bucketer = GradBucketer(self.arena, bucket_mb, process_group)
         self.graph = None
+        self.segments = None
         self.static = None
         if self.world > 1:
             dist.broadcast(self.arena.p, src=0, group=self.pg)
         self.eng.mark_weights_dirty()
 
-    def _step_impl(self, x: torch.Tensor, context: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
-        eng = self.eng
-        y = eng.forward(x, context)
+    def _forward_and_loss(self, x: torch.Tensor, context: torch.Tensor, target: torch.Tensor) -> None:
+        y = self.eng.forward(x, context)
         self.loss.zero_()
         ops.l1_loss_fwd_bwd(y, target, self.loss, self.dy)
-        eng.backward(self.dy, out=self.arena.grad_views, on_ready=self.bucketer.on_ready)
-        self.bucketer.wait_all()
+
+    def _optimizer(self) -> None:
         self.step_dev.add_(1)
         ops.adam_step(self.arena.p, self.arena.g, self.m, self.v, self.lr, self.betas[0], self.betas[1], self.eps, 0,
                       step_dev=self.step_dev)
-        eng.mark_weights_dirty()
+        self.eng.mark_weights_dirty()
+
+    def _step_impl(self, x: torch.Tensor, context: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
+        self._forward_and_loss(x, context, target)
+        self.eng.backward(self.dy, out=self.arena.grad_views, on_ready=self.bucketer.on_ready)
+        self.bucketer.wait_all()
+        self._optimizer()
         return self.loss
 
     def step(self, x: torch.Tensor, context: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
@@ -468,12 +474,21 @@ class AttenUNetTrainer:
         for dst, src in zip(self.static, (x, ctx, target)):
             if dst.data_ptr() != src.data_ptr():
                 dst.copy_(src, non_blocking=True)
-        self.graph.replay()
+        if self.segments is None:
+            self.graph.replay()
+            return self.loss
+        for graph, last_param in self.segments:
+            graph.replay()
+            self.bucketer.on_ready(last_param)       # eager NCCL launch between graph segments (side stream)
+        self.bucketer.wait_all()
+        self.graph.replay()                          # Adam
         return self.loss
 
     def capture(self, warmup: int = 2) -> None:
-        if self.world > 1:
-            raise RuntimeError("AttenUNetTrainer.capture supports world_size 1; data-parallel runs launch eagerly")
+        """Capture the step into CUDA graphs.  Single GPU: one graph.  Data parallel: the collectives stay outside the
+        graphs -- the step is cut at every gradient-bucket boundary into [fwd + loss + backward-until-bucket-0]
+        [..until bucket 1] ... [Adam]; each bucket's all-reduce is launched eagerly on the side stream right after
+        its segment and overlaps the next one (same scheme as Unet3dTrainer.capture)."""
         state = [self.arena.p, self.m, self.v, self.step_dev]
         snap = [t.clone() for t in state]
         n = self.dy.shape[0]
@@ -487,9 +502,34 @@ class AttenUNetTrainer:
                 self._step_impl(*self.static)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize(self.dev)
-        g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
-            self._step_impl(*self.static)
+        pool = torch.cuda.graph_pool_handle()
+        if self.world == 1:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, pool=pool):
+                self._step_impl(*self.static)
+            self.segments = None
+        else:
+            closers = set(self.bucketer._bucket_of_last)
+            segments = []
+            cur = {"g": torch.cuda.CUDAGraph()}
+            cur["ctx"] = torch.cuda.graph(cur["g"], pool=pool)
+            cur["ctx"].__enter__()
+
+            def cut(prm) -> None:                    # called right after the op that completes prm's gradient
+                if id(prm) not in closers:
+                    return
+                cur["ctx"].__exit__(None, None, None)
+                segments.append((cur["g"], prm))
+                cur["g"] = torch.cuda.CUDAGraph()
+                cur["ctx"] = torch.cuda.graph(cur["g"], pool=pool)
+                cur["ctx"].__enter__()
+
+            self._forward_and_loss(*self.static)
+            self.eng.backward(self.dy, out=self.arena.grad_views, on_ready=cut)
+            self._optimizer()                        # the open capture holds only what follows the last bucket: Adam
+            cur["ctx"].__exit__(None, None, None)
+            g = cur["g"]
+            self.segments = segments
         for dst, src in zip(state, snap):
             dst.copy_(src)
         self.eng.mark_weights_dirty()        # the captured step begins with the repack, so no eager refresh is needed
