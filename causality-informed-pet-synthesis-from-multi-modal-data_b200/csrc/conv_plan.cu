@@ -479,8 +479,9 @@ static int32_t finish_side(GemmSide& g, int N, bool allow_slab = false) {
     }
     g.subs.push_back(sub);
   }
-  if (allow_slab && !g.out_fp32 && g.Kc % 16 == 0 && g.Kc <= 64 && g.R % 16 == 0 && g.R <= 64 &&
-      slab_smem_bytes(27, g.Kc / 16, g.R, ((g.Kc / 16) * kSlabWp * kSlabHp * 32 + 1023) / 1024 * 1024, 4) <= 224 * 1024 &&
+  if (allow_slab && (!g.out_fp32 || g.R <= 32) && g.Kc % 16 == 0 && g.Kc <= 64 && g.R % 16 == 0 && g.R <= 64 &&
+      slab_smem_bytes(27, g.Kc / 16, g.R, ((g.Kc / 16) * kSlabWp * kSlabHp * 32 + 1023) / 1024 * 1024, 4, g.out_fp32 ? 4 : 2) <=
+          224 * 1024 &&
       (int64_t)g.out_w * g.out_h * g.out_d * N >= 128 * 148) {
     g.slab = true;
     g.ksplit = 1;
@@ -496,12 +497,13 @@ static int32_t view_map(CUtensorMap* out, const void* base, const ViewSpec& v, b
 
 // tensor map of an NDHWC bf16 view for the slab kernels: dims (16 ch, W, atoms, H, D*N) so that one box load lands as
 // [h][atom][w][16 ch] in shared memory (32B swizzle)
-static int32_t slab_view_map(CUtensorMap* out, const void* base, const ViewSpec& v, int atoms, int box_w, int box_h) {
+static int32_t slab_view_map(CUtensorMap* out, const void* base, const ViewSpec& v, int atoms, int box_w, int box_h,
+                             int box_atoms = 0) {
   const uint64_t cs = (uint64_t)v.cstride * 2;
   const uint8_t* b = reinterpret_cast<const uint8_t*>(base) + (uint64_t)v.coff * 2;
   uint64_t dims[5] = {16, (uint64_t)v.W, (uint64_t)atoms, (uint64_t)v.H, (uint64_t)v.D * v.N};
   uint64_t strides[4] = {cs, 32, cs * v.W, cs * v.W * v.H};
-  uint32_t box[5] = {16u, (uint32_t)box_w, (uint32_t)atoms, (uint32_t)box_h, 1u};
+  uint32_t box[5] = {16u, (uint32_t)box_w, (uint32_t)(box_atoms > 0 ? box_atoms : atoms), (uint32_t)box_h, 1u};
   return encode_tmap(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, b, dims, strides, box, 32);
 }
 
@@ -521,7 +523,9 @@ static int32_t bind_slab(GemmSide& g, const ViewSpec& va, const ViewSpec& vc, co
     rc = encode_tmap(&p.b_map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, b, dims, strides, box, 32);
     if (rc) return rc;
   }
-  rc = view_map(&p.c_map, c, vc, false, 0, 2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, g.R, kSlabW, kSlabH, 1, 0);
+  rc = view_map(&p.c_map, c, vc, false, 0, g.out_fp32 ? 4 : 2,
+                g.out_fp32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, g.R, kSlabW, kSlabH, 1, 0);
+  p.out_f32 = g.out_fp32 ? 1 : 0;
   if (rc) return rc;
   if (g.prog.subs.size() != 1 || g.prog.subs[0].size() != 27) return fail(PETSYN_EINVAL, "slab path needs one 27-tap program");
   for (int t = 0; t < 27; ++t) {
@@ -538,7 +542,7 @@ static int32_t bind_slab(GemmSide& g, const ViewSpec& va, const ViewSpec& vc, co
   p.slab_tx = atoms * kSlabWp * kSlabHp * 32;
   p.slab_bytes = (p.slab_tx + 1023) / 1024 * 1024;
   // ring depth and CTAs per SM from the shared-memory budget
-  const int fixed = slab_smem_bytes(p.ntaps, atoms, g.R, p.slab_bytes, 0);
+  const int fixed = slab_smem_bytes(p.ntaps, atoms, g.R, p.slab_bytes, 0, g.out_fp32 ? 4 : 2);
   const int ring = (fixed + 8 * p.slab_bytes <= 110 * 1024) ? 8 : 4;
   p.ring = ring;
   g.slab_smem = fixed + ring * p.slab_bytes;
@@ -974,8 +978,8 @@ int32_t petsyn_conv_plan_create(const petsyn_conv_desc* d, petsyn_conv_plan** ou
       ks2 = std::max<int64_t>(1, std::min<int64_t>(ks2, std::max<int64_t>(1, nboxes / 8)));
       pl->wg_ksplit = (int)ks2;
     }
-    if (slab_ok && d->cin % 16 == 0 && d->cin <= 48 && d->cout % 16 == 0 && d->cout <= 64 &&
-        (int64_t)d->w * d->h * d->d * d->n >= 256 * 148) {
+    if (slab_ok && d->cin % 16 == 0 && d->cin <= 96 && d->cout % 16 == 0 && d->cout <= 64 &&
+        (int64_t)d->w * d->h * d->d * d->n >= 32768) {
       pl->wg_slab = true;
       pl->wg_small = false;
     }
@@ -1032,7 +1036,10 @@ size_t petsyn_conv_packed_fprop_bytes(const petsyn_conv_plan* pl) { return pl ? 
 size_t petsyn_conv_packed_dgrad_bytes(const petsyn_conv_plan* pl) { return pl ? packed_bytes(pl->dgrad) : 0; }
 size_t petsyn_conv_wgrad_scratch_bytes(const petsyn_conv_plan* pl) {
   if (!pl) return 0;
-  if (pl->wg_slab) return (size_t)(pl->desc.cout / 16) * 3 * 48 * (3 * (pl->desc.cin / 16) * 16) * sizeof(float);
+  if (pl->wg_slab) {
+    const int atoms = pl->desc.cin / 16, groups = (atoms + 2) / 3, apg = (atoms + groups - 1) / groups;
+    return (size_t)groups * (pl->desc.cout / 16) * 3 * 48 * (3 * apg * 16) * sizeof(float);
+  }
   if (pl->wg_small) return (size_t)pl->fprop.subs.size() * pl->wg_mtiles * 128 * pl->wg_npad * sizeof(float);
   return packed_bytes(pl->fprop) * 2;
 }
@@ -1176,11 +1183,13 @@ int32_t petsyn_conv_wgrad(petsyn_conv_plan* pl, const void* x, const void* dy, v
   cudaStream_t st = as_stream(stream);
   if (pl->wg_slab) {
     SlabWgradParams& q = pl->wgl_params;
-    const int atoms = pl->desc.cin / 16, co_atoms = pl->desc.cout / 16;
+    const int atoms_total = pl->desc.cin / 16, co_atoms = pl->desc.cout / 16;
+    const int groups = (atoms_total + 2) / 3;              // <= 3 atoms (48 channels) per CTA: 3 accumulators x 144 TMEM columns
+    const int atoms = (atoms_total + groups - 1) / groups; // atoms per group; a short last group reads zero-filled atoms
     const int ncols = 3 * atoms * 16;
     if (!(pl->wg_key_x == x && pl->wg_key_g == dy && pl->wg_key_s == scratch)) {
       memset(&q, 0, sizeof(q));
-      int32_t rc = slab_view_map(&q.x_map, x, pl->vx, atoms, kWgW, kWgH + 2);
+      int32_t rc = slab_view_map(&q.x_map, x, pl->vx, atoms_total, kWgW, kWgH + 2, atoms);
       if (rc) return rc;
       {
         const ViewSpec& v = pl->vdy;
@@ -1208,14 +1217,14 @@ int32_t petsyn_conv_wgrad(petsyn_conv_plan* pl, const void* x, const void* dy, v
       q.xring = slab_wgrad_smem_bytes(q.xslab_bytes, q.gslab_bytes, ncols, 8, q.gring) <= cap ? 8 : 4;
       pl->wg_slab_smem = slab_wgrad_smem_bytes(q.xslab_bytes, q.gslab_bytes, ncols, q.xring, q.gring);
       const int occ = q.tmem_cols == 256 ? std::max(1, std::min(2, (227 * 1024) / (pl->wg_slab_smem + 1024))) : 1;
-      const int ctas = std::max(1, 148 * occ / co_atoms);
+      const int ctas = std::max(1, 148 * occ / (co_atoms * groups));
       slab_split(q.W, q.H, q.D, q.batch, kWgW, kWgH, ctas, &q.dchunk, &q.nchunks, &q.items);
       pl->wg_slab_grid = std::min(ctas, q.items);
       PETSYN_CHECK_CUDA(cudaFuncSetAttribute(slab_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
       pl->wg_key_x = x; pl->wg_key_g = dy; pl->wg_key_s = scratch;
     }
     PETSYN_CHECK_CUDA(cudaMemsetAsync(scratch, 0, petsyn_conv_wgrad_scratch_bytes(pl), st));
-    dim3 grid((unsigned)pl->wg_slab_grid, (unsigned)co_atoms);
+    dim3 grid((unsigned)pl->wg_slab_grid, (unsigned)co_atoms, (unsigned)groups);
     slab_wgrad_kernel<<<grid, 192, pl->wg_slab_smem, st>>>(q);
     int32_t rc = check_launch("slab_wgrad_kernel");
     if (rc) return rc;

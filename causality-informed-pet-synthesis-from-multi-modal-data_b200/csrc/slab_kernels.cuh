@@ -50,6 +50,7 @@ struct alignas(64) SlabParams {
   int32_t epi_act;
   float epi_slope;
   int32_t reduce;       // 1: add into the destination (bf16 TMA reduction)
+  int32_t out_f32;      // 1: fp32 output (the one-channel network head keeps full precision), c_map is an fp32 map
 };
 
 // tcgen05.mma with the 64-bit shared-memory descriptors given as (lo, hi) halves: the MMA-issuing thread only ever
@@ -74,9 +75,9 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 __device__ __forceinline__ void tma_store_wait_read_1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 
 // smem: [weights: ntaps*atoms*N*32][ring: 4*slab_bytes][staging: 2*128*N*2][barriers]
-__host__ __device__ inline int slab_smem_bytes(int ntaps, int atoms, int n, int slab_bytes, int ring) {
+__host__ __device__ inline int slab_smem_bytes(int ntaps, int atoms, int n, int slab_bytes, int ring, int esz = 2) {
   const int wbytes = (ntaps * atoms * n * 32 + 1023) / 1024 * 1024;
-  const int stg = (2 * 128 * n * 2 + 1023) / 1024 * 1024;
+  const int stg = (2 * 128 * n * esz + 1023) / 1024 * 1024;
   return wbytes + ring * slab_bytes + stg + 1024 /*barriers + tap table*/ + 1024 /*align*/;
 }
 
@@ -86,7 +87,8 @@ __global__ void __launch_bounds__(192) slab_conv_kernel(const __grid_constant__ 
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int N = p.block_n;
   const int wbytes = (p.ntaps * p.atoms * N * 32 + 1023) / 1024 * 1024;
-  const int stg_bytes = (2 * 128 * N * 2 + 1023) / 1024 * 1024;
+  const int esz = p.out_f32 ? 4 : 2;
+  const int stg_bytes = (2 * 128 * N * esz + 1023) / 1024 * 1024;
   uint8_t* s_w = smem;
   uint8_t* s_ring = smem + wbytes;
   const int R = p.ring;
@@ -234,7 +236,7 @@ __global__ void __launch_bounds__(192) slab_conv_kernel(const __grid_constant__ 
         // the TMA store that last read this staging buffer (two tiles ago) must have finished reading it
         if (leader) tma_store_wait_read_1();
         named_bar_sync(1, 128);
-        uint8_t* stg = s_stg + buf * (128 * N * 2) + row * (N * 2);
+        uint8_t* stg = s_stg + buf * (128 * N * esz) + row * (N * esz);
         const uint32_t taddr = tmem_base + buf * 64 + (uint32_t(quad * 32) << 16);
         for (int c0 = 0; c0 < N; c0 += 16) {
           uint32_t v[16];
@@ -251,14 +253,20 @@ __global__ void __launch_bounds__(192) slab_conv_kernel(const __grid_constant__ 
 #pragma unroll
             for (int i = 0; i < 16; ++i) f[i] = apply_act(f[i], p.epi_act, p.epi_slope);
           }
-          uint32_t pk[8];
+          if (p.out_f32) {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            __nv_bfloat162 b2 = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
-            pk[i] = *reinterpret_cast<uint32_t*>(&b2);
+            for (int q = 0; q < 4; ++q)
+              *reinterpret_cast<float4*>(stg + c0 * 4 + q * 16) = make_float4(f[4 * q], f[4 * q + 1], f[4 * q + 2], f[4 * q + 3]);
+          } else {
+            uint32_t pk[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              __nv_bfloat162 b2 = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+              pk[i] = *reinterpret_cast<uint32_t*>(&b2);
+            }
+            *reinterpret_cast<uint4*>(stg + c0 * 2) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            *reinterpret_cast<uint4*>(stg + c0 * 2 + 16) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
           }
-          *reinterpret_cast<uint4*>(stg + c0 * 2) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-          *reinterpret_cast<uint4*>(stg + c0 * 2 + 16) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
         }
         // accumulator drained: hand the TMEM buffer back to the MMA warp
         ptx::tc_fence_before_sync();
@@ -267,7 +275,7 @@ __global__ void __launch_bounds__(192) slab_conv_kernel(const __grid_constant__ 
         ptx::fence_proxy_async_smem();
         named_bar_sync(1, 128);
         if (leader) {
-          const uint8_t* src = s_stg + buf * (128 * N * 2);
+          const uint8_t* src = s_stg + buf * (128 * N * esz);
           if (p.reduce)
             ptx::tma_reduce_add_5d(&p.c_map, src, 0, tw * kSlabW, th * kSlabH, d0 + dz, nb);
           else
@@ -292,8 +300,8 @@ constexpr int kWgMaxRing = 8;
 struct alignas(64) SlabWgradParams {
   CUtensorMap x_map;    // dims (16 ch, W, atoms, H, D*N); box (16, 16, atoms, 18, 1); 32B swizzle -> smem [h][atom][w][16]
   CUtensorMap g_map;    // dy co-atom view: dims (16 ch, W, H, D*N); box (16, 18, 16, 1); 32B swizzle -> smem [h][w 18][16]
-  float* scratch;       // fp32 [co_atoms][3 (c)][48 (i, co)][ncols = 3 (b) * atoms * 16]
-  int32_t atoms, co_atoms;
+  float* scratch;       // fp32 [ci_groups][co_atoms][3 (c)][48 (i, co)][ncols = 3 (b) * atoms * 16]
+  int32_t atoms, co_atoms;   // atoms = 16-channel atoms of x PER channel group (grid.z = group), <= 3
   int32_t W, H, D, batch;
   int32_t tiles_w, tiles_h, dchunk, nchunks, items;
   int32_t xslab_bytes, gslab_bytes;   // ring pitches (multiples of 1024)
@@ -314,7 +322,7 @@ __device__ __forceinline__ void bulk_reduce_add_f32(float* gdst, const void* ssr
                : "memory");
 }
 
-// grid: x = persistent CTAs, y = co atom
+// grid: x = persistent CTAs, y = co atom, z = input-channel group (atoms * 16 channels each)
 __global__ void __launch_bounds__(192) slab_wgrad_kernel(const __grid_constant__ SlabWgradParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -335,6 +343,7 @@ __global__ void __launch_bounds__(192) slab_wgrad_kernel(const __grid_constant__
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
   const int coa = blockIdx.y;
+  const int cig = blockIdx.z;
   const int G = gridDim.x;
   const bool has_work = (int)blockIdx.x < p.items;
 
@@ -374,8 +383,8 @@ __global__ void __launch_bounds__(192) slab_wgrad_kernel(const __grid_constant__
             const int d = d0 - 1 + s;
             const bool oob = d < 0 || d >= p.D;
             ptx::mbar_expect_tx(&xfull[slot], uint32_t(p.xslab_tx));
-            ptx::tma_load_5d(s_x + slot * p.xslab_bytes, &p.x_map, &xfull[slot], 0, oob ? p.W + 64 : tw * kWgW, 0,
-                             th * kWgH - 1, oob ? 0 : nb * p.D + d);
+            ptx::tma_load_5d(s_x + slot * p.xslab_bytes, &p.x_map, &xfull[slot], 0, oob ? p.W + 64 : tw * kWgW,
+                             cig * p.atoms, th * kWgH - 1, oob ? 0 : nb * p.D + d);
             ++xseq;
           }
           if (s >= 2) {
@@ -471,7 +480,7 @@ __global__ void __launch_bounds__(192) slab_wgrad_kernel(const __grid_constant__
       }
       named_bar_sync(1, 128);
       if (warp == 4 && (tid & 31) == 0) {
-        bulk_reduce_add_f32(p.scratch + ((size_t)(coa * 3 + c) * 48) * ncols, stg, uint32_t(48 * ncols * 4));
+        bulk_reduce_add_f32(p.scratch + ((size_t)((cig * p.co_atoms + coa) * 3 + c) * 48) * ncols, stg, uint32_t(48 * ncols * 4));
         ptx::tma_store_commit();
         ptx::tma_store_wait_read();
       }
@@ -484,18 +493,21 @@ __global__ void __launch_bounds__(192) slab_wgrad_kernel(const __grid_constant__
   if (warp == 1) ptx::tmem_dealloc(tmem_base, uint32_t(p.tmem_cols));
 }
 
-// scratch [co_atoms][3 (c = kd)][48 = (2 - kw) * 16 + co % 16][(kh * atoms + ci / 16) * 16 + ci % 16] -> dw[co][ci][kd][kh][kw]
+// scratch [ci_group][co_atoms][3 (c = kd)][48 = (2 - kw) * 16 + co % 16][(kh * apg + q) * 16 + ci % 16], ci atom = group * apg + q
+//   -> dw[co][ci][kd][kh][kw]
 __global__ void __launch_bounds__(256) slab_wgrad_unpack_kernel(const float* __restrict__ scratch, float* __restrict__ dw,
-                                                                int cout, int cin, int atoms, int accumulate) {
+                                                                int cout, int cin, int apg, int accumulate) {
   const int total = cout * cin * 27;
-  const int ncols = 3 * atoms * 16;
+  const int ncols = 3 * apg * 16;
+  const int co_atoms = cout >> 4;
   for (int i = blockIdx.x * 256 + threadIdx.x; i < total; i += gridDim.x * 256) {
     const int k = i % 27;
     const int ci = (i / 27) % cin;
     const int co = i / (27 * cin);
     const int kw = k % 3, kh = (k / 3) % 3, kd = k / 9;
-    const float v = scratch[((size_t)((co >> 4) * 3 + kd) * 48 + (2 - kw) * 16 + (co & 15)) * ncols +
-                            (kh * atoms + (ci >> 4)) * 16 + (ci & 15)];
+    const int atom = ci >> 4, grp = atom / apg, q = atom - grp * apg;
+    const float v = scratch[((size_t)((grp * co_atoms + (co >> 4)) * 3 + kd) * 48 + (2 - kw) * 16 + (co & 15)) * ncols +
+                            (kh * apg + q) * 16 + (ci & 15)];
     dw[i] = accumulate ? dw[i] + v : v;
   }
 }

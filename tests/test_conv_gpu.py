@@ -61,6 +61,9 @@ CASES = [
     ("conv", 1, 24, 40, 40, 48, 32, 3, 1, 1),      # 3 atoms in, ragged tiles in w and h
     ("conv", 1, 20, 32, 64, 32, 48, 3, 1, 1),      # N = 48; dgrad runs 48 -> 32
     ("conv", 3, 7, 48, 40, 16, 64, 3, 1, 1),       # short depth, 3 samples, N = 64
+    ("conv", 2, 16, 32, 48, 96, 32, 3, 1, 1),      # slab wgrad with two input-channel groups of 3 atoms
+    ("conv", 1, 24, 40, 40, 64, 48, 3, 1, 1),      # two groups of 2 atoms; slab fprop with 4 atoms
+    ("conv", 2, 12, 32, 48, 80, 16, 3, 1, 1),      # 5 atoms: the second group's last atom is zero-filled by TMA
 ]
 
 
@@ -168,6 +171,25 @@ def test_slab_path_slices_bias_act_accumulate(petsyn):
     plan.wgrad(xbuf, dybuf, dw2, accumulate=True)
     torch.cuda.synchronize()
     close(dw2, 2 * w32.grad, "slab accumulating wgrad")
+
+
+def test_slab_path_fp32_output(petsyn):
+    """One-channel network heads keep an fp32 output (cout padded to 16): slab kernel with an fp32 epilogue."""
+    ops = petsyn.ops
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device="cpu").manual_seed(3)
+    n, d, h, w, cin, cout = 2, 12, 32, 40, 16, 16
+    x = torch.randn(n, d, h, w, cin, generator=g).to(dev).to(torch.bfloat16)
+    wt = (torch.randn(cout, cin, 3, 3, 3, generator=g) / (cin * 27) ** 0.5).to(dev)
+    bias = torch.randn(cout, generator=g).to(dev)
+    plan = ops.ConvPlan(ops.OP_CONV, n, d, h, w, cin, cout, 3, 1, 1, y_fp32=True)
+    assert plan.kernel_path[0] == 1
+    plan.pack(wt, need_dgrad=False)
+    y = torch.empty(n, d, h, w, cout, dtype=torch.float32, device=dev)
+    plan.fprop(x, y, bias)
+    torch.cuda.synchronize()
+    ref = F.conv3d(from_ndhwc(x).float(), wt.to(torch.bfloat16).float(), bias, padding=1)
+    assert (from_ndhwc(y) - ref).abs().max().item() <= 2e-4 * ref.abs().max().item()      # fp32 epilogue: no bf16 rounding
 
 
 def test_conv_bad_config_raises(petsyn):
