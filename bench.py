@@ -45,6 +45,12 @@ WORKLOADS = {
     # first field = generator config name
     "bmgan_adv_step_s2": ("full", (96, 128, 96), 1),
     "bmgan_adv_step_small": ("small", (64, 96, 64), 1),
+    # BASELINE configs[3]: full-resolution 160x192x160 inference (eval + no_grad, output_predict.py:104-105), --batch 1..16;
+    # first field = generator family, last = micro-batch run per forward call (the batch is processed in chunks)
+    "infer_atten_unet_s3": ("atten", (160, 192, 160), 2),
+    "infer_unet3d_s3": ("unet3d", (160, 192, 160), 2),
+    "infer_bmgan_s3": ("bmgan", (160, 192, 160), 1),
+    "infer_atten_unet_small": ("atten", (32, 48, 32), 2),
 }
 BMGAN_CFG = {
     "full": {},
@@ -670,7 +676,7 @@ def run_petsyn_atten(args, shape, batch):
         dom_flops = 2.0 * vox * 16 * 16 * 27
         roof = {"bound": "hbm", "kernel": "slab_conv_kernel<1> (Conv3d 16->16 k3 s1 p1 at 96x128x96, batch 2: the "
                 f"{len(dom)} full-resolution ResnetBlock convs; fprop launches timed)", "achieved": None, "peak": peak_bw,
-                "unit": "GB/s", "frac": None, "traffic": 110.9e6,
+                "unit": "GB/s", "frac": None, "traffic": 111.2e6,
                 "traffic_source": "profiles/r1_slab_conv_ncu_full_summary.csv (dram read + write bytes of one launch)",
                 "algorithmic_bytes_per_launch": dom_bytes, "algorithmic_flops_per_launch": dom_flops,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6459 GB/s"}
@@ -721,6 +727,143 @@ def run_reference_atten(args, shape, batch):
         flush=True)
 
 
+# ---------------------------------------------------------------------------------------------- inference arms
+INFER_METRIC = "3D T1->PET inference throughput (eval forward, no_grad)"
+
+
+def _infer_model_and_inputs(family, shape, micro, dev, seed):
+    import torch
+
+    import petsyn
+    g = torch.Generator().manual_seed(seed)
+    d, h, w = shape
+    x = torch.rand(micro, 1, d, h, w, generator=g)
+    if family == "atten":
+        model = petsyn.AttenUNet(**ATTEN_CFG)
+        redraw_parameters_(model.named_parameters(), seed=777)
+        extra = (torch.rand(micro, 1, 5, generator=g),)
+    elif family == "unet3d":
+        torch.manual_seed(777)
+        model = petsyn.UnetGenerator3d(1, 1, num_downs=4, ngf=64)
+        extra = ()
+    else:
+        torch.manual_seed(777)
+        model = petsyn.dense_unet_generator()
+        extra = (torch.randn(micro, 8, generator=g),)
+    return model.to(dev).eval(), x, extra
+
+
+def run_petsyn_infer(args, family, shape, micro):
+    """configs[3]: ``unet.eval(); with torch.no_grad(): unet(t1[, condition])`` (output_predict.py:85-105) through the
+    drop-in module's public forward.  A batch of B volumes is run as B / micro forward calls; ranks are independent
+    replicas (no collective).  value: inputs resident; e2e: H2D of the volumes + D2H of the synthesized PET."""
+    import torch
+    import torch.distributed as dist
+
+    import petsyn  # noqa: F401  (registers the petsyn_b200 package alias)
+    from petsyn_b200 import ops
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B = max(1, args.batch)
+    micro = min(micro, B)
+    chunks = (B + micro - 1) // micro
+    model, x_host, extra_host = _infer_model_and_inputs(family, shape, micro, dev, 777 + rank)
+    pool = 3
+    xs = [(x_host + 0.01 * i).clamp_(0, 1) for i in range(pool)]
+    pinned = [t.pin_memory() for t in xs]
+    resident = [t.to(dev) for t in xs]
+    extra = tuple(t.to(dev) for t in extra_host)
+    out_host = torch.empty(micro, 1, *shape).pin_memory()
+    x_dev = torch.empty_like(resident[0])
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step(i, e2e=False):
+        for c in range(chunks):
+            if e2e:
+                x_dev.copy_(pinned[(i + c) % pool], non_blocking=True)
+                y = model(x_dev, *extra)
+                out_host.copy_(y, non_blocking=True)
+            else:
+                y = model(resident[(i + c) % pool], *extra)
+        return y
+
+    with torch.no_grad():
+        for i in range(max(args.warmup, 3)):
+            step(i)
+        torch.cuda.synchronize()
+        n0 = ops.launch_count()
+        step(0)
+        torch.cuda.synchronize()
+        launches = ops.launch_count() - n0
+        sampler = ClockSampler(local_rank)
+        if rank == 0:
+            sampler.start()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(args.steps):
+            step(i)
+        e1.record()
+        barrier()
+        ms_total = e0.elapsed_time(e1)
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record()
+        for i in range(args.steps):
+            step(i, e2e=True)
+            torch.cuda.current_stream().synchronize()
+        f1.record()
+        barrier()
+        ms_e2e = f0.elapsed_time(f1)
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms_total, ms_e2e], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total, ms_e2e = t.tolist()
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak_tf = float(peaks.get("bf16_tflops_sustained", 1400.0))
+        eng = next(iter(model._engines.values())) if hasattr(model, "_engines") else model.engine_for(resident[0])
+        fwd = float(getattr(eng, "flops_algorithmic", 0.0))          # of one micro-batch forward
+        vols = world * chunks * micro * args.steps
+        ms = ms_total / args.steps
+        d, h, w = shape
+        ach = fwd * chunks / (ms * 1e-3) / 1e12 if fwd else None
+        line = {
+            "metric": INFER_METRIC, "value": vols / (ms_total * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": args.workload, "model": type(model).__name__, "volume": list(shape),
+                       "per_gpu_batch": chunks * micro, "micro_batch": micro, "global_batch": chunks * micro * world,
+                       "parallelism": f"replicas x{world} (no collective)", "cuda_graph": False,
+                       "l2": "activations of one forward (> 5 GB) exceed the 126 MB L2; inputs rotate over 3 volumes"},
+            "e2e": {"value": vols / (ms_e2e * 1e-3), "unit": UNIT,
+                    "h2d_bytes_per_step": chunks * micro * d * h * w * 4, "d2h_bytes_per_step": chunks * micro * d * h * w * 4,
+                    "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": launches * args.steps, "clocks": clocks,
+            "roofline": {"bound": "tensor", "kernel": "whole forward: algorithmic conv (+ attention) FLOPs / time",
+                         "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": (ach / peak_tf) if ach else None,
+                         "traffic": None, "forward_gflop_per_volume": fwd / micro / 1e9 if fwd else None,
+                         "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback"},
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def count_launches(trainer, batch) -> int:
     """Kernels of OUR library launched by one trainer.step() (petsyn_launch_count() delta)."""
     import torch
@@ -742,9 +885,16 @@ def main():
     ap.add_argument("--workload", default="atten_unet_train_cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch kernels eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--batch", type=int, default=1, help="inference workloads: volumes per step and GPU (1..16)")
     args = ap.parse_args()
     ngf, shape, batch = WORKLOADS[args.workload]
-    if args.workload.startswith("atten"):
+    if args.workload.startswith("infer"):
+        if args.impl == "reference":
+            print(json.dumps({"impl": "reference", "unavailable": "inference workloads have no CPU arm in this round; "
+                              "the reference arm covers the training workloads"}), flush=True)
+            return
+        run_petsyn_infer(args, ngf, shape, batch)
+    elif args.workload.startswith("atten"):
         (run_reference_atten if args.impl == "reference" else run_petsyn_atten)(args, shape, batch)
     elif args.workload.startswith("bmgan"):
         (run_reference_bmgan if args.impl == "reference" else run_petsyn_bmgan)(args, ngf, shape, batch)

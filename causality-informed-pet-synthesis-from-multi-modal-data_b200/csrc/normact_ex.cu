@@ -205,9 +205,11 @@ __global__ void __launch_bounds__(256, 3) fwd_kernel(const Dev d) {
   const float slope = d.slope_dev ? __ldg(d.slope_dev) : d.slope;
   const int a1 = ACT >= 0 ? ACT : d.act1, a2 = ACT >= 0 ? ACT : d.act2;
   const int64_t stride = (int64_t)gridDim.x * it.rpp;
-  for (int64_t r0 = (int64_t)blockIdx.x * it.rpp + it.ty; r0 < d.rows; r0 += 2 * stride) {
-    const int64_t ra = base + r0, rb = ra + stride;
-    const bool two = r0 + stride < d.rows;
+  for (int64_t q0 = (int64_t)blockIdx.x * it.rpp + it.ty; q0 < d.rows; q0 += 2 * stride) {
+    // rows are visited in DESCENDING order: the pass that ran just before (statistics / backward reduction) read the
+    // tensor ascending, so its tail is what the 126 MB L2 still holds
+    const bool two = q0 + stride < d.rows;
+    const int64_t ra = base + (d.rows - 1 - q0), rb = ra - stride;
     const F8 xa = load8(d.z + ra * d.C + it.tx * 8);
     F8 xb = splat(0.f), rsa = splat(0.f), rsb = splat(0.f);
     if (two) xb = load8(d.z + rb * d.C + it.tx * 8);
@@ -342,9 +344,9 @@ __global__ void __launch_bounds__(256, 2) bwd_apply_kernel(const Dev d) {
   const int a1 = ACT >= 0 ? ACT : d.act1, a2 = ACT >= 0 ? ACT : d.act2;
   const int64_t stride = (int64_t)gridDim.x * it.rpp;
   const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
-  for (int64_t r0 = (int64_t)blockIdx.x * it.rpp + it.ty; r0 < d.rows; r0 += 2 * stride) {
-    const int64_t ra = base + r0, rb = ra + stride;
-    const bool two = r0 + stride < d.rows;
+  for (int64_t q0 = (int64_t)blockIdx.x * it.rpp + it.ty; q0 < d.rows; q0 += 2 * stride) {
+    const bool two = q0 + stride < d.rows;                          // descending row order (see fwd_kernel)
+    const int64_t ra = base + (d.rows - 1 - q0), rb = ra - stride;
     uint4 xr[2], ar[2], br[2];
     xr[0] = load_raw(d.z + ra * d.C + it.tx * 8);
     ar[0] = load_raw(d.t1 + ra * d.cs1 + d.co1 + it.tx * 8);
