@@ -12,6 +12,7 @@
 //   ConvTranspose s2   y[2q+b]  = sum_{k: b+p-k even} W[k] x[q + (b+p-k)/2]    8 output phase views
 // and the backward-data operators are the same four shapes with x and y exchanged.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -543,10 +544,12 @@ static int32_t bind_slab(GemmSide& g, const ViewSpec& va, const ViewSpec& vc, co
   p.slab_bytes = (p.slab_tx + 1023) / 1024 * 1024;
   // ring depth and CTAs per SM from the shared-memory budget
   const int fixed = slab_smem_bytes(p.ntaps, atoms, g.R, p.slab_bytes, 0, g.out_fp32 ? 4 : 2);
-  const int ring = (fixed + 8 * p.slab_bytes <= 110 * 1024) ? 8 : 4;
+  int ring = (fixed + 8 * p.slab_bytes <= 110 * 1024) ? 8 : 4;
+  if (const char* e = getenv("PETSYN_SLAB_RING")) ring = atoi(e) == 4 ? 4 : 8;       // tuning experiments only
   p.ring = ring;
   g.slab_smem = fixed + ring * p.slab_bytes;
   int occ = std::max(1, std::min(3, (227 * 1024) / (g.slab_smem + 1024)));
+  if (const char* e = getenv("PETSYN_SLAB_OCC")) occ = std::max(1, std::min(atoi(e), (227 * 1024) / (g.slab_smem + 1024)));
   const int ctas = 148 * occ;
   slab_split(va.W, va.H, va.D, va.N, kSlabW, kSlabH, ctas, &p.dchunk, &p.nchunks, &p.items);
   g.slab_grid = std::min(ctas, p.items);
