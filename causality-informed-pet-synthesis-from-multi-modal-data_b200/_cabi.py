@@ -58,7 +58,7 @@ class NormActDesc(C.Structure):
         ("res", C.c_void_p), ("res_cstride", C.c_int32), ("res_coff", C.c_int32), ("res_accumulate", C.c_int32),
         ("sums", C.c_void_p), ("dz", C.c_void_p), ("dgamma", C.c_void_p), ("dbeta", C.c_void_p),
         ("group_size", C.c_int32), ("dz_accumulate", C.c_int32), ("affine_accumulate", C.c_int32),
-        ("slope_dev", C.c_void_p), ("dslope", C.c_void_p),
+        ("slope_dev", C.c_void_p), ("dslope", C.c_void_p), ("dz_colsum", C.c_void_p),
     ]
 
 

@@ -165,12 +165,25 @@ __global__ void __launch_bounds__(256) head_scatter_bwd_kernel(const float* __re
 __global__ void __launch_bounds__(256) concat_latent_kernel(const float* __restrict__ x, const float* __restrict__ zvec,
                                                             __nv_bfloat16* __restrict__ out, int64_t rows_per_sample,
                                                             int64_t rows, int nz, int cpad) {
-  for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < rows; r += (int64_t)gridDim.x * blockDim.x) {
+  // one thread per (row, 8-channel chunk): 16-byte stores, consecutive threads write consecutive chunks
+  const int cpr = cpad >> 3;
+  const int64_t total = rows * cpr;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / cpr;
+    const int c0 = (int)(i - r * cpr) * 8;
     const int n = (int)(r / rows_per_sample);
-    __nv_bfloat16* o = out + r * cpad;
-    o[0] = __float2bfloat16(x[r]);
-    for (int j = 0; j < nz; ++j) o[1 + j] = __float2bfloat16(zvec[n * nz + j]);
-    for (int j = 1 + nz; j < cpad; ++j) o[j] = __float2bfloat16(0.f);
+    float f[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = c0 + j;
+      f[j] = c == 0 ? __ldg(x + r) : (c <= nz ? __ldg(zvec + n * nz + c - 1) : 0.f);
+    }
+    uint4 o;
+    __nv_bfloat162 b0 = __floats2bfloat162_rn(f[0], f[1]), b1 = __floats2bfloat162_rn(f[2], f[3]);
+    __nv_bfloat162 b2 = __floats2bfloat162_rn(f[4], f[5]), b3 = __floats2bfloat162_rn(f[6], f[7]);
+    o.x = *reinterpret_cast<uint32_t*>(&b0); o.y = *reinterpret_cast<uint32_t*>(&b1);
+    o.z = *reinterpret_cast<uint32_t*>(&b2); o.w = *reinterpret_cast<uint32_t*>(&b3);
+    *reinterpret_cast<uint4*>(out + r * cpad + c0) = o;
   }
 }
 // y[r] = src[r, 0]   (channel 0 of a padded fp32 conv output -> contiguous N,1,D,H,W)
@@ -183,12 +196,19 @@ __global__ void __launch_bounds__(256) take_channel0_kernel(const float* __restr
 __global__ void __launch_bounds__(256) put_channel0_grad_kernel(const float* __restrict__ y, const float* __restrict__ dy,
                                                                 __nv_bfloat16* __restrict__ dz, int64_t rows, int cpad,
                                                                 int tanh_out) {
-  for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < rows; r += (int64_t)gridDim.x * blockDim.x) {
-    float g = dy[r];
-    if (tanh_out) { const float v = y[r]; g *= 1.f - v * v; }
-    __nv_bfloat16* o = dz + r * cpad;
-    o[0] = __float2bfloat16(g);
-    for (int j = 1; j < cpad; ++j) o[j] = __float2bfloat16(0.f);
+  const int cpr = cpad >> 3;
+  const int64_t total = rows * cpr;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / cpr;
+    const int c0 = (int)(i - r * cpr) * 8;
+    uint4 o = make_uint4(0u, 0u, 0u, 0u);
+    if (c0 == 0) {
+      float g = __ldg(dy + r);
+      if (tanh_out) { const float v = __ldg(y + r); g *= 1.f - v * v; }
+      __nv_bfloat162 b0 = __floats2bfloat162_rn(g, 0.f);
+      o.x = *reinterpret_cast<uint32_t*>(&b0);
+    }
+    *reinterpret_cast<uint4*>(dz + r * cpad + c0) = o;
   }
 }
 
@@ -224,7 +244,7 @@ int32_t petsyn_concat_latent(const float* x, const float* zvec, void* out, int64
   PETSYN_REQUIRE(x && zvec && out, "null argument");
   PETSYN_REQUIRE(n > 0 && rows_per_sample > 0 && nz >= 0 && 1 + nz <= cpad && cpad % 8 == 0, "bad channel layout");
   const int64_t rows = rows_per_sample * n;
-  const int blocks = (int)std::min<int64_t>((rows + 255) / 256, 148 * 16);
+  const int blocks = (int)std::min<int64_t>((rows * (cpad / 8) + 255) / 256, 148 * 16);
   concat_latent_kernel<<<blocks, 256, 0, as_stream(stream)>>>(x, zvec, reinterpret_cast<__nv_bfloat16*>(out),
                                                               rows_per_sample, rows, nz, cpad);
   return check_launch("concat_latent_kernel");
@@ -240,7 +260,8 @@ int32_t petsyn_take_channel0(const float* src, float* y, int64_t rows, int32_t c
 int32_t petsyn_put_channel0_grad(const float* y, const float* dy, void* dz, int64_t rows, int32_t cpad,
                                  int32_t tanh_out, void* stream) {
   PETSYN_REQUIRE(dy && dz && rows > 0 && cpad > 0 && (!tanh_out || y), "bad argument");
-  const int blocks = (int)std::min<int64_t>((rows + 255) / 256, 148 * 16);
+  PETSYN_REQUIRE(cpad % 8 == 0, "padded channel count must be a multiple of 8");
+  const int blocks = (int)std::min<int64_t>((rows * (cpad / 8) + 255) / 256, 148 * 16);
   put_channel0_grad_kernel<<<blocks, 256, 0, as_stream(stream)>>>(y, dy, reinterpret_cast<__nv_bfloat16*>(dz), rows, cpad,
                                                                   tanh_out);
   return check_launch("put_channel0_grad_kernel");

@@ -189,6 +189,7 @@ struct Dev {   // device copy of petsyn_normact_desc with typed pointers
   float* dslope;
   const float *ka, *kb;   // per (sample, channel) backward constants of the affine/group path (nullptr: plain path)
   int dz_acc;
+  float* dz_colsum;       // optional [C] += column sums of dz
 };
 
 // ACT < 0: activation codes read from the descriptor at run time (rare combinations); ACT >= 0: act1 == act2 == ACT
@@ -300,6 +301,7 @@ __global__ void __launch_bounds__(256, 2) bwd_reduce_kernel(const Dev d) {
 
 template <int ACT>
 __global__ void __launch_bounds__(256, 2) bwd_apply_kernel(const Dev d) {
+  extern __shared__ float smem_f[];
   RowIter it(d.C);
   if (blockIdx.x == 0 && blockIdx.y == 0 && d.dgamma != nullptr && d.ka == nullptr) {
     for (int c = threadIdx.x; c < d.C; c += blockDim.x) {
@@ -307,7 +309,10 @@ __global__ void __launch_bounds__(256, 2) bwd_apply_kernel(const Dev d) {
       d.dgamma[c] = d.sums[d.C + c];
     }
   }
-  if (!it.active) return;
+  float csum[1][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) csum[0][i] = 0.f;
+  if (it.active) {
   const int s = blockIdx.y;
   const int64_t base = (int64_t)s * d.rows;
   const int so = d.per_sample ? s * d.C : 0;
@@ -375,6 +380,7 @@ __global__ void __launch_bounds__(256, 2) bwd_apply_kernel(const Dev d) {
         }
         o.v[i] = k0.v[i] * g - kA.v[i] - x.v[i] * kB.v[i];
         dr.v[i] = av.v[i] + bv.v[i];
+        csum[0][i] += o.v[i];
       }
       if (d.dz_acc) {
         const F8 old = load8(d.dz + r * d.C + it.tx * 8);
@@ -393,6 +399,8 @@ __global__ void __launch_bounds__(256, 2) bwd_apply_kernel(const Dev d) {
       }
     }
   }
+  }   // it.active
+  if (d.dz_colsum != nullptr) block_reduce_channels<1>(it, csum, smem_f, d.dz_colsum, d.C);
 }
 
 // GroupNorm / per-sample affine backward constants.  With S0 = sum g, S1 = sum g*zhat per (sample, channel):
@@ -491,6 +499,8 @@ static int32_t to_dev(const petsyn_normact_desc* d, Dev* o) {
   o->slope_dev = d->slope_dev; o->dslope = d->dslope;
   o->ka = o->kb = nullptr;
   o->dz_acc = d->dz_accumulate;
+  o->dz_colsum = d->dz_colsum;
+  PETSYN_REQUIRE(!(d->dz_colsum && d->dz_accumulate), "dz_colsum cannot be combined with dz_accumulate");
   return PETSYN_OK;
 }
 
@@ -578,7 +588,10 @@ int32_t petsyn_normact_bwd(const petsyn_normact_desc* desc, void* stream) {
       d.kb = kb;
     }
   }
-  PETSYN_NX_DISPATCH(bwd_apply_kernel, grid, 0, st, d);
+  {
+    const size_t apply_smem = d.dz_colsum ? (size_t)(256 / (d.C / 8)) * d.C * sizeof(float) : 0;
+    PETSYN_NX_DISPATCH(bwd_apply_kernel, grid, apply_smem, st, d);
+  }
   return check_launch("normact bwd_apply_kernel");
 }
 

@@ -269,30 +269,32 @@ __global__ void __launch_bounds__(128) covariate_bias_bwd_kernel(const float* __
                                                                  const float* __restrict__ dbias, float* __restrict__ dwv,
                                                                  float* __restrict__ dwo, float* __restrict__ dbo, int N,
                                                                  int Cctx, int C) {
-  extern __shared__ float sdv[];  // [N][C]
-  for (int e = threadIdx.x; e < N * C; e += blockDim.x) {
-    const int n = e / C, j = e % C;
+  // one block per channel c: row c of dWo, dbo[c], dv[:, c] and row c of dWv -- no dependency between blocks
+  extern __shared__ float sdv[];  // [N]: dv[n, c] = sum_c' Wo[c', c] * dbias[n, c']
+  const int c = blockIdx.x;
+  for (int j = threadIdx.x; j < C; j += blockDim.x) {
     float s = 0.f;
-    for (int c = 0; c < C; ++c) s += wo[c * C + j] * dbias[n * C + c];
-    sdv[e] = s;
+    for (int n = 0; n < N; ++n) s += dbias[n * C + c] * vbuf[n * C + j];
+    dwo[c * C + j] = s;
   }
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+  if (threadIdx.x == 0) {
     float s = 0.f;
     for (int n = 0; n < N; ++n) s += dbias[n * C + c];
     dbo[c] = s;
   }
-  for (int e = threadIdx.x; e < C * C; e += blockDim.x) {
-    const int c = e / C, j = e % C;
+  // dv[n, c]: warp w handles samples w, w + nwarps, ...; lanes split the c' sum
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  for (int n = warp; n < N; n += nwarps) {
     float s = 0.f;
-    for (int n = 0; n < N; ++n) s += dbias[n * C + c] * vbuf[n * C + j];
-    dwo[e] = s;
+    for (int cc = lane; cc < C; cc += 32) s += wo[cc * C + c] * dbias[n * C + cc];
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) sdv[n] = s;
   }
   __syncthreads();
-  for (int e = threadIdx.x; e < C * Cctx; e += blockDim.x) {
-    const int c = e / Cctx, j = e % Cctx;
+  for (int j = threadIdx.x; j < Cctx; j += blockDim.x) {
     float s = 0.f;
-    for (int n = 0; n < N; ++n) s += sdv[n * C + c] * ctx[n * Cctx + j];
-    dwv[e] = s;
+    for (int n = 0; n < N; ++n) s += sdv[n] * ctx[n * Cctx + j];
+    dwv[c * Cctx + j] = s;
   }
 }
 
@@ -387,7 +389,7 @@ int32_t petsyn_covariate_bias_bwd(const float* ctx, const float* wo, const float
   sample_colsum_kernel<<<grid, 256, 0, st>>>(CBFP(dtokens), dbias, rows_per_sample, c);
   int32_t rc = check_launch("sample_colsum_kernel");
   if (rc) return rc;
-  covariate_bias_bwd_kernel<<<1, 128, (size_t)n * c * sizeof(float), st>>>(ctx, wo, vbuf, dbias, dwv, dwo, dbo, n, cctx, c);
+  covariate_bias_bwd_kernel<<<c, 128, (size_t)n * sizeof(float), st>>>(ctx, wo, vbuf, dbias, dwv, dwo, dbo, n, cctx, c);
   return check_launch("covariate_bias_bwd_kernel");
 }
 

@@ -123,6 +123,7 @@ class ConvOp(Op):
             self.bias_stage = torch.zeros(self.cout, dtype=torch.float32, device=dev)
         self.dbias_stage = torch.zeros(self.cout, dtype=torch.float32, device=dev) if bias is not None else None
         self.acc_dx = False
+        self.colsum_done = False  # set by the NormActOp consuming z when it already summed dz over the rows (bias gradient)
         self.acc_dw = False      # add into grad_w / grad_b instead of overwriting (several backward calls per step)
         self._ver = None
         self.grad_w: Optional[torch.Tensor] = None     # set by the owner: where dW / dbias go
@@ -207,9 +208,12 @@ class ConvOp(Op):
                 self.plan.wgrad(self.x.buf.t, dz, self.grad_w, accumulate=self.acc_dw)
             if self.bias is not None:
                 if self.use_bias:
-                    cs, co = (self.out_sl.buf.c, self.out_sl.off) if self.out_sl is not None else (self.cout, 0)
-                    check(lib.petsyn_colsum(ptr(dz), cs, co, ptr(self.dbias_stage), dz.shape[0], self.cout,
-                                            stream_ptr()), "colsum")
+                    if self.colsum_done:
+                        self.colsum_done = False
+                    else:
+                        cs, co = (self.out_sl.buf.c, self.out_sl.off) if self.out_sl is not None else (self.cout, 0)
+                        check(lib.petsyn_colsum(ptr(dz), cs, co, ptr(self.dbias_stage), dz.shape[0], self.cout,
+                                                stream_ptr()), "colsum")
                     if self.acc_dw:
                         self.grad_b.add_(self.dbias_stage[:self.cout_w])
                     else:
@@ -233,6 +237,7 @@ class NormActOp(Op):
         assert kind in ("instance", "batch", "group", "none") and 1 <= len(dsts) <= 2
         self.gn = gn                            # nn.GroupNorm (kind == "group"): affine, num_groups, eps
         self.acc_dz = False
+        self.colsum_conv: Optional["ConvOp"] = None   # conv that produced z: its bias gradient is a by-product of bwd
         self.slope_param = slope_param          # nn.PReLU weight (one element): slope read from device memory
         self.grad_slope: Optional[torch.Tensor] = None
         self.z, self.kind, self.act, self.dsts, self.res, self.slope, self.bn, self.eps = z, kind, act, list(dsts), res, \
@@ -285,6 +290,8 @@ class NormActOp(Op):
             d.res_accumulate = int(self.acc_res)
         if backward:
             d.dz = ptr(z.g)
+            if self.colsum_conv is not None and not self.acc_dz:
+                d.dz_colsum = ptr(self.colsum_conv.dbias_stage)
             if self.grad_gamma is not None:
                 if self.acc_dw:
                     if self._tmp_gb is None:
@@ -333,6 +340,9 @@ class NormActOp(Op):
     def bwd(self) -> None:
         if self.grad_slope is not None and not self.acc_dw:
             self.grad_slope.zero_()
+        if self.colsum_conv is not None and not self.acc_dz:
+            self.colsum_conv.dbias_stage.zero_()
+            self.colsum_conv.colsum_done = True
         d = self._desc(True)
         check(lib.petsyn_normact_bwd(C.byref(d), stream_ptr()), "normact_bwd")
         if self.acc_dw and self.grad_gamma is not None:
@@ -494,6 +504,17 @@ class Tape:
                     op.acc_dz = covered
                 if not covered:
                     ranges.append((lo, hi))
+        # bias gradients as a by-product: a conv whose raw output z has exactly one gradient writer, a NormActOp's dz
+        writers: Dict[int, int] = {}
+        for op in self.ops:
+            for _, s in op.grad_writes():
+                writers[id(s.buf)] = writers.get(id(s.buf), 0) + 1
+        convs = {id(op.z): op for op in self.ops
+                 if isinstance(op, ConvOp) and op.z is not None and op.use_bias and op.need_dw and op.bias is not None}
+        for op in self.ops:
+            if isinstance(op, NormActOp):
+                c = convs.get(id(op.z))
+                op.colsum_conv = c if (c is not None and writers.get(id(op.z), 0) == 1 and not op.acc_dz) else None
         self._final = True
 
     def repack(self) -> None:

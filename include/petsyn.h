@@ -246,6 +246,9 @@ typedef struct petsyn_normact_desc {
   int32_t affine_accumulate; /* bwd: add into dgamma/dbeta (group/per-sample-affine path) */
   const float* slope_dev;    /* PETSYN_ACT_PRELU: device scalar holding the slope (MONAI ResidualUnit act="PRELU") */
   float* dslope;             /* bwd: d(loss)/d(slope) accumulated into this device scalar (caller-zeroed) */
+  float* dz_colsum;          /* bwd, optional: [c] += column sums of dz over all rows and samples (caller-zeroed) -- the bias
+                              * gradient of the convolution that produced z, as a by-product of the apply pass.  Not with
+                              * dz_accumulate */
 } petsyn_normact_desc;
 
 /* sums[sample][0:c] = sum z, sums[sample][c:2c] = sum z^2 (fp32, caller-zeroed). */
