@@ -61,6 +61,31 @@ __device__ __forceinline__ F8 splat(float x) {
   return r;
 }
 
+// Per-thread software pipeline: every thread prefetches ITS OWN 16-byte pieces of the next kPf - 1 row iterations into a
+// shared-memory ring with cp.async, so the bytes in flight live in shared memory instead of registers (a streaming
+// kernel needs ~64 KB in flight per SM to saturate HBM3e).  A slot is only ever touched by its owner: no barriers.
+constexpr int kPf = 4;
+struct PfRing {
+  uint32_t base;   // shared-memory address of this thread's slot 0
+  int nt;
+  __device__ PfRing(void* smem, int ntensors) : nt(ntensors) {
+    base = (uint32_t)__cvta_generic_to_shared(smem) + threadIdx.x * 16;
+  }
+  __device__ __forceinline__ void issue(int stage, int t, const void* g) const {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(base + (stage * nt + t) * 4096), "l"(g) : "memory");
+  }
+  __device__ __forceinline__ uint4 get(int stage, int t) const {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                 : "r"(base + (stage * nt + t) * 4096));
+    return v;
+  }
+  static __device__ __forceinline__ void commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+  static __device__ __forceinline__ void wait() { asm volatile("cp.async.wait_group %0;" ::"n"(kPf - 1) : "memory"); }
+  static __host__ __device__ size_t bytes(int ntensors) { return (size_t)kPf * ntensors * 4096; }
+};
+
 __device__ __forceinline__ float act_fwd(float b, int act, float slope) {
   switch (act) {
     case PETSYN_ACT_RELU: return fmaxf(b, 0.f);
@@ -114,7 +139,8 @@ __device__ __forceinline__ void block_reduce_channels(const RowIter& it, float (
 // sums[sample][0:C] += sum z, sums[sample][C:2C] += sum z^2
 __global__ void __launch_bounds__(256) stats_kernel(const __nv_bfloat16* __restrict__ z, float* __restrict__ sums,
                                                     int64_t rows, int C) {
-  extern __shared__ float smem_f[];
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  float* smem_f = reinterpret_cast<float*>(smem_raw + PfRing::bytes(1));
   RowIter it(C);
   z += (int64_t)blockIdx.y * rows * C;
   sums += (int64_t)blockIdx.y * 2 * C;
@@ -122,14 +148,25 @@ __global__ void __launch_bounds__(256) stats_kernel(const __nv_bfloat16* __restr
 #pragma unroll
   for (int i = 0; i < 8; ++i) acc[0][i] = acc[1][i] = 0.f;
   if (it.active) {
+    PfRing pf(smem_raw, 1);
     const int64_t stride = (int64_t)gridDim.x * it.rpp;
-    for (int64_t r = (int64_t)blockIdx.x * it.rpp + it.ty; r < rows; r += 2 * stride) {
-      F8 x0 = load8(z + r * C + it.tx * 8), x1 = splat(0.f);
-      if (r + stride < rows) x1 = load8(z + (r + stride) * C + it.tx * 8);
+    const int64_t r0 = (int64_t)blockIdx.x * it.rpp + it.ty;
+    const __nv_bfloat16* src = z + it.tx * 8;
+    for (int k = 0; k < kPf - 1; ++k) {
+      if (r0 + k * stride < rows) pf.issue(k, 0, src + (r0 + k * stride) * C);
+      PfRing::commit();
+    }
+    int k = 0;
+    for (int64_t r = r0; r < rows; r += stride, ++k) {
+      const int64_t rn = r + (kPf - 1) * stride;
+      if (rn < rows) pf.issue((k + kPf - 1) % kPf, 0, src + rn * C);
+      PfRing::commit();
+      PfRing::wait();
+      const F8 x0 = unpack8(pf.get(k % kPf, 0));
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        acc[0][i] += x0.v[i] + x1.v[i];
-        acc[1][i] += x0.v[i] * x0.v[i] + x1.v[i] * x1.v[i];
+        acc[0][i] += x0.v[i];
+        acc[1][i] += x0.v[i] * x0.v[i];
       }
     }
   }
@@ -196,6 +233,7 @@ struct Dev {   // device copy of petsyn_normact_desc with typed pointers
 // known at compile time (the common case), so the inner loop carries no switch.
 template <int ACT>
 __global__ void __launch_bounds__(256, 3) fwd_kernel(const Dev d) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
   RowIter it(d.C);
   if (!it.active) return;
   const int s = blockIdx.y;
@@ -206,40 +244,49 @@ __global__ void __launch_bounds__(256, 3) fwd_kernel(const Dev d) {
   const float slope = d.slope_dev ? __ldg(d.slope_dev) : d.slope;
   const int a1 = ACT >= 0 ? ACT : d.act1, a2 = ACT >= 0 ? ACT : d.act2;
   const int64_t stride = (int64_t)gridDim.x * it.rpp;
-  for (int64_t q0 = (int64_t)blockIdx.x * it.rpp + it.ty; q0 < d.rows; q0 += 2 * stride) {
-    // rows are visited in DESCENDING order: the pass that ran just before (statistics / backward reduction) read the
-    // tensor ascending, so its tail is what the 126 MB L2 still holds
-    const bool two = q0 + stride < d.rows;
-    const int64_t ra = base + (d.rows - 1 - q0), rb = ra - stride;
-    const F8 xa = load8(d.z + ra * d.C + it.tx * 8);
-    F8 xb = splat(0.f), rsa = splat(0.f), rsb = splat(0.f);
-    if (two) xb = load8(d.z + rb * d.C + it.tx * 8);
-    if (d.res) {
-      rsa = load8(d.res + ra * d.csr + d.cor + it.tx * 8);
-      if (two) rsb = load8(d.res + rb * d.csr + d.cor + it.tx * 8);
+  const bool has_res = d.res != nullptr;
+  PfRing pf(smem_raw, has_res ? 2 : 1);
+  // rows are visited in DESCENDING order: the pass that ran just before (statistics) read the tensor ascending, so its
+  // tail is what the 126 MB L2 still holds
+  const int64_t q0 = (int64_t)blockIdx.x * it.rpp + it.ty;
+  const __nv_bfloat16* zsrc = d.z + it.tx * 8;
+  const __nv_bfloat16* rsrc = has_res ? d.res + d.cor + it.tx * 8 : nullptr;
+  auto issue = [&](int k) {
+    const int64_t q = q0 + k * stride;
+    if (q < d.rows) {
+      const int64_t r = base + (d.rows - 1 - q);
+      pf.issue(k % kPf, 0, zsrc + r * d.C);
+      if (has_res) pf.issue(k % kPf, 1, rsrc + r * d.csr);
     }
+    PfRing::commit();
+  };
+  for (int k = 0; k < kPf - 1; ++k) issue(k);
+  int k = 0;
+  for (int64_t q = q0; q < d.rows; q += stride, ++k) {
+    issue(k + kPf - 1);
+    PfRing::wait();
+    const int64_t r = base + (d.rows - 1 - q);
+    const F8 x = unpack8(pf.get(k % kPf, 0));
+    F8 rs = splat(0.f);
+    if (has_res) rs = unpack8(pf.get(k % kPf, 1));
+    F8 o1, o2;
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      if (h == 1 && !two) break;
-      const F8& x = h ? xb : xa;
-      const F8& rs = h ? rsb : rsa;
-      const int64_t r = h ? rb : ra;
-      F8 o1, o2;
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float b = x.v[i] * sc.v[i] + sh.v[i];
-        o1.v[i] = act_fwd(b, a1, slope) + rs.v[i];
-        o2.v[i] = (ACT >= 0) ? o1.v[i] : act_fwd(b, a2, slope) + rs.v[i];
-      }
-      store8(d.t1 + r * d.cs1 + d.co1 + it.tx * 8, o1);
-      if (d.t2) store8(d.t2 + r * d.cs2 + d.co2 + it.tx * 8, o2);
+    for (int i = 0; i < 8; ++i) {
+      const float b = x.v[i] * sc.v[i] + sh.v[i];
+      o1.v[i] = act_fwd(b, a1, slope) + rs.v[i];
+      o2.v[i] = (ACT >= 0) ? o1.v[i] : act_fwd(b, a2, slope) + rs.v[i];
     }
+    store8(d.t1 + r * d.cs1 + d.co1 + it.tx * 8, o1);
+    if (d.t2) store8(d.t2 + r * d.cs2 + d.co2 + it.tx * 8, o2);
   }
 }
 
 template <int ACT>
 __global__ void __launch_bounds__(256, 2) bwd_reduce_kernel(const Dev d) {
-  extern __shared__ float smem_f[];
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  const bool has_t2 = d.t2 != nullptr;
+  const int nt = has_t2 ? 3 : 2;
+  float* smem_f = reinterpret_cast<float*>(smem_raw + PfRing::bytes(nt));
   RowIter it(d.C);
   const int s = blockIdx.y;
   const int64_t base = (int64_t)s * d.rows;
@@ -254,38 +301,41 @@ __global__ void __launch_bounds__(256, 2) bwd_reduce_kernel(const Dev d) {
     F8 sc = splat(1.f), sh = splat(0.f);
     if (d.scale) { sc = load8f(d.scale + so + it.tx * 8); sh = load8f(d.shift + so + it.tx * 8); }
     const int64_t stride = (int64_t)gridDim.x * it.rpp;
-    const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
-    for (int64_t r0 = (int64_t)blockIdx.x * it.rpp + it.ty; r0 < d.rows; r0 += 2 * stride) {
-      const int64_t ra = base + r0, rb = ra + stride;
-      const bool two = r0 + stride < d.rows;
-      uint4 xr[2], ar[2], br[2];
-      xr[0] = load_raw(d.z + ra * d.C + it.tx * 8);
-      ar[0] = load_raw(d.t1 + ra * d.cs1 + d.co1 + it.tx * 8);
-      br[0] = br[1] = xr[1] = ar[1] = zero;
-      if (d.t2) br[0] = load_raw(d.t2 + ra * d.cs2 + d.co2 + it.tx * 8);
-      if (two) {
-        xr[1] = load_raw(d.z + rb * d.C + it.tx * 8);
-        ar[1] = load_raw(d.t1 + rb * d.cs1 + d.co1 + it.tx * 8);
-        if (d.t2) br[1] = load_raw(d.t2 + rb * d.cs2 + d.co2 + it.tx * 8);
+    PfRing pf(smem_raw, nt);
+    const int64_t r0 = (int64_t)blockIdx.x * it.rpp + it.ty;
+    const __nv_bfloat16* zsrc = d.z + base * d.C + it.tx * 8;
+    const __nv_bfloat16* asrc = d.t1 + base * d.cs1 + d.co1 + it.tx * 8;
+    const __nv_bfloat16* bsrc = has_t2 ? d.t2 + base * d.cs2 + d.co2 + it.tx * 8 : nullptr;
+    auto issue = [&](int k) {
+      const int64_t r = r0 + k * stride;
+      if (r < d.rows) {
+        pf.issue(k % kPf, 0, zsrc + r * d.C);
+        pf.issue(k % kPf, 1, asrc + r * d.cs1);
+        if (has_t2) pf.issue(k % kPf, 2, bsrc + r * d.cs2);
       }
+      PfRing::commit();
+    };
+    for (int k = 0; k < kPf - 1; ++k) issue(k);
+    int k = 0;
+    for (int64_t r = r0; r < d.rows; r += stride, ++k) {
+      issue(k + kPf - 1);
+      PfRing::wait();
+      const F8 x = unpack8(pf.get(k % kPf, 0)), av = unpack8(pf.get(k % kPf, 1));
+      F8 bv = splat(0.f);
+      if (has_t2) bv = unpack8(pf.get(k % kPf, 2));
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        if (h == 1 && !two) break;
-        const F8 x = unpack8(xr[h]), av = unpack8(ar[h]), bv = unpack8(br[h]);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float b = x.v[i] * sc.v[i] + sh.v[i];
-          float g;
-          if (ACT >= 0) {
-            g = (av.v[i] + bv.v[i]) * act_grad(b, a1, slope);
-          } else {
-            g = av.v[i] * act_grad(b, a1, slope);
-            if (d.t2) g += bv.v[i] * act_grad(b, a2, slope);
-          }
-          acc[0][i] += g;
-          acc[1][i] += g * x.v[i];
-          if (d.dslope != nullptr && b < 0.f) dsl += (av.v[i] + bv.v[i]) * b;   // d PReLU / d slope = min(b, 0)
+      for (int i = 0; i < 8; ++i) {
+        const float b = x.v[i] * sc.v[i] + sh.v[i];
+        float g;
+        if (ACT >= 0) {
+          g = (av.v[i] + bv.v[i]) * act_grad(b, a1, slope);
+        } else {
+          g = av.v[i] * act_grad(b, a1, slope);
+          if (has_t2) g += bv.v[i] * act_grad(b, a2, slope);
         }
+        acc[0][i] += g;
+        acc[1][i] += g * x.v[i];
+        if (d.dslope != nullptr && b < 0.f) dsl += (av.v[i] + bv.v[i]) * b;   // d PReLU / d slope = min(b, 0)
       }
     }
     const F8 mu = load8f(d.mean + so + it.tx * 8), rs = load8f(d.rstd + so + it.tx * 8);
@@ -301,7 +351,8 @@ __global__ void __launch_bounds__(256, 2) bwd_reduce_kernel(const Dev d) {
 
 template <int ACT>
 __global__ void __launch_bounds__(256, 2) bwd_apply_kernel(const Dev d) {
-  extern __shared__ float smem_f[];
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  float* smem_f = reinterpret_cast<float*>(smem_raw + PfRing::bytes(d.t2 != nullptr ? 3 : 2));
   RowIter it(d.C);
   if (blockIdx.x == 0 && blockIdx.y == 0 && d.dgamma != nullptr && d.ka == nullptr) {
     for (int c = threadIdx.x; c < d.C; c += blockDim.x) {
@@ -348,55 +399,60 @@ __global__ void __launch_bounds__(256, 2) bwd_apply_kernel(const Dev d) {
   const float slope = d.slope_dev ? __ldg(d.slope_dev) : d.slope;
   const int a1 = ACT >= 0 ? ACT : d.act1, a2 = ACT >= 0 ? ACT : d.act2;
   const int64_t stride = (int64_t)gridDim.x * it.rpp;
-  const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
-  for (int64_t q0 = (int64_t)blockIdx.x * it.rpp + it.ty; q0 < d.rows; q0 += 2 * stride) {
-    const bool two = q0 + stride < d.rows;                          // descending row order (see fwd_kernel)
-    const int64_t ra = base + (d.rows - 1 - q0), rb = ra - stride;
-    uint4 xr[2], ar[2], br[2];
-    xr[0] = load_raw(d.z + ra * d.C + it.tx * 8);
-    ar[0] = load_raw(d.t1 + ra * d.cs1 + d.co1 + it.tx * 8);
-    br[0] = br[1] = xr[1] = ar[1] = zero;
-    if (d.t2) br[0] = load_raw(d.t2 + ra * d.cs2 + d.co2 + it.tx * 8);
-    if (two) {
-      xr[1] = load_raw(d.z + rb * d.C + it.tx * 8);
-      ar[1] = load_raw(d.t1 + rb * d.cs1 + d.co1 + it.tx * 8);
-      if (d.t2) br[1] = load_raw(d.t2 + rb * d.cs2 + d.co2 + it.tx * 8);
+  const bool has_t2 = d.t2 != nullptr;
+  PfRing pf(smem_raw, has_t2 ? 3 : 2);
+  const int64_t q0 = (int64_t)blockIdx.x * it.rpp + it.ty;              // descending row order (see fwd_kernel)
+  const __nv_bfloat16* zsrc = d.z + it.tx * 8;
+  const __nv_bfloat16* asrc = d.t1 + d.co1 + it.tx * 8;
+  const __nv_bfloat16* bsrc = has_t2 ? d.t2 + d.co2 + it.tx * 8 : nullptr;
+  auto issue = [&](int k) {
+    const int64_t q = q0 + k * stride;
+    if (q < d.rows) {
+      const int64_t r = base + (d.rows - 1 - q);
+      pf.issue(k % kPf, 0, zsrc + r * d.C);
+      pf.issue(k % kPf, 1, asrc + r * d.cs1);
+      if (has_t2) pf.issue(k % kPf, 2, bsrc + r * d.cs2);
     }
+    PfRing::commit();
+  };
+  for (int k = 0; k < kPf - 1; ++k) issue(k);
+  int k = 0;
+  for (int64_t q = q0; q < d.rows; q += stride, ++k) {
+    issue(k + kPf - 1);
+    PfRing::wait();
+    const int64_t r = base + (d.rows - 1 - q);
+    const F8 x = unpack8(pf.get(k % kPf, 0)), av = unpack8(pf.get(k % kPf, 1));
+    F8 bv = splat(0.f);
+    if (has_t2) bv = unpack8(pf.get(k % kPf, 2));
+    F8 o, dr;
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      if (h == 1 && !two) break;
-      const int64_t r = h ? rb : ra;
-      const F8 x = unpack8(xr[h]), av = unpack8(ar[h]), bv = unpack8(br[h]);
-      F8 o, dr;
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float b = x.v[i] * sc.v[i] + sh.v[i];
-        float g;
-        if (ACT >= 0) {
-          g = (av.v[i] + bv.v[i]) * act_grad(b, a1, slope);
-        } else {
-          g = av.v[i] * act_grad(b, a1, slope);
-          if (d.t2) g += bv.v[i] * act_grad(b, a2, slope);
-        }
-        o.v[i] = k0.v[i] * g - kA.v[i] - x.v[i] * kB.v[i];
-        dr.v[i] = av.v[i] + bv.v[i];
-        csum[0][i] += o.v[i];
+    for (int i = 0; i < 8; ++i) {
+      const float b = x.v[i] * sc.v[i] + sh.v[i];
+      float g;
+      if (ACT >= 0) {
+        g = (av.v[i] + bv.v[i]) * act_grad(b, a1, slope);
+      } else {
+        g = av.v[i] * act_grad(b, a1, slope);
+        if (has_t2) g += bv.v[i] * act_grad(b, a2, slope);
       }
-      if (d.dz_acc) {
-        const F8 old = load8(d.dz + r * d.C + it.tx * 8);
+      o.v[i] = k0.v[i] * g - kA.v[i] - x.v[i] * kB.v[i];
+      dr.v[i] = av.v[i] + bv.v[i];
+      csum[0][i] += o.v[i];
+    }
+    if (d.dz_acc) {
+      const F8 old = load8(d.dz + r * d.C + it.tx * 8);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) o.v[i] += old.v[i];
-      }
-      store8(d.dz + r * d.C + it.tx * 8, o);
-      if (d.res) {
-        __nv_bfloat16* p = d.res + r * d.csr + d.cor + it.tx * 8;
-        if (d.res_acc) {
-          const F8 old = load8(p);
+      for (int i = 0; i < 8; ++i) o.v[i] += old.v[i];
+    }
+    store8(d.dz + r * d.C + it.tx * 8, o);
+    if (d.res) {
+      __nv_bfloat16* p = d.res + r * d.csr + d.cor + it.tx * 8;
+      if (d.res_acc) {
+        const F8 old = load8(p);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) dr.v[i] += old.v[i];
-        }
-        store8(p, dr);
+        for (int i = 0; i < 8; ++i) dr.v[i] += old.v[i];
       }
+      store8(p, dr);
     }
   }
   }   // it.active
@@ -511,15 +567,25 @@ using namespace petsyn;
 using namespace petsyn::nx;
 
 // compile-time activation when both destinations share it (always true for the module mirrors), run-time otherwise
+#define PETSYN_NX_CASE(KERNEL, A, GRID, SMEM, ST, D)                                                         \
+  {                                                                                                          \
+    static bool attr_ = false;                                                                               \
+    if (!attr_) {                                                                                            \
+      PETSYN_CHECK_CUDA(cudaFuncSetAttribute(KERNEL<A>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024)); \
+      attr_ = true;                                                                                          \
+    }                                                                                                        \
+    KERNEL<A><<<GRID, 256, SMEM, ST>>>(D);                                                                   \
+  }                                                                                                          \
+  break;
 #define PETSYN_NX_DISPATCH(KERNEL, GRID, SMEM, ST, D)                                         \
   do {                                                                                        \
     const int _a = ((D).t2 == nullptr || (D).act1 == (D).act2) ? (D).act1 : -1;               \
     switch (_a) {                                                                             \
-      case PETSYN_ACT_NONE: KERNEL<PETSYN_ACT_NONE><<<GRID, 256, SMEM, ST>>>(D); break;       \
-      case PETSYN_ACT_RELU: KERNEL<PETSYN_ACT_RELU><<<GRID, 256, SMEM, ST>>>(D); break;       \
-      case PETSYN_ACT_LRELU: KERNEL<PETSYN_ACT_LRELU><<<GRID, 256, SMEM, ST>>>(D); break;     \
-      case PETSYN_ACT_SILU: KERNEL<PETSYN_ACT_SILU><<<GRID, 256, SMEM, ST>>>(D); break;       \
-      default: KERNEL<-1><<<GRID, 256, SMEM, ST>>>(D); break;                                 \
+      case PETSYN_ACT_NONE: PETSYN_NX_CASE(KERNEL, PETSYN_ACT_NONE, GRID, SMEM, ST, D)        \
+      case PETSYN_ACT_RELU: PETSYN_NX_CASE(KERNEL, PETSYN_ACT_RELU, GRID, SMEM, ST, D)        \
+      case PETSYN_ACT_LRELU: PETSYN_NX_CASE(KERNEL, PETSYN_ACT_LRELU, GRID, SMEM, ST, D)      \
+      case PETSYN_ACT_SILU: PETSYN_NX_CASE(KERNEL, PETSYN_ACT_SILU, GRID, SMEM, ST, D)        \
+      default: PETSYN_NX_CASE(KERNEL, -1, GRID, SMEM, ST, D)                                  \
     }                                                                                         \
   } while (0)
 
@@ -529,7 +595,7 @@ int32_t petsyn_norm_stats(const void* z, float* sums, int64_t rows, int32_t c, i
   PETSYN_REQUIRE(z && sums && rows > 0 && nsamples >= 1, "bad argument");
   PETSYN_REQUIRE(c % 8 == 0 && c >= 8 && c <= 2048, "channels must be a multiple of 8 in [8, 2048]");
   const int rpp = 256 / (c / 8);
-  const size_t smem = (size_t)rpp * 2 * c * sizeof(float);
+  const size_t smem = PfRing::bytes(1) + (size_t)rpp * 2 * c * sizeof(float);
   dim3 grid((unsigned)row_blocks(rows, c, nsamples), (unsigned)nsamples);
   stats_kernel<<<grid, 256, smem, as_stream(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(z), sums, rows, c);
   return check_launch("stats_kernel");
@@ -554,7 +620,7 @@ int32_t petsyn_normact_fwd(const petsyn_normact_desc* desc, void* stream) {
   if (rc) return rc;
   PETSYN_REQUIRE(d.t1 != nullptr, "missing destination");
   dim3 grid((unsigned)row_blocks(d.rows, d.C, desc->nsamples), (unsigned)desc->nsamples);
-  PETSYN_NX_DISPATCH(fwd_kernel, grid, 0, as_stream(stream), d);
+  PETSYN_NX_DISPATCH(fwd_kernel, grid, PfRing::bytes(d.res ? 2 : 1), as_stream(stream), d);
   return check_launch("normact fwd_kernel");
 }
 
@@ -570,7 +636,7 @@ int32_t petsyn_normact_bwd(const petsyn_normact_desc* desc, void* stream) {
     const int nst = d.per_sample ? desc->nsamples : 1;
     PETSYN_CHECK_CUDA(cudaMemsetAsync(d.sums, 0, (size_t)nst * 2 * d.C * sizeof(float), st));
     const int rpp = 256 / (d.C / 8);
-    const size_t smem = (size_t)rpp * 2 * d.C * sizeof(float);
+    const size_t smem = PfRing::bytes(d.t2 ? 3 : 2) + (size_t)rpp * 2 * d.C * sizeof(float);
     PETSYN_NX_DISPATCH(bwd_reduce_kernel, grid, smem, st, d);
     rc = check_launch("normact bwd_reduce_kernel");
     if (rc) return rc;
@@ -589,7 +655,7 @@ int32_t petsyn_normact_bwd(const petsyn_normact_desc* desc, void* stream) {
     }
   }
   {
-    const size_t apply_smem = d.dz_colsum ? (size_t)(256 / (d.C / 8)) * d.C * sizeof(float) : 0;
+    const size_t apply_smem = PfRing::bytes(d.t2 ? 3 : 2) + (d.dz_colsum ? (size_t)(256 / (d.C / 8)) * d.C * sizeof(float) : 0);
     PETSYN_NX_DISPATCH(bwd_apply_kernel, grid, apply_smem, st, d);
   }
   return check_launch("normact bwd_apply_kernel");
