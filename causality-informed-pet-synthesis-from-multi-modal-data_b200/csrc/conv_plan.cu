@@ -357,6 +357,7 @@ struct GemmSide {           // one gather-form GEMM (fprop or dgrad)
   IgemmParams params;
   // small-channel slab path (slab_kernels.cuh): k3 s1 p1, 16..64 channels, many voxels
   bool slab = false;
+  int slab_halo = 1;        // 1: 3x3x3, 0: 1x1x1
   int slab_grid = 0, slab_smem = 0;
   SlabParams sparams;
 };
@@ -390,7 +391,8 @@ struct petsyn_conv_plan {
   petsyn::WgradSmallParams wgs_params;
   const void* wg_key_x = nullptr; const void* wg_key_g = nullptr; const void* wg_key_s = nullptr;
   petsyn::WgradParams wg_params;
-  bool wg_slab = false;         // slab path (slab_wgrad_kernel): k3 s1 p1, Cin <= 48, many voxels
+  bool wg_slab = false;         // slab path (slab_wgrad_kernel): k3 s1 p1 or k1, Cin <= 96, many voxels
+  int wg_slab_halo = 1;
   int wg_slab_grid = 0, wg_slab_smem = 0;
   petsyn::SlabWgradParams wgl_params;
 };
@@ -441,7 +443,7 @@ static void slab_split(int W, int H, int D, int N, int tile_w, int tile_h, int c
   *items = cols * *nchunks;
 }
 
-static int32_t finish_side(GemmSide& g, int N, bool allow_slab = false) {
+static int32_t finish_side(GemmSide& g, int N, int allow_slab = 0 /* 0 no, 1 = k3 s1 p1, 2 = k1 s1 p0 */) {
   g.kch = 64;
   g.kc_pad = (g.Kc + g.kch - 1) / g.kch * g.kch;
   if (g.R >= 128) g.block_n = 128;
@@ -481,10 +483,11 @@ static int32_t finish_side(GemmSide& g, int N, bool allow_slab = false) {
     g.subs.push_back(sub);
   }
   if (allow_slab && (!g.out_fp32 || g.R <= 32) && g.Kc % 16 == 0 && g.Kc <= 64 && g.R % 16 == 0 && g.R <= 64 &&
-      slab_smem_bytes(27, g.Kc / 16, g.R, ((g.Kc / 16) * kSlabWp * kSlabHp * 32 + 1023) / 1024 * 1024, 4, g.out_fp32 ? 4 : 2) <=
-          224 * 1024 &&
+      slab_smem_bytes(allow_slab == 1 ? 27 : 1, g.Kc / 16, g.R, ((g.Kc / 16) * kSlabWp * kSlabHp * 32 + 1023) / 1024 * 1024, 4,
+                      g.out_fp32 ? 4 : 2) <= 224 * 1024 &&
       (int64_t)g.out_w * g.out_h * g.out_d * N >= 128 * 148) {
     g.slab = true;
+    g.slab_halo = allow_slab == 1 ? 1 : 0;
     g.ksplit = 1;
     g.block_n = g.R;
   }
@@ -515,7 +518,8 @@ static int32_t bind_slab(GemmSide& g, const ViewSpec& va, const ViewSpec& vc, co
   p.reduce = g.accumulate ? 1 : 0;
   if (g.key_a == a && g.key_b == b && g.key_c == c) return PETSYN_OK;
   const int atoms = g.Kc / 16;
-  int32_t rc = slab_view_map(&p.a_map, a, va, atoms, kSlabWp, kSlabHp);
+  const int halo = g.slab_halo;
+  int32_t rc = slab_view_map(&p.a_map, a, va, atoms, kSlabW + 2 * halo, kSlabH + 2 * halo);
   if (rc) return rc;
   {
     uint64_t dims[2] = {(uint64_t)g.prog.max_taps * g.kc_pad, (uint64_t)g.subs.size() * g.R};
@@ -528,8 +532,9 @@ static int32_t bind_slab(GemmSide& g, const ViewSpec& va, const ViewSpec& vc, co
                 g.out_fp32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, g.R, kSlabW, kSlabH, 1, 0);
   p.out_f32 = g.out_fp32 ? 1 : 0;
   if (rc) return rc;
-  if (g.prog.subs.size() != 1 || g.prog.subs[0].size() != 27) return fail(PETSYN_EINVAL, "slab path needs one 27-tap program");
-  for (int t = 0; t < 27; ++t) {
+  if (g.prog.subs.size() != 1 || (int)g.prog.subs[0].size() != (halo ? 27 : 1))
+    return fail(PETSYN_EINVAL, "slab path needs one 27-tap (k3) or 1-tap (k1) program");
+  for (int t = 0; t < (halo ? 27 : 0); ++t) {
     const TapDef& td = g.prog.subs[0][t];
     if (td.dd != g.prog.subs[0][t / 9 * 9].dd) return fail(PETSYN_EINVAL, "slab path: taps are not grouped by depth offset");
     p.tap_off[t] = (((td.dh + 1) * atoms) * (kSlabWp * 32) + (td.dw + 1) * 32) >> 4;
@@ -540,7 +545,8 @@ static int32_t bind_slab(GemmSide& g, const ViewSpec& va, const ViewSpec& vc, co
   p.W = va.W; p.H = va.H; p.D = va.D; p.batch = va.N;
   p.tiles_w = (va.W + kSlabW - 1) / kSlabW;
   p.tiles_h = (va.H + kSlabH - 1) / kSlabH;
-  p.slab_tx = atoms * kSlabWp * kSlabHp * 32;
+  p.halo = halo;
+  p.slab_tx = atoms * (kSlabW + 2 * halo) * (kSlabH + 2 * halo) * 32;
   p.slab_bytes = (p.slab_tx + 1023) / 1024 * 1024;
   // ring depth and CTAs per SM from the shared-memory budget
   const int fixed = slab_smem_bytes(p.ntaps, atoms, g.R, p.slab_bytes, 0, g.out_fp32 ? 4 : 2);
@@ -933,7 +939,8 @@ int32_t petsyn_conv_plan_create(const petsyn_conv_desc* d, petsyn_conv_plan** ou
   f.out_h = f.prog.out_phased ? oh / 2 : oh;
   f.out_d = f.prog.out_phased ? od / 2 : od;
   f.out_rows_full = (int64_t)d->n * od * oh * ow;
-  const bool slab_ok = d->op == PETSYN_OP_CONV && k == 3 && s == 1 && p == 1;
+  const int slab_ok = (d->op == PETSYN_OP_CONV && k == 3 && s == 1 && p == 1) ? 1
+                      : (d->op == PETSYN_OP_CONV && k == 1 && s == 1 && p == 0) ? 2 : 0;
   int32_t rc = finish_side(f, d->n, slab_ok);
   GemmSide& g = pl->dgrad;
   if (!rc) {
@@ -981,6 +988,7 @@ int32_t petsyn_conv_plan_create(const petsyn_conv_desc* d, petsyn_conv_plan** ou
       ks2 = std::max<int64_t>(1, std::min<int64_t>(ks2, std::max<int64_t>(1, nboxes / 8)));
       pl->wg_ksplit = (int)ks2;
     }
+    pl->wg_slab_halo = slab_ok == 1 ? 1 : 0;
     if (slab_ok && d->cin % 16 == 0 && d->cin <= 96 && d->cout % 16 == 0 && d->cout <= 64 &&
         (int64_t)d->w * d->h * d->d * d->n >= 32768) {
       pl->wg_slab = true;
@@ -1041,7 +1049,8 @@ size_t petsyn_conv_wgrad_scratch_bytes(const petsyn_conv_plan* pl) {
   if (!pl) return 0;
   if (pl->wg_slab) {
     const int atoms = pl->desc.cin / 16, groups = (atoms + 2) / 3, apg = (atoms + groups - 1) / groups;
-    return (size_t)groups * (pl->desc.cout / 16) * 3 * 48 * (3 * apg * 16) * sizeof(float);
+    const int nacc = pl->wg_slab_halo ? 3 : 1;
+    return (size_t)groups * (pl->desc.cout / 16) * nacc * 48 * (nacc * apg * 16) * sizeof(float);
   }
   if (pl->wg_small) return (size_t)pl->fprop.subs.size() * pl->wg_mtiles * 128 * pl->wg_npad * sizeof(float);
   return packed_bytes(pl->fprop) * 2;
@@ -1189,10 +1198,11 @@ int32_t petsyn_conv_wgrad(petsyn_conv_plan* pl, const void* x, const void* dy, v
     const int atoms_total = pl->desc.cin / 16, co_atoms = pl->desc.cout / 16;
     const int groups = (atoms_total + 2) / 3;              // <= 3 atoms (48 channels) per CTA: 3 accumulators x 144 TMEM columns
     const int atoms = (atoms_total + groups - 1) / groups; // atoms per group; a short last group reads zero-filled atoms
-    const int ncols = 3 * atoms * 16;
+    const int hh = pl->wg_slab_halo, nacc = hh ? 3 : 1;
+    const int ncols = nacc * atoms * 16;
     if (!(pl->wg_key_x == x && pl->wg_key_g == dy && pl->wg_key_s == scratch)) {
       memset(&q, 0, sizeof(q));
-      int32_t rc = slab_view_map(&q.x_map, x, pl->vx, atoms_total, kWgW, kWgH + 2, atoms);
+      int32_t rc = slab_view_map(&q.x_map, x, pl->vx, atoms_total, kWgW, kWgH + 2 * hh, atoms);
       if (rc) return rc;
       {
         const ViewSpec& v = pl->vdy;
@@ -1209,17 +1219,18 @@ int32_t petsyn_conv_wgrad(petsyn_conv_plan* pl, const void* x, const void* dy, v
       q.W = pl->desc.w; q.H = pl->desc.h; q.D = pl->desc.d; q.batch = pl->desc.n;
       q.tiles_w = (q.W + kWgW - 1) / kWgW;
       q.tiles_h = (q.H + kWgH - 1) / kWgH;
-      q.xslab_tx = atoms * kWgW * (kWgH + 2) * 32;
+      q.halo = hh;
+      q.xslab_tx = atoms * kWgW * (kWgH + 2 * hh) * 32;
       q.xslab_bytes = (q.xslab_tx + 1023) / 1024 * 1024;
       q.gslab_tx = (kWgW + 2) * kWgH * 32;
       q.gslab_bytes = (q.gslab_tx + 7 * 32 + 1023) / 1024 * 1024;   // M atoms 3..7 read past the last row: keep it in bounds
       q.acc_stride = ncols;
-      q.tmem_cols = 3 * ncols <= 256 ? 256 : 512;
+      q.tmem_cols = nacc * ncols <= 64 ? 64 : (nacc * ncols <= 128 ? 128 : (nacc * ncols <= 256 ? 256 : 512));
       q.gring = 4;
-      const int cap = (q.tmem_cols == 256 ? 110 : 200) * 1024;
+      const int cap = (q.tmem_cols <= 256 ? 110 : 200) * 1024;
       q.xring = slab_wgrad_smem_bytes(q.xslab_bytes, q.gslab_bytes, ncols, 8, q.gring) <= cap ? 8 : 4;
       pl->wg_slab_smem = slab_wgrad_smem_bytes(q.xslab_bytes, q.gslab_bytes, ncols, q.xring, q.gring);
-      const int occ = q.tmem_cols == 256 ? std::max(1, std::min(2, (227 * 1024) / (pl->wg_slab_smem + 1024))) : 1;
+      const int occ = q.tmem_cols <= 256 ? std::max(1, std::min(2, (227 * 1024) / (pl->wg_slab_smem + 1024))) : 1;
       const int ctas = std::max(1, 148 * occ / (co_atoms * groups));
       slab_split(q.W, q.H, q.D, q.batch, kWgW, kWgH, ctas, &q.dchunk, &q.nchunks, &q.items);
       pl->wg_slab_grid = std::min(ctas, q.items);
@@ -1231,9 +1242,9 @@ int32_t petsyn_conv_wgrad(petsyn_conv_plan* pl, const void* x, const void* dy, v
     slab_wgrad_kernel<<<grid, 192, pl->wg_slab_smem, st>>>(q);
     int32_t rc = check_launch("slab_wgrad_kernel");
     if (rc) return rc;
-    const int total = pl->desc.cout * pl->desc.cin * 27;
+    const int total = pl->desc.cout * pl->desc.cin * pl->k3;
     slab_wgrad_unpack_kernel<<<std::min((total + 255) / 256, 148 * 8), 256, 0, st>>>(
-        reinterpret_cast<const float*>(scratch), dw, pl->desc.cout, pl->desc.cin, atoms, accumulate);
+        reinterpret_cast<const float*>(scratch), dw, pl->desc.cout, pl->desc.cin, atoms, pl->k3, accumulate);
     return check_launch("slab_wgrad_unpack_kernel");
   }
   if (pl->wg_small) {

@@ -51,6 +51,7 @@ struct alignas(64) SlabParams {
   float epi_slope;
   int32_t reduce;       // 1: add into the destination (bf16 TMA reduction)
   int32_t out_f32;      // 1: fp32 output (the one-channel network head keeps full precision), c_map is an fp32 map
+  int32_t halo;         // 1: 3x3x3 conv (27 taps over three 10x18 slabs); 0: 1x1x1 conv (one tap, one 8x16 slab per tile)
 };
 
 // tcgen05.mma with the 64-bit shared-memory descriptors given as (lo, hi) halves: the MMA-issuing thread only ever
@@ -146,23 +147,25 @@ __global__ void __launch_bounds__(192) slab_conv_kernel(const __grid_constant__ 
         const int nb = t;
         const int d0 = ch * p.dchunk;
         const int len = min(p.dchunk, p.D - d0);
-        for (int s = 0; s < len + 2; ++s, ++seq) {
+        for (int s = 0; s < len + 2 * p.halo; ++s, ++seq) {
           const int slot = seq & Rm;
           const uint32_t ph = (seq / uint32_t(R)) & 1;
           ptx::mbar_wait(&empty_bar[slot], ph ^ 1);
-          const int d = d0 - 1 + s;
+          const int d = d0 - p.halo + s;
           const bool oob = d < 0 || d >= p.D;
           ptx::mbar_expect_tx(&full_bar[slot], uint32_t(p.slab_tx));
           // a depth slice outside the volume must read zeros, not the neighbouring sample: push the box out of range in w
-          ptx::tma_load_5d(s_ring + slot * p.slab_bytes, &p.a_map, &full_bar[slot], 0, oob ? p.W + 64 : tw * kSlabW - 1, 0,
-                           th * kSlabH - 1, oob ? 0 : nb * p.D + d);
+          ptx::tma_load_5d(s_ring + slot * p.slab_bytes, &p.a_map, &full_bar[slot], 0, oob ? p.W + 64 : tw * kSlabW - p.halo,
+                           0, th * kSlabH - p.halo, oob ? 0 : nb * p.D + d);
         }
       }
     }
   } else if (warp == 1) {
     if (ptx::elect_one()) {
       // ---------------- MMA issuer ----------------
-      const uint64_t a_desc_base = ptx::umma_desc_base(16, uint32_t(ATOMS * kSlabWp * 32), 6);   // K-major, 32B swizzle
+      const uint32_t wp = kSlabW + 2 * p.halo;             // voxels per slab row
+      const uint32_t nslab = 1 + 2 * p.halo;               // slabs a tile reads
+      const uint64_t a_desc_base = ptx::umma_desc_base(16, uint32_t(ATOMS) * wp * 32, 6);   // K-major, 32B swizzle
       const uint64_t b_desc_base = ptx::umma_desc_base(16, 256, 6);
       const uint32_t a_hi = uint32_t(a_desc_base >> 32), a_lo0 = uint32_t(a_desc_base);
       const uint32_t b_hi = uint32_t(b_desc_base >> 32), b_lo0 = uint32_t(b_desc_base);
@@ -179,7 +182,7 @@ __global__ void __launch_bounds__(192) slab_conv_kernel(const __grid_constant__ 
         const int len = min(p.dchunk, p.D - ch * p.dchunk);
         for (int t = 0; t < len; ++t, ++tile) {
           // slabs seq+t .. seq+t+2 must have landed (the first tile of an item waits for all three)
-          for (int s2 = (t == 0 ? 0 : 2); s2 < 3; ++s2) {
+          for (uint32_t s2 = (t == 0 ? 0 : nslab - 1); s2 < nslab; ++s2) {
             const uint32_t q = seq + t + s2;
             ptx::mbar_wait(&full_bar[q & Rm], (q >> rshift) & 1);
           }
@@ -191,6 +194,13 @@ __global__ void __launch_bounds__(192) slab_conv_kernel(const __grid_constant__ 
 #pragma unroll
           for (int s2 = 0; s2 < 3; ++s2) slab_lo[s2] = ring_lo + ((seq + t + s2) & Rm) * slab16;
           uint32_t b_lo = w_lo;
+          if (p.halo == 0) {
+#pragma unroll
+            for (int q = 0; q < ATOMS; ++q) {
+              umma_bf16_split(acc, slab_lo[0] + q * (kSlabW * 2), a_hi, b_lo, b_hi, idesc, q != 0 ? 1u : 0u);
+              b_lo += bstep;
+            }
+          } else {
 #pragma unroll
           for (int g = 0; g < 3; ++g) {
             const int sl = p.tap_slab[g];
@@ -205,14 +215,15 @@ __global__ void __launch_bounds__(192) slab_conv_kernel(const __grid_constant__ 
               }
             }
           }
+          }
           ptx::umma_commit(&acc_full[buf]);
           ptx::umma_commit(&empty_bar[(seq + t) & Rm]);     // the oldest slab is no longer needed
-          if (t == len - 1) {
+          if (t == len - 1 && p.halo) {
             ptx::umma_commit(&empty_bar[(seq + t + 1) & Rm]);
             ptx::umma_commit(&empty_bar[(seq + t + 2) & Rm]);
           }
         }
-        seq += len + 2;
+        seq += len + 2 * p.halo;
       }
     }
   } else {
@@ -308,6 +319,7 @@ struct alignas(64) SlabWgradParams {
   int32_t xslab_tx, gslab_tx;
   int32_t xring, gring;               // ring depths: 4 or 8 / 2 or 4 (powers of two)
   int32_t tmem_cols, acc_stride;      // TMEM allocation (power of two) and column pitch of the three accumulators
+  int32_t halo;                       // 1: 3x3x3 (27 taps); 0: 1x1x1 (one tap: no halo, one accumulator, ncols = atoms * 16)
 };
 
 __host__ __device__ inline int slab_wgrad_smem_bytes(int xslab_bytes, int gslab_bytes, int ncols, int xring, int gring) {
@@ -326,7 +338,9 @@ __device__ __forceinline__ void bulk_reduce_add_f32(float* gdst, const void* ssr
 __global__ void __launch_bounds__(192) slab_wgrad_kernel(const __grid_constant__ SlabWgradParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const int ncols = 3 * p.atoms * 16;
+  const int hh = p.halo;
+  const int nacc = hh ? 3 : 1;
+  const int ncols = nacc * p.atoms * 16;
   const int stg_bytes = (48 * ncols * 4 + 1023) / 1024 * 1024;
   const int XR = p.xring, GR = p.gring;
   const int ring_bytes = XR * p.xslab_bytes + GR * p.gslab_bytes;
@@ -376,27 +390,27 @@ __global__ void __launch_bounds__(192) slab_wgrad_kernel(const __grid_constant__
         const int d0 = ch * p.dchunk;
         const int len = min(p.dchunk, p.D - d0);
         // interleave: x slabs d0-1, d0, then per output slice: x slab d+1 and dy slab d
-        for (int s = 0; s < len + 2; ++s) {
+        for (int s = 0; s < len + 2 * hh; ++s) {
           {
             const int slot = xseq & (XR - 1);
             ptx::mbar_wait(&xempty[slot], ((xseq / uint32_t(XR)) & 1) ^ 1);
-            const int d = d0 - 1 + s;
+            const int d = d0 - hh + s;
             const bool oob = d < 0 || d >= p.D;
             ptx::mbar_expect_tx(&xfull[slot], uint32_t(p.xslab_tx));
             ptx::tma_load_5d(s_x + slot * p.xslab_bytes, &p.x_map, &xfull[slot], 0, oob ? p.W + 64 : tw * kWgW,
-                             cig * p.atoms, th * kWgH - 1, oob ? 0 : nb * p.D + d);
+                             cig * p.atoms, th * kWgH - hh, oob ? 0 : nb * p.D + d);
             ++xseq;
           }
-          if (s >= 2) {
+          if (s >= 2 * hh) {
             const int slot = gseq & (GR - 1);
             ptx::mbar_wait(&gempty[slot], ((gseq / uint32_t(GR)) & 1) ^ 1);
-            const int d = d0 + s - 2;
+            const int d = d0 + s - 2 * hh;
             ptx::mbar_expect_tx(&gfull[slot], uint32_t(p.gslab_tx));
             asm volatile(
                 "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], "
                 "[%2];" ::"r"(ptx::smem_u32(s_g + slot * p.gslab_bytes)),
                 "l"(reinterpret_cast<uint64_t>(&p.g_map)), "r"(ptx::smem_u32(&gfull[slot])), "r"(coa * 16),
-                "r"(tw * kWgW - 1), "r"(th * kWgH), "r"(nb * p.D + d)
+                "r"(tw * kWgW - hh), "r"(th * kWgH), "r"(nb * p.D + d)
                 : "memory");
             ++gseq;
           }
@@ -423,7 +437,7 @@ __global__ void __launch_bounds__(192) slab_wgrad_kernel(const __grid_constant__
         const int ch = (item / (p.tiles_w * p.tiles_h)) % p.nchunks;
         const int len = min(p.dchunk, p.D - ch * p.dchunk);
         for (int t = 0; t < len; ++t) {
-          for (int s2 = (t == 0 ? 0 : 2); s2 < 3; ++s2) {
+          for (int s2 = (t == 0 ? 0 : nacc - 1); s2 < nacc; ++s2) {
             const uint32_t q = xseq + t + s2;
             ptx::mbar_wait(&xfull[q & XRm], (q >> xshift) & 1);
           }
@@ -432,6 +446,7 @@ __global__ void __launch_bounds__(192) slab_wgrad_kernel(const __grid_constant__
           const uint32_t g0 = g_lo + (gseq & GRm) * gslab16;
 #pragma unroll
           for (int c = 0; c < 3; ++c) {
+            if (c >= nacc) break;
             const uint32_t x0 = x_lo + ((xseq + t + c) & XRm) * xslab16;
             const uint32_t acc = tmem_base + c * p.acc_stride;
 #pragma unroll
@@ -443,13 +458,13 @@ __global__ void __launch_bounds__(192) slab_wgrad_kernel(const __grid_constant__
           started = 1;
           ptx::umma_commit(&gempty[gseq & GRm]);
           ptx::umma_commit(&xempty[(xseq + t) & XRm]);
-          if (t == len - 1) {
+          if (t == len - 1 && hh) {
             ptx::umma_commit(&xempty[(xseq + t + 1) & XRm]);
             ptx::umma_commit(&xempty[(xseq + t + 2) & XRm]);
           }
           ++gseq;
         }
-        xseq += len + 2;
+        xseq += len + 2 * hh;
       }
       ptx::umma_commit(done_bar);
     }
@@ -461,7 +476,7 @@ __global__ void __launch_bounds__(192) slab_wgrad_kernel(const __grid_constant__
     // rows (lanes) 0..47 hold (i = 2 - a, co); warps 2 and 3 own TMEM lanes 64..127 / 96..127 -> use quads 0 and 1:
     // warp 4 reads lanes 0..31 (quad 0), warp 5 reads lanes 32..63 (quad 1, only 32..47 are useful).
     float* stg = reinterpret_cast<float*>(smem);
-    for (int c = 0; c < 3; ++c) {
+    for (int c = 0; c < nacc; ++c) {
       if (warp == 4 || warp == 5) {
         const int quad = warp & 3;
         const int row = quad * 32 + (tid & 31);
@@ -480,7 +495,7 @@ __global__ void __launch_bounds__(192) slab_wgrad_kernel(const __grid_constant__
       }
       named_bar_sync(1, 128);
       if (warp == 4 && (tid & 31) == 0) {
-        bulk_reduce_add_f32(p.scratch + ((size_t)((cig * p.co_atoms + coa) * 3 + c) * 48) * ncols, stg, uint32_t(48 * ncols * 4));
+        bulk_reduce_add_f32(p.scratch + ((size_t)((cig * p.co_atoms + coa) * nacc + c) * 48) * ncols, stg, uint32_t(48 * ncols * 4));
         ptx::tma_store_commit();
         ptx::tma_store_wait_read();
       }
@@ -493,20 +508,22 @@ __global__ void __launch_bounds__(192) slab_wgrad_kernel(const __grid_constant__
   if (warp == 1) ptx::tmem_dealloc(tmem_base, uint32_t(p.tmem_cols));
 }
 
-// scratch [ci_group][co_atoms][3 (c = kd)][48 = (2 - kw) * 16 + co % 16][(kh * apg + q) * 16 + ci % 16], ci atom = group * apg + q
-//   -> dw[co][ci][kd][kh][kw]
+// scratch [ci_group][co_atoms][nacc (c = kd)][48 = (2 - kw) * 16 + co % 16][(kh * apg + q) * 16 + ci % 16], ci atom = group * apg + q
+//   -> dw[co][ci][kd][kh][kw]            (k3 = 27; for 1x1x1 convs k3 = 1, nacc = 1 and the only tap sits in row block 0)
 __global__ void __launch_bounds__(256) slab_wgrad_unpack_kernel(const float* __restrict__ scratch, float* __restrict__ dw,
-                                                                int cout, int cin, int apg, int accumulate) {
-  const int total = cout * cin * 27;
-  const int ncols = 3 * apg * 16;
+                                                                int cout, int cin, int apg, int k3, int accumulate) {
+  const int total = cout * cin * k3;
+  const int nacc = k3 == 27 ? 3 : 1;
+  const int ncols = nacc * apg * 16;
   const int co_atoms = cout >> 4;
   for (int i = blockIdx.x * 256 + threadIdx.x; i < total; i += gridDim.x * 256) {
-    const int k = i % 27;
-    const int ci = (i / 27) % cin;
-    const int co = i / (27 * cin);
+    const int k = i % k3;
+    const int ci = (i / k3) % cin;
+    const int co = i / (k3 * cin);
     const int kw = k % 3, kh = (k / 3) % 3, kd = k / 9;
     const int atom = ci >> 4, grp = atom / apg, q = atom - grp * apg;
-    const float v = scratch[((size_t)((grp * co_atoms + (co >> 4)) * 3 + kd) * 48 + (2 - kw) * 16 + (co & 15)) * ncols +
+    const int rowblk = k3 == 27 ? 2 - kw : 0;
+    const float v = scratch[((size_t)((grp * co_atoms + (co >> 4)) * nacc + kd) * 48 + rowblk * 16 + (co & 15)) * ncols +
                             (kh * apg + q) * 16 + (ci & 15)];
     dw[i] = accumulate ? dw[i] + v : v;
   }
