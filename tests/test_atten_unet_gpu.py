@@ -84,3 +84,48 @@ def test_contracts(petsyn):
         m(torch.rand(1, 1, 12, 16, 16, device="cuda"), torch.rand(1, 1, 5, device="cuda"))    # 12 % 8 != 0
     with pytest.raises(ValueError):
         m(torch.rand(1, 1, 16, 16, 16, device="cuda"), torch.rand(1, 1, 6, device="cuda"))    # wrong covariate count
+
+
+def test_trainer_eager_and_graph_follow_autograd_adam(petsyn):
+    """AttenUNetTrainer (flat arenas, batched weight re-pack, fused Adam; eager and CUDA-graph replay) follows the
+    trajectory of the drop-in module driven by autograd + torch.optim.Adam (train_unet.py:147-168 with the L1 term only).
+    First-step losses agree to bf16 noise; after Adam updates every near-zero gradient element moves its weight by a
+    full lr, so later steps agree to O(steps * lr) only."""
+    from petsyn_b200.train import AttenUNetTrainer
+    shape, seed, steps, lr = (2, 32, 48, 32), 11, 3, 5e-4
+    batches = [synth(shape, 200 + i) for i in range(steps)]
+
+    def run(mode):
+        model = petsyn.AttenUNet(**OA.TRAINING_JSON)
+        OA.randomize_(model.named_parameters(), seed=seed)
+        model = model.cuda().train()
+        losses = []
+        if mode == "autograd":
+            opt = torch.optim.Adam(model.parameters(), lr=lr)
+            for x, ctx, tgt in batches:
+                opt.zero_grad()
+                loss = torch.nn.functional.l1_loss(model(x.cuda(), ctx.cuda()), tgt.cuda())
+                loss.backward()
+                opt.step()
+                losses.append(loss.item())
+        else:
+            tr = AttenUNetTrainer(model, lr=lr, example_input=batches[0][0].cuda())
+            if mode == "graph":
+                tr.capture()
+            for x, ctx, tgt in batches:
+                losses.append(tr.step(x.cuda(), ctx.cuda(), tgt.cuda()).item())
+            assert tr.step_count == steps and int(tr.step_dev.item()) == steps     # capture() restored the optimiser state
+        return losses, {k: v.detach().float().cpu().clone() for k, v in model.state_dict().items()}
+
+    la, sa = run("autograd")
+    le, se = run("eager")
+    lg, sg = run("graph")
+    print("losses autograd/eager/graph", la, le, lg)
+    assert abs(la[0] - le[0]) < 1e-3 and abs(la[0] - lg[0]) < 1e-3
+    for a, b, c in zip(la, le, lg):
+        assert abs(a - b) < 1e-2 and abs(a - c) < 1e-2, (la, le, lg)
+    assert la[-1] < la[0]                                                          # the step actually trains
+    for k, ref in sa.items():
+        tol = 2e-3 * (ref.abs().max().item() + 1e-6) + 2.5 * steps * lr            # lr-sized motion per step and weight
+        assert (se[k] - ref).abs().max().item() <= tol, k
+        assert (sg[k] - se[k]).abs().max().item() <= tol, k
