@@ -358,6 +358,7 @@ struct GemmSide {           // one gather-form GEMM (fprop or dgrad)
   // small-channel slab path (slab_kernels.cuh): k3 s1 p1, 16..64 channels, many voxels
   bool slab = false;
   int slab_halo = 1;        // 1: 3x3x3, 0: 1x1x1
+  bool slab3 = false;       // depth-folded kernel (slab_conv3_kernel): three depth taps per MMA
   int slab_grid = 0, slab_smem = 0;
   SlabParams sparams;
 };
@@ -540,6 +541,28 @@ static int32_t bind_slab(GemmSide& g, const ViewSpec& va, const ViewSpec& vc, co
     p.tap_off[t] = (((td.dh + 1) * atoms) * (kSlabWp * 32) + (td.dw + 1) * 32) >> 4;
     p.tap_slab[t / 9] = td.dd + 1;
   }
+  g.slab3 = false;
+  if (halo) {
+    // depth-folded variant: pair j = (dh, dw); B block b of pair j is the tap (dd5[b], dh, dw)
+    static const int dd5[5] = {+1, 0, -1, +1, 0};
+    bool ok = true;
+    for (int j = 0; j < 9 && ok; ++j) {
+      const int dh = j / 3 - 1, dw = j % 3 - 1;
+      p.pair_off[j] = (((dh + 1) * atoms) * (kSlabWp * 32) + (dw + 1) * 32) >> 4;
+      for (int b = 0; b < 5; ++b) {
+        int found = -1;
+        for (int t = 0; t < 27; ++t) {
+          const TapDef& td = g.prog.subs[0][t];
+          if (td.dd == dd5[b] && td.dh == dh && td.dw == dw) found = t;
+        }
+        if (found < 0) ok = false;
+        p.wtap[j][b] = found;
+      }
+    }
+    const int slab_b = (atoms * kSlabWp * kSlabHp * 32 + 1023) / 1024 * 1024;
+    g.slab3 = ok && getenv("PETSYN_NO_SLAB3") == nullptr &&
+              slab3_smem_bytes(atoms, g.R, slab_b, 4, g.out_fp32 ? 4 : 2) <= 200 * 1024;
+  }
   p.ntaps = g.subs[0].tap_count; p.atoms = atoms; p.kc_pad = g.kc_pad; p.b_row = g.subs[0].b_row;
   p.block_n = g.R; p.rows = g.R;
   p.W = va.W; p.H = va.H; p.D = va.D; p.batch = va.N;
@@ -549,18 +572,31 @@ static int32_t bind_slab(GemmSide& g, const ViewSpec& va, const ViewSpec& vc, co
   p.slab_tx = atoms * (kSlabW + 2 * halo) * (kSlabH + 2 * halo) * 32;
   p.slab_bytes = (p.slab_tx + 1023) / 1024 * 1024;
   // ring depth and CTAs per SM from the shared-memory budget
-  const int fixed = slab_smem_bytes(p.ntaps, atoms, g.R, p.slab_bytes, 0, g.out_fp32 ? 4 : 2);
+  const int fixed = g.slab3 ? slab3_smem_bytes(atoms, g.R, p.slab_bytes, 0, g.out_fp32 ? 4 : 2)
+                            : slab_smem_bytes(p.ntaps, atoms, g.R, p.slab_bytes, 0, g.out_fp32 ? 4 : 2);
   int ring = (fixed + 8 * p.slab_bytes <= 110 * 1024) ? 8 : 4;
+  if (g.slab3) ring = 4;                                  // the depth-folded kernel keeps one slab live + prefetch
   if (const char* e = getenv("PETSYN_SLAB_RING")) ring = atoi(e) == 4 ? 4 : 8;       // tuning experiments only
   p.ring = ring;
   g.slab_smem = fixed + ring * p.slab_bytes;
-  int occ = std::max(1, std::min(3, (227 * 1024) / (g.slab_smem + 1024)));
+  int occ = std::max(1, std::min(g.slab3 ? 4 : 3, (227 * 1024) / (g.slab_smem + 1024)));
   if (const char* e = getenv("PETSYN_SLAB_OCC")) occ = std::max(1, std::min(atoi(e), (227 * 1024) / (g.slab_smem + 1024)));
   const int ctas = 148 * occ;
   slab_split(va.W, va.H, va.D, va.N, kSlabW, kSlabH, ctas, &p.dchunk, &p.nchunks, &p.items);
   g.slab_grid = std::min(ctas, p.items);
   g.key_a = a; g.key_b = b; g.key_c = c;
   return PETSYN_OK;
+}
+
+template <int ATOMS>
+static int32_t launch_slab3(const GemmSide& g, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    PETSYN_CHECK_CUDA(cudaFuncSetAttribute(slab_conv3_kernel<ATOMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+    attr_set = true;
+  }
+  slab_conv3_kernel<ATOMS><<<g.slab_grid, 192, g.slab_smem, st>>>(g.sparams);
+  return check_launch("slab_conv3_kernel");
 }
 
 template <int ATOMS>
@@ -575,6 +611,15 @@ static int32_t launch_slab(const GemmSide& g, cudaStream_t st) {
 }
 
 static int32_t run_slab(GemmSide& g, cudaStream_t st) {
+  if (g.slab3) {
+    switch (g.Kc / 16) {
+      case 1: return launch_slab3<1>(g, st);
+      case 2: return launch_slab3<2>(g, st);
+      case 3: return launch_slab3<3>(g, st);
+      case 4: return launch_slab3<4>(g, st);
+      default: return fail(PETSYN_EINVAL, "slab path: unsupported channel count %d", g.Kc);
+    }
+  }
   switch (g.Kc / 16) {
     case 1: return launch_slab<1>(g, st);
     case 2: return launch_slab<2>(g, st);

@@ -52,6 +52,9 @@ struct alignas(64) SlabParams {
   int32_t reduce;       // 1: add into the destination (bf16 TMA reduction)
   int32_t out_f32;      // 1: fp32 output (the one-channel network head keeps full precision), c_map is an fp32 map
   int32_t halo;         // 1: 3x3x3 conv (27 taps over three 10x18 slabs); 0: 1x1x1 conv (one tap, one 8x16 slab per tile)
+  // depth-folded variant (slab_conv3_kernel): the three depth taps of a (dh, dw) pair are stacked in the MMA's N dimension
+  int32_t pair_off[9];  // A start-address delta of pair j = (dh, dw): (((dh+1) * atoms) * 320 + (dw+1) * 32) >> 4
+  int32_t wtap[9][5];   // packed-weight tap index of B block b of pair j: the tap (dd5[b], dh, dw), dd5 = {+1, 0, -1, +1, 0}
 };
 
 // tcgen05.mma with the 64-bit shared-memory descriptors given as (lo, hi) halves: the MMA-issuing thread only ever
@@ -300,6 +303,254 @@ __global__ void __launch_bounds__(192) slab_conv_kernel(const __grid_constant__ 
   ptx::tc_fence_before_sync();
   __syncthreads();
   if (warp == 1) ptx::tmem_dealloc(tmem_base, 128);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Depth-folded fprop / dgrad: ONE A read per (slab, (dh, dw) pair, channel atom) feeds all three depth taps.
+//
+// A slab at depth s contributes to the output tiles at depths s-1, s, s+1 through the taps dd = +1, 0, -1.  Stacking those
+// three weight tiles in N (N = 3 * Cout) turns them into ONE tcgen05.mma whose 3 * Cout accumulator columns are three
+// DIFFERENT output tiles: a ring of three TMEM blocks, tile t living in block t % 3.  The weights are stored as five
+// blocks per pair (dd = +1, 0, -1, +1, 0) so that the three cyclic rotations the ring needs are plain windows.  Every MMA
+// accumulates; a tile is complete once the slab after its own has been issued, then the epilogue warps read its block
+// AND zero it (tcgen05.st) before the MMA warp may open the tile three steps later in the same block.  Shared-memory
+// reads per output tile drop from 27 * (4 KB + B) to 9 * (4 KB + 3 B).
+// ------------------------------------------------------------------------------------------------------------
+__host__ __device__ inline int slab3_smem_bytes(int atoms, int n, int slab_bytes, int ring, int esz = 2) {
+  const int wbytes = (9 * atoms * 5 * n * 32 + 1023) / 1024 * 1024;
+  const int stg = (2 * 128 * n * esz + 1023) / 1024 * 1024;
+  return wbytes + ring * slab_bytes + stg + 1024 + 1024;
+}
+
+template <int ATOMS>
+__global__ void __launch_bounds__(192) slab_conv3_kernel(const __grid_constant__ SlabParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int N = p.block_n;
+  const int wbytes = (9 * ATOMS * 5 * N * 32 + 1023) / 1024 * 1024;
+  const int esz = p.out_f32 ? 4 : 2;
+  const int stg_bytes = (2 * 128 * N * esz + 1023) / 1024 * 1024;
+  uint8_t* s_w = smem;
+  uint8_t* s_ring = smem + wbytes;
+  const int R = p.ring;
+  const uint32_t Rm = uint32_t(R - 1);
+  uint8_t* s_stg = s_ring + R * p.slab_bytes;
+  uint8_t* tail = s_stg + stg_bytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);          // [ring]
+  uint64_t* empty_bar = full_bar + kSlabMaxRing;                    // [ring]
+  uint64_t* w_bar = empty_bar + kSlabMaxRing;                       // [1]
+  uint64_t* acc_full = w_bar + 1;                                   // [3]
+  uint64_t* acc_free = acc_full + 3;                                // [3]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_free + 3);
+  const uint32_t tmem_cols = 3 * N <= 64 ? 64 : (3 * N <= 128 ? 128 : 256);
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5;
+
+  if (warp == 0 && ptx::elect_one()) {
+    for (int s = 0; s < R; ++s) {
+      ptx::mbar_init(&full_bar[s], 1);
+      ptx::mbar_init(&empty_bar[s], 1);
+    }
+    ptx::mbar_init(w_bar, 1);
+    for (int b = 0; b < 3; ++b) {
+      ptx::mbar_init(&acc_full[b], 1);
+      ptx::mbar_init(&acc_free[b], 4);
+    }
+    ptx::fence_mbar_init();
+    ptx::prefetch_tmap(&p.a_map);
+    ptx::prefetch_tmap(&p.b_map);
+    ptx::prefetch_tmap(&p.c_map);
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(tmem_slot, tmem_cols);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  ptx::tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int G = gridDim.x;
+  if (warp == 0) {
+    if (ptx::elect_one()) {
+      // ---------------- TMA producer: 45 * ATOMS weight tiles once, then one slab per depth step ----------------
+      ptx::mbar_expect_tx(w_bar, uint32_t(9 * ATOMS * 5 * N * 32));
+      for (int j = 0; j < 9; ++j)
+        for (int q = 0; q < ATOMS; ++q)
+          for (int b = 0; b < 5; ++b)
+            ptx::tma_load_2d(s_w + ((j * ATOMS + q) * 5 + b) * N * 32, &p.b_map, w_bar, p.wtap[j][b] * p.kc_pad + q * 16,
+                             p.b_row);
+      uint32_t seq = 0;
+      for (int item = blockIdx.x; item < p.items; item += G) {
+        int t = item;
+        const int tw = t % p.tiles_w; t /= p.tiles_w;
+        const int th = t % p.tiles_h; t /= p.tiles_h;
+        const int ch = t % p.nchunks; t /= p.nchunks;
+        const int nb = t;
+        const int d0 = ch * p.dchunk;
+        const int len = min(p.dchunk, p.D - d0);
+        for (int s = 0; s < len + 2; ++s, ++seq) {
+          const int slot = seq & Rm;
+          const uint32_t ph = (seq / uint32_t(R)) & 1;
+          ptx::mbar_wait(&empty_bar[slot], ph ^ 1);
+          const int d = d0 - 1 + s;
+          const bool oob = d < 0 || d >= p.D;
+          ptx::mbar_expect_tx(&full_bar[slot], uint32_t(p.slab_tx));
+          ptx::tma_load_5d(s_ring + slot * p.slab_bytes, &p.a_map, &full_bar[slot], 0, oob ? p.W + 64 : tw * kSlabW - 1, 0,
+                           th * kSlabH - 1, oob ? 0 : nb * p.D + d);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (ptx::elect_one()) {
+      // ---------------- MMA issuer: slab g feeds tiles g, g+1, g+2 (tile t is centred on slab t - 1) ----------------
+      const uint64_t a_desc_base = ptx::umma_desc_base(16, uint32_t(ATOMS * kSlabWp * 32), 6);   // K-major, 32B swizzle
+      const uint64_t b_desc_base = ptx::umma_desc_base(16, 256, 6);
+      const uint32_t a_hi = uint32_t(a_desc_base >> 32), a_lo0 = uint32_t(a_desc_base);
+      const uint32_t b_hi = uint32_t(b_desc_base >> 32), b_lo0 = uint32_t(b_desc_base);
+      const uint32_t idesc = ptx::umma_idesc_bf16(128, uint32_t(3 * N), 0, 0);
+      const uint32_t ring_lo = a_lo0 + (ptx::smem_u32(s_ring) >> 4);
+      const uint32_t w_lo = b_lo0 + (ptx::smem_u32(s_w) >> 4);
+      const uint32_t slab16 = uint32_t(p.slab_bytes) >> 4;
+      const uint32_t blk16 = uint32_t(N) * 2;                  // one weight block (N rows x 32 B) in 16-byte units
+      const uint32_t rshift = (R == 8) ? 3 : 2;
+      ptx::mbar_wait(w_bar, 0);
+      for (int b = 0; b < 3; ++b) ptx::mbar_wait(&acc_free[b], 0);      // the epilogue warps zeroed the three blocks
+      ptx::tc_fence_after_sync();
+      uint32_t g = 0, r = 0;                                    // r = g % 3
+      for (int item = blockIdx.x; item < p.items; item += G) {
+        const int ch = (item / (p.tiles_w * p.tiles_h)) % p.nchunks;
+        const int len = min(p.dchunk, p.D - ch * p.dchunk);
+        for (int s = 0; s < len + 2; ++s, ++g) {
+          ptx::mbar_wait(&full_bar[g & Rm], (g >> rshift) & 1);
+          if (g > 0) {
+            // this slab opens tile g + 2 in the block tile g - 1 used: its epilogue must have read and zeroed it
+            const uint32_t t2 = g + 2;
+            ptx::mbar_wait(&acc_free[t2 % 3], (t2 / 3) & 1);
+          }
+          ptx::tc_fence_after_sync();
+          const uint32_t slab_lo = ring_lo + (g & Rm) * slab16;
+          const uint32_t win = (r == 0 ? 0u : (r == 1 ? 2u : 1u)) * blk16;   // rotation window into the 5 blocks
+#pragma unroll
+          for (int j = 0; j < 9; ++j) {
+            const uint32_t a_lo = slab_lo + uint32_t(p.pair_off[j]);
+#pragma unroll
+            for (int q = 0; q < ATOMS; ++q)
+              umma_bf16_split(tmem_base, a_lo + q * (kSlabWp * 2), a_hi, w_lo + (uint32_t(j * ATOMS + q) * 5) * blk16 + win, b_hi,
+                              idesc, 1u);
+          }
+          ptx::umma_commit(&acc_full[r]);                       // tile g (block g % 3) is complete
+          ptx::umma_commit(&empty_bar[g & Rm]);
+          r = r == 2 ? 0 : r + 1;
+        }
+      }
+    }
+  } else {
+    // ---------------- epilogue warps (2..5) ----------------
+    const int quad = warp & 3;
+    const int row = quad * 32 + (tid & 31);
+    const bool leader = (warp == 2) && ((tid & 31) == 0);
+    const uint32_t lane_addr = tmem_base + (uint32_t(quad * 32) << 16);
+    uint32_t zeros[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) zeros[i] = 0u;
+    for (int c0 = 0; c0 < 3 * N; c0 += 16) ptx::tmem_st_32x16(lane_addr + uint32_t(c0), zeros);
+    ptx::tmem_st_wait();
+    ptx::tc_fence_before_sync();
+    __syncwarp();
+    if ((tid & 31) == 0)
+      for (int b = 0; b < 3; ++b) ptx::mbar_arrive(&acc_free[b]);
+    uint32_t g = 0, r = 0, stores = 0;
+    for (int item = blockIdx.x; item < p.items; item += G) {
+      int t = item;
+      const int tw = t % p.tiles_w; t /= p.tiles_w;
+      const int th = t % p.tiles_h; t /= p.tiles_h;
+      const int ch = t % p.nchunks; t /= p.nchunks;
+      const int nb = t;
+      const int d0 = ch * p.dchunk;
+      const int len = min(p.dchunk, p.D - d0);
+      for (int s = 0; s < len + 2; ++s, ++g) {
+        // tile g was closed by slab g; it is a real output tile iff s >= 2 (depth d0 + s - 2)
+        ptx::mbar_wait(&acc_full[r], (g / 3) & 1);
+        ptx::tc_fence_after_sync();
+        const bool real = s >= 2;
+        const uint32_t buf = stores & 1;
+        uint8_t* stg = s_stg + buf * (128 * N * esz) + row * (N * esz);
+        if (real) {
+          // the TMA store that last read this staging buffer (two stores ago) must have finished reading it
+          if (leader) tma_store_wait_read_1();
+          named_bar_sync(1, 128);
+        }
+        const uint32_t taddr = lane_addr + r * uint32_t(N);
+        // TMEM handoff first (it is on the MMA warp's critical path): read the whole block into registers, zero it, release
+        uint32_t v[4][16];
+        if (real) {
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+            if (c * 16 < N) ptx::tmem_ld_32x16(taddr + uint32_t(c * 16), v[c]);
+          ptx::tmem_ld_wait();
+        }
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          if (c * 16 < N) ptx::tmem_st_32x16(taddr + uint32_t(c * 16), zeros);
+        ptx::tmem_st_wait();
+        ptx::tc_fence_before_sync();
+        __syncwarp();
+        if ((tid & 31) == 0) ptx::mbar_arrive(&acc_free[r]);
+        if (real) {
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            if (c * 16 >= N) break;
+            const int c0 = c * 16;
+            float f[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[c][i]);
+            if (p.bias != nullptr) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) f[i] += __ldg(p.bias + c0 + i);
+            }
+            if (p.epi_act != PETSYN_ACT_NONE) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) f[i] = apply_act(f[i], p.epi_act, p.epi_slope);
+            }
+            if (p.out_f32) {
+#pragma unroll
+              for (int q = 0; q < 4; ++q)
+                *reinterpret_cast<float4*>(stg + c0 * 4 + q * 16) = make_float4(f[4 * q], f[4 * q + 1], f[4 * q + 2], f[4 * q + 3]);
+            } else {
+              uint32_t pk[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                __nv_bfloat162 b2 = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+                pk[i] = *reinterpret_cast<uint32_t*>(&b2);
+              }
+              *reinterpret_cast<uint4*>(stg + c0 * 2) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+              *reinterpret_cast<uint4*>(stg + c0 * 2 + 16) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+            }
+          }
+        }
+        if (real) {
+          ptx::fence_proxy_async_smem();
+          named_bar_sync(1, 128);
+          if (leader) {
+            const uint8_t* src = s_stg + buf * (128 * N * esz);
+            if (p.reduce)
+              ptx::tma_reduce_add_5d(&p.c_map, src, 0, tw * kSlabW, th * kSlabH, d0 + s - 2, nb);
+            else
+              ptx::tma_store_5d(&p.c_map, src, 0, tw * kSlabW, th * kSlabH, d0 + s - 2, nb);
+            ptx::tma_store_commit();
+          }
+          ++stores;
+        }
+        r = r == 2 ? 0 : r + 1;
+      }
+    }
+    if (leader) ptx::tma_store_wait_all();
+  }
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) ptx::tmem_dealloc(tmem_base, tmem_cols);
 }
 
 // ------------------------------------------------------------------------------------------------------------
