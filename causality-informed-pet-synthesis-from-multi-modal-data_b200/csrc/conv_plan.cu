@@ -1265,6 +1265,7 @@ int32_t petsyn_conv_wgrad(petsyn_conv_plan* pl, const void* x, const void* dy, v
       q.tiles_w = (q.W + kWgW - 1) / kWgW;
       q.tiles_h = (q.H + kWgH - 1) / kWgH;
       q.halo = hh;
+      q.m64 = getenv("PETSYN_WGRAD_M64") != nullptr ? atoi(getenv("PETSYN_WGRAD_M64")) : 1;   // M = 64 unless switched off
       q.xslab_tx = atoms * kWgW * (kWgH + 2 * hh) * 32;
       q.xslab_bytes = (q.xslab_tx + 1023) / 1024 * 1024;
       q.gslab_tx = (kWgW + 2) * kWgH * 32;

@@ -571,6 +571,8 @@ struct alignas(64) SlabWgradParams {
   int32_t xring, gring;               // ring depths: 4 or 8 / 2 or 4 (powers of two)
   int32_t tmem_cols, acc_stride;      // TMEM allocation (power of two) and column pitch of the three accumulators
   int32_t halo;                       // 1: 3x3x3 (27 taps); 0: 1x1x1 (one tap: no halo, one accumulator, ncols = atoms * 16)
+  int32_t m64;                        // 1: M = 64 MMAs (4 dy shift atoms instead of 8: half the A-operand smem reads);
+                                      //    accumulator row m then sits in TMEM lane (m / 16) * 32 + m % 16
 };
 
 __host__ __device__ inline int slab_wgrad_smem_bytes(int xslab_bytes, int gslab_bytes, int ncols, int xring, int gring) {
@@ -675,7 +677,7 @@ __global__ void __launch_bounds__(192) slab_wgrad_kernel(const __grid_constant__
       // B = x brick [h][atom][w 16][16 ch]: N atoms ((h-shift, channel atom)) 512 B apart
       const uint64_t b_desc_base = ptx::umma_desc_base(512, 256, 6);
       const uint32_t a_hi = uint32_t(a_desc_base >> 32), b_hi = uint32_t(b_desc_base >> 32);
-      const uint32_t idesc = ptx::umma_idesc_bf16(128, uint32_t(ncols), 1, 1);
+      const uint32_t idesc = ptx::umma_idesc_bf16(p.m64 ? 64 : 128, uint32_t(ncols), 1, 1);
       const uint32_t x_lo = uint32_t(b_desc_base) + (ptx::smem_u32(s_x) >> 4);
       const uint32_t g_lo = uint32_t(a_desc_base) + (ptx::smem_u32(s_g) >> 4);
       const uint32_t xrow16 = uint32_t(p.atoms) * 32;   // one h row of the x brick (atoms * 512 B) in 16-byte units
@@ -728,15 +730,20 @@ __global__ void __launch_bounds__(192) slab_wgrad_kernel(const __grid_constant__
     // warp 4 reads lanes 0..31 (quad 0), warp 5 reads lanes 32..63 (quad 1, only 32..47 are useful).
     float* stg = reinterpret_cast<float*>(smem);
     for (int c = 0; c < nacc; ++c) {
-      if (warp == 4 || warp == 5) {
-        const int quad = warp & 3;
-        const int row = quad * 32 + (tid & 31);
+      // M = 128: accumulator row m = TMEM lane m (rows 0..47 useful: quads 0 and 1 = warps 4 and 5).
+      // M = 64 : row m sits in lane (m / 16) * 32 + m % 16: rows 0..47 = the first 16 lanes of quads 0, 1, 2 (warps 4, 5, 2).
+      const int quad = warp & 3;
+      const int lane = tid & 31;
+      const bool reader = p.m64 ? (quad <= 2) : (quad <= 1);
+      if (reader) {
+        const int row = p.m64 ? quad * 16 + lane : quad * 32 + lane;
+        const bool valid = p.m64 ? lane < 16 : row < 48;
         const uint32_t taddr = tmem_base + c * p.acc_stride + (uint32_t(quad * 32) << 16);
         for (int c0 = 0; c0 < ncols; c0 += 16) {
           uint32_t v[16];
           ptx::tmem_ld_32x16(taddr + uint32_t(c0), v);
           ptx::tmem_ld_wait();
-          if (row < 48) {
+          if (valid) {
 #pragma unroll
             for (int q = 0; q < 4; ++q)
               *reinterpret_cast<uint4*>(stg + row * ncols + c0 + 4 * q) = make_uint4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
