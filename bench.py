@@ -13,8 +13,8 @@ generator (AttenUNet(**unet/config/training.json atten_unet_def, cross_attention
 
   value        volumes/s with inputs resident in HBM, timed with CUDA events, max over ranks
   e2e          same step driven from pinned HOST buffers (H2D of t1 + covariates + pet every step), loss read back (D2H)
-  roofline     dominant kernel of the step, timed live with CUDA events in extra eager steps: the slab convolution
-               kernel on the full-resolution 16 -> 16 channel layers (HBM-bound: AI 216 F/B < ridge)
+  roofline     dominant kernel of the step, timed live with CUDA events in extra eager steps: the depth-folded slab
+               convolution kernel on the full-resolution 16 -> 16 channel layers (HBM-bound: AI 216 F/B < ridge)
   cpu_baseline the oracle port of the reference (PyTorch fp32 on the host cores) on a bounded sample of the workload
 """
 from __future__ import annotations
@@ -650,7 +650,7 @@ def run_petsyn_atten(args, shape, batch):
     for (idx, which), ms_ in op_ms.items():
         key = f"{type(tape.ops[idx]).__name__}.{which}"
         by_kind[key] = by_kind.get(key, 0.0) + ms_
-    # the dominant kernel: slab_conv_kernel on the full-resolution 16 -> 16 layers (one launch = one fprop)
+    # the dominant kernel: slab_conv3_kernel on the full-resolution 16 -> 16 layers (one launch = one fprop)
     dom = [i for i, op in enumerate(tape.ops) if isinstance(op, G.ConvOp) and op.plan.kernel_path[0] == 1
            and op.cin == 16 and op.cout == 16 and op.x.buf.rows == batch * shape[0] * shape[1] * shape[2]]
     dom_ms = statistics.mean(op_ms[(i, "fwd")] for i in dom) if dom else None
@@ -674,10 +674,10 @@ def run_petsyn_atten(args, shape, batch):
         vox = batch * d * h * w
         dom_bytes = vox * 16 * 2 * 2                      # bf16 read-once of x + write-once of y, 16 channels each
         dom_flops = 2.0 * vox * 16 * 16 * 27
-        roof = {"bound": "hbm", "kernel": "slab_conv_kernel<1> (Conv3d 16->16 k3 s1 p1 at 96x128x96, batch 2: the "
+        roof = {"bound": "hbm", "kernel": "slab_conv3_kernel<1> (Conv3d 16->16 k3 s1 p1 at 96x128x96, batch 2: the "
                 f"{len(dom)} full-resolution ResnetBlock convs; fprop launches timed)", "achieved": None, "peak": peak_bw,
-                "unit": "GB/s", "frac": None, "traffic": 111.2e6,
-                "traffic_source": "profiles/r1_slab_conv_ncu_full_summary.csv (dram read + write bytes of one launch)",
+                "unit": "GB/s", "frac": None, "traffic": 111.0e6,
+                "traffic_source": "profiles/r1_slab_conv3_ncu_full_summary.csv (dram read + write bytes of one launch)",
                 "algorithmic_bytes_per_launch": dom_bytes, "algorithmic_flops_per_launch": dom_flops,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6459 GB/s"}
         if dom_ms:
