@@ -153,13 +153,13 @@ __global__ void __launch_bounds__(256) stats_kernel(const __nv_bfloat16* __restr
     const int64_t r0 = (int64_t)blockIdx.x * it.rpp + it.ty;
     const __nv_bfloat16* src = z + it.tx * 8;
     for (int k = 0; k < kPf - 1; ++k) {
-      if (r0 + k * stride < rows) pf.issue(k, 0, src + (r0 + k * stride) * C);
+      if (r0 + k * stride < rows) pf.issue(k, 0, src + (rows - 1 - (r0 + k * stride)) * C);   // descending, see below
       PfRing::commit();
     }
     int k = 0;
     for (int64_t r = r0; r < rows; r += stride, ++k) {
       const int64_t rn = r + (kPf - 1) * stride;
-      if (rn < rows) pf.issue((k + kPf - 1) % kPf, 0, src + rn * C);
+      if (rn < rows) pf.issue((k + kPf - 1) % kPf, 0, src + (rows - 1 - rn) * C);
       PfRing::commit();
       PfRing::wait();
       const F8 x0 = unpack8(pf.get(k % kPf, 0));
@@ -246,15 +246,16 @@ __global__ void __launch_bounds__(256, 3) fwd_kernel(const Dev d) {
   const int64_t stride = (int64_t)gridDim.x * it.rpp;
   const bool has_res = d.res != nullptr;
   PfRing pf(smem_raw, has_res ? 2 : 1);
-  // rows are visited in DESCENDING order: the pass that ran just before (statistics) read the tensor ascending, so its
-  // tail is what the 126 MB L2 still holds
+  // Row order alternates between consecutive passes over the same tensor so that each pass starts with what the previous
+  // one touched last (still in the 126 MB L2): producers (convs) write ascending, statistics / backward-reduce read
+  // DESCENDING, the apply passes read ascending again
   const int64_t q0 = (int64_t)blockIdx.x * it.rpp + it.ty;
   const __nv_bfloat16* zsrc = d.z + it.tx * 8;
   const __nv_bfloat16* rsrc = has_res ? d.res + d.cor + it.tx * 8 : nullptr;
   auto issue = [&](int k) {
     const int64_t q = q0 + k * stride;
     if (q < d.rows) {
-      const int64_t r = base + (d.rows - 1 - q);
+      const int64_t r = base + q;
       pf.issue(k % kPf, 0, zsrc + r * d.C);
       if (has_res) pf.issue(k % kPf, 1, rsrc + r * d.csr);
     }
@@ -265,7 +266,7 @@ __global__ void __launch_bounds__(256, 3) fwd_kernel(const Dev d) {
   for (int64_t q = q0; q < d.rows; q += stride, ++k) {
     issue(k + kPf - 1);
     PfRing::wait();
-    const int64_t r = base + (d.rows - 1 - q);
+    const int64_t r = base + q;
     const F8 x = unpack8(pf.get(k % kPf, 0));
     F8 rs = splat(0.f);
     if (has_res) rs = unpack8(pf.get(k % kPf, 1));
@@ -307,8 +308,9 @@ __global__ void __launch_bounds__(256, 2) bwd_reduce_kernel(const Dev d) {
     const __nv_bfloat16* asrc = d.t1 + base * d.cs1 + d.co1 + it.tx * 8;
     const __nv_bfloat16* bsrc = has_t2 ? d.t2 + base * d.cs2 + d.co2 + it.tx * 8 : nullptr;
     auto issue = [&](int k) {
-      const int64_t r = r0 + k * stride;
-      if (r < d.rows) {
+      const int64_t q = r0 + k * stride;
+      if (q < d.rows) {
+        const int64_t r = d.rows - 1 - q;               // descending (see stats_kernel)
         pf.issue(k % kPf, 0, zsrc + r * d.C);
         pf.issue(k % kPf, 1, asrc + r * d.cs1);
         if (has_t2) pf.issue(k % kPf, 2, bsrc + r * d.cs2);
@@ -401,14 +403,14 @@ __global__ void __launch_bounds__(256, 2) bwd_apply_kernel(const Dev d) {
   const int64_t stride = (int64_t)gridDim.x * it.rpp;
   const bool has_t2 = d.t2 != nullptr;
   PfRing pf(smem_raw, has_t2 ? 3 : 2);
-  const int64_t q0 = (int64_t)blockIdx.x * it.rpp + it.ty;              // descending row order (see fwd_kernel)
+  const int64_t q0 = (int64_t)blockIdx.x * it.rpp + it.ty;              // ascending row order (see fwd_kernel)
   const __nv_bfloat16* zsrc = d.z + it.tx * 8;
   const __nv_bfloat16* asrc = d.t1 + d.co1 + it.tx * 8;
   const __nv_bfloat16* bsrc = has_t2 ? d.t2 + d.co2 + it.tx * 8 : nullptr;
   auto issue = [&](int k) {
     const int64_t q = q0 + k * stride;
     if (q < d.rows) {
-      const int64_t r = base + (d.rows - 1 - q);
+      const int64_t r = base + q;
       pf.issue(k % kPf, 0, zsrc + r * d.C);
       pf.issue(k % kPf, 1, asrc + r * d.cs1);
       if (has_t2) pf.issue(k % kPf, 2, bsrc + r * d.cs2);
@@ -420,7 +422,7 @@ __global__ void __launch_bounds__(256, 2) bwd_apply_kernel(const Dev d) {
   for (int64_t q = q0; q < d.rows; q += stride, ++k) {
     issue(k + kPf - 1);
     PfRing::wait();
-    const int64_t r = base + (d.rows - 1 - q);
+    const int64_t r = base + q;
     const F8 x = unpack8(pf.get(k % kPf, 0)), av = unpack8(pf.get(k % kPf, 1));
     F8 bv = splat(0.f);
     if (has_t2) bv = unpack8(pf.get(k % kPf, 2));
