@@ -203,6 +203,40 @@ def l1_loss_fwd_bwd(y: torch.Tensor, t: torch.Tensor, loss: torch.Tensor, dy: Op
           "l1_loss")
 
 
+class SsimLoss:
+    """1 - mean(SSIM) on fp32 [N,1,D,H,W] volumes (Gaussian window, kernel 5, sigma 0.5, data_range 1 -- the parameters of
+    ``unet/scripts/output_predict.py:73``), value and gradient w.r.t. the prediction.  Holds the derivative-map workspace."""
+
+    def __init__(self, shape, device, data_range: float = 1.0, sigma: float = 0.5):
+        n, c, d, h, w = shape
+        if c != 1:
+            raise ValueError("SSIM kernels take single-channel volumes")
+        self.n, self.d, self.h, self.w = n, d, h, w
+        self.data_range, self.sigma = data_range, sigma
+        self.count = n * (d - 4) * (h - 4) * (w - 4)
+        self.workspace = torch.empty(lib.petsyn_ssim_workspace_bytes(n, d, h, w), dtype=torch.uint8, device=device)
+        self.sum = torch.zeros(1, dtype=torch.float32, device=device)
+
+    def __call__(self, x: torch.Tensor, y: torch.Tensor, dx: Optional[torch.Tensor] = None, grad_scale: float = 1.0,
+                 accumulate: bool = False) -> torch.Tensor:
+        """Returns the device scalar mean SSIM; ``dx`` (if given) receives grad_scale * d(1 - mean SSIM)/dx (added to its
+        contents when ``accumulate``)."""
+        self.sum.zero_()
+        check(lib.petsyn_ssim_fwd_bwd(ptr(x), ptr(y), ptr(self.sum), ptr(dx), ptr(self.workspace) if dx is not None else None,
+                                      self.n, self.d, self.h, self.w, self.data_range, self.sigma, grad_scale, int(accumulate),
+                                      stream_ptr()), "ssim")
+        return self.sum / self.count
+
+
+def eval_metrics(x: torch.Tensor, y: torch.Tensor, data_range: float = 1.0):
+    """MAE and PSNR of a synthesized volume (output_predict.py:121-133); returns device scalars."""
+    out = torch.zeros(2, dtype=torch.float32, device=x.device)
+    check(lib.petsyn_abs_sq_err(ptr(x), ptr(y), ptr(out), x.numel(), stream_ptr()), "abs_sq_err")
+    mae = out[0] / x.numel()
+    psnr = 10.0 * torch.log10(data_range ** 2 / (out[1] / x.numel()))
+    return mae, psnr
+
+
 def mse_const_fwd_bwd(x, target: float, loss, dx, grad_scale: float = 1.0) -> None:
     check(lib.petsyn_mse_const_fwd_bwd(ptr(x), target, ptr(loss), ptr(dx), x.numel(), grad_scale, stream_ptr()),
           "mse_const")

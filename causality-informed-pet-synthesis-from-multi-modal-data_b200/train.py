@@ -422,7 +422,10 @@ class AttenUNetTrainer:
     Single GPU: the whole step replays as one CUDA graph after ``capture()``."""
 
     def __init__(self, model, lr: float = 5e-4, betas=(0.9, 0.999), eps: float = 1e-8, bucket_mb: float = 32.0,
-                 process_group=None, example_input: Optional[torch.Tensor] = None):
+                 process_group=None, example_input: Optional[torch.Tensor] = None, ssim_weight: float = 0.0):
+        """``ssim_weight`` > 0 adds ``ssim_weight * (1 - SSIM)`` (Gaussian window 5, sigma 0.5, data_range 1 -- the
+        parameters of the reference's evaluation, output_predict.py:73) to the L1 reconstruction loss; the reference's own
+        training loss is L1 (+ LPIPS / adversarial terms that do not exist offline), so the default is 0."""
         if example_input is None:
             raise ValueError("example_input (a tensor of the training shape) is required to lay out the arenas")
         self.model = model
@@ -440,6 +443,9 @@ class AttenUNetTrainer:
         self.step_count = 0
         self.loss = torch.zeros(1, dtype=torch.float32, device=dev)
         self.dy = torch.zeros(example_input.shape, dtype=torch.float32, device=dev)
+        self.ssim_weight = float(ssim_weight)
+        self.ssim = ops.SsimLoss(tuple(example_input.shape), dev) if self.ssim_weight > 0 else None
+        self.ssim_value: Optional[torch.Tensor] = None      # mean SSIM of the last step (device scalar)
         self.bucketer = GradBucketer(self.arena, bucket_mb, process_group)
         self.graph = None
         self.segments = None
@@ -452,6 +458,8 @@ class AttenUNetTrainer:
         y = self.eng.forward(x, context)
         self.loss.zero_()
         ops.l1_loss_fwd_bwd(y, target, self.loss, self.dy)
+        if self.ssim is not None:
+            self.ssim_value = self.ssim(y, target, self.dy, grad_scale=self.ssim_weight, accumulate=True)
 
     def _optimizer(self) -> None:
         self.step_dev.add_(1)

@@ -129,3 +129,35 @@ def test_trainer_eager_and_graph_follow_autograd_adam(petsyn):
         tol = 2e-3 * (ref.abs().max().item() + 1e-6) + 2.5 * steps * lr            # lr-sized motion per step and weight
         assert (se[k] - ref).abs().max().item() <= tol, k
         assert (sg[k] - se[k]).abs().max().item() <= tol, k
+
+
+def test_trainer_l1_plus_ssim_gradient(petsyn):
+    """AttenUNetTrainer(ssim_weight=w): the gradient seed is d(L1 + w * (1 - SSIM))/dy -- checked through the first Adam step:
+    identical weights, one step with and without the SSIM term must differ, and the SSIM value must match the oracle's on the
+    network output."""
+    from oracle import ssim as OS
+    from petsyn_b200.train import AttenUNetTrainer
+    shape, seed = (2, 32, 48, 32), 4
+    x, ctx, tgt = synth(shape, 77)
+
+    def make():
+        m = petsyn.AttenUNet(**OA.TRAINING_JSON)
+        OA.randomize_(m.named_parameters(), seed=seed)
+        return m.cuda().train()
+
+    m0 = make()
+    with torch.no_grad():
+        y0 = m0(x.cuda(), ctx.cuda()).float().cpu()
+    ref_ssim = OS.ssim_map(y0.double(), tgt.double()).mean().item()
+    tr = AttenUNetTrainer(make(), lr=5e-4, example_input=x.cuda(), ssim_weight=0.5)
+    tr.step(x.cuda(), ctx.cuda(), tgt.cuda())
+    torch.cuda.synchronize()
+    assert abs(tr.ssim_value.item() - ref_ssim) <= 2e-3 * max(1.0, abs(ref_ssim))       # bf16 network output vs fp32 eval output
+    # the seed really contains the SSIM term: dy == sign(y - t)/numel - 0.5 * dSSIM/dy
+    y = tr.eng.y
+    d_l1 = torch.sign(y - tgt.cuda()) / y.numel()
+    extra = (tr.dy - d_l1).abs().max().item()
+    assert extra > 1e-9
+    yd = y.detach().double().cpu().requires_grad_(True)
+    (0.5 * OS.ssim_loss(yd, tgt.double())).backward()
+    assert ((tr.dy - d_l1).cpu() - yd.grad.float()).abs().max().item() <= 1e-4 * yd.grad.abs().max().item() + 1e-10

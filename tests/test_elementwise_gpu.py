@@ -197,3 +197,30 @@ def test_flash_attention_matches_torch(n, L, H, petsyn):
     for i, name in enumerate("qkv"):
         sl = slice(i * H * hd, (i + 1) * H * hd)
         assert rel(dqkv[:, sl], ref_dqkv[:, sl]) <= 3e-2, (name, rel(dqkv[:, sl], ref_dqkv[:, sl]))
+
+
+@pytest.mark.parametrize("shape", [(2, 1, 20, 24, 40), (1, 1, 9, 13, 37), (1, 1, 32, 48, 32)])
+def test_ssim_loss_matches_oracle(shape, petsyn):
+    """Single-scale SSIM (Gaussian 5-tap window, sigma 0.5, data_range 1: output_predict.py:73) and the gradient of the
+    loss 1 - mean(SSIM) against the float64 CPU oracle (oracle/ssim.py, autograd); MAE / PSNR against their definitions.
+    fp32 arithmetic: 1e-5 on the value, 1e-4 of the gradient's max."""
+    from oracle import ssim as OS
+    ops = petsyn.ops
+    g = torch.Generator().manual_seed(9)
+    x = torch.rand(shape, generator=g)
+    y = (x + 0.2 * torch.randn(shape, generator=g)).clamp(0, 1)
+    xd = x.double().requires_grad_(True)
+    loss_o = OS.ssim_loss(xd, y.double())
+    loss_o.backward()
+    xc, yc = x.cuda(), y.cuda()
+    dx = torch.empty_like(xc)
+    crit = ops.SsimLoss(shape, xc.device)
+    mean_ssim = crit(xc, yc, dx, grad_scale=1.0)
+    torch.cuda.synchronize()
+    assert abs((1.0 - mean_ssim.item()) - loss_o.item()) <= 1e-5
+    gref = xd.grad.float()
+    assert (dx.cpu() - gref).abs().max().item() <= 1e-4 * gref.abs().max().item()
+    assert abs(crit(xc, yc).item() - mean_ssim.item()) <= 1e-6          # evaluation-only call (no gradient, no workspace)
+    mae, psnr = ops.eval_metrics(xc, yc)
+    assert abs(mae.item() - (x - y).abs().mean().item()) <= 1e-6
+    assert abs(psnr.item() - (10 * torch.log10(1.0 / ((x - y) ** 2).mean())).item()) <= 1e-3
