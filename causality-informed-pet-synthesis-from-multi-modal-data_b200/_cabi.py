@@ -113,6 +113,7 @@ SIGNATURES = {
     "petsyn_ssim_workspace_bytes": (_sz, [_i32, _i32, _i32, _i32]),
     "petsyn_ssim_fwd_bwd": (_i32, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _f32, _f32, _f32, _i32, _vp]),
     "petsyn_abs_sq_err": (_i32, [_vp, _vp, _vp, _i64, _vp]),
+    "petsyn_avgpool2_f32": (_i32, [_vp, _vp, _i32, _i32, _i32, _i32, _vp]),
     "petsyn_mse_const_fwd_bwd": (_i32, [_vp, _f32, _vp, _vp, _i64, _f32, _vp]),
     "petsyn_resample2": (_i32, [_vp, _i32, _i32, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _f32, _i32, _vp]),
     "petsyn_layernorm_fwd": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _f32, _vp]),

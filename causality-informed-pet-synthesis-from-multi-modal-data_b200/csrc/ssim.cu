@@ -66,7 +66,7 @@ __global__ void __launch_bounds__(256) ssim_fwd_kernel(const float* __restrict__
     sy[ld][lh][lw] = ok ? __ldg(yn + off) : 0.f;
   }
   __syncthreads();
-  float acc = 0.f;
+  float acc = 0.f, acc_cs = 0.f;
   for (int o = threadIdx.x; o < kTW * kTH * kTD; o += 256) {
     const int lw = o % kTW, lh = (o / kTW) % kTH, ld = o / (kTW * kTH);
     const int gw = w0 + lw, gh = h0 + lh, gd = d0 + ld;           // output voxel (valid-region coordinates)
@@ -91,6 +91,7 @@ __global__ void __launch_bounds__(256) ssim_fwd_kernel(const float* __restrict__
     const float inv = 1.f / (b1 * b2);
     const float s = a1 * a2 * inv;
     acc += s;
+    acc_cs += a2 / b2;                    // contrast-structure term (what MS-SSIM multiplies across scales)
     if (maps != nullptr) {
       const int64_t ovol = (int64_t)od * oh * ow;
       const int64_t oo = n * 3 * ovol + ((int64_t)gd * oh + gh) * ow + gw;
@@ -100,7 +101,12 @@ __global__ void __launch_bounds__(256) ssim_fwd_kernel(const float* __restrict__
     }
   }
   const float tot = block_sum256(acc, red);
-  if (threadIdx.x == 0) atomicAdd(ssim_sum, tot);
+  __syncthreads();
+  const float tot_cs = block_sum256(acc_cs, red);
+  if (threadIdx.x == 0) {
+    atomicAdd(ssim_sum + 2 * n, tot);
+    atomicAdd(ssim_sum + 2 * n + 1, tot_cs);
+  }
 }
 
 // grid: (tiles over the FULL volume, N)
@@ -151,6 +157,24 @@ __global__ void __launch_bounds__(256) ssim_bwd_kernel(const float* __restrict__
     const int64_t off = n * vol + ((int64_t)gd * H + gh) * W + gw;
     const float gval = scale * (fa + 2.f * __ldg(x + off) * fb + __ldg(y + off) * fc);
     dx[off] = accumulate ? dx[off] + gval : gval;
+  }
+}
+
+// dst[n, d/2, h/2, w/2] = mean of the 2x2x2 block (F.avg_pool3d(kernel 2) between MS-SSIM scales; odd tails are dropped)
+__global__ void __launch_bounds__(256) avgpool2_kernel(const float* __restrict__ src, float* __restrict__ dst, int N, int D,
+                                                       int H, int W) {
+  const int od = D / 2, oh = H / 2, ow = W / 2;
+  const int64_t total = (int64_t)N * od * oh * ow;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int w = (int)(i % ow), h = (int)((i / ow) % oh), d = (int)((i / ((int64_t)ow * oh)) % od);
+    const int n = (int)(i / ((int64_t)ow * oh * od));
+    const float* p = src + (((int64_t)n * D + 2 * d) * H + 2 * h) * W + 2 * w;
+    float s = 0.f;
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+      for (int b = 0; b < 2; ++b) s += p[((int64_t)a * H + b) * W] + p[((int64_t)a * H + b) * W + 1];
+    dst[i] = 0.125f * s;
   }
 }
 
@@ -227,6 +251,14 @@ int32_t petsyn_ssim_fwd_bwd(const float* x, const float* y, float* ssim_sum, flo
     if (rc) return rc;
   }
   return PETSYN_OK;
+}
+
+int32_t petsyn_avgpool2_f32(const float* src, float* dst, int32_t n, int32_t d, int32_t h, int32_t w, void* stream) {
+  PETSYN_REQUIRE(src && dst && n > 0 && d >= 2 && h >= 2 && w >= 2, "bad argument");
+  const int64_t total = (int64_t)n * (d / 2) * (h / 2) * (w / 2);
+  const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>((total + 255) / 256, 148 * 8));
+  ssim::avgpool2_kernel<<<blocks, 256, 0, as_stream(stream)>>>(src, dst, n, d, h, w);
+  return check_launch("avgpool2_kernel");
 }
 
 int32_t petsyn_abs_sq_err(const float* x, const float* y, float* out, int64_t numel, void* stream) {

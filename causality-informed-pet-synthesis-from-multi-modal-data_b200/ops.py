@@ -214,8 +214,9 @@ class SsimLoss:
         self.n, self.d, self.h, self.w = n, d, h, w
         self.data_range, self.sigma = data_range, sigma
         self.count = n * (d - 4) * (h - 4) * (w - 4)
+        self.per_sample = (d - 4) * (h - 4) * (w - 4)
         self.workspace = torch.empty(lib.petsyn_ssim_workspace_bytes(n, d, h, w), dtype=torch.uint8, device=device)
-        self.sum = torch.zeros(1, dtype=torch.float32, device=device)
+        self.sum = torch.zeros(n, 2, dtype=torch.float32, device=device)     # per sample: sum SSIM, sum contrast-structure
 
     def __call__(self, x: torch.Tensor, y: torch.Tensor, dx: Optional[torch.Tensor] = None, grad_scale: float = 1.0,
                  accumulate: bool = False) -> torch.Tensor:
@@ -225,7 +226,35 @@ class SsimLoss:
         check(lib.petsyn_ssim_fwd_bwd(ptr(x), ptr(y), ptr(self.sum), ptr(dx), ptr(self.workspace) if dx is not None else None,
                                       self.n, self.d, self.h, self.w, self.data_range, self.sigma, grad_scale, int(accumulate),
                                       stream_ptr()), "ssim")
-        return self.sum / self.count
+        return self.sum[:, 0].sum() / self.count
+
+
+MS_SSIM_BETAS = (0.0448, 0.2856, 0.3001, 0.2363, 0.1333)
+
+
+def ms_ssim(x: torch.Tensor, y: torch.Tensor, data_range: float = 1.0, sigma: float = 0.5) -> torch.Tensor:
+    """Multi-scale SSIM as the reference evaluates it (``MultiScaleStructuralSimilarityIndexMeasure(kernel_size=5,
+    sigma=0.5, data_range=1)``, unet/scripts/output_predict.py:73,126): five scales, 2x average pooling in between, per
+    image prod_i relu(cs_i)^beta_i * relu(ssim_last)^beta_last, averaged over the batch.  Returns a device scalar."""
+    n, c, d, h, w = x.shape
+    if min(d, h, w) // 2 ** (len(MS_SSIM_BETAS) - 1) < 5:
+        raise ValueError("MS-SSIM with a 5-tap window needs at least 80 voxels per axis (5 at the coarsest of 5 scales)")
+    x, y = x.contiguous().float(), y.contiguous().float()
+    terms = []
+    for i, beta in enumerate(MS_SSIM_BETAS):
+        crit = SsimLoss(tuple(x.shape), x.device, data_range, sigma)
+        crit(x, y)
+        last = i == len(MS_SSIM_BETAS) - 1
+        val = crit.sum[:, 0 if last else 1] / crit.per_sample
+        terms.append(torch.relu(val) ** beta)
+        if not last:
+            nd, nh, nw = x.shape[2] // 2, x.shape[3] // 2, x.shape[4] // 2
+            px, py = (torch.empty(n, 1, nd, nh, nw, dtype=torch.float32, device=x.device) for _ in range(2))
+            for src, dst in ((x, px), (y, py)):
+                check(lib.petsyn_avgpool2_f32(ptr(src), ptr(dst), n, x.shape[2], x.shape[3], x.shape[4], stream_ptr()),
+                      "avgpool2")
+            x, y = px, py
+    return torch.stack(terms).prod(0).mean()
 
 
 def eval_metrics(x: torch.Tensor, y: torch.Tensor, data_range: float = 1.0):

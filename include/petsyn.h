@@ -323,7 +323,8 @@ int32_t petsyn_l1_loss_fwd_bwd(const float* y, const float* t, float* loss, floa
  * definition behind the reference's evaluation (unet/scripts/output_predict.py:73,126: gaussian window, kernel_size 5,
  * sigma 0.5, data_range 1), averaged over the voxels whose window lies inside the volume, and the gradient of the
  * reconstruction loss 1 - mean(SSIM) (BASELINE north star: L1/SSIM loss).
- *   ssim_sum[0] += sum of SSIM over the n*(d-4)*(h-4)*(w-4) valid voxels (caller-zeroed; mean = sum / count)
+ *   ssim_sum[2*i + 0] += sum of SSIM over the (d-4)*(h-4)*(w-4) valid voxels of sample i (caller-zeroed, 2*n floats)
+ *   ssim_sum[2*i + 1] += sum of the contrast-structure term (2 s_xy + C2)/(s_x^2 + s_y^2 + C2) (MS-SSIM's per-scale factor)
  *   dx          (+)= grad_scale * d(1 - mean SSIM)/dx (added when `accumulate`, e.g. on top of the L1 gradient), or NULL
  *               for evaluation only
  *   workspace   petsyn_ssim_workspace_bytes() bytes (three derivative maps), needed when dx != NULL */
@@ -331,6 +332,8 @@ size_t petsyn_ssim_workspace_bytes(int32_t n, int32_t d, int32_t h, int32_t w);
 int32_t petsyn_ssim_fwd_bwd(const float* x, const float* y, float* ssim_sum, float* dx, void* workspace, int32_t n,
                             int32_t d, int32_t h, int32_t w, float data_range, float sigma, float grad_scale, int32_t accumulate,
                             void* stream);
+/* F.avg_pool3d(kernel_size=2) on fp32 [n,1,d,h,w]: the down-sampling between MS-SSIM scales. */
+int32_t petsyn_avgpool2_f32(const float* src, float* dst, int32_t n, int32_t d, int32_t h, int32_t w, void* stream);
 /* out[0] += sum |x - y|, out[1] += sum (x - y)^2 (caller-zeroed): MAE and MSE -> PSNR = 10 log10(range^2 / MSE)
  * (output_predict.py:121-133). */
 int32_t petsyn_abs_sq_err(const float* x, const float* y, float* out, int64_t numel, void* stream);

@@ -30,3 +30,26 @@ def ssim_map(x: torch.Tensor, y: torch.Tensor, data_range: float = 1.0, kernel_s
 
 def ssim_loss(x: torch.Tensor, y: torch.Tensor, **kw) -> torch.Tensor:
     return 1.0 - ssim_map(x, y, **kw).mean()
+
+
+MS_SSIM_BETAS = (0.0448, 0.2856, 0.3001, 0.2363, 0.1333)
+
+
+def ms_ssim(x: torch.Tensor, y: torch.Tensor, data_range: float = 1.0, kernel_size: int = 5, sigma: float = 0.5) -> torch.Tensor:
+    """torchmetrics ``multiscale_structural_similarity_index_measure`` (normalize="relu", default betas), restated:
+    per image prod_i relu(cs_i)^beta_i with the last factor replaced by relu(ssim), avg_pool3d(2) between scales."""
+    w = gaussian_window(kernel_size, sigma, x.dtype)
+    c1, c2 = (0.01 * data_range) ** 2, (0.03 * data_range) ** 2
+    terms = []
+    for i, beta in enumerate(MS_SSIM_BETAS):
+        mx, my = F.conv3d(x, w), F.conv3d(y, w)
+        sxx, syy, sxy = F.conv3d(x * x, w), F.conv3d(y * y, w), F.conv3d(x * y, w)
+        vx, vy, cxy = sxx - mx * mx, syy - my * my, sxy - mx * my
+        cs = (2 * cxy + c2) / (vx + vy + c2)
+        sim = ((2 * mx * my + c1) / (mx * mx + my * my + c1)) * cs
+        last = i == len(MS_SSIM_BETAS) - 1
+        val = (sim if last else cs).flatten(1).mean(1)
+        terms.append(torch.relu(val) ** beta)
+        if not last:
+            x, y = F.avg_pool3d(x, 2), F.avg_pool3d(y, 2)
+    return torch.stack(terms).prod(0).mean()

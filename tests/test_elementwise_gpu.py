@@ -224,3 +224,18 @@ def test_ssim_loss_matches_oracle(shape, petsyn):
     mae, psnr = ops.eval_metrics(xc, yc)
     assert abs(mae.item() - (x - y).abs().mean().item()) <= 1e-6
     assert abs(psnr.item() - (10 * torch.log10(1.0 / ((x - y) ** 2).mean())).item()) <= 1e-3
+
+
+def test_ms_ssim_matches_oracle(petsyn):
+    """The reference's evaluation metric (output_predict.py:73,126: MS-SSIM, kernel 5, sigma 0.5, data_range 1) composed from
+    the SSIM kernel's per-sample contrast-structure sums and 2x average pooling, against the float64 oracle."""
+    from oracle import ssim as OS
+    g = torch.Generator().manual_seed(21)
+    shape = (2, 1, 80, 96, 88)
+    x = torch.rand(shape, generator=g)
+    y = (x + 0.1 * torch.randn(shape, generator=g)).clamp(0, 1)
+    ref = OS.ms_ssim(x.double(), y.double()).item()
+    got = petsyn.ops.ms_ssim(x.cuda(), y.cuda()).item()
+    assert abs(got - ref) <= 1e-4, (got, ref)
+    with pytest.raises(ValueError):
+        petsyn.ops.ms_ssim(x[..., :40].cuda(), y[..., :40].cuda())
