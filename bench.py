@@ -51,6 +51,10 @@ WORKLOADS = {
     "infer_unet3d_s3": ("unet3d", (160, 192, 160), 2),
     "infer_bmgan_s3": ("bmgan", (160, 192, 160), 1),
     "infer_atten_unet_small": ("atten", (32, 48, 32), 2),
+    # BASELINE configs[4]: synthesize -> classify, device to device: AttenUNet inference feeding the pMCI/sMCI classifier
+    # (pet_for_classification/, training_atten.json; the classifier is a labelled restatement)
+    "infer_synth_classify_s2": ("synth_classify", (96, 128, 96), 2),
+    "infer_synth_classify_small": ("synth_classify", (32, 64, 32), 2),
 }
 BMGAN_CFG = {
     "full": {},
@@ -495,6 +499,11 @@ ATTEN_METRIC = "covariate-conditioned 3D T1->PET generator (AttenUNet) training-
 
 
 # unet/config/training.json:8-38 (atten_unet_def) + cross_attention_dim injected at train_unet.py:64-68
+# pet_for_classification/config/training_atten.json + cross_attention_dim (train_atten_encoder_MCI.py:85-86)
+CLASSIFIER_CFG = dict(spatial_dims=3, in_channels=1, out_channels=2, num_channels=[16, 32, 64, 128, 128], num_res_blocks=2,
+                      attention_levels=[False, False, False, True, True], norm_num_groups=16, norm_eps=1e-6,
+                      resblock_updown=True, num_head_channels=[0, 0, 0, 32, 32], with_conditioning=True,
+                      transformer_num_layers=1, upcast_attention=False, cross_attention_dim=5)
 ATTEN_CFG = dict(spatial_dims=3, in_channels=1, out_channels=1, num_channels=[16, 32, 64, 128], num_res_blocks=2,
                  attention_levels=[False, False, False, True], norm_num_groups=16, norm_eps=1e-6, resblock_updown=True,
                  num_head_channels=[0, 0, 0, 32], with_conditioning=True, transformer_num_layers=1,
@@ -738,6 +747,31 @@ def _infer_model_and_inputs(family, shape, micro, dev, seed):
     g = torch.Generator().manual_seed(seed)
     d, h, w = shape
     x = torch.rand(micro, 1, d, h, w, generator=g)
+    if family == "synth_classify":
+        gen = petsyn.AttenUNet(**ATTEN_CFG)
+        redraw_parameters_(gen.named_parameters(), seed=777)
+        feats = 128 * (d >> 5) * (h >> 5) * (w >> 5)       # every one of the five levels down-samples
+        cls = petsyn.DiffusionModelEncoder(**CLASSIFIER_CFG, head_in_features=feats)
+        redraw_parameters_(cls.named_parameters(), seed=778)
+        gen, cls = gen.to(dev).eval(), cls.to(dev).eval()
+
+        class Pipeline(torch.nn.Module):
+            """output_predict.py:104-105 -> test_MCI.py:125 without the NIfTI round trip."""
+
+            def __init__(self):
+                super().__init__()
+                self.gen, self.cls = gen, cls
+                self._engines = {}
+
+            def forward(self, t1, cond):
+                pet = self.gen(t1, cond)
+                return self.cls(pet, None, cond)
+
+            def flops(self):
+                return sum(float(getattr(e, "flops_algorithmic", 0.0)) for m in (self.gen, self.cls)
+                           for e in m._engines.values())
+
+        return Pipeline(), x, (torch.rand(micro, 1, 5, generator=g),)
     if family == "atten":
         model = petsyn.AttenUNet(**ATTEN_CFG)
         redraw_parameters_(model.named_parameters(), seed=777)
@@ -778,7 +812,7 @@ def run_petsyn_infer(args, family, shape, micro):
     pinned = [t.pin_memory() for t in xs]
     resident = [t.to(dev) for t in xs]
     extra = tuple(t.to(dev) for t in extra_host)
-    out_host = torch.empty(micro, 1, *shape).pin_memory()
+    out_host = (torch.empty(micro, 2) if family == "synth_classify" else torch.empty(micro, 1, *shape)).pin_memory()
     x_dev = torch.empty_like(resident[0])
 
     def barrier():
@@ -835,14 +869,18 @@ def run_petsyn_infer(args, family, shape, micro):
         except Exception:
             pass
         peak_tf = float(peaks.get("bf16_tflops_sustained", 1400.0))
-        eng = next(iter(model._engines.values())) if hasattr(model, "_engines") else model.engine_for(resident[0])
-        fwd = float(getattr(eng, "flops_algorithmic", 0.0))          # of one micro-batch forward
+        if family == "synth_classify":
+            fwd = model.flops()
+        else:
+            eng = next(iter(model._engines.values())) if hasattr(model, "_engines") else model.engine_for(resident[0])
+            fwd = float(getattr(eng, "flops_algorithmic", 0.0))      # of one micro-batch forward
         vols = world * chunks * micro * args.steps
         ms = ms_total / args.steps
         d, h, w = shape
         ach = fwd * chunks / (ms * 1e-3) / 1e12 if fwd else None
         line = {
-            "metric": INFER_METRIC, "value": vols / (ms_total * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "metric": ("3D T1->PET synthesize-then-classify throughput (generator + classifier inference, device to device)"
+                       if family == "synth_classify" else INFER_METRIC), "value": vols / (ms_total * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": args.workload, "model": type(model).__name__, "volume": list(shape),
@@ -850,7 +888,8 @@ def run_petsyn_infer(args, family, shape, micro):
                        "parallelism": f"replicas x{world} (no collective)", "cuda_graph": False,
                        "l2": "activations of one forward (> 5 GB) exceed the 126 MB L2; inputs rotate over 3 volumes"},
             "e2e": {"value": vols / (ms_e2e * 1e-3), "unit": UNIT,
-                    "h2d_bytes_per_step": chunks * micro * d * h * w * 4, "d2h_bytes_per_step": chunks * micro * d * h * w * 4,
+                    "h2d_bytes_per_step": chunks * micro * d * h * w * 4,
+                    "d2h_bytes_per_step": chunks * micro * (8 if family == "synth_classify" else d * h * w * 4),
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches * args.steps, "clocks": clocks,
             "roofline": {"bound": "tensor", "kernel": "whole forward: algorithmic conv (+ attention) FLOPs / time",

@@ -7,7 +7,7 @@ C ABI of ``lib/libpetsyn.so`` (``include/petsyn.h``).  No Triton, no backend dis
 from . import _cabi  # noqa: F401  (fails loudly when the CUDA library has not been built)
 from . import ops  # noqa: F401
 from .unet_model import UnetGenerator3d, UnetSkipConnectionBlock3d  # noqa: F401
-from .atten_unet_model import AttenUNet  # noqa: F401
+from .atten_unet_model import AttenUNet, DiffusionModelEncoder  # noqa: F401
 from .bmgan_model import ResNet_encoder, dense_unet_generator, patch_discriminator  # noqa: F401
 
-__all__ = ["AttenUNet", "UnetGenerator3d", "UnetSkipConnectionBlock3d", "dense_unet_generator", "patch_discriminator", "ResNet_encoder", "ops"]
+__all__ = ["AttenUNet", "DiffusionModelEncoder", "UnetGenerator3d", "UnetSkipConnectionBlock3d", "dense_unet_generator", "patch_discriminator", "ResNet_encoder", "ops"]

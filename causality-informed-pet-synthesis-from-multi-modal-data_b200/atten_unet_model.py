@@ -511,3 +511,173 @@ class _AttenEngine(_EngineBase):
             for p in self._zero_params:
                 on_ready(p)
         return [g.clone() for g in grads] if out is None else []
+
+
+# ======================================================================================================================
+# pMCI / sMCI classifier for synthesize -> classify (BASELINE configs[4]) -- a LABELLED RESTATEMENT, parity unpinned.
+# ======================================================================================================================
+class DiffusionModelEncoder(nn.Module):
+    """Encoder + fully connected head in the shape of ``DiffusionModelEncoder`` (vendored copy:
+    ``unet/utils/atten_unet_model.py:1863-2032``; used as ``model(imgs, zeros_timesteps, info)`` at
+    ``pet_for_classification/train_atten_encoder_MCI.py:87,169`` with ``config/training_atten.json``).
+
+    **Restatement, parity unpinned.**  The class the reference scripts import lives in the authors'
+    un-vendored fork; the vendored copy cannot run (``get_timestep_embedding`` is undefined, its ResnetBlocks take no time
+    embedding, and ``Linear(4096, 512)`` does not match the 4 608 features a 96x128x96 input produces).  This class keeps
+    what the vendored source does define -- constructor signature, argument checks, module tree and state-dict keys
+    (``conv_in``, ``time_embed``, ``down_blocks.{i}.{attentions,resnets,downsampler}``, ``out.{0,3}``), every level ends in a
+    down-sampling ResnetBlock because ``is_final_block = i == len(num_channels)`` is never true (:1966), flatten in NCDHW
+    order, ``Linear -> ReLU -> Dropout(0.1) -> Linear`` -- and documents what it decides: ``timesteps`` is accepted and
+    ignored (the scripts always pass zeros), ``time_embed`` holds parameters that nothing reads, and the head's input width is
+    the constructor argument ``head_in_features`` (default 4096 as written; 4608 for the reference crop).
+    Inference only (``eval()`` + ``no_grad``): that is what configs[4] runs."""
+
+    def __init__(self, spatial_dims: int, in_channels: int, out_channels: int,
+                 num_res_blocks: Sequence[int] | int = (2, 2, 2, 2), num_channels: Sequence[int] = (32, 64, 64, 64),
+                 attention_levels: Sequence[bool] = (False, False, True, True), norm_num_groups: int = 32,
+                 norm_eps: float = 1e-6, resblock_updown: bool = False, num_head_channels: int | Sequence[int] = 8,
+                 with_conditioning: bool = False, transformer_num_layers: int = 1,
+                 cross_attention_dim: int | None = None, num_class_embeds: int | None = None,
+                 upcast_attention: bool = False, head_in_features: int = 4096) -> None:
+        super().__init__()
+        if with_conditioning is True and cross_attention_dim is None:
+            raise ValueError("DiffusionModelEncoder expects dimension of the cross-attention conditioning "
+                             "(cross_attention_dim) when using with_conditioning.")
+        if cross_attention_dim is not None and with_conditioning is False:
+            raise ValueError("DiffusionModelEncoder expects with_conditioning=True when specifying the cross_attention_dim.")
+        if any((c % norm_num_groups) != 0 for c in num_channels):
+            raise ValueError("DiffusionModelEncoder expects all num_channels being multiple of norm_num_groups")
+        if len(num_channels) != len(attention_levels):
+            raise ValueError("DiffusionModelEncoder expects num_channels being same size of attention_levels")
+        n = len(num_channels)
+        num_head_channels = _rep(num_head_channels, n)
+        if len(num_head_channels) != n:
+            raise ValueError("num_head_channels should have the same length as attention_levels.")
+        num_res_blocks = _rep(num_res_blocks, n)
+        if spatial_dims != 3 or in_channels != 1:
+            raise NotImplementedError("petsyn DiffusionModelEncoder: 3-D, one input channel (PET only)")
+        if not (resblock_updown and with_conditioning) or transformer_num_layers != 1 or num_class_embeds is not None:
+            raise NotImplementedError("petsyn DiffusionModelEncoder implements the training_atten.json family")
+        for lvl, a in enumerate(attention_levels):
+            if a and num_head_channels[lvl] != 32:
+                raise NotImplementedError("attention levels need num_head_channels == 32 (the attention kernel's head size)")
+        self.cfg = dict(num_channels=list(num_channels), num_res_blocks=num_res_blocks,
+                        attention_levels=list(attention_levels), num_head_channels=num_head_channels,
+                        norm_num_groups=norm_num_groups, norm_eps=norm_eps, cross_attention_dim=cross_attention_dim)
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.block_out_channels = num_channels
+        self.with_conditioning = with_conditioning
+        ch, g, e = list(num_channels), norm_num_groups, norm_eps
+        self.conv_in = _Convolution(in_channels, ch[0], 3)
+        ted = ch[0] * 4
+        self.time_embed = nn.Sequential(nn.Linear(ch[0], ted), nn.SiLU(), nn.Linear(ted, ted))
+        self.down_blocks = nn.ModuleList([])
+        out_c = ch[0]
+        for i in range(n):
+            in_c, out_c = out_c, ch[i]
+            attn = None
+            if attention_levels[i]:
+                attn = dict(heads=ch[i] // num_head_channels[i], head_channels=num_head_channels[i],
+                            num_layers=transformer_num_layers, norm_num_groups=g, norm_eps=e,
+                            cross_attention_dim=cross_attention_dim)
+            self.down_blocks.append(_DownBlock(in_c, out_c, num_res_blocks[i], g, e, True, attn))
+        self.out = nn.Sequential(nn.Linear(head_in_features, 512), nn.ReLU(), nn.Dropout(0.1),
+                                 nn.Linear(512, out_channels))
+        self._engines: Dict[Tuple, "_ClsEngine"] = {}
+
+    def forward(self, x: torch.Tensor, timesteps: torch.Tensor | None = None, context: torch.Tensor | None = None,
+                class_labels: torch.Tensor | None = None) -> torch.Tensor:
+        if class_labels is not None:
+            raise NotImplementedError("class labels are not used by the reference scripts")
+        if context is None:
+            raise ValueError("DiffusionModelEncoder(with_conditioning=True) needs the tabular context tensor")
+        if not x.is_cuda:
+            raise RuntimeError("petsyn DiffusionModelEncoder runs on CUDA (sm_100a) only; there is no CPU path")
+        if x.dim() != 5 or x.shape[1] != 1:
+            raise ValueError(f"expected x of shape [N, 1, D, H, W], got {tuple(x.shape)}")
+        if self.training or torch.is_grad_enabled():
+            raise NotImplementedError("petsyn DiffusionModelEncoder is inference-only: call .eval() under torch.no_grad()")
+        x = x.contiguous().float()
+        ctx = context.reshape(x.shape[0], -1).contiguous().float()
+        if ctx.shape[1] != self.cfg["cross_attention_dim"]:
+            raise ValueError(f"context has {ctx.shape[1]} values, expected {self.cfg['cross_attention_dim']}")
+        key = (tuple(x.shape), x.device.index)
+        eng = self._engines.get(key)
+        if eng is None:
+            eng = _ClsEngine(self, tuple(x.shape), x.device)
+            self._engines[key] = eng
+        return eng.forward(x, ctx).clone()
+
+
+class _ClsEngine(_AttenEngine):
+    """Op tape of the classifier for one input shape: the AttenUNet down path + two linears (inference only)."""
+
+    def __init__(self, net: DiffusionModelEncoder, shape, dev):
+        _EngineBase.__init__(self, net, dev)
+        n, _, D, H, W = shape
+        cfg = net.cfg
+        ch = cfg["num_channels"]
+        nl = len(ch)
+        if D % (1 << nl) or H % (1 << nl) or W % (1 << nl):
+            raise ValueError(f"spatial dims {D}x{H}x{W} must be divisible by {1 << nl} (every level down-samples)")
+        self.shape, self.n = shape, n
+        self.context = None
+        self.zero = _ZeroGrad()
+        self._zero_params = []
+        t = self.tape
+        self.inp = Buf(n, D, H, W, self.CPAD, dev, "cls.input")
+        c_in = self._conv(self.inp.sl(), net.conv_in.conv, ksize=3, stride=1, pad=1, need_dx=False, name="cls.conv_in")
+        h = c_in.z
+        for i, blk in enumerate(net.down_blocks):
+            for j, rb in enumerate(blk.resnets):
+                h = self._resnet(rb, h, i, [None], f"cls.down{i}.{j}")
+                if cfg["attention_levels"][i]:
+                    h = self._transformer(blk.attentions[j], h, i, [None], f"cls.down{i}.{j}.attn")
+            h = self._resnet(blk.downsampler, h, i, [None], f"cls.down{i}.ds", down=True)
+        feats = (h.rows // n) * h.c
+        lin1, lin2 = net.out[0], net.out[3]
+        if feats != lin1.in_features:
+            raise ValueError(f"the encoder produces {h.c} x {h.d}x{h.h}x{h.w} = {feats} features for this input but the head "
+                             f"was built with head_in_features={lin1.in_features} (the vendored class hard-codes 4096, "
+                             "atten_unet_model.py:1987; a 96x128x96 input needs 4608)")
+        self.vox, self.fc = h.rows // n, h.c
+        flat = h.alias(n, 1, 1, 1, feats, "cls.flat")
+        self.lin1, self.lin2 = lin1, lin2
+        self.w1 = torch.zeros(512, feats, 1, 1, 1, dtype=torch.float32, device=dev)
+        self.plan1 = ops.ConvPlan(ops.OP_CONV, n, 1, 1, 1, feats, 512, 1, 1, 0, act=ops.ACT_RELU)
+        self.hid = torch.zeros(n, 512, dtype=torch.bfloat16, device=dev)
+        self.w2 = torch.zeros(16, 512, 1, 1, 1, dtype=torch.float32, device=dev)
+        self.b2 = torch.zeros(16, dtype=torch.float32, device=dev)
+        self.plan2 = ops.ConvPlan(ops.OP_CONV, n, 1, 1, 1, 512, 16, 1, 1, 0, y_fp32=True)
+        self.logits = torch.zeros(n, 16, dtype=torch.float32, device=dev)
+        self.flat = flat
+        self._head_ver = None
+        self._finish()
+
+    def _pack_head(self) -> None:
+        l1, l2 = self.lin1, self.lin2
+        ver = (l1.weight._version, l1.weight.data_ptr(), l2.weight._version, l2.weight.data_ptr(), l1.bias._version,
+               l2.bias._version)
+        if ver == self._head_ver:
+            return
+        # nn.Flatten order is (c, voxel); the channels-last buffer is (voxel, c)
+        self.w1[:, :, 0, 0, 0].copy_(l1.weight.detach().view(512, self.fc, self.vox).permute(0, 2, 1).reshape(512, -1))
+        self.plan1.pack(self.w1, need_dgrad=False)
+        oc = l2.out_features
+        self.w2.zero_()
+        self.w2[:oc, :, 0, 0, 0].copy_(l2.weight.detach())
+        self.b2.zero_()
+        self.b2[:oc].copy_(l2.bias.detach())
+        self.plan2.pack(self.w2, need_dgrad=False)
+        self._head_ver = ver
+
+    def forward(self, x: torch.Tensor, context: torch.Tensor) -> torch.Tensor:
+        n, _, D, H, W = self.shape
+        self.context = context
+        check(lib.petsyn_concat_latent(ptr(x), ptr(x), ptr(self.inp.t), D * H * W, n, 0, self.CPAD, stream_ptr()),
+              "concat_latent")
+        self.tape.forward(False)
+        self._pack_head()
+        self.plan1.fprop(self.flat.t, self.hid, self.lin1.bias.detach())      # Linear + ReLU (Dropout is identity in eval)
+        self.plan2.fprop(self.hid, self.logits, self.b2)
+        return self.logits[:, :self.lin2.out_features]
