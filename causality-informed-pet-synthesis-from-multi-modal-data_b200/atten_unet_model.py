@@ -412,7 +412,14 @@ class _AttenEngine(_EngineBase):
         elif up:
             xs = Buf(n, 2 * x.d, 2 * x.h, 2 * x.w, cin, dev, name + ".xs")
             t.add(ResampleOp(x.sl(), xs.sl(), up=True))
-            c1 = self._conv(a1.sl(), rb.conv1.conv, ksize=3, stride=1, pad=1, op=ops.OP_UPCONV, name=name + ".conv1")
+            if cin <= 32 and cout <= 32:
+                # few channels (the full-resolution end of the up path): materialising the up-sampled tensor (a bandwidth-bound copy) and running the
+                # slab kernels on it beats the phase-decomposed gather-form kernel, whose 64-channel K chunks are half empty
+                a1u = Buf(n, 2 * x.d, 2 * x.h, 2 * x.w, cin, dev, name + ".a1u")
+                t.add(ResampleOp(a1.sl(), a1u.sl(), up=True))
+                c1 = self._conv(a1u.sl(), rb.conv1.conv, ksize=3, stride=1, pad=1, name=name + ".conv1")
+            else:
+                c1 = self._conv(a1.sl(), rb.conv1.conv, ksize=3, stride=1, pad=1, op=ops.OP_UPCONV, name=name + ".conv1")
         else:
             xs = x
             c1 = self._conv(a1.sl(), rb.conv1.conv, ksize=3, stride=1, pad=1, name=name + ".conv1")
