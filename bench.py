@@ -650,8 +650,13 @@ def run_petsyn_atten(args, shape, batch):
     tape.timers = {}
     saved_graph, trainer.graph = trainer.graph, None
     for i in range(4):
+        if args.profile_one_step and i == 3:          # `ncu --profile-from-start off`: exactly one step is profiled
+            torch.cuda.synchronize()
+            torch.cuda.profiler.start()
         trainer.step(*resident[i % pool])
     torch.cuda.synchronize()
+    if args.profile_one_step:
+        torch.cuda.profiler.stop()
     trainer.graph = saved_graph
     timers, tape.timers = tape.timers, None
     op_ms = {k: statistics.mean(a.elapsed_time(b) for a, b in v[1:]) for k, v in timers.items()}   # first step = warm-up
@@ -663,6 +668,20 @@ def run_petsyn_atten(args, shape, batch):
     dom = [i for i, op in enumerate(tape.ops) if isinstance(op, G.ConvOp) and op.plan.kernel_path[0] == 1
            and op.cin == 16 and op.cout == 16 and op.x.buf.rows == batch * shape[0] * shape[1] * shape[2]]
     dom_ms = statistics.mean(op_ms[(i, "fwd")] for i in dom) if dom else None
+    # second largest: the slab weight-gradient kernel of the same layers, timed in isolation (memset + kernel + unpack)
+    wg_ms = None
+    if dom:
+        op = tape.ops[dom[0]]
+        dw = torch.empty_like(op.weight)
+        evs = []
+        for _ in range(6):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            op.plan.wgrad(op.x.buf.t, op.dout(), dw)
+            b.record()
+            evs.append((a, b))
+        torch.cuda.synchronize()
+        wg_ms = statistics.mean(a.elapsed_time(b) for a, b in evs[2:])
 
     t = torch.tensor([ms_total, ms_e2e], dtype=torch.float64, device=dev)
     if world > 1:
@@ -684,7 +703,8 @@ def run_petsyn_atten(args, shape, batch):
         dom_bytes = vox * 16 * 2 * 2                      # bf16 read-once of x + write-once of y, 16 channels each
         dom_flops = 2.0 * vox * 16 * 16 * 27
         roof = {"bound": "hbm", "kernel": "slab_conv3_kernel<1> (Conv3d 16->16 k3 s1 p1 at 96x128x96, batch 2: the "
-                f"{len(dom)} full-resolution ResnetBlock convs; fprop launches timed)", "achieved": None, "peak": peak_bw,
+                f"{len(dom)} full-resolution ResnetBlock convs; fprop launches timed; all slab_conv3 instantiations together "
+                "are the largest kernel of the step, 14 %: profiles/r1_launches_default_bench_summary.csv)", "achieved": None, "peak": peak_bw,
                 "unit": "GB/s", "frac": None, "traffic": 111.0e6,
                 "traffic_source": "profiles/r1_slab_conv3_ncu_full_summary.csv (dram read + write bytes of one launch)",
                 "algorithmic_bytes_per_launch": dom_bytes, "algorithmic_flops_per_launch": dom_flops,
@@ -693,6 +713,11 @@ def run_petsyn_atten(args, shape, batch):
             roof.update(achieved=dom_bytes / (dom_ms * 1e-3) / 1e9, launch_ms=dom_ms,
                         tensor_tflops=dom_flops / (dom_ms * 1e-3) / 1e12)
             roof["frac"] = roof["achieved"] / peak_bw
+        if wg_ms:
+            # weight gradient of the same layer: reads x and dy once (the 27x16x16 result is negligible)
+            roof["also"] = {"kernel": "slab_wgrad_kernel (same 16->16 layer; memset + kernel + unpack)", "bound": "hbm",
+                            "launch_ms": wg_ms, "achieved": dom_bytes / (wg_ms * 1e-3) / 1e9, "unit": "GB/s",
+                            "frac": dom_bytes / (wg_ms * 1e-3) / 1e9 / peak_bw}
         line = {
             "metric": ATTEN_METRIC, "value": world * batch * args.steps / (ms_total * 1e-3), "unit": UNIT,
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms,
@@ -925,6 +950,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch kernels eagerly instead of replaying a CUDA graph")
     ap.add_argument("--batch", type=int, default=1, help="inference workloads: volumes per step and GPU (1..16)")
+    ap.add_argument("--profile-one-step", action="store_true",
+                    help="bracket ONE eager step of the roofline leg with cudaProfilerStart/Stop (ncu --profile-from-start off)")
     args = ap.parse_args()
     ngf, shape, batch = WORKLOADS[args.workload]
     if args.workload.startswith("infer"):
