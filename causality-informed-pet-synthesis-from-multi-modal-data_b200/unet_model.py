@@ -15,6 +15,8 @@ engine that runs fused CUDA kernels over channels-last bf16 activations (fp32 ac
 """
 from __future__ import annotations
 
+import os
+
 import functools
 from typing import Dict, List, Optional, Tuple
 
@@ -332,6 +334,24 @@ class _Engine:
                 on_ready(p)
         return [g.clone() for g in grads] if grads is not None else []
 
+    def _wgrad_dgrad(self, plan, x, dz, gw, dx, timers, name: str) -> None:
+        """Weight and data gradient of one conv.  They are independent: outside the profiling leg the data gradient runs
+        on a side stream concurrently with the weight gradient (kept as a branch by CUDA-graph capture; joined before
+        the caller yields, so a graph-segment cut never separates fork and join)."""
+        if timers is None and not os.environ.get("PETSYN_NO_FORK"):
+            from .graph import _side_stream
+            main, side = torch.cuda.current_stream(), _side_stream(dz.device)
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                plan.dgrad(dz, dx)
+            plan.wgrad(x, dz, gw)
+            main.wait_stream(side)
+            return
+        with _timed(timers, f"{name}.wgrad"):
+            plan.wgrad(x, dz, gw)
+        with _timed(timers, f"{name}.dgrad"):
+            plan.dgrad(dz, dx)
+
     def backward_iter(self, dy: torch.Tensor, slot: Dict[int, torch.Tensor], timers=None):
         """Generator form of backward: enqueues kernels and yields each parameter as soon as the kernels producing
         its gradient (into ``slot[id(param)]``) have been enqueued.  The trainer uses the yield points to cut the
@@ -355,22 +375,17 @@ class _Engine:
             yield nm.bn.bias
             src = self.r if i == L - 1 else self.cat[i + 1]
             dsrc = self.dr if i == L - 1 else self.dcat[i + 1]
-            with _timed(timers, f"up{i}.wgrad"):
-                self.up[i].wgrad(src, self.dzu[i], gw(lv[i]._refs["upconv"]))
+            self._wgrad_dgrad(self.up[i], src, self.dzu[i], gw(lv[i]._refs["upconv"]), dsrc, timers, f"up{i}")
             yield lv[i]._refs["upconv"].weight
-            with _timed(timers, f"up{i}.dgrad"):
-                self.up[i].dgrad(self.dzu[i], dsrc)
         # ---- innermost: through ReLU(z) ----
         ci = self.inner[L - 1]
         ops.norm_act_bwd(self.z[L - 1], None, None, None, None, None, self.dr, ci, 0, ops.ACT_RELU, None, 0, 0,
                          ops.ACT_NONE, LRELU_SLOPE, None, self.dz[L - 1], None, None, self.rows[L], ci)
         # ---- down path, inner -> outer ----
         for i in range(L - 1, 0, -1):
-            with _timed(timers, f"down{i}.wgrad"):
-                self.down[i].wgrad(self.a[i], self.dz[i], gw(lv[i]._refs["downconv"]))
+            self._wgrad_dgrad(self.down[i], self.a[i], self.dz[i], gw(lv[i]._refs["downconv"]), self.da[i], timers,
+                              f"down{i}")
             yield lv[i]._refs["downconv"].weight
-            with _timed(timers, f"down{i}.dgrad"):
-                self.down[i].dgrad(self.dz[i], self.da[i])
             prev = self.dnorm[i - 1]
             c = self.outer[i]
             ops.norm_act_bwd(self.z[i - 1], prev.scale if prev else None, prev.shift if prev else None,
