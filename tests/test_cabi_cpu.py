@@ -70,3 +70,19 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in text.lower(), f"{f} mentions the oracle"
+
+
+def test_tools_and_bench_gpu_arms_never_import_the_oracle():
+    """Only tests/, smoke() and bench.py's CPU arms may use oracle/: tools/ and petsyn.py must not mention it, and in
+    bench.py every ``oracle`` import sits inside a ``cpu_*`` function."""
+    import ast
+    for rel in [os.path.join("tools", f) for f in os.listdir(os.path.join(ROOT, "tools"))] + ["petsyn.py"]:
+        if rel.endswith(".py"):
+            assert "oracle" not in open(os.path.join(ROOT, rel)).read().lower(), f"{rel} mentions the oracle"
+    tree = ast.parse(open(os.path.join(ROOT, "bench.py")).read())
+    for fn in [n for n in ast.walk(tree) if isinstance(n, ast.FunctionDef)]:
+        for node in ast.walk(fn):
+            if isinstance(node, ast.ImportFrom) and (node.module or "").startswith("oracle"):
+                assert fn.name.startswith("cpu_"), f"bench.py:{fn.name} imports the oracle"
+    for node in tree.body:
+        assert not (isinstance(node, (ast.Import, ast.ImportFrom)) and "oracle" in ast.dump(node)), "module-level oracle import"
