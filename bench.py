@@ -738,7 +738,7 @@ def run_petsyn_atten(args, shape, batch):
             "final_loss": final,
         }
         if not args.no_cpu_baseline and world == 1:
-            v, sample, cores, _ = cpu_atten_steps(shape, batch, 1, 0, budget_s=30.0)
+            v, sample, cores, _ = cpu_atten_steps(shape, batch, 3, 1, budget_s=30.0)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
         print(json.dumps(line), flush=True)
     if world > 1:
