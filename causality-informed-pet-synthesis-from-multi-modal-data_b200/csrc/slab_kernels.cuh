@@ -7,17 +7,21 @@
 // UMMA shared-memory descriptor (the hardware swizzle is a function of the absolute shared-memory address, so a
 // descriptor may start at any 32-byte voxel row of a 32B-swizzled brick).
 //
-//  slab_conv_kernel  : fprop / dgrad.  Persistent CTAs sweep columns of 8(w) x 16(h) output tiles along depth; each
-//                      new depth step loads ONE halo slab (10 x 18 voxels x Cin) by TMA, issues 27 x Cin/16
-//                      tcgen05.mma (M = 128 voxels, N = Cout, K = 16) against smem-resident weights into a
-//                      double-buffered TMEM accumulator, and overlaps the epilogue (TMEM -> bf16 -> TMA store) of the
-//                      previous tile.
+//  slab_conv3_kernel : fprop / dgrad of 3x3x3 convs (the default).  Persistent CTAs sweep columns of 8(w) x 16(h) output
+//                      tiles along depth; each depth step loads ONE halo slab (10 x 18 voxels x Cin) by TMA.  The three
+//                      depth taps of every (dh, dw) pair are stacked in the MMA's N dimension (N = 3 * Cout), so a slab
+//                      feeds the three output tiles it touches with 9 * Cin/16 tcgen05.mma (M = 128 voxels, K = 16)
+//                      against smem-resident weights; the accumulators form a ring of three TMEM blocks that the
+//                      epilogue warps read, zero and hand back (see the kernel's own header).
+//  slab_conv_kernel  : the same sweep with one MMA per tap (27 * Cin/16 per tile, double-buffered TMEM accumulator):
+//                      1x1x1 convs (halo = 0: one tap, one 8 x 16 slab per tile) and the 3x3x3 shapes whose five-block
+//                      weight image does not fit shared memory.
 //  slab_wgrad_kernel : weight gradient.  dW[(a,b,c), ci, co] = sum_v x[v + (a,b,c) - 1, ci] dy[v, co].  Both operands
 //                      are voxel-major (MN-major UMMA operands, K = 16 consecutive voxels along w).  The three w-taps
-//                      are folded into M as one-voxel shifts of the dy brick (atom stride 32 B), the three h-taps and
-//                      the Cin/16 channel atoms into N as row shifts of the x brick (atom stride 512 B); the three
-//                      d-taps are three accumulators.  Accumulators stay in TMEM for the whole (persistent) CTA and
-//                      are added to an fp32 scratch once at the end.
+//                      are folded into M as one-voxel shifts of the dy brick (atom stride 32 B; M = 64 MMAs), the three
+//                      h-taps and the Cin/16 channel atoms into N as row shifts of the x brick (atom stride 512 B); the
+//                      three d-taps are three accumulators.  Accumulators stay in TMEM for the whole (persistent) CTA
+//                      and are added to an fp32 scratch once at the end.  Input-channel groups of <= 48 on grid.z.
 //
 // Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner, warps 2..5 = epilogue.
 #pragma once
