@@ -164,7 +164,7 @@ def run_reference(args, ngf, shape, batch):
         "impl": "reference", "metric": METRIC, "value": vol_s, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": args.workload, "model": f"UnetGenerator3d(1,1,num_downs=4,ngf={ngf})",
+        "config": {"workload": args.workload, "network": f"UnetGenerator3d(1,1,num_downs=4,ngf={ngf})",
                    "volume": list(shape), "per_gpu_batch": batch},
         "cpu_baseline": {"value": vol_s, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": vol_s, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -283,7 +283,7 @@ def run_petsyn(args, ngf, shape, batch):
             "metric": METRIC, "value": vol_s, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": args.workload, "model": f"UnetGenerator3d(1,1,num_downs=4,ngf={ngf})",
+            "config": {"workload": args.workload, "network": f"UnetGenerator3d(1,1,num_downs=4,ngf={ngf})",
                        "volume": list(shape), "per_gpu_batch": batch, "global_batch": batch * world,
                        "parallelism": f"dp{world}", "optimizer": "Adam(lr=5e-4)", "loss": "L1", "cuda_graph": trainer.graphs is not None,
                        "l2": "per-step working set (weights+packed operands+activations > 1 GB) exceeds the 126 MB L2; "
@@ -453,7 +453,7 @@ def run_petsyn_bmgan(args, cfg_name, shape, batch):
             "value": world * batch * args.steps / (ms_total * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": args.workload, "model": f"dense_unet_generator({cfg_name}) + patch_discriminator()" + (" + ResNet_encoder()" if enc is not None else ""),
+            "config": {"workload": args.workload, "network": f"dense_unet_generator({cfg_name}) + patch_discriminator()" + (" + ResNet_encoder()" if enc is not None else ""),
                        "volume": list(shape), "per_gpu_batch": batch, "global_batch": batch * world,
                        "parallelism": f"dp{world}", "optimizer": "Adam(lr=2e-4) on G; D as written (never stepped)",
                        "loss": "LSGAN + 20*L1", "cuda_graph": trainer.graph is not None,
@@ -487,7 +487,7 @@ def run_reference_bmgan(args, cfg_name, shape, batch):
         "without LPIPS/encoder)", "value": vol_s, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": args.workload, "model": f"dense_unet_generator({cfg_name}) + patch_discriminator()",
+        "config": {"workload": args.workload, "network": f"dense_unet_generator({cfg_name}) + patch_discriminator()",
                    "volume": list(shape), "per_gpu_batch": batch},
         "cpu_baseline": {"value": vol_s, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": vol_s, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}),
@@ -722,7 +722,7 @@ def run_petsyn_atten(args, shape, batch):
             "metric": ATTEN_METRIC, "value": world * batch * args.steps / (ms_total * 1e-3), "unit": UNIT,
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": args.workload, "model": "AttenUNet(**training.json atten_unet_def, cross_attention_dim=5)",
+            "config": {"workload": args.workload, "network": "AttenUNet(**training.json atten_unet_def, cross_attention_dim=5)",
                        "volume": list(shape), "per_gpu_batch": batch, "global_batch": batch * world,
                        "parallelism": f"dp{world}", "optimizer": "Adam(lr=5e-4)", "loss": "L1",
                        "cuda_graph": trainer.graph is not None, "weights": "re-drawn by name (zero_module tensors non-zero)",
@@ -754,7 +754,7 @@ def run_reference_atten(args, shape, batch):
         "impl": "reference", "metric": ATTEN_METRIC, "value": vol_s, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": args.workload, "model": "AttenUNet(**training.json atten_unet_def, cross_attention_dim=5)",
+        "config": {"workload": args.workload, "network": "AttenUNet(**training.json atten_unet_def, cross_attention_dim=5)",
                    "volume": list(shape), "per_gpu_batch": batch},
         "cpu_baseline": {"value": vol_s, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": vol_s, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}),
@@ -908,7 +908,7 @@ def run_petsyn_infer(args, family, shape, micro):
                        if family == "synth_classify" else INFER_METRIC), "value": vols / (ms_total * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": args.workload, "model": type(model).__name__, "volume": list(shape),
+            "config": {"workload": args.workload, "network": type(model).__name__, "volume": list(shape),
                        "per_gpu_batch": chunks * micro, "micro_batch": micro, "global_batch": chunks * micro * world,
                        "parallelism": f"replicas x{world} (no collective)", "cuda_graph": False,
                        "l2": "activations of one forward (> 5 GB) exceed the 126 MB L2; inputs rotate over 3 volumes"},
