@@ -59,6 +59,8 @@ class NormActDesc(C.Structure):
         ("sums", C.c_void_p), ("dz", C.c_void_p), ("dgamma", C.c_void_p), ("dbeta", C.c_void_p),
         ("group_size", C.c_int32), ("dz_accumulate", C.c_int32), ("affine_accumulate", C.c_int32),
         ("slope_dev", C.c_void_p), ("dslope", C.c_void_p), ("dz_colsum", C.c_void_p),
+        ("t1_stats", C.c_void_p), ("t1_stats_c", C.c_int32), ("t1_stats_coff", C.c_int32),
+        ("t2_stats", C.c_void_p), ("t2_stats_c", C.c_int32), ("t2_stats_coff", C.c_int32),
     ]
 
 

@@ -136,6 +136,26 @@ __device__ __forceinline__ void block_reduce_channels(const RowIter& it, float (
   }
 }
 
+// the same reduction into a statistics block of a WIDER tensor: out[v * pitch + off + c]
+template <int NV>
+__device__ __forceinline__ void block_reduce_channels_to(const RowIter& it, float (&acc)[NV][8], float* smem, float* out1,
+                                                         int pitch1, int off1, float* out2, int pitch2, int off2, int C) {
+  if (it.active) {
+#pragma unroll
+    for (int v = 0; v < NV; ++v)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) smem[(it.ty * NV + v) * C + it.tx * 8 + i] = acc[v][i];
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < NV * C; e += blockDim.x) {
+    float s = 0.f;
+    for (int r = 0; r < it.rpp; ++r) s += smem[r * NV * C + e];
+    const int v = e / C, c = e - v * C;
+    if (out1) atomicAdd(out1 + v * pitch1 + off1 + c, s);
+    if (out2) atomicAdd(out2 + v * pitch2 + off2 + c, s);
+  }
+}
+
 // sums[sample][0:C] += sum z, sums[sample][C:2C] += sum z^2
 __global__ void __launch_bounds__(256) stats_kernel(const __nv_bfloat16* __restrict__ z, float* __restrict__ sums,
                                                     int64_t rows, int C) {
@@ -227,6 +247,8 @@ struct Dev {   // device copy of petsyn_normact_desc with typed pointers
   const float *ka, *kb;   // per (sample, channel) backward constants of the affine/group path (nullptr: plain path)
   int dz_acc;
   float* dz_colsum;       // optional [C] += column sums of dz
+  float* st1; int st1_c, st1_off;   // optional statistics of destination 1 for the norm that consumes it
+  float* st2; int st2_c, st2_off;
 };
 
 // ACT < 0: activation codes read from the descriptor at run time (rare combinations); ACT >= 0: act1 == act2 == ACT
@@ -235,50 +257,69 @@ template <int ACT>
 __global__ void __launch_bounds__(256, 3) fwd_kernel(const Dev d) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   RowIter it(d.C);
-  if (!it.active) return;
-  const int s = blockIdx.y;
-  const int64_t base = (int64_t)s * d.rows;
-  const int so = d.per_sample ? s * d.C : 0;
-  F8 sc = splat(1.f), sh = splat(0.f);
-  if (d.scale) { sc = load8f(d.scale + so + it.tx * 8); sh = load8f(d.shift + so + it.tx * 8); }
-  const float slope = d.slope_dev ? __ldg(d.slope_dev) : d.slope;
-  const int a1 = ACT >= 0 ? ACT : d.act1, a2 = ACT >= 0 ? ACT : d.act2;
-  const int64_t stride = (int64_t)gridDim.x * it.rpp;
   const bool has_res = d.res != nullptr;
-  PfRing pf(smem_raw, has_res ? 2 : 1);
-  // Row order alternates between consecutive passes over the same tensor so that each pass starts with what the previous
-  // one touched last (still in the 126 MB L2): producers (convs) write ascending, statistics / backward-reduce read
-  // DESCENDING, the apply passes read ascending again
-  const int64_t q0 = (int64_t)blockIdx.x * it.rpp + it.ty;
-  const __nv_bfloat16* zsrc = d.z + it.tx * 8;
-  const __nv_bfloat16* rsrc = has_res ? d.res + d.cor + it.tx * 8 : nullptr;
-  auto issue = [&](int k) {
-    const int64_t q = q0 + k * stride;
-    if (q < d.rows) {
-      const int64_t r = base + q;
-      pf.issue(k % kPf, 0, zsrc + r * d.C);
-      if (has_res) pf.issue(k % kPf, 1, rsrc + r * d.csr);
-    }
-    PfRing::commit();
-  };
-  for (int k = 0; k < kPf - 1; ++k) issue(k);
-  int k = 0;
-  for (int64_t q = q0; q < d.rows; q += stride, ++k) {
-    issue(k + kPf - 1);
-    PfRing::wait();
-    const int64_t r = base + q;
-    const F8 x = unpack8(pf.get(k % kPf, 0));
-    F8 rs = splat(0.f);
-    if (has_res) rs = unpack8(pf.get(k % kPf, 1));
-    F8 o1, o2;
+  const bool want_stats = d.st1 != nullptr || d.st2 != nullptr;      // uniform over the grid
+  const int s = blockIdx.y;
+  float st[2][8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const float b = x.v[i] * sc.v[i] + sh.v[i];
-      o1.v[i] = act_fwd(b, a1, slope) + rs.v[i];
-      o2.v[i] = (ACT >= 0) ? o1.v[i] : act_fwd(b, a2, slope) + rs.v[i];
+  for (int i = 0; i < 8; ++i) st[0][i] = st[1][i] = 0.f;
+  if (it.active) {
+    const int64_t base = (int64_t)s * d.rows;
+    const int so = d.per_sample ? s * d.C : 0;
+    F8 sc = splat(1.f), sh = splat(0.f);
+    if (d.scale) { sc = load8f(d.scale + so + it.tx * 8); sh = load8f(d.shift + so + it.tx * 8); }
+    const float slope = d.slope_dev ? __ldg(d.slope_dev) : d.slope;
+    const int a1 = ACT >= 0 ? ACT : d.act1, a2 = ACT >= 0 ? ACT : d.act2;
+    const int64_t stride = (int64_t)gridDim.x * it.rpp;
+    PfRing pf(smem_raw, has_res ? 2 : 1);
+    // Row order alternates between consecutive passes over the same tensor so that each pass starts with what the
+    // previous one touched last (still in the 126 MB L2): producers (convs) write ascending, statistics / backward-reduce
+    // read DESCENDING, the apply passes read ascending again
+    const int64_t q0 = (int64_t)blockIdx.x * it.rpp + it.ty;
+    const __nv_bfloat16* zsrc = d.z + it.tx * 8;
+    const __nv_bfloat16* rsrc = has_res ? d.res + d.cor + it.tx * 8 : nullptr;
+    auto issue = [&](int k) {
+      const int64_t q = q0 + k * stride;
+      if (q < d.rows) {
+        const int64_t r = base + q;
+        pf.issue(k % kPf, 0, zsrc + r * d.C);
+        if (has_res) pf.issue(k % kPf, 1, rsrc + r * d.csr);
+      }
+      PfRing::commit();
+    };
+    for (int k = 0; k < kPf - 1; ++k) issue(k);
+    int k = 0;
+    for (int64_t q = q0; q < d.rows; q += stride, ++k) {
+      issue(k + kPf - 1);
+      PfRing::wait();
+      const int64_t r = base + q;
+      const F8 x = unpack8(pf.get(k % kPf, 0));
+      F8 rs = splat(0.f);
+      if (has_res) rs = unpack8(pf.get(k % kPf, 1));
+      F8 o1, o2;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float b = x.v[i] * sc.v[i] + sh.v[i];
+        o1.v[i] = act_fwd(b, a1, slope) + rs.v[i];
+        o2.v[i] = (ACT >= 0) ? o1.v[i] : act_fwd(b, a2, slope) + rs.v[i];
+      }
+      store8(d.t1 + r * d.cs1 + d.co1 + it.tx * 8, o1);
+      if (d.t2) store8(d.t2 + r * d.cs2 + d.co2 + it.tx * 8, o2);
+      if (want_stats) {
+        // statistics of what was STORED (bf16-rounded), so the consumer sees exactly what a separate pass would compute
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float v = __bfloat162float(__float2bfloat16(o1.v[i]));
+          st[0][i] += v;
+          st[1][i] += v * v;
+        }
+      }
     }
-    store8(d.t1 + r * d.cs1 + d.co1 + it.tx * 8, o1);
-    if (d.t2) store8(d.t2 + r * d.cs2 + d.co2 + it.tx * 8, o2);
+  }
+  if (want_stats) {
+    float* smem_f = reinterpret_cast<float*>(smem_raw + PfRing::bytes(has_res ? 2 : 1));
+    block_reduce_channels_to<2>(it, st, smem_f, d.st1 ? d.st1 + (int64_t)s * 2 * d.st1_c : nullptr, d.st1_c, d.st1_off,
+                                d.st2 ? d.st2 + (int64_t)s * 2 * d.st2_c : nullptr, d.st2_c, d.st2_off, d.C);
   }
 }
 
@@ -558,6 +599,9 @@ static int32_t to_dev(const petsyn_normact_desc* d, Dev* o) {
   o->ka = o->kb = nullptr;
   o->dz_acc = d->dz_accumulate;
   o->dz_colsum = d->dz_colsum;
+  o->st1 = d->t1_stats; o->st1_c = d->t1_stats_c; o->st1_off = d->t1_stats_coff;
+  o->st2 = d->t2_stats; o->st2_c = d->t2_stats_c; o->st2_off = d->t2_stats_coff;
+  PETSYN_REQUIRE(!(d->t2_stats && !d->t2), "t2_stats without a second destination");
   PETSYN_REQUIRE(!(d->dz_colsum && d->dz_accumulate), "dz_colsum cannot be combined with dz_accumulate");
   return PETSYN_OK;
 }
@@ -622,7 +666,11 @@ int32_t petsyn_normact_fwd(const petsyn_normact_desc* desc, void* stream) {
   if (rc) return rc;
   PETSYN_REQUIRE(d.t1 != nullptr, "missing destination");
   dim3 grid((unsigned)row_blocks(d.rows, d.C, desc->nsamples), (unsigned)desc->nsamples);
-  PETSYN_NX_DISPATCH(fwd_kernel, grid, PfRing::bytes(d.res ? 2 : 1), as_stream(stream), d);
+  PETSYN_REQUIRE(!(d.st1 || d.st2) || desc->act1 == desc->act2 || d.t2 == nullptr,
+                 "destination statistics need one activation for both destinations");
+  const size_t fwd_smem = PfRing::bytes(d.res ? 2 : 1) +
+                          ((d.st1 || d.st2) ? (size_t)(256 / (d.C / 8)) * 2 * d.C * sizeof(float) : 0);
+  PETSYN_NX_DISPATCH(fwd_kernel, grid, fwd_smem, as_stream(stream), d);
   return check_launch("normact fwd_kernel");
 }
 

@@ -265,11 +265,14 @@ class NormActOp(Op):
         self.gn = gn                            # nn.GroupNorm (kind == "group"): affine, num_groups, eps
         self.acc_dz = False
         self.colsum_conv: Optional["ConvOp"] = None   # conv that produced z: its bias gradient is a by-product of bwd
+        # statistics as a by-product: a "none" op may sum what it writes for the norm that consumes the destination ...
+        self.stats_from_producers = False              # ... and that norm then skips its own statistics pass
         self.slope_param = slope_param          # nn.PReLU weight (one element): slope read from device memory
         self.grad_slope: Optional[torch.Tensor] = None
         self.z, self.kind, self.act, self.dsts, self.res, self.slope, self.bn, self.eps = z, kind, act, list(dsts), res, \
             slope, bn, eps
         self.name = name
+        self.stats_for = [None] * len(self.dsts)       # per destination: (consumer norm op, channel offset in its z)
         dev = z.t.device
         self.ns = z.n if kind in ("instance", "group") else 1
         self.rows = z.rows // self.ns
@@ -301,6 +304,17 @@ class NormActOp(Op):
                 d.sums = ptr(self.bsums)
                 if self.bn is not None and self.bn.weight is not None:
                     d.gamma = ptr(self.bn.weight)
+        if not backward and any(t is not None for t in self.stats_for):
+            # per-sample launch so that the statistics land in the consumer's [sample][2][C] layout
+            d.nsamples, d.rows = z.n, z.rows // z.n
+            for i, tgt in enumerate(self.stats_for):
+                if tgt is None:
+                    continue
+                q, off = tgt
+                if i == 0:
+                    d.t1_stats, d.t1_stats_c, d.t1_stats_coff = ptr(q.sums), q.z.c, off
+                else:
+                    d.t2_stats, d.t2_stats_c, d.t2_stats_coff = ptr(q.sums), q.z.c, off
         src = (lambda s: s.buf.g) if backward else (lambda s: s.buf.t)
         s1 = self.dsts[0]
         d.t1, d.t1_cstride, d.t1_coff, d.act1 = ptr(src(s1)), s1.buf.c, s1.off, self.act
@@ -338,8 +352,9 @@ class NormActOp(Op):
                                            stream_ptr()), "norm_finalize")
         elif self.kind == "group":
             gn = self.gn
-            self.sums.zero_()
-            check(lib.petsyn_norm_stats(ptr(z.t), ptr(self.sums), self.rows, z.c, z.n, stream_ptr()), "norm_stats")
+            if not self.stats_from_producers:
+                self.sums.zero_()
+                check(lib.petsyn_norm_stats(ptr(z.t), ptr(self.sums), self.rows, z.c, z.n, stream_ptr()), "norm_stats")
             check(lib.petsyn_norm_finalize(ptr(self.sums), ptr(gn.weight), ptr(gn.bias), None, None, ptr(self.scale),
                                            ptr(self.shift), ptr(self.mean), ptr(self.rstd), self.rows, z.c, z.n,
                                            z.c // gn.num_groups, gn.eps, 0.0, 1, stream_ptr()), "norm_finalize")
@@ -542,6 +557,49 @@ class Tape:
             if isinstance(op, NormActOp):
                 c = convs.get(id(op.z))
                 op.colsum_conv = c if (c is not None and writers.get(id(op.z), 0) == 1 and not op.acc_dz) else None
+        # statistics as a by-product: a GroupNorm whose input buffer is written, channel range by channel range, only by
+        # un-normalised NormActOps (residual sums, copies into concat buffers) takes its sums from those producers
+        produced: Dict[int, List[Tuple[NormActOp, int, Sl]]] = {}
+        other_writers = set()
+        for op in self.ops:
+            if isinstance(op, NormActOp):
+                for i, sl in enumerate(op.dsts):
+                    if op.kind == "none" and op.slope_param is None:
+                        produced.setdefault(id(sl.buf), []).append((op, i, sl))
+                    else:
+                        other_writers.add(id(sl.buf))
+            elif isinstance(op, ConvOp):
+                other_writers.add(id(op.out_sl.buf) if op.out_sl is not None else id(op.z))
+            else:
+                for v in vars(op).values():            # any other op that holds the buffer may write it: be conservative
+                    if isinstance(v, Buf):
+                        other_writers.add(id(v))
+                    elif isinstance(v, Sl):
+                        other_writers.add(id(v.buf))
+        shared = []
+        for q in self.ops:
+            if not (isinstance(q, NormActOp) and q.kind == "group" and not os.environ.get("PETSYN_NO_STATS_FUSION")):
+                continue
+            prods = produced.get(id(q.z), [])
+            if id(q.z) in other_writers or not prods:
+                continue
+            cover = sorted((sl.off, sl.off + sl.c) for _, _, sl in prods)
+            if cover[0][0] != 0 or cover[-1][1] != q.z.c or any(a[1] != b[0] for a, b in zip(cover, cover[1:])):
+                continue
+            if any(p.stats_for[i] is not None for p, i, _ in prods):
+                continue                               # a destination feeds one consumer's statistics only
+            for p, i, sl in prods:
+                p.stats_for[i] = (q, sl.off)
+            q.stats_from_producers = True
+            shared.append(q)
+        if shared:
+            dev = shared[0].z.t.device
+            self._stats_arena = torch.zeros(sum(q.sums.numel() for q in shared), dtype=torch.float32, device=dev)
+            off = 0
+            for q in shared:
+                n_ = q.sums.numel()
+                q.sums = self._stats_arena[off:off + n_]
+                off += n_
         self._final = True
 
     def repack(self) -> None:
@@ -584,9 +642,13 @@ class Tape:
         e1.record()
         self.timers.setdefault((idx, which), []).append((e0, e1))
 
+    _stats_arena: Optional[torch.Tensor] = None
+
     def forward(self, training: bool) -> None:
         assert self._final
         self.repack()
+        if self._stats_arena is not None:
+            self._stats_arena.zero_()              # the producers of fused statistics accumulate into these sums
         if self.timers is not None:
             for i, op in enumerate(self.ops):
                 self._timed(i, "fwd", lambda: op.fwd(training))

@@ -249,6 +249,12 @@ typedef struct petsyn_normact_desc {
   float* dz_colsum;          /* bwd, optional: [c] += column sums of dz over all rows and samples (caller-zeroed) -- the bias
                               * gradient of the convolution that produced z, as a by-product of the apply pass.  Not with
                               * dz_accumulate */
+  float* t1_stats;           /* fwd, optional: statistics of what is written to destination 1, for the normalisation that
+                              * consumes it: [nsamples][2][t1_stats_c] fp32 (sum, sum of squares), this op's channels at
+                              * offset t1_stats_coff; caller-zeroed; needs nsamples = per-sample launch */
+  int32_t t1_stats_c, t1_stats_coff;
+  float* t2_stats;           /* the same for destination 2 (same values, another consumer) */
+  int32_t t2_stats_c, t2_stats_coff;
 } petsyn_normact_desc;
 
 /* sums[sample][0:c] = sum z, sums[sample][c:2c] = sum z^2 (fp32, caller-zeroed). */
