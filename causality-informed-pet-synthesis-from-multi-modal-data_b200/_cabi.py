@@ -64,6 +64,10 @@ class NormActDesc(C.Structure):
     ]
 
 
+class VolumeSrc(C.Structure):
+    _fields_ = [("data", C.c_void_p), ("d", C.c_int32), ("h", C.c_int32), ("w", C.c_int32)]
+
+
 _vp, _i32, _i64, _f32, _sz = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_size_t
 
 # name -> (restype, argtypes); every symbol declared in include/petsyn.h
@@ -129,6 +133,8 @@ SIGNATURES = {
     "petsyn_kl_fwd_bwd": (_i32, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _f32, _vp]),
     "petsyn_adam_step": (_i32, [_vp, _vp, _vp, _vp, _i64, _f32, _f32, _f32, _f32, _i32, _vp, _vp]),
     "petsyn_sumsq": (_i32, [_vp, _vp, _i64, _vp]),
+    "petsyn_volume_prepare": (_i32, [C.POINTER(VolumeSrc), _i32, _vp, _i32, _i32, _i32, _vp, _vp]),
+    "petsyn_volume_window_offset": (_i32, [_i32, _i32]),
 }
 
 for _name, (_res, _args) in SIGNATURES.items():

@@ -94,7 +94,92 @@ class GradBucketer:
         self._pending.clear()
 
 
-class Unet3dTrainer:
+def adam_state_dict(params: List[torch.nn.Parameter], exp_avg: List[torch.Tensor], exp_avg_sq: List[torch.Tensor],
+                    step: int, lr: float, betas, eps: float) -> dict:
+    """``torch.optim.Adam(params, lr).state_dict()`` for externally held moments: what the reference stores under
+    ``'g_optimizer'`` (train_unet.py:297-302) and feeds back through ``g_optimizer.load_state_dict`` (:109).  ``params`` in
+    ``model.parameters()`` order (the order ``Adam(unet.parameters())`` indexes its state by)."""
+    groups = torch.optim.Adam([torch.nn.Parameter(torch.zeros(1))], lr=lr, betas=tuple(betas), eps=eps).state_dict()[
+        "param_groups"]
+    groups[0]["params"] = list(range(len(params)))
+    state = {}
+    if step > 0:                                   # torch creates per-parameter state lazily at the first step
+        for i, (m, v) in enumerate(zip(exp_avg, exp_avg_sq)):
+            state[i] = {"step": torch.tensor(float(step)), "exp_avg": m.detach().clone(),
+                        "exp_avg_sq": v.detach().clone()}
+    return {"state": state, "param_groups": groups}
+
+
+def read_adam_state_dict(sd: dict, exp_avg: List[torch.Tensor], exp_avg_sq: List[torch.Tensor]) -> int:
+    """Inverse of ``adam_state_dict``: copies the moments into the given views and returns the step count."""
+    idx = sd["param_groups"][0]["params"]
+    if len(idx) != len(exp_avg):
+        raise ValueError(f"optimizer state holds {len(idx)} parameters, the model has {len(exp_avg)}")
+    step = 0
+    for k, (m, v) in zip(idx, zip(exp_avg, exp_avg_sq)):
+        st = sd["state"].get(k)
+        if st is None:
+            m.zero_(); v.zero_()
+            continue
+        if tuple(st["exp_avg"].shape) != tuple(m.shape):
+            raise ValueError(f"optimizer state {k}: shape {tuple(st['exp_avg'].shape)} != parameter {tuple(m.shape)}")
+        m.copy_(st["exp_avg"]); v.copy_(st["exp_avg_sq"])
+        step = max(step, int(float(st["step"])))
+    return step
+
+
+class _CheckpointMixin:
+    """The reference's checkpoint dictionary (train_unet.py:85-109 resume, :297-302 save):
+    ``{'unet', 'discriminator', 'epoch', 'g_optimizer', 'eval_loss'}`` with ``state_dict()`` s as values, so a checkpoint
+    written here resumes in the reference script and vice versa (under DDP the keys carry a ``module.`` prefix there;
+    ``load_checkpoint`` strips it)."""
+
+    def _moments(self):
+        off = {id(p): o for p, o in zip(self.arena.params, self.arena.offsets)}
+        ps = list(self.model.parameters())
+        m = [self.m[off[id(p)]:off[id(p)] + p.numel()].view_as(p) for p in ps]
+        v = [self.v[off[id(p)]:off[id(p)] + p.numel()].view_as(p) for p in ps]
+        return ps, m, v
+
+    def optimizer_state_dict(self) -> dict:
+        ps, m, v = self._moments()
+        return adam_state_dict(ps, m, v, int(self.step_dev.item()), self.lr, self.betas, self.eps)
+
+    def load_optimizer_state_dict(self, sd: dict) -> None:
+        g = sd["param_groups"][0]
+        hyper = (float(g["lr"]), tuple(g["betas"]), float(g["eps"]))
+        captured = getattr(self, "graph", None) is not None or getattr(self, "graphs", None) is not None
+        if captured and hyper != (self.lr, tuple(self.betas), self.eps):
+            raise RuntimeError("lr / betas / eps are baked into the captured step: load the optimizer state before capture()")
+        _, m, v = self._moments()
+        self.step_dev.fill_(read_adam_state_dict(sd, m, v))
+        self.lr, self.betas, self.eps = hyper
+
+    def checkpoint(self, epoch: int, eval_loss: float = float("nan"), discriminator=None, model_key: str = "unet") -> dict:
+        out = {model_key: self.model.state_dict(), "epoch": epoch, "g_optimizer": self.optimizer_state_dict(),
+               "eval_loss": eval_loss}
+        if discriminator is not None:
+            out["discriminator"] = discriminator.state_dict()
+        return out
+
+    def save_checkpoint(self, path: str, epoch: int, eval_loss: float = float("nan"), discriminator=None) -> None:
+        torch.save(self.checkpoint(epoch, eval_loss, discriminator), path)
+
+    def load_checkpoint(self, ckpt, discriminator=None, model_key: str = "unet") -> int:
+        """``ckpt``: a path or an already loaded dictionary.  Returns the epoch to resume from (train_unet.py:89)."""
+        if isinstance(ckpt, (str, bytes)) or hasattr(ckpt, "__fspath__"):
+            ckpt = torch.load(ckpt, map_location=self.dev, weights_only=False)
+        strip = lambda sd: {(k[7:] if k.startswith("module.") else k): v for k, v in sd.items()}
+        self.model.load_state_dict(strip(ckpt[model_key]))       # parameters are views of the arena: copied in place
+        if discriminator is not None and "discriminator" in ckpt:
+            discriminator.load_state_dict(strip(ckpt["discriminator"]))
+        if "g_optimizer" in ckpt:
+            self.load_optimizer_state_dict(ckpt["g_optimizer"])
+        self.eng.mark_weights_dirty()
+        return int(ckpt["epoch"]) + 1
+
+
+class Unet3dTrainer(_CheckpointMixin):
     """Fused training step for a petsyn ``UnetGenerator3d``; data-parallel when a process group is initialised."""
 
     def __init__(self, model, lr: float = 5e-4, betas=(0.9, 0.999), eps: float = 1e-8, bucket_mb: float = 32.0,
@@ -416,7 +501,7 @@ class BmganTrainer:
         self.graph = g
 
 
-class AttenUNetTrainer:
+class AttenUNetTrainer(_CheckpointMixin):
     """Fused training step for the covariate-conditioned generator (``train_unet.py:136-168`` with the offline-available
     terms: zero_grad -> unet(t1, condition) -> nn.L1Loss -> backward -> Adam), data-parallel like Unet3dTrainer.
     Single GPU: the whole step replays as one CUDA graph after ``capture()``."""

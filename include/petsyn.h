@@ -357,6 +357,27 @@ int32_t petsyn_adam_step(float* p, const float* g, float* m, float* v, int64_t n
 /* sum of squares of a flat fp32 array, accumulated into out[0] (caller-zeroed); used for gradient norms. */
 int32_t petsyn_sumsq(const float* g, float* out, int64_t numel, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * Input data format
+ * ---------------------------------------------------------------------------------------------------------- */
+
+/* One raw volume as the reference's loader holds it after sitk.GetArrayFromImage: fp32 [d, h, w], contiguous, in device
+ * memory (the H2D copy of the raw array is the caller's). */
+typedef struct petsyn_volume_src {
+  const float* data;
+  int32_t d, h, w;
+} petsyn_volume_src;
+
+/* pair_PET_T1dataset._preprocess_img (unet/utils/dataset.py:70-105) for a batch of n <= 16 raw volumes of individual
+ * extents: SpatialPad(crop) -> CenterSpatialCrop(crop) -> img / torch.max(img), written as the network input
+ * dst fp32 [n, d, h, w] (= [n, 1, d, h, w]).  vmax [n] fp32 receives each volume's maximum over the window (zero padding
+ * included when the volume is smaller than the crop).  `srcs` is a HOST array; the division is IEEE fp32, so the result is
+ * bit-identical to the torch expression (an all-zero volume gives NaN there and here). */
+int32_t petsyn_volume_prepare(const petsyn_volume_src* srcs, int32_t n, float* dst, int32_t d, int32_t h, int32_t w,
+                              float* vmax, void* stream);
+/* The window of the two MONAI transforms along one axis: output voxel o reads raw voxel o + offset (outside = 0). */
+int32_t petsyn_volume_window_offset(int32_t raw, int32_t roi);
+
 #ifdef __cplusplus
 }
 #endif

@@ -234,3 +234,51 @@ def install_atten() -> None:
             sys.modules[name] = m
     sys.modules["monai.networks.layers.factories"].Pool = _PoolFactory()
     sys.modules["monai.utils"].ensure_tuple_rep = lambda v, n: tuple(v) if isinstance(v, (list, tuple)) else (v,) * n
+
+
+# ------------------------------------------------------------------------------------------------ dataset imports
+class SpatialPad:
+    """Upstream ``monai.transforms.SpatialPad(spatial_size)`` (unet/utils/dataset.py:12,81), channel-first input, default
+    ``method="symmetric"``, zero padding: per spatial axis width = max(target - size, 0), pad (width // 2, width - width // 2)."""
+
+    def __init__(self, spatial_size):
+        self.spatial_size = tuple(spatial_size)
+
+    def __call__(self, img):
+        pads = []
+        for s, r in zip(img.shape[1:], self.spatial_size):
+            width = max(r - s, 0)
+            pads.append((width // 2, width - width // 2))
+        flat = [p for pair in reversed(pads) for p in pair]
+        return nn.functional.pad(img, flat)
+
+
+class CenterSpatialCrop:
+    """Upstream ``monai.transforms.CenterSpatialCrop(roi_size)`` (dataset.py:12,83): centre = size // 2,
+    start = max(centre - roi // 2, 0), end = start + roi, per spatial axis of a channel-first input."""
+
+    def __init__(self, roi_size):
+        self.roi_size = tuple(roi_size)
+
+    def __call__(self, img):
+        sl = [slice(None)]
+        for s, r in zip(img.shape[1:], self.roi_size):
+            start = max(s // 2 - r // 2, 0)
+            sl.append(slice(start, start + r))
+        return img[tuple(sl)]
+
+
+def install_dataset() -> None:
+    """Stub ``monai.transforms`` and ``SimpleITK`` so that ``unet/utils/dataset.py`` imports unmodified (:9,12); only the
+    two transforms ``_preprocess_img`` uses with crop=True are restated, the others raise if touched."""
+    install()
+
+    def _absent(*a, **k):
+        raise NotImplementedError("not restated: only SpatialPad / CenterSpatialCrop are on the path")
+
+    tr = types.ModuleType("monai.transforms")
+    tr.SpatialPad, tr.CenterSpatialCrop, tr.Resize, tr.RandSpatialCrop = SpatialPad, CenterSpatialCrop, _absent, _absent
+    sys.modules["monai.transforms"] = tr
+    sys.modules["monai"].transforms = tr
+    if "SimpleITK" not in sys.modules:
+        sys.modules["SimpleITK"] = types.ModuleType("SimpleITK")
