@@ -256,10 +256,10 @@ def run_petsyn(args, ngf, shape, batch):
     torch.cuda.synchronize()
     per_kernel = {k: statistics.mean(a.elapsed_time(b) for a, b in v) for k, v in timers.items()}
 
-    t = torch.tensor([ms_total, ms_e2e], dtype=torch.float64, device=dev)
+    t = torch.tensor([ms_total, ms_e2e, ms_loader], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total, ms_e2e = t.tolist()
+    ms_total, ms_e2e, ms_loader = t.tolist()
 
     if rank == 0:
         eng = trainer.eng
@@ -429,10 +429,10 @@ def run_petsyn_bmgan(args, cfg_name, shape, batch):
     barrier()
     ms_e2e = f0.elapsed_time(f1)
     clocks = sampler.stop() if rank == 0 else None
-    t = torch.tensor([ms_total, ms_e2e], dtype=torch.float64, device=dev)
+    t = torch.tensor([ms_total, ms_e2e, ms_loader], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total, ms_e2e = t.tolist()
+    ms_total, ms_e2e, ms_loader = t.tolist()
     if rank == 0:
         peaks = {}
         try:
@@ -645,6 +645,31 @@ def run_petsyn_atten(args, shape, batch):
     ms_e2e = f0.elapsed_time(f1)
     clocks = sampler.stop() if rank == 0 else None
 
+    # ---- timed region 3: the same step fed by PairVolumeLoader -- RAW ragged volumes (~107x149x107, the reference's
+    # registered grid) from pinned memory, H2D + pad/crop/max-normalisation (volume_prepare) on the copy stream one batch
+    # ahead, covariates min-max scaled: the reference's dataset contract (unet/utils/dataset.py:70-139) end to end ----
+    src = petsyn.SyntheticPairSource(length=world * batch * (args.steps + 2), seed=777)
+    loader = petsyn.PairVolumeLoader(src, batch, dev, crop_size=shape, need_values=src.NEED_VALUES,
+                                     min_and_max=src.MIN_AND_MAX, rank=rank, world_size=world, seed=777)
+    it = iter(loader)
+    for _ in range(2):                                  # warm-up: pinned slabs touched, look-ahead primed
+        t1, pet, info, *_ = next(it)
+        trainer.step(t1, info, pet)
+    barrier()
+    h2d0 = loader.h2d_bytes
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    g0.record()
+    n_loader = 0
+    for t1, pet, info, *_ in it:
+        l = trainer.step(t1, info, pet)
+        loss_host.copy_(l, non_blocking=True)
+        n_loader += 1
+    torch.cuda.current_stream().synchronize()
+    g1.record()
+    barrier()
+    ms_loader = g0.elapsed_time(g1)
+    loader_h2d = (loader.h2d_bytes - h2d0) / max(1, n_loader)
+
     # ---- roofline leg: CUDA-event brackets around every op of a few extra EAGER steps (same kernels as the graph) ----
     tape = trainer.eng.tape
     tape.timers = {}
@@ -683,10 +708,10 @@ def run_petsyn_atten(args, shape, batch):
         torch.cuda.synchronize()
         wg_ms = statistics.mean(a.elapsed_time(b) for a, b in evs[2:])
 
-    t = torch.tensor([ms_total, ms_e2e], dtype=torch.float64, device=dev)
+    t = torch.tensor([ms_total, ms_e2e, ms_loader], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total, ms_e2e = t.tolist()
+    ms_total, ms_e2e, ms_loader = t.tolist()
     if rank == 0:
         peaks = {}
         try:
@@ -730,6 +755,11 @@ def run_petsyn_atten(args, shape, batch):
             "e2e": {"value": world * batch * args.steps / (ms_e2e * 1e-3), "unit": UNIT,
                     "h2d_bytes_per_step": 2 * batch * d * h * w * 4 + batch * 20, "d2h_bytes_per_step": 4,
                     "ms_per_step": ms_e2e / args.steps},
+            "e2e_loader": {"value": world * batch * n_loader / (ms_loader * 1e-3), "unit": UNIT, "steps": n_loader,
+                           "ms_per_step": ms_loader / max(1, n_loader), "h2d_bytes_per_step": loader_h2d,
+                           "what": "step fed by PairVolumeLoader: raw ragged ~107x149x107 volumes from pinned memory, H2D + "
+                                   "pad/centre-crop/max-normalise on the copy stream one batch ahead, covariates min-max "
+                                   "scaled (the reference's pair_PET_T1dataset contract)"},
             "gpu_launches": launches * args.steps, "clocks": clocks,
             "roofline": roof,
             "step_breakdown": {"per_op_class_ms": {k: round(v, 4) for k, v in sorted(by_kind.items(), key=lambda kv: -kv[1])},
@@ -883,10 +913,10 @@ def run_petsyn_infer(args, family, shape, micro):
         barrier()
         ms_e2e = f0.elapsed_time(f1)
     clocks = sampler.stop() if rank == 0 else None
-    t = torch.tensor([ms_total, ms_e2e], dtype=torch.float64, device=dev)
+    t = torch.tensor([ms_total, ms_e2e, ms_loader], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total, ms_e2e = t.tolist()
+    ms_total, ms_e2e, ms_loader = t.tolist()
     if rank == 0:
         peaks = {}
         try:

@@ -99,8 +99,7 @@ class SyntheticPairSource:
         rng = np.random.default_rng(self.seed * 1000003 + i)
         shp = tuple(int(b + rng.integers(-self.jitter, self.jitter + 1)) for b in self.base)
         a, b = self._pool[i % len(self._pool)]
-        t1 = np.ascontiguousarray(a[:shp[0], :shp[1], :shp[2]])
-        pet = np.ascontiguousarray(b[:shp[0], :shp[1], :shp[2]])
+        t1, pet = a[:shp[0], :shp[1], :shp[2]], b[:shp[0], :shp[1], :shp[2]]        # strided views: the loader gathers them
         row = {"Subject": f"synthetic_{i:04d}", "T1_date": "2000-01-01", "PET_date": "2000-01-02",
                "ABETA": repr(float(rng.uniform(200, 1700))), "Age": repr(float(rng.uniform(55, 93))),
                "Sex": repr(float(rng.integers(0, 2))), "APOE4": repr(float(rng.integers(0, 3))),
@@ -113,8 +112,8 @@ class PairVolumeLoader:
     with the preprocessing on the device and one batch of look-ahead.
 
     Per batch: raw arrays -> pinned staging slab (host memcpy) -> one async H2D per volume on the copy stream ->
-    ``volume_prepare`` on the copy stream -> event; the consumer's stream waits on the event only.  Two staging / output
-    slots alternate, so the H2D + preparation of batch k+1 overlaps the training step of batch k.
+    ``volume_prepare`` on the copy stream -> event; the consumer's stream waits on the event only.  Three staging / output
+    slots rotate, so the host staging, H2D and preparation of batch k+1 overlap the training step of batch k-1 / k.
     """
 
     def __init__(self, source, batch_size: int, device, crop_size: Tuple[int, int, int] = (96, 128, 96),
@@ -128,10 +127,10 @@ class PairVolumeLoader:
         self.rank, self.world, self.shuffle, self.seed, self.drop_last = rank, world_size, shuffle, seed, drop_last
         self.epoch = 0
         if max_raw_voxels is None:
-            max_raw_voxels = int(np.prod([2 * c for c in self.crop]))
+            max_raw_voxels = int(np.prod([c + c // 2 for c in self.crop]))        # raw extents up to 1.5x the crop
         self.cap = max_raw_voxels
         self.copy_stream = torch.cuda.Stream(device=self.dev)
-        nslots = 2
+        nslots = 3          # batch k+1 is staged while step k-1 still runs: its slot was last read by step k-2
         mk = lambda *shape: torch.empty(*shape, dtype=torch.float32, device=self.dev)
         self.slots = [{
             "pin": torch.empty(2 * batch_size, self.cap, dtype=torch.float32).pin_memory(),
@@ -142,6 +141,8 @@ class PairVolumeLoader:
             "vmax": mk(2 * batch_size),
             "ready": torch.cuda.Event(), "free": torch.cuda.Event(),
         } for _ in range(nslots)]
+        for sl in self.slots:
+            sl["pin_np"] = sl["pin"].numpy()               # shares the pinned allocation
         self.h2d_bytes = 0
 
     # -------------------------------------------------------------------------------------------- sampler
@@ -159,16 +160,17 @@ class PairVolumeLoader:
     # -------------------------------------------------------------------------------------------- pipeline
     def _stage(self, slot: dict, items: List[int]) -> dict:
         """Host side of one batch: copy into pinned memory, enqueue H2D + device preparation on the copy stream."""
-        slot["free"].synchronize()                       # the step that consumed this slot two batches ago is done
+        slot["free"].synchronize()                       # the step that consumed this slot three batches ago is done
         b = len(items)
         meta, shapes = [], []
         for j, i in enumerate(items):
             t1, pet, row = self.source[i]
             for k, a in ((2 * j, t1), (2 * j + 1, pet)):
-                a = np.asarray(a, dtype=np.float32)
+                a = np.asarray(a)
                 if a.ndim != 3 or a.size > self.cap:
                     raise ValueError(f"raw volume {a.shape} does not fit the staging slab ({self.cap} voxels)")
-                slot["pin"][k, :a.size].copy_(torch.from_numpy(np.ascontiguousarray(a).reshape(-1)))
+                # one pass: gathers a strided view and converts the dtype straight into pinned memory
+                np.copyto(slot["pin_np"][k, :a.size].reshape(a.shape), a, casting="unsafe")
                 shapes.append(a.shape)
             cov = normalise_covariates(row, self.need_values, self.min_and_max)
             if cov:
@@ -195,7 +197,7 @@ class PairVolumeLoader:
         pending = self._stage(self.slots[0], batches[0]) if batches else None
         for k in range(len(batches)):
             cur = pending
-            pending = self._stage(self.slots[(k + 1) % 2], batches[k + 1]) if k + 1 < len(batches) else None
+            pending = self._stage(self.slots[(k + 1) % len(self.slots)], batches[k + 1]) if k + 1 < len(batches) else None
             slot, b = cur["slot"], cur["b"]
             consumer = torch.cuda.current_stream(self.dev)
             consumer.wait_event(slot["ready"])

@@ -97,7 +97,7 @@ def test_synthetic_source_is_seeded_and_ragged(petsyn):
         t1b, petb, rowb = b[i]
         assert np.array_equal(t1a, t1b) and np.array_equal(peta, petb) and rowa == rowb
         shapes.add(t1a.shape)
-        assert t1a.dtype == np.float32 and t1a.flags["C_CONTIGUOUS"]
+        assert t1a.dtype == np.float32 and t1a.ndim == 3
     assert len(shapes) > 1
     from petsyn_b200.data import normalise_covariates
     cov = normalise_covariates(rowa, a.NEED_VALUES, a.MIN_AND_MAX)
