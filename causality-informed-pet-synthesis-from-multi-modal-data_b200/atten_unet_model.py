@@ -279,10 +279,15 @@ class _ZeroGrad(graph.Op):
 
     def __init__(self):
         self.slots: List[torch.Tensor] = []
+        self._zeroed: tuple = ()
 
     def bwd(self) -> None:
-        for s in self.slots:
-            s.zero_()
+        # nothing on the path ever writes these slots, so they are cleared once per binding (24 fill launches a step otherwise)
+        key = tuple(s.data_ptr() for s in self.slots)
+        if key != self._zeroed:
+            for s in self.slots:
+                s.zero_()
+            self._zeroed = key
 
 
 class _AttenEngine(_EngineBase):

@@ -684,7 +684,7 @@ int32_t petsyn_normact_bwd(const petsyn_normact_desc* desc, void* stream) {
   dim3 grid((unsigned)row_blocks(d.rows, d.C, desc->nsamples), (unsigned)desc->nsamples);
   if (d.mean != nullptr) {
     const int nst = d.per_sample ? desc->nsamples : 1;
-    PETSYN_CHECK_CUDA(cudaMemsetAsync(d.sums, 0, (size_t)nst * 2 * d.C * sizeof(float), st));
+    if (!desc->sums_prezeroed) PETSYN_CHECK_CUDA(cudaMemsetAsync(d.sums, 0, (size_t)nst * 2 * d.C * sizeof(float), st));
     const int rpp = 256 / (d.C / 8);
     const size_t smem = PfRing::bytes(d.t2 ? 3 : 2) + (size_t)rpp * 2 * d.C * sizeof(float);
     PETSYN_NX_DISPATCH(bwd_reduce_kernel, grid, smem, st, d);

@@ -134,6 +134,7 @@ class ConvOp(Op):
         if self.use_bias and self.cout != cout_w:
             self.bias_stage = torch.zeros(self.cout, dtype=torch.float32, device=dev)
         self.dbias_stage = torch.zeros(self.cout, dtype=torch.float32, device=dev) if bias is not None else None
+        self.tape_zeroes_dbias = False                 # Tape.finalize moved `dbias_stage` into its per-backward zero arena
         # the data gradient runs on a side stream concurrently with the weight gradient (a fork/join that CUDA-graph
         # capture keeps as a branch): layers whose kernels cannot fill 148 SMs (deep levels, transformer linears) overlap
         # fully, large ones overlap their ramp-up / tail.  Measured on configs[1]: 18.54 -> 17.82 ms per step.
@@ -267,6 +268,8 @@ class NormActOp(Op):
         self.colsum_conv: Optional["ConvOp"] = None   # conv that produced z: its bias gradient is a by-product of bwd
         # statistics as a by-product: a "none" op may sum what it writes for the norm that consumes the destination ...
         self.stats_from_producers = False              # ... and that norm then skips its own statistics pass
+        self.tape_zeroes_sums = False                  # Tape.finalize moved `sums` into its per-step zero arena
+        self.tape_zeroes_bsums = False                 # ... and `bsums` into its per-backward zero arena
         self.slope_param = slope_param          # nn.PReLU weight (one element): slope read from device memory
         self.grad_slope: Optional[torch.Tensor] = None
         self.z, self.kind, self.act, self.dsts, self.res, self.slope, self.bn, self.eps = z, kind, act, list(dsts), res, \
@@ -302,6 +305,7 @@ class NormActOp(Op):
             if backward:
                 d.mean, d.rstd = ptr(self.mean), ptr(self.rstd)
                 d.sums = ptr(self.bsums)
+                d.sums_prezeroed = 1 if self.tape_zeroes_bsums else 0
                 if self.bn is not None and self.bn.weight is not None:
                     d.gamma = ptr(self.bn.weight)
         if not backward and any(t is not None for t in self.stats_for):
@@ -345,7 +349,8 @@ class NormActOp(Op):
     def fwd(self, training: bool) -> None:
         z = self.z
         if self.kind == "instance":
-            self.sums.zero_()
+            if not self.tape_zeroes_sums:
+                self.sums.zero_()
             check(lib.petsyn_norm_stats(ptr(z.t), ptr(self.sums), self.rows, z.c, z.n, stream_ptr()), "norm_stats")
             check(lib.petsyn_norm_finalize(ptr(self.sums), None, None, None, None, ptr(self.scale), ptr(self.shift),
                                            ptr(self.mean), ptr(self.rstd), self.rows, z.c, z.n, 1, self.eps, 0.0, 1,
@@ -353,7 +358,8 @@ class NormActOp(Op):
         elif self.kind == "group":
             gn = self.gn
             if not self.stats_from_producers:
-                self.sums.zero_()
+                if not self.tape_zeroes_sums:
+                    self.sums.zero_()
                 check(lib.petsyn_norm_stats(ptr(z.t), ptr(self.sums), self.rows, z.c, z.n, stream_ptr()), "norm_stats")
             check(lib.petsyn_norm_finalize(ptr(self.sums), ptr(gn.weight), ptr(gn.bias), None, None, ptr(self.scale),
                                            ptr(self.shift), ptr(self.mean), ptr(self.rstd), self.rows, z.c, z.n,
@@ -361,7 +367,8 @@ class NormActOp(Op):
         elif self.kind == "batch":
             bn = self.bn
             if training:
-                self.sums.zero_()
+                if not self.tape_zeroes_sums:
+                    self.sums.zero_()
                 check(lib.petsyn_norm_stats(ptr(z.t), ptr(self.sums), z.rows, z.c, 1, stream_ptr()), "norm_stats")
                 if bn.num_batches_tracked is not None:
                     bn.num_batches_tracked.add_(1)
@@ -383,7 +390,8 @@ class NormActOp(Op):
         if self.grad_slope is not None and not self.acc_dw:
             self.grad_slope.zero_()
         if self.colsum_conv is not None and not self.acc_dz:
-            self.colsum_conv.dbias_stage.zero_()
+            if not self.colsum_conv.tape_zeroes_dbias:
+                self.colsum_conv.dbias_stage.zero_()
             self.colsum_conv.colsum_done = True
         d = self._desc(True)
         check(lib.petsyn_normact_bwd(C.byref(d), stream_ptr()), "normact_bwd")
@@ -592,14 +600,38 @@ class Tape:
                 p.stats_for[i] = (q, sl.off)
             q.stats_from_producers = True
             shared.append(q)
-        if shared:
-            dev = shared[0].z.t.device
-            self._stats_arena = torch.zeros(sum(q.sums.numel() for q in shared), dtype=torch.float32, device=dev)
+        # every small fp32 accumulator a step starts from zero lives in one of two arenas, cleared by ONE fill at the start
+        # of forward / backward instead of a fill launch per op (~90 launches per AttenUNet step)
+        def arena(pairs):
+            if not pairs:
+                return None
+            dev = getattr(*pairs[0]).device
+            sizes = [(getattr(h, a).numel() + 3) // 4 * 4 for h, a in pairs]            # 16-byte aligned views
+            buf = torch.zeros(sum(sizes), dtype=torch.float32, device=dev)
             off = 0
-            for q in shared:
-                n_ = q.sums.numel()
-                q.sums = self._stats_arena[off:off + n_]
+            for (h, a), n_ in zip(pairs, sizes):
+                old_t = getattr(h, a)
+                setattr(h, a, buf[off:off + old_t.numel()].view_as(old_t))
                 off += n_
+            return buf
+
+        use = not os.environ.get("PETSYN_NO_ZERO_ARENA")
+        normed = [op for op in self.ops if isinstance(op, NormActOp) and op.kind in ("instance", "group", "batch")]
+        own = [op for op in normed if not op.stats_from_producers and use]
+        for op in own:
+            op.tape_zeroes_sums = True
+        self._stats_arena = arena([(op, "sums") for op in shared + own])
+        bwd_pairs = []
+        if use:
+            for op in self.ops:
+                c = op.colsum_conv if isinstance(op, NormActOp) else None
+                if c is not None and not op.acc_dz and c.dbias_stage is not None and not c.tape_zeroes_dbias:
+                    c.tape_zeroes_dbias = True
+                    bwd_pairs.append((c, "dbias_stage"))
+            for op in normed:
+                op.tape_zeroes_bsums = True
+                bwd_pairs.append((op, "bsums"))
+        self._bwd_arena = arena(bwd_pairs)
         self._final = True
 
     def repack(self) -> None:
@@ -643,12 +675,13 @@ class Tape:
         self.timers.setdefault((idx, which), []).append((e0, e1))
 
     _stats_arena: Optional[torch.Tensor] = None
+    _bwd_arena: Optional[torch.Tensor] = None
 
     def forward(self, training: bool) -> None:
         assert self._final
         self.repack()
         if self._stats_arena is not None:
-            self._stats_arena.zero_()              # the producers of fused statistics accumulate into these sums
+            self._stats_arena.zero_()              # statistics sums: accumulated by the statistics passes / fused producers
         if self.timers is not None:
             for i, op in enumerate(self.ops):
                 self._timed(i, "fwd", lambda: op.fwd(training))
@@ -657,6 +690,8 @@ class Tape:
             op.fwd(training)
 
     def backward(self, on_op_done=None) -> None:
+        if self._bwd_arena is not None:
+            self._bwd_arena.zero_()                # bias-gradient column sums + the backward reductions of every norm
         for i in range(len(self.ops) - 1, -1, -1):
             op = self.ops[i]
             if self.timers is not None:

@@ -255,6 +255,8 @@ typedef struct petsyn_normact_desc {
   int32_t t1_stats_c, t1_stats_coff;
   float* t2_stats;           /* the same for destination 2 (same values, another consumer) */
   int32_t t2_stats_c, t2_stats_coff;
+  int32_t sums_prezeroed;    /* bwd: the caller has already cleared the first nsamples * 2 * c floats of `sums` (one fill for
+                              * all the normalisations of a step instead of a memset per call) */
 } petsyn_normact_desc;
 
 /* sums[sample][0:c] = sum z, sums[sample][c:2c] = sum z^2 (fp32, caller-zeroed). */
