@@ -61,6 +61,8 @@ class NormActDesc(C.Structure):
         ("slope_dev", C.c_void_p), ("dslope", C.c_void_p), ("dz_colsum", C.c_void_p),
         ("t1_stats", C.c_void_p), ("t1_stats_c", C.c_int32), ("t1_stats_coff", C.c_int32),
         ("t2_stats", C.c_void_p), ("t2_stats_c", C.c_int32), ("t2_stats_coff", C.c_int32),
+        ("fin_sums", C.c_void_p), ("fin_gamma", C.c_void_p), ("fin_beta", C.c_void_p),
+        ("fin_group_size", C.c_int32), ("fin_eps", C.c_float), ("separate_group_combine", C.c_int32),
         ("sums_prezeroed", C.c_int32),
     ]
 

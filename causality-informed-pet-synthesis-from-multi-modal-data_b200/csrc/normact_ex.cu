@@ -249,6 +249,12 @@ struct Dev {   // device copy of petsyn_normact_desc with typed pointers
   float* dz_colsum;       // optional [C] += column sums of dz
   float* st1; int st1_c, st1_off;   // optional statistics of destination 1 for the norm that consumes it
   float* st2; int st2_c, st2_off;
+  // fused finalize (forward): statistics sums -> scale / shift / mean / rstd inside the apply kernel
+  const float *fin_sums, *fin_gamma, *fin_beta;
+  int fin_gs;
+  float fin_eps;
+  // fused group combine (backward): ka / kb / dgamma / dbeta inside the apply kernel
+  int gc_gs, gc_ns, gc_acc;   // gc_gs > 0: enabled
 };
 
 // ACT < 0: activation codes read from the descriptor at run time (rare combinations); ACT >= 0: act1 == act2 == ACT
@@ -263,11 +269,41 @@ __global__ void __launch_bounds__(256, 3) fwd_kernel(const Dev d) {
   float st[2][8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) st[0][i] = st[1][i] = 0.f;
+  // Fused finalize (Instance / Group normalisation): every CTA derives its sample's scale / shift from the statistics sums
+  // (the arithmetic of finalize_kernel, one thread per channel) into shared memory; the first CTA of each sample also
+  // publishes scale / shift / mean / rstd for the backward pass.  Saves a 4 us launch in front of every apply pass.
+  float* fin = reinterpret_cast<float*>(smem_raw + PfRing::bytes(has_res ? 2 : 1));
+  if (d.fin_sums != nullptr) {
+    const float* sm = d.fin_sums + (int64_t)s * 2 * d.C;
+    const double cnt = (double)d.rows * d.fin_gs;
+    for (int c = threadIdx.x; c < d.C; c += blockDim.x) {
+      const int g0 = c / d.fin_gs * d.fin_gs;
+      double a = 0, b = 0;
+      for (int j = 0; j < d.fin_gs; ++j) { a += sm[g0 + j]; b += sm[d.C + g0 + j]; }
+      const double mean = a / cnt;
+      double var = b / cnt - mean * mean;
+      if (var < 0) var = 0;
+      const double rstd = 1.0 / sqrt(var + (double)d.fin_eps);
+      const float g = d.fin_gamma ? d.fin_gamma[c] : 1.f, be = d.fin_beta ? d.fin_beta[c] : 0.f;
+      const float scl = (float)(g * rstd), shf = (float)(be - mean * g * rstd);
+      fin[c] = scl;
+      fin[d.C + c] = shf;
+      if (blockIdx.x == 0) {
+        const int i = s * d.C + c;
+        const_cast<float*>(d.scale)[i] = scl;
+        const_cast<float*>(d.shift)[i] = shf;
+        const_cast<float*>(d.mean)[i] = (float)mean;
+        const_cast<float*>(d.rstd)[i] = (float)rstd;
+      }
+    }
+    __syncthreads();
+  }
   if (it.active) {
     const int64_t base = (int64_t)s * d.rows;
     const int so = d.per_sample ? s * d.C : 0;
     F8 sc = splat(1.f), sh = splat(0.f);
-    if (d.scale) { sc = load8f(d.scale + so + it.tx * 8); sh = load8f(d.shift + so + it.tx * 8); }
+    if (d.fin_sums != nullptr) { sc = load8f(fin + it.tx * 8); sh = load8f(fin + d.C + it.tx * 8); }
+    else if (d.scale) { sc = load8f(d.scale + so + it.tx * 8); sh = load8f(d.shift + so + it.tx * 8); }
     const float slope = d.slope_dev ? __ldg(d.slope_dev) : d.slope;
     const int a1 = ACT >= 0 ? ACT : d.act1, a2 = ACT >= 0 ? ACT : d.act2;
     const int64_t stride = (int64_t)gridDim.x * it.rpp;
@@ -317,7 +353,7 @@ __global__ void __launch_bounds__(256, 3) fwd_kernel(const Dev d) {
     }
   }
   if (want_stats) {
-    float* smem_f = reinterpret_cast<float*>(smem_raw + PfRing::bytes(has_res ? 2 : 1));
+    float* smem_f = fin + (d.fin_sums != nullptr ? 2 * d.C : 0);
     block_reduce_channels_to<2>(it, st, smem_f, d.st1 ? d.st1 + (int64_t)s * 2 * d.st1_c : nullptr, d.st1_c, d.st1_off,
                                 d.st2 ? d.st2 + (int64_t)s * 2 * d.st2_c : nullptr, d.st2_c, d.st2_off, d.C);
   }
@@ -397,7 +433,7 @@ __global__ void __launch_bounds__(256, 2) bwd_apply_kernel(const Dev d) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   float* smem_f = reinterpret_cast<float*>(smem_raw + PfRing::bytes(d.t2 != nullptr ? 3 : 2));
   RowIter it(d.C);
-  if (blockIdx.x == 0 && blockIdx.y == 0 && d.dgamma != nullptr && d.ka == nullptr) {
+  if (blockIdx.x == 0 && blockIdx.y == 0 && d.dgamma != nullptr && d.ka == nullptr && d.gc_gs == 0) {
     for (int c = threadIdx.x; c < d.C; c += blockDim.x) {
       d.dbeta[c] = d.sums[c];
       d.dgamma[c] = d.sums[d.C + c];
@@ -406,6 +442,38 @@ __global__ void __launch_bounds__(256, 2) bwd_apply_kernel(const Dev d) {
   float csum[1][8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) csum[0][i] = 0.f;
+  // Fused group combine (GroupNorm / per-sample affine): with S0 = sum g, S1 = sum g*zhat per (sample, channel) from the reduce pass,
+  //   ka[c] = rstd[c] * sum_{c' in group(c)} gamma[c'] S0[c'] / (rows * group_size),  kb likewise with S1  (this CTA's sample);
+  //   dgamma[c] = sum_s S1[s,c], dbeta[c] = sum_s S0[s,c]                                      (CTA (0, 0) only)
+  float* comb = smem_f + (d.dz_colsum != nullptr ? it.rpp * d.C : 0);
+  if (d.gc_gs > 0) {
+    const int s = blockIdx.y;
+    const float* sm = d.sums + (int64_t)s * 2 * d.C;
+    const float inv = 1.f / ((float)d.rows * (float)d.gc_gs);
+    for (int c = threadIdx.x; c < d.C; c += blockDim.x) {
+      const int g0 = c / d.gc_gs * d.gc_gs;
+      float a = 0.f, b = 0.f;
+      for (int j = 0; j < d.gc_gs; ++j) {
+        const float ga = d.gamma ? d.gamma[g0 + j] : 1.f;
+        a += ga * sm[g0 + j];
+        b += ga * sm[d.C + g0 + j];
+      }
+      const float r = d.rstd[s * d.C + c];
+      comb[c] = r * a * inv;
+      comb[d.C + c] = r * b * inv;
+    }
+    if (blockIdx.x == 0 && blockIdx.y == 0 && d.dgamma != nullptr) {
+      for (int c = threadIdx.x; c < d.C; c += blockDim.x) {
+        float a = 0.f, b = 0.f;
+        for (int q = 0; q < d.gc_ns; ++q) {
+          a += d.sums[(int64_t)q * 2 * d.C + d.C + c];
+          b += d.sums[(int64_t)q * 2 * d.C + c];
+        }
+        if (d.gc_acc) { d.dgamma[c] += a; d.dbeta[c] += b; } else { d.dgamma[c] = a; d.dbeta[c] = b; }
+      }
+    }
+    __syncthreads();
+  }
   if (it.active) {
   const int s = blockIdx.y;
   const int64_t base = (int64_t)s * d.rows;
@@ -417,7 +485,12 @@ __global__ void __launch_bounds__(256, 2) bwd_apply_kernel(const Dev d) {
     const F8 mu = load8f(d.mean + so + it.tx * 8), rs = load8f(d.rstd + so + it.tx * 8);
     const F8 ga = d.gamma ? load8f(d.gamma + it.tx * 8) : splat(1.f);
     F8 k1, k2;
-    if (d.ka != nullptr) {                     // group statistics and/or per-sample affine: constants precomputed
+    if (d.gc_gs > 0) {                         // group statistics and/or per-sample affine: constants from the prologue
+      k1 = load8f(comb + it.tx * 8);
+      k2 = load8f(comb + d.C + it.tx * 8);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) k0.v[i] = ga.v[i] * rs.v[i];
+    } else if (d.ka != nullptr) {              // ... or precomputed by group_combine_kernel
       k1 = load8f(d.ka + so + it.tx * 8);
       k2 = load8f(d.kb + so + it.tx * 8);
 #pragma unroll
@@ -601,6 +674,12 @@ static int32_t to_dev(const petsyn_normact_desc* d, Dev* o) {
   o->dz_colsum = d->dz_colsum;
   o->st1 = d->t1_stats; o->st1_c = d->t1_stats_c; o->st1_off = d->t1_stats_coff;
   o->st2 = d->t2_stats; o->st2_c = d->t2_stats_c; o->st2_off = d->t2_stats_coff;
+  o->fin_sums = d->fin_sums; o->fin_gamma = d->fin_gamma; o->fin_beta = d->fin_beta;
+  o->fin_gs = d->fin_group_size > 1 ? d->fin_group_size : 1; o->fin_eps = d->fin_eps;
+  o->gc_gs = o->gc_ns = o->gc_acc = 0;
+  PETSYN_REQUIRE(d->fin_sums == nullptr || (d->scale && d->shift && d->mean && d->rstd && d->per_sample_stats &&
+                                            d->c % o->fin_gs == 0),
+                 "fused finalize needs per-sample statistics and the scale / shift / mean / rstd outputs");
   PETSYN_REQUIRE(!(d->t2_stats && !d->t2), "t2_stats without a second destination");
   PETSYN_REQUIRE(!(d->dz_colsum && d->dz_accumulate), "dz_colsum cannot be combined with dz_accumulate");
   return PETSYN_OK;
@@ -668,7 +747,7 @@ int32_t petsyn_normact_fwd(const petsyn_normact_desc* desc, void* stream) {
   dim3 grid((unsigned)row_blocks(d.rows, d.C, desc->nsamples), (unsigned)desc->nsamples);
   PETSYN_REQUIRE(!(d.st1 || d.st2) || desc->act1 == desc->act2 || d.t2 == nullptr,
                  "destination statistics need one activation for both destinations");
-  const size_t fwd_smem = PfRing::bytes(d.res ? 2 : 1) +
+  const size_t fwd_smem = PfRing::bytes(d.res ? 2 : 1) + (d.fin_sums ? (size_t)2 * d.C * sizeof(float) : 0) +
                           ((d.st1 || d.st2) ? (size_t)(256 / (d.C / 8)) * 2 * d.C * sizeof(float) : 0);
   PETSYN_NX_DISPATCH(fwd_kernel, grid, fwd_smem, as_stream(stream), d);
   return check_launch("normact fwd_kernel");
@@ -691,7 +770,9 @@ int32_t petsyn_normact_bwd(const petsyn_normact_desc* desc, void* stream) {
     rc = check_launch("normact bwd_reduce_kernel");
     if (rc) return rc;
     const int gs = desc->group_size > 1 ? desc->group_size : 1;
-    if (d.per_sample && (gs > 1 || d.gamma != nullptr)) {
+    if (d.per_sample && (gs > 1 || d.gamma != nullptr) && !desc->separate_group_combine) {
+      d.gc_gs = gs; d.gc_ns = nst; d.gc_acc = desc->affine_accumulate;      // combined inside bwd_apply_kernel's prologue
+    } else if (d.per_sample && (gs > 1 || d.gamma != nullptr)) {
       // the sums workspace holds [S0|S1] for every sample followed by ka and kb: 4 * nsamples * C floats
       float* ka = d.sums + (size_t)nst * 2 * d.C;
       float* kb = ka + (size_t)nst * d.C;
@@ -705,7 +786,8 @@ int32_t petsyn_normact_bwd(const petsyn_normact_desc* desc, void* stream) {
     }
   }
   {
-    const size_t apply_smem = PfRing::bytes(d.t2 ? 3 : 2) + (d.dz_colsum ? (size_t)(256 / (d.C / 8)) * d.C * sizeof(float) : 0);
+    const size_t apply_smem = PfRing::bytes(d.t2 ? 3 : 2) + (d.dz_colsum ? (size_t)(256 / (d.C / 8)) * d.C * sizeof(float) : 0) +
+                              (d.gc_gs > 0 ? (size_t)2 * d.C * sizeof(float) : 0);
     PETSYN_NX_DISPATCH(bwd_apply_kernel, grid, apply_smem, st, d);
   }
   return check_launch("normact bwd_apply_kernel");

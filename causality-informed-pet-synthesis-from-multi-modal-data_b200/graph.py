@@ -256,6 +256,10 @@ class ConvOp(Op):
             self._bwd_dx(dz)
 
 
+# debugging / A-B switch: run norm finalize and the backward group combine as their own launches (the first version)
+SEPARATE_FINALIZE = bool(os.environ.get("PETSYN_SEPARATE_FINALIZE"))
+
+
 class NormActOp(Op):
     """dst_i = act(norm(z)) [+ res] for one or two destinations (channel slices)."""
 
@@ -302,6 +306,15 @@ class NormActOp(Op):
         d.dz_accumulate = int(self.acc_dz)
         if self.kind != "none":
             d.scale, d.shift = ptr(self.scale), ptr(self.shift)
+            if not backward and self.kind in ("instance", "group") and not SEPARATE_FINALIZE:
+                # finalize folded into the apply launch: sums in, scale / shift / mean / rstd out
+                d.fin_sums, d.mean, d.rstd = ptr(self.sums), ptr(self.mean), ptr(self.rstd)
+                if self.kind == "group":
+                    d.fin_gamma, d.fin_beta = ptr(self.gn.weight), ptr(self.gn.bias)
+                    d.fin_group_size, d.fin_eps = z.c // self.gn.num_groups, self.gn.eps
+                else:
+                    d.fin_group_size, d.fin_eps = 1, self.eps
+            d.separate_group_combine = int(SEPARATE_FINALIZE)
             if backward:
                 d.mean, d.rstd = ptr(self.mean), ptr(self.rstd)
                 d.sums = ptr(self.bsums)
@@ -352,18 +365,20 @@ class NormActOp(Op):
             if not self.tape_zeroes_sums:
                 self.sums.zero_()
             check(lib.petsyn_norm_stats(ptr(z.t), ptr(self.sums), self.rows, z.c, z.n, stream_ptr()), "norm_stats")
-            check(lib.petsyn_norm_finalize(ptr(self.sums), None, None, None, None, ptr(self.scale), ptr(self.shift),
-                                           ptr(self.mean), ptr(self.rstd), self.rows, z.c, z.n, 1, self.eps, 0.0, 1,
-                                           stream_ptr()), "norm_finalize")
+            if SEPARATE_FINALIZE:        # default: folded into the apply launch below (fin_* fields of the descriptor)
+                check(lib.petsyn_norm_finalize(ptr(self.sums), None, None, None, None, ptr(self.scale), ptr(self.shift),
+                                               ptr(self.mean), ptr(self.rstd), self.rows, z.c, z.n, 1, self.eps, 0.0, 1,
+                                               stream_ptr()), "norm_finalize")
         elif self.kind == "group":
             gn = self.gn
             if not self.stats_from_producers:
                 if not self.tape_zeroes_sums:
                     self.sums.zero_()
                 check(lib.petsyn_norm_stats(ptr(z.t), ptr(self.sums), self.rows, z.c, z.n, stream_ptr()), "norm_stats")
-            check(lib.petsyn_norm_finalize(ptr(self.sums), ptr(gn.weight), ptr(gn.bias), None, None, ptr(self.scale),
-                                           ptr(self.shift), ptr(self.mean), ptr(self.rstd), self.rows, z.c, z.n,
-                                           z.c // gn.num_groups, gn.eps, 0.0, 1, stream_ptr()), "norm_finalize")
+            if SEPARATE_FINALIZE:
+                check(lib.petsyn_norm_finalize(ptr(self.sums), ptr(gn.weight), ptr(gn.bias), None, None, ptr(self.scale),
+                                               ptr(self.shift), ptr(self.mean), ptr(self.rstd), self.rows, z.c, z.n,
+                                               z.c // gn.num_groups, gn.eps, 0.0, 1, stream_ptr()), "norm_finalize")
         elif self.kind == "batch":
             bn = self.bn
             if training:

@@ -255,6 +255,15 @@ typedef struct petsyn_normact_desc {
   int32_t t1_stats_c, t1_stats_coff;
   float* t2_stats;           /* the same for destination 2 (same values, another consumer) */
   int32_t t2_stats_c, t2_stats_coff;
+  const float* fin_sums;     /* fwd, optional: fuse petsyn_norm_finalize (Instance / Group normalisation) into this launch.
+                              * [nsamples][2][c] statistics sums (petsyn_norm_stats layout); scale / shift / mean / rstd then
+                              * are OUTPUTS ([nsamples][c], written for the backward pass); needs per_sample_stats */
+  const float* fin_gamma;    /* [c] affine weight or NULL */
+  const float* fin_beta;     /* [c] affine bias or NULL */
+  int32_t fin_group_size;    /* channels sharing their statistics (GroupNorm); <= 1: per channel */
+  float fin_eps;
+  int32_t separate_group_combine; /* bwd: 1 = run the GroupNorm / per-sample-affine constant combine as its own launch (the
+                              * default folds it into the apply kernel's prologue) */
   int32_t sums_prezeroed;    /* bwd: the caller has already cleared the first nsamples * 2 * c floats of `sums` (one fill for
                               * all the normalisations of a step instead of a memset per call) */
 } petsyn_normact_desc;
