@@ -256,10 +256,10 @@ def run_petsyn(args, ngf, shape, batch):
     torch.cuda.synchronize()
     per_kernel = {k: statistics.mean(a.elapsed_time(b) for a, b in v) for k, v in timers.items()}
 
-    t = torch.tensor([ms_total, ms_e2e, ms_loader], dtype=torch.float64, device=dev)
+    t = torch.tensor([ms_total, ms_e2e], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total, ms_e2e, ms_loader = t.tolist()
+    ms_total, ms_e2e = t.tolist()
 
     if rank == 0:
         eng = trainer.eng
@@ -429,10 +429,10 @@ def run_petsyn_bmgan(args, cfg_name, shape, batch):
     barrier()
     ms_e2e = f0.elapsed_time(f1)
     clocks = sampler.stop() if rank == 0 else None
-    t = torch.tensor([ms_total, ms_e2e, ms_loader], dtype=torch.float64, device=dev)
+    t = torch.tensor([ms_total, ms_e2e], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total, ms_e2e, ms_loader = t.tolist()
+    ms_total, ms_e2e = t.tolist()
     if rank == 0:
         peaks = {}
         try:
@@ -913,10 +913,10 @@ def run_petsyn_infer(args, family, shape, micro):
         barrier()
         ms_e2e = f0.elapsed_time(f1)
     clocks = sampler.stop() if rank == 0 else None
-    t = torch.tensor([ms_total, ms_e2e, ms_loader], dtype=torch.float64, device=dev)
+    t = torch.tensor([ms_total, ms_e2e], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total, ms_e2e, ms_loader = t.tolist()
+    ms_total, ms_e2e = t.tolist()
     if rank == 0:
         peaks = {}
         try:
