@@ -269,6 +269,27 @@ __global__ void __launch_bounds__(256, 3) fwd_kernel(const Dev d) {
   float st[2][8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) st[0][i] = st[1][i] = 0.f;
+  const int64_t base = (int64_t)s * d.rows;
+  const int64_t stride = (int64_t)gridDim.x * it.rpp;
+  PfRing pf(smem_raw, has_res ? 2 : 1);
+  // Row order alternates between consecutive passes over the same tensor so that each pass starts with what the
+  // previous one touched last (still in the 126 MB L2): producers (convs) write ascending, statistics / backward-reduce
+  // read DESCENDING, the apply passes read ascending again
+  const int64_t q0 = (int64_t)blockIdx.x * it.rpp + it.ty;
+  const __nv_bfloat16* zsrc = d.z + it.tx * 8;
+  const __nv_bfloat16* rsrc = has_res ? d.res + d.cor + it.tx * 8 : nullptr;
+  auto issue = [&](int k) {
+    const int64_t q = q0 + k * stride;
+    if (q < d.rows) {
+      const int64_t r = base + q;
+      pf.issue(k % kPf, 0, zsrc + r * d.C);
+      if (has_res) pf.issue(k % kPf, 1, rsrc + r * d.csr);
+    }
+    PfRing::commit();
+  };
+  // the first rows are in flight before the finalize prologue below, so its latency hides behind the HBM round trip
+  if (it.active)
+    for (int k = 0; k < kPf - 1; ++k) issue(k);
   // Fused finalize (Instance / Group normalisation): every CTA derives its sample's scale / shift from the statistics sums
   // (the arithmetic of finalize_kernel, one thread per channel) into shared memory; the first CTA of each sample also
   // publishes scale / shift / mean / rstd for the backward pass.  Saves a 4 us launch in front of every apply pass.
@@ -299,31 +320,12 @@ __global__ void __launch_bounds__(256, 3) fwd_kernel(const Dev d) {
     __syncthreads();
   }
   if (it.active) {
-    const int64_t base = (int64_t)s * d.rows;
     const int so = d.per_sample ? s * d.C : 0;
     F8 sc = splat(1.f), sh = splat(0.f);
     if (d.fin_sums != nullptr) { sc = load8f(fin + it.tx * 8); sh = load8f(fin + d.C + it.tx * 8); }
     else if (d.scale) { sc = load8f(d.scale + so + it.tx * 8); sh = load8f(d.shift + so + it.tx * 8); }
     const float slope = d.slope_dev ? __ldg(d.slope_dev) : d.slope;
     const int a1 = ACT >= 0 ? ACT : d.act1, a2 = ACT >= 0 ? ACT : d.act2;
-    const int64_t stride = (int64_t)gridDim.x * it.rpp;
-    PfRing pf(smem_raw, has_res ? 2 : 1);
-    // Row order alternates between consecutive passes over the same tensor so that each pass starts with what the
-    // previous one touched last (still in the 126 MB L2): producers (convs) write ascending, statistics / backward-reduce
-    // read DESCENDING, the apply passes read ascending again
-    const int64_t q0 = (int64_t)blockIdx.x * it.rpp + it.ty;
-    const __nv_bfloat16* zsrc = d.z + it.tx * 8;
-    const __nv_bfloat16* rsrc = has_res ? d.res + d.cor + it.tx * 8 : nullptr;
-    auto issue = [&](int k) {
-      const int64_t q = q0 + k * stride;
-      if (q < d.rows) {
-        const int64_t r = base + q;
-        pf.issue(k % kPf, 0, zsrc + r * d.C);
-        if (has_res) pf.issue(k % kPf, 1, rsrc + r * d.csr);
-      }
-      PfRing::commit();
-    };
-    for (int k = 0; k < kPf - 1; ++k) issue(k);
     int k = 0;
     for (int64_t q = q0; q < d.rows; q += stride, ++k) {
       issue(k + kPf - 1);
@@ -442,6 +444,27 @@ __global__ void __launch_bounds__(256, 2) bwd_apply_kernel(const Dev d) {
   float csum[1][8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) csum[0][i] = 0.f;
+  const int64_t base = (int64_t)blockIdx.y * d.rows;
+  const int64_t stride = (int64_t)gridDim.x * it.rpp;
+  const bool has_t2 = d.t2 != nullptr;
+  PfRing pf(smem_raw, has_t2 ? 3 : 2);
+  const int64_t q0 = (int64_t)blockIdx.x * it.rpp + it.ty;              // ascending row order (see fwd_kernel)
+  const __nv_bfloat16* zsrc = d.z + it.tx * 8;
+  const __nv_bfloat16* asrc = d.t1 + d.co1 + it.tx * 8;
+  const __nv_bfloat16* bsrc = has_t2 ? d.t2 + d.co2 + it.tx * 8 : nullptr;
+  auto issue = [&](int k) {
+    const int64_t q = q0 + k * stride;
+    if (q < d.rows) {
+      const int64_t r = base + q;
+      pf.issue(k % kPf, 0, zsrc + r * d.C);
+      pf.issue(k % kPf, 1, asrc + r * d.cs1);
+      if (has_t2) pf.issue(k % kPf, 2, bsrc + r * d.cs2);
+    }
+    PfRing::commit();
+  };
+  // first rows in flight before the constant prologue below (its latency hides behind the HBM round trip)
+  if (it.active)
+    for (int k = 0; k < kPf - 1; ++k) issue(k);
   // Fused group combine (GroupNorm / per-sample affine): with S0 = sum g, S1 = sum g*zhat per (sample, channel) from the reduce pass,
   //   ka[c] = rstd[c] * sum_{c' in group(c)} gamma[c'] S0[c'] / (rows * group_size),  kb likewise with S1  (this CTA's sample);
   //   dgamma[c] = sum_s S1[s,c], dbeta[c] = sum_s S0[s,c]                                      (CTA (0, 0) only)
@@ -476,7 +499,6 @@ __global__ void __launch_bounds__(256, 2) bwd_apply_kernel(const Dev d) {
   }
   if (it.active) {
   const int s = blockIdx.y;
-  const int64_t base = (int64_t)s * d.rows;
   const int so = d.per_sample ? s * d.C : 0;
   // dz = k0*g - k1 - zhat*k2 with zhat = (x - mu)*rstd   ==   k0*g - kA - x*kB,  kA = k1 - mu*rstd*k2, kB = rstd*k2
   F8 sc = splat(1.f), sh = splat(0.f), k0 = splat(1.f), kA = splat(0.f), kB = splat(0.f);
@@ -514,24 +536,6 @@ __global__ void __launch_bounds__(256, 2) bwd_apply_kernel(const Dev d) {
   }
   const float slope = d.slope_dev ? __ldg(d.slope_dev) : d.slope;
   const int a1 = ACT >= 0 ? ACT : d.act1, a2 = ACT >= 0 ? ACT : d.act2;
-  const int64_t stride = (int64_t)gridDim.x * it.rpp;
-  const bool has_t2 = d.t2 != nullptr;
-  PfRing pf(smem_raw, has_t2 ? 3 : 2);
-  const int64_t q0 = (int64_t)blockIdx.x * it.rpp + it.ty;              // ascending row order (see fwd_kernel)
-  const __nv_bfloat16* zsrc = d.z + it.tx * 8;
-  const __nv_bfloat16* asrc = d.t1 + d.co1 + it.tx * 8;
-  const __nv_bfloat16* bsrc = has_t2 ? d.t2 + d.co2 + it.tx * 8 : nullptr;
-  auto issue = [&](int k) {
-    const int64_t q = q0 + k * stride;
-    if (q < d.rows) {
-      const int64_t r = base + q;
-      pf.issue(k % kPf, 0, zsrc + r * d.C);
-      pf.issue(k % kPf, 1, asrc + r * d.cs1);
-      if (has_t2) pf.issue(k % kPf, 2, bsrc + r * d.cs2);
-    }
-    PfRing::commit();
-  };
-  for (int k = 0; k < kPf - 1; ++k) issue(k);
   int k = 0;
   for (int64_t q = q0; q < d.rows; q += stride, ++k) {
     issue(k + kPf - 1);
