@@ -194,6 +194,9 @@ class PairVolumeLoader:
         batches = [idx[i:i + self.bs] for i in range(0, len(idx), self.bs)]
         if self.drop_last and batches and len(batches[-1]) < self.bs:
             batches.pop()
+        # a previous (possibly abandoned) iteration may have left consumer work in flight on the slots: order this epoch's
+        # copies and preparation kernels after everything the consumer has enqueued so far
+        self.copy_stream.wait_stream(torch.cuda.current_stream(self.dev))
         pending = self._stage(self.slots[0], batches[0]) if batches else None
         for k in range(len(batches)):
             cur = pending
