@@ -41,6 +41,36 @@ def test_struct_layout_matches_header(petsyn):
     assert ctypes.sizeof(_cabi.ConvDesc) == 4 * len(fields)
 
 
+def _parse_struct(name):
+    """[(field name, ctypes type)] of a struct in include/petsyn.h, in declaration order."""
+    import ctypes as C
+    src = open(os.path.join(ROOT, "include", "petsyn.h")).read()
+    body = src[src.index("typedef struct %s {" % name):src.index("} %s;" % name)]
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    out = []
+    for stmt in body.split("{", 1)[1].split(";"):
+        stmt = " ".join(stmt.split())
+        if not stmt:
+            continue
+        m = re.match(r"(const )?(void|float|int32_t|int64_t)\s*(\*)?\s*(.+)", stmt)
+        assert m, stmt
+        ptr, base = m.group(3), m.group(2)
+        ctype = C.c_void_p if ptr else {"float": C.c_float, "int32_t": C.c_int32, "int64_t": C.c_int64}[base]
+        out += [(f.strip(), ctype) for f in m.group(4).split(",")]
+    return out
+
+
+@pytest.mark.parametrize("cname,attr", [("petsyn_normact_desc", "NormActDesc"), ("petsyn_volume_src", "VolumeSrc")])
+def test_descriptor_structs_match_header(petsyn, cname, attr):
+    """Field order and types of the ctypes mirrors follow the header exactly (a mismatch would shift every later field)."""
+    from petsyn_b200 import _cabi
+    want = _parse_struct(cname)
+    got = list(getattr(_cabi, attr)._fields_)
+    assert [n for n, _ in got] == [n for n, _ in want]
+    for (n, a), (_, b) in zip(got, want):
+        assert a is b, (n, a, b)
+
+
 def test_bad_descriptor_is_rejected_without_a_gpu(petsyn):
     """Validation happens before any CUDA call, so the ValueError contract is testable on a CPU box."""
     import ctypes as C
