@@ -265,11 +265,13 @@ class AttenUNet(nn.Module):
 class _AttenFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx_, eng, x, context, *params):
-        ctx_.eng = eng
-        return eng.forward(x, context).clone()
+        y = eng.forward(x, context).clone()
+        eng.stamp(ctx_, (x, context))
+        return y
 
     @staticmethod
     def backward(ctx_, dy):
+        ctx_.eng.restore(ctx_)
         grads = ctx_.eng.backward(dy.contiguous().float())
         return (None, None, None, *grads)
 
@@ -506,10 +508,11 @@ class _AttenEngine(_EngineBase):
 
     def forward(self, x: torch.Tensor, context: torch.Tensor) -> torch.Tensor:
         n, _, D, H, W = self.shape
+        self.generation += 1
         self.context = context
         check(lib.petsyn_concat_latent(ptr(x), ptr(x), ptr(self.inp.t), D * H * W, n, 0, self.CPAD, stream_ptr()),
               "concat_latent")
-        self.tape.forward(self.module.training)
+        self.tape.forward(self.training())
         check(lib.petsyn_take_channel0(ptr(self.head.zf), ptr(self.y), self.y.numel(), self.head.cout, stream_ptr()),
               "take_channel0")
         return self.y

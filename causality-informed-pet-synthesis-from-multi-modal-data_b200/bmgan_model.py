@@ -136,7 +136,7 @@ class dense_unet_generator(nn.Module):
         params = eng.params
         if torch.is_grad_enabled() and any(p.requires_grad for p in params):
             return _TapeFn.apply(eng, x, z, *params)
-        return eng.forward(x, z)
+        return eng.forward(x, z).clone()        # the engine owns its output buffer: hand out a copy (no aliasing across calls)
 
 
 class _TapeFn(torch.autograd.Function):
@@ -144,12 +144,14 @@ class _TapeFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, eng, x, extra, *params):
-        ctx.eng = eng
         ctx.need_dx = x.requires_grad
-        return eng.forward(x, extra).clone()
+        y = eng.forward(x, extra).clone()
+        eng.stamp(ctx, (x, extra))
+        return y
 
     @staticmethod
     def backward(ctx, dy):
+        ctx.eng.restore(ctx)
         dx, grads = ctx.eng.backward(dy.contiguous().float(), need_dx=ctx.need_dx)
         return (None, dx, None, *grads)
 
@@ -164,6 +166,38 @@ class _EngineBase:
         self.params: List[nn.Parameter] = []
         self._slots: Optional[List[torch.Tensor]] = None
         self._bind: List[Tuple[object, str, nn.Parameter]] = []     # (op, attribute, parameter)
+        # An engine holds ONE set of saved activations.  Every forward bumps `generation`; an autograd node remembers the
+        # generation it ran in and its inputs, and `restore` re-runs the forward when a later call has overwritten them.
+        self.generation = 0
+        self._training_override: Optional[bool] = None
+
+    # ------------------------------------------------------------------------------------------------ re-entrancy
+    def training(self) -> bool:
+        return self.module.training if self._training_override is None else self._training_override
+
+    def stamp(self, ctx, inputs) -> None:
+        """Called by the autograd bridge right after its forward: remember what is needed to redo that forward."""
+        ctx.eng, ctx.gen, ctx.mode = self, self.generation, self.training()
+        ctx.versions = tuple(p._version for p in self.params)
+        ctx.save_for_backward(*inputs)
+
+    def restore(self, ctx) -> None:
+        """Called by the autograd bridge before its backward.  Two forwards followed by one backward (the encoder in
+        train_bmgan.py:170-180; D(fake) + D(real) summed) leave the activations of the LAST call in the engine: the
+        earlier node re-runs its forward from the saved inputs first (same mode; BatchNorm running statistics are not
+        moved a second time), so each node backpropagates through its own activations."""
+        if self.generation == ctx.gen:
+            return
+        if tuple(p._version for p in self.params) != ctx.versions:
+            raise RuntimeError("a parameter of this petsyn module was modified in place between forward and backward")
+        self._training_override = ctx.mode
+        graph.RunState.freeze_running_stats = True
+        try:
+            self.forward(*ctx.saved_tensors)
+        finally:
+            graph.RunState.freeze_running_stats = False
+            self._training_override = None
+        ctx.gen = self.generation
 
     def _conv(self, x: Sl, conv: nn.Module, **kw) -> ConvOp:
         op = ConvOp(x, conv.weight, conv.bias, **kw)
@@ -331,9 +365,10 @@ class _GenEngine(_EngineBase):
     # ------------------------------------------------------------------------------------------------
     def forward(self, x: torch.Tensor, z: torch.Tensor) -> torch.Tensor:
         n, _, D, H, W = self.shape
+        self.generation += 1
         check(lib.petsyn_concat_latent(ptr(x), ptr(z), ptr(self.inp.t), D * H * W, n, z.shape[1], self.CPAD_IN,
                                        stream_ptr()), "concat_latent")
-        self.tape.forward(self.module.training)
+        self.tape.forward(self.training())
         check(lib.petsyn_take_channel0(ptr(self.head.zf), ptr(self.y), self.y.numel(), self.head.cout, stream_ptr()),
               "take_channel0")
         return self.y
@@ -417,7 +452,7 @@ class patch_discriminator(nn.Module):
         eng = self.engine_for(x)
         if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in eng.params)):
             return _TapeFn.apply(eng, x, None, *eng.params)
-        return eng.forward(x, None)
+        return eng.forward(x, None).clone()     # e.g. D(fake) then D(real) under no_grad (train_bmgan.py:243-247)
 
 
 class _StemOp(graph.Op):
@@ -508,8 +543,9 @@ class _DiscEngine(_EngineBase):
                 op.acc_dw = accumulate
 
     def forward(self, x: torch.Tensor, _unused=None) -> torch.Tensor:
+        self.generation += 1
         self.x = x
-        self.tape.forward(self.module.training)
+        self.tape.forward(self.training())
         check(lib.petsyn_take_channel0(ptr(self.head.zf), ptr(self.logits), self.logits.numel(), self.head.cout,
                                        stream_ptr()), "take_channel0")
         return self.logits
@@ -591,11 +627,13 @@ class ResNet_encoder(nn.Module):
 class _EncFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, eng, x, *params):
-        ctx.eng = eng
-        return eng.forward(x).clone()
+        out = eng.forward(x).clone()
+        eng.stamp(ctx, (x,))
+        return out
 
     @staticmethod
     def backward(ctx, dout):
+        ctx.eng.restore(ctx)
         grads = ctx.eng.backward(dout.contiguous().float())
         return (None, None, *grads)
 
@@ -704,9 +742,10 @@ class _EncEngine(_EngineBase):
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         n, _, D, H, W = self.shape
+        self.generation += 1
         check(lib.petsyn_concat_latent(ptr(x), ptr(x), ptr(self.inp.t), D * H * W, n, 0, self.CPAD_IN, stream_ptr()),
               "concat_latent")
-        self.tape.forward(self.module.training)
+        self.tape.forward(self.training())
         return self.heads.out
 
     def backward(self, dout: torch.Tensor, out: Optional[Dict[int, torch.Tensor]] = None, accumulate: bool = False):

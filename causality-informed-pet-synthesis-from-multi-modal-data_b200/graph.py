@@ -70,6 +70,14 @@ class Op:
 _SIDE_STREAMS: Dict[int, torch.cuda.Stream] = {}
 
 
+class RunState:
+    """Process-wide switches read by the ops while a tape runs."""
+    # True while an engine re-runs a forward pass only to restore the activations of an earlier autograd node (two
+    # forwards, one backward: train_bmgan.py:170-180): BatchNorm normalises with the batch statistics again but must
+    # not move its running statistics / num_batches_tracked a second time.
+    freeze_running_stats = False
+
+
 def _side_stream(dev) -> torch.cuda.Stream:
     s = _SIDE_STREAMS.get(dev.index)
     if s is None:
@@ -269,6 +277,7 @@ class NormActOp(Op):
         assert kind in ("instance", "batch", "group", "none") and 1 <= len(dsts) <= 2
         self.gn = gn                            # nn.GroupNorm (kind == "group"): affine, num_groups, eps
         self.acc_dz = False
+        self.fwd_batch_stats = True             # kind == "batch": the last forward normalised with batch statistics
         self.colsum_conv: Optional["ConvOp"] = None   # conv that produced z: its bias gradient is a by-product of bwd
         # statistics as a by-product: a "none" op may sum what it writes for the norm that consumes the destination ...
         self.stats_from_producers = False              # ... and that norm then skips its own statistics pass
@@ -381,17 +390,21 @@ class NormActOp(Op):
                                                z.c // gn.num_groups, gn.eps, 0.0, 1, stream_ptr()), "norm_finalize")
         elif self.kind == "batch":
             bn = self.bn
-            if training:
+            if bn.momentum is None:
+                raise NotImplementedError("BatchNorm3d(momentum=None) (cumulative moving average) is not implemented")
+            use_batch = training or bn.running_mean is None
+            freeze = RunState.freeze_running_stats
+            if use_batch:
                 if not self.tape_zeroes_sums:
                     self.sums.zero_()
                 check(lib.petsyn_norm_stats(ptr(z.t), ptr(self.sums), z.rows, z.c, 1, stream_ptr()), "norm_stats")
-                if bn.num_batches_tracked is not None:
+                if bn.num_batches_tracked is not None and not freeze:
                     bn.num_batches_tracked.add_(1)
-            mom = 0.1 if bn.momentum is None else bn.momentum
-            check(lib.petsyn_norm_finalize(ptr(self.sums), ptr(bn.weight), ptr(bn.bias), ptr(bn.running_mean),
-                                           ptr(bn.running_var), ptr(self.scale), ptr(self.shift), ptr(self.mean),
-                                           ptr(self.rstd), z.rows, z.c, 1, 1, bn.eps, mom, int(training), stream_ptr()),
-                  "norm_finalize")
+            self.fwd_batch_stats = use_batch
+            rm, rv = (None, None) if (use_batch and freeze) else (ptr(bn.running_mean), ptr(bn.running_var))
+            check(lib.petsyn_norm_finalize(ptr(self.sums), ptr(bn.weight), ptr(bn.bias), rm, rv, ptr(self.scale),
+                                           ptr(self.shift), ptr(self.mean), ptr(self.rstd), z.rows, z.c, 1, 1, bn.eps,
+                                           bn.momentum, int(use_batch), stream_ptr()), "norm_finalize")
         d = self._desc(False)
         check(lib.petsyn_normact_fwd(C.byref(d), stream_ptr()), "normact_fwd")
 
@@ -402,6 +415,10 @@ class NormActOp(Op):
         return w
 
     def bwd(self) -> None:
+        if self.kind == "batch" and not self.fwd_batch_stats:
+            # eval(): the layer is affine in its input (running statistics); the kernels implement the batch-statistics
+            # backward only, which would silently add a mean / variance correction that does not exist here
+            raise NotImplementedError("backward through BatchNorm3d in eval() mode is not implemented; call .train()")
         if self.grad_slope is not None and not self.acc_dw:
             self.grad_slope.zero_()
         if self.colsum_conv is not None and not self.acc_dz:

@@ -128,12 +128,23 @@ class UnetGenerator3d(nn.Module):
 class _UnetFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, eng, *params):
-        ctx.eng = eng
-        return eng.forward(x, save=True)
+        y = eng.forward(x, save=True)
+        ctx.eng, ctx.gen, ctx.mode = eng, eng.generation, eng.gen.training
+        ctx.versions = tuple(p._version for p in params)
+        ctx.save_for_backward(x)
+        return y
 
     @staticmethod
     def backward(ctx, dy):
-        grads = ctx.eng.backward(dy.contiguous().float())
+        eng = ctx.eng
+        if eng.generation != ctx.gen:
+            # a later forward overwrote this node's activations (forward, forward, backward): redo this node's forward
+            # from its saved input, same mode, without moving the BatchNorm running statistics a second time
+            if tuple(p._version for p in eng.param_list()) != ctx.versions:
+                raise RuntimeError("a parameter of this petsyn module was modified in place between forward and backward")
+            eng.forward(ctx.saved_tensors[0], save=True, clone_output=False, training=ctx.mode, update_running=False)
+            ctx.gen = eng.generation
+        grads = eng.backward(dy.contiguous().float())
         return (None, None, *grads)
 
 
@@ -216,6 +227,8 @@ class _Engine:
         self._packed_versions: Dict[int, int] = {}
         self._grads: Optional[List[torch.Tensor]] = None
         self._saved_x: Optional[torch.Tensor] = None
+        self.generation = 0             # bumped by every forward: one set of saved activations per engine (see _UnetFn)
+        self.fwd_training = True
 
     # ------------------------------------------------------------------------------------------------ parameters
     def param_list(self) -> List[torch.Tensor]:
@@ -244,20 +257,26 @@ class _Engine:
                 self._packed_versions[id(obj)] = ver
 
     # ------------------------------------------------------------------------------------------------ forward
-    def _bn_forward(self, nm: _Norm, z: torch.Tensor, rows: int, c: int, training: bool) -> None:
+    def _bn_forward(self, nm: _Norm, z: torch.Tensor, rows: int, c: int, training: bool, update_running: bool) -> None:
         bn = nm.bn
-        if training:
+        if bn.momentum is None:
+            raise NotImplementedError("BatchNorm3d(momentum=None) (cumulative moving average) is not implemented")
+        use_batch = training or bn.running_mean is None
+        if use_batch:
             nm.sums.zero_()
             ops.bn_stats(z, nm.sums, rows, c)
-            if bn.track_running_stats and bn.num_batches_tracked is not None:
+            if update_running and bn.track_running_stats and bn.num_batches_tracked is not None:
                 bn.num_batches_tracked.add_(1)
-        momentum = 0.1 if bn.momentum is None else bn.momentum
-        ops.bn_finalize(nm.sums, bn.weight, bn.bias, bn.running_mean, bn.running_var, nm.scale, nm.shift, nm.mean,
-                        nm.rstd, rows, c, bn.eps, momentum, training)
+        keep = use_batch and not update_running
+        ops.bn_finalize(nm.sums, bn.weight, bn.bias, None if keep else bn.running_mean, None if keep else bn.running_var,
+                        nm.scale, nm.shift, nm.mean, nm.rstd, rows, c, bn.eps, bn.momentum, use_batch)
 
-    def forward(self, x: torch.Tensor, save: bool, timers=None, clone_output: bool = True) -> torch.Tensor:
+    def forward(self, x: torch.Tensor, save: bool, timers=None, clone_output: bool = True,
+                training: Optional[bool] = None, update_running: bool = True) -> torch.Tensor:
         L = self.L
-        training = self.gen.training
+        training = self.gen.training if training is None else training
+        self.generation += 1
+        self.fwd_training = training
         self._repack(need_dgrad=save)
         lv = self.lv
         self._saved_x = x if save else None
@@ -267,7 +286,7 @@ class _Engine:
             prev = self.dnorm[i - 1]
             c = self.outer[i]
             if prev is not None:
-                self._bn_forward(prev, self.z[i - 1], self.rows[i], c, training)
+                self._bn_forward(prev, self.z[i - 1], self.rows[i], c, training, update_running)
             ops.norm_act_fwd(self.z[i - 1], prev.scale if prev else None, prev.shift if prev else None,
                              self.a[i], c, 0, ops.ACT_LRELU, self.cat[i], 2 * c, c, ops.ACT_RELU, LRELU_SLOPE,
                              self.rows[i], c)
@@ -284,7 +303,7 @@ class _Engine:
                 self.up[i].fprop(src, self.zu[i])
             nm = self.unorm[i]
             c = self.outer[i]
-            self._bn_forward(nm, self.zu[i], self.rows[i], c, training)
+            self._bn_forward(nm, self.zu[i], self.rows[i], c, training, update_running)
             ops.norm_act_fwd(self.zu[i], nm.scale, nm.shift, self.cat[i], 2 * c, 0, ops.ACT_RELU, None, 0, 0,
                              ops.ACT_NONE, LRELU_SLOPE, self.rows[i], c)
         n, _, d, h, w = self.shape
@@ -358,6 +377,8 @@ class _Engine:
         backward pass into CUDA-graph segments with a bucket all-reduce launched between them."""
         L = self.L
         lv = self.lv
+        if not self.fwd_training and any(nm is not None and nm.bn.running_mean is not None for nm in self.dnorm + self.unorm):
+            raise NotImplementedError("backward through BatchNorm3d in eval() mode is not implemented; call .train()")
         gw = lambda conv: slot[id(conv.weight)]
         n = self.shape[0]
         d1, h1, w1 = self.dims[1]

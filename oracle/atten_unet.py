@@ -148,3 +148,86 @@ def train_step(x, context, target, sd, cfg=TRAINING_JSON):
     loss = (y - target).abs().mean()
     loss.backward()
     return loss.detach(), y.detach(), {k: p.grad if p.grad is not None else torch.zeros_like(p) for k, p in params.items()}
+
+
+def param_shapes(cfg=TRAINING_JSON) -> Dict[str, tuple]:
+    """State-dict keys and shapes of ``AttenUNet(**cfg)`` (resblock_updown / with_conditioning family) in the reference's
+    registration order, derived from the constructor walk (atten_unet_model.py:1676-1790) -- lets the oracle run without
+    any module object (``tests/test_oracle_cpu.py`` checks it against the live reference class)."""
+    ch: Sequence[int] = cfg["num_channels"]
+    n = len(ch)
+    nres = cfg["num_res_blocks"]
+    nres = [nres] * n if isinstance(nres, int) else list(nres)
+    att, cdim = cfg["attention_levels"], cfg["cross_attention_dim"]
+    out: Dict[str, tuple] = {}
+
+    def conv(pre, cin, cout, k):
+        out[pre + "conv.weight"], out[pre + "conv.bias"] = (cout, cin, k, k, k), (cout,)
+
+    def norm(pre, c):
+        out[pre + "weight"], out[pre + "bias"] = (c,), (c,)
+
+    def resnet(pre, cin, cout):
+        norm(pre + "norm1.", cin)
+        conv(pre + "conv1.", cin, cout, 3)
+        norm(pre + "norm2.", cout)
+        conv(pre + "conv2.", cout, cout, 3)
+        if cin != cout:
+            conv(pre + "skip_connection.", cin, cout, 1)
+
+    def transformer(pre, c):
+        norm(pre + "norm.", c)
+        conv(pre + "proj_in.", c, c, 1)
+        b = pre + "transformer_blocks.0."
+        for a, kv in (("attn1.", c), ("attn2.", cdim)):
+            out[b + a + "to_q.weight"], out[b + a + "to_k.weight"], out[b + a + "to_v.weight"] = (c, c), (c, kv), (c, kv)
+            out[b + a + "to_out.0.weight"], out[b + a + "to_out.0.bias"] = (c, c), (c,)
+            if a == "attn1.":
+                out[b + "ff.linear1.weight"], out[b + "ff.linear1.bias"] = (8 * c, c), (8 * c,)
+                out[b + "ff.linear2.weight"], out[b + "ff.linear2.bias"] = (c, 4 * c), (c,)
+        for nm in ("norm1.", "norm2.", "norm3."):
+            norm(b + nm, c)
+        conv(pre + "proj_out.", c, c, 1)
+
+    conv("conv_in.", 1, ch[0], 3)
+    oc = ch[0]
+    for i in range(n):
+        ic, oc = oc, ch[i]
+        pre = f"down_blocks.{i}."
+        if att[i]:                                        # CrossAttnDownBlock registers attentions before resnets
+            for j in range(nres[i]):
+                transformer(pre + f"attentions.{j}.", oc)
+        for j in range(nres[i]):
+            resnet(pre + f"resnets.{j}.", ic if j == 0 else oc, oc)
+        if i != n - 1:
+            resnet(pre + "downsampler.", oc, oc)
+    resnet("middle_block.resnet_1.", ch[-1], ch[-1])
+    transformer("middle_block.attention.", ch[-1])
+    resnet("middle_block.resnet_2.", ch[-1], ch[-1])
+    rch = list(reversed(ch))
+    oc = rch[0]
+    for i in range(n):
+        prev, oc = oc, rch[i]
+        ic = rch[min(i + 1, n - 1)]
+        lvl = n - 1 - i
+        pre = f"up_blocks.{i}."
+        nr = nres[lvl] + 1
+        if att[lvl]:
+            for j in range(nr):
+                transformer(pre + f"attentions.{j}.", oc)
+        for j in range(nr):
+            skip_c = ic if j == nr - 1 else oc
+            in_c = prev if j == 0 else oc
+            resnet(pre + f"resnets.{j}.", in_c + skip_c, oc)
+        if i != n - 1:
+            resnet(pre + "upsampler.", oc, oc)
+    norm("out.0.", ch[0])
+    conv("out.2.", ch[0], 1, 3)
+    return out
+
+
+def init_state_dict(cfg=TRAINING_JSON, seed: int = 0) -> Dict[str, torch.Tensor]:
+    """A full set of seeded, non-zero parameters (``randomize_`` by name) for ``forward`` / ``train_step``."""
+    sd = {k: torch.zeros(s) for k, s in param_shapes(cfg).items()}
+    randomize_(sd.items(), seed=seed)
+    return sd

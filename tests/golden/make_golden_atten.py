@@ -37,7 +37,13 @@ def main():
     cfg["cross_attention_dim"] = 5
     assert cfg == OA.TRAINING_JSON, (cfg, OA.TRAINING_JSON)
     torch.set_num_threads(os.cpu_count() or 1)
-    for name, shape, seed in (("atten_unet_2x32x48x32", (2, 32, 48, 32), 777),):
+    cases = (("atten_unet_2x32x48x32", (2, 32, 48, 32), 777, 1),
+             # BASELINE configs[1] at full size (the bench default): output stored on a stride-3 lattice, small gradients whole
+             ("atten_unet_2x96x128x96", (2, 96, 128, 96), 777, 3))
+    only = sys.argv[1:]
+    for name, shape, seed, stride in cases:
+        if only and name not in only:
+            continue
         model = AttenUNet(**cfg).train()
         OA.randomize_(model.named_parameters(), seed=seed)
         x, ctx, tgt = synth(shape, seed)
@@ -45,12 +51,15 @@ def main():
         loss = torch.nn.L1Loss()(y, tgt)
         loss.backward()
         out = {"shape": np.array(shape), "seed": np.int64(seed), "loss": np.float64(loss.item()),
-               "output": y.detach().numpy()}
+               "stride": np.int64(stride), "output": y.detach().numpy()[:, :, ::stride, ::stride, ::stride].copy(),
+               "output_absmax": np.float64(y.detach().abs().max().item())}
         tot = 0.0
         for k, p in model.named_parameters():
             gnorm = 0.0 if p.grad is None else p.grad.double().norm().item()
             out["gradnorm/" + k] = np.float64(gnorm)
             out["wsum/" + k] = np.float64(p.detach().double().abs().sum().item())
+            if stride > 1 and p.grad is not None and p.numel() <= 8192:
+                out["grad/" + k] = p.grad.numpy().copy()
             tot += gnorm ** 2
         out["grad_norm_total"] = np.float64(tot ** 0.5)
         path = os.path.join(HERE, name + ".npz")

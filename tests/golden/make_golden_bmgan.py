@@ -21,7 +21,9 @@ REF = os.environ.get("PETSYN_REFERENCE", "/root/reference")
 
 SMALL = dict(input_conv_channel=64, output_conv_channel=64, down_channels=[64, 128, 128, 128], middle_channels=[128],
              up_channels=[128, 128, 128, 128, 64])
-CASES = {"bmgan_small_2x64x96x64": (SMALL, (2, 64, 96, 64), 777)}
+# "full": the reference's default constructor (247.6 M parameters) on the reference crop = BASELINE configs[2]'s generator
+CASES = {"bmgan_small_2x64x96x64": (SMALL, (2, 64, 96, 64), 777, 2),
+         "bmgan_full_1x96x128x96": ({}, (1, 96, 128, 96), 777, 3)}
 
 
 def synth(shape, seed):
@@ -38,7 +40,10 @@ def main():
     sys.path.insert(0, os.path.join(REF, "bl_methods", "BMGAN"))
     ref = importlib.import_module("bmgan_model")
     torch.set_num_threads(os.cpu_count() or 1)
-    for name, (cfg, shape, seed) in CASES.items():
+    only = sys.argv[1:]
+    for name, (cfg, shape, seed, stride) in CASES.items():
+        if only and name not in only:
+            continue
         torch.manual_seed(seed)
         gen = ref.dense_unet_generator(**cfg).train()
         disc = ref.patch_discriminator().train()
@@ -50,7 +55,8 @@ def main():
         loss, adv, l1, fake = OB.generator_step(gen, disc, t1, pet, z)
         loss.backward()
         out.update(g_loss=np.float64(loss.item()), g_adv=np.float64(adv.item()), g_l1=np.float64(l1.item()),
-                   fake_sample=fake.detach().numpy()[:, :, ::2, ::2, ::2].copy())
+                   fake_sample=fake.detach().numpy()[:, :, ::stride, ::stride, ::stride].copy(),
+                   stride=np.int64(stride))
         for k, p in gen.named_parameters():
             out["gradnorm/" + k] = np.float64(p.grad.double().norm().item())
         dl = OB.discriminator_step(disc, fake.detach(), pet)

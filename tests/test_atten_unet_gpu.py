@@ -70,6 +70,71 @@ def test_train_step_matches_oracle_and_golden(petsyn):
     assert abs(tot ** 0.5 - tot_o ** 0.5) <= max(2.0 * abs(tot_p ** 0.5 - tot_o ** 0.5), 2e-2 * tot_o ** 0.5)
 
 
+def test_full_size_cfg2_matches_golden_and_peer(petsyn):
+    """BASELINE configs[1] at its real size -- AttenUNet(**training.json), batch 2, 96x128x96 (L = 2 304 tokens, every slab
+    kernel with its full-size tiling and multi-CTA-per-sample sweeps) -- against the fixture generated from the reference
+    class on the CPU (``make_golden_atten.py``: output on a stride-3 lattice, loss, per-parameter gradient norms, the small
+    gradients whole), peer-calibrated against the oracle graph under bf16 autocast / cuDNN on the same GPU."""
+    gold = np.load(os.path.join(GOLD, "atten_unet_2x96x128x96.npz"))
+    shape, seed, st = tuple(int(v) for v in gold["shape"]), int(gold["seed"]), int(gold["stride"])
+    assert shape == (2, 96, 128, 96)
+    model = petsyn.AttenUNet(**OA.TRAINING_JSON).train()
+    OA.randomize_(model.named_parameters(), seed=seed)
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    for k, v in sd.items():
+        ref = float(gold["wsum/" + k])
+        assert abs(float(v.double().abs().sum()) - ref) <= 1e-6 * max(1.0, ref), k
+    x, ctx, tgt = synth(shape, seed)
+    y_gold = torch.from_numpy(gold["output"])
+    # peer: the oracle graph under bf16 autocast on the GPU
+    pp = {k: v.detach().clone().cuda().requires_grad_(True) for k, v in sd.items()}
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        y_p = OA.forward(x.cuda(), ctx.cuda(), pp)
+    loss_p = (y_p.float() - tgt.cuda()).abs().mean()
+    loss_p.backward()
+    peer_err = (y_p.detach().float().cpu()[:, :, ::st, ::st, ::st] - y_gold).abs()
+    peer_norm = {k: (0.0 if v.grad is None else v.grad.double().norm().item()) for k, v in pp.items()}
+    peer_grad = {k: v.grad.detach().float().cpu() for k, v in pp.items() if v.grad is not None and "grad/" + k in gold}
+    del pp, y_p
+    torch.cuda.empty_cache()
+
+    model = model.cuda()
+    y = model(x.cuda(), ctx.cuda())
+    loss = torch.nn.functional.l1_loss(y, tgt.cuda())
+    loss.backward()
+    torch.cuda.synchronize()
+    err = (y.detach().cpu()[:, :, ::st, ::st, ::st] - y_gold).abs()
+    print("cfg2 full size: out err ours max/mean", err.max().item(), err.mean().item(), "peer", peer_err.max().item(),
+          peer_err.mean().item(), "| |y|max", float(gold["output_absmax"]), "| loss ours/gold/peer", loss.item(),
+          float(gold["loss"]), loss_p.item())
+    assert err.max().item() <= 2.0 * peer_err.max().item() + 5e-3
+    assert err.mean().item() <= 2.0 * peer_err.mean().item() + 5e-4
+    assert abs(loss.item() - float(gold["loss"])) <= max(2.0 * abs(loss_p.item() - float(gold["loss"])), 2e-3)
+    gtot = float(gold["grad_norm_total"])
+    tot = tot_p = 0.0
+    worst = worst_p = 0.0
+    for k, p in model.named_parameters():
+        gn, ref = p.grad.double().norm().item(), float(gold["gradnorm/" + k])
+        tot += gn * gn
+        tot_p += peer_norm[k] ** 2
+        if ".attn2.to_q." in k or ".attn2.to_k." in k or ".transformer_blocks.0.norm2." in k:
+            assert gn == 0.0 and ref < 1e-12, k                                          # SURVEY 9 Q3
+            continue
+        if ref > 1e-2 * gtot:
+            rel, rel_p = abs(gn - ref) / ref, abs(peer_norm[k] - ref) / ref
+            worst, worst_p = max(worst, rel), max(worst_p, rel_p)
+            assert rel <= max(2.0 * rel_p, 0.05), (k, gn, ref, peer_norm[k])
+        if "grad/" + k in gold and ref > 1e-3 * gtot:
+            a, b, c = p.grad.double().cpu().flatten(), torch.from_numpy(gold["grad/" + k]).double().flatten(), \
+                peer_grad[k].double().flatten()
+            cos = (torch.dot(a, b) / (a.norm() * b.norm())).item()
+            cos_p = (torch.dot(c, b) / (c.norm() * b.norm())).item()
+            assert 1 - cos <= max(2.0 * (1 - cos_p), 2e-2), (k, cos, cos_p)
+    print("cfg2 full size: grad-norm ours/gold/peer", tot ** 0.5, gtot, tot_p ** 0.5, "| worst per-tensor rel", worst,
+          "peer", worst_p)
+    assert abs(tot ** 0.5 - gtot) <= max(2.0 * abs(tot_p ** 0.5 - gtot), 2e-2 * gtot)
+
+
 def test_contracts(petsyn):
     cfg = dict(OA.TRAINING_JSON)
     with pytest.raises(ValueError):

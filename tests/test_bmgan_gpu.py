@@ -113,6 +113,77 @@ def test_generator_step_matches_oracle_and_golden(petsyn):
         assert 1.0 - cos <= max(3.0 * (1.0 - cos_peer), 2e-2), (k, cos, cos_peer)      # same run-to-run spread as above
 
 
+def test_full_generator_cfg3_matches_golden_and_peer(petsyn):
+    """BASELINE configs[2]'s generator at its real size: the reference's DEFAULT ``dense_unet_generator()`` (247.6 M
+    parameters) + ``patch_discriminator()`` on one 96x128x96 volume, G phase of train_bmgan.py:141-161, against the fixture
+    generated from the reference file on the CPU (``make_golden_bmgan.py bmgan_full_1x96x128x96``: synthesized volume on a
+    stride-3 lattice, losses, per-parameter gradient norms), peer-calibrated against the oracle graph under bf16 autocast."""
+    import copy
+    gold = np.load(os.path.join(GOLD, "bmgan_full_1x96x128x96.npz"))
+    shape, seed, st = tuple(int(v) for v in gold["shape"]), int(gold["seed"]), int(gold["stride"])
+    assert shape == (1, 96, 128, 96)
+    torch.manual_seed(seed)
+    gen = petsyn.dense_unet_generator().train()
+    disc = petsyn.patch_discriminator().train()
+    assert sum(p.numel() for p in gen.parameters()) == 247592897
+    for k, v in list(gen.state_dict().items()) + [("D." + k, v) for k, v in disc.state_dict().items()]:
+        if v.dtype.is_floating_point:
+            ref = float(gold["wsum/" + k])
+            assert abs(float(v.double().abs().sum()) - ref) <= 1e-6 * max(1.0, ref), k
+    t1, pet, z = synth(shape, seed)
+    f_gold = torch.from_numpy(gold["fake_sample"])
+    # ---- peer: the oracle graph with the same weights under bf16 autocast on the GPU ----
+    pg, pd = OB.DenseUnetGenerator().train(), OB.PatchDiscriminatorWrapper().train()
+    pg.load_state_dict(gen.state_dict())
+    pd.load_state_dict(disc.state_dict())
+    pg, pd = pg.cuda(), pd.cuda()
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        lp, ap, l1p, fp = OB.generator_step(pg, pd, t1.cuda(), pet.cuda(), z.cuda())
+    lp.float().backward()
+    peer_err = (fp.detach().float().cpu()[:, :, ::st, ::st, ::st] - f_gold).abs()
+    peer_norm = {k: p.grad.double().norm().item() for k, p in pg.named_parameters()}
+    lp, ap = lp.item(), ap.item()
+    del pg, pd, fp
+    torch.cuda.empty_cache()
+
+    gen, disc = gen.cuda(), disc.cuda()
+    for p in disc.parameters():
+        p.requires_grad_(False)
+    fake = gen(t1.cuda(), z.cuda())
+    logits = disc(fake.contiguous().float())[-1]
+    adv = ((logits - 1.0) ** 2).mean()
+    l1 = (fake - pet.cuda()).abs().mean()
+    loss = adv + 20.0 * l1
+    loss.backward()
+    torch.cuda.synchronize()
+    err = (fake.detach().cpu()[:, :, ::st, ::st, ::st] - f_gold).abs()
+    gl, ga = float(gold["g_loss"]), float(gold["g_adv"])
+    print("cfg3 full G: fake err ours max/mean", err.max().item(), err.mean().item(), "peer", peer_err.max().item(),
+          peer_err.mean().item(), "| loss ours/gold/peer", loss.item(), gl, lp, "| adv", adv.item(), ga, ap)
+    assert err.max().item() <= 2.0 * peer_err.max().item() + 1e-2
+    assert err.mean().item() <= 2.0 * peer_err.mean().item() + 1e-3
+    assert abs(loss.item() - gl) <= max(2.0 * abs(lp - gl), 5e-3 * gl)
+    assert abs(adv.item() - ga) <= max(2.0 * abs(ap - ga), 1e-2 * ga)
+    ref_norms = {k: float(gold["gradnorm/" + k]) for k, _ in gen.named_parameters()}
+    energy = sum(v * v for v in ref_norms.values())
+    tot = tot_peer = 0.0
+    worst = worst_peer = 0.0
+    for k, p in gen.named_parameters():
+        gn, ref = p.grad.double().norm().item(), ref_norms[k]
+        tot += gn * gn
+        tot_peer += peer_norm[k] ** 2
+        if ref * ref > 1e-3 * energy:
+            rel, rel_peer = abs(gn - ref) / ref, abs(peer_norm[k] - ref) / ref
+            worst, worst_peer = max(worst, rel), max(worst_peer, rel_peer)
+            assert rel <= max(2.0 * rel_peer, 0.05), (k, gn, ref, peer_norm[k])
+        elif k.endswith("bias") and ref < 1e-6:
+            assert gn < 1e-4, (k, gn)
+    tot, tot_ref, tot_peer = tot ** 0.5, energy ** 0.5, tot_peer ** 0.5
+    print("cfg3 full G: global grad-norm ours/gold/peer", tot, tot_ref, tot_peer, "| worst per-tensor rel", worst, "peer",
+          worst_peer)
+    assert abs(tot - tot_ref) <= max(2.0 * abs(tot_peer - tot_ref), 2e-2 * tot_ref)
+
+
 def test_discriminator_phase_matches_oracle_and_golden(petsyn):
     gold = np.load(os.path.join(GOLD, "bmgan_small_2x64x96x64.npz"))
     shape, seed = tuple(int(v) for v in gold["shape"]), int(gold["seed"])
