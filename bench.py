@@ -41,6 +41,10 @@ WORKLOADS = {
     # (train_unet.py:319), 96x128x96 (train_unet.py:111), 5 covariates
     "atten_unet_train_cfg2": ("atten", (96, 128, 96), 2),
     "atten_unet_train_small": ("atten", (32, 48, 32), 2),
+    # the same step with the reference's adversarial part (train_unet.py:153-193, training.json: adv_weight 0.1,
+    # PatchDiscriminator 64 ch x 3 layers, disc_lr 1e-4): G phase with the LSGAN term + the two-backward D phase
+    "atten_unet_adv_train_cfg2": ("atten_adv", (96, 128, 96), 2),
+    "atten_unet_adv_train_small": ("atten_adv", (32, 48, 32), 2),
     # BASELINE configs[2]: BMGAN generator + discriminator adversarial step, per-GPU batch 1 (train_bmgan.py:315);
     # first field = generator config name
     "bmgan_adv_step_s2": ("full", (96, 128, 96), 1),
@@ -504,6 +508,7 @@ CLASSIFIER_CFG = dict(spatial_dims=3, in_channels=1, out_channels=2, num_channel
                       attention_levels=[False, False, False, True, True], norm_num_groups=16, norm_eps=1e-6,
                       resblock_updown=True, num_head_channels=[0, 0, 0, 32, 32], with_conditioning=True,
                       transformer_num_layers=1, upcast_attention=False, cross_attention_dim=5)
+DISC_CFG = dict(spatial_dims=3, num_channels=64, num_layers_d=3, in_channels=1, out_channels=1)   # training.json:40-46
 ATTEN_CFG = dict(spatial_dims=3, in_channels=1, out_channels=1, num_channels=[16, 32, 64, 128], num_res_blocks=2,
                  attention_levels=[False, False, False, True], norm_num_groups=16, norm_eps=1e-6, resblock_updown=True,
                  num_head_channels=[0, 0, 0, 32], with_conditioning=True, transformer_num_layers=1,
@@ -537,45 +542,228 @@ def atten_batch(shape, seed, batch):
             torch.rand(batch, 1, d, h, w, generator=g))
 
 
-def cpu_atten_steps(shape, batch, steps, warmup, budget_s=150.0):
-    """Oracle port of the AttenUNet train step (fwd + L1 + bwd + SGD-sized update) on the host cores."""
+REF_DIR = os.path.join(ROOT, "baseline", "_ref")
+
+
+def reference_atten_class():
+    """The UNMODIFIED reference ``AttenUNet`` (unet/utils/atten_unet_model.py:1575) imported from ``baseline/_ref`` (where
+    ``__graft_entry__.build()`` installs the reference's model files) over the MONAI stub; None when the install is absent."""
+    if not os.path.exists(os.path.join(REF_DIR, "unet", "utils", "atten_unet_model.py")):
+        return None
+    from oracle import monai_stub
+    monai_stub.install_atten()
+    if REF_DIR not in sys.path:
+        sys.path.insert(0, REF_DIR)
+    from unet.utils.atten_unet_model import AttenUNet
+    return AttenUNet
+
+
+def cpu_atten_steps(shape, batch, steps, warmup, adv=False):
+    """The reference's covariate-conditioned training step (train_unet.py:139-168 with the terms that exist offline: fwd + L1
+    + bwd + Adam, fp32) on the host cores, FULL volume, no crop.  Runs the unmodified reference class when ``baseline/_ref``
+    holds it (kind "reference"), else the oracle port (kind "port").  Nothing of the product is imported here."""
     import torch
-    from oracle import atten_unet as OA
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    # parameter shapes come from the oracle's own key walk: build them from a throw-away CUDA-free module mirror
-    import petsyn
-    sd = {k: v.detach().clone() for k, v in petsyn.AttenUNet(**ATTEN_CFG).state_dict().items()}
-    redraw_parameters_(sd.items(), seed=777)
-
-    def one(shape_):
-        x, ctx, tgt = atten_batch(shape_, 777, batch)
-        t0 = time.perf_counter()
-        loss, _, grads = OA.train_step(x, ctx, tgt, sd)
-        with torch.no_grad():
-            for k in sd:
-                sd[k] = sd[k] - 1e-4 * grads[k]
-        return time.perf_counter() - t0
-
+    cls = reference_atten_class()
     d, h, w = shape
-    small = (32, 48, 32)
-    t_small = one(small)
-    frac_small = (small[0] * small[1] * small[2]) / (d * h * w)
-    use, frac = shape, 1.0
-    if t_small / frac_small * (steps + warmup) > budget_s:
-        use, frac = small, frac_small
-    for _ in range(warmup):
-        one(use)
-    ts = [one(use) for _ in range(steps)]
+    if cls is not None:
+        kind = "reference"
+        model = cls(**ATTEN_CFG).train()
+        redraw_parameters_(model.named_parameters(), seed=777)
+        opt = torch.optim.Adam(model.parameters(), lr=5e-4)                     # training.json:53, train_unet.py:97
+        if adv:
+            from oracle import monai_stub
+            torch.manual_seed(778)
+            disc = monai_stub.PatchDiscriminator(**DISC_CFG).train()             # the un-vendored class, restated (train_unet.py:74)
+            d_opt = torch.optim.Adam(disc.parameters(), lr=1e-4)
+            mse = lambda t, v: ((t - v) ** 2).mean()
+
+        def one(i):
+            x, ctx, tgt = atten_batch(shape, 777 + i % 3, batch)
+            ctx = ctx[:, None, :]
+            t0 = time.perf_counter()
+            if adv:                                                              # train_unet.py:136-193
+                for p in disc.parameters():
+                    p.requires_grad_(False)
+                y = model(x, ctx)
+                g_loss = torch.nn.functional.l1_loss(y, tgt) + 0.1 * mse(disc(y.contiguous().float())[-1], 1.0)
+                opt.zero_grad()
+                g_loss.backward()
+                opt.step()
+                for p in disc.parameters():
+                    p.requires_grad_(True)
+                d_opt.zero_grad()
+                with torch.no_grad():
+                    y = model(x, ctx)
+                mse(disc(y.contiguous().detach())[-1], 0.0).backward()
+                mse(disc(tgt.contiguous().detach())[-1], 1.0).backward()
+                d_opt.step()
+            else:
+                opt.zero_grad()
+                loss = torch.nn.functional.l1_loss(model(x, ctx), tgt)
+                loss.backward()
+                opt.step()
+            return time.perf_counter() - t0
+    else:
+        if adv:
+            raise RuntimeError("the adversarial CPU arm needs the reference class in baseline/_ref (run build())")
+        kind = "port"
+        from oracle import atten_unet as OA
+        sd = OA.init_state_dict(ATTEN_CFG, seed=777)
+
+        def one(i):
+            x, ctx, tgt = atten_batch(shape, 777 + i % 3, batch)
+            t0 = time.perf_counter()
+            _, _, grads = OA.train_step(x, ctx, tgt, sd, ATTEN_CFG)
+            with torch.no_grad():
+                for k in sd:
+                    sd[k] = sd[k] - 1e-4 * grads[k]
+            return time.perf_counter() - t0
+
+    for i in range(warmup):
+        one(i)
+    ts = [one(i) for i in range(steps)]
     total = sum(ts)
-    sample = (f"{steps} timed + {warmup} warm-up AttenUNet train steps of the oracle port (PyTorch fp32 CPU, {cores} "
-              f"threads) on {'the full' if frac == 1.0 else f'a {use[0]}x{use[1]}x{use[2]} crop ({frac:.4f} of the)'} "
-              f"{d}x{h}x{w} volume, batch {batch}; volumes/s scaled by voxel fraction (attention cost is "
-              f"super-linear in the crop, so the crop flatters the CPU)")
-    return batch * frac * steps / total, sample, cores, total / steps * 1e3
+    what = ("the UNMODIFIED reference class unet/utils/atten_unet_model.py:AttenUNet (baseline/_ref, MONAI blocks stubbed) + "
+            "nn.L1Loss + torch.optim.Adam" + (" + the LSGAN term and discriminator phase of train_unet.py:153-193 "
+                                                "(PatchDiscriminator restated from upstream)" if adv else "")
+            if kind == "reference" else "the oracle port (oracle/atten_unet.py)")
+    sample = (f"{steps} timed + {warmup} warm-up training steps of {what}, PyTorch fp32 on {cores} host threads, the full "
+              f"{d}x{h}x{w} volume, batch {batch} (same config as the GPU arm)")
+    return batch * steps / total, sample, cores, total / steps * 1e3, kind
 
 
-def run_petsyn_atten(args, shape, batch):
+def incumbent_atten(shape, batch, dev, steps=6):
+    """The GPU incumbent SURVEY 2.1 / BASELINE.md 5 name: the reference network run by PyTorch + cuDNN on the SAME B200, same
+    config and synthetic inputs, CUDA-event timed -- (a) as the reference script runs it (fp32, NCDHW, cudnn.benchmark=True:
+    train_unet.py:43; TF32 convolutions are PyTorch's default), (b) tuned: bf16 autocast + channels_last_3d.  Training step =
+    zero_grad + fwd + L1 + bwd + Adam; inference = eval forward under no_grad.  Returns a dict (or {"unavailable": why})."""
+    import torch
+    cls = reference_atten_class()
+    torch.backends.cudnn.benchmark = True
+    out = {"what": "reference AttenUNet (baseline/_ref) on PyTorch " + torch.__version__ + " / cuDNN "
+           + str(torch.backends.cudnn.version()) + ", same GPU, same config, CUDA events"}
+    d, h, w = shape
+    batches = [tuple(t.to(dev) for t in atten_batch(shape, 900 + i, batch)) for i in range(3)]
+
+    def run(mode):
+        if cls is None:
+            return None
+        model = cls(**ATTEN_CFG)
+        redraw_parameters_(model.named_parameters(), seed=777)
+        model = model.to(dev).train()
+        cl = mode == "bf16_channels_last"
+        if cl:
+            model = model.to(memory_format=torch.channels_last_3d)
+        opt = torch.optim.Adam(model.parameters(), lr=5e-4, fused=cl)
+
+        def fwd(x, ctx):
+            if cl:
+                x = x.contiguous(memory_format=torch.channels_last_3d)
+                with torch.autocast("cuda", dtype=torch.bfloat16):
+                    return model(x, ctx[:, None, :]).float()
+            return model(x, ctx[:, None, :])
+
+        def train(i):
+            x, ctx, tgt = batches[i % 3]
+            opt.zero_grad(set_to_none=True)
+            loss = torch.nn.functional.l1_loss(fwd(x, ctx), tgt)
+            loss.backward()
+            opt.step()
+
+        def infer(i):
+            x, ctx, _ = batches[i % 3]
+            with torch.no_grad():
+                fwd(x, ctx)
+
+        res = {}
+        for name, fn in (("train", train), ("infer", infer)):
+            if name == "infer":
+                model.eval()
+            for i in range(3):                        # cudnn.benchmark autotunes in the first calls
+                fn(i)
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for i in range(steps):
+                fn(i)
+            b.record()
+            torch.cuda.synchronize()
+            ms = a.elapsed_time(b) / steps
+            res[name + "_ms_per_step"] = ms
+            res[name + "_volumes_per_s"] = batch / (ms * 1e-3)
+        del model, opt
+        torch.cuda.empty_cache()
+        return res
+
+    try:
+        for mode in ("fp32_as_written", "bf16_channels_last"):
+            r = run(mode)
+            if r is None:
+                return {"unavailable": "baseline/_ref does not hold the reference model files (run __graft_entry__.build() "
+                                       "where /root/reference exists)"}
+            out[mode] = r
+    except Exception as e:  # pragma: no cover - keep the bench line alive
+        out["error"] = f"{type(e).__name__}: {e}"
+    return out
+
+
+def step_roofline(tape, n_params, out_voxels, peak_tf, peak_bw):
+    """Step-level roofline: sum over the ops of the training step of max(FLOPs / tensor peak, minimum bytes /
+    HBM bandwidth).  FLOPs are algorithmic (direct convolution); minimum bytes are a bf16 read-once of every input and a
+    write-once of every output of the op (weights and per-channel vectors are negligible), i.e. the traffic of the op
+    graph as it is fused here -- the further fusion the judge's floor assumes (no materialised activated tensor) would lower
+    the HBM part.  Returns milliseconds."""
+    from petsyn_b200 import graph as G
+    tf, bw = peak_tf * 1e12, peak_bw * 1e9
+    t_tensor = t_hbm = t_roof = 0.0
+
+    def add(flops, nbytes):
+        nonlocal t_tensor, t_hbm, t_roof
+        a, b = flops / tf, nbytes / bw
+        t_tensor += a
+        t_hbm += b
+        t_roof += max(a, b)
+
+    for op in tape.ops:
+        if isinstance(op, G.ConvOp):
+            xin = op.x.buf.rows * op.cin_w * 2
+            od, oh, ow = op.plan.out_dims
+            yout = op.x.buf.n * od * oh * ow * op.cout_w * (4 if op.y_fp32 else 2)
+            add(op.flops, xin + yout)                               # fprop
+            if op.need_dx:
+                add(op.flops, xin + yout)                           # dgrad
+            if op.need_dw:
+                add(op.flops, xin + yout)                           # wgrad reads x and dy
+        elif isinstance(op, G.NormActOp):
+            e = op.z.rows * op.c * 2
+            nd = len(op.dsts)
+            r = 1 if op.res is not None else 0
+            add(0.0, e * (1 + nd + r))                              # fwd: z (+ res) in, destinations out
+            if not op.no_bwd:
+                add(0.0, e * (nd + 1 + 1 + r) if op.kind != "none" else e * (nd + 1 + r))   # bwd: dy's (+ z) in, dz (+ dres) out
+        elif isinstance(op, G.ResampleOp):
+            e = (op.src.buf.rows * op.src.c + op.dst.buf.rows * op.dst.c) * 2
+            add(0.0, e); add(0.0, e)
+        elif isinstance(op, G.LayerNormOp):
+            e = op.x.rows * op.x.c * 2
+            add(0.0, 2 * e); add(0.0, 3 * e)
+        elif isinstance(op, G.GegluOp):
+            e = op.o.rows * op.o.c * 2
+            add(0.0, 3 * e); add(0.0, 5 * e)
+        elif isinstance(op, G.AttentionOp):
+            e = (op.qkv.rows * op.qkv.c + op.o.rows * op.o.c) * 2
+            add(op.flops, e); add(2.5 * op.flops, 2 * e)
+        elif isinstance(op, G.CovariateBiasOp):
+            e = op.t.rows * op.t.c * 2
+            add(0.0, 2 * e); add(0.0, e)
+    add(0.0, out_voxels * 4 * 3)                                    # L1: read y and target, write dy (fp32)
+    add(0.0, n_params * 28)                                         # Adam: p, g, m, v in; p, m, v out
+    return {"t_roof_ms": t_roof * 1e3, "tensor_part_ms": t_tensor * 1e3, "hbm_part_ms": t_hbm * 1e3}
+
+
+def run_petsyn_atten(args, shape, batch, adv=False):
     import torch
     import torch.distributed as dist
 
@@ -598,7 +786,12 @@ def run_petsyn_atten(args, shape, batch):
     host = [atten_batch(shape, 777 + 1000 * rank + i, batch) for i in range(pool)]
     pinned = [tuple(t.pin_memory() for t in b) for b in host]
     resident = [tuple(t.to(dev) for t in b) for b in host]
-    trainer = AttenUNetTrainer(model, lr=5e-4, example_input=resident[0][0])
+    disc = None
+    if adv:
+        torch.manual_seed(778)
+        disc = petsyn.PatchDiscriminator(**DISC_CFG).to(dev).train()
+    trainer = AttenUNetTrainer(model, lr=5e-4, example_input=resident[0][0], discriminator=disc, adv_weight=0.1 if adv else 0.0,
+                               disc_lr=1e-4)
 
     def barrier():
         if world > 1:
@@ -723,7 +916,10 @@ def run_petsyn_atten(args, shape, batch):
         d, h, w = shape
         fwd = trainer.eng.flops_algorithmic
         ms = ms_total / args.steps
-        ach = 3.0 * fwd / (ms * 1e-3) / 1e12
+        step_flops = 3.0 * fwd
+        if adv:      # + the D phase's generator forward; D: 3 forwards, one data-gradient-only backward, two full backwards
+            step_flops += fwd + (3.0 + 1.0 + 4.0) * trainer.deng.flops_algorithmic
+        ach = step_flops / (ms * 1e-3) / 1e12
         vox = batch * d * h * w
         dom_bytes = vox * 16 * 2 * 2                      # bf16 read-once of x + write-once of y, 16 channels each
         dom_flops = 2.0 * vox * 16 * 16 * 27
@@ -744,12 +940,14 @@ def run_petsyn_atten(args, shape, batch):
                             "launch_ms": wg_ms, "achieved": dom_bytes / (wg_ms * 1e-3) / 1e9, "unit": "GB/s",
                             "frac": dom_bytes / (wg_ms * 1e-3) / 1e9 / peak_bw}
         line = {
-            "metric": ATTEN_METRIC, "value": world * batch * args.steps / (ms_total * 1e-3), "unit": UNIT,
+            "metric": ATTEN_METRIC + (" + LSGAN adversarial term + discriminator phase (train_unet.py:153-193)" if adv else ""),
+            "value": world * batch * args.steps / (ms_total * 1e-3), "unit": UNIT,
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": args.workload, "network": "AttenUNet(**training.json atten_unet_def, cross_attention_dim=5)",
                        "volume": list(shape), "per_gpu_batch": batch, "global_batch": batch * world,
-                       "parallelism": f"dp{world}", "optimizer": "Adam(lr=5e-4)", "loss": "L1",
+                       "parallelism": f"dp{world}", "optimizer": "Adam(lr=5e-4)" + (" on G, Adam(lr=1e-4) on D" if adv else ""),
+                       "loss": "L1 + 0.1 * LSGAN; D: LSGAN(fake) + LSGAN(real)" if adv else "L1",
                        "cuda_graph": trainer.graph is not None, "weights": "re-drawn by name (zero_module tensors non-zero)",
                        "l2": "per-step working set (> 4 GB of activations) exceeds the 126 MB L2; inputs rotate over 3 batches"},
             "e2e": {"value": world * batch * args.steps / (ms_e2e * 1e-3), "unit": UNIT,
@@ -767,26 +965,40 @@ def run_petsyn_atten(args, shape, batch):
                                "model_frac_of_tensor_peak": ach / peak_tf},
             "final_loss": final,
         }
+        sr = step_roofline(tape, trainer.arena.numel, vox, peak_tf, peak_bw)
+        sr.update(measured_ms=ms, frac=sr["t_roof_ms"] / ms,
+                  what="sum over the ops of the step of max(algorithmic FLOPs / tensor peak, minimum bf16 bytes / HBM peak) "
+                       "against the measured step; peaks from MEASURED_PEAKS.json (sustained tensor, copy bandwidth)")
+        line["step_roofline"] = sr
+        if not args.no_incumbent and world == 1 and not adv:
+            inc = incumbent_atten(shape, batch, dev)
+            line["incumbent"] = inc
+            best = min((inc[k]["train_ms_per_step"] for k in ("fp32_as_written", "bf16_channels_last") if k in inc),
+                       default=None)
+            if best:
+                line["incumbent"]["speedup_vs_best_incumbent_train"] = best / ms
         if not args.no_cpu_baseline and world == 1:
-            v, sample, cores, _ = cpu_atten_steps(shape, batch, 3, 1, budget_s=30.0)
-            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+            v, sample, cores, _, kind = cpu_atten_steps(shape, batch, 2, 1, adv=adv)
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
 
 
-def run_reference_atten(args, shape, batch):
+def run_reference_atten(args, shape, batch, adv=False):
     if int(os.environ.get("RANK", "0")) != 0:
         return
-    vol_s, sample, cores, ms = cpu_atten_steps(shape, batch, args.steps, args.warmup)
+    vol_s, sample, cores, ms, kind = cpu_atten_steps(shape, batch, args.steps, args.warmup, adv=adv)
     print(json.dumps({
-        "impl": "reference", "metric": ATTEN_METRIC, "value": vol_s, "unit": UNIT, "n_gpus": args.gpus,
+        "impl": "reference", "metric": ATTEN_METRIC + (" + LSGAN adversarial term + discriminator phase (train_unet.py:153-193)"
+                                                      if adv else ""), "value": vol_s, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": args.workload, "network": "AttenUNet(**training.json atten_unet_def, cross_attention_dim=5)",
-                   "volume": list(shape), "per_gpu_batch": batch},
-        "cpu_baseline": {"value": vol_s, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+                   "volume": list(shape), "per_gpu_batch": batch, "global_batch": batch, "optimizer": "Adam(lr=5e-4)",
+                   "loss": "L1"},
+        "cpu_baseline": {"value": vol_s, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": vol_s, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}),
         flush=True)
 
@@ -978,6 +1190,7 @@ def main():
     ap.add_argument("--impl", default="petsyn", choices=["petsyn", "reference"])
     ap.add_argument("--workload", default="atten_unet_train_cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-incumbent", action="store_true", help="skip the PyTorch/cuDNN same-GPU incumbent leg")
     ap.add_argument("--no-graph", action="store_true", help="launch kernels eagerly instead of replaying a CUDA graph")
     ap.add_argument("--batch", type=int, default=1, help="inference workloads: volumes per step and GPU (1..16)")
     ap.add_argument("--profile-one-step", action="store_true",
@@ -991,7 +1204,7 @@ def main():
             return
         run_petsyn_infer(args, ngf, shape, batch)
     elif args.workload.startswith("atten"):
-        (run_reference_atten if args.impl == "reference" else run_petsyn_atten)(args, shape, batch)
+        (run_reference_atten if args.impl == "reference" else run_petsyn_atten)(args, shape, batch, adv=(ngf == "atten_adv"))
     elif args.workload.startswith("bmgan"):
         (run_reference_bmgan if args.impl == "reference" else run_petsyn_bmgan)(args, ngf, shape, batch)
     elif args.impl == "reference":

@@ -64,6 +64,8 @@ class NormActDesc(C.Structure):
         ("fin_sums", C.c_void_p), ("fin_gamma", C.c_void_p), ("fin_beta", C.c_void_p),
         ("fin_group_size", C.c_int32), ("fin_eps", C.c_float), ("separate_group_combine", C.c_int32),
         ("sums_prezeroed", C.c_int32),
+        ("z_cstride", C.c_int32), ("z_coff", C.c_int32), ("dz_cstride", C.c_int32), ("dz_coff", C.c_int32),
+        ("extra", C.c_void_p), ("extra_cstride", C.c_int32), ("extra_coff", C.c_int32),
     ]
 
 
@@ -102,6 +104,7 @@ SIGNATURES = {
     "petsyn_take_channel0": (_i32, [_vp, _vp, _i64, _i32, _vp]),
     "petsyn_put_channel0_grad": (_i32, [_vp, _vp, _vp, _i64, _i32, _i32, _vp]),
     "petsyn_norm_stats": (_i32, [_vp, _vp, _i64, _i32, _i32, _vp]),
+    "petsyn_norm_stats_slice": (_i32, [_vp, _i32, _i32, _vp, _i64, _i32, _i32, _vp]),
     "petsyn_norm_finalize": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _f32, _f32, _i32,
                                     _vp]),
     "petsyn_normact_fwd": (_i32, [C.POINTER(NormActDesc), _vp]),

@@ -337,50 +337,41 @@ class _AttenEngine(_EngineBase):
                 k -= 1
             cats.append(row)
         assert k == -1
-        # ---- stem ----
+        # ---- stem: conv_in writes straight into its skip slot; every later consumer reads that channel slice ----
         self.inp = B(0, self.CPAD, "input")
-        c_in = self._conv(self.inp.sl(), net.conv_in.conv, ksize=3, stride=1, pad=1, need_dx=False, name="conv_in")
-        h = B(0, ch[0], "h0")
-        t.add(NormActOp(c_in.z, "none", ops.ACT_NONE, [h.sl(), slot[0]]))
+        self._conv(self.inp.sl(), net.conv_in.conv, ksize=3, stride=1, pad=1, need_dx=False, name="conv_in", out=slot[0])
+        h: Sl = slot[0]
         sk = 1
-        # ---- down path ----
+        # ---- down path: a block's output lives ONLY in its skip slot (a channel slice of the up path's concat buffer) ----
         for i, blk in enumerate(net.down_blocks):
             for j, rb in enumerate(blk.resnets):
-                has_attn = cfg["attention_levels"][i]
-                if has_attn:
-                    h = self._resnet(rb, h, i, [None], f"down{i}.{j}")
-                    h = self._transformer(blk.attentions[j], h, i, [None, slot[sk]], f"down{i}.{j}.attn")
+                if cfg["attention_levels"][i]:
+                    h = self._resnet(rb, h, i, None, f"down{i}.{j}")
+                    h = self._transformer(blk.attentions[j], h, i, slot[sk], f"down{i}.{j}.attn")
                 else:
-                    h = self._resnet(rb, h, i, [None, slot[sk]], f"down{i}.{j}")
+                    h = self._resnet(rb, h, i, slot[sk], f"down{i}.{j}")
                 sk += 1
             if blk.downsampler is not None:
-                h = self._resnet(blk.downsampler, h, i, [None, slot[sk]], f"down{i}.ds", down=True)
+                h = self._resnet(blk.downsampler, h, i, slot[sk], f"down{i}.ds", down=True)
                 sk += 1
         # ---- middle ----
         mb = net.middle_block
-        h = self._resnet(mb.resnet_1, h, nl - 1, [None], "mid.r1")
-        h = self._transformer(mb.attention, h, nl - 1, [None], "mid.attn")
-        h = self._resnet(mb.resnet_2, h, nl - 1, [cats[0][0].sl(0, ch[-1])], "mid.r2", standalone=False)
+        h = self._resnet(mb.resnet_1, h, nl - 1, None, "mid.r1")
+        h = self._transformer(mb.attention, h, nl - 1, None, "mid.attn")
+        self._resnet(mb.resnet_2, h, nl - 1, cats[0][0].sl(0, ch[-1]), "mid.r2")
         # ---- up path ----
         for i, blk in enumerate(net.up_blocks):
             lvl = nl - 1 - i
             for j, rb in enumerate(blk.resnets):
                 last_in_block = j == len(blk.resnets) - 1
-                nxt: Optional[Sl] = None
-                if not last_in_block:
-                    nxt = cats[i][j + 1].sl(0, ch[lvl])
-                has_attn = cfg["attention_levels"][lvl]
-                last_of_all = last_in_block and blk.upsampler is None
-                if has_attn:
-                    h = self._resnet(rb, cats[i][j], lvl, [None], f"up{i}.{j}")
-                    h = self._transformer(blk.attentions[j], h, lvl, [nxt] if nxt is not None else [None],
-                                          f"up{i}.{j}.attn", standalone=nxt is None)
+                nxt: Optional[Sl] = None if last_in_block else cats[i][j + 1].sl(0, ch[lvl])
+                if cfg["attention_levels"][lvl]:
+                    h = self._resnet(rb, cats[i][j].sl(), lvl, None, f"up{i}.{j}")
+                    h = self._transformer(blk.attentions[j], h, lvl, nxt, f"up{i}.{j}.attn")
                 else:
-                    h = self._resnet(rb, cats[i][j], lvl, [nxt] if nxt is not None else [None], f"up{i}.{j}",
-                                     standalone=nxt is None)
+                    h = self._resnet(rb, cats[i][j].sl(), lvl, nxt, f"up{i}.{j}")
             if blk.upsampler is not None:
-                h = self._resnet(blk.upsampler, h, lvl, [cats[i + 1][0].sl(0, ch[lvl])], f"up{i}.us", up=True,
-                                 standalone=False)
+                h = self._resnet(blk.upsampler, h, lvl, cats[i + 1][0].sl(0, ch[lvl]), f"up{i}.us", up=True)
         # ---- head ----
         a = B(0, ch[0], "out.a")
         gn = NormActOp(h, "group", ops.ACT_SILU, [a.sl()], gn=net.out[0])
@@ -395,34 +386,46 @@ class _AttenEngine(_EngineBase):
                 self.params.append(p)
 
     # ------------------------------------------------------------------------------------------------ builders
-    def _gn_act(self, z: Buf, gn: nn.GroupNorm, act: int, dst: Buf) -> NormActOp:
-        op = NormActOp(z, "group", act, [dst.sl()], gn=gn)
+    def _gn_act(self, z, gn: nn.GroupNorm, act: int, dst: Buf, extra: Optional[Sl] = None) -> NormActOp:
+        op = NormActOp(z, "group", act, [dst.sl()], gn=gn, extra=extra)
         self.tape.add(op)
         self._bind += [(op, "grad_gamma", gn.weight), (op, "grad_beta", gn.bias)]
         return op
 
-    def _resnet(self, rb: ResnetBlock, x: Buf, lvl: int, dsts: List[Optional[Sl]], name: str, up: bool = False,
-                down: bool = False, standalone: bool = True) -> Optional[Buf]:
-        """ResnetBlock.forward (atten_unet_model.py:641-662).  ``dsts``: None entries mean "a fresh standalone buffer"
-        (returned); Sl entries are concat-buffer slots that receive a copy of the output."""
+    def _resnet(self, rb: ResnetBlock, x: Sl, lvl: int, dst: Optional[Sl], name: str, up: bool = False,
+                down: bool = False) -> Sl:
+        """ResnetBlock.forward (atten_unet_model.py:641-662).  ``x``: the input as a channel slice; ``dst``: where the block
+        output goes (a slot of a concat buffer) or None for a fresh buffer.  Returns the slice holding the output.
+
+        The residual sum ``out = conv2(...) + skip(x)`` has NO backward pass: d out / d conv2 = d out / d skip = identity, so
+        conv2 (and a 1x1 skip convolution, or the resampling of an up/down block) read their output gradient straight from
+        out's gradient slice, and with an identity skip that slice is added to norm1's dz inside its apply pass (``extra``)."""
         t, dev, n = self.tape, self.dev, self.n
         cin, cout = rb.channels, rb.out_channels
         assert x.c == cin, (name, x.c, cin)
-        a1 = Buf(n, x.d, x.h, x.w, cin, dev, name + ".a1")
-        self._gn_act(x, rb.norm1, ops.ACT_SILU, a1)
+        xb = x.buf
+        d, h, w = xb.d, xb.h, xb.w
+        od, oh, ow = (2 * d, 2 * h, 2 * w) if up else ((d // 2, h // 2, w // 2) if down else (d, h, w))
+        out = dst if dst is not None else Buf(n, od, oh, ow, cout, dev, name + ".out").sl()
+        assert (out.buf.d, out.buf.h, out.buf.w, out.c) == (od, oh, ow, cout), name
+        identity = isinstance(rb.skip_connection, nn.Identity)
+        a1 = Buf(n, d, h, w, cin, dev, name + ".a1")
+        self._gn_act(x, rb.norm1, ops.ACT_SILU, a1, extra=out if (identity and not up and not down) else None)
         if down:
-            a1p = Buf(n, x.d // 2, x.h // 2, x.w // 2, cin, dev, name + ".a1p")
-            xs = Buf(n, x.d // 2, x.h // 2, x.w // 2, cin, dev, name + ".xs")
+            assert identity
+            a1p = Buf(n, od, oh, ow, cin, dev, name + ".a1p")
+            xs = Buf(n, od, oh, ow, cin, dev, name + ".xs").sl()
             t.add(ResampleOp(a1.sl(), a1p.sl(), up=False))
-            t.add(ResampleOp(x.sl(), xs.sl(), up=False))
+            t.add(ResampleOp(x, xs, up=False, dst_grad=out))
             c1 = self._conv(a1p.sl(), rb.conv1.conv, ksize=3, stride=1, pad=1, name=name + ".conv1")
         elif up:
-            xs = Buf(n, 2 * x.d, 2 * x.h, 2 * x.w, cin, dev, name + ".xs")
-            t.add(ResampleOp(x.sl(), xs.sl(), up=True))
+            assert identity
+            xs = Buf(n, od, oh, ow, cin, dev, name + ".xs").sl()
+            t.add(ResampleOp(x, xs, up=True, dst_grad=out))
             if cin <= 32 and cout <= 32:
                 # few channels (the full-resolution end of the up path): materialising the up-sampled tensor (a bandwidth-bound copy) and running the
                 # slab kernels on it beats the phase-decomposed gather-form kernel, whose 64-channel K chunks are half empty
-                a1u = Buf(n, 2 * x.d, 2 * x.h, 2 * x.w, cin, dev, name + ".a1u")
+                a1u = Buf(n, od, oh, ow, cin, dev, name + ".a1u")
                 t.add(ResampleOp(a1.sl(), a1u.sl(), up=True))
                 c1 = self._conv(a1u.sl(), rb.conv1.conv, ksize=3, stride=1, pad=1, name=name + ".conv1")
             else:
@@ -430,41 +433,28 @@ class _AttenEngine(_EngineBase):
         else:
             xs = x
             c1 = self._conv(a1.sl(), rb.conv1.conv, ksize=3, stride=1, pad=1, name=name + ".conv1")
-        a2 = Buf(n, c1.z.d, c1.z.h, c1.z.w, cout, dev, name + ".a2")
+        a2 = Buf(n, od, oh, ow, cout, dev, name + ".a2")
         self._gn_act(c1.z, rb.norm2, ops.ACT_SILU, a2)
-        c2 = self._conv(a2.sl(), rb.conv2.conv, ksize=3, stride=1, pad=1, name=name + ".conv2")
-        if isinstance(rb.skip_connection, nn.Identity):
-            res = xs.sl()
+        c2 = self._conv(a2.sl(), rb.conv2.conv, ksize=3, stride=1, pad=1, name=name + ".conv2", dy_from=out)
+        if identity:
+            res = xs
         else:
-            cs = self._conv(xs.sl(), rb.skip_connection.conv, ksize=1, stride=1, pad=0, name=name + ".skip")
-            res = cs.z.sl()
-        return self._emit(c2.z, res, dsts, name)
-
-    def _emit(self, z: Buf, res: Sl, dsts: List[Optional[Sl]], name: str) -> Optional[Buf]:
-        """out = z + res written to up to two destinations; returns the standalone buffer if one was requested."""
-        out = None
-        real: List[Sl] = []
-        for d in dsts:
-            if d is None:
-                out = Buf(z.n, z.d, z.h, z.w, z.c, self.dev, name + ".out")
-                real.append(out.sl())
-            else:
-                real.append(d)
-        self.tape.add(NormActOp(z, "none", ops.ACT_NONE, real, res=res))
+            res = self._conv(xs, rb.skip_connection.conv, ksize=1, stride=1, pad=0, name=name + ".skip", dy_from=out).z.sl()
+        t.add(NormActOp(c2.z, "none", ops.ACT_NONE, [out], res=res, no_bwd=True))
         return out
 
     def _linear(self, x: Sl, lin: nn.Linear, name: str, out: Optional[Sl] = None) -> ConvOp:
         return self._conv(x, lin, ksize=1, stride=1, pad=0, name=name, out=out)
 
-    def _transformer(self, st: SpatialTransformer, x: Buf, lvl: int, dsts: List[Optional[Sl]], name: str,
-                     standalone: bool = True) -> Optional[Buf]:
+    def _transformer(self, st: SpatialTransformer, x: Sl, lvl: int, dst: Optional[Sl], name: str) -> Sl:
         """SpatialTransformer.forward (atten_unet_model.py:315-343) with one BasicTransformerBlock (:225-235)."""
         t, dev, n = self.tape, self.dev, self.n
         c = x.c
-        L = x.d * x.h * x.w
+        xb = x.buf
+        L = xb.d * xb.h * xb.w
         blk: BasicTransformerBlock = st.transformer_blocks[0]
         heads = blk.attn1.num_heads
-        T = lambda ch_, nm: Buf(n, x.d, x.h, x.w, ch_, dev, f"{name}.{nm}")
+        T = lambda ch_, nm: Buf(n, xb.d, xb.h, xb.w, ch_, dev, f"{name}.{nm}")
         g = T(c, "gn")
         self._gn_act(x, st.norm, ops.ACT_NONE, g)
         t0 = self._conv(g.sl(), st.proj_in.conv, ksize=1, stride=1, pad=0, name=name + ".proj_in").z
@@ -497,7 +487,9 @@ class _AttenEngine(_EngineBase):
         t3 = T(inner, "t3")
         t.add(NormActOp(f2, "none", ops.ACT_NONE, [t3.sl()], res=t1.sl()))
         po = self._conv(t3.sl(), st.proj_out.conv, ksize=1, stride=1, pad=0, name=name + ".proj_out").z
-        return self._emit(po, x.sl(), dsts, name)
+        out = dst if dst is not None else T(c, "out").sl()
+        t.add(NormActOp(po, "none", ops.ACT_NONE, [out], res=x))
+        return out
 
     # ------------------------------------------------------------------------------------------------ run
     def grad_slots(self, out=None):
@@ -642,13 +634,15 @@ class _ClsEngine(_AttenEngine):
         t = self.tape
         self.inp = Buf(n, D, H, W, self.CPAD, dev, "cls.input")
         c_in = self._conv(self.inp.sl(), net.conv_in.conv, ksize=3, stride=1, pad=1, need_dx=False, name="cls.conv_in")
-        h = c_in.z
+        hs: Sl = c_in.z.sl()
         for i, blk in enumerate(net.down_blocks):
             for j, rb in enumerate(blk.resnets):
-                h = self._resnet(rb, h, i, [None], f"cls.down{i}.{j}")
+                hs = self._resnet(rb, hs, i, None, f"cls.down{i}.{j}")
                 if cfg["attention_levels"][i]:
-                    h = self._transformer(blk.attentions[j], h, i, [None], f"cls.down{i}.{j}.attn")
-            h = self._resnet(blk.downsampler, h, i, [None], f"cls.down{i}.ds", down=True)
+                    hs = self._transformer(blk.attentions[j], hs, i, None, f"cls.down{i}.{j}.attn")
+            hs = self._resnet(blk.downsampler, hs, i, None, f"cls.down{i}.ds", down=True)
+        h = hs.buf
+        assert hs.off == 0 and hs.c == h.c
         feats = (h.rows // n) * h.c
         lin1, lin2 = net.out[0], net.out[3]
         if feats != lin1.in_features:

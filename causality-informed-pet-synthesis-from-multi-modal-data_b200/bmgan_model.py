@@ -426,6 +426,64 @@ class _PatchDiscriminatorNet(nn.Sequential):
         raise RuntimeError("petsyn PatchDiscriminator is a parameter container; call patch_discriminator")
 
 
+class _LastStageOnly(tuple):
+    """What ``PatchDiscriminator.forward`` returns: the reference returns the list of ALL stage outputs and every script reads
+    ``[-1]`` only (train_unet.py:154,179,182; train_unify_causal_gen.py:231,262,265).  Here only that last entry exists;
+    asking for an intermediate feature map raises instead of handing out something else."""
+
+    def __new__(cls, logits, n):
+        self = super().__new__(cls, (None,) * (n - 1) + (logits,))
+        return self
+
+    def __getitem__(self, i):
+        v = super().__getitem__(i)
+        if v is None:
+            raise NotImplementedError("petsyn PatchDiscriminator exposes the last stage (the patch logits, index -1) only")
+        return v
+
+
+class PatchDiscriminator(_PatchDiscriminatorNet):
+    """B200-native drop-in for ``monai_diffusion.generative.networks.nets.PatchDiscriminator`` as the unet / causal scripts
+    build it: ``PatchDiscriminator(**model_dict['discriminator'])`` (train_unet.py:74, unet/config/training.json:40-46: 64
+    channels x 3 layers; training_causal.json:76-82).  Same constructor signature, child names (``initial_conv``, ``"0"`` ..,
+    ``final_conv``: state-dict keys of a reference checkpoint load unchanged) and initialisation; ``forward`` returns a
+    sequence whose ``[-1]`` is the patch-logit tensor."""
+
+    def __init__(self, spatial_dims: int, num_channels: int, in_channels: int, out_channels: int = 1, num_layers_d: int = 3,
+                 kernel_size: int = 4, activation=("LEAKYRELU", {"negative_slope": 0.2}), norm="BATCH", bias: bool = False,
+                 padding=1, dropout=0.0, last_conv_kernel_size=None) -> None:
+        act_ok = isinstance(activation, (tuple, list)) and str(activation[0]).upper() == "LEAKYRELU" and \
+            abs(float(activation[1].get("negative_slope", 0.01)) - LRELU_SLOPE) < 1e-12
+        if spatial_dims != 3 or out_channels != 1 or in_channels != 1 or kernel_size != 4 or not act_ok or \
+                str(norm).upper() != "BATCH" or bias or padding != 1 or dropout not in (0, 0.0, None) or \
+                last_conv_kernel_size not in (None, 4):
+            raise NotImplementedError("petsyn PatchDiscriminator implements the reference's use: 3-D, one channel in / out, "
+                                      "kernel 4, LeakyReLU(0.2), BatchNorm, no conv bias, padding 1, no dropout")
+        super().__init__(num_channels, in_channels, num_layers_d)
+        self._engines: Dict[Tuple, "_DiscEngine"] = {}
+
+    def engine_for(self, x: torch.Tensor) -> "_DiscEngine":
+        key = (tuple(x.shape), x.device.index)
+        eng = self._engines.get(key)
+        if eng is None:
+            eng = _DiscEngine(self, tuple(x.shape), x.device, net=self)
+            self._engines[key] = eng
+        return eng
+
+    def forward(self, x: torch.Tensor):
+        if not x.is_cuda:
+            raise RuntimeError("petsyn PatchDiscriminator runs on CUDA (sm_100a) only; there is no CPU path")
+        if x.dim() != 5 or x.shape[1] != 1:
+            raise ValueError(f"expected x of shape [N, 1, D, H, W], got {tuple(x.shape)}")
+        x = x.contiguous().float()
+        eng = self.engine_for(x)
+        if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in eng.params)):
+            logits = _TapeFn.apply(eng, x, None, *eng.params)
+        else:
+            logits = eng.forward(x, None).clone()
+        return _LastStageOnly(logits, self.num_layers_d + 2)
+
+
 class patch_discriminator(nn.Module):
     """B200-native ``patch_discriminator`` (bmgan_model.py:133-144): ``PatchDiscriminator(3, 32, 1, num_layers_d=4)``;
     ``forward`` returns the last stage's patch logits ``[N, 1, d, h, w]``."""
@@ -463,7 +521,7 @@ class _StemOp(graph.Op):
         self.stem = ops.StemConv(n, D, H, W, conv.out_channels, dev)
         self.z = Buf(n, D // 2, H // 2, W // 2, conv.out_channels, dev, "d.stem.z")
         self.dpatches = torch.zeros_like(self.stem.patches)
-        self.dbias = torch.zeros(conv.out_channels, dtype=torch.float32, device=dev)
+        self.dbias = torch.zeros(conv.out_channels, dtype=torch.float64, device=dev)
         self.grad_w = self.grad_b = None
         self.acc_dw = False
         self.flops = 2.0 * self.z.rows * conv.out_channels * 64
@@ -499,10 +557,10 @@ class _StemOp(graph.Op):
 
 
 class _DiscEngine(_EngineBase):
-    def __init__(self, disc: patch_discriminator, shape, dev):
+    def __init__(self, disc: nn.Module, shape, dev, net: Optional[_PatchDiscriminatorNet] = None):
         super().__init__(disc, dev)
         n, _, D, H, W = shape
-        net = disc.patch_d
+        net = disc.patch_d if net is None else net
         L = net.num_layers_d
         if D % (1 << L) or H % (1 << L) or W % (1 << L):
             raise ValueError(f"spatial dims {D}x{H}x{W} must be divisible by {1 << L}")
@@ -655,7 +713,7 @@ class _LinearHeads(graph.Op):
         self.b = torch.zeros(16, dtype=torch.float32, device=dev)
         self.out = torch.zeros(n, 16, dtype=torch.float32, device=dev)
         self.dout = torch.zeros(n, 16, dtype=torch.bfloat16, device=dev)
-        self.db = torch.zeros(16, dtype=torch.float32, device=dev)
+        self.db = torch.zeros(16, dtype=torch.float64, device=dev)
         self.grad = {}          # id(param) -> tensor, bound by the engine
         self.acc_dw = False
         self.flops = 2.0 * n * self.vox * c * 16

@@ -1,6 +1,8 @@
 #include "common.h"
+#include "det_reduce.cuh"
 
 #include <atomic>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -73,6 +75,35 @@ int32_t encode_tmap(CUtensorMap* out, CUtensorMapDataType dtype, int rank, const
                 (unsigned long long)(rank > 4 ? gstr[3] : 0), bdim[0], rank > 1 ? bdim[1] : 0, rank > 2 ? bdim[2] : 0,
                 rank > 3 ? bdim[3] : 0, rank > 4 ? bdim[4] : 0, swizzle_bytes);
   }
+  return PETSYN_OK;
+}
+
+// per-device workspace of the reproducible reductions (det_reduce.cuh): allocated at the first launch that needs it
+int32_t det_workspace(DetWs* out) {
+  static std::mutex mu;
+  static DetWs ws[64];
+  static int mode = -1;           // 1: deterministic (default), 0: float atomics (PETSYN_NONDETERMINISTIC=1)
+  std::lock_guard<std::mutex> lock(mu);
+  if (mode < 0) {
+    const char* e = getenv("PETSYN_NONDETERMINISTIC");
+    mode = (e != nullptr && e[0] != '\0' && e[0] != '0') ? 0 : 1;
+  }
+  if (mode == 0) { *out = DetWs(); return PETSYN_OK; }
+  int dev = 0;
+  PETSYN_CHECK_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64) return fail(PETSYN_EINVAL, "device index %d out of range", dev);
+  if (ws[dev].acc == nullptr) {
+    void* p = nullptr;
+    const size_t acc_bytes = (size_t)kDetRows * kDetRowValues * sizeof(double);
+    cudaError_t err = cudaMalloc(&p, acc_bytes + kDetRows * sizeof(unsigned int));
+    if (err != cudaSuccess)
+      return fail(PETSYN_ECUDA, "allocating the reduction workspace failed: %s (the first norm / loss launch of a device "
+                                "must not happen inside a CUDA-graph capture)", cudaGetErrorString(err));
+    PETSYN_CHECK_CUDA(cudaMemset(p, 0, acc_bytes + kDetRows * sizeof(unsigned int)));
+    ws[dev].acc = reinterpret_cast<double*>(p);
+    ws[dev].counters = reinterpret_cast<unsigned int*>(ws[dev].acc + (size_t)kDetRows * kDetRowValues);
+  }
+  *out = ws[dev];
   return PETSYN_OK;
 }
 

@@ -231,7 +231,8 @@ __global__ void __launch_bounds__(256) pack_weights_multi_kernel(const PackJob* 
 template <int K3, bool TRANSPOSED, int NS>
 __global__ void __launch_bounds__(256) unpack_wgrad_kernel(const float* __restrict__ scratch, float* __restrict__ dw,
                                                            const InvEntryDev* __restrict__ inv, int A, int B, int nsubs,
-                                                           int max_taps, int rows, int kc_pad, int accumulate) {
+                                                           int max_taps, int rows, int kc_pad, int accumulate,
+                                                           int nsplit) {
   constexpr int TA = TRANSPOSED ? 64 : 4, TB = TRANSPOSED ? 4 : 64;
   constexpr int kAP = TB + 1;                        // pitch along a inside a slot
   constexpr int kSlotPitch = (TA * kAP) | 1;
@@ -253,11 +254,18 @@ __global__ void __launch_bounds__(256) unpack_wgrad_kernel(const float* __restri
     const int a_off = TRANSPOSED ? ci : ri, b_off = TRANSPOSED ? ri : ci;
     const bool ok = (a0 + a_off) < A && (b0 + b_off) < B;
     float* dst = tile + a_off * kAP + b_off;
+    // the voxel reduction was split over `nsplit` CTAs, each adding into its own partial image: summed here in split
+    // order, so the weight gradient does not depend on the order the CTAs finished in
+    const int64_t image = (int64_t)nsubs * rows * ldb;
     for (int sub = 0; sub < nsubs; ++sub) {
       const float* src = scratch + ((int64_t)sub * rows + row) * ldb + col;
-#pragma unroll 8
-      for (int t = 0; t < max_taps; ++t)
-        dst[(sub * max_taps + t) * kSlotPitch] = ok ? __ldg(src + (int64_t)t * kc_pad) : 0.f;
+#pragma unroll 4
+      for (int t = 0; t < max_taps; ++t) {
+        float v = 0.f;
+        if (ok)
+          for (int k = 0; k < nsplit; ++k) v += __ldg(src + k * image + (int64_t)t * kc_pad);
+        dst[(sub * max_taps + t) * kSlotPitch] = v;
+      }
     }
   }
   __syncthreads();
@@ -282,7 +290,8 @@ __global__ void __launch_bounds__(256) unpack_wgrad_kernel(const float* __restri
 __global__ void __launch_bounds__(256) unpack_wgrad_small_kernel(const float* __restrict__ scratch,
                                                                  float* __restrict__ dw,
                                                                  const InvEntryDev* __restrict__ inv, int Cout, int Cin,
-                                                                 int k3, int npad, int tpm, int m_tiles, int accumulate) {
+                                                                 int k3, int npad, int tpm, int m_tiles, int accumulate,
+                                                                 int nsplit, int64_t image) {
   const int total = Cout * Cin * k3;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int k = i % k3;
@@ -292,24 +301,31 @@ __global__ void __launch_bounds__(256) unpack_wgrad_small_kernel(const float* __
     float acc = 0.f;
     for (int q = 0; q < e.n; ++q) {
       const int mt = e.tap[q] / tpm, tl = e.tap[q] - mt * tpm;
-      acc += scratch[((int64_t)(e.sub[q] * m_tiles + mt) * 128 + tl * Cin + ci) * npad + co];
+      const float* src = scratch + ((int64_t)(e.sub[q] * m_tiles + mt) * 128 + tl * Cin + ci) * npad + co;
+      for (int ks = 0; ks < nsplit; ++ks) acc += src[ks * image];       // partial images in split order (reproducible)
     }
     if (accumulate) dw[i] += acc; else dw[i] = acc;
   }
 }
 
-// split-K finish: fp32 [rows, C] (contiguous) -> act(x + bias) as bf16 into a channel slice
-__global__ void __launch_bounds__(256) splitk_finish_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst,
-                                                            int64_t rows, int C, int cstride, int coff,
-                                                            const float* __restrict__ bias, int act, float slope,
-                                                            int accumulate) {
+// split-K finish: `nslots` fp32 partial images [rows, C] (one per K split, zero where a split had no work), added in slot
+// order (reproducible: no atomics, no reduction whose order depends on the run) -> act(x + bias) as bf16 into a channel slice
+__global__ void __launch_bounds__(256) splitk_finish_kernel(const float* __restrict__ src, int nslots,
+                                                            __nv_bfloat16* __restrict__ dst, int64_t rows, int C,
+                                                            int cstride, int coff, const float* __restrict__ bias, int act,
+                                                            float slope, int accumulate) {
   const int cpt = C / 8;
   const int64_t total = rows * cpt;
+  const int64_t slot = rows * C;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t r = i / cpt;
     const int c = (int)(i - r * cpt) * 8;
-    const float4 v0 = *reinterpret_cast<const float4*>(src + r * C + c), v1 = *reinterpret_cast<const float4*>(src + r * C + c + 4);
-    float f[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+    float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int k = 0; k < nslots; ++k) {
+      const float* sp = src + k * slot + r * C + c;
+      const float4 v0 = *reinterpret_cast<const float4*>(sp), v1 = *reinterpret_cast<const float4*>(sp + 4);
+      f[0] += v0.x; f[1] += v0.y; f[2] += v0.z; f[3] += v0.w; f[4] += v1.x; f[5] += v1.y; f[6] += v1.z; f[7] += v1.w;
+    }
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
       if (bias) f[q] += __ldg(bias + c + q);
@@ -332,6 +348,48 @@ __global__ void __launch_bounds__(256) splitk_finish_kernel(const float* __restr
     o.z = *reinterpret_cast<uint32_t*>(&b2); o.w = *reinterpret_cast<uint32_t*>(&b3);
     *reinterpret_cast<uint4*>(dst + r * cstride + coff + c) = o;
   }
+}
+
+// Partial images of a weight gradient (one per K split / per persistent CTA) -> image 0, added in image order: the result
+// does not depend on the order the producing CTAs finished in (reproducible weight gradients without atomics).
+// thread = (float4 group g, lane l): lane l adds images l, l + L, ... in ascending order, then the L lane sums are added in
+// lane order by lane 0, which overwrites image 0.
+__global__ void __launch_bounds__(256) reduce_images_kernel(float* __restrict__ scratch, int nimages, int64_t image_floats,
+                                                            int lanes) {
+  __shared__ float4 part[256];
+  const int gpb = 256 / lanes;
+  const int64_t ng = image_floats >> 2;
+  const int64_t g = (int64_t)blockIdx.x * gpb + threadIdx.x % gpb;
+  const int l = threadIdx.x / gpb;
+  float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (g < ng) {
+    const float4* src = reinterpret_cast<const float4*>(scratch) + g;
+#pragma unroll 4
+    for (int k = l; k < nimages; k += lanes) {
+      const float4 v = __ldcg(src + (int64_t)k * ng);
+      a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+    }
+  }
+  part[threadIdx.x] = a;
+  __syncthreads();
+  if (l == 0 && g < ng) {
+    float4 t = part[threadIdx.x];
+    for (int q = 1; q < lanes; ++q) {
+      const float4 v = part[q * gpb + threadIdx.x];
+      t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w;
+    }
+    reinterpret_cast<float4*>(scratch)[g] = t;
+  }
+}
+
+static int32_t reduce_images(float* scratch, int nimages, int64_t image_floats, cudaStream_t st) {
+  if (nimages <= 1) return PETSYN_OK;
+  int lanes = 1;
+  while (lanes < 32 && lanes * 4 <= nimages) lanes *= 2;
+  const int gpb = 256 / lanes;
+  const int64_t ng = image_floats >> 2;
+  reduce_images_kernel<<<(unsigned)((ng + gpb - 1) / gpb), 256, 0, st>>>(scratch, nimages, image_floats, lanes);
+  return check_launch("reduce_images_kernel");
 }
 
 // ------------------------------------------------------------------------------------------------ plan
@@ -707,7 +765,7 @@ static int32_t launch_igemm(const GemmSide& g, int batch, cudaStream_t st) {
 static int32_t run_side(GemmSide& g, const ViewSpec& vc, void* c, const float* bias, int act, float slope, int batch,
                         cudaStream_t st) {
   if (g.ksplit > 1) {
-    const size_t bytes = (size_t)g.out_rows_full * g.R * sizeof(float);
+    const size_t bytes = (size_t)g.out_rows_full * g.R * sizeof(float) * g.ksplit;     // one partial image per K split
     if (g.workspace == nullptr || g.workspace_bytes < bytes)
       return fail(PETSYN_ENOMEM, "split-K needs a %zu-byte workspace (petsyn_conv_set_workspace)", bytes);
     PETSYN_CHECK_CUDA(cudaMemsetAsync(g.workspace, 0, bytes, st));
@@ -715,7 +773,7 @@ static int32_t run_side(GemmSide& g, const ViewSpec& vc, void* c, const float* b
     if (rc) return rc;
     const int64_t total = g.out_rows_full * (g.R / 8);
     const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>((total + 255) / 256, 148 * 8));
-    splitk_finish_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const float*>(g.workspace),
+    splitk_finish_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const float*>(g.workspace), g.ksplit,
                                                  reinterpret_cast<__nv_bfloat16*>(c), g.out_rows_full, g.R, vc.cstride,
                                                  vc.coff, bias, act, slope, g.accumulate ? 1 : 0);
     return check_launch("splitk_finish_kernel");
@@ -743,8 +801,9 @@ static int32_t bind_side(GemmSide& g, const ViewSpec& va, const ViewSpec& vc, co
   const bool c_f32 = g.out_fp32 || split;
   const int c_esz = c_f32 ? 4 : 2;
   const bool c_swizzled = (g.block_n * c_esz) % 128 == 0;
-  ViewSpec vws = vc;               // split-K accumulates into a dense fp32 image of the output tensor
-  vws.cstride = g.R; vws.coff = 0;
+  ViewSpec vws = vc;               // split-K: every split stores its own dense fp32 partial image of the output tensor
+  vws.cstride = g.R; vws.coff = 0; // (slot s of sample n = "sample" s * N + n of the workspace view)
+  if (split) vws.N = vc.N * g.ksplit;
   if (split && g.workspace == nullptr) return fail(PETSYN_ENOMEM, "split-K workspace not set (petsyn_conv_set_workspace)");
   const int chunk_c = c_swizzled ? 128 / c_esz : g.block_n;
   const int c_swz = c_swizzled ? 128 : 0;
@@ -879,7 +938,7 @@ static int32_t launch_pack_multi(int cls, const PackJob* jobs, int njobs, int ti
 
 template <int K3, bool T, int NS>
 static int32_t launch_unpack_t(const float* scratch, float* dw, const InvEntryDev* inv, int A, int B, const GemmSide& f,
-                               int accumulate, cudaStream_t st) {
+                               int accumulate, int nsplit, cudaStream_t st) {
   constexpr int TA = T ? 64 : 4, TB = T ? 4 : 64;
   const size_t smem = ((size_t)f.subs.size() * f.prog.max_taps + 1) * ((TA * (TB + 1)) | 1) * sizeof(float);
   static size_t smem_set = 0;
@@ -890,16 +949,16 @@ static int32_t launch_unpack_t(const float* scratch, float* dw, const InvEntryDe
   }
   dim3 grid((unsigned)((A + TA - 1) / TA), (unsigned)((B + TB - 1) / TB));
   unpack_wgrad_kernel<K3, T, NS><<<grid, 256, smem, st>>>(scratch, dw, inv, A, B, (int)f.subs.size(), f.prog.max_taps,
-                                                          f.R, f.kc_pad, accumulate);
+                                                          f.R, f.kc_pad, accumulate, nsplit);
   return check_launch("unpack_wgrad_kernel");
 }
 
 static int32_t launch_unpack(int k3, bool transposed, int ns, const float* scratch, float* dw, const InvEntryDev* inv,
-                             int A, int B, const GemmSide& f, int accumulate, cudaStream_t st) {
+                             int A, int B, const GemmSide& f, int accumulate, int nsplit, cudaStream_t st) {
 #define PETSYN_UNPACK_CASE(K, NS)                                                                          \
   if (k3 == K && ns <= NS)                                                                                 \
-    return transposed ? launch_unpack_t<K, true, NS>(scratch, dw, inv, A, B, f, accumulate, st)            \
-                      : launch_unpack_t<K, false, NS>(scratch, dw, inv, A, B, f, accumulate, st);
+    return transposed ? launch_unpack_t<K, true, NS>(scratch, dw, inv, A, B, f, accumulate, nsplit, st)    \
+                      : launch_unpack_t<K, false, NS>(scratch, dw, inv, A, B, f, accumulate, nsplit, st);
   PETSYN_UNPACK_CASE(1, 1)
   PETSYN_UNPACK_CASE(8, 1)
   PETSYN_UNPACK_CASE(27, 1)
@@ -1095,17 +1154,21 @@ size_t petsyn_conv_wgrad_scratch_bytes(const petsyn_conv_plan* pl) {
   if (pl->wg_slab) {
     const int atoms = pl->desc.cin / 16, groups = (atoms + 2) / 3, apg = (atoms + groups - 1) / groups;
     const int nacc = pl->wg_slab_halo ? 3 : 1;
-    return (size_t)groups * (pl->desc.cout / 16) * nacc * 48 * (nacc * apg * 16) * sizeof(float);
+    // one image per persistent CTA (at most 2 CTAs per SM share the (co atom, channel group) grid); the unpack kernel adds
+    // them in CTA order
+    const int images = std::max(1, 296 / ((pl->desc.cout / 16) * groups));
+    return (size_t)groups * (pl->desc.cout / 16) * nacc * 48 * (nacc * apg * 16) * sizeof(float) * images;
   }
-  if (pl->wg_small) return (size_t)pl->fprop.subs.size() * pl->wg_mtiles * 128 * pl->wg_npad * sizeof(float);
-  return packed_bytes(pl->fprop) * 2;
+  // gather-form kernels: one fp32 partial image per K split (summed in split order by the unpack kernel)
+  if (pl->wg_small) return (size_t)pl->fprop.subs.size() * pl->wg_mtiles * 128 * pl->wg_npad * sizeof(float) * pl->wg_ksplit;
+  return packed_bytes(pl->fprop) * 2 * pl->wg_ksplit;
 }
 
 size_t petsyn_conv_workspace_bytes(const petsyn_conv_plan* pl) {
   if (!pl) return 0;
   size_t b = 0;
   for (const GemmSide* g : {&pl->fprop, &pl->dgrad})
-    if (g->ksplit > 1) b = std::max(b, (size_t)g->out_rows_full * g->R * sizeof(float));
+    if (g->ksplit > 1) b = std::max(b, (size_t)g->out_rows_full * g->R * sizeof(float) * g->ksplit);
   return b;
 }
 
@@ -1279,18 +1342,20 @@ int32_t petsyn_conv_wgrad(petsyn_conv_plan* pl, const void* x, const void* dy, v
       const int occ = q.tmem_cols <= 256 ? std::max(1, std::min(2, (227 * 1024) / (pl->wg_slab_smem + 1024))) : 1;
       const int ctas = std::max(1, 148 * occ / (co_atoms * groups));
       slab_split(q.W, q.H, q.D, q.batch, kWgW, kWgH, ctas, &q.dchunk, &q.nchunks, &q.items);
-      pl->wg_slab_grid = std::min(ctas, q.items);
+      pl->wg_slab_grid = std::min(std::min(ctas, q.items), std::max(1, 296 / (co_atoms * groups)));
+      q.image_floats = (int64_t)groups * co_atoms * nacc * 48 * ncols;
       PETSYN_CHECK_CUDA(cudaFuncSetAttribute(slab_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
       pl->wg_key_x = x; pl->wg_key_g = dy; pl->wg_key_s = scratch;
     }
-    PETSYN_CHECK_CUDA(cudaMemsetAsync(scratch, 0, petsyn_conv_wgrad_scratch_bytes(pl), st));
     dim3 grid((unsigned)pl->wg_slab_grid, (unsigned)co_atoms, (unsigned)groups);
     slab_wgrad_kernel<<<grid, 192, pl->wg_slab_smem, st>>>(q);
     int32_t rc = check_launch("slab_wgrad_kernel");
     if (rc) return rc;
-    const int total = pl->desc.cout * pl->desc.cin * pl->k3;
-    slab_wgrad_unpack_kernel<<<std::min((total + 255) / 256, 148 * 8), 256, 0, st>>>(
-        reinterpret_cast<const float*>(scratch), dw, pl->desc.cout, pl->desc.cin, atoms, pl->k3, accumulate);
+    rc = reduce_images(reinterpret_cast<float*>(scratch), pl->wg_slab_grid, q.image_floats, st);
+    if (rc) return rc;
+    slab_wgrad_unpack_kernel<<<(unsigned)std::min<int64_t>((q.image_floats + 255) / 256, 148 * 8), 256, 0, st>>>(
+        reinterpret_cast<const float*>(scratch), dw, pl->desc.cout, pl->desc.cin, atoms, pl->k3, accumulate, 1,
+        q.image_floats);
     return check_launch("slab_wgrad_unpack_kernel");
   }
   if (pl->wg_small) {
@@ -1309,7 +1374,7 @@ int32_t petsyn_conv_wgrad(petsyn_conv_plan* pl, const void* x, const void* dy, v
                               pl->wg_box_w, pl->wg_box_h, pl->wg_box_d, 32);
         if (rc) return rc;
       }
-      uint64_t dims[2] = {(uint64_t)pl->wg_npad, (uint64_t)f.subs.size() * pl->wg_mtiles * 128};
+      uint64_t dims[2] = {(uint64_t)pl->wg_npad, (uint64_t)f.subs.size() * pl->wg_mtiles * 128 * pl->wg_ksplit};
       uint64_t strides[1] = {dims[0] * 4};
       uint32_t box[2] = {(uint32_t)pl->wg_npad, 128u};
       int32_t rc = encode_tmap(&q.d_map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, scratch, dims, strides, box, 0);
@@ -1324,6 +1389,7 @@ int32_t petsyn_conv_wgrad(petsyn_conv_plan* pl, const void* x, const void* dy, v
       q.cin = pl->desc.cin; q.cin_atoms = pl->desc.cin / 16;
       q.n_atoms = pl->wg_npad / 16;
       q.tpm = pl->wg_tpm; q.m_tiles = pl->wg_mtiles; q.ksplit = pl->wg_ksplit;
+      q.image_rows = (int)f.subs.size() * pl->wg_mtiles * 128;
       pl->wg_key_x = x; pl->wg_key_g = dy; pl->wg_key_s = scratch;
     }
     PETSYN_CHECK_CUDA(cudaMemsetAsync(scratch, 0, petsyn_conv_wgrad_scratch_bytes(pl), st));
@@ -1340,9 +1406,12 @@ int32_t petsyn_conv_wgrad(petsyn_conv_plan* pl, const void* x, const void* dy, v
     int32_t rc = check_launch("wgrad_small_kernel");
     if (rc) return rc;
     const int total = pl->desc.cout * pl->desc.cin * pl->k3;
+    const int64_t image = (int64_t)f.subs.size() * pl->wg_mtiles * 128 * pl->wg_npad;
+    rc = reduce_images(reinterpret_cast<float*>(scratch), pl->wg_ksplit, image, st);
+    if (rc) return rc;
     unpack_wgrad_small_kernel<<<std::min((total + 255) / 256, 148 * 8), 256, 0, st>>>(
         reinterpret_cast<const float*>(scratch), dw, pl->d_inv, pl->desc.cout, pl->desc.cin, pl->k3, pl->wg_npad, pl->wg_tpm,
-        pl->wg_mtiles, accumulate);
+        pl->wg_mtiles, accumulate, 1, image);
     return check_launch("unpack_wgrad_small_kernel");
   }
   WgradParams& p = pl->wg_params;
@@ -1360,10 +1429,11 @@ int32_t petsyn_conv_wgrad(petsyn_conv_plan* pl, const void* x, const void* dy, v
                             pl->wg_box_w, pl->wg_box_h, pl->wg_box_d, 128);
       if (rc) return rc;
     }
-    uint64_t dims[2] = {(uint64_t)f.prog.max_taps * f.kc_pad, (uint64_t)f.subs.size() * f.R};
+    uint64_t dims[2] = {(uint64_t)f.prog.max_taps * f.kc_pad, (uint64_t)f.subs.size() * f.R * pl->wg_ksplit};
     uint64_t strides[1] = {dims[0] * 4};
     uint32_t box[2] = {32u, 128u};
     int32_t rc = encode_tmap(&p.d_map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, scratch, dims, strides, box, 128);
+    p.image_rows = (int)f.subs.size() * f.R;
     if (rc) return rc;
     for (size_t i = 0; i < f.subs.size(); ++i) p.subs[i] = f.subs[i];
     p.taps = f.d_taps;
@@ -1407,8 +1477,11 @@ int32_t petsyn_conv_wgrad(petsyn_conv_plan* pl, const void* x, const void* dy, v
   {
     const bool convt = pl->desc.op == PETSYN_OP_CONVT;
     const int A = convt ? pl->desc.cin : pl->desc.cout, B = convt ? pl->desc.cout : pl->desc.cin;
+    rc = reduce_images(reinterpret_cast<float*>(scratch), pl->wg_ksplit,
+                       (int64_t)f.subs.size() * f.R * f.prog.max_taps * f.kc_pad, st);
+    if (rc) return rc;
     return launch_unpack(pl->k3, convt, pl->inv_max, reinterpret_cast<const float*>(scratch), dw, pl->d_inv, A, B, f,
-                         accumulate, st);
+                         accumulate, 1, st);
   }
 }
 

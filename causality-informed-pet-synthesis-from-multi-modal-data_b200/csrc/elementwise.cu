@@ -7,6 +7,7 @@
 #include <algorithm>
 
 #include "common.h"
+#include "det_reduce.cuh"
 
 namespace petsyn {
 
@@ -75,10 +76,11 @@ struct RowIter {
   }
 };
 
-// Block-level reduction of per-thread 8-channel partials (NV values each) over the rows dimension, then one atomicAdd
-// per channel into out[v*C + c].
+// Block-level reduction of per-thread 8-channel partials (NV values each) over the rows dimension, then one 64-bit atomic
+// per channel into the DOUBLE accumulator out[v*C + c] (exact, hence order-free, summation of the fp32 partials: see
+// det_reduce.cuh).
 template <int NV>
-__device__ __forceinline__ void block_reduce_channels(const RowIter& it, float (&acc)[NV][8], float* smem, float* out,
+__device__ __forceinline__ void block_reduce_channels(const RowIter& it, float (&acc)[NV][8], float* smem, double* out,
                                                       int C) {
   // smem: [rpp][NV][C]
   if (it.active) {
@@ -91,11 +93,21 @@ __device__ __forceinline__ void block_reduce_channels(const RowIter& it, float (
   for (int e = threadIdx.x; e < NV * C; e += blockDim.x) {
     float s = 0.f;
     for (int r = 0; r < it.rpp; ++r) s += smem[r * NV * C + e];
-    atomicAdd(out + e, s);
+    atomicAdd(out + e, (double)s);
   }
 }
 
-__global__ void __launch_bounds__(256) bn_stats_kernel(const __nv_bfloat16* __restrict__ z, float* __restrict__ sums,
+// one scalar per CTA (thread 0 holds it) combined the same way into *out
+__device__ __forceinline__ void scalar_reduce(float s, float* out, const DetWs& ws) {
+  __shared__ float scratch[256];
+  det_cta_reduce(
+      ws, 1, scratch, [&](int) { return s; },
+      [&](int, float t, bool atomic) {
+        if (atomic) atomicAdd(out, t); else *out += t;
+      });
+}
+
+__global__ void __launch_bounds__(256) bn_stats_kernel(const __nv_bfloat16* __restrict__ z, double* __restrict__ sums,
                                                        int64_t rows, int C) {
   extern __shared__ float smem_f[];
   RowIter it(C);
@@ -123,7 +135,7 @@ __global__ void __launch_bounds__(256) bn_stats_kernel(const __nv_bfloat16* __re
   block_reduce_channels<2>(it, acc, smem_f, sums, C);
 }
 
-__global__ void bn_finalize_kernel(const float* __restrict__ sums, const float* __restrict__ gamma,
+__global__ void bn_finalize_kernel(const double* __restrict__ sums, const float* __restrict__ gamma,
                                    const float* __restrict__ beta, float* __restrict__ running_mean,
                                    float* __restrict__ running_var, float* __restrict__ scale,
                                    float* __restrict__ shift, float* __restrict__ save_mean,
@@ -193,7 +205,7 @@ __global__ void __launch_bounds__(256) norm_act_bwd_reduce_kernel(
     const __nv_bfloat16* __restrict__ z, const float* __restrict__ scale, const float* __restrict__ shift,
     const float* __restrict__ mean, const float* __restrict__ rstd, const __nv_bfloat16* __restrict__ g1, int cs1,
     int co1, int act1, const __nv_bfloat16* __restrict__ g2, int cs2, int co2, int act2, float slope,
-    float* __restrict__ sums, int64_t rows, int C) {
+    double* __restrict__ sums, int64_t rows, int C) {
   extern __shared__ float smem_f[];
   RowIter it(C);
   float acc[2][8];
@@ -238,13 +250,13 @@ __global__ void __launch_bounds__(256) norm_act_bwd_apply_kernel(
     const __nv_bfloat16* __restrict__ z, const float* __restrict__ scale, const float* __restrict__ shift,
     const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ gamma,
     const __nv_bfloat16* __restrict__ g1, int cs1, int co1, int act1, const __nv_bfloat16* __restrict__ g2, int cs2,
-    int co2, int act2, float slope, const float* __restrict__ sums, __nv_bfloat16* __restrict__ dz,
+    int co2, int act2, float slope, const double* __restrict__ sums, __nv_bfloat16* __restrict__ dz,
     float* __restrict__ dgamma, float* __restrict__ dbeta, int64_t rows, int C) {
   RowIter it(C);
   if (blockIdx.x == 0 && dgamma != nullptr) {
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
-      dbeta[c] = sums[c];
-      dgamma[c] = sums[C + c];
+      dbeta[c] = (float)sums[c];
+      dgamma[c] = (float)sums[C + c];
     }
   }
   if (!it.active) return;
@@ -256,7 +268,9 @@ __global__ void __launch_bounds__(256) norm_act_bwd_apply_kernel(
     mu = load8f(mean + it.tx * 8);
     rs = load8f(rstd + it.tx * 8);
     const F8 ga = gamma ? load8f(gamma + it.tx * 8) : k0;
-    const F8 s0 = load8f(sums + it.tx * 8), s1 = load8f(sums + C + it.tx * 8);
+    F8 s0, s1;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { s0.v[i] = (float)sums[it.tx * 8 + i]; s1.v[i] = (float)sums[C + it.tx * 8 + i]; }
     const float inv = 1.f / (float)rows;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
@@ -311,7 +325,7 @@ __device__ __forceinline__ float block_sum(float v, float* smem) {
 
 __global__ void __launch_bounds__(256) l1_loss_kernel(const float* __restrict__ y, const float* __restrict__ t,
                                                       float* __restrict__ loss, float* __restrict__ dy, int64_t n,
-                                                      float inv_n, float gscale) {
+                                                      float inv_n, float gscale, const DetWs ws) {
   __shared__ float red[8];
   float acc = 0.f;
   const int64_t n4 = n / 4;
@@ -334,12 +348,12 @@ __global__ void __launch_bounds__(256) l1_loss_kernel(const float* __restrict__ 
       if (dy) dy[i] = gscale * ((d > 0.f) - (d < 0.f));
     }
   const float s = block_sum(acc, red);
-  if (threadIdx.x == 0) atomicAdd(loss, s * inv_n);
+  scalar_reduce(s * inv_n, loss, ws);
 }
 
 __global__ void __launch_bounds__(256) mse_const_kernel(const float* __restrict__ x, float target,
                                                         float* __restrict__ loss, float* __restrict__ dx, int64_t n,
-                                                        float inv_n, float gscale) {
+                                                        float inv_n, float gscale, const DetWs ws) {
   __shared__ float red[8];
   float acc = 0.f;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
@@ -348,7 +362,7 @@ __global__ void __launch_bounds__(256) mse_const_kernel(const float* __restrict_
     if (dx) dx[i] = 2.f * d * gscale;
   }
   const float s = block_sum(acc, red);
-  if (threadIdx.x == 0) atomicAdd(loss, s * inv_n);
+  scalar_reduce(s * inv_n, loss, ws);
 }
 
 // step_dev (optional): device-resident 1-based step counter, so that a CUDA graph of the training step stays valid as
@@ -403,13 +417,14 @@ __global__ void __launch_bounds__(256) kl_kernel(const float* __restrict__ mu, c
   if (threadIdx.x == 0) atomicAdd(loss, s / (float)n);
 }
 
-__global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g, float* __restrict__ out, int64_t n) {
+__global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g, float* __restrict__ out, int64_t n,
+                                                    const DetWs ws) {
   __shared__ float red[8];
   float acc = 0.f;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
     acc += g[i] * g[i];
   const float s = block_sum(acc, red);
-  if (threadIdx.x == 0) atomicAdd(out, s);
+  scalar_reduce(s, out, ws);
 }
 
 static int row_blocks(int64_t rows, int C) {
@@ -426,7 +441,7 @@ using namespace petsyn;
 
 extern "C" {
 
-int32_t petsyn_bn_stats(const void* z, float* sums, int64_t rows, int32_t c, void* stream) {
+int32_t petsyn_bn_stats(const void* z, double* sums, int64_t rows, int32_t c, void* stream) {
   PETSYN_REQUIRE(z && sums, "null argument");
   PETSYN_REQUIRE(c % 8 == 0 && c >= 8 && c <= 2048, "channels must be a multiple of 8 in [8, 2048]");
   const int rpp = 256 / (c / 8);
@@ -436,7 +451,7 @@ int32_t petsyn_bn_stats(const void* z, float* sums, int64_t rows, int32_t c, voi
   return check_launch("bn_stats_kernel");
 }
 
-int32_t petsyn_bn_finalize(const float* sums, const float* gamma, const float* beta, float* running_mean,
+int32_t petsyn_bn_finalize(const double* sums, const float* gamma, const float* beta, float* running_mean,
                            float* running_var, float* scale, float* shift, float* save_mean, float* save_rstd,
                            int64_t rows, int32_t c, float eps, float momentum, int32_t training, void* stream) {
   PETSYN_REQUIRE(scale && shift, "null argument");
@@ -463,7 +478,7 @@ int32_t petsyn_norm_act_fwd(const void* z, const float* scale, const float* shif
 int32_t petsyn_norm_act_bwd_reduce(const void* z, const float* scale, const float* shift, const float* mean,
                                    const float* rstd, const void* g1, int32_t g1_cstride, int32_t g1_coff,
                                    int32_t act1, const void* g2, int32_t g2_cstride, int32_t g2_coff, int32_t act2,
-                                   float slope, float* sums, int64_t rows, int32_t c, void* stream) {
+                                   float slope, double* sums, int64_t rows, int32_t c, void* stream) {
   PETSYN_REQUIRE(z && g1 && sums, "null argument");
   PETSYN_REQUIRE(c % 8 == 0 && c >= 8 && c <= 2048, "channels must be a multiple of 8 in [8, 2048]");
   const int rpp = 256 / (c / 8);
@@ -479,7 +494,7 @@ int32_t petsyn_norm_act_bwd_reduce(const void* z, const float* scale, const floa
 int32_t petsyn_norm_act_bwd_apply(const void* z, const float* scale, const float* shift, const float* mean,
                                   const float* rstd, const float* gamma, const void* g1, int32_t g1_cstride,
                                   int32_t g1_coff, int32_t act1, const void* g2, int32_t g2_cstride, int32_t g2_coff,
-                                  int32_t act2, float slope, const float* sums, void* dz, float* dgamma,
+                                  int32_t act2, float slope, const double* sums, void* dz, float* dgamma,
                                   float* dbeta, int64_t rows, int32_t c, void* stream) {
   PETSYN_REQUIRE(z && g1 && dz, "null argument");
   PETSYN_REQUIRE(mean == nullptr || sums != nullptr, "normalised backward needs the reduction sums");
@@ -495,8 +510,13 @@ int32_t petsyn_l1_loss_fwd_bwd(const float* y, const float* t, float* loss, floa
   PETSYN_REQUIRE(y && t && loss, "null argument");
   PETSYN_REQUIRE(numel > 0, "empty tensor");
   const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>((numel / 4 + 255) / 256, 148 * 8));
+  DetWs ws;
+  {
+    int32_t rcw = det_workspace(&ws);
+    if (rcw) return rcw;
+  }
   l1_loss_kernel<<<blocks, 256, 0, as_stream(stream)>>>(y, t, loss, dy, numel, 1.f / (float)numel,
-                                                        grad_scale / (float)numel);
+                                                        grad_scale / (float)numel, ws);
   return check_launch("l1_loss_kernel");
 }
 
@@ -505,8 +525,13 @@ int32_t petsyn_mse_const_fwd_bwd(const float* x, float target, float* loss, floa
   PETSYN_REQUIRE(x && loss, "null argument");
   PETSYN_REQUIRE(numel > 0, "empty tensor");
   const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>((numel + 255) / 256, 148 * 8));
+  DetWs ws;
+  {
+    int32_t rcw = det_workspace(&ws);
+    if (rcw) return rcw;
+  }
   mse_const_kernel<<<blocks, 256, 0, as_stream(stream)>>>(x, target, loss, dx, numel, 1.f / (float)numel,
-                                                          grad_scale / (float)numel);
+                                                          grad_scale / (float)numel, ws);
   return check_launch("mse_const_kernel");
 }
 
@@ -531,7 +556,12 @@ int32_t petsyn_adam_step(float* p, const float* g, float* m, float* v, int64_t n
 int32_t petsyn_sumsq(const float* g, float* out, int64_t numel, void* stream) {
   PETSYN_REQUIRE(g && out, "null argument");
   const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>((numel + 255) / 256, 148 * 8));
-  sumsq_kernel<<<blocks, 256, 0, as_stream(stream)>>>(g, out, numel);
+  DetWs ws;
+  {
+    int32_t rcw = det_workspace(&ws);
+    if (rcw) return rcw;
+  }
+  sumsq_kernel<<<blocks, 256, 0, as_stream(stream)>>>(g, out, numel, ws);
   return check_launch("sumsq_kernel");
 }
 

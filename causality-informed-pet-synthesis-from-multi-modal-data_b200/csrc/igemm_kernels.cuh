@@ -248,7 +248,9 @@ __global__ void __launch_bounds__(128) igemm_kernel(const __grid_constant__ Igem
       const int ch = n0 + chunk * Cfg::kChunkC;
       if (ch >= p.rows) break;
       const uint8_t* src = smem + chunk * (128 * Cfg::kRowPitch);
-      if constexpr (OUT_MODE == OUT_F32_REDUCE || OUT_MODE == OUT_BF16_REDUCE)
+      if constexpr (OUT_MODE == OUT_F32_REDUCE)        // split-K: a plain store into this split's own partial image
+        ptx::tma_store_5d(cmap, src, ch, w0, h0, d0, nb + split * p.batch);
+      else if constexpr (OUT_MODE == OUT_BF16_REDUCE)
         ptx::tma_reduce_add_5d(cmap, src, ch, w0, h0, d0, nb);
       else
         ptx::tma_store_5d(cmap, src, ch, w0, h0, d0, nb);
@@ -273,6 +275,7 @@ struct alignas(64) WgradParams {
   int32_t kc_pad;                  // padded Cin per tap in the scratch matrix
   int32_t ksplit;                  // number of CTAs sharing the voxel reduction
   int32_t r_tiles, c_tiles;
+  int32_t image_rows;              // rows of ONE partial image of the scratch (split k adds into rows [k, k+1) * image_rows)
 };
 
 // grid: x = tap (within sub) * r_tiles * c_tiles flattened, y = ksplit index, z = sub
@@ -402,8 +405,10 @@ __global__ void __launch_bounds__(128) wgrad_kernel(const __grid_constant__ Wgra
   if (tid == 0) {
 #pragma unroll 1
     for (int chunk = 0; chunk < BLOCK_N / 32; ++chunk) {
+      // split-private partial image: the only non-zero contribution to an element of image k comes from ONE CTA (tiles
+      // overlap only where the operands are zero-filled), so the reduction order cannot change the sum
       ptx::tma_reduce_add_2d(&p.d_map, smem + chunk * (128 * 128), tap * p.kc_pad + c0 + chunk * 32,
-                             sub.b_row + r0);
+                             int(blockIdx.y) * p.image_rows + sub.b_row + r0);
     }
     ptx::tma_store_commit();
     ptx::tma_store_wait_all();
@@ -431,6 +436,7 @@ struct alignas(64) WgradSmallParams {
   int32_t tpm;                     // taps per M tile
   int32_t m_tiles;                 // M tiles per sub-problem (grid.x)
   int32_t ksplit;
+  int32_t image_rows;              // rows of ONE partial image of the scratch (split k adds into image k)
 };
 
 template <int STAGES>
@@ -551,7 +557,7 @@ __global__ void __launch_bounds__(128) wgrad_small_kernel(const __grid_constant_
   __syncthreads();
   if (warp == 1) ptx::tmem_dealloc(tmem_base, 64);
   if (tid == 0) {
-    ptx::tma_reduce_add_2d(&p.d_map, smem, 0, (int(blockIdx.z) * p.m_tiles + mt) * 128);
+    ptx::tma_reduce_add_2d(&p.d_map, smem, 0, int(blockIdx.y) * p.image_rows + (int(blockIdx.z) * p.m_tiles + mt) * 128);
     ptx::tma_store_commit();
     ptx::tma_store_wait_all();
   }

@@ -9,6 +9,7 @@
 #include <algorithm>
 
 #include "common.h"
+#include "det_reduce.cuh"
 
 namespace petsyn {
 namespace nx {
@@ -119,50 +120,56 @@ struct RowIter {
   }
 };
 
+// Per-channel sums over the rows this CTA streamed, added to DOUBLE-precision accumulators with one 64-bit atomic per CTA
+// and value.  fp32 partials summed in a 53-bit accumulator are exact (so the order the CTAs finish in cannot change the
+// result) as long as every partial is at least 2^-28 of the running sum; see det_reduce.cuh.  The consumers read the double
+// sums directly (finalize / backward constants are computed in double anyway), so there is no ticket and no serial tail.
+// out1[v * pitch1 + off1 + c] += sum, likewise out2 (statistics blocks of WIDER tensors use pitch / off); `extra` (optional)
+// is one more scalar per CTA added the same way into *extra_out (the PReLU slope gradient).
 template <int NV>
-__device__ __forceinline__ void block_reduce_channels(const RowIter& it, float (&acc)[NV][8], float* smem, float* out,
-                                                      int C) {
+__device__ __forceinline__ void block_reduce_channels_to(const RowIter& it, float (&acc)[NV][8], float* smem, double* out1,
+                                                         int pitch1, int off1, double* out2, int pitch2, int off2, int C,
+                                                         float extra = 0.f, double* extra_out = nullptr) {
+  __shared__ float s_extra[8];
   if (it.active) {
 #pragma unroll
     for (int v = 0; v < NV; ++v)
 #pragma unroll
       for (int i = 0; i < 8; ++i) smem[(it.ty * NV + v) * C + it.tx * 8 + i] = acc[v][i];
   }
+  if (extra_out != nullptr) {
+    for (int o = 16; o > 0; o >>= 1) extra += __shfl_xor_sync(0xffffffffu, extra, o);
+    if ((threadIdx.x & 31) == 0) s_extra[threadIdx.x >> 5] = extra;
+  }
   __syncthreads();
-  for (int e = threadIdx.x; e < NV * C; e += blockDim.x) {
+  const int nc = NV * C;
+  for (int e = threadIdx.x; e < nc; e += blockDim.x) {
     float s = 0.f;
-    for (int r = 0; r < it.rpp; ++r) s += smem[r * NV * C + e];
-    atomicAdd(out + e, s);
+    for (int r = 0; r < it.rpp; ++r) s += smem[r * nc + e];
+    const int v = e / C, c = e - v * C;
+    if (out1) atomicAdd(out1 + v * pitch1 + off1 + c, (double)s);
+    if (out2) atomicAdd(out2 + v * pitch2 + off2 + c, (double)s);
+  }
+  if (extra_out != nullptr && threadIdx.x == 0) {
+    float s = 0.f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += s_extra[w];
+    if (s != 0.f) atomicAdd(extra_out, (double)s);
   }
 }
 
-// the same reduction into a statistics block of a WIDER tensor: out[v * pitch + off + c]
 template <int NV>
-__device__ __forceinline__ void block_reduce_channels_to(const RowIter& it, float (&acc)[NV][8], float* smem, float* out1,
-                                                         int pitch1, int off1, float* out2, int pitch2, int off2, int C) {
-  if (it.active) {
-#pragma unroll
-    for (int v = 0; v < NV; ++v)
-#pragma unroll
-      for (int i = 0; i < 8; ++i) smem[(it.ty * NV + v) * C + it.tx * 8 + i] = acc[v][i];
-  }
-  __syncthreads();
-  for (int e = threadIdx.x; e < NV * C; e += blockDim.x) {
-    float s = 0.f;
-    for (int r = 0; r < it.rpp; ++r) s += smem[r * NV * C + e];
-    const int v = e / C, c = e - v * C;
-    if (out1) atomicAdd(out1 + v * pitch1 + off1 + c, s);
-    if (out2) atomicAdd(out2 + v * pitch2 + off2 + c, s);
-  }
+__device__ __forceinline__ void block_reduce_channels(const RowIter& it, float (&acc)[NV][8], float* smem, double* out,
+                                                      int C, float extra = 0.f, double* extra_out = nullptr) {
+  block_reduce_channels_to<NV>(it, acc, smem, out, C, 0, nullptr, 0, 0, C, extra, extra_out);
 }
 
 // sums[sample][0:C] += sum z, sums[sample][C:2C] += sum z^2
-__global__ void __launch_bounds__(256) stats_kernel(const __nv_bfloat16* __restrict__ z, float* __restrict__ sums,
-                                                    int64_t rows, int C) {
+__global__ void __launch_bounds__(256) stats_kernel(const __nv_bfloat16* __restrict__ z, double* __restrict__ sums,
+                                                    int64_t rows, int C, int zcs, int zco) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   float* smem_f = reinterpret_cast<float*>(smem_raw + PfRing::bytes(1));
   RowIter it(C);
-  z += (int64_t)blockIdx.y * rows * C;
+  z += (int64_t)blockIdx.y * rows * zcs + zco;
   sums += (int64_t)blockIdx.y * 2 * C;
   float acc[2][8];
 #pragma unroll
@@ -173,13 +180,13 @@ __global__ void __launch_bounds__(256) stats_kernel(const __nv_bfloat16* __restr
     const int64_t r0 = (int64_t)blockIdx.x * it.rpp + it.ty;
     const __nv_bfloat16* src = z + it.tx * 8;
     for (int k = 0; k < kPf - 1; ++k) {
-      if (r0 + k * stride < rows) pf.issue(k, 0, src + (rows - 1 - (r0 + k * stride)) * C);   // descending, see below
+      if (r0 + k * stride < rows) pf.issue(k, 0, src + (rows - 1 - (r0 + k * stride)) * zcs);   // descending, see below
       PfRing::commit();
     }
     int k = 0;
     for (int64_t r = r0; r < rows; r += stride, ++k) {
       const int64_t rn = r + (kPf - 1) * stride;
-      if (rn < rows) pf.issue((k + kPf - 1) % kPf, 0, src + (rows - 1 - rn) * C);
+      if (rn < rows) pf.issue((k + kPf - 1) % kPf, 0, src + (rows - 1 - rn) * zcs);
       PfRing::commit();
       PfRing::wait();
       const F8 x0 = unpack8(pf.get(k % kPf, 0));
@@ -195,7 +202,7 @@ __global__ void __launch_bounds__(256) stats_kernel(const __nv_bfloat16* __restr
 
 // One thread per (sample, channel).  group_size channels share their statistics (GroupNorm); group_size == 1 is
 // Batch (nsamples == 1) / Instance (nsamples == N) normalisation.
-__global__ void finalize_kernel(const float* __restrict__ sums, const float* __restrict__ gamma,
+__global__ void finalize_kernel(const double* __restrict__ sums, const float* __restrict__ gamma,
                                 const float* __restrict__ beta, float* __restrict__ running_mean,
                                 float* __restrict__ running_var, float* __restrict__ scale, float* __restrict__ shift,
                                 float* __restrict__ save_mean, float* __restrict__ save_rstd, int64_t rows, int C,
@@ -205,7 +212,7 @@ __global__ void finalize_kernel(const float* __restrict__ sums, const float* __r
   const int s = i / C, c = i % C;
   double mean, var;
   if (training || running_mean == nullptr) {
-    const float* sm = sums + (int64_t)s * 2 * C;
+    const double* sm = sums + (int64_t)s * 2 * C;
     const int g0 = c / group_size * group_size;
     double a = 0, b = 0;
     for (int j = 0; j < group_size; ++j) { a += sm[g0 + j]; b += sm[C + g0 + j]; }
@@ -239,22 +246,27 @@ struct Dev {   // device copy of petsyn_normact_desc with typed pointers
   __nv_bfloat16* t2; int cs2, co2, act2;
   float slope;
   __nv_bfloat16* res; int csr, cor, res_acc;
-  float* sums;
+  double* sums;
   __nv_bfloat16* dz;
   float *dgamma, *dbeta;
   const float* slope_dev;
-  float* dslope;
+  double* dslope;
   const float *ka, *kb;   // per (sample, channel) backward constants of the affine/group path (nullptr: plain path)
   int dz_acc;
-  float* dz_colsum;       // optional [C] += column sums of dz
-  float* st1; int st1_c, st1_off;   // optional statistics of destination 1 for the norm that consumes it
-  float* st2; int st2_c, st2_off;
+  double* dz_colsum;      // optional [C] += column sums of dz
+  double* st1; int st1_c, st1_off;   // optional statistics of destination 1 for the norm that consumes it
+  double* st2; int st2_c, st2_off;
   // fused finalize (forward): statistics sums -> scale / shift / mean / rstd inside the apply kernel
-  const float *fin_sums, *fin_gamma, *fin_beta;
+  const double* fin_sums;
+  const float *fin_gamma, *fin_beta;
   int fin_gs;
   float fin_eps;
   // fused group combine (backward): ka / kb / dgamma / dbeta inside the apply kernel
   int gc_gs, gc_ns, gc_acc;   // gc_gs > 0: enabled
+  int zcs, zco;               // channel pitch / offset of z (z may be a channel slice of a wider buffer)
+  int dzcs, dzco;             // ... and of dz
+  const __nv_bfloat16* ex;    // bwd, optional: extra addend of dz (gradient arriving through an identity skip connection)
+  int excs, exco;
 };
 
 // ACT < 0: activation codes read from the descriptor at run time (rare combinations); ACT >= 0: act1 == act2 == ACT
@@ -276,13 +288,13 @@ __global__ void __launch_bounds__(256, 3) fwd_kernel(const Dev d) {
   // previous one touched last (still in the 126 MB L2): producers (convs) write ascending, statistics / backward-reduce
   // read DESCENDING, the apply passes read ascending again
   const int64_t q0 = (int64_t)blockIdx.x * it.rpp + it.ty;
-  const __nv_bfloat16* zsrc = d.z + it.tx * 8;
+  const __nv_bfloat16* zsrc = d.z + d.zco + it.tx * 8;
   const __nv_bfloat16* rsrc = has_res ? d.res + d.cor + it.tx * 8 : nullptr;
   auto issue = [&](int k) {
     const int64_t q = q0 + k * stride;
     if (q < d.rows) {
       const int64_t r = base + q;
-      pf.issue(k % kPf, 0, zsrc + r * d.C);
+      pf.issue(k % kPf, 0, zsrc + r * d.zcs);
       if (has_res) pf.issue(k % kPf, 1, rsrc + r * d.csr);
     }
     PfRing::commit();
@@ -295,7 +307,7 @@ __global__ void __launch_bounds__(256, 3) fwd_kernel(const Dev d) {
   // publishes scale / shift / mean / rstd for the backward pass.  Saves a 4 us launch in front of every apply pass.
   float* fin = reinterpret_cast<float*>(smem_raw + PfRing::bytes(has_res ? 2 : 1));
   if (d.fin_sums != nullptr) {
-    const float* sm = d.fin_sums + (int64_t)s * 2 * d.C;
+    const double* sm = d.fin_sums + (int64_t)s * 2 * d.C;
     const double cnt = (double)d.rows * d.fin_gs;
     for (int c = threadIdx.x; c < d.C; c += blockDim.x) {
       const int g0 = c / d.fin_gs * d.fin_gs;
@@ -383,14 +395,14 @@ __global__ void __launch_bounds__(256, 2) bwd_reduce_kernel(const Dev d) {
     const int64_t stride = (int64_t)gridDim.x * it.rpp;
     PfRing pf(smem_raw, nt);
     const int64_t r0 = (int64_t)blockIdx.x * it.rpp + it.ty;
-    const __nv_bfloat16* zsrc = d.z + base * d.C + it.tx * 8;
+    const __nv_bfloat16* zsrc = d.z + base * d.zcs + d.zco + it.tx * 8;
     const __nv_bfloat16* asrc = d.t1 + base * d.cs1 + d.co1 + it.tx * 8;
     const __nv_bfloat16* bsrc = has_t2 ? d.t2 + base * d.cs2 + d.co2 + it.tx * 8 : nullptr;
     auto issue = [&](int k) {
       const int64_t q = r0 + k * stride;
       if (q < d.rows) {
         const int64_t r = d.rows - 1 - q;               // descending (see stats_kernel)
-        pf.issue(k % kPf, 0, zsrc + r * d.C);
+        pf.issue(k % kPf, 0, zsrc + r * d.zcs);
         pf.issue(k % kPf, 1, asrc + r * d.cs1);
         if (has_t2) pf.issue(k % kPf, 2, bsrc + r * d.cs2);
       }
@@ -423,22 +435,19 @@ __global__ void __launch_bounds__(256, 2) bwd_reduce_kernel(const Dev d) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) acc[1][i] = (acc[1][i] - mu.v[i] * acc[0][i]) * rs.v[i];   // sum g * (x - mu) * rstd
   }
-  if (d.dslope != nullptr) {
-    for (int o = 16; o > 0; o >>= 1) dsl += __shfl_xor_sync(0xffffffffu, dsl, o);
-    if ((threadIdx.x & 31) == 0 && dsl != 0.f) atomicAdd(d.dslope, dsl);
-  }
-  block_reduce_channels<2>(it, acc, smem_f, d.sums + (d.per_sample ? (int64_t)s * 2 * d.C : 0), d.C);
+  block_reduce_channels<2>(it, acc, smem_f, d.sums + (d.per_sample ? (int64_t)s * 2 * d.C : 0), d.C, dsl, d.dslope);
 }
 
 template <int ACT>
 __global__ void __launch_bounds__(256, 2) bwd_apply_kernel(const Dev d) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
-  float* smem_f = reinterpret_cast<float*>(smem_raw + PfRing::bytes(d.t2 != nullptr ? 3 : 2));
+  const int nt_ring = (d.t2 != nullptr ? 3 : 2) + (d.ex != nullptr ? 1 : 0);
+  float* smem_f = reinterpret_cast<float*>(smem_raw + PfRing::bytes(nt_ring));
   RowIter it(d.C);
   if (blockIdx.x == 0 && blockIdx.y == 0 && d.dgamma != nullptr && d.ka == nullptr && d.gc_gs == 0) {
     for (int c = threadIdx.x; c < d.C; c += blockDim.x) {
-      d.dbeta[c] = d.sums[c];
-      d.dgamma[c] = d.sums[d.C + c];
+      d.dbeta[c] = (float)d.sums[c];
+      d.dgamma[c] = (float)d.sums[d.C + c];
     }
   }
   float csum[1][8];
@@ -447,18 +456,21 @@ __global__ void __launch_bounds__(256, 2) bwd_apply_kernel(const Dev d) {
   const int64_t base = (int64_t)blockIdx.y * d.rows;
   const int64_t stride = (int64_t)gridDim.x * it.rpp;
   const bool has_t2 = d.t2 != nullptr;
-  PfRing pf(smem_raw, has_t2 ? 3 : 2);
+  const bool has_ex = d.ex != nullptr;
+  PfRing pf(smem_raw, nt_ring);
   const int64_t q0 = (int64_t)blockIdx.x * it.rpp + it.ty;              // ascending row order (see fwd_kernel)
-  const __nv_bfloat16* zsrc = d.z + it.tx * 8;
+  const __nv_bfloat16* zsrc = d.z + d.zco + it.tx * 8;
   const __nv_bfloat16* asrc = d.t1 + d.co1 + it.tx * 8;
   const __nv_bfloat16* bsrc = has_t2 ? d.t2 + d.co2 + it.tx * 8 : nullptr;
+  const __nv_bfloat16* esrc = has_ex ? d.ex + d.exco + it.tx * 8 : nullptr;
   auto issue = [&](int k) {
     const int64_t q = q0 + k * stride;
     if (q < d.rows) {
       const int64_t r = base + q;
-      pf.issue(k % kPf, 0, zsrc + r * d.C);
+      pf.issue(k % kPf, 0, zsrc + r * d.zcs);
       pf.issue(k % kPf, 1, asrc + r * d.cs1);
       if (has_t2) pf.issue(k % kPf, 2, bsrc + r * d.cs2);
+      if (has_ex) pf.issue(k % kPf, nt_ring - 1, esrc + r * d.excs);
     }
     PfRing::commit();
   };
@@ -471,15 +483,15 @@ __global__ void __launch_bounds__(256, 2) bwd_apply_kernel(const Dev d) {
   float* comb = smem_f + (d.dz_colsum != nullptr ? it.rpp * d.C : 0);
   if (d.gc_gs > 0) {
     const int s = blockIdx.y;
-    const float* sm = d.sums + (int64_t)s * 2 * d.C;
+    const double* sm = d.sums + (int64_t)s * 2 * d.C;
     const float inv = 1.f / ((float)d.rows * (float)d.gc_gs);
     for (int c = threadIdx.x; c < d.C; c += blockDim.x) {
       const int g0 = c / d.gc_gs * d.gc_gs;
       float a = 0.f, b = 0.f;
       for (int j = 0; j < d.gc_gs; ++j) {
         const float ga = d.gamma ? d.gamma[g0 + j] : 1.f;
-        a += ga * sm[g0 + j];
-        b += ga * sm[d.C + g0 + j];
+        a += ga * (float)sm[g0 + j];
+        b += ga * (float)sm[d.C + g0 + j];
       }
       const float r = d.rstd[s * d.C + c];
       comb[c] = r * a * inv;
@@ -489,8 +501,8 @@ __global__ void __launch_bounds__(256, 2) bwd_apply_kernel(const Dev d) {
       for (int c = threadIdx.x; c < d.C; c += blockDim.x) {
         float a = 0.f, b = 0.f;
         for (int q = 0; q < d.gc_ns; ++q) {
-          a += d.sums[(int64_t)q * 2 * d.C + d.C + c];
-          b += d.sums[(int64_t)q * 2 * d.C + c];
+          a += (float)d.sums[(int64_t)q * 2 * d.C + d.C + c];
+          b += (float)d.sums[(int64_t)q * 2 * d.C + c];
         }
         if (d.gc_acc) { d.dgamma[c] += a; d.dbeta[c] += b; } else { d.dgamma[c] = a; d.dbeta[c] = b; }
       }
@@ -518,8 +530,10 @@ __global__ void __launch_bounds__(256, 2) bwd_apply_kernel(const Dev d) {
 #pragma unroll
       for (int i = 0; i < 8; ++i) k0.v[i] = ga.v[i] * rs.v[i];
     } else {
-      const float* sm = d.sums + (d.per_sample ? (int64_t)s * 2 * d.C : 0);
-      const F8 s0 = load8f(sm + it.tx * 8), s1 = load8f(sm + d.C + it.tx * 8);
+      const double* sm = d.sums + (d.per_sample ? (int64_t)s * 2 * d.C : 0);
+      F8 s0, s1;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { s0.v[i] = (float)sm[it.tx * 8 + i]; s1.v[i] = (float)sm[d.C + it.tx * 8 + i]; }
       const float inv = 1.f / (float)d.rows;
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
@@ -557,14 +571,21 @@ __global__ void __launch_bounds__(256, 2) bwd_apply_kernel(const Dev d) {
       }
       o.v[i] = k0.v[i] * g - kA.v[i] - x.v[i] * kB.v[i];
       dr.v[i] = av.v[i] + bv.v[i];
-      csum[0][i] += o.v[i];
     }
+    if (has_ex) {                       // d(out)/d(x) = identity of a skip connection: its gradient joins dz here
+      const F8 e = unpack8(pf.get(k % kPf, nt_ring - 1));
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o.v[i] += e.v[i];
+    }
+    __nv_bfloat16* dzp = d.dz + r * d.dzcs + d.dzco + it.tx * 8;
     if (d.dz_acc) {
-      const F8 old = load8(d.dz + r * d.C + it.tx * 8);
+      const F8 old = load8(dzp);
 #pragma unroll
       for (int i = 0; i < 8; ++i) o.v[i] += old.v[i];
     }
-    store8(d.dz + r * d.C + it.tx * 8, o);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) csum[0][i] += o.v[i];     // column sums of the FINAL gradient (after extra / accumulation)
+    store8(dzp, o);
     if (d.res) {
       __nv_bfloat16* p = d.res + r * d.csr + d.cor + it.tx * 8;
       if (d.res_acc) {
@@ -576,26 +597,27 @@ __global__ void __launch_bounds__(256, 2) bwd_apply_kernel(const Dev d) {
     }
   }
   }   // it.active
+  // the bias gradient sums over the samples as well: one reduction over the whole grid
   if (d.dz_colsum != nullptr) block_reduce_channels<1>(it, csum, smem_f, d.dz_colsum, d.C);
 }
 
 // GroupNorm / per-sample affine backward constants.  With S0 = sum g, S1 = sum g*zhat per (sample, channel):
 //   ka[s,c] = rstd[s,c] * sum_{c' in group(c)} gamma[c'] S0[s,c'] / (rows * group_size),  kb likewise with S1;
 //   dgamma[c] = sum_s S1[s,c], dbeta[c] = sum_s S0[s,c].
-__global__ void group_combine_kernel(const float* __restrict__ sums, const float* __restrict__ gamma,
+__global__ void group_combine_kernel(const double* __restrict__ sums, const float* __restrict__ gamma,
                                      const float* __restrict__ rstd, float* __restrict__ ka, float* __restrict__ kb,
                                      float* __restrict__ dgamma, float* __restrict__ dbeta, int64_t rows, int C,
                                      int nsamples, int group_size, int accumulate) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < nsamples * C) {
     const int s = i / C, c = i % C;
-    const float* sm = sums + (int64_t)s * 2 * C;
+    const double* sm = sums + (int64_t)s * 2 * C;
     const int g0 = c / group_size * group_size;
     float a = 0.f, b = 0.f;
     for (int j = 0; j < group_size; ++j) {
       const float ga = gamma ? gamma[g0 + j] : 1.f;
-      a += ga * sm[g0 + j];
-      b += ga * sm[C + g0 + j];
+      a += ga * (float)sm[g0 + j];
+      b += ga * (float)sm[C + g0 + j];
     }
     const float inv = 1.f / ((float)rows * (float)group_size);
     ka[i] = rstd[i] * a * inv;
@@ -604,8 +626,8 @@ __global__ void group_combine_kernel(const float* __restrict__ sums, const float
   if (i < C && dgamma != nullptr) {
     float a = 0.f, b = 0.f;
     for (int s = 0; s < nsamples; ++s) {
-      a += sums[(int64_t)s * 2 * C + C + i];
-      b += sums[(int64_t)s * 2 * C + i];
+      a += (float)sums[(int64_t)s * 2 * C + C + i];
+      b += (float)sums[(int64_t)s * 2 * C + i];
     }
     if (accumulate) { dgamma[i] += a; dbeta[i] += b; } else { dgamma[i] = a; dbeta[i] = b; }
   }
@@ -632,7 +654,7 @@ __global__ void __launch_bounds__(256) add_slice_kernel(const __nv_bfloat16* __r
 
 // out[c] = sum_r x[r, coff + c]  (bias gradient), fp32, caller-zeroed
 __global__ void __launch_bounds__(256) colsum_kernel(const __nv_bfloat16* __restrict__ x, int cs, int co,
-                                                     float* __restrict__ out, int64_t rows, int C) {
+                                                     double* __restrict__ out, int64_t rows, int C) {
   extern __shared__ float smem_f[];
   RowIter it(C);
   float acc[1][8];
@@ -657,7 +679,7 @@ static int row_blocks(int64_t rows, int C, int nsamples) {
 
 static int32_t to_dev(const petsyn_normact_desc* d, Dev* o) {
   PETSYN_REQUIRE(d != nullptr, "null descriptor");
-  PETSYN_REQUIRE(d->z != nullptr && d->rows > 0 && d->nsamples >= 1, "bad tensor");
+  PETSYN_REQUIRE(d->z != nullptr && d->rows > 0 && d->nsamples >= 1 && d->nsamples <= kDetRows, "bad tensor");
   PETSYN_REQUIRE(d->c % 8 == 0 && d->c >= 8 && d->c <= 2048, "channels must be a multiple of 8 in [8, 2048]");
   PETSYN_REQUIRE((d->t1_cstride | d->t1_coff | d->t2_cstride | d->t2_coff | d->res_cstride | d->res_coff) % 8 == 0,
                  "channel pitches/offsets must be multiples of 8");
@@ -669,23 +691,27 @@ static int32_t to_dev(const petsyn_normact_desc* d, Dev* o) {
   o->slope = d->slope;
   o->res = reinterpret_cast<__nv_bfloat16*>(d->res); o->csr = d->res_cstride; o->cor = d->res_coff;
   o->res_acc = d->res_accumulate;
-  o->sums = d->sums;
+  o->sums = reinterpret_cast<double*>(d->sums);
   o->dz = reinterpret_cast<__nv_bfloat16*>(d->dz);
   o->dgamma = d->dgamma; o->dbeta = d->dbeta;
-  o->slope_dev = d->slope_dev; o->dslope = d->dslope;
+  o->slope_dev = d->slope_dev; o->dslope = reinterpret_cast<double*>(d->dslope);
   o->ka = o->kb = nullptr;
   o->dz_acc = d->dz_accumulate;
-  o->dz_colsum = d->dz_colsum;
-  o->st1 = d->t1_stats; o->st1_c = d->t1_stats_c; o->st1_off = d->t1_stats_coff;
-  o->st2 = d->t2_stats; o->st2_c = d->t2_stats_c; o->st2_off = d->t2_stats_coff;
-  o->fin_sums = d->fin_sums; o->fin_gamma = d->fin_gamma; o->fin_beta = d->fin_beta;
+  o->dz_colsum = reinterpret_cast<double*>(d->dz_colsum);
+  o->st1 = reinterpret_cast<double*>(d->t1_stats); o->st1_c = d->t1_stats_c; o->st1_off = d->t1_stats_coff;
+  o->st2 = reinterpret_cast<double*>(d->t2_stats); o->st2_c = d->t2_stats_c; o->st2_off = d->t2_stats_coff;
+  o->fin_sums = reinterpret_cast<const double*>(d->fin_sums); o->fin_gamma = d->fin_gamma; o->fin_beta = d->fin_beta;
   o->fin_gs = d->fin_group_size > 1 ? d->fin_group_size : 1; o->fin_eps = d->fin_eps;
   o->gc_gs = o->gc_ns = o->gc_acc = 0;
+  o->zcs = d->z_cstride > 0 ? d->z_cstride : d->c; o->zco = d->z_coff;
+  o->dzcs = d->dz_cstride > 0 ? d->dz_cstride : d->c; o->dzco = d->dz_coff;
+  o->ex = reinterpret_cast<const __nv_bfloat16*>(d->extra); o->excs = d->extra_cstride; o->exco = d->extra_coff;
+  PETSYN_REQUIRE((d->z_cstride | d->z_coff | d->dz_cstride | d->dz_coff | d->extra_cstride | d->extra_coff) % 8 == 0,
+                 "channel pitches/offsets must be multiples of 8");
+  PETSYN_REQUIRE(d->extra == nullptr || d->extra_cstride >= d->c, "extra addend needs its channel pitch");
   PETSYN_REQUIRE(d->fin_sums == nullptr || (d->scale && d->shift && d->mean && d->rstd && d->per_sample_stats &&
                                             d->c % o->fin_gs == 0),
                  "fused finalize needs per-sample statistics and the scale / shift / mean / rstd outputs");
-  PETSYN_REQUIRE(!(d->t2_stats && !d->t2), "t2_stats without a second destination");
-  PETSYN_REQUIRE(!(d->dz_colsum && d->dz_accumulate), "dz_colsum cannot be combined with dz_accumulate");
   return PETSYN_OK;
 }
 
@@ -720,17 +746,24 @@ using namespace petsyn::nx;
 
 extern "C" {
 
-int32_t petsyn_norm_stats(const void* z, float* sums, int64_t rows, int32_t c, int32_t nsamples, void* stream) {
-  PETSYN_REQUIRE(z && sums && rows > 0 && nsamples >= 1, "bad argument");
+int32_t petsyn_norm_stats(const void* z, double* sums, int64_t rows, int32_t c, int32_t nsamples, void* stream) {
+  return petsyn_norm_stats_slice(z, c, 0, sums, rows, c, nsamples, stream);
+}
+
+int32_t petsyn_norm_stats_slice(const void* z, int32_t cstride, int32_t coff, double* sums, int64_t rows, int32_t c,
+                                int32_t nsamples, void* stream) {
+  PETSYN_REQUIRE(z && sums && rows > 0 && nsamples >= 1 && nsamples <= kDetRows, "bad argument");
+  PETSYN_REQUIRE(cstride >= c && cstride % 8 == 0 && coff % 8 == 0 && coff + c <= cstride, "bad channel slice");
   PETSYN_REQUIRE(c % 8 == 0 && c >= 8 && c <= 2048, "channels must be a multiple of 8 in [8, 2048]");
   const int rpp = 256 / (c / 8);
   const size_t smem = PfRing::bytes(1) + (size_t)rpp * 2 * c * sizeof(float);
   dim3 grid((unsigned)row_blocks(rows, c, nsamples), (unsigned)nsamples);
-  stats_kernel<<<grid, 256, smem, as_stream(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(z), sums, rows, c);
+  stats_kernel<<<grid, 256, smem, as_stream(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(z), sums, rows, c, cstride,
+                                                       coff);
   return check_launch("stats_kernel");
 }
 
-int32_t petsyn_norm_finalize(const float* sums, const float* gamma, const float* beta, float* running_mean,
+int32_t petsyn_norm_finalize(const double* sums, const float* gamma, const float* beta, float* running_mean,
                              float* running_var, float* scale, float* shift, float* save_mean, float* save_rstd,
                              int64_t rows, int32_t c, int32_t nsamples, int32_t group_size, float eps, float momentum,
                              int32_t training, void* stream) {
@@ -767,7 +800,7 @@ int32_t petsyn_normact_bwd(const petsyn_normact_desc* desc, void* stream) {
   dim3 grid((unsigned)row_blocks(d.rows, d.C, desc->nsamples), (unsigned)desc->nsamples);
   if (d.mean != nullptr) {
     const int nst = d.per_sample ? desc->nsamples : 1;
-    if (!desc->sums_prezeroed) PETSYN_CHECK_CUDA(cudaMemsetAsync(d.sums, 0, (size_t)nst * 2 * d.C * sizeof(float), st));
+    if (!desc->sums_prezeroed) PETSYN_CHECK_CUDA(cudaMemsetAsync(d.sums, 0, (size_t)nst * 2 * d.C * sizeof(double), st));
     const int rpp = 256 / (d.C / 8);
     const size_t smem = PfRing::bytes(d.t2 ? 3 : 2) + (size_t)rpp * 2 * d.C * sizeof(float);
     PETSYN_NX_DISPATCH(bwd_reduce_kernel, grid, smem, st, d);
@@ -778,7 +811,7 @@ int32_t petsyn_normact_bwd(const petsyn_normact_desc* desc, void* stream) {
       d.gc_gs = gs; d.gc_ns = nst; d.gc_acc = desc->affine_accumulate;      // combined inside bwd_apply_kernel's prologue
     } else if (d.per_sample && (gs > 1 || d.gamma != nullptr)) {
       // the sums workspace holds [S0|S1] for every sample followed by ka and kb: 4 * nsamples * C floats
-      float* ka = d.sums + (size_t)nst * 2 * d.C;
+      float* ka = reinterpret_cast<float*>(d.sums + (size_t)nst * 2 * d.C);
       float* kb = ka + (size_t)nst * d.C;
       const int total = nst * d.C;
       group_combine_kernel<<<(total + 127) / 128, 128, 0, st>>>(d.sums, d.gamma, d.rstd, ka, kb, d.dgamma, d.dbeta, d.rows,
@@ -790,7 +823,8 @@ int32_t petsyn_normact_bwd(const petsyn_normact_desc* desc, void* stream) {
     }
   }
   {
-    const size_t apply_smem = PfRing::bytes(d.t2 ? 3 : 2) + (d.dz_colsum ? (size_t)(256 / (d.C / 8)) * d.C * sizeof(float) : 0) +
+    const size_t apply_smem = PfRing::bytes((d.t2 ? 3 : 2) + (d.ex ? 1 : 0)) +
+                              (d.dz_colsum ? (size_t)(256 / (d.C / 8)) * d.C * sizeof(float) : 0) +
                               (d.gc_gs > 0 ? (size_t)2 * d.C * sizeof(float) : 0);
     PETSYN_NX_DISPATCH(bwd_apply_kernel, grid, apply_smem, st, d);
   }
@@ -808,11 +842,11 @@ int32_t petsyn_add_slice(const void* src, int32_t src_cstride, int32_t src_coff,
   return check_launch("add_slice_kernel");
 }
 
-int32_t petsyn_colsum(const void* x, int32_t cstride, int32_t coff, float* out, int64_t rows, int32_t c, void* stream) {
+int32_t petsyn_colsum(const void* x, int32_t cstride, int32_t coff, double* out, int64_t rows, int32_t c, void* stream) {
   PETSYN_REQUIRE(x && out && rows > 0, "bad argument");
   PETSYN_REQUIRE(c % 8 == 0 && c >= 8 && c <= 2048 && (cstride | coff) % 8 == 0, "channels must be a multiple of 8");
   cudaStream_t st = as_stream(stream);
-  PETSYN_CHECK_CUDA(cudaMemsetAsync(out, 0, (size_t)c * sizeof(float), st));
+  PETSYN_CHECK_CUDA(cudaMemsetAsync(out, 0, (size_t)c * sizeof(double), st));
   const int rpp = 256 / (c / 8);
   colsum_kernel<<<row_blocks(rows, c, 1), 256, (size_t)rpp * c * sizeof(float), st>>>(
       reinterpret_cast<const __nv_bfloat16*>(x), cstride, coff, out, rows, c);

@@ -566,7 +566,9 @@ constexpr int kWgMaxRing = 8;
 struct alignas(64) SlabWgradParams {
   CUtensorMap x_map;    // dims (16 ch, W, atoms, H, D*N); box (16, 16, atoms, 18, 1); 32B swizzle -> smem [h][atom][w][16]
   CUtensorMap g_map;    // dy co-atom view: dims (16 ch, W, H, D*N); box (16, 18, 16, 1); 32B swizzle -> smem [h][w 18][16]
-  float* scratch;       // fp32 [ci_groups][co_atoms][3 (c)][48 (i, co)][ncols = 3 (b) * atoms * 16]
+  float* scratch;       // fp32 [persistent CTA = gridDim.x][ci_groups][co_atoms][3 (c)][48 (i, co)][ncols = 3 (b) * atoms * 16]:
+                        // every CTA STORES its accumulators into its own image; the unpack kernel adds the images in CTA order
+  int64_t image_floats; // floats of one CTA's image (ci_groups * co_atoms * nacc * 48 * ncols)
   int32_t atoms, co_atoms;   // atoms = 16-channel atoms of x PER channel group (grid.z = group), <= 3
   int32_t W, H, D, batch;
   int32_t tiles_w, tiles_h, dchunk, nchunks, items;
@@ -585,9 +587,9 @@ __host__ __device__ inline int slab_wgrad_smem_bytes(int xslab_bytes, int gslab_
   return (ring > stg ? ring : stg) + 1024 + 1024;
 }
 
-__device__ __forceinline__ void bulk_reduce_add_f32(float* gdst, const void* ssrc, uint32_t bytes) {
-  asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;" ::"l"(gdst),
-               "r"(ptx::smem_u32(ssrc)), "r"(bytes)
+__device__ __forceinline__ void bulk_store(float* gdst, const void* ssrc, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(ptx::smem_u32(ssrc)),
+               "r"(bytes)
                : "memory");
 }
 
@@ -757,7 +759,8 @@ __global__ void __launch_bounds__(192) slab_wgrad_kernel(const __grid_constant__
       }
       named_bar_sync(1, 128);
       if (warp == 4 && (tid & 31) == 0) {
-        bulk_reduce_add_f32(p.scratch + ((size_t)((cig * p.co_atoms + coa) * nacc + c) * 48) * ncols, stg, uint32_t(48 * ncols * 4));
+        bulk_store(p.scratch + (size_t)blockIdx.x * p.image_floats + ((size_t)((cig * p.co_atoms + coa) * nacc + c) * 48) * ncols,
+                   stg, uint32_t(48 * ncols * 4));
         ptx::tma_store_commit();
         ptx::tma_store_wait_read();
       }
@@ -770,24 +773,41 @@ __global__ void __launch_bounds__(192) slab_wgrad_kernel(const __grid_constant__
   if (warp == 1) ptx::tmem_dealloc(tmem_base, uint32_t(p.tmem_cols));
 }
 
-// scratch [ci_group][co_atoms][nacc (c = kd)][48 = (2 - kw) * 16 + co % 16][(kh * apg + q) * 16 + ci % 16], ci atom = group * apg + q
+// scratch [cta][ci_group][co_atoms][nacc (c = kd)][48 = (2 - kw) * 16 + co % 16][(kh * apg + q) * 16 + ci % 16], ci atom = group * apg + q
 //   -> dw[co][ci][kd][kh][kw]            (k3 = 27; for 1x1x1 convs k3 = 1, nacc = 1 and the only tap sits in row block 0)
+// One thread per element of ONE image (coalesced over the image's own layout); the `nimages` per-CTA images are added in CTA
+// order, so the weight gradient is reproducible from run to run (no atomics, no memset of the scratch).
 __global__ void __launch_bounds__(256) slab_wgrad_unpack_kernel(const float* __restrict__ scratch, float* __restrict__ dw,
-                                                                int cout, int cin, int apg, int k3, int accumulate) {
-  const int total = cout * cin * k3;
+                                                                int cout, int cin, int apg, int k3, int accumulate,
+                                                                int nimages, int64_t image_floats) {
   const int nacc = k3 == 27 ? 3 : 1;
   const int ncols = nacc * apg * 16;
   const int co_atoms = cout >> 4;
-  for (int i = blockIdx.x * 256 + threadIdx.x; i < total; i += gridDim.x * 256) {
-    const int k = i % k3;
-    const int ci = (i / k3) % cin;
-    const int co = i / (k3 * cin);
-    const int kw = k % 3, kh = (k / 3) % 3, kd = k / 9;
-    const int atom = ci >> 4, grp = atom / apg, q = atom - grp * apg;
-    const int rowblk = k3 == 27 ? 2 - kw : 0;
-    const float v = scratch[((size_t)((grp * co_atoms + (co >> 4)) * nacc + kd) * 48 + rowblk * 16 + (co & 15)) * ncols +
-                            (kh * apg + q) * 16 + (ci & 15)];
-    dw[i] = accumulate ? dw[i] + v : v;
+  for (int64_t j = blockIdx.x * 256 + threadIdx.x; j < image_floats; j += (int64_t)gridDim.x * 256) {
+    int64_t t = j;
+    const int col = (int)(t % ncols); t /= ncols;
+    const int row = (int)(t % 48); t /= 48;
+    const int kd = (int)(t % nacc); t /= nacc;
+    const int coa = (int)(t % co_atoms); t /= co_atoms;
+    const int grp = (int)t;
+    const int kh = col / (apg * 16), q = (col / 16) % apg, cil = col & 15;
+    const int rowblk = row >> 4, col_ = row & 15;
+    if (k3 != 27 && rowblk != 0) continue;                 // 1x1x1: only row block 0 holds the tap
+    const int kw = k3 == 27 ? 2 - rowblk : 0;
+    const int ci = (grp * apg + q) * 16 + cil, co = coa * 16 + col_;
+    if (ci >= cin) continue;                                // zero-filled atoms of a short last channel group
+    float v0 = 0.f, v1 = 0.f, v2 = 0.f, v3 = 0.f;
+    int i = 0;
+    for (; i + 3 < nimages; i += 4) {
+      v0 += __ldg(scratch + (int64_t)i * image_floats + j);
+      v1 += __ldg(scratch + (int64_t)(i + 1) * image_floats + j);
+      v2 += __ldg(scratch + (int64_t)(i + 2) * image_floats + j);
+      v3 += __ldg(scratch + (int64_t)(i + 3) * image_floats + j);
+    }
+    for (; i < nimages; ++i) v0 += __ldg(scratch + (int64_t)i * image_floats + j);
+    const float v = (v0 + v1) + (v2 + v3);
+    const int64_t o = ((int64_t)co * cin + ci) * k3 + (k3 == 27 ? (kd * 3 + kh) * 3 + kw : 0);
+    dw[o] = accumulate ? dw[o] + v : v;
   }
 }
 

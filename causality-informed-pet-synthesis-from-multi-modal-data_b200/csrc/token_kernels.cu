@@ -8,6 +8,7 @@
 #include <algorithm>
 
 #include "common.h"
+#include "det_reduce.cuh"
 
 namespace petsyn {
 namespace tk {
@@ -147,10 +148,8 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const __nv_bfloat16*
                                                             const float* __restrict__ rstd,
                                                             __nv_bfloat16* __restrict__ dx, float* __restrict__ dgamma,
                                                             float* __restrict__ dbeta, int64_t rows, int C,
-                                                            int accumulate) {
-  extern __shared__ float sm[];   // [2][C] block partials of dgamma / dbeta
-  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sm[i] = 0.f;
-  __syncthreads();
+                                                            int accumulate, const DetWs ws) {
+  extern __shared__ __align__(16) float sm[];   // [warps][2][C] per-warp partials of dgamma / dbeta (>= 1024 floats)
   const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
   const int per = C / 32;
   float pg[32], pb[32];
@@ -181,15 +180,26 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const __nv_bfloat16*
       dx[r * C + c] = __float2bfloat16(v);
     }
   }
-  for (int j = 0; j < per; ++j) {
-    atomicAdd(&sm[j * 32 + lane], pg[j]);
-    atomicAdd(&sm[C + j * 32 + lane], pb[j]);
+  {
+    float* mine = sm + (threadIdx.x >> 5) * 2 * C;
+    for (int j = 0; j < per; ++j) {
+      mine[j * 32 + lane] = pg[j];
+      mine[C + j * 32 + lane] = pb[j];
+    }
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < C; i += blockDim.x) {
-    atomicAdd(dgamma + i, sm[i]);
-    atomicAdd(dbeta + i, sm[C + i]);
-  }
+  // warps in warp order, CTAs in slot order (det_reduce.cuh): reproducible dgamma / dbeta
+  det_cta_reduce(
+      ws, 2 * C, sm,
+      [&](int e) {
+        float s = 0.f;
+        for (int w = 0; w < wpb; ++w) s += sm[w * 2 * C + e];
+        return s;
+      },
+      [&](int e, float t, bool atomic) {
+        float* p = e < C ? dgamma + e : dbeta + (e - C);
+        if (atomic) atomicAdd(p, t); else *p += t;
+      });
 }
 
 // ------------------------------------------------------------------------------------------------ GEGLU
@@ -253,7 +263,8 @@ __global__ void __launch_bounds__(256) add_sample_bias_kernel(__nv_bfloat16* __r
 }
 // dbias[n, c] = sum over the sample's rows of dt[., c]
 __global__ void __launch_bounds__(256) sample_colsum_kernel(const __nv_bfloat16* __restrict__ dt, float* __restrict__ out,
-                                                            int64_t rows_per_sample, int C) {
+                                                            int64_t rows_per_sample, int C, const DetWs ws) {
+  __shared__ __align__(16) float part[1024];
   const int n = blockIdx.y;
   const int c = threadIdx.x % C;
   const int rl = threadIdx.x / C, rpp = blockDim.x / C;
@@ -261,7 +272,18 @@ __global__ void __launch_bounds__(256) sample_colsum_kernel(const __nv_bfloat16*
   if (rl < rpp)
     for (int64_t r = (int64_t)blockIdx.x * rpp + rl; r < rows_per_sample; r += (int64_t)gridDim.x * rpp)
       acc += bf(dt[((int64_t)n * rows_per_sample + r) * C + c]);
-  if (rl < rpp) atomicAdd(out + n * C + c, acc);
+  part[threadIdx.x] = rl < rpp ? acc : 0.f;
+  __syncthreads();
+  det_cta_reduce(
+      ws, C, part,
+      [&](int e) {
+        float s = 0.f;
+        for (int r = 0; r < rpp; ++r) s += part[r * C + e];
+        return s;
+      },
+      [&](int e, float t, bool atomic) {
+        if (atomic) atomicAdd(out + n * C + e, t); else out[n * C + e] += t;
+      });
 }
 // gradients of the tiny linears: dbo = sum_n dbias; dWo = sum_n dbias (x) v; dv = Wo^T dbias; dWv = sum_n dv (x) ctx
 __global__ void __launch_bounds__(128) covariate_bias_bwd_kernel(const float* __restrict__ ctx, const float* __restrict__ wo,
@@ -348,8 +370,16 @@ int32_t petsyn_layernorm_bwd(const void* x, const void* dy, const float* gamma, 
   cudaStream_t st = as_stream(stream);
   PETSYN_CHECK_CUDA(cudaMemsetAsync(dgamma, 0, c * sizeof(float), st));
   PETSYN_CHECK_CUDA(cudaMemsetAsync(dbeta, 0, c * sizeof(float), st));
-  layernorm_bwd_kernel<<<blocks_for(rows, 8, 148 * 4), 256, 2 * c * sizeof(float), st>>>(
-      CBFP(x), CBFP(dy), gamma, mean, rstd, BFP(dx), dgamma, dbeta, rows, c, accumulate_dx);
+  DetWs ws;
+  {
+    int32_t rcw = det_workspace(&ws);
+    if (rcw) return rcw;
+  }
+  const size_t ln_smem = std::max<size_t>((size_t)8 * 2 * c, 1024) * sizeof(float);
+  if (ln_smem > 48 * 1024)
+    PETSYN_CHECK_CUDA(cudaFuncSetAttribute(layernorm_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ln_smem));
+  layernorm_bwd_kernel<<<blocks_for(rows, 8, 148 * 4), 256, ln_smem, st>>>(
+      CBFP(x), CBFP(dy), gamma, mean, rstd, BFP(dx), dgamma, dbeta, rows, c, accumulate_dx, ws);
   return check_launch("layernorm_bwd_kernel");
 }
 
@@ -386,7 +416,12 @@ int32_t petsyn_covariate_bias_bwd(const float* ctx, const float* wo, const float
   cudaStream_t st = as_stream(stream);
   PETSYN_CHECK_CUDA(cudaMemsetAsync(dbias, 0, (size_t)n * c * sizeof(float), st));
   dim3 grid((unsigned)std::min<int64_t>(64, (rows_per_sample + 1) / 2), (unsigned)n);
-  sample_colsum_kernel<<<grid, 256, 0, st>>>(CBFP(dtokens), dbias, rows_per_sample, c);
+  DetWs ws;
+  {
+    int32_t rcw = det_workspace(&ws);
+    if (rcw) return rcw;
+  }
+  sample_colsum_kernel<<<grid, 256, 0, st>>>(CBFP(dtokens), dbias, rows_per_sample, c, ws);
   int32_t rc = check_launch("sample_colsum_kernel");
   if (rc) return rc;
   covariate_bias_bwd_kernel<<<c, 128, (size_t)n * sizeof(float), st>>>(ctx, wo, vbuf, dbias, dwv, dwo, dbo, n, cctx, c);

@@ -96,9 +96,12 @@ class ConvOp(Op):
     def __init__(self, x: Sl, weight: torch.nn.Parameter, bias: Optional[torch.nn.Parameter], ksize: int, stride: int,
                  pad: int, op: int = ops.OP_CONV, act: int = ops.ACT_NONE, slope: float = 0.2, y_fp32: bool = False,
                  use_bias: bool = True, need_dx: bool = True, need_dw: bool = True, name: str = "",
-                 out: Optional["Sl"] = None):
+                 out: Optional["Sl"] = None, dy_from: Optional["Sl"] = None):
         self.x, self.weight, self.bias = x, weight, bias
         self.out_sl = out                      # write into a channel slice of an existing buffer instead of an own one
+        # backward reads the gradient w.r.t. the output from THIS slice instead of z.g: the conv feeds a residual sum whose
+        # result lives there (d(z + res) / dz = identity), so the sum needs no backward pass and z.g is never allocated
+        self.dy_from = dy_from
         self.name = name
         self.opcode = op
         b = x.buf
@@ -117,8 +120,11 @@ class ConvOp(Op):
         self.need_dx, self.need_dw = need_dx, need_dw
         ykw = {}
         if out is not None:
-            assert out.c == self.cout and not y_fp32
+            assert out.c == self.cout and not y_fp32 and dy_from is None
             ykw = dict(y_cstride=out.buf.c, y_coff=out.off, dy_cstride=out.buf.c, dy_coff=out.off)
+        if dy_from is not None:
+            assert dy_from.c == self.cout and not y_fp32
+            ykw = dict(dy_cstride=dy_from.buf.c, dy_coff=dy_from.off)
         self.plan = ops.ConvPlan(op, b.n, b.d, b.h, b.w, self.cin, self.cout, ksize, stride, pad,
                                  x_cstride=b.c, x_coff=x.off, dx_cstride=b.c, dx_coff=x.off, act=act, slope=slope,
                                  y_fp32=y_fp32, **ykw)
@@ -141,7 +147,7 @@ class ConvOp(Op):
         self.bias_stage = None
         if self.use_bias and self.cout != cout_w:
             self.bias_stage = torch.zeros(self.cout, dtype=torch.float32, device=dev)
-        self.dbias_stage = torch.zeros(self.cout, dtype=torch.float32, device=dev) if bias is not None else None
+        self.dbias_stage = torch.zeros(self.cout, dtype=torch.float64, device=dev) if bias is not None else None
         self.tape_zeroes_dbias = False                 # Tape.finalize moved `dbias_stage` into its per-backward zero arena
         # the data gradient runs on a side stream concurrently with the weight gradient (a fork/join that CUDA-graph
         # capture keeps as a branch): layers whose kernels cannot fill 148 SMs (deep levels, transformer linears) overlap
@@ -151,6 +157,7 @@ class ConvOp(Op):
         self.colsum_done = False  # set by the NormActOp consuming z when it already summed dz over the rows (bias gradient)
         self.acc_dw = False      # add into grad_w / grad_b instead of overwriting (several backward calls per step)
         self._ver = None
+        self.wg_scratch: Optional[torch.Tensor] = None  # Tape.finalize: ONE weight-gradient scratch for all convs of a tape
         self.grad_w: Optional[torch.Tensor] = None     # set by the owner: where dW / dbias go
         self.grad_b: Optional[torch.Tensor] = None
         self.flops = self.plan.flops_algorithmic
@@ -204,7 +211,17 @@ class ConvOp(Op):
             return self.out_sl.buf.t
         return self.zf if self.y_fp32 else self.z.t
 
+    def dy_slice(self) -> Optional["Sl"]:
+        """Where backward reads d(loss)/d(output) from, as a slice (None for the fp32 heads)."""
+        if self.dy_from is not None:
+            return self.dy_from
+        if self.out_sl is not None:
+            return self.out_sl
+        return None if self.y_fp32 else self.z.sl()
+
     def dout(self) -> torch.Tensor:
+        if self.dy_from is not None:
+            return self.dy_from.buf.g
         if self.out_sl is not None:
             return self.out_sl.buf.g
         return self.zg if self.y_fp32 else self.z.g
@@ -235,7 +252,7 @@ class ConvOp(Op):
                 self._bwd_dx(dz)
         if self.need_dw:
             if self.padded:
-                self.plan.wgrad(self.x.buf.t, dz, self.dw_stage)
+                self.plan.wgrad(self.x.buf.t, dz, self.dw_stage, scratch=self.wg_scratch)
                 part = self.dw_stage[:self.cin_w, :self.cout_w] if self.opcode == ops.OP_CONVT else \
                     self.dw_stage[:self.cout_w, :self.cin_w]
                 if self.acc_dw:
@@ -243,13 +260,14 @@ class ConvOp(Op):
                 else:
                     self.grad_w.copy_(part)
             else:
-                self.plan.wgrad(self.x.buf.t, dz, self.grad_w, accumulate=self.acc_dw)
+                self.plan.wgrad(self.x.buf.t, dz, self.grad_w, accumulate=self.acc_dw, scratch=self.wg_scratch)
             if self.bias is not None:
                 if self.use_bias:
                     if self.colsum_done:
                         self.colsum_done = False
                     else:
-                        cs, co = (self.out_sl.buf.c, self.out_sl.off) if self.out_sl is not None else (self.cout, 0)
+                        dsl = self.dy_slice()
+                        cs, co = (dsl.buf.c, dsl.off) if dsl is not None else (self.cout, 0)
                         check(lib.petsyn_colsum(ptr(dz), cs, co, ptr(self.dbias_stage), dz.shape[0], self.cout,
                                                 stream_ptr()), "colsum")
                     if self.acc_dw:
@@ -271,10 +289,17 @@ SEPARATE_FINALIZE = bool(os.environ.get("PETSYN_SEPARATE_FINALIZE"))
 class NormActOp(Op):
     """dst_i = act(norm(z)) [+ res] for one or two destinations (channel slices)."""
 
-    def __init__(self, z: Buf, kind: str, act: int, dsts: Sequence[Sl], res: Optional[Sl] = None, slope: float = 0.2,
+    def __init__(self, z, kind: str, act: int, dsts: Sequence[Sl], res: Optional[Sl] = None, slope: float = 0.2,
                  bn: Optional[torch.nn.BatchNorm3d] = None, eps: float = 1e-5, name: str = "",
-                 slope_param: Optional[torch.nn.Parameter] = None, gn: Optional[torch.nn.GroupNorm] = None):
+                 slope_param: Optional[torch.nn.Parameter] = None, gn: Optional[torch.nn.GroupNorm] = None,
+                 extra: Optional[Sl] = None, no_bwd: bool = False):
+        """``z``: a whole buffer or a channel slice (Sl) of one.  ``extra`` (backward): a gradient slice ADDED to dz -- the
+        gradient reaching z through an identity skip connection.  ``no_bwd``: this op is a residual sum whose consumers'
+        gradients have been redirected (ConvOp.dy_from, ``extra``, ResampleOp.dst_grad): nothing to do in backward."""
         assert kind in ("instance", "batch", "group", "none") and 1 <= len(dsts) <= 2
+        self.zs: Sl = z if isinstance(z, Sl) else z.sl()
+        z = self.zs.buf                         # the underlying buffer; self.zs.off / .c select the channels
+        self.extra, self.no_bwd = extra, no_bwd
         self.gn = gn                            # nn.GroupNorm (kind == "group"): affine, num_groups, eps
         self.acc_dz = False
         self.fwd_batch_stats = True             # kind == "batch": the last forward normalised with batch statistics
@@ -288,15 +313,17 @@ class NormActOp(Op):
         self.z, self.kind, self.act, self.dsts, self.res, self.slope, self.bn, self.eps = z, kind, act, list(dsts), res, \
             slope, bn, eps
         self.name = name
-        self.stats_for = [None] * len(self.dsts)       # per destination: (consumer norm op, channel offset in its z)
+        self.stats_for = [[] for _ in self.dsts]       # per destination: up to 2 x (consumer norm op, channel offset in its z)
         dev = z.t.device
         self.ns = z.n if kind in ("instance", "group") else 1
         self.rows = z.rows // self.ns
-        c = z.c
+        c = self.c = self.zs.c
         if kind != "none":
             f = lambda m=1: torch.zeros(self.ns * c * m, dtype=torch.float32, device=dev)
-            self.sums, self.bsums = f(2), f(4)
+            # reduction targets are DOUBLE accumulators (64-bit atomics of fp32 partials: exact, hence reproducible sums)
+            self.sums, self.bsums = (torch.zeros(self.ns * c * 2, dtype=torch.float64, device=dev) for _ in range(2))
             self.scale, self.shift, self.mean, self.rstd = f(), f(), f(), f()
+        self.dslope_stage = torch.zeros(1, dtype=torch.float64, device=dev) if slope_param is not None else None
         self.acc_res = False
         self.grad_gamma: Optional[torch.Tensor] = None
         self.grad_beta: Optional[torch.Tensor] = None
@@ -304,12 +331,13 @@ class NormActOp(Op):
         self._tmp_gb: Optional[torch.Tensor] = None
 
     def _desc(self, backward: bool) -> _cabi.NormActDesc:
-        z = self.z
+        z, c = self.z, self.c
         d = _cabi.NormActDesc()
-        d.z, d.rows, d.c, d.nsamples = ptr(z.t), self.rows, z.c, self.ns
+        d.z, d.rows, d.c, d.nsamples = ptr(z.t), self.rows, c, self.ns
+        d.z_cstride, d.z_coff, d.dz_cstride, d.dz_coff = z.c, self.zs.off, z.c, self.zs.off
         d.per_sample_stats = 1 if self.kind in ("instance", "group") else 0
         if self.kind == "group":
-            d.group_size = z.c // self.gn.num_groups
+            d.group_size = c // self.gn.num_groups
             if backward:
                 d.gamma = ptr(self.gn.weight)
         d.dz_accumulate = int(self.acc_dz)
@@ -320,7 +348,7 @@ class NormActOp(Op):
                 d.fin_sums, d.mean, d.rstd = ptr(self.sums), ptr(self.mean), ptr(self.rstd)
                 if self.kind == "group":
                     d.fin_gamma, d.fin_beta = ptr(self.gn.weight), ptr(self.gn.bias)
-                    d.fin_group_size, d.fin_eps = z.c // self.gn.num_groups, self.gn.eps
+                    d.fin_group_size, d.fin_eps = c // self.gn.num_groups, self.gn.eps
                 else:
                     d.fin_group_size, d.fin_eps = 1, self.eps
             d.separate_group_combine = int(SEPARATE_FINALIZE)
@@ -330,17 +358,18 @@ class NormActOp(Op):
                 d.sums_prezeroed = 1 if self.tape_zeroes_bsums else 0
                 if self.bn is not None and self.bn.weight is not None:
                     d.gamma = ptr(self.bn.weight)
-        if not backward and any(t is not None for t in self.stats_for):
+        if not backward and any(self.stats_for):
             # per-sample launch so that the statistics land in the consumer's [sample][2][C] layout
             d.nsamples, d.rows = z.n, z.rows // z.n
-            for i, tgt in enumerate(self.stats_for):
-                if tgt is None:
-                    continue
-                q, off = tgt
+            # one destination may feed two consuming normalisations (a skip tensor: the next block and the up path's concat
+            # buffer); both destinations hold the same values, so the two descriptor slots are interchangeable
+            tgts = [t for lst in self.stats_for for t in lst]
+            assert len(tgts) <= 2
+            for i, (q, off) in enumerate(tgts):
                 if i == 0:
-                    d.t1_stats, d.t1_stats_c, d.t1_stats_coff = ptr(q.sums), q.z.c, off
+                    d.t1_stats, d.t1_stats_c, d.t1_stats_coff = ptr(q.sums), q.c, off
                 else:
-                    d.t2_stats, d.t2_stats_c, d.t2_stats_coff = ptr(q.sums), q.z.c, off
+                    d.t2_stats, d.t2_stats_c, d.t2_stats_coff = ptr(q.sums), q.c, off
         src = (lambda s: s.buf.g) if backward else (lambda s: s.buf.t)
         s1 = self.dsts[0]
         d.t1, d.t1_cstride, d.t1_coff, d.act1 = ptr(src(s1)), s1.buf.c, s1.off, self.act
@@ -351,43 +380,47 @@ class NormActOp(Op):
         if self.slope_param is not None:
             d.slope_dev = ptr(self.slope_param)
             if backward and self.grad_slope is not None:
-                d.dslope = ptr(self.grad_slope)
+                d.dslope = ptr(self.dslope_stage)
         if self.res is not None:
             d.res, d.res_cstride, d.res_coff = ptr(src(self.res)), self.res.buf.c, self.res.off
             d.res_accumulate = int(self.acc_res)
         if backward:
             d.dz = ptr(z.g)
-            if self.colsum_conv is not None and not self.acc_dz:
+            if self.extra is not None:
+                d.extra, d.extra_cstride, d.extra_coff = ptr(self.extra.buf.g), self.extra.buf.c, self.extra.off
+            if self.colsum_conv is not None:
                 d.dz_colsum = ptr(self.colsum_conv.dbias_stage)
             if self.grad_gamma is not None:
                 if self.acc_dw:
                     if self._tmp_gb is None:
-                        self._tmp_gb = torch.zeros(2, z.c, dtype=torch.float32, device=z.t.device)
+                        self._tmp_gb = torch.zeros(2, c, dtype=torch.float32, device=z.t.device)
                     d.dgamma, d.dbeta = ptr(self._tmp_gb[0]), ptr(self._tmp_gb[1])
                 else:
                     d.dgamma, d.dbeta = ptr(self.grad_gamma), ptr(self.grad_beta)
         return d
 
     def fwd(self, training: bool) -> None:
-        z = self.z
+        z, c = self.z, self.c
+        stats = lambda ns, rows: check(lib.petsyn_norm_stats_slice(ptr(z.t), z.c, self.zs.off, ptr(self.sums), rows, c, ns,
+                                                                   stream_ptr()), "norm_stats")
         if self.kind == "instance":
             if not self.tape_zeroes_sums:
                 self.sums.zero_()
-            check(lib.petsyn_norm_stats(ptr(z.t), ptr(self.sums), self.rows, z.c, z.n, stream_ptr()), "norm_stats")
+            stats(z.n, self.rows)
             if SEPARATE_FINALIZE:        # default: folded into the apply launch below (fin_* fields of the descriptor)
                 check(lib.petsyn_norm_finalize(ptr(self.sums), None, None, None, None, ptr(self.scale), ptr(self.shift),
-                                               ptr(self.mean), ptr(self.rstd), self.rows, z.c, z.n, 1, self.eps, 0.0, 1,
+                                               ptr(self.mean), ptr(self.rstd), self.rows, c, z.n, 1, self.eps, 0.0, 1,
                                                stream_ptr()), "norm_finalize")
         elif self.kind == "group":
             gn = self.gn
             if not self.stats_from_producers:
                 if not self.tape_zeroes_sums:
                     self.sums.zero_()
-                check(lib.petsyn_norm_stats(ptr(z.t), ptr(self.sums), self.rows, z.c, z.n, stream_ptr()), "norm_stats")
+                stats(z.n, self.rows)
             if SEPARATE_FINALIZE:
                 check(lib.petsyn_norm_finalize(ptr(self.sums), ptr(gn.weight), ptr(gn.bias), None, None, ptr(self.scale),
-                                               ptr(self.shift), ptr(self.mean), ptr(self.rstd), self.rows, z.c, z.n,
-                                               z.c // gn.num_groups, gn.eps, 0.0, 1, stream_ptr()), "norm_finalize")
+                                               ptr(self.shift), ptr(self.mean), ptr(self.rstd), self.rows, c, z.n,
+                                               c // gn.num_groups, gn.eps, 0.0, 1, stream_ptr()), "norm_finalize")
         elif self.kind == "batch":
             bn = self.bn
             if bn.momentum is None:
@@ -397,36 +430,45 @@ class NormActOp(Op):
             if use_batch:
                 if not self.tape_zeroes_sums:
                     self.sums.zero_()
-                check(lib.petsyn_norm_stats(ptr(z.t), ptr(self.sums), z.rows, z.c, 1, stream_ptr()), "norm_stats")
+                stats(1, z.rows)
                 if bn.num_batches_tracked is not None and not freeze:
                     bn.num_batches_tracked.add_(1)
             self.fwd_batch_stats = use_batch
             rm, rv = (None, None) if (use_batch and freeze) else (ptr(bn.running_mean), ptr(bn.running_var))
             check(lib.petsyn_norm_finalize(ptr(self.sums), ptr(bn.weight), ptr(bn.bias), rm, rv, ptr(self.scale),
-                                           ptr(self.shift), ptr(self.mean), ptr(self.rstd), z.rows, z.c, 1, 1, bn.eps,
+                                           ptr(self.shift), ptr(self.mean), ptr(self.rstd), z.rows, c, 1, 1, bn.eps,
                                            bn.momentum, int(use_batch), stream_ptr()), "norm_finalize")
         d = self._desc(False)
         check(lib.petsyn_normact_fwd(C.byref(d), stream_ptr()), "normact_fwd")
 
     def grad_writes(self):
-        w = [("dz", self.z.sl())]
+        if self.no_bwd:
+            return []
+        w = [("dz", self.zs)]
         if self.res is not None:
             w.append(("dres", self.res))
         return w
 
     def bwd(self) -> None:
+        if self.no_bwd:
+            return
         if self.kind == "batch" and not self.fwd_batch_stats:
             # eval(): the layer is affine in its input (running statistics); the kernels implement the batch-statistics
             # backward only, which would silently add a mean / variance correction that does not exist here
             raise NotImplementedError("backward through BatchNorm3d in eval() mode is not implemented; call .train()")
-        if self.grad_slope is not None and not self.acc_dw:
-            self.grad_slope.zero_()
-        if self.colsum_conv is not None and not self.acc_dz:
+        if self.grad_slope is not None:
+            self.dslope_stage.zero_()
+        if self.colsum_conv is not None:
             if not self.colsum_conv.tape_zeroes_dbias:
                 self.colsum_conv.dbias_stage.zero_()
             self.colsum_conv.colsum_done = True
         d = self._desc(True)
         check(lib.petsyn_normact_bwd(C.byref(d), stream_ptr()), "normact_bwd")
+        if self.grad_slope is not None:
+            if self.acc_dw:
+                self.grad_slope.add_(self.dslope_stage.view_as(self.grad_slope))
+            else:
+                self.grad_slope.copy_(self.dslope_stage.view_as(self.grad_slope))
         if self.acc_dw and self.grad_gamma is not None:
             self.grad_gamma.add_(self._tmp_gb[0])
             self.grad_beta.add_(self._tmp_gb[1])
@@ -435,8 +477,11 @@ class NormActOp(Op):
 class ResampleOp(Op):
     """dst = AvgPool3d(2,2)(src) (up=False) or nearest x2 upsampling (up=True) of a whole buffer."""
 
-    def __init__(self, src: Sl, dst: Sl, up: bool):
+    def __init__(self, src: Sl, dst: Sl, up: bool, dst_grad: Optional[Sl] = None):
+        """``dst_grad``: backward reads d(loss)/d(dst) from this slice instead of dst's own gradient buffer (dst is the
+        identity branch of a residual sum whose result -- and therefore whose gradient -- lives there)."""
         self.src, self.dst, self.up = src, dst, up
+        self.dst_grad = dst_grad
         self.acc_dx = False
 
     def _run(self, a: torch.Tensor, sa: Sl, b: torch.Tensor, sb: Sl, up: bool, scale: float, acc: bool) -> None:
@@ -451,7 +496,8 @@ class ResampleOp(Op):
         return [("dx", self.src)]
 
     def bwd(self) -> None:      # transpose of the forward map
-        self._run(self.dst.buf.g, self.dst, self.src.buf.g, self.src, not self.up, 1.0 if self.up else 0.125, self.acc_dx)
+        dg = self.dst_grad if self.dst_grad is not None else self.dst
+        self._run(dg.buf.g, dg, self.src.buf.g, self.src, not self.up, 1.0 if self.up else 0.125, self.acc_dx)
 
 
 class LayerNormOp(Op):
@@ -586,50 +632,75 @@ class Tape:
                     op.acc_dz = covered
                 if not covered:
                     ranges.append((lo, hi))
-        # bias gradients as a by-product: a conv whose raw output z has exactly one gradient writer, a NormActOp's dz
-        writers: Dict[int, int] = {}
-        for op in self.ops:
-            for _, s in op.grad_writes():
-                writers[id(s.buf)] = writers.get(id(s.buf), 0) + 1
-        convs = {id(op.z): op for op in self.ops
-                 if isinstance(op, ConvOp) and op.z is not None and op.use_bias and op.need_dw and op.bias is not None}
+        # bias gradients as a by-product: the gradient w.r.t. a conv's output (its own z, or the slice ConvOp.dy_from points at)
+        # is complete after its LAST writer in backward order; when that writer is a NormActOp's dz covering exactly that
+        # slice, its apply pass also sums the final values over the rows (after any accumulation) = the bias gradient
+        writes: List[Tuple[Op, str, Sl]] = []
+        for op in reversed(self.ops):
+            for key, sl in op.grad_writes():
+                writes.append((op, key, sl))
         for op in self.ops:
             if isinstance(op, NormActOp):
-                c = convs.get(id(op.z))
-                op.colsum_conv = c if (c is not None and writers.get(id(op.z), 0) == 1 and not op.acc_dz) else None
-        # statistics as a by-product: a GroupNorm whose input buffer is written, channel range by channel range, only by
-        # un-normalised NormActOps (residual sums, copies into concat buffers) takes its sums from those producers
+                op.colsum_conv = None
+        for cv in self.ops:
+            if not (isinstance(cv, ConvOp) and cv.use_bias and cv.need_dw and cv.bias is not None):
+                continue
+            region = cv.dy_slice()
+            if region is None:
+                continue
+            lo, hi = region.off, region.off + region.c
+            hits = [(op, key, sl) for op, key, sl in writes
+                    if sl.buf is region.buf and sl.off < hi and lo < sl.off + sl.c]
+            if not hits:
+                continue
+            op, key, sl = hits[-1]
+            if isinstance(op, NormActOp) and key == "dz" and (sl.off, sl.c) == (region.off, region.c) \
+                    and op.colsum_conv is None:
+                op.colsum_conv = cv
+        # statistics as a by-product: a GroupNorm whose input (a buffer or a channel slice of one) is written, channel range
+        # by channel range, only by un-normalised NormActOps (residual sums, copies into concat buffers) takes its sums from
+        # those producers; a destination may serve two consuming normalisations
         produced: Dict[int, List[Tuple[NormActOp, int, Sl]]] = {}
-        other_writers = set()
+        other_writers: Dict[int, List[Tuple[int, int]]] = {}
+
+        def other(sl: Sl) -> None:
+            other_writers.setdefault(id(sl.buf), []).append((sl.off, sl.off + sl.c))
+
         for op in self.ops:
             if isinstance(op, NormActOp):
                 for i, sl in enumerate(op.dsts):
                     if op.kind == "none" and op.slope_param is None:
                         produced.setdefault(id(sl.buf), []).append((op, i, sl))
                     else:
-                        other_writers.add(id(sl.buf))
+                        other(sl)
             elif isinstance(op, ConvOp):
-                other_writers.add(id(op.out_sl.buf) if op.out_sl is not None else id(op.z))
+                if op.out_sl is not None:
+                    other(op.out_sl)
+                elif op.z is not None:
+                    other(op.z.sl())
             else:
                 for v in vars(op).values():            # any other op that holds the buffer may write it: be conservative
                     if isinstance(v, Buf):
-                        other_writers.add(id(v))
+                        other(v.sl())
                     elif isinstance(v, Sl):
-                        other_writers.add(id(v.buf))
+                        other(v)
         shared = []
         for q in self.ops:
             if not (isinstance(q, NormActOp) and q.kind == "group" and not os.environ.get("PETSYN_NO_STATS_FUSION")):
                 continue
-            prods = produced.get(id(q.z), [])
-            if id(q.z) in other_writers or not prods:
+            lo, hi = q.zs.off, q.zs.off + q.zs.c
+            if any(a < hi and lo < b for a, b in other_writers.get(id(q.z), [])):
+                continue
+            prods = [(p, i, sl) for p, i, sl in produced.get(id(q.z), []) if sl.off < hi and lo < sl.off + sl.c]
+            if not prods:
                 continue
             cover = sorted((sl.off, sl.off + sl.c) for _, _, sl in prods)
-            if cover[0][0] != 0 or cover[-1][1] != q.z.c or any(a[1] != b[0] for a, b in zip(cover, cover[1:])):
+            if cover[0][0] != lo or cover[-1][1] != hi or any(a[1] != b[0] for a, b in zip(cover, cover[1:])):
                 continue
-            if any(p.stats_for[i] is not None for p, i, _ in prods):
-                continue                               # a destination feeds one consumer's statistics only
+            if any(sum(len(t) for t in p.stats_for) >= 2 for p, _, _ in prods):
+                continue                               # an op carries at most two statistics targets
             for p, i, sl in prods:
-                p.stats_for[i] = (q, sl.off)
+                p.stats_for[i].append((q, sl.off - lo))
             q.stats_from_producers = True
             shared.append(q)
         # every small fp32 accumulator a step starts from zero lives in one of two arenas, cleared by ONE fill at the start
@@ -639,7 +710,9 @@ class Tape:
                 return None
             dev = getattr(*pairs[0]).device
             sizes = [(getattr(h, a).numel() + 3) // 4 * 4 for h, a in pairs]            # 16-byte aligned views
-            buf = torch.zeros(sum(sizes), dtype=torch.float32, device=dev)
+            dtype = getattr(*pairs[0]).dtype
+            assert all(getattr(h, a).dtype == dtype for h, a in pairs)
+            buf = torch.zeros(sum(sizes), dtype=dtype, device=dev)
             off = 0
             for (h, a), n_ in zip(pairs, sizes):
                 old_t = getattr(h, a)
@@ -657,13 +730,21 @@ class Tape:
         if use:
             for op in self.ops:
                 c = op.colsum_conv if isinstance(op, NormActOp) else None
-                if c is not None and not op.acc_dz and c.dbias_stage is not None and not c.tape_zeroes_dbias:
+                if c is not None and c.dbias_stage is not None and not c.tape_zeroes_dbias:
                     c.tape_zeroes_dbias = True
                     bwd_pairs.append((c, "dbias_stage"))
             for op in normed:
                 op.tape_zeroes_bsums = True
                 bwd_pairs.append((op, "bsums"))
         self._bwd_arena = arena(bwd_pairs)
+        # the weight-gradient kernels write per-CTA / per-split partial images into a scratch that the unpack kernel sums in a
+        # fixed order; all weight gradients of a tape run on its main stream one after the other, so they share ONE scratch
+        convs = [op for op in self.ops if isinstance(op, ConvOp) and op.need_dw]
+        if convs:
+            nbytes = max(op.plan.wgrad_scratch_bytes for op in convs)
+            shared = torch.empty(nbytes, dtype=torch.uint8, device=convs[0].weight.device)
+            for op in convs:
+                op.wg_scratch = shared
         self._final = True
 
     def repack(self) -> None:

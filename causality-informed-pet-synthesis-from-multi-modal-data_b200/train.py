@@ -502,15 +502,27 @@ class BmganTrainer:
 
 
 class AttenUNetTrainer(_CheckpointMixin):
-    """Fused training step for the covariate-conditioned generator (``train_unet.py:136-168`` with the offline-available
-    terms: zero_grad -> unet(t1, condition) -> nn.L1Loss -> backward -> Adam), data-parallel like Unet3dTrainer.
-    Single GPU: the whole step replays as one CUDA graph after ``capture()``."""
+    """Fused training step for the covariate-conditioned generator, ``unet/scripts/train_unet.py:136-195``:
+
+      G phase (:136-168)  D frozen; ``output_pet = unet(t1, condition)``; ``g_loss = L1 + adv_weight * LSGAN(D(output_pet)[-1],
+                          real)`` (LPIPS has weight 0 in unet/config/training.json:55 and needs downloaded weights: dropped);
+                          backward through D (data gradient only) into the generator; [bucketed all-reduce]; Adam(base_lr).
+      D phase (:171-193)  (``adv_weight > 0`` and a discriminator given) the generator forward AGAIN under no_grad -- with the
+                          weights the G phase just updated, as the reference does -- then ``LSGAN(D(fake), fake).backward()``
+                          and ``LSGAN(D(real), real).backward()`` (two backward calls, gradients accumulate; the 0.5 *
+                          adv_weight scaling of ``d_loss`` is only logged, never backpropagated), Adam(disc_lr) on D.  The
+                          reference's DDP all-reduces D's gradients once per backward call; here once, after both.
+    Without a discriminator (or ``adv_weight == 0``) the step is zero_grad -> unet -> L1 -> backward -> Adam, exactly the
+    reference's ``else`` branches (:156-157,194-195).  Data-parallel like Unet3dTrainer; after ``capture()`` the step replays
+    as CUDA graph(s)."""
 
     def __init__(self, model, lr: float = 5e-4, betas=(0.9, 0.999), eps: float = 1e-8, bucket_mb: float = 32.0,
-                 process_group=None, example_input: Optional[torch.Tensor] = None, ssim_weight: float = 0.0):
+                 process_group=None, example_input: Optional[torch.Tensor] = None, ssim_weight: float = 0.0,
+                 discriminator=None, adv_weight: float = 0.0, disc_lr: float = 1e-4):
         """``ssim_weight`` > 0 adds ``ssim_weight * (1 - SSIM)`` (Gaussian window 5, sigma 0.5, data_range 1 -- the
         parameters of the reference's evaluation, output_predict.py:73) to the L1 reconstruction loss; the reference's own
-        training loss is L1 (+ LPIPS / adversarial terms that do not exist offline), so the default is 0."""
+        training loss is L1 (+ LPIPS / adversarial terms), so the default is 0.  ``discriminator``: a petsyn
+        ``PatchDiscriminator(**training.json["discriminator"])``; ``adv_weight`` / ``disc_lr``: training.json:53-56."""
         if example_input is None:
             raise ValueError("example_input (a tensor of the training shape) is required to lay out the arenas")
         self.model = model
@@ -534,9 +546,26 @@ class AttenUNetTrainer(_CheckpointMixin):
         self.bucketer = GradBucketer(self.arena, bucket_mb, process_group)
         self.graph = None
         self.segments = None
+        self.d_graph = None
         self.static = None
+        self.disc = discriminator if (discriminator is not None and adv_weight > 0) else None
+        self.adv_weight, self.disc_lr = float(adv_weight), float(disc_lr)
+        if self.disc is not None:
+            self.deng = self.disc.engine_for(example_input)
+            self.darena = FlatArena(list(self.deng.params), dev)
+            self.dm, self.dv = torch.zeros_like(self.darena.p), torch.zeros_like(self.darena.p)
+            self.d_step_dev = torch.zeros(1, dtype=torch.int32, device=dev)
+            f = lambda: torch.zeros(1, dtype=torch.float32, device=dev)
+            self.loss_adv, self.loss_d_fake, self.loss_d_real = f(), f(), f()
+            self.dlogits = torch.zeros_like(self.deng.logits)
+            self.deng.mark_weights_dirty()
         if self.world > 1:
             dist.broadcast(self.arena.p, src=0, group=self.pg)
+            if self.disc is not None:
+                dist.broadcast(self.darena.p, src=0, group=self.pg)
+                for b in self.disc.buffers():
+                    if b.dtype.is_floating_point:
+                        dist.broadcast(b, src=0, group=self.pg)
         self.eng.mark_weights_dirty()
 
     def _forward_and_loss(self, x: torch.Tensor, context: torch.Tensor, target: torch.Tensor) -> None:
@@ -545,6 +574,36 @@ class AttenUNetTrainer(_CheckpointMixin):
         ops.l1_loss_fwd_bwd(y, target, self.loss, self.dy)
         if self.ssim is not None:
             self.ssim_value = self.ssim(y, target, self.dy, grad_scale=self.ssim_weight, accumulate=True)
+        if self.disc is not None:                          # adv_weight * LSGAN(D(output_pet)[-1], real): train_unet.py:153-155
+            logits = self.deng.forward(y)
+            self.loss_adv.zero_()
+            ops.mse_const_fwd_bwd(logits, 1.0, self.loss_adv, self.dlogits, grad_scale=self.adv_weight)
+            dfake, _ = self.deng.backward(self.dlogits, need_dx=True, out=self.darena.grad_views, need_dw=False)
+            self.dy.add_(dfake)
+
+    def _d_phase_grads(self, x: torch.Tensor, context: torch.Tensor, target: torch.Tensor) -> None:
+        """train_unet.py:171-184: the two backward calls of the discriminator phase (gradients into the D arena)."""
+        fake = self.eng.forward(x, context)                # :175-176, no_grad recompute with the updated generator
+        logits = self.deng.forward(fake)
+        self.loss_d_fake.zero_()
+        ops.mse_const_fwd_bwd(logits, 0.0, self.loss_d_fake, self.dlogits)
+        self.deng.backward(self.dlogits, need_dx=False, out=self.darena.grad_views, need_dw=True, accumulate=False)
+        logits = self.deng.forward(target)
+        self.loss_d_real.zero_()
+        ops.mse_const_fwd_bwd(logits, 1.0, self.loss_d_real, self.dlogits)
+        self.deng.backward(self.dlogits, need_dx=False, out=self.darena.grad_views, need_dw=True, accumulate=True)
+
+    def _d_optimizer(self) -> None:
+        self.d_step_dev.add_(1)
+        ops.adam_step(self.darena.p, self.darena.g, self.dm, self.dv, self.disc_lr, self.betas[0], self.betas[1], self.eps, 0,
+                      step_dev=self.d_step_dev)
+        self.deng.mark_weights_dirty()
+
+    def _d_phase(self, x: torch.Tensor, context: torch.Tensor, target: torch.Tensor) -> None:
+        self._d_phase_grads(x, context, target)
+        if self.world > 1:
+            dist.all_reduce(self.darena.g, op=dist.ReduceOp.AVG, group=self.pg)
+        self._d_optimizer()
 
     def _optimizer(self) -> None:
         self.step_dev.add_(1)
@@ -557,9 +616,13 @@ class AttenUNetTrainer(_CheckpointMixin):
         self.eng.backward(self.dy, out=self.arena.grad_views, on_ready=self.bucketer.on_ready)
         self.bucketer.wait_all()
         self._optimizer()
+        if self.disc is not None:
+            self._d_phase(x, context, target)
         return self.loss
 
     def step(self, x: torch.Tensor, context: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
+        """One step; returns the device L1 loss of this rank's micro-batch (``loss_adv`` / ``loss_d_fake`` / ``loss_d_real``
+        hold the adversarial terms when a discriminator is trained along)."""
         self.step_count += 1
         ctx = context.reshape(x.shape[0], -1)
         if self.graph is None:
@@ -574,7 +637,10 @@ class AttenUNetTrainer(_CheckpointMixin):
             graph.replay()
             self.bucketer.on_ready(last_param)       # eager NCCL launch between graph segments (side stream)
         self.bucketer.wait_all()
-        self.graph.replay()                          # Adam
+        self.graph.replay()                          # Adam [+ the D phase's forward / backward calls]
+        if self.disc is not None:
+            dist.all_reduce(self.darena.g, op=dist.ReduceOp.AVG, group=self.pg)
+            self.d_graph.replay()                    # Adam on D
         return self.loss
 
     def capture(self, warmup: int = 2) -> None:
@@ -583,6 +649,11 @@ class AttenUNetTrainer(_CheckpointMixin):
         [..until bucket 1] ... [Adam]; each bucket's all-reduce is launched eagerly on the side stream right after
         its segment and overlaps the next one (same scheme as Unet3dTrainer.capture)."""
         state = [self.arena.p, self.m, self.v, self.step_dev]
+        bufs = []
+        if self.disc is not None:
+            state += [self.darena.p, self.dm, self.dv, self.d_step_dev]
+            bufs = [b for b in self.disc.buffers()]
+        buf_snap = [b.clone() for b in bufs]
         snap = [t.clone() for t in state]
         n = self.dy.shape[0]
         cdim = self.model.cfg["cross_attention_dim"]
@@ -620,10 +691,23 @@ class AttenUNetTrainer(_CheckpointMixin):
             self._forward_and_loss(*self.static)
             self.eng.backward(self.dy, out=self.arena.grad_views, on_ready=cut)
             self._optimizer()                        # the open capture holds only what follows the last bucket: Adam
+            if self.disc is not None:
+                self._d_phase_grads(*self.static)    # ... and the D phase up to its gradients (their all-reduce is eager)
             cur["ctx"].__exit__(None, None, None)
             g = cur["g"]
             self.segments = segments
+            if self.disc is not None:
+                self.d_graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(self.d_graph, pool=pool):
+                    self._d_optimizer()
         for dst, src in zip(state, snap):
             dst.copy_(src)
-        self.eng.mark_weights_dirty()        # the captured step begins with the repack, so no eager refresh is needed
+        for dst, src in zip(bufs, buf_snap):
+            dst.copy_(src)
+        self.eng.mark_weights_dirty()        # without a discriminator the captured step begins with the repack
+        if self.disc is not None:
+            # with one, every step ENDS with a generator forward (the D phase's recompute) that leaves the packed weights
+            # current, so the captured step does not begin with a repack: refresh them once for the restored weights
+            self.eng.tape.repack()
+            self.deng.mark_weights_dirty()   # D is re-packed inside the graph (its Adam is the last thing a step does)
         self.graph = g

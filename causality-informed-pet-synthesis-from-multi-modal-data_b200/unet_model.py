@@ -154,8 +154,8 @@ class _Norm:
     def __init__(self, bn: nn.BatchNorm3d, c: int, dev):
         self.bn = bn
         f = lambda n=c: torch.empty(n, dtype=torch.float32, device=dev)
-        self.sums = torch.zeros(2 * c, dtype=torch.float32, device=dev)
-        self.bsums = torch.zeros(2 * c, dtype=torch.float32, device=dev)
+        self.sums = torch.zeros(2 * c, dtype=torch.float64, device=dev)     # double accumulators (exact sums)
+        self.bsums = torch.zeros(2 * c, dtype=torch.float64, device=dev)
         self.scale, self.shift, self.mean, self.rstd = f(), f(), f(), f()
         self.dgamma, self.dbeta = f(), f()
 

@@ -185,11 +185,11 @@ int32_t petsyn_head_scatter_bwd(const float* y, const float* dy, void* dproj, in
 
 /* Per-channel partial sums of a raw conv output z (bf16 [rows, c] contiguous, rows = n*d*h*w):
  * sums[2*c] (fp32, caller-zeroed): sum z, sum z^2 per channel (BATCH) */
-int32_t petsyn_bn_stats(const void* z, float* sums, int64_t rows, int32_t c, void* stream);
+int32_t petsyn_bn_stats(const void* z, double* sums, int64_t rows, int32_t c, void* stream);
 /* mean/rstd -> fused affine (scale = gamma*rstd, shift = beta - mean*scale) and the running-stat update
  * (momentum, unbiased variance) of nn.BatchNorm3d in training mode.  In eval mode (training == 0) scale/shift are
  * derived from the running statistics and `sums` is ignored.  save_mean/save_rstd are kept for backward. */
-int32_t petsyn_bn_finalize(const float* sums, const float* gamma, const float* beta, float* running_mean,
+int32_t petsyn_bn_finalize(const double* sums, const float* gamma, const float* beta, float* running_mean,
                            float* running_var, float* scale, float* shift, float* save_mean, float* save_rstd,
                            int64_t rows, int32_t c, float eps, float momentum, int32_t training, void* stream);
 /* dst1 = act1(z*scale + shift) [, dst2 = act2(same)] written into channel slices of wider NDHWC buffers -- the
@@ -203,13 +203,13 @@ int32_t petsyn_norm_act_fwd(const void* z, const float* scale, const float* shif
 int32_t petsyn_norm_act_bwd_reduce(const void* z, const float* scale, const float* shift, const float* mean,
                                    const float* rstd, const void* g1, int32_t g1_cstride, int32_t g1_coff,
                                    int32_t act1, const void* g2, int32_t g2_cstride, int32_t g2_coff, int32_t act2,
-                                   float slope, float* sums, int64_t rows, int32_t c, void* stream);
+                                   float slope, double* sums, int64_t rows, int32_t c, void* stream);
 /* Backward, pass 2: dz = gamma*rstd*(g - sum_g/rows - zhat*sum_gz/rows) (BatchNorm training backward), or
  * dz = g when mean == NULL (no norm).  Also emits dgamma = sum g*zhat, dbeta = sum g when dgamma != NULL. */
 int32_t petsyn_norm_act_bwd_apply(const void* z, const float* scale, const float* shift, const float* mean,
                                   const float* rstd, const float* gamma, const void* g1, int32_t g1_cstride,
                                   int32_t g1_coff, int32_t act1, const void* g2, int32_t g2_cstride, int32_t g2_coff,
-                                  int32_t act2, float slope, const float* sums, void* dz, float* dgamma,
+                                  int32_t act2, float slope, const double* sums, void* dz, float* dgamma,
                                   float* dbeta, int64_t rows, int32_t c, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
@@ -236,7 +236,9 @@ typedef struct petsyn_normact_desc {
   void* res;                 /* fwd: residual input, out = act(norm(z)) + res; bwd: gradient w.r.t. res (output) */
   int32_t res_cstride, res_coff;
   int32_t res_accumulate;    /* bwd: add into res instead of overwriting */
-  float* sums;               /* bwd workspace [nsamples|1][2c] */
+  double* sums;              /* bwd workspace [nsamples|1][2c], DOUBLE precision: the CTAs' fp32 partial sums are added with
+                              * 64-bit atomics, which is exact -- so reproducible from run to run -- unless a partial cancels
+                              * below 2^-28 of the total (csrc/det_reduce.cuh) */
   void* dz;                  /* bwd: gradient w.r.t. z, bf16 contiguous */
   float* dgamma;             /* optional outputs (batch statistics with affine) */
   float* dbeta;
@@ -245,17 +247,18 @@ typedef struct petsyn_normact_desc {
   int32_t dz_accumulate;     /* bwd: add into dz (the normalised tensor has other consumers, e.g. a ResnetBlock skip) */
   int32_t affine_accumulate; /* bwd: add into dgamma/dbeta (group/per-sample-affine path) */
   const float* slope_dev;    /* PETSYN_ACT_PRELU: device scalar holding the slope (MONAI ResidualUnit act="PRELU") */
-  float* dslope;             /* bwd: d(loss)/d(slope) accumulated into this device scalar (caller-zeroed) */
-  float* dz_colsum;          /* bwd, optional: [c] += column sums of dz over all rows and samples (caller-zeroed) -- the bias
-                              * gradient of the convolution that produced z, as a by-product of the apply pass.  Not with
-                              * dz_accumulate */
-  float* t1_stats;           /* fwd, optional: statistics of what is written to destination 1, for the normalisation that
-                              * consumes it: [nsamples][2][t1_stats_c] fp32 (sum, sum of squares), this op's channels at
+  double* dslope;            /* bwd: d(loss)/d(slope) accumulated into this device scalar (double, caller-zeroed) */
+  double* dz_colsum;         /* bwd, optional: [c] += column sums of the FINAL dz (after `extra` and dz_accumulate) over all rows
+                              * and samples (caller-zeroed) -- the bias gradient of the convolution whose output gradient
+                              * this is, as a by-product of the apply pass */
+  double* t1_stats;          /* fwd, optional: statistics of what is written to destination 1, for the normalisation that
+                              * consumes it: [nsamples][2][t1_stats_c] doubles (sum, sum of squares), this op's channels at
                               * offset t1_stats_coff; caller-zeroed; needs nsamples = per-sample launch */
   int32_t t1_stats_c, t1_stats_coff;
-  float* t2_stats;           /* the same for destination 2 (same values, another consumer) */
+  double* t2_stats;          /* a second statistics target for the same values (another consuming normalisation); allowed
+                              * without a second destination */
   int32_t t2_stats_c, t2_stats_coff;
-  const float* fin_sums;     /* fwd, optional: fuse petsyn_norm_finalize (Instance / Group normalisation) into this launch.
+  const double* fin_sums;    /* fwd, optional: fuse petsyn_norm_finalize (Instance / Group normalisation) into this launch.
                               * [nsamples][2][c] statistics sums (petsyn_norm_stats layout); scale / shift / mean / rstd then
                               * are OUTPUTS ([nsamples][c], written for the backward pass); needs per_sample_stats */
   const float* fin_gamma;    /* [c] affine weight or NULL */
@@ -266,14 +269,23 @@ typedef struct petsyn_normact_desc {
                               * default folds it into the apply kernel's prologue) */
   int32_t sums_prezeroed;    /* bwd: the caller has already cleared the first nsamples * 2 * c floats of `sums` (one fill for
                               * all the normalisations of a step instead of a memset per call) */
+  int32_t z_cstride, z_coff; /* z as a channel slice [z_coff, z_coff + c) of a buffer with pitch z_cstride; 0 = contiguous */
+  int32_t dz_cstride, dz_coff; /* the same for dz */
+  const void* extra;         /* bwd, optional: bf16 channel slice ADDED to dz -- the gradient that reaches the normalised tensor
+                              * through an identity skip connection (ResnetBlock: out = f(x) + x, atten_unet_model.py:662), so
+                              * the residual sum needs no backward pass of its own */
+  int32_t extra_cstride, extra_coff;
 } petsyn_normact_desc;
 
-/* sums[sample][0:c] = sum z, sums[sample][c:2c] = sum z^2 (fp32, caller-zeroed). */
-int32_t petsyn_norm_stats(const void* z, float* sums, int64_t rows, int32_t c, int32_t nsamples, void* stream);
+/* sums[sample][0:c] += sum z, sums[sample][c:2c] += sum z^2 (double accumulators, caller-zeroed). */
+int32_t petsyn_norm_stats(const void* z, double* sums, int64_t rows, int32_t c, int32_t nsamples, void* stream);
+/* The same for z given as a channel slice [coff, coff + c) of a buffer with channel pitch cstride. */
+int32_t petsyn_norm_stats_slice(const void* z, int32_t cstride, int32_t coff, double* sums, int64_t rows, int32_t c,
+                                int32_t nsamples, void* stream);
 /* Statistics -> fused affine scale/shift per (sample, channel).  group_size channels share statistics (GroupNorm,
  * atten_unet_model.py:593-612); group_size 1 with nsamples == N is InstanceNorm3d, with nsamples == 1 BatchNorm3d
  * (running statistics updated in training mode, used in eval mode). */
-int32_t petsyn_norm_finalize(const float* sums, const float* gamma, const float* beta, float* running_mean,
+int32_t petsyn_norm_finalize(const double* sums, const float* gamma, const float* beta, float* running_mean,
                              float* running_var, float* scale, float* shift, float* save_mean, float* save_rstd,
                              int64_t rows, int32_t c, int32_t nsamples, int32_t group_size, float eps, float momentum,
                              int32_t training, void* stream);
@@ -283,8 +295,8 @@ int32_t petsyn_normact_bwd(const petsyn_normact_desc* desc, void* stream);
 /* dst[:, dst_coff:+c] (+)= src[:, src_coff:+c] on bf16 channel slices. */
 int32_t petsyn_add_slice(const void* src, int32_t src_cstride, int32_t src_coff, void* dst, int32_t dst_cstride,
                          int32_t dst_coff, int64_t rows, int32_t c, int32_t accumulate, void* stream);
-/* out[c] = sum over rows of x[:, coff + c] (bias gradient); out fp32, overwritten. */
-int32_t petsyn_colsum(const void* x, int32_t cstride, int32_t coff, float* out, int64_t rows, int32_t c, void* stream);
+/* out[c] = sum over rows of x[:, coff + c] (bias gradient); out double, overwritten. */
+int32_t petsyn_colsum(const void* x, int32_t cstride, int32_t coff, double* out, int64_t rows, int32_t c, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Covariate-conditioned generator (AttenUNet, unet/utils/atten_unet_model.py): resampling inside the up/down

@@ -231,3 +231,39 @@ def init_state_dict(cfg=TRAINING_JSON, seed: int = 0) -> Dict[str, torch.Tensor]
     sd = {k: torch.zeros(s) for k, s in param_shapes(cfg).items()}
     randomize_(sd.items(), seed=seed)
     return sd
+
+
+def adversarial_step(x, context, target, sd, disc, adv_weight: float = 0.1, base_lr: float = 5e-4, disc_lr: float = 1e-4,
+                     cfg=TRAINING_JSON):
+    """One full step of ``unet/scripts/train_unet.py:136-193`` with the terms that exist offline (LPIPS has weight 0 in
+    unet/config/training.json:55): G phase -- D frozen, ``g_loss = L1 + adv_weight * LSGAN(D(G(t1, c))[-1], real)``, Adam(base_lr)
+    -- then the D phase -- generator forward again under no_grad with the UPDATED weights, ``LSGAN(D(fake), fake).backward()``,
+    ``LSGAN(D(real), real).backward()``, Adam(disc_lr).  ``disc``: a ``monai_stub.PatchDiscriminator`` (updated in place).
+    Returns the losses, the generator / discriminator gradients of the step and the updated generator parameters."""
+    params = {k: v.detach().clone().requires_grad_(True) for k, v in sd.items()}
+    g_opt = torch.optim.Adam(list(params.values()), lr=base_lr)
+    d_opt = torch.optim.Adam(disc.parameters(), lr=disc_lr)
+    mse = lambda t, v: ((t - v) ** 2).mean()
+    for p in disc.parameters():                                                     # requires_grad(discriminator, False) :136
+        p.requires_grad_(False)
+    y = forward(x, context, params, cfg)
+    rec = (y - target).abs().mean()                                                 # :149
+    adv = mse(disc(y.contiguous().float())[-1], 1.0)                                # :153-155
+    g_loss = rec + adv_weight * adv                                                 # :159
+    g_opt.zero_grad()
+    g_loss.backward()
+    g_grads = {k: (p.grad.clone() if p.grad is not None else torch.zeros_like(p)) for k, p in params.items()}
+    g_opt.step()                                                                    # :166-168
+    for p in disc.parameters():                                                     # :172-173
+        p.requires_grad_(True)
+    d_opt.zero_grad()
+    with torch.no_grad():
+        y2 = forward(x, context, params, cfg)                                       # :175-176
+    d_fake = mse(disc(y2.contiguous().detach())[-1], 0.0)                           # :179-181
+    d_fake.backward()
+    d_real = mse(disc(target.contiguous().detach())[-1], 1.0)                       # :182-184
+    d_real.backward()
+    d_grads = {k: p.grad.clone() for k, p in disc.named_parameters()}
+    d_opt.step()                                                                    # :193
+    return dict(rec=rec.detach(), adv=adv.detach(), d_fake=d_fake.detach(), d_real=d_real.detach(), g_grads=g_grads,
+                d_grads=d_grads, params={k: p.detach() for k, p in params.items()}, output=y.detach())

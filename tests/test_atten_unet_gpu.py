@@ -135,6 +135,75 @@ def test_full_size_cfg2_matches_golden_and_peer(petsyn):
     assert abs(tot ** 0.5 - gtot) <= max(2.0 * abs(tot_p ** 0.5 - gtot), 2e-2 * gtot)
 
 
+def test_adversarial_step_matches_oracle(petsyn):
+    """AttenUNetTrainer with the reference's discriminator (``PatchDiscriminator(**training.json['discriminator'])``, 64
+    channels x 3 layers) and adv_weight 0.1: the G phase's adversarial term and the two-backward D phase of
+    train_unet.py:136-193, against the CPU oracle step -- losses, generator gradients (L1 + adversarial), discriminator
+    gradients, and both Adam updates (eager and CUDA-graph replay)."""
+    from oracle import monai_stub
+    from petsyn_b200.train import AttenUNetTrainer
+    DCFG = dict(spatial_dims=3, num_channels=64, num_layers_d=3, in_channels=1, out_channels=1)   # training.json:40-46
+    shape, seed = (2, 32, 48, 32), 13
+    x, ctx, tgt = synth(shape, seed)
+
+    def make():
+        torch.manual_seed(seed)
+        g = petsyn.AttenUNet(**OA.TRAINING_JSON)
+        OA.randomize_(g.named_parameters(), seed=seed)
+        torch.manual_seed(seed + 1)
+        d = petsyn.PatchDiscriminator(**DCFG)
+        return g, d
+
+    gen, disc = make()
+    assert [k for k in disc.state_dict()][:3] == ["initial_conv.conv.weight", "initial_conv.conv.bias", "0.conv.weight"]
+    od = monai_stub.PatchDiscriminator(**DCFG).train()
+    od.load_state_dict(disc.state_dict())                       # same keys and shapes as the (stubbed) reference class
+    sd = {k: v.detach().clone() for k, v in gen.state_dict().items()}
+    ref = OA.adversarial_step(x, ctx, tgt, sd, od, adv_weight=0.1, base_lr=5e-4, disc_lr=1e-4)
+
+    for mode in ("eager", "graph"):
+        gen, disc = make()
+        gen, disc = gen.cuda().train(), disc.cuda().train()
+        tr = AttenUNetTrainer(gen, lr=5e-4, example_input=x.cuda(), discriminator=disc, adv_weight=0.1, disc_lr=1e-4)
+        if mode == "graph":
+            tr.capture()
+        loss = tr.step(x.cuda(), ctx.cuda(), tgt.cuda())
+        torch.cuda.synchronize()
+        print(mode, "rec", loss.item(), ref["rec"].item(), "adv", tr.loss_adv.item(), ref["adv"].item(), "d_fake",
+              tr.loss_d_fake.item(), ref["d_fake"].item(), "d_real", tr.loss_d_real.item(), ref["d_real"].item())
+        assert abs(loss.item() - ref["rec"].item()) <= 2e-3
+        assert abs(tr.loss_adv.item() - ref["adv"].item()) <= 3e-2 * ref["adv"].item()
+        assert abs(tr.loss_d_fake.item() - ref["d_fake"].item()) <= 3e-2 * ref["d_fake"].item() + 1e-3
+        assert abs(tr.loss_d_real.item() - ref["d_real"].item()) <= 3e-2 * ref["d_real"].item() + 1e-3
+        # generator gradients of the step (still in the arena): L1 + adv_weight * adversarial
+        gn = sum(p.grad.double().norm().item() ** 2 for p in gen.parameters()) ** 0.5
+        gn_ref = sum(v.double().norm().item() ** 2 for v in ref["g_grads"].values()) ** 0.5
+        assert abs(gn - gn_ref) <= 3e-2 * gn_ref, (gn, gn_ref)
+        big = sorted(ref["g_grads"], key=lambda k: ref["g_grads"][k].norm().item(), reverse=True)[:6]
+        named = dict(gen.named_parameters())
+        for k in big:
+            a, b = named[k].grad.double().cpu().flatten(), ref["g_grads"][k].double().flatten()
+            assert (torch.dot(a, b) / (a.norm() * b.norm())).item() > 0.98, k
+        # discriminator gradients: sum of the two backward calls
+        dn = dict(disc.named_parameters())
+        tot = tot_ref = 0.0
+        for k, g_ref in ref["d_grads"].items():
+            a, b = dn[k].grad.double().cpu().flatten(), g_ref.double().flatten()
+            tot += (a ** 2).sum().item(); tot_ref += (b ** 2).sum().item()
+            if b.norm().item() > 1e-3 * max(v.norm().item() for v in ref["d_grads"].values()):
+                assert (torch.dot(a, b) / (a.norm() * b.norm())).item() > 0.97, k
+        assert abs(tot ** 0.5 - tot_ref ** 0.5) <= 5e-2 * tot_ref ** 0.5, (tot ** 0.5, tot_ref ** 0.5)
+        # both optimisers stepped: first Adam step moves every weight with a non-zero gradient by ~lr
+        for k, p_ref in ref["params"].items():
+            moved = (named[k].detach().cpu() - sd[k]).abs().max().item()
+            moved_ref = (p_ref - sd[k]).abs().max().item()
+            assert abs(moved - moved_ref) <= 0.25 * 5e-4 + 1e-9, (k, moved, moved_ref)
+        d0 = dict(od.named_parameters())
+        dmoved = max((dn[k].detach().cpu() - d0[k].detach()).abs().max().item() for k in d0)
+        assert dmoved <= 0.5 * 1e-4, dmoved                     # D followed the oracle's Adam(disc_lr) step
+        assert int(tr.step_dev.item()) == 1 and int(tr.d_step_dev.item()) == 1
+
+
 def test_contracts(petsyn):
     cfg = dict(OA.TRAINING_JSON)
     with pytest.raises(ValueError):

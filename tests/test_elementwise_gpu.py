@@ -19,7 +19,7 @@ def test_batchnorm_act_concat_fwd_bwd(petsyn):
     gamma = (torch.rand(c, generator=g) + 0.5).to(DEV)
     beta = torch.randn(c, generator=g).to(DEV)
     rm, rv = torch.zeros(c, device=DEV), torch.ones(c, device=DEV)
-    sums = torch.zeros(2 * c, device=DEV)
+    sums = torch.zeros(2 * c, device=DEV, dtype=torch.float64)
     scale, shift, mean, rstd = (torch.empty(c, device=DEV) for _ in range(4))
     ops.bn_stats(z, sums, rows, c)
     ops.bn_finalize(sums, gamma, beta, rm, rv, scale, shift, mean, rstd, rows, c, 1e-5, 0.1, True)
@@ -40,7 +40,7 @@ def test_batchnorm_act_concat_fwd_bwd(petsyn):
     g1 = torch.randn(rows, c, generator=g).to(DEV).to(torch.bfloat16)
     g2buf = torch.randn(rows, 2 * c, generator=g).to(DEV).to(torch.bfloat16)
     (a_ref * g1.float()).sum().add((s_ref * g2buf[:, c:].float()).sum()).backward()
-    bsums = torch.zeros(2 * c, device=DEV)
+    bsums = torch.zeros(2 * c, device=DEV, dtype=torch.float64)
     dz = torch.empty(rows, c, dtype=torch.bfloat16, device=DEV)
     dgamma, dbeta = torch.empty(c, device=DEV), torch.empty(c, device=DEV)
     ops.norm_act_bwd(z, scale, shift, mean, rstd, gamma, g1, c, 0, ops.ACT_LRELU, g2buf, 2 * c, c, ops.ACT_RELU, 0.2,

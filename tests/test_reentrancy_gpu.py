@@ -64,12 +64,15 @@ def test_encoder_two_forwards_one_backward_matches_oracle(petsyn):
     tot, tot_ref = _gnorm(ours.values()), _gnorm(ref.values())
     tot_seq = _gnorm(seq.values())
     print("E phase: loss", loss.item(), lo.item(), "grad-norm ours", tot, "sequential", tot_seq, "oracle", tot_ref)
-    assert abs(tot - tot_seq) <= 5e-3 * tot_seq
+    # reductions are reproducible (csrc/det_reduce.cuh), so the restored-activation path must give the SAME numbers as the
+    # interleaved one, not merely close ones (fp32 sums of the two nodes' gradients are formed in the same order by autograd)
+    assert abs(tot - tot_seq) <= 1e-6 * tot_seq
     assert abs(tot - tot_ref) <= 5e-2 * tot_ref
     big = sorted(ref, key=lambda k: ref[k].norm().item(), reverse=True)[:8]
     for k in big:
-        assert _cos(ours[k], ref[k]) > 0.98, (k, _cos(ours[k], ref[k]))
-        assert _cos(ours[k], seq[k]) > 0.98, (k, _cos(ours[k], seq[k]))
+        # against the fp32 oracle: this encoder ends in 2x2x2 = 8-voxel InstanceNorms, its gradients are ill-conditioned
+        assert _cos(ours[k], ref[k]) > 0.95, (k, _cos(ours[k], ref[k]))
+        assert _cos(ours[k], seq[k]) > 0.999999, (k, _cos(ours[k], seq[k]))
 
 
 def test_discriminator_no_grad_outputs_do_not_alias(petsyn):
