@@ -400,8 +400,8 @@ def run_petsyn_bmgan(args, cfg_name, shape, batch):
     trainer.step(*resident[0])
     torch.cuda.synchronize()
     launches = ops.launch_count() - n0
-    if not args.no_graph and world == 1:
-        trainer.capture()
+    if not args.no_graph:
+        trainer.capture()                  # one graph on one GPU; graph segments around the collectives when data parallel
     for i in range(max(args.warmup, 3)):
         trainer.step(*resident[i % pool])
     barrier()
@@ -437,6 +437,7 @@ def run_petsyn_bmgan(args, cfg_name, shape, batch):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_total, ms_e2e = t.tolist()
+    in_sync = replicas_in_sync([trainer.garena.p, trainer.darena.p] + ([trainer.earena.p] if enc is not None else []), world, dev)
     if rank == 0:
         peaks = {}
         try:
@@ -472,6 +473,7 @@ def run_petsyn_bmgan(args, cfg_name, shape, batch):
                          "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback",
                          "generator_fwd_gflop": gf / 1e9, "discriminator_fwd_gflop": df / 1e9},
             "final_losses": {"adv": final[0], "l1": final[1], "d_fake": final[2], "d_real": final[3]},
+            "replicas_in_sync": in_sync,
         }
         if not args.no_cpu_baseline and world == 1:
             v, sample, cores, _ = cpu_bmgan_steps(cfg_name, shape, batch, 1, 0, budget_s=30.0)
@@ -709,6 +711,98 @@ def incumbent_atten(shape, batch, dev, steps=6):
     return out
 
 
+def extra_workloads(args, rank, world, dev):
+    """Two short side measurements carried by the default line so that the driver's 1/2/4/8-GPU runs also record BASELINE
+    configs[2] (BMGAN adversarial step, batch-sharded data parallel, per-GPU batch 1) and configs[3] (full-resolution
+    160x192x160 inference, independent replicas): ``{"bmgan_dp": {...}, "infer_s3": {...}}``.  Every rank runs them (the BMGAN
+    step holds the gradient all-reduces); a failure is reported in the object instead of killing the headline line, after all
+    ranks agreed that the set-up worked."""
+    import torch
+    import torch.distributed as dist
+
+    import petsyn
+    from petsyn_b200.train import BmganTrainer
+    out = {}
+
+    def agreed(ok: bool) -> bool:
+        flag = torch.tensor([1 if ok else 0], device=dev)
+        if world > 1:
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        return bool(flag.item())
+
+    def timed(fn, steps):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for i in range(steps):
+            fn(i)
+        b.record()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()) / steps
+
+    # ---- configs[2]: BMGAN adversarial step (G + E + D phases), per-GPU batch 1, 96x128x96 ----
+    shape, steps = (96, 128, 96), 6
+    trainer = err = None
+    try:
+        torch.manual_seed(777)
+        gen = petsyn.dense_unet_generator().to(dev).train()
+        disc = petsyn.patch_discriminator().to(dev).train()
+        enc = petsyn.ResNet_encoder().to(dev).train()
+        batches = [tuple(t.to(dev) for t in bmgan_batch(shape, 777 + 1000 * rank + i, 1)) for i in range(3)]
+        trainer = BmganTrainer(gen, disc, lr=2e-4, example_input=batches[0][0], enc=enc)
+    except Exception as e:  # pragma: no cover
+        err = f"{type(e).__name__}: {e}"
+    if agreed(err is None):
+        for i in range(2):
+            trainer.step(*batches[i % 3])
+        trainer.capture()
+        for i in range(3):
+            trainer.step(*batches[i % 3])
+        ms = timed(lambda i: trainer.step(*batches[i % 3]), steps)
+        sync = replicas_in_sync([trainer.garena.p, trainer.darena.p, trainer.earena.p], world, dev)
+        gf, df, ef = trainer.geng.flops_algorithmic, trainer.deng.flops_algorithmic, trainer.eeng.flops_algorithmic
+        flops = 5.0 * gf + 8.0 * df + 6.0 * ef
+        out["bmgan_dp"] = {"workload": "bmgan_adv_step_s2", "metric": "BMGAN adversarial-step throughput (G, E, D phases of "
+                           "train_bmgan.py:141-200, LPIPS dropped)", "value": world * 1 / (ms * 1e-3), "unit": UNIT,
+                           "n_gpus": world, "steps": steps, "ms_per_step": ms, "per_gpu_batch": 1, "global_batch": world,
+                           "scaling": "weak", "cuda_graph": "segments" if world > 1 else True, "replicas_in_sync": sync,
+                           "grad_bytes_allreduced_per_step": 4 * (trainer.garena.numel + trainer.earena.numel),
+                           "algorithmic_tflops_per_gpu": flops / (ms * 1e-3) / 1e12}
+    else:
+        out["bmgan_dp"] = {"error": err or "another rank failed to build the workload"}
+    del trainer
+    torch.cuda.empty_cache()
+
+    # ---- configs[3]: full-resolution inference, 160x192x160, micro-batch 2, replicas ----
+    model = err = None
+    try:
+        model, x_host, extra_host = _infer_model_and_inputs("atten", (160, 192, 160), 2, dev, 777 + rank)
+        xs = [x_host.to(dev), (x_host * 0.5).to(dev)]
+        extra = tuple(t.to(dev) for t in extra_host)
+    except Exception as e:  # pragma: no cover
+        err = f"{type(e).__name__}: {e}"
+    if agreed(err is None):
+        with torch.no_grad():
+            for i in range(3):
+                model(xs[i % 2], *extra)
+            ms = timed(lambda i: model(xs[i % 2], *extra), 6)
+        out["infer_s3"] = {"workload": "infer_atten_unet_s3", "metric": INFER_METRIC, "value": world * 2 / (ms * 1e-3),
+                           "unit": UNIT, "n_gpus": world, "steps": 6, "ms_per_step": ms, "volume": [160, 192, 160],
+                           "per_gpu_batch": 2, "parallelism": f"replicas x{world} (no collective)"}
+    else:
+        out["infer_s3"] = {"error": err or "another rank failed to build the workload"}
+    del model
+    torch.cuda.empty_cache()
+    return out
+
+
 def step_roofline(tape, n_params, out_voxels, peak_tf, peak_bw):
     """Step-level roofline: sum over the ops of the training step of max(FLOPs / tensor peak, minimum bytes /
     HBM bandwidth).  FLOPs are algorithmic (direct convolution); minimum bytes are a bf16 read-once of every input and a
@@ -905,6 +999,10 @@ def run_petsyn_atten(args, shape, batch, adv=False):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_total, ms_e2e, ms_loader = t.tolist()
+    in_sync = replicas_in_sync([trainer.arena.p] + ([trainer.darena.p] if adv else []), world, dev)
+    extras = {}
+    if not args.no_extras and args.workload == "atten_unet_train_cfg2":
+        extras = extra_workloads(args, rank, world, dev)
     if rank == 0:
         peaks = {}
         try:
@@ -963,8 +1061,9 @@ def run_petsyn_atten(args, shape, batch, adv=False):
             "step_breakdown": {"per_op_class_ms": {k: round(v, 4) for k, v in sorted(by_kind.items(), key=lambda kv: -kv[1])},
                                "model_tflops_algorithmic": ach, "forward_gflop": fwd / 1e9,
                                "model_frac_of_tensor_peak": ach / peak_tf},
-            "final_loss": final,
+            "final_loss": final, "replicas_in_sync": in_sync,
         }
+        line.update(extras)
         sr = step_roofline(tape, trainer.arena.numel, vox, peak_tf, peak_bw)
         sr.update(measured_ms=ms, frac=sr["t_roof_ms"] / ms,
                   what="sum over the ops of the step of max(algorithmic FLOPs / tensor peak, minimum bf16 bytes / HBM peak) "
@@ -1170,6 +1269,19 @@ def run_petsyn_infer(args, family, shape, micro):
         dist.destroy_process_group()
 
 
+def replicas_in_sync(arenas, world, dev):
+    """After the timed loop: every rank's parameters must be identical (data parallel = the same weights everywhere).  Each
+    rank sums its parameter arenas in float64; the sums are all-gathered and compared bit for bit."""
+    import torch
+    import torch.distributed as dist
+    mine = torch.stack([a.double().sum() for a in arenas] + [a.double().abs().sum() for a in arenas]).to(dev)
+    if world == 1:
+        return True
+    allv = [torch.zeros_like(mine) for _ in range(world)]
+    dist.all_gather(allv, mine)
+    return all(torch.equal(v, allv[0]) for v in allv)
+
+
 def count_launches(trainer, batch) -> int:
     """Kernels of OUR library launched by one trainer.step() (petsyn_launch_count() delta)."""
     import torch
@@ -1191,6 +1303,8 @@ def main():
     ap.add_argument("--workload", default="atten_unet_train_cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-incumbent", action="store_true", help="skip the PyTorch/cuDNN same-GPU incumbent leg")
+    ap.add_argument("--no-extras", action="store_true",
+                    help="default workload only: skip the short bmgan_dp / infer_s3 side measurements")
     ap.add_argument("--no-graph", action="store_true", help="launch kernels eagerly instead of replaying a CUDA graph")
     ap.add_argument("--batch", type=int, default=1, help="inference workloads: volumes per step and GPU (1..16)")
     ap.add_argument("--profile-one-step", action="store_true",

@@ -9,7 +9,8 @@ from . import ops  # noqa: F401
 from .unet_model import UnetGenerator3d, UnetSkipConnectionBlock3d  # noqa: F401
 from .atten_unet_model import AttenUNet, DiffusionModelEncoder  # noqa: F401
 from .data import PairVolumeLoader, SyntheticPairSource, volume_prepare  # noqa: F401
+from .causal_model import Decoder, DiffusionModelDecoder, kl_divergence, reparameterize  # noqa: F401
 from .bmgan_model import PatchDiscriminator, ResNet_encoder, dense_unet_generator, patch_discriminator  # noqa: F401
 
-__all__ = ["AttenUNet", "DiffusionModelEncoder", "UnetGenerator3d", "UnetSkipConnectionBlock3d", "dense_unet_generator", "patch_discriminator", "PatchDiscriminator", "ResNet_encoder", "ops",
+__all__ = ["AttenUNet", "DiffusionModelEncoder", "UnetGenerator3d", "UnetSkipConnectionBlock3d", "dense_unet_generator", "patch_discriminator", "PatchDiscriminator", "Decoder", "DiffusionModelDecoder", "kl_divergence", "reparameterize", "ResNet_encoder", "ops",
            "PairVolumeLoader", "SyntheticPairSource", "volume_prepare"]

@@ -66,6 +66,7 @@ class NormActDesc(C.Structure):
         ("sums_prezeroed", C.c_int32),
         ("z_cstride", C.c_int32), ("z_coff", C.c_int32), ("dz_cstride", C.c_int32), ("dz_coff", C.c_int32),
         ("extra", C.c_void_p), ("extra_cstride", C.c_int32), ("extra_coff", C.c_int32),
+        ("dz_colsum_coff", C.c_int32), ("dz_colsum_c", C.c_int32),
     ]
 
 
@@ -99,6 +100,7 @@ SIGNATURES = {
     "petsyn_conv_dgrad": (_i32, [_vp, _vp, _vp, _vp, _vp]),
     "petsyn_conv_dgrad_accumulate": (_i32, [_vp, _vp, _vp, _vp, _vp]),
     "petsyn_conv_wgrad": (_i32, [_vp, _vp, _vp, _vp, _vp, _i32, _vp]),
+    "petsyn_conv_wgrad_bias": (_i32, [_vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _i32, _vp]),
     "petsyn_stem_col2im_k4s2": (_i32, [_vp, _vp, _i32, _i32, _i32, _i32, _vp]),
     "petsyn_concat_latent": (_i32, [_vp, _vp, _vp, _i64, _i32, _i32, _i32, _vp]),
     "petsyn_take_channel0": (_i32, [_vp, _vp, _i64, _i32, _vp]),

@@ -45,9 +45,27 @@ class _Container(nn.Module):
 class _Convolution(nn.Sequential):
     """MONAI ``Convolution(conv_only=True)``: one child named ``conv``."""
 
-    def __init__(self, cin: int, cout: int, k: int):
+    def __init__(self, cin: int, cout: int, k: int, stride: int = 1):
         super().__init__()
-        self.add_module("conv", nn.Conv3d(cin, cout, k, stride=1, padding=(k - 1) // 2, bias=True))
+        self.add_module("conv", nn.Conv3d(cin, cout, k, stride=stride, padding=(k - 1) // 2, bias=True))
+
+
+class Downsample(_Container):
+    """``Downsample(use_conv=True)`` (atten_unet_model.py:464-507): ``op`` = Conv3d(k3, stride 2, padding 1)."""
+
+    def __init__(self, channels: int):
+        super().__init__()
+        self.num_channels = self.out_channels = channels
+        self.op = _Convolution(channels, channels, 3, stride=2)
+
+
+class Upsample(_Container):
+    """``Upsample(use_conv=True)`` (atten_unet_model.py:510-562): nearest x2, then ``conv`` = Conv3d(k3, padding 1)."""
+
+    def __init__(self, channels: int, out_channels: Optional[int] = None):
+        super().__init__()
+        self.num_channels, self.out_channels = channels, out_channels or channels
+        self.conv = _Convolution(channels, self.out_channels, 3)
 
 
 class ResnetBlock(_Container):
@@ -76,7 +94,7 @@ class CrossAttention(_Container):
         super().__init__()
         inner = heads * head_channels
         cross_attention_dim = cross_attention_dim if cross_attention_dim is not None else query_dim
-        self.num_heads = heads
+        self.num_heads, self.head_channels = heads, head_channels
         self.to_q = nn.Linear(query_dim, inner, bias=False)
         self.to_k = nn.Linear(cross_attention_dim, inner, bias=False)
         self.to_v = nn.Linear(cross_attention_dim, inner, bias=False)
@@ -115,14 +133,16 @@ class SpatialTransformer(_Container):
 
 
 class _DownBlock(_Container):
-    def __init__(self, cin, cout, nres, groups, eps, add_downsample, attn: Optional[dict]):
+    def __init__(self, cin, cout, nres, groups, eps, add_downsample, attn: Optional[dict], resblock_updown: bool = True):
         super().__init__()
         resnets = [ResnetBlock(cin if i == 0 else cout, cout, norm_num_groups=groups, norm_eps=eps) for i in range(nres)]
         if attn is not None:      # the reference's CrossAttn blocks register `attentions` before `resnets`
             self.attentions = nn.ModuleList([SpatialTransformer(cout, **attn) for _ in range(nres)])
         self.resnets = nn.ModuleList(resnets)
-        self.downsampler = (ResnetBlock(cout, cout, down=True, norm_num_groups=groups, norm_eps=eps)
-                            if add_downsample else None)
+        self.downsampler = None
+        if add_downsample:        # atten_unet_model.py:712-730: a down-sampling ResnetBlock, or Downsample(use_conv=True)
+            self.downsampler = (ResnetBlock(cout, cout, down=True, norm_num_groups=groups, norm_eps=eps)
+                                if resblock_updown else Downsample(cout))
 
 
 class _MidBlock(_Container):
@@ -134,7 +154,7 @@ class _MidBlock(_Container):
 
 
 class _UpBlock(_Container):
-    def __init__(self, cin, prev, cout, nres, groups, eps, add_upsample, attn: Optional[dict]):
+    def __init__(self, cin, prev, cout, nres, groups, eps, add_upsample, attn: Optional[dict], resblock_updown: bool = True):
         super().__init__()
         resnets = []
         for i in range(nres):
@@ -144,8 +164,10 @@ class _UpBlock(_Container):
         if attn is not None:
             self.attentions = nn.ModuleList([SpatialTransformer(cout, **attn) for _ in range(nres)])
         self.resnets = nn.ModuleList(resnets)
-        self.upsampler = (ResnetBlock(cout, cout, up=True, norm_num_groups=groups, norm_eps=eps)
-                          if add_upsample else None)
+        self.upsampler = None
+        if add_upsample:          # atten_unet_model.py:1148-1165
+            self.upsampler = (ResnetBlock(cout, cout, up=True, norm_num_groups=groups, norm_eps=eps)
+                              if resblock_updown else Upsample(cout))
 
 
 def _rep(v, n):
@@ -186,16 +208,21 @@ class AttenUNet(nn.Module):
                              "as `num_channels`.")
         if spatial_dims != 3 or in_channels != 1 or out_channels != 1:
             raise NotImplementedError("petsyn AttenUNet implements the reference use: 3-D, one channel in, one out")
-        if not (resblock_updown and with_conditioning) or transformer_num_layers != 1 or num_class_embeds is not None \
-                or dropout_cattn != 0.0:
-            raise NotImplementedError("petsyn AttenUNet implements the training.json family: resblock_updown=True, "
-                                      "with_conditioning=True, transformer_num_layers=1, no class embeddings/dropout")
-        for lvl, a in enumerate(attention_levels):
-            if a and num_head_channels[lvl] != 32:
-                raise NotImplementedError("attention levels need num_head_channels == 32 (the attention kernel's head size)")
+        if not with_conditioning or transformer_num_layers != 1 or num_class_embeds is not None or dropout_cattn != 0.0:
+            raise NotImplementedError("petsyn AttenUNet implements with_conditioning=True (cross-attention transformer blocks; "
+                                      "the unconditioned AttentionBlock family is not built), transformer_num_layers=1, no class "
+                                      "embeddings / dropout")
+        for lvl, a in enumerate(list(attention_levels) + [True]):          # the middle block always attends
+            hc = num_head_channels[min(lvl, n - 1)]
+            if a and hc not in (8, 16, 32):
+                raise NotImplementedError("attention needs num_head_channels in {8, 16, 32} (heads narrower than the attention "
+                                          "kernel's 32 channels are zero-padded)")
+            if a and num_channels[min(lvl, n - 1)] % hc:
+                raise ValueError("num_channels must be divisible by num_head_channels at attention levels")
         self.cfg = dict(num_channels=list(num_channels), num_res_blocks=num_res_blocks,
                         attention_levels=list(attention_levels), num_head_channels=num_head_channels,
-                        norm_num_groups=norm_num_groups, norm_eps=norm_eps, cross_attention_dim=cross_attention_dim)
+                        norm_num_groups=norm_num_groups, norm_eps=norm_eps, cross_attention_dim=cross_attention_dim,
+                        resblock_updown=bool(resblock_updown))
         self.in_channels, self.out_channels = in_channels, out_channels
         self.block_out_channels = num_channels
         self.with_conditioning = with_conditioning
@@ -213,12 +240,10 @@ class AttenUNet(nn.Module):
         out_c = ch[0]
         for i in range(n):
             in_c, out_c = out_c, ch[i]
-            self.down_blocks.append(_DownBlock(in_c, out_c, num_res_blocks[i], g, e, i != n - 1, attn_kw(i)))
+            self.down_blocks.append(_DownBlock(in_c, out_c, num_res_blocks[i], g, e, i != n - 1, attn_kw(i), resblock_updown))
         mid_attn = dict(heads=ch[-1] // num_head_channels[-1], head_channels=num_head_channels[-1],
                         num_layers=transformer_num_layers, norm_num_groups=g, norm_eps=e,
                         cross_attention_dim=cross_attention_dim)
-        if num_head_channels[-1] != 32:
-            raise NotImplementedError("the middle block's attention needs num_head_channels[-1] == 32")
         self.middle_block = _MidBlock(ch[-1], g, e, mid_attn)
         self.up_blocks = nn.ModuleList([])
         rch = list(reversed(ch))
@@ -227,7 +252,8 @@ class AttenUNet(nn.Module):
             prev, out_c = out_c, rch[i]
             in_c = rch[min(i + 1, n - 1)]
             lvl = n - 1 - i
-            self.up_blocks.append(_UpBlock(in_c, prev, out_c, num_res_blocks[lvl] + 1, g, e, i != n - 1, attn_kw(lvl)))
+            self.up_blocks.append(_UpBlock(in_c, prev, out_c, num_res_blocks[lvl] + 1, g, e, i != n - 1, attn_kw(lvl),
+                                           resblock_updown))
         self.out = nn.Sequential(nn.GroupNorm(g, ch[0], eps=e, affine=True), nn.SiLU(),
                                  zero_module(_Convolution(ch[0], out_channels, 3)))
         self._engines: Dict[Tuple, "_AttenEngine"] = {}
@@ -352,7 +378,11 @@ class _AttenEngine(_EngineBase):
                     h = self._resnet(rb, h, i, slot[sk], f"down{i}.{j}")
                 sk += 1
             if blk.downsampler is not None:
-                h = self._resnet(blk.downsampler, h, i, slot[sk], f"down{i}.ds", down=True)
+                if isinstance(blk.downsampler, ResnetBlock):
+                    h = self._resnet(blk.downsampler, h, i, slot[sk], f"down{i}.ds", down=True)
+                else:                                   # Downsample(use_conv=True): Conv3d k3 s2 p1 straight into the slot
+                    self._conv(h, blk.downsampler.op.conv, ksize=3, stride=2, pad=1, name=f"down{i}.ds", out=slot[sk])
+                    h = slot[sk]
                 sk += 1
         # ---- middle ----
         mb = net.middle_block
@@ -371,7 +401,13 @@ class _AttenEngine(_EngineBase):
                 else:
                     h = self._resnet(rb, cats[i][j].sl(), lvl, nxt, f"up{i}.{j}")
             if blk.upsampler is not None:
-                h = self._resnet(blk.upsampler, h, lvl, cats[i + 1][0].sl(0, ch[lvl]), f"up{i}.us", up=True)
+                nxt_h = cats[i + 1][0].sl(0, ch[lvl])
+                if isinstance(blk.upsampler, ResnetBlock):
+                    h = self._resnet(blk.upsampler, h, lvl, nxt_h, f"up{i}.us", up=True)
+                else:                                   # Upsample(use_conv=True): nearest x2 + Conv3d k3 (never materialised)
+                    self._conv(h, blk.upsampler.conv.conv, ksize=3, stride=1, pad=1, op=ops.OP_UPCONV, name=f"up{i}.us",
+                               out=nxt_h)
+                    h = nxt_h
         # ---- head ----
         a = B(0, ch[0], "out.a")
         gn = NormActOp(h, "group", ops.ACT_SILU, [a.sl()], gn=net.out[0])
@@ -443,8 +479,8 @@ class _AttenEngine(_EngineBase):
         t.add(NormActOp(c2.z, "none", ops.ACT_NONE, [out], res=res, no_bwd=True))
         return out
 
-    def _linear(self, x: Sl, lin: nn.Linear, name: str, out: Optional[Sl] = None) -> ConvOp:
-        return self._conv(x, lin, ksize=1, stride=1, pad=0, name=name, out=out)
+    def _linear(self, x: Sl, lin: nn.Linear, name: str, out: Optional[Sl] = None, **kw) -> ConvOp:
+        return self._conv(x, lin, ksize=1, stride=1, pad=0, name=name, out=out, **kw)
 
     def _transformer(self, st: SpatialTransformer, x: Sl, lvl: int, dst: Optional[Sl], name: str) -> Sl:
         """SpatialTransformer.forward (atten_unet_model.py:315-343) with one BasicTransformerBlock (:225-235)."""
@@ -463,12 +499,26 @@ class _AttenEngine(_EngineBase):
         ln1 = LayerNormOp(t0, n1, blk.norm1)
         t.add(ln1)
         self._bind += [(ln1, "grad_gamma", blk.norm1.weight), (ln1, "grad_beta", blk.norm1.bias)]
-        qkv = T(3 * inner, "qkv")
-        for idx, lin in enumerate((blk.attn1.to_q, blk.attn1.to_k, blk.attn1.to_v)):
-            self._linear(n1.sl(), lin, f"{name}.qkv{idx}", out=qkv.sl(idx * inner, inner))
-        o = T(inner, "o")
-        t.add(AttentionOp(qkv, o, heads, L))
-        p = self._linear(o.sl(), blk.attn1.to_out[0], name + ".to_out").z
+        hd = blk.attn1.head_channels
+        if hd == 32:
+            qkv = T(3 * inner, "qkv")
+            for idx, lin in enumerate((blk.attn1.to_q, blk.attn1.to_k, blk.attn1.to_v)):
+                self._linear(n1.sl(), lin, f"{name}.qkv{idx}", out=qkv.sl(idx * inner, inner))
+            o = T(inner, "o")
+            t.add(AttentionOp(qkv, o, heads, L))
+            p = self._linear(o.sl(), blk.attn1.to_out[0], name + ".to_out").z
+        else:
+            # heads of 8 / 16 channels (the reference's default num_head_channels = 8): every head is zero-padded to the
+            # attention kernel's 32 channels through the weight staging of to_q / to_k / to_v (zero output rows) and to_out
+            # (zero input columns); zero channels change neither q k^T nor p v, the softmax scale stays 1 / sqrt(hd)
+            wide = heads * 32
+            at = [h_ * 32 + j for h_ in range(heads) for j in range(hd)]
+            qkv = T(3 * wide, "qkv")
+            for idx, lin in enumerate((blk.attn1.to_q, blk.attn1.to_k, blk.attn1.to_v)):
+                self._linear(n1.sl(), lin, f"{name}.qkv{idx}", out=qkv.sl(idx * wide, wide), cout_pad=wide, out_index=at)
+            o = T(wide, "o")
+            t.add(AttentionOp(qkv, o, heads, L, true_head_dim=hd))
+            p = self._conv(o.sl(), blk.attn1.to_out[0], ksize=1, stride=1, pad=0, name=name + ".to_out", in_index=at).z
         t1 = T(inner, "t1")
         t.add(NormActOp(p, "none", ops.ACT_NONE, [t1.sl()], res=t0.sl()))
         cb = CovariateBiasOp(t1, self, blk.attn2.to_v, blk.attn2.to_out[0], L)

@@ -232,7 +232,10 @@ template <int K3, bool TRANSPOSED, int NS>
 __global__ void __launch_bounds__(256) unpack_wgrad_kernel(const float* __restrict__ scratch, float* __restrict__ dw,
                                                            const InvEntryDev* __restrict__ inv, int A, int B, int nsubs,
                                                            int max_taps, int rows, int kc_pad, int accumulate,
-                                                           int nsplit) {
+                                                           int nsplit, const double* __restrict__ dbias_acc,
+                                                           float* __restrict__ dbias, int nbias) {
+  if (dbias != nullptr && blockIdx.x == 0 && blockIdx.y == 0)       // bias gradient: double accumulator -> fp32 slot
+    for (int i = threadIdx.x; i < nbias; i += 256) dbias[i] = accumulate ? dbias[i] + (float)dbias_acc[i] : (float)dbias_acc[i];
   constexpr int TA = TRANSPOSED ? 64 : 4, TB = TRANSPOSED ? 4 : 64;
   constexpr int kAP = TB + 1;                        // pitch along a inside a slot
   constexpr int kSlotPitch = (TA * kAP) | 1;
@@ -259,12 +262,19 @@ __global__ void __launch_bounds__(256) unpack_wgrad_kernel(const float* __restri
     const int64_t image = (int64_t)nsubs * rows * ldb;
     for (int sub = 0; sub < nsubs; ++sub) {
       const float* src = scratch + ((int64_t)sub * rows + row) * ldb + col;
-#pragma unroll 4
-      for (int t = 0; t < max_taps; ++t) {
-        float v = 0.f;
-        if (ok)
-          for (int k = 0; k < nsplit; ++k) v += __ldg(src + k * image + (int64_t)t * kc_pad);
-        dst[(sub * max_taps + t) * kSlotPitch] = v;
+      if (nsplit == 1) {
+#pragma unroll 8
+        for (int t = 0; t < max_taps; ++t)
+          dst[(sub * max_taps + t) * kSlotPitch] = ok ? __ldg(src + (int64_t)t * kc_pad) : 0.f;
+      } else {
+        for (int t = 0; t < max_taps; ++t) {
+          float v = 0.f;
+          if (ok) {
+#pragma unroll 8
+            for (int k = 0; k < nsplit; ++k) v += __ldg(src + k * image + (int64_t)t * kc_pad);   // split order: reproducible
+          }
+          dst[(sub * max_taps + t) * kSlotPitch] = v;
+        }
       }
     }
   }
@@ -291,7 +301,11 @@ __global__ void __launch_bounds__(256) unpack_wgrad_small_kernel(const float* __
                                                                  float* __restrict__ dw,
                                                                  const InvEntryDev* __restrict__ inv, int Cout, int Cin,
                                                                  int k3, int npad, int tpm, int m_tiles, int accumulate,
-                                                                 int nsplit, int64_t image) {
+                                                                 int nsplit, int64_t image,
+                                                                 const double* __restrict__ dbias_acc,
+                                                                 float* __restrict__ dbias, int nbias) {
+  if (dbias != nullptr && blockIdx.x == 0)
+    for (int i = threadIdx.x; i < nbias; i += 256) dbias[i] = accumulate ? dbias[i] + (float)dbias_acc[i] : (float)dbias_acc[i];
   const int total = Cout * Cin * k3;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int k = i % k3;
@@ -302,7 +316,8 @@ __global__ void __launch_bounds__(256) unpack_wgrad_small_kernel(const float* __
     for (int q = 0; q < e.n; ++q) {
       const int mt = e.tap[q] / tpm, tl = e.tap[q] - mt * tpm;
       const float* src = scratch + ((int64_t)(e.sub[q] * m_tiles + mt) * 128 + tl * Cin + ci) * npad + co;
-      for (int ks = 0; ks < nsplit; ++ks) acc += src[ks * image];       // partial images in split order (reproducible)
+#pragma unroll 8
+      for (int ks = 0; ks < nsplit; ++ks) acc += __ldg(src + ks * image);   // partial images in split order (reproducible)
     }
     if (accumulate) dw[i] += acc; else dw[i] = acc;
   }
@@ -936,9 +951,11 @@ static int32_t launch_pack_multi(int cls, const PackJob* jobs, int njobs, int ti
   }
 }
 
+struct BiasCast { const double* acc = nullptr; float* out = nullptr; int n = 0; };
+
 template <int K3, bool T, int NS>
 static int32_t launch_unpack_t(const float* scratch, float* dw, const InvEntryDev* inv, int A, int B, const GemmSide& f,
-                               int accumulate, int nsplit, cudaStream_t st) {
+                               int accumulate, int nsplit, const BiasCast& bc, cudaStream_t st) {
   constexpr int TA = T ? 64 : 4, TB = T ? 4 : 64;
   const size_t smem = ((size_t)f.subs.size() * f.prog.max_taps + 1) * ((TA * (TB + 1)) | 1) * sizeof(float);
   static size_t smem_set = 0;
@@ -949,16 +966,17 @@ static int32_t launch_unpack_t(const float* scratch, float* dw, const InvEntryDe
   }
   dim3 grid((unsigned)((A + TA - 1) / TA), (unsigned)((B + TB - 1) / TB));
   unpack_wgrad_kernel<K3, T, NS><<<grid, 256, smem, st>>>(scratch, dw, inv, A, B, (int)f.subs.size(), f.prog.max_taps,
-                                                          f.R, f.kc_pad, accumulate, nsplit);
+                                                          f.R, f.kc_pad, accumulate, nsplit, bc.acc, bc.out, bc.n);
   return check_launch("unpack_wgrad_kernel");
 }
 
 static int32_t launch_unpack(int k3, bool transposed, int ns, const float* scratch, float* dw, const InvEntryDev* inv,
-                             int A, int B, const GemmSide& f, int accumulate, int nsplit, cudaStream_t st) {
+                             int A, int B, const GemmSide& f, int accumulate, int nsplit, const BiasCast& bc,
+                             cudaStream_t st) {
 #define PETSYN_UNPACK_CASE(K, NS)                                                                          \
   if (k3 == K && ns <= NS)                                                                                 \
-    return transposed ? launch_unpack_t<K, true, NS>(scratch, dw, inv, A, B, f, accumulate, nsplit, st)    \
-                      : launch_unpack_t<K, false, NS>(scratch, dw, inv, A, B, f, accumulate, nsplit, st);
+    return transposed ? launch_unpack_t<K, true, NS>(scratch, dw, inv, A, B, f, accumulate, nsplit, bc, st) \
+                      : launch_unpack_t<K, false, NS>(scratch, dw, inv, A, B, f, accumulate, nsplit, bc, st);
   PETSYN_UNPACK_CASE(1, 1)
   PETSYN_UNPACK_CASE(8, 1)
   PETSYN_UNPACK_CASE(27, 1)
@@ -1298,7 +1316,15 @@ int32_t petsyn_conv_dgrad_accumulate(petsyn_conv_plan* pl, const void* dy, const
 
 int32_t petsyn_conv_wgrad(petsyn_conv_plan* pl, const void* x, const void* dy, void* scratch, float* dw,
                           int32_t accumulate, void* stream) {
+  return petsyn_conv_wgrad_bias(pl, x, dy, scratch, dw, accumulate, nullptr, nullptr, 0, stream);
+}
+
+int32_t petsyn_conv_wgrad_bias(petsyn_conv_plan* pl, const void* x, const void* dy, void* scratch, float* dw,
+                               int32_t accumulate, const double* dbias_acc, float* dbias, int32_t nbias, void* stream) {
   PETSYN_REQUIRE(pl && x && dy && scratch && dw, "null argument");
+  PETSYN_REQUIRE(dbias == nullptr || (dbias_acc != nullptr && nbias > 0), "bias gradient needs its accumulator and length");
+  BiasCast bc;
+  bc.acc = dbias_acc; bc.out = dbias; bc.n = nbias;
   GemmSide& f = pl->fprop;
   cudaStream_t st = as_stream(stream);
   if (pl->wg_slab) {
@@ -1355,7 +1381,7 @@ int32_t petsyn_conv_wgrad(petsyn_conv_plan* pl, const void* x, const void* dy, v
     if (rc) return rc;
     slab_wgrad_unpack_kernel<<<(unsigned)std::min<int64_t>((q.image_floats + 255) / 256, 148 * 8), 256, 0, st>>>(
         reinterpret_cast<const float*>(scratch), dw, pl->desc.cout, pl->desc.cin, atoms, pl->k3, accumulate, 1,
-        q.image_floats);
+        q.image_floats, bc.acc, bc.out, bc.n);
     return check_launch("slab_wgrad_unpack_kernel");
   }
   if (pl->wg_small) {
@@ -1407,11 +1433,15 @@ int32_t petsyn_conv_wgrad(petsyn_conv_plan* pl, const void* x, const void* dy, v
     if (rc) return rc;
     const int total = pl->desc.cout * pl->desc.cin * pl->k3;
     const int64_t image = (int64_t)f.subs.size() * pl->wg_mtiles * 128 * pl->wg_npad;
-    rc = reduce_images(reinterpret_cast<float*>(scratch), pl->wg_ksplit, image, st);
-    if (rc) return rc;
+    // few splits: added in split order by the unpack kernel itself; many: one coalesced pass first
+    const int inline_split = pl->wg_ksplit <= 4 ? pl->wg_ksplit : 1;
+    if (inline_split == 1) {
+      rc = reduce_images(reinterpret_cast<float*>(scratch), pl->wg_ksplit, image, st);
+      if (rc) return rc;
+    }
     unpack_wgrad_small_kernel<<<std::min((total + 255) / 256, 148 * 8), 256, 0, st>>>(
         reinterpret_cast<const float*>(scratch), dw, pl->d_inv, pl->desc.cout, pl->desc.cin, pl->k3, pl->wg_npad, pl->wg_tpm,
-        pl->wg_mtiles, accumulate, 1, image);
+        pl->wg_mtiles, accumulate, inline_split, image, bc.acc, bc.out, bc.n);
     return check_launch("unpack_wgrad_small_kernel");
   }
   WgradParams& p = pl->wg_params;
@@ -1477,11 +1507,15 @@ int32_t petsyn_conv_wgrad(petsyn_conv_plan* pl, const void* x, const void* dy, v
   {
     const bool convt = pl->desc.op == PETSYN_OP_CONVT;
     const int A = convt ? pl->desc.cin : pl->desc.cout, B = convt ? pl->desc.cout : pl->desc.cin;
-    rc = reduce_images(reinterpret_cast<float*>(scratch), pl->wg_ksplit,
-                       (int64_t)f.subs.size() * f.R * f.prog.max_taps * f.kc_pad, st);
-    if (rc) return rc;
+    // few loads per thread: the splits are added (in split order) by the unpack kernel itself; else one coalesced pass first
+    const int inline_split = pl->wg_ksplit * f.prog.max_taps <= 16 ? pl->wg_ksplit : 1;
+    if (inline_split == 1) {
+      rc = reduce_images(reinterpret_cast<float*>(scratch), pl->wg_ksplit,
+                         (int64_t)f.subs.size() * f.R * f.prog.max_taps * f.kc_pad, st);
+      if (rc) return rc;
+    }
     return launch_unpack(pl->k3, convt, pl->inv_max, reinterpret_cast<const float*>(scratch), dw, pl->d_inv, A, B, f,
-                         accumulate, 1, st);
+                         accumulate, inline_split, bc, st);
   }
 }
 

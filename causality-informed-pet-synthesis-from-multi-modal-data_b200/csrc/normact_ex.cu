@@ -253,6 +253,7 @@ struct Dev {   // device copy of petsyn_normact_desc with typed pointers
   double* dslope;
   const float *ka, *kb;   // per (sample, channel) backward constants of the affine/group path (nullptr: plain path)
   int dz_acc;
+  int cs_off, cs_n;       // channel sub-range of dz that dz_colsum covers
   double* dz_colsum;      // optional [C] += column sums of dz
   double* st1; int st1_c, st1_off;   // optional statistics of destination 1 for the norm that consumes it
   double* st2; int st2_c, st2_off;
@@ -598,7 +599,19 @@ __global__ void __launch_bounds__(256, 2) bwd_apply_kernel(const Dev d) {
   }
   }   // it.active
   // the bias gradient sums over the samples as well: one reduction over the whole grid
-  if (d.dz_colsum != nullptr) block_reduce_channels<1>(it, csum, smem_f, d.dz_colsum, d.C);
+  if (d.dz_colsum != nullptr) {
+    // column sums of the final dz over the rows of this CTA -> double accumulator, channels [cs_off, cs_off + cs_n) only
+    if (it.active) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) smem_f[it.ty * d.C + it.tx * 8 + i] = csum[0][i];
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < d.cs_n; e += blockDim.x) {
+      float s = 0.f;
+      for (int r = 0; r < it.rpp; ++r) s += smem_f[r * d.C + d.cs_off + e];
+      atomicAdd(d.dz_colsum + e, (double)s);
+    }
+  }
 }
 
 // GroupNorm / per-sample affine backward constants.  With S0 = sum g, S1 = sum g*zhat per (sample, channel):
@@ -698,6 +711,9 @@ static int32_t to_dev(const petsyn_normact_desc* d, Dev* o) {
   o->ka = o->kb = nullptr;
   o->dz_acc = d->dz_accumulate;
   o->dz_colsum = reinterpret_cast<double*>(d->dz_colsum);
+  o->cs_off = d->dz_colsum_c > 0 ? d->dz_colsum_coff : 0;
+  o->cs_n = d->dz_colsum_c > 0 ? d->dz_colsum_c : d->c;
+  PETSYN_REQUIRE(o->cs_off >= 0 && o->cs_off + o->cs_n <= d->c, "dz_colsum channel range outside dz");
   o->st1 = reinterpret_cast<double*>(d->t1_stats); o->st1_c = d->t1_stats_c; o->st1_off = d->t1_stats_coff;
   o->st2 = reinterpret_cast<double*>(d->t2_stats); o->st2_c = d->t2_stats_c; o->st2_off = d->t2_stats_coff;
   o->fin_sums = reinterpret_cast<const double*>(d->fin_sums); o->fin_gamma = d->fin_gamma; o->fin_beta = d->fin_beta;

@@ -779,7 +779,11 @@ __global__ void __launch_bounds__(192) slab_wgrad_kernel(const __grid_constant__
 // order, so the weight gradient is reproducible from run to run (no atomics, no memset of the scratch).
 __global__ void __launch_bounds__(256) slab_wgrad_unpack_kernel(const float* __restrict__ scratch, float* __restrict__ dw,
                                                                 int cout, int cin, int apg, int k3, int accumulate,
-                                                                int nimages, int64_t image_floats) {
+                                                                int nimages, int64_t image_floats,
+                                                                const double* __restrict__ dbias_acc,
+                                                                float* __restrict__ dbias, int nbias) {
+  if (dbias != nullptr && blockIdx.x == 0)                 // bias gradient: double accumulator -> fp32 gradient slot
+    for (int i = threadIdx.x; i < nbias; i += 256) dbias[i] = accumulate ? dbias[i] + (float)dbias_acc[i] : (float)dbias_acc[i];
   const int nacc = k3 == 27 ? 3 : 1;
   const int ncols = nacc * apg * 16;
   const int co_atoms = cout >> 4;

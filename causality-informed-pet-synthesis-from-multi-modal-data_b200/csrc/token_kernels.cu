@@ -114,27 +114,32 @@ __global__ void __launch_bounds__(256) resample_up_kernel(const __nv_bfloat16* _
 }
 
 // ------------------------------------------------------------------------------------------------ LayerNorm (warp per row)
-// x, y: bf16 [rows, C] contiguous, C <= 1024 and C % 32 == 0
+// x, y: bf16 [rows, C] contiguous, C <= 1024 and C % 8 == 0 (lane l owns channels l, l + 32, ...; a last partial pass when
+// C is not a multiple of 32)
 __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const __nv_bfloat16* __restrict__ x,
                                                             const float* __restrict__ gamma,
                                                             const float* __restrict__ beta,
                                                             __nv_bfloat16* __restrict__ y, float* __restrict__ mean,
                                                             float* __restrict__ rstd, int64_t rows, int C, float eps) {
   const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
-  const int per = C / 32;
+  const int per = (C + 31) / 32;
   for (int64_t r = (int64_t)blockIdx.x * wpb + (threadIdx.x >> 5); r < rows; r += (int64_t)gridDim.x * wpb) {
     float v[32];
     float s = 0.f;
-    for (int j = 0; j < per; ++j) { v[j] = bf(x[r * C + j * 32 + lane]); s += v[j]; }
+    for (int j = 0; j < per; ++j) {
+      const int c = j * 32 + lane;
+      v[j] = c < C ? bf(x[r * C + c]) : 0.f;
+      s += v[j];
+    }
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     const float mu = s / (float)C;
     float q = 0.f;
-    for (int j = 0; j < per; ++j) { const float d = v[j] - mu; q += d * d; }
+    for (int j = 0; j < per; ++j) { const float d = (j * 32 + lane < C) ? v[j] - mu : 0.f; q += d * d; }
     for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
     const float rs = rsqrtf(q / (float)C + eps);
     for (int j = 0; j < per; ++j) {
       const int c = j * 32 + lane;
-      y[r * C + c] = __float2bfloat16((v[j] - mu) * rs * gamma[c] + beta[c]);
+      if (c < C) y[r * C + c] = __float2bfloat16((v[j] - mu) * rs * gamma[c] + beta[c]);
     }
     if (lane == 0) { mean[r] = mu; rstd[r] = rs; }
   }
@@ -151,7 +156,7 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const __nv_bfloat16*
                                                             int accumulate, const DetWs ws) {
   extern __shared__ __align__(16) float sm[];   // [warps][2][C] per-warp partials of dgamma / dbeta (>= 1024 floats)
   const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
-  const int per = C / 32;
+  const int per = (C + 31) / 32;
   float pg[32], pb[32];
   for (int j = 0; j < per; ++j) pg[j] = pb[j] = 0.f;
   for (int64_t r = (int64_t)blockIdx.x * wpb + (threadIdx.x >> 5); r < rows; r += (int64_t)gridDim.x * wpb) {
@@ -160,9 +165,10 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const __nv_bfloat16*
     float s0 = 0.f, s1 = 0.f;
     for (int j = 0; j < per; ++j) {
       const int c = j * 32 + lane;
-      const float g = bf(dy[r * C + c]);
-      xh[j] = (bf(x[r * C + c]) - mu) * rs;
-      gg[j] = g * gamma[c];
+      const bool in = c < C;
+      const float g = in ? bf(dy[r * C + c]) : 0.f;
+      xh[j] = in ? (bf(x[r * C + c]) - mu) * rs : 0.f;
+      gg[j] = in ? g * gamma[c] : 0.f;
       s0 += gg[j];
       s1 += gg[j] * xh[j];
       pg[j] += g * xh[j];
@@ -175,6 +181,7 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const __nv_bfloat16*
     s0 /= (float)C; s1 /= (float)C;
     for (int j = 0; j < per; ++j) {
       const int c = j * 32 + lane;
+      if (c >= C) continue;
       float v = rs * (gg[j] - s0 - xh[j] * s1);
       if (accumulate) v += bf(dx[r * C + c]);
       dx[r * C + c] = __float2bfloat16(v);
@@ -183,8 +190,10 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const __nv_bfloat16*
   {
     float* mine = sm + (threadIdx.x >> 5) * 2 * C;
     for (int j = 0; j < per; ++j) {
-      mine[j * 32 + lane] = pg[j];
-      mine[C + j * 32 + lane] = pb[j];
+      const int c = j * 32 + lane;
+      if (c >= C) continue;
+      mine[c] = pg[j];
+      mine[C + c] = pb[j];
     }
   }
   __syncthreads();
@@ -356,7 +365,7 @@ int32_t petsyn_resample2(const void* src, int32_t src_cstride, int32_t src_coff,
 int32_t petsyn_layernorm_fwd(const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd,
                              int64_t rows, int32_t c, float eps, void* stream) {
   PETSYN_REQUIRE(x && gamma && beta && y && mean && rstd && rows > 0, "bad argument");
-  PETSYN_REQUIRE(c % 32 == 0 && c <= 1024, "LayerNorm width must be a multiple of 32, at most 1024");
+  PETSYN_REQUIRE(c % 8 == 0 && c >= 8 && c <= 1024, "LayerNorm width must be a multiple of 8, at most 1024");
   layernorm_fwd_kernel<<<blocks_for(rows, 8), 256, 0, as_stream(stream)>>>(CBFP(x), gamma, beta, BFP(y), mean, rstd, rows,
                                                                            c, eps);
   return check_launch("layernorm_fwd_kernel");
@@ -366,7 +375,7 @@ int32_t petsyn_layernorm_bwd(const void* x, const void* dy, const float* gamma, 
                              void* dx, float* dgamma, float* dbeta, int64_t rows, int32_t c, int32_t accumulate_dx,
                              void* stream) {
   PETSYN_REQUIRE(x && dy && gamma && mean && rstd && dx && dgamma && dbeta && rows > 0, "bad argument");
-  PETSYN_REQUIRE(c % 32 == 0 && c <= 1024, "LayerNorm width must be a multiple of 32, at most 1024");
+  PETSYN_REQUIRE(c % 8 == 0 && c >= 8 && c <= 1024, "LayerNorm width must be a multiple of 8, at most 1024");
   cudaStream_t st = as_stream(stream);
   PETSYN_CHECK_CUDA(cudaMemsetAsync(dgamma, 0, c * sizeof(float), st));
   PETSYN_CHECK_CUDA(cudaMemsetAsync(dbeta, 0, c * sizeof(float), st));

@@ -96,7 +96,11 @@ class ConvOp(Op):
     def __init__(self, x: Sl, weight: torch.nn.Parameter, bias: Optional[torch.nn.Parameter], ksize: int, stride: int,
                  pad: int, op: int = ops.OP_CONV, act: int = ops.ACT_NONE, slope: float = 0.2, y_fp32: bool = False,
                  use_bias: bool = True, need_dx: bool = True, need_dw: bool = True, name: str = "",
-                 out: Optional["Sl"] = None, dy_from: Optional["Sl"] = None):
+                 out: Optional["Sl"] = None, dy_from: Optional["Sl"] = None, cout_pad: Optional[int] = None,
+                 out_index: Optional[Sequence[int]] = None, in_index: Optional[Sequence[int]] = None):
+        """``out_index`` / ``in_index`` (with ``cout_pad``): position of every true output / input channel of the weight inside
+        the (wider, otherwise zero) channel range the kernels see -- attention heads of 8 or 16 channels padded to the
+        kernel's 32-channel head: Conv3d / Linear layouts only."""
         self.x, self.weight, self.bias = x, weight, bias
         self.out_sl = out                      # write into a channel slice of an existing buffer instead of an own one
         # backward reads the gradient w.r.t. the output from THIS slice instead of z.g: the conv feeds a residual sum whose
@@ -114,8 +118,19 @@ class ConvOp(Op):
         self.cin, self.cout = x.c, (cout_w + 7) // 8 * 8
         if cout_w < 8:
             self.cout = 16                     # one-channel heads: smallest UMMA N with an unswizzled 32-byte row
+        if cout_pad is not None:
+            assert cout_pad >= self.cout and cout_pad % 8 == 0
+            self.cout = cout_pad
         assert cin_w <= self.cin, (cin_w, self.cin)
-        self.padded = (self.cin != cin_w) or (self.cout != cout_w)
+        self.padded = (self.cin != cin_w) or (self.cout != cout_w) or out_index is not None or in_index is not None
+        self._oidx = self._iidx = None
+        if out_index is not None or in_index is not None:
+            assert op != ops.OP_CONVT
+            oi = list(out_index) if out_index is not None else list(range(cout_w))
+            ii = list(in_index) if in_index is not None else list(range(cin_w))
+            assert len(oi) == cout_w and len(ii) == cin_w and max(oi) < self.cout and max(ii) < self.cin
+            self._oidx = torch.tensor(oi, dtype=torch.long, device=dev)
+            self._iidx = torch.tensor(ii, dtype=torch.long, device=dev)
         self.use_bias = use_bias and bias is not None
         self.need_dx, self.need_dw = need_dx, need_dw
         ykw = {}
@@ -157,6 +172,7 @@ class ConvOp(Op):
         self.colsum_done = False  # set by the NormActOp consuming z when it already summed dz over the rows (bias gradient)
         self.acc_dw = False      # add into grad_w / grad_b instead of overwriting (several backward calls per step)
         self._ver = None
+        self._zero_b = None      # data_ptr of the bias-gradient slot that was cleared (biases with identically zero gradient)
         self.wg_scratch: Optional[torch.Tensor] = None  # Tape.finalize: ONE weight-gradient scratch for all convs of a tape
         self.grad_w: Optional[torch.Tensor] = None     # set by the owner: where dW / dbias go
         self.grad_b: Optional[torch.Tensor] = None
@@ -178,15 +194,36 @@ class ConvOp(Op):
         if self.need_dx and p.w_dgrad is None:
             p.w_dgrad = torch.empty(p.packed_dgrad_bytes, dtype=torch.uint8, device=dev)
 
+    def _stage_weights(self) -> None:
+        """fp32 master weights (and bias) -> the zero-padded staging copies the pack kernels read."""
+        w = self.weight.detach()
+        if self.padded:
+            if self._oidx is not None:
+                k = self.w_stage.shape[-1]
+                self.w_stage[self._oidx[:, None], self._iidx[None, :]] = w.reshape(self.cout_w, self.cin_w, k, k, k)
+            elif self.opcode == ops.OP_CONVT:
+                self.w_stage[:self.cin_w, :self.cout_w].copy_(w)
+            else:
+                self.w_stage[:self.cout_w, :self.cin_w].copy_(w)
+        if self.bias_stage is not None:
+            if self._oidx is not None:
+                self.bias_stage[self._oidx] = self.bias.detach()
+            else:
+                self.bias_stage[:self.cout_w].copy_(self.bias.detach())
+
+    def _dw_part(self) -> torch.Tensor:
+        if self._oidx is not None:
+            return self.dw_stage[self._oidx[:, None], self._iidx[None, :]]
+        if self.opcode == ops.OP_CONVT:
+            return self.dw_stage[:self.cin_w, :self.cout_w]
+        return self.dw_stage[:self.cout_w, :self.cin_w]
+
+    def _db_part(self) -> torch.Tensor:
+        return self.dbias_stage[self._oidx] if self._oidx is not None else self.dbias_stage[:self.cout_w]
+
     def stage_padded(self) -> None:
         w = self.weight
-        if self.padded:
-            if self.opcode == ops.OP_CONVT:
-                self.w_stage[:self.cin_w, :self.cout_w].copy_(w.detach())
-            else:
-                self.w_stage[:self.cout_w, :self.cin_w].copy_(w.detach())
-        if self.bias_stage is not None:
-            self.bias_stage[:self.cout_w].copy_(self.bias.detach())
+        self._stage_weights()
         self._ver = (w._version, w.data_ptr(), self.need_dx)
 
     def repack(self, force: bool = False) -> None:
@@ -194,16 +231,8 @@ class ConvOp(Op):
         ver = (w._version, w.data_ptr(), self.need_dx)
         if not force and ver == self._ver:
             return
-        src = w.detach()
-        if self.padded:
-            if self.opcode == ops.OP_CONVT:
-                self.w_stage[:self.cin_w, :self.cout_w].copy_(src)
-            else:
-                self.w_stage[:self.cout_w, :self.cin_w].copy_(src)
-            src = self.w_stage
-        self.plan.pack(src, need_dgrad=self.need_dx)
-        if self.bias_stage is not None:
-            self.bias_stage[:self.cout_w].copy_(self.bias.detach())
+        self._stage_weights()
+        self.plan.pack(self.w_stage if self.padded else w.detach(), need_dgrad=self.need_dx)
         self._ver = ver
 
     def out(self) -> torch.Tensor:
@@ -251,16 +280,9 @@ class ConvOp(Op):
             with torch.cuda.stream(side):
                 self._bwd_dx(dz)
         if self.need_dw:
-            if self.padded:
-                self.plan.wgrad(self.x.buf.t, dz, self.dw_stage, scratch=self.wg_scratch)
-                part = self.dw_stage[:self.cin_w, :self.cout_w] if self.opcode == ops.OP_CONVT else \
-                    self.dw_stage[:self.cout_w, :self.cin_w]
-                if self.acc_dw:
-                    self.grad_w.add_(part)
-                else:
-                    self.grad_w.copy_(part)
-            else:
-                self.plan.wgrad(self.x.buf.t, dz, self.grad_w, accumulate=self.acc_dw, scratch=self.wg_scratch)
+            # bias gradient: column sums of dy (a by-product of the normalisation backward that wrote dy last, else a pass of
+            # its own) sit in a float64 accumulator; the weight-gradient launch converts them into the fp32 slot
+            bkw = {}
             if self.bias is not None:
                 if self.use_bias:
                     if self.colsum_done:
@@ -270,12 +292,27 @@ class ConvOp(Op):
                         cs, co = (dsl.buf.c, dsl.off) if dsl is not None else (self.cout, 0)
                         check(lib.petsyn_colsum(ptr(dz), cs, co, ptr(self.dbias_stage), dz.shape[0], self.cout,
                                                 stream_ptr()), "colsum")
-                    if self.acc_dw:
-                        self.grad_b.add_(self.dbias_stage[:self.cout_w])
-                    else:
-                        self.grad_b.copy_(self.dbias_stage[:self.cout_w])
-                elif not self.acc_dw:
-                    self.grad_b.zero_()     # a bias in front of a non-affine InstanceNorm has exactly zero gradient
+                    if self.grad_b.is_contiguous() and not self.padded:
+                        bkw = dict(dbias_acc=self.dbias_stage, dbias=self.grad_b)
+                elif not self.acc_dw and self._zero_b != self.grad_b.data_ptr():
+                    # a bias in front of a non-affine InstanceNorm has exactly zero gradient and nothing ever writes its
+                    # slot: cleared once per binding instead of once per step
+                    self.grad_b.zero_()
+                    self._zero_b = self.grad_b.data_ptr()
+            if self.padded:
+                self.plan.wgrad(self.x.buf.t, dz, self.dw_stage, scratch=self.wg_scratch, **bkw)
+                part = self._dw_part().reshape(self.grad_w.shape)
+                if self.acc_dw:
+                    self.grad_w.add_(part)
+                else:
+                    self.grad_w.copy_(part)
+            else:
+                self.plan.wgrad(self.x.buf.t, dz, self.grad_w, accumulate=self.acc_dw, scratch=self.wg_scratch, **bkw)
+            if self.bias is not None and self.use_bias and not bkw:
+                if self.acc_dw:
+                    self.grad_b.add_(self._db_part())
+                else:
+                    self.grad_b.copy_(self._db_part())
         if fork:
             main.wait_stream(side)
         elif self.need_dx:
@@ -303,6 +340,7 @@ class NormActOp(Op):
         self.gn = gn                            # nn.GroupNorm (kind == "group"): affine, num_groups, eps
         self.acc_dz = False
         self.fwd_batch_stats = True             # kind == "batch": the last forward normalised with batch statistics
+        self.colsum_range = (0, 0)              # (first channel, count) of dz that belongs to colsum_conv; count 0 = all
         self.colsum_conv: Optional["ConvOp"] = None   # conv that produced z: its bias gradient is a by-product of bwd
         # statistics as a by-product: a "none" op may sum what it writes for the norm that consumes the destination ...
         self.stats_from_producers = False              # ... and that norm then skips its own statistics pass
@@ -390,6 +428,7 @@ class NormActOp(Op):
                 d.extra, d.extra_cstride, d.extra_coff = ptr(self.extra.buf.g), self.extra.buf.c, self.extra.off
             if self.colsum_conv is not None:
                 d.dz_colsum = ptr(self.colsum_conv.dbias_stage)
+                d.dz_colsum_coff, d.dz_colsum_c = self.colsum_range
             if self.grad_gamma is not None:
                 if self.acc_dw:
                     if self._tmp_gb is None:
@@ -548,15 +587,18 @@ class AttentionOp(Op):
     """o = softmax(scale * q k^T) v per (sample, head); qkv = (q | k | v) columns of one buffer."""
     can_accumulate = False
 
-    def __init__(self, qkv: Buf, out: Buf, heads: int, tokens_per_sample: int):
+    def __init__(self, qkv: Buf, out: Buf, heads: int, tokens_per_sample: int, true_head_dim: Optional[int] = None):
+        """``true_head_dim``: the model's head width when the buffers hold heads zero-padded to the kernel's 32 channels (the
+        softmax scale is 1 / sqrt(true width); zero channels change neither q k^T nor p v)."""
         self.qkv, self.o, self.heads, self.L = qkv, out, heads, tokens_per_sample
         self.n = qkv.rows // tokens_per_sample
         self.hd = out.c // heads
         dev = qkv.t.device
         self.lse = torch.zeros(self.n * heads * self.L, dtype=torch.float32, device=dev)
         self.delta = torch.zeros_like(self.lse)
-        self.scale = 1.0 / (self.hd ** 0.5)
-        self.flops = 4.0 * self.n * heads * self.L * self.L * self.hd
+        thd = true_head_dim or self.hd
+        self.scale = 1.0 / (thd ** 0.5)
+        self.flops = 4.0 * self.n * heads * self.L * self.L * thd
 
     def fwd(self, training: bool) -> None:
         check(lib.petsyn_attention_fwd(ptr(self.qkv.t), ptr(self.o.t), ptr(self.lse), self.n, self.L, self.heads, self.hd,
@@ -654,9 +696,9 @@ class Tape:
             if not hits:
                 continue
             op, key, sl = hits[-1]
-            if isinstance(op, NormActOp) and key == "dz" and (sl.off, sl.c) == (region.off, region.c) \
-                    and op.colsum_conv is None:
-                op.colsum_conv = cv
+            if isinstance(op, NormActOp) and key == "dz" and sl.off <= lo and hi <= sl.off + sl.c and op.colsum_conv is None:
+                op.colsum_conv = cv                    # the conv's channels may be a sub-range of the op's dz
+                op.colsum_range = (lo - sl.off, region.c)
         # statistics as a by-product: a GroupNorm whose input (a buffer or a channel slice of one) is written, channel range
         # by channel range, only by un-normalised NormActOps (residual sums, copies into concat buffers) takes its sums from
         # those producers; a destination may serve two consuming normalisations
@@ -678,6 +720,8 @@ class Tape:
                     other(op.out_sl)
                 elif op.z is not None:
                     other(op.z.sl())
+            elif isinstance(op, ResampleOp):
+                other(op.dst)                          # src / dst_grad are only read
             else:
                 for v in vars(op).values():            # any other op that holds the buffer may write it: be conservative
                     if isinstance(v, Buf):

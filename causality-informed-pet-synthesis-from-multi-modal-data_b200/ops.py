@@ -85,14 +85,22 @@ class ConvPlan:
         return dx
 
     def wgrad(self, x: torch.Tensor, dy: torch.Tensor, dw: torch.Tensor, accumulate: bool = False,
-              scratch: Optional[torch.Tensor] = None) -> torch.Tensor:
+              scratch: Optional[torch.Tensor] = None, dbias_acc: Optional[torch.Tensor] = None,
+              dbias: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """``dbias_acc`` (float64 column sums of dy, filled earlier on this stream) / ``dbias`` (fp32 gradient slot): the bias
+        gradient is converted into its slot by the launch that lays out dw (no launch of its own)."""
         if scratch is None:
             if self._scratch is None:
                 self._scratch = torch.empty(self.wgrad_scratch_bytes, dtype=torch.uint8, device=x.device)
             scratch = self._scratch
         assert scratch.numel() * scratch.element_size() >= self.wgrad_scratch_bytes
-        check(lib.petsyn_conv_wgrad(self._h, ptr(x), ptr(dy), ptr(scratch), ptr(dw), int(accumulate), stream_ptr()),
-              "conv_wgrad")
+        if dbias is not None:
+            assert dbias_acc.dtype == torch.float64 and dbias.dtype == torch.float32 and dbias.is_contiguous()
+            check(lib.petsyn_conv_wgrad_bias(self._h, ptr(x), ptr(dy), ptr(scratch), ptr(dw), int(accumulate), ptr(dbias_acc),
+                                             ptr(dbias), dbias.numel(), stream_ptr()), "conv_wgrad_bias")
+        else:
+            check(lib.petsyn_conv_wgrad(self._h, ptr(x), ptr(dy), ptr(scratch), ptr(dw), int(accumulate), stream_ptr()),
+                  "conv_wgrad")
         return dw
 
 

@@ -94,6 +94,40 @@ class GradBucketer:
         self._pending.clear()
 
 
+class GraphSegments:
+    """A training step captured as CUDA-graph SEGMENTS with eager actions (NCCL collectives) in between.
+
+    Collectives stay outside the graphs: while a step function is being captured, ``cut(action)`` closes the open graph,
+    remembers ``action`` and opens the next one; ``replay()`` then alternates ``graph.replay()`` and ``action()``.  The same
+    step function therefore serves the eager path (actions run inline) and the captured one."""
+
+    def __init__(self):
+        self.items: List[tuple] = []
+        self.pool = torch.cuda.graph_pool_handle()
+        self._g = self._ctx = None
+
+    def open(self) -> None:
+        self._g = torch.cuda.CUDAGraph()
+        self._ctx = torch.cuda.graph(self._g, pool=self.pool)
+        self._ctx.__enter__()
+
+    def cut(self, action) -> None:
+        self._ctx.__exit__(None, None, None)
+        self.items.append((self._g, action))
+        self.open()
+
+    def finish(self) -> None:
+        self._ctx.__exit__(None, None, None)
+        self.items.append((self._g, None))
+        self._g = self._ctx = None
+
+    def replay(self) -> None:
+        for g, action in self.items:
+            g.replay()
+            if action is not None:
+                action()
+
+
 def adam_state_dict(params: List[torch.nn.Parameter], exp_avg: List[torch.Tensor], exp_avg_sq: List[torch.Tensor],
                     step: int, lr: float, betas, eps: float) -> dict:
     """``torch.optim.Adam(params, lr).state_dict()`` for externally held moments: what the reference stores under
@@ -380,6 +414,7 @@ class BmganTrainer:
         self.dlogits = torch.zeros_like(self.deng.logits)
         self.bucketer = GradBucketer(self.garena, bucket_mb, process_group)
         self.graph = None
+        self._cap: Optional[GraphSegments] = None      # set while capture() records the step
         self.static = None
         if self.world > 1:
             dist.broadcast(self.garena.p, src=0, group=self.pg)
@@ -396,6 +431,18 @@ class BmganTrainer:
             if hasattr(op, "_ver"):
                 op._ver = None
 
+    def _collective(self, fn) -> None:
+        """Run a collective now (eager step) or -- while the step is being captured -- end the open graph segment and let
+        ``fn`` run between the segments at replay time."""
+        if self._cap is not None:
+            self._cap.cut(fn)
+        else:
+            fn()
+
+    def _bucket_ready(self, p) -> None:
+        if self.world > 1 and id(p) in self.bucketer._bucket_of_last:
+            self._collective(lambda: self.bucketer.on_ready(p))
+
     def _step_impl(self, t1: torch.Tensor, pet: torch.Tensor, z: torch.Tensor) -> None:
         geng, deng = self.geng, self.deng
         # ---------------- G phase ----------------
@@ -407,8 +454,9 @@ class BmganTrainer:
         self.loss_l1.zero_()
         ops.l1_loss_fwd_bwd(fake, pet, self.loss_l1, self.dy, grad_scale=self.lamda_l1)
         self.dy.add_(dfake)
-        geng.backward(self.dy, out=self.garena.grad_views, on_ready=self.bucketer.on_ready)
-        self.bucketer.wait_all()
+        geng.backward(self.dy, out=self.garena.grad_views, on_ready=self._bucket_ready)
+        if self.world > 1:
+            self._collective(self.bucketer.wait_all)
         self.step_dev.add_(1)
         ops.adam_step(self.garena.p, self.garena.g, self.gm, self.gv, self.lr, self.betas[0], self.betas[1], self.eps, 0,
                       step_dev=self.step_dev)
@@ -424,7 +472,7 @@ class BmganTrainer:
                 ops.kl_fwd_bwd(lat, lat[:, 8:], self.loss_kl, self.dlatent, self.dlatent[:, 8:], n, 8, 16)
                 eeng.backward(self.dlatent, out=self.earena.grad_views, accumulate=(i == 1))
             if self.world > 1:
-                dist.all_reduce(self.earena.g, op=dist.ReduceOp.AVG, group=self.pg)
+                self._collective(lambda: dist.all_reduce(self.earena.g, op=dist.ReduceOp.AVG, group=self.pg))
             ops.adam_step(self.earena.p, self.earena.g, self.em, self.ev, self.lr, self.betas[0], self.betas[1], self.eps,
                           0, step_dev=self.step_dev)
             for op in eeng.tape.ops:
@@ -443,7 +491,7 @@ class BmganTrainer:
         deng.backward(self.dlogits, need_dx=False, out=self.darena.grad_views, need_dw=True, accumulate=True)
         if self.step_discriminator:
             if self.world > 1:
-                dist.all_reduce(self.darena.g, op=dist.ReduceOp.AVG, group=self.pg)
+                self._collective(lambda: dist.all_reduce(self.darena.g, op=dist.ReduceOp.AVG, group=self.pg))
             ops.adam_step(self.darena.p, self.darena.g, self.dm, self.dv, self.lr, self.betas[0], self.betas[1], self.eps,
                           0, step_dev=self.step_dev)
             for op in self.deng.tape.ops:
@@ -463,9 +511,10 @@ class BmganTrainer:
         return self.loss_adv, self.loss_l1, self.loss_d_fake, self.loss_d_real
 
     def capture(self, warmup: int = 2) -> None:
-        """Single-GPU only: the whole adversarial step as one CUDA graph (state is restored after the warm-up)."""
-        if self.world > 1:
-            raise RuntimeError("BmganTrainer.capture supports world_size 1; data-parallel runs launch eagerly")
+        """The whole adversarial step as CUDA graph(s) (state is restored after the warm-up).  One GPU: a single graph.
+        Data parallel: graph SEGMENTS cut wherever a collective happens -- after the last gradient of every generator bucket
+        (its all-reduce is launched on the side stream and overlaps the next segment), before the generator's Adam (wait),
+        around the encoder's / discriminator's gradient all-reduce."""
         state = [self.garena.p, self.gm, self.gv, self.darena.p, self.darena.g, self.dm, self.dv, self.step_dev]
         if self.enc is not None:
             state += [self.earena.p, self.em, self.ev]
@@ -481,9 +530,14 @@ class BmganTrainer:
                 self._step_impl(*self.static)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize(self.dev)
-        g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
+        g = GraphSegments()
+        g.open()
+        self._cap = g
+        try:
             self._step_impl(*self.static)
+        finally:
+            self._cap = None
+        g.finish()
         for dst, src in zip(state, snap):
             dst.copy_(src)
         for dst, src in zip(list(self.gen.buffers()) + list(self.disc.buffers()), bufs):

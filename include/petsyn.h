@@ -137,6 +137,11 @@ int32_t petsyn_conv_dgrad_accumulate(petsyn_conv_plan* plan, const void* dy, con
  * accumulate != 0 adds into dw instead of overwriting (autograd .grad accumulation). */
 int32_t petsyn_conv_wgrad(petsyn_conv_plan* plan, const void* x, const void* dy, void* scratch, float* dw,
                           int32_t accumulate, void* stream);
+/* The same, and -- in the launch that lays the weight gradient out -- the bias gradient: dbias[0:nbias] (+)= dbias_acc[0:nbias]
+ * (the double accumulator that petsyn_colsum / a normalisation's backward filled earlier on this stream -> the fp32 gradient
+ * slot; added when `accumulate`).  Saves a conversion launch per convolution. */
+int32_t petsyn_conv_wgrad_bias(petsyn_conv_plan* plan, const void* x, const void* dy, void* scratch, float* dw,
+                               int32_t accumulate, const double* dbias_acc, float* dbias, int32_t nbias, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Edge layers of the pix2pix U-Net (Cin = 1 / Cout = 1): small layout kernels that turn them into 1x1x1 GEMMs for the
@@ -275,6 +280,8 @@ typedef struct petsyn_normact_desc {
                               * through an identity skip connection (ResnetBlock: out = f(x) + x, atten_unet_model.py:662), so
                               * the residual sum needs no backward pass of its own */
   int32_t extra_cstride, extra_coff;
+  int32_t dz_colsum_coff, dz_colsum_c; /* dz_colsum covers channels [dz_colsum_coff, +dz_colsum_c) of dz only (the convolution
+                              * wrote a channel slice of a wider concat buffer); dz_colsum_c == 0: all c channels */
 } petsyn_normact_desc;
 
 /* sums[sample][0:c] += sum z, sums[sample][c:2c] += sum z^2 (double accumulators, caller-zeroed). */

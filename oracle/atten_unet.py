@@ -6,7 +6,7 @@ Functional restatement of ``unet/utils/atten_unet_model.py`` driven by the refer
 ``SpatialTransformer`` :238-343, ``BasicTransformerBlock`` :178-235, ``CrossAttention`` :65-175, ``AttenUNet.forward``
 :1792-1860.  The two MONAI pieces the file imports are restated per upstream: ``Convolution(conv_only=True)`` =
 ``nn.Conv3d`` child named ``conv``; ``MLPBlock(act="GEGLU")`` = linear1 -> chunk -> x*gelu(gate) -> linear2.
-Pinned by ``tests/test_oracle_cpu.py::test_atten_unet_oracle_matches_live_reference`` (the reference class imported
+Pinned by ``tests/test_oracle_cpu.py::test_atten_unet_oracle_matches_live_reference`` and ``::test_atten_unet_oracle_matches_golden`` (the reference class imported
 unmodified over a stub ``monai``) and ``tests/golden/atten_unet_*.npz``.
 """
 from __future__ import annotations
@@ -16,6 +16,12 @@ from typing import Dict, List, Sequence
 
 import torch
 import torch.nn.functional as F
+
+# the reference's own smoke configuration (unet/utils/atten_unet_model.py:2034-2051): conv-form down / up sampling
+# (resblock_updown=False), the default 8-channel attention heads, 8 GroupNorm groups, a 2-D context of 3 covariates
+SMOKE_CFG = dict(spatial_dims=3, in_channels=1, out_channels=1, cross_attention_dim=3, with_conditioning=True,
+                 num_res_blocks=(1, 1, 1), num_channels=(8, 16, 16), norm_num_groups=8, attention_levels=[False, False, True],
+                 norm_eps=1e-6, resblock_updown=False, num_head_channels=8)
 
 TRAINING_JSON = dict(  # unet/config/training.json:8-38 (atten_unet_def) + cross_attention_dim injected at train_unet.py:64-68
     spatial_dims=3, in_channels=1, out_channels=1, num_channels=[16, 32, 64, 128], num_res_blocks=2,
@@ -109,8 +115,9 @@ def forward(x: torch.Tensor, context: torch.Tensor, sd: Dict[str, torch.Tensor],
     att = cfg["attention_levels"]
     hc = cfg["num_head_channels"]
     hc = [hc] * len(ch) if isinstance(hc, int) else list(hc)
-    groups, eps = cfg["norm_num_groups"], cfg["norm_eps"]
-    assert cfg["resblock_updown"] and cfg["with_conditioning"]
+    groups, eps = cfg["norm_num_groups"], cfg.get("norm_eps", 1e-6)
+    updown = cfg.get("resblock_updown", False)
+    assert cfg["with_conditioning"]
     if context.dim() < 3:
         context = context.unsqueeze(1)                                            # :110-112
     heads = lambda lvl: ch[lvl] // hc[lvl]
@@ -123,7 +130,11 @@ def forward(x: torch.Tensor, context: torch.Tensor, sd: Dict[str, torch.Tensor],
                 h = transformer(sd, f"down_blocks.{i}.attentions.{j}.", h, context, groups, eps, heads(i))
             skips.append(h)
         if i != len(ch) - 1:
-            h = resnet(sd, f"down_blocks.{i}.downsampler.", h, groups, eps, down=True)
+            if updown:
+                h = resnet(sd, f"down_blocks.{i}.downsampler.", h, groups, eps, down=True)
+            else:                                                                   # Downsample(use_conv=True) :464-507
+                pre = f"down_blocks.{i}.downsampler.op."
+                h = F.conv3d(h, sd[pre + "conv.weight"], sd[pre + "conv.bias"], stride=2, padding=1)
             skips.append(h)
     h = resnet(sd, "middle_block.resnet_1.", h, groups, eps)
     h = transformer(sd, "middle_block.attention.", h, context, groups, eps, heads(len(ch) - 1))
@@ -136,7 +147,10 @@ def forward(x: torch.Tensor, context: torch.Tensor, sd: Dict[str, torch.Tensor],
             if att[lvl]:
                 h = transformer(sd, f"up_blocks.{i}.attentions.{j}.", h, context, groups, eps, heads(lvl))
         if i != len(ch) - 1:
-            h = resnet(sd, f"up_blocks.{i}.upsampler.", h, groups, eps, up=True)
+            if updown:
+                h = resnet(sd, f"up_blocks.{i}.upsampler.", h, groups, eps, up=True)
+            else:                                                                   # Upsample(use_conv=True) :510-562
+                h = _conv(sd, f"up_blocks.{i}.upsampler.conv.", F.interpolate(h, scale_factor=2.0, mode="nearest"), 1)
     h = F.silu(F.group_norm(h, groups, sd["out.0.weight"], sd["out.0.bias"], eps))
     return F.conv3d(h, sd["out.2.conv.weight"], sd["out.2.conv.bias"], padding=1)
 
@@ -159,6 +173,7 @@ def param_shapes(cfg=TRAINING_JSON) -> Dict[str, tuple]:
     nres = cfg["num_res_blocks"]
     nres = [nres] * n if isinstance(nres, int) else list(nres)
     att, cdim = cfg["attention_levels"], cfg["cross_attention_dim"]
+    updown = cfg.get("resblock_updown", False)
     out: Dict[str, tuple] = {}
 
     def conv(pre, cin, cout, k):
@@ -200,7 +215,10 @@ def param_shapes(cfg=TRAINING_JSON) -> Dict[str, tuple]:
         for j in range(nres[i]):
             resnet(pre + f"resnets.{j}.", ic if j == 0 else oc, oc)
         if i != n - 1:
-            resnet(pre + "downsampler.", oc, oc)
+            if updown:
+                resnet(pre + "downsampler.", oc, oc)
+            else:
+                conv(pre + "downsampler.op.", oc, oc, 3)
     resnet("middle_block.resnet_1.", ch[-1], ch[-1])
     transformer("middle_block.attention.", ch[-1])
     resnet("middle_block.resnet_2.", ch[-1], ch[-1])
@@ -220,7 +238,10 @@ def param_shapes(cfg=TRAINING_JSON) -> Dict[str, tuple]:
             in_c = prev if j == 0 else oc
             resnet(pre + f"resnets.{j}.", in_c + skip_c, oc)
         if i != n - 1:
-            resnet(pre + "upsampler.", oc, oc)
+            if updown:
+                resnet(pre + "upsampler.", oc, oc)
+            else:
+                conv(pre + "upsampler.conv.", oc, oc, 3)
     norm("out.0.", ch[0])
     conv("out.2.", ch[0], 1, 3)
     return out

@@ -6,7 +6,7 @@ Restates, as plain functional PyTorch on CPU, what the reference's
 ``UnetGenerator3d`` / ``UnetSkipConnectionBlock3d`` compute
 (reference: ``unet/utils/unet_model.py:5-99``).  Parameters are addressed by the
 reference's own state-dict keys, so a reference checkpoint drives the oracle
-unchanged.  Pinned by ``tests/test_oracle_vs_reference.py`` (live reference) and
+unchanged.  Pinned by ``tests/test_oracle_cpu.py::test_oracle_matches_live_reference`` (live reference) and
 ``tests/golden/unet3d_*.npz``.
 """
 from __future__ import annotations

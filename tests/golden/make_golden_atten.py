@@ -20,10 +20,10 @@ sys.path.insert(0, ROOT)
 REF = os.environ.get("PETSYN_REFERENCE", "/root/reference")
 
 
-def synth(shape, seed):
+def synth(shape, seed, cdim=5):
     g = torch.Generator().manual_seed(seed)
     n, d, h, w = shape
-    return (torch.rand(n, 1, d, h, w, generator=g), torch.rand(n, 1, 5, generator=g),
+    return (torch.rand(n, 1, d, h, w, generator=g), torch.rand(n, 1, cdim, generator=g),
             torch.rand(n, 1, d, h, w, generator=g))
 
 
@@ -37,16 +37,21 @@ def main():
     cfg["cross_attention_dim"] = 5
     assert cfg == OA.TRAINING_JSON, (cfg, OA.TRAINING_JSON)
     torch.set_num_threads(os.cpu_count() or 1)
-    cases = (("atten_unet_2x32x48x32", (2, 32, 48, 32), 777, 1),
+    cases = (("atten_unet_2x32x48x32", (2, 32, 48, 32), 777, 1, cfg),
              # BASELINE configs[1] at full size (the bench default): output stored on a stride-3 lattice, small gradients whole
-             ("atten_unet_2x96x128x96", (2, 96, 128, 96), 777, 3))
+             ("atten_unet_2x96x128x96", (2, 96, 128, 96), 777, 3, cfg),
+             # the reference's own smoke configuration (atten_unet_model.py:2034-2051: conv-form resampling, 8-channel heads,
+             # 2-D context) on a volume whose coarsest grid is odd (11 x 16 x 11)
+             ("atten_unet_smoke_1x44x64x44", (1, 44, 64, 44), 777, 2, OA.SMOKE_CFG))
     only = sys.argv[1:]
-    for name, shape, seed, stride in cases:
+    for name, shape, seed, stride, case_cfg in cases:
         if only and name not in only:
             continue
-        model = AttenUNet(**cfg).train()
+        model = AttenUNet(**case_cfg).train()
         OA.randomize_(model.named_parameters(), seed=seed)
-        x, ctx, tgt = synth(shape, seed)
+        x, ctx, tgt = synth(shape, seed, case_cfg["cross_attention_dim"])
+        if case_cfg is OA.SMOKE_CFG:
+            ctx = ctx[:, 0]                       # [N, C]: the x.dim() < 3 -> unsqueeze branch (:110-112)
         y = model(x, ctx)
         loss = torch.nn.L1Loss()(y, tgt)
         loss.backward()

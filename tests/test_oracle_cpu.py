@@ -87,3 +87,124 @@ def test_oracle_matches_live_reference():
         assert torch.allclose(p.grad, go[k], atol=1e-6, rtol=1e-5), k
     for k, v in bo.items():
         assert torch.allclose(ref.state_dict()[k].float(), v.float(), atol=1e-6), k
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# AttenUNet / BMGAN oracles: pinned to the fixtures generated from the reference classes (make_golden_atten.py /
+# make_golden_bmgan.py) here on the CPU, and -- marker `reference` -- to the live classes imported over the MONAI stub.
+# ---------------------------------------------------------------------------------------------------------------------
+def _atten_inputs(shape, seed, cdim):
+    g = torch.Generator().manual_seed(seed)
+    n, d, h, w = shape
+    return (torch.rand(n, 1, d, h, w, generator=g), torch.rand(n, 1, cdim, generator=g), torch.rand(n, 1, d, h, w, generator=g))
+
+
+@pytest.mark.parametrize("name,cfg_name", [("atten_unet_2x32x48x32", "TRAINING_JSON"), ("atten_unet_smoke_1x44x64x44", "SMOKE_CFG")])
+def test_atten_unet_oracle_matches_golden(name, cfg_name):
+    from oracle import atten_unet as OA
+    cfg = getattr(OA, cfg_name)
+    gold = np.load(os.path.join(GOLD, name + ".npz"))
+    shape, seed = tuple(int(v) for v in gold["shape"]), int(gold["seed"])
+    st = int(gold["stride"]) if "stride" in gold.files else 1
+    sd = OA.init_state_dict(cfg, seed=seed)                       # randomize_ by NAME == what the fixture script drew
+    for k, v in sd.items():
+        ref = float(gold["wsum/" + k])
+        assert abs(float(v.double().abs().sum()) - ref) <= 1e-6 * max(1.0, ref), k
+    x, ctx, tgt = _atten_inputs(shape, seed, cfg["cross_attention_dim"])
+    if cfg_name == "SMOKE_CFG":
+        ctx = ctx[:, 0]                                            # 2-D context (atten_unet_model.py:110-112)
+    loss, y, grads = OA.train_step(x, ctx, tgt, sd, cfg)
+    assert abs(float(loss) - float(gold["loss"])) < 1e-6
+    assert np.abs(y.numpy()[:, :, ::st, ::st, ::st] - gold["output"]).max() < 1e-5
+    tot = 0.0
+    for k, g in grads.items():
+        ref = float(gold["gradnorm/" + k])
+        tot += g.double().norm().item() ** 2
+        # (biases in front of a GroupNorm have a mathematically zero gradient: what is left is fp32 rounding noise)
+        assert abs(g.double().norm().item() - ref) <= 1e-4 * ref + 1e-7 * float(gold["grad_norm_total"]), k
+    assert abs(tot ** 0.5 - float(gold["grad_norm_total"])) <= 1e-5 * float(gold["grad_norm_total"])
+
+
+def test_atten_unet_oracle_shapes_and_zero_init_quirk():
+    from oracle import atten_unet as OA
+    shapes = OA.param_shapes()
+    assert len(shapes) == 416 and sum(int(np.prod(s)) for s in shapes.values()) == 12562945
+    assert shapes["down_blocks.3.attentions.0.transformer_blocks.0.attn2.to_k.weight"] == (128, 5)
+    assert "down_blocks.0.downsampler.op.conv.weight" in OA.param_shapes(OA.SMOKE_CFG)
+
+
+def test_bmgan_oracle_matches_golden():
+    """Forward of the small dense U-Net generator + both loss terms against the fixture generated from the reference's
+    bmgan_model.py (the backward of this case is covered on the GPU box, where the test time is not a concern)."""
+    from oracle import bmgan as OB
+    SMALL = dict(input_conv_channel=64, output_conv_channel=64, down_channels=[64, 128, 128, 128], middle_channels=[128],
+                 up_channels=[128, 128, 128, 128, 64])
+    gold = np.load(os.path.join(GOLD, "bmgan_small_2x64x96x64.npz"))
+    shape, seed = tuple(int(v) for v in gold["shape"]), int(gold["seed"])
+    torch.manual_seed(seed)
+    gen, disc = OB.DenseUnetGenerator(**SMALL).train(), OB.PatchDiscriminatorWrapper().train()
+    for k, v in list(gen.state_dict().items()) + [("D." + k, v) for k, v in disc.state_dict().items()]:
+        if v.dtype.is_floating_point:                             # same construction order => same seeded init
+            ref = float(gold["wsum/" + k])
+            assert abs(float(v.double().abs().sum()) - ref) <= 1e-6 * max(1.0, ref), k
+    g = torch.Generator().manual_seed(seed)
+    n, d, h, w = shape
+    t1, pet = torch.rand(n, 1, d, h, w, generator=g), torch.rand(n, 1, d, h, w, generator=g) * 2 - 1
+    z = torch.randn(n, 8, generator=g)
+    with torch.no_grad():
+        loss, adv, l1, fake = OB.generator_step(gen, disc, t1, pet, z)
+    assert abs(loss.item() - float(gold["g_loss"])) <= 1e-5 * abs(float(gold["g_loss"]))
+    assert abs(adv.item() - float(gold["g_adv"])) <= 1e-5 * abs(float(gold["g_adv"]))
+    assert np.abs(fake.numpy()[:, :, ::2, ::2, ::2] - gold["fake_sample"]).max() < 1e-4
+
+
+@pytest.mark.reference
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "unet", "utils")), reason="reference checkout not mounted")
+@pytest.mark.parametrize("cfg_name", ["TRAINING_JSON", "SMOKE_CFG"])
+def test_atten_unet_oracle_matches_live_reference(cfg_name):
+    from oracle import atten_unet as OA
+    from oracle import monai_stub
+    monai_stub.install_atten()
+    if REF not in sys.path:
+        sys.path.insert(0, REF)
+    from unet.utils.atten_unet_model import AttenUNet
+    cfg = getattr(OA, cfg_name)
+    model = AttenUNet(**cfg).train()
+    OA.randomize_(model.named_parameters(), seed=3)
+    assert {k: tuple(v.shape) for k, v in model.state_dict().items()} == OA.param_shapes(cfg)
+    x, ctx, tgt = _atten_inputs((1, 16, 32, 24), 4, cfg["cross_attention_dim"])
+    y = model(x, ctx)
+    loss = (y - tgt).abs().mean()
+    loss.backward()
+    lo, yo, go = OA.train_step(x, ctx, tgt, {k: v.detach().clone() for k, v in model.state_dict().items()}, cfg)
+    assert abs(float(loss) - float(lo)) < 1e-6 and (y.detach() - yo).abs().max().item() < 1e-5
+    for k, p in model.named_parameters():
+        g = p.grad if p.grad is not None else torch.zeros_like(p)
+        assert torch.allclose(g, go[k], atol=1e-6, rtol=1e-4), k
+
+
+@pytest.mark.reference
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "bl_methods", "BMGAN")), reason="reference checkout not mounted")
+def test_bmgan_oracle_matches_live_reference():
+    import importlib
+    from oracle import bmgan as OB
+    from oracle import monai_stub
+    monai_stub.install()
+    p = os.path.join(REF, "bl_methods", "BMGAN")
+    if p not in sys.path:
+        sys.path.insert(0, p)
+    ref = importlib.import_module("bmgan_model")
+    tiny = dict(input_conv_channel=8, output_conv_channel=8, down_channels=[8, 16, 16, 16], middle_channels=[16],
+                up_channels=[16, 16, 16, 16, 8])
+    torch.manual_seed(2)
+    rg, rd, re_ = ref.dense_unet_generator(**tiny).train(), ref.patch_discriminator().train(), ref.ResNet_encoder().train()
+    og, od, oe = OB.DenseUnetGenerator(**tiny).train(), OB.PatchDiscriminatorWrapper().train(), OB.ResNetEncoder().train()
+    og.load_state_dict(rg.state_dict()); od.load_state_dict(rd.state_dict()); oe.load_state_dict(re_.state_dict())   # same keys
+    g = torch.Generator().manual_seed(2)
+    t1, z = torch.rand(1, 1, 64, 64, 64, generator=g), torch.randn(1, 8, generator=g)
+    yr, yo = rg(t1, z), og(t1, z)
+    assert (yr - yo).abs().max().item() < 1e-6
+    assert (rd(yr) - od(yo)).abs().max().item() < 1e-6
+    vol = torch.rand(1, 1, 128, 128, 128, generator=g)
+    (mr, lr_), (mo, lo) = re_(vol), oe(vol)
+    assert (mr - mo).abs().max().item() < 1e-5 and (lr_ - lo).abs().max().item() < 1e-5
