@@ -1309,8 +1309,13 @@ def main():
     ap.add_argument("--batch", type=int, default=1, help="inference workloads: volumes per step and GPU (1..16)")
     ap.add_argument("--profile-one-step", action="store_true",
                     help="bracket ONE eager step of the roofline leg with cudaProfilerStart/Stop (ncu --profile-from-start off)")
+    ap.add_argument("--train-batch", type=int, default=0,
+                    help="experiments only: override the per-GPU batch of a training workload (the config then differs "
+                         "from BASELINE's; the line says so in config.per_gpu_batch)")
     args = ap.parse_args()
     ngf, shape, batch = WORKLOADS[args.workload]
+    if args.train_batch > 0 and not args.workload.startswith("infer"):
+        batch = args.train_batch
     if args.workload.startswith("infer"):
         if args.impl == "reference":
             print(json.dumps({"impl": "reference", "unavailable": "inference workloads have no CPU arm in this round; "

@@ -28,7 +28,7 @@ import torch.nn as nn
 from . import graph, ops
 from ._cabi import check, lib, ptr, stream_ptr
 from .bmgan_model import _EngineBase
-from .graph import (AttentionOp, Buf, ConvOp, CovariateBiasOp, GegluOp, LayerNormOp, NormActOp, ResampleOp, Sl, Tape)
+from .graph import (AttentionOp, Buf, ConvOp, CovariateBiasOp, DropoutOp, GegluOp, LayerNormOp, NormActOp, ResampleOp, Sl, Tape)
 
 
 def zero_module(module: nn.Module) -> nn.Module:
@@ -587,7 +587,9 @@ class DiffusionModelEncoder(nn.Module):
     order, ``Linear -> ReLU -> Dropout(0.1) -> Linear`` -- and documents what it decides: ``timesteps`` is accepted and
     ignored (the scripts always pass zeros), ``time_embed`` holds parameters that nothing reads, and the head's input width is
     the constructor argument ``head_in_features`` (default 4096 as written; 4608 for the reference crop).
-    Inference only (``eval()`` + ``no_grad``): that is what configs[4] runs."""
+    Forward and backward: ``eval()`` + ``no_grad`` is what configs[4] runs; with gradients enabled the module is differentiable
+    w.r.t. its parameters (the training step of train_atten_encoder_MCI.py:169-175: logits -> weighted cross-entropy ->
+    backward -> Adam; ``time_embed`` receives exact zero gradients)."""
 
     def __init__(self, spatial_dims: int, in_channels: int, out_channels: int,
                  num_res_blocks: Sequence[int] | int = (2, 2, 2, 2), num_channels: Sequence[int] = (32, 64, 64, 64),
@@ -652,8 +654,6 @@ class DiffusionModelEncoder(nn.Module):
             raise RuntimeError("petsyn DiffusionModelEncoder runs on CUDA (sm_100a) only; there is no CPU path")
         if x.dim() != 5 or x.shape[1] != 1:
             raise ValueError(f"expected x of shape [N, 1, D, H, W], got {tuple(x.shape)}")
-        if self.training or torch.is_grad_enabled():
-            raise NotImplementedError("petsyn DiffusionModelEncoder is inference-only: call .eval() under torch.no_grad()")
         x = x.contiguous().float()
         ctx = context.reshape(x.shape[0], -1).contiguous().float()
         if ctx.shape[1] != self.cfg["cross_attention_dim"]:
@@ -663,6 +663,8 @@ class DiffusionModelEncoder(nn.Module):
         if eng is None:
             eng = _ClsEngine(self, tuple(x.shape), x.device)
             self._engines[key] = eng
+        if torch.is_grad_enabled() and any(p.requires_grad for p in eng.params):
+            return _AttenFn.apply(eng, x, ctx, *eng.params)      # train_atten_encoder_MCI.py:169-175: predict -> CE -> backward
         return eng.forward(x, ctx).clone()
 
 
@@ -699,44 +701,40 @@ class _ClsEngine(_AttenEngine):
             raise ValueError(f"the encoder produces {h.c} x {h.d}x{h.h}x{h.w} = {feats} features for this input but the head "
                              f"was built with head_in_features={lin1.in_features} (the vendored class hard-codes 4096, "
                              "atten_unet_model.py:1987; a 96x128x96 input needs 4608)")
-        self.vox, self.fc = h.rows // n, h.c
+        vox, fc = h.rows // n, h.c
         flat = h.alias(n, 1, 1, 1, feats, "cls.flat")
-        self.lin1, self.lin2 = lin1, lin2
-        self.w1 = torch.zeros(512, feats, 1, 1, 1, dtype=torch.float32, device=dev)
-        self.plan1 = ops.ConvPlan(ops.OP_CONV, n, 1, 1, 1, feats, 512, 1, 1, 0, act=ops.ACT_RELU)
-        self.hid = torch.zeros(n, 512, dtype=torch.bfloat16, device=dev)
-        self.w2 = torch.zeros(16, 512, 1, 1, 1, dtype=torch.float32, device=dev)
-        self.b2 = torch.zeros(16, dtype=torch.float32, device=dev)
-        self.plan2 = ops.ConvPlan(ops.OP_CONV, n, 1, 1, 1, 512, 16, 1, 1, 0, y_fp32=True)
-        self.logits = torch.zeros(n, 16, dtype=torch.float32, device=dev)
-        self.flat = flat
-        self._head_ver = None
+        # head (atten_unet_model.py:1987): Linear -> ReLU -> Dropout(0.1) -> Linear on nn.Flatten() of the NCDHW map.  Flatten
+        # order is (c, voxel), the channels-last buffer is (voxel, c): input column c * vox + v of linear1 reads position
+        # v * C + c -- a channel index map of the weight staging, like the padded attention heads.
+        perm = [v * fc + c for c in range(fc) for v in range(vox)]
+        l1 = self._conv(flat.sl(), lin1, ksize=1, stride=1, pad=0, name="cls.linear1", in_index=perm)
+        hid = Buf(n, 1, 1, 1, 512, dev, "cls.hid")
+        t.add(NormActOp(l1.z, "none", ops.ACT_RELU, [hid.sl()]))
+        t.add(DropoutOp(hid, net.out[2]))
+        self.head = self._conv(hid.sl(), lin2, ksize=1, stride=1, pad=0, y_fp32=True, name="cls.linear2")
+        self.nout = lin2.out_features
+        self._zero_params += list(net.time_embed.parameters())          # parameters nothing reads: exact zero gradients
+        t.add(self.zero)
         self._finish()
-
-    def _pack_head(self) -> None:
-        l1, l2 = self.lin1, self.lin2
-        ver = (l1.weight._version, l1.weight.data_ptr(), l2.weight._version, l2.weight.data_ptr(), l1.bias._version,
-               l2.bias._version)
-        if ver == self._head_ver:
-            return
-        # nn.Flatten order is (c, voxel); the channels-last buffer is (voxel, c)
-        self.w1[:, :, 0, 0, 0].copy_(l1.weight.detach().view(512, self.fc, self.vox).permute(0, 2, 1).reshape(512, -1))
-        self.plan1.pack(self.w1, need_dgrad=False)
-        oc = l2.out_features
-        self.w2.zero_()
-        self.w2[:oc, :, 0, 0, 0].copy_(l2.weight.detach())
-        self.b2.zero_()
-        self.b2[:oc].copy_(l2.bias.detach())
-        self.plan2.pack(self.w2, need_dgrad=False)
-        self._head_ver = ver
+        for p in self._zero_params:
+            if all(p is not q for q in self.params):
+                self.params.append(p)
 
     def forward(self, x: torch.Tensor, context: torch.Tensor) -> torch.Tensor:
         n, _, D, H, W = self.shape
+        self.generation += 1
         self.context = context
         check(lib.petsyn_concat_latent(ptr(x), ptr(x), ptr(self.inp.t), D * H * W, n, 0, self.CPAD, stream_ptr()),
               "concat_latent")
-        self.tape.forward(False)
-        self._pack_head()
-        self.plan1.fprop(self.flat.t, self.hid, self.lin1.bias.detach())      # Linear + ReLU (Dropout is identity in eval)
-        self.plan2.fprop(self.hid, self.logits, self.b2)
-        return self.logits[:, :self.lin2.out_features]
+        self.tape.forward(self.training())
+        return self.head.zf[:, :self.nout]
+
+    def backward(self, dlogits: torch.Tensor, out: Optional[Dict[int, torch.Tensor]] = None, on_ready=None):
+        grads = self.grad_slots(out)
+        self.head.zg.zero_()
+        self.head.zg[:, :self.nout].copy_(dlogits)
+        self.run_backward(on_ready)
+        if on_ready is not None:
+            for p in self._zero_params:
+                on_ready(p)
+        return [g.clone() for g in grads] if out is None else []

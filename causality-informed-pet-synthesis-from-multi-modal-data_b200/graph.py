@@ -76,6 +76,8 @@ class RunState:
     # forwards, one backward: train_bmgan.py:170-180): BatchNorm normalises with the batch statistics again but must
     # not move its running statistics / num_batches_tracked a second time.
     freeze_running_stats = False
+    # weight-gradient kernels were queued on the side stream and have not been joined into the main stream yet
+    side_pending = False
 
 
 def _side_stream(dev) -> torch.cuda.Stream:
@@ -168,6 +170,11 @@ class ConvOp(Op):
         # capture keeps as a branch): layers whose kernels cannot fill 148 SMs (deep levels, transformer linears) overlap
         # fully, large ones overlap their ramp-up / tail.  Measured on configs[1]: 18.54 -> 17.82 ms per step.
         self.fork_bwd = not os.environ.get("PETSYN_NO_FORK")
+        # "wgrad": the WEIGHT gradient (with its reduce / unpack launches) runs on the side stream and is only joined at the end
+        # of the tape's backward (or where a gradient bucket closes), so it overlaps the critical chain data gradient ->
+        # normalisation backward -> next data gradient, whose HBM-bound norm kernels use other resources than the
+        # shared-memory-bound weight-gradient kernels.  "dgrad" (round 1): the data gradient forks, joined inside the op.
+        self.fork_mode = os.environ.get("PETSYN_FORK_MODE", "wgrad")
         self.acc_dx = False
         self.colsum_done = False  # set by the NormActOp consuming z when it already summed dz over the rows (bias gradient)
         self.acc_dw = False      # add into grad_w / grad_b instead of overwriting (several backward calls per step)
@@ -271,52 +278,75 @@ class ConvOp(Op):
         else:
             self.plan.dgrad(dz, self.x.buf.g)
 
+    def _bwd_dw(self, dz: torch.Tensor) -> None:
+        """Weight (and bias) gradient of this conv into grad_w / grad_b."""
+        # bias gradient: column sums of dy (a by-product of the normalisation backward that wrote dy last, else a pass of
+        # its own) sit in a float64 accumulator; the weight-gradient launch converts them into the fp32 slot
+        bkw = {}
+        if self.bias is not None:
+            if self.use_bias:
+                if self.colsum_done:
+                    self.colsum_done = False
+                else:
+                    dsl = self.dy_slice()
+                    cs, co = (dsl.buf.c, dsl.off) if dsl is not None else (self.cout, 0)
+                    check(lib.petsyn_colsum(ptr(dz), cs, co, ptr(self.dbias_stage), dz.shape[0], self.cout,
+                                            stream_ptr()), "colsum")
+                if self.grad_b.is_contiguous() and not self.padded:
+                    bkw = dict(dbias_acc=self.dbias_stage, dbias=self.grad_b)
+            elif not self.acc_dw and self._zero_b != self.grad_b.data_ptr():
+                # a bias in front of a non-affine InstanceNorm has exactly zero gradient and nothing ever writes its
+                # slot: cleared once per binding instead of once per step
+                self.grad_b.zero_()
+                self._zero_b = self.grad_b.data_ptr()
+        if self.padded:
+            self.plan.wgrad(self.x.buf.t, dz, self.dw_stage, scratch=self.wg_scratch, **bkw)
+            part = self._dw_part().reshape(self.grad_w.shape)
+            if self.acc_dw:
+                self.grad_w.add_(part)
+            else:
+                self.grad_w.copy_(part)
+        else:
+            self.plan.wgrad(self.x.buf.t, dz, self.grad_w, accumulate=self.acc_dw, scratch=self.wg_scratch, **bkw)
+        if self.bias is not None and self.use_bias and not bkw:
+            if self.acc_dw:
+                self.grad_b.add_(self._db_part())
+            else:
+                self.grad_b.copy_(self._db_part())
+
     def bwd(self) -> None:
         dz = self.dout()
         fork = self.fork_bwd and self.need_dw and self.need_dx
+        if self.fork_bwd and self.need_dw and self.fork_mode == "wgrad":
+            # EVERY weight gradient of the tape goes to the side stream, also the ones without a data gradient to overlap
+            # (conv_in): they share one scratch image, so they must stay serialised among themselves
+            main, side = torch.cuda.current_stream(), _side_stream(dz.device)
+            side.wait_stream(main)                       # dy (and the bias column sums) are final on the main stream here
+            with torch.cuda.stream(side):
+                self._bwd_dw(dz)
+            RunState.side_pending = True                 # joined by Tape.backward / GradBucketer.on_ready
+            if self.need_dx:
+                self._bwd_dx(dz)
+            return
         if fork:
             main, side = torch.cuda.current_stream(), _side_stream(dz.device)
             side.wait_stream(main)
             with torch.cuda.stream(side):
                 self._bwd_dx(dz)
         if self.need_dw:
-            # bias gradient: column sums of dy (a by-product of the normalisation backward that wrote dy last, else a pass of
-            # its own) sit in a float64 accumulator; the weight-gradient launch converts them into the fp32 slot
-            bkw = {}
-            if self.bias is not None:
-                if self.use_bias:
-                    if self.colsum_done:
-                        self.colsum_done = False
-                    else:
-                        dsl = self.dy_slice()
-                        cs, co = (dsl.buf.c, dsl.off) if dsl is not None else (self.cout, 0)
-                        check(lib.petsyn_colsum(ptr(dz), cs, co, ptr(self.dbias_stage), dz.shape[0], self.cout,
-                                                stream_ptr()), "colsum")
-                    if self.grad_b.is_contiguous() and not self.padded:
-                        bkw = dict(dbias_acc=self.dbias_stage, dbias=self.grad_b)
-                elif not self.acc_dw and self._zero_b != self.grad_b.data_ptr():
-                    # a bias in front of a non-affine InstanceNorm has exactly zero gradient and nothing ever writes its
-                    # slot: cleared once per binding instead of once per step
-                    self.grad_b.zero_()
-                    self._zero_b = self.grad_b.data_ptr()
-            if self.padded:
-                self.plan.wgrad(self.x.buf.t, dz, self.dw_stage, scratch=self.wg_scratch, **bkw)
-                part = self._dw_part().reshape(self.grad_w.shape)
-                if self.acc_dw:
-                    self.grad_w.add_(part)
-                else:
-                    self.grad_w.copy_(part)
-            else:
-                self.plan.wgrad(self.x.buf.t, dz, self.grad_w, accumulate=self.acc_dw, scratch=self.wg_scratch, **bkw)
-            if self.bias is not None and self.use_bias and not bkw:
-                if self.acc_dw:
-                    self.grad_b.add_(self._db_part())
-                else:
-                    self.grad_b.copy_(self._db_part())
+            self._bwd_dw(dz)
         if fork:
             main.wait_stream(side)
         elif self.need_dx:
             self._bwd_dx(dz)
+
+
+def join_side_stream(dev=None) -> None:
+    """Make the current stream wait for the weight-gradient work queued on the side stream (no-op when nothing is pending)."""
+    if RunState.side_pending:
+        d = dev if dev is not None else torch.device("cuda", torch.cuda.current_device())
+        torch.cuda.current_stream().wait_stream(_side_stream(d))
+        RunState.side_pending = False
 
 
 # debugging / A-B switch: run norm finalize and the backward group combine as their own launches (the first version)
@@ -641,6 +671,28 @@ class CovariateBiasOp(Op):
                                             self.n, ctx.shape[1], self.t.c, self.L, stream_ptr()), "covariate_bias_bwd")
 
 
+class DropoutOp(Op):
+    """nn.Dropout(p) on a small token buffer, in place (the classifier head: Linear -> ReLU -> Dropout(0.1) -> Linear,
+    atten_unet_model.py:1987).  The mask comes from torch's device generator (one rand launch on a [N, 512] tensor); identity
+    in eval mode or with p == 0."""
+
+    def __init__(self, x: Buf, module: torch.nn.Dropout):
+        self.x, self.module = x, module
+        self.mask: Optional[torch.Tensor] = None
+
+    def fwd(self, training: bool) -> None:
+        p = float(self.module.p)
+        if not training or p == 0.0:
+            self.mask = None
+            return
+        self.mask = (torch.rand(self.x.t.shape, device=self.x.t.device) >= p).to(torch.bfloat16) / (1.0 - p)
+        self.x.t.mul_(self.mask)
+
+    def bwd(self) -> None:
+        if self.mask is not None:
+            self.x.g.mul_(self.mask)
+
+
 class Tape:
     """Ordered op list with static gradient write/accumulate analysis."""
 
@@ -857,6 +909,7 @@ class Tape:
                 op.bwd()
             if on_op_done is not None:
                 on_op_done(op)
+        join_side_stream()                                # weight gradients queued on the side stream
 
     def flops(self) -> float:
         return sum(getattr(op, "flops", 0.0) for op in self.ops)

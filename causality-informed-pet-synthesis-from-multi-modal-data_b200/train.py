@@ -77,6 +77,8 @@ class GradBucketer:
         view = self.arena.g[start:end]
         op = dist.ReduceOp.AVG if self._avg else dist.ReduceOp.SUM
         if self.cuda:
+            from .graph import join_side_stream
+            join_side_stream(self.arena.g.device)      # weight gradients of this bucket may still run on the side stream
             ev = torch.cuda.Event()
             ev.record()                                # compute stream: bucket i is complete after this point
             self.comm_stream.wait_event(ev)
@@ -112,6 +114,8 @@ class GraphSegments:
         self._ctx.__enter__()
 
     def cut(self, action) -> None:
+        from .graph import join_side_stream
+        join_side_stream()                           # a capture may only end with its forked weight-gradient branch joined
         self._ctx.__exit__(None, None, None)
         self.items.append((self._g, action))
         self.open()
@@ -736,6 +740,8 @@ class AttenUNetTrainer(_CheckpointMixin):
             def cut(prm) -> None:                    # called right after the op that completes prm's gradient
                 if id(prm) not in closers:
                     return
+                from .graph import join_side_stream
+                join_side_stream()                   # a capture may only end with its forked weight-gradient branch joined
                 cur["ctx"].__exit__(None, None, None)
                 segments.append((cur["g"], prm))
                 cur["g"] = torch.cuda.CUDAGraph()

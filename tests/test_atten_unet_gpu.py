@@ -206,9 +206,12 @@ def test_adversarial_step_matches_oracle(petsyn):
             # lr * g / (|g| + eps), anywhere in [0, lr]; all others by lr)
             assert abs(moved - moved_ref) <= 1.0 * G_LR + 1e-9, (k, moved, moved_ref)
         assert max((named[k].detach().cpu() - sd[k]).abs().max().item() for k in sd) >= 0.9 * G_LR
+        # D followed the oracle's Adam(disc_lr) step: the first Adam step moves a weight by +-lr with the SIGN of its gradient, so
+        # an element whose gradient is rounding noise may end 2 lr away from the oracle's; nearly all must coincide
         d0 = dict(od.named_parameters())
-        dmoved = max((dn[k].detach().cpu() - d0[k].detach()).abs().max().item() for k in d0)
-        assert dmoved <= 0.5 * 1e-4, dmoved                     # D followed the oracle's Adam(disc_lr) step
+        diffs = torch.cat([(dn[k].detach().cpu() - d0[k].detach()).abs().flatten() for k in d0])
+        assert diffs.max().item() <= 2.1e-4, diffs.max().item()
+        assert (diffs < 0.5e-4).float().mean().item() > 0.97, (diffs < 0.5e-4).float().mean().item()
         assert int(tr.step_dev.item()) == 1 and int(tr.d_step_dev.item()) == 1
 
 
