@@ -67,6 +67,19 @@ class NormActDesc(C.Structure):
         ("z_cstride", C.c_int32), ("z_coff", C.c_int32), ("dz_cstride", C.c_int32), ("dz_coff", C.c_int32),
         ("extra", C.c_void_p), ("extra_cstride", C.c_int32), ("extra_coff", C.c_int32),
         ("dz_colsum_coff", C.c_int32), ("dz_colsum_c", C.c_int32),
+        ("sums_precomputed", C.c_int32),
+    ]
+
+
+class ConvEpilogue(C.Structure):
+    """``petsyn_conv_epilogue`` (include/petsyn.h)."""
+    _fields_ = [
+        ("side", C.c_void_p), ("side_cstride", C.c_int32), ("side_coff", C.c_int32), ("add_side", C.c_int32),
+        ("stats1", C.c_void_p), ("stats1_c", C.c_int32), ("stats1_coff", C.c_int32),
+        ("stats2", C.c_void_p), ("stats2_c", C.c_int32), ("stats2_coff", C.c_int32),
+        ("norm_scale", C.c_void_p), ("norm_shift", C.c_void_p), ("norm_mean", C.c_void_p), ("norm_rstd", C.c_void_p),
+        ("norm_act", C.c_int32), ("norm_slope", C.c_float),
+        ("bsums", C.c_void_p),
     ]
 
 
@@ -99,6 +112,9 @@ SIGNATURES = {
     "petsyn_conv_fprop": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp]),
     "petsyn_conv_dgrad": (_i32, [_vp, _vp, _vp, _vp, _vp]),
     "petsyn_conv_dgrad_accumulate": (_i32, [_vp, _vp, _vp, _vp, _vp]),
+    "petsyn_conv_epilogue_supported": (_i32, [_vp, _i32]),
+    "petsyn_conv_fprop_epi": (_i32, [_vp, _vp, _vp, _vp, _vp, C.POINTER(ConvEpilogue), _vp]),
+    "petsyn_conv_dgrad_epi": (_i32, [_vp, _vp, _vp, _vp, C.POINTER(ConvEpilogue), _vp]),
     "petsyn_conv_wgrad": (_i32, [_vp, _vp, _vp, _vp, _vp, _i32, _vp]),
     "petsyn_conv_wgrad_bias": (_i32, [_vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _i32, _vp]),
     "petsyn_stem_col2im_k4s2": (_i32, [_vp, _vp, _i32, _i32, _i32, _i32, _vp]),

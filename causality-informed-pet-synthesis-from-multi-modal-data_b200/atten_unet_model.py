@@ -22,6 +22,8 @@ from __future__ import annotations
 
 from typing import Dict, List, Optional, Sequence, Tuple
 
+import os
+
 import torch
 import torch.nn as nn
 
@@ -318,6 +320,19 @@ class _ZeroGrad(graph.Op):
             self._zeroed = key
 
 
+_EPI_PROBE: Dict[Tuple, bool] = {}
+
+
+def _residual_epilogue_ok(n: int, d: int, h: int, w: int, c: int) -> bool:
+    """Can a Conv3d(c -> c, k3 s1 p1) on this grid add its residual in the kernel epilogue (petsyn_conv_fprop_epi)?"""
+    if os.environ.get("PETSYN_NO_EPI_RES"):
+        return False
+    key = (n, d, h, w, c)
+    if key not in _EPI_PROBE:
+        _EPI_PROBE[key] = ops.ConvPlan(ops.OP_CONV, n, d, h, w, c, c, 3, 1, 1).epi_ok[0]
+    return _EPI_PROBE[key]
+
+
 class _AttenEngine(_EngineBase):
     CPAD = 16
 
@@ -471,6 +486,18 @@ class _AttenEngine(_EngineBase):
             c1 = self._conv(a1.sl(), rb.conv1.conv, ksize=3, stride=1, pad=1, name=name + ".conv1")
         a2 = Buf(n, od, oh, ow, cout, dev, name + ".a2")
         self._gn_act(c1.z, rb.norm2, ops.ACT_SILU, a2)
+        if _residual_epilogue_ok(n, od, oh, ow, cout):
+            # the residual sum happens in conv2's epilogue (the tile is added to the skip tile before it is stored, and summed
+            # for the GroupNorm that reads the block output): no pass of its own.  A 1x1 skip convolution first writes its
+            # result into the output slot, where conv2's epilogue picks it up and overwrites it with the sum.
+            if identity:
+                res = xs
+            else:
+                sk = self._conv(xs, rb.skip_connection.conv, ksize=1, stride=1, pad=0, name=name + ".skip", out=out)
+                sk.absorbed = True
+                res = out
+            self._conv(a2.sl(), rb.conv2.conv, ksize=3, stride=1, pad=1, name=name + ".conv2", out=out, res=res)
+            return out
         c2 = self._conv(a2.sl(), rb.conv2.conv, ksize=3, stride=1, pad=1, name=name + ".conv2", dy_from=out)
         if identity:
             res = xs

@@ -19,6 +19,7 @@
 #include "common.h"
 #include "igemm_kernels.cuh"
 #include "slab_kernels.cuh"
+#include "slab_epi_kernel.cuh"
 
 namespace petsyn {
 
@@ -434,6 +435,12 @@ struct GemmSide {           // one gather-form GEMM (fprop or dgrad)
   bool slab3 = false;       // depth-folded kernel (slab_conv3_kernel): three depth taps per MMA
   int slab_grid = 0, slab_smem = 0;
   SlabParams sparams;
+  // fused-epilogue variant of the depth-folded slab kernel (slab_epi_kernel.cuh); geometry re-planned for its smem footprint
+  SlabParams eparams;
+  SlabEpi epi;
+  int epi_grid = 0, epi_smem = 0;
+  const void* ekey_a = nullptr; const void* ekey_b = nullptr; const void* ekey_c = nullptr; const void* ekey_side = nullptr;
+  int ekey_cs = -1, ekey_co = -1;
 };
 
 struct ViewSpec {           // an NDHWC tensor (channel slice) and how to derive its tensor maps
@@ -700,6 +707,79 @@ static int32_t run_slab(GemmSide& g, cudaStream_t st) {
     case 4: return launch_slab<4>(g, st);
     default: return fail(PETSYN_EINVAL, "slab path: unsupported channel count %d", g.Kc);
   }
+}
+
+// ---------------------------------------------------------------------------------------------- fused epilogue
+static bool epi_supported(const GemmSide& g, int batch) {
+  if (!g.slab || g.slab_halo != 1 || g.out_fp32 || getenv("PETSYN_NO_EPI") != nullptr || getenv("PETSYN_NO_SLAB3") != nullptr)
+    return false;
+  if (!(g.R == 16 || g.R == 32) || g.Kc % 16 != 0 || g.Kc / 16 < 1 || g.Kc / 16 > 3 || batch > kEpiMaxBatch) return false;
+  const int atoms = g.Kc / 16;
+  const int slab_b = (atoms * kSlabWp * kSlabHp * 32 + 1023) / 1024 * 1024;
+  if (slab3_smem_bytes(atoms, g.R, slab_b, 4, 2) > 200 * 1024) return false;          // same bound as bind_slab's slab3 choice
+  return slab3_smem_bytes(atoms, g.R, slab_b, 4, 2) + slab3_epi_extra_bytes(g.R, 2, batch) <= 224 * 1024;
+}
+
+// `g` has been bound by bind_slab for (a, b, c); plan the fused variant and fill its epilogue block
+static int32_t run_slab_epi(GemmSide& g, const ViewSpec& va, const ViewSpec& vc, const void* a, const void* b, const void* c,
+                            const petsyn_conv_epilogue* ep, bool is_dgrad, cudaStream_t st) {
+  if (!g.slab3) return fail(PETSYN_EINVAL, "fused epilogue needs the depth-folded slab kernel");
+  static const petsyn_conv_epilogue none = {};
+  const bool plain = ep == nullptr;       // the same kernel template without epilogue work (channel counts known at compile time)
+  if (plain) ep = &none;
+  if (g.accumulate && !plain) return fail(PETSYN_EINVAL, "fused epilogue cannot add into the destination");
+  const int N = g.R, atoms = g.Kc / 16;
+  const bool side = ep->side != nullptr;
+  PETSYN_REQUIRE(!(ep->add_side && !side), "add_side without a side tensor");
+  PETSYN_REQUIRE(plain || !is_dgrad || (side && ep->norm_scale && ep->norm_shift && ep->norm_mean && ep->norm_rstd && ep->bsums),
+                 "dgrad epilogue needs z and the normalisation constants");
+  PETSYN_REQUIRE(plain || is_dgrad || ep->add_side || ep->stats1 || ep->stats2, "empty epilogue");
+  SlabParams& p = g.eparams;
+  const int flags = plain ? 0 : ((ep->add_side ? kEpiSide : 0) | ((!is_dgrad && (ep->stats1 || ep->stats2)) ? kEpiStats : 0) |
+                                 (is_dgrad ? kEpiNormReduce : 0));
+  const bool rekey = !(g.ekey_a == a && g.ekey_b == b && g.ekey_c == c && g.ekey_side == ep->side &&
+                       g.ekey_cs == ep->side_cstride && g.ekey_co == ep->side_coff && g.epi.flags == flags);
+  if (rekey) {
+    p = g.sparams;
+    // shared-memory plan: a side ring of 4 tiles unless that costs a resident CTA (occupancy from the runtime: registers count)
+    const int fixed = slab3_smem_bytes(atoms, N, p.slab_bytes, 0, 2) + p.ring * p.slab_bytes;
+    const int smem4 = fixed + slab3_epi_extra_bytes(N, 4, va.N), smem2 = fixed + slab3_epi_extra_bytes(N, side ? 2 : 0, va.N);
+    const int occ4 = (side && smem4 <= 224 * 1024) ? slab3_epi_occupancy(atoms, N / 16, flags, smem4) : 0;
+    const int occ2 = slab3_epi_occupancy(atoms, N / 16, flags, smem2);
+    const int ring = (occ4 >= occ2 && occ4 > 0) ? 4 : 2;          // (without a side tensor the ring is never touched)
+    int occ = ring == 4 ? occ4 : occ2;
+    if (occ < 1) return fail(PETSYN_ECUDA, "fused epilogue kernel does not fit an SM (%d bytes of shared memory)", smem2);
+    if (getenv("PETSYN_DEBUG_PLAN"))
+      fprintf(stderr, "[petsyn] epi plan: atoms %d N %d flags %d side ring %d smem %d occ %d\n", atoms, N, flags, ring,
+              ring == 4 ? smem4 : smem2, occ);
+    g.epi.side_ring = side ? ring : 0;
+    g.epi_smem = ring == 4 ? smem4 : smem2;
+    if (const char* e = getenv("PETSYN_SLAB_OCC")) occ = std::max(1, std::min(atoi(e), occ));
+    const int ctas = 148 * occ;
+    slab_split(va.W, va.H, va.D, va.N, kSlabW, kSlabH, ctas, &p.dchunk, &p.nchunks, &p.items);
+    g.epi_grid = std::min(ctas, p.items);
+    if (side) {
+      ViewSpec vs = vc;
+      vs.cstride = ep->side_cstride > 0 ? ep->side_cstride : N;
+      vs.coff = ep->side_coff;
+      PETSYN_REQUIRE(vs.cstride % 8 == 0 && vs.coff % 8 == 0 && vs.coff + N <= vs.cstride, "bad side channel slice");
+      int32_t rc = view_map(&g.epi.e_map, ep->side, vs, false, 0, 2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, N, kSlabW, kSlabH, 1, 0);
+      if (rc) return rc;
+    }
+    g.ekey_a = a; g.ekey_b = b; g.ekey_c = c; g.ekey_side = ep->side; g.ekey_cs = ep->side_cstride; g.ekey_co = ep->side_coff;
+  }
+  // per-call scalars (bind_slab refreshed them in sparams)
+  p.bias = g.sparams.bias; p.epi_act = g.sparams.epi_act; p.epi_slope = g.sparams.epi_slope; p.reduce = g.sparams.reduce;
+  SlabEpi& e = g.epi;
+  e.flags = flags;
+  e.nact = ep->norm_act; e.nslope = ep->norm_slope;
+  e.st1 = ep->stats1; e.st1_c = ep->stats1_c; e.st1_off = ep->stats1_coff;
+  e.st2 = ep->stats2; e.st2_c = ep->stats2_c; e.st2_off = ep->stats2_coff;
+  PETSYN_REQUIRE(!e.st1 || (e.st1_off >= 0 && e.st1_off + N <= e.st1_c), "statistics channel range outside the target");
+  PETSYN_REQUIRE(!e.st2 || (e.st2_off >= 0 && e.st2_off + N <= e.st2_c), "statistics channel range outside the target");
+  e.nscale = ep->norm_scale; e.nshift = ep->norm_shift; e.nmean = ep->norm_mean; e.nrstd = ep->norm_rstd;
+  e.bsums = ep->bsums;
+  return slab3_epi_launch(atoms, N / 16, flags, p, e, g.epi_grid, g.epi_smem, st);
 }
 
 // tensor map of (a phase of) an NDHWC bf16/fp32 view; box = (box_c, bw, bh, bd, 1)
@@ -1281,6 +1361,8 @@ int32_t petsyn_conv_fprop(petsyn_conv_plan* pl, const void* x, const void* packe
   PETSYN_REQUIRE(pl && x && packed && y, "null argument");
   if (pl->fprop.slab) {
     int32_t rs = bind_slab(pl->fprop, pl->vx, pl->vy, x, packed, y, bias, pl->desc.epi_act, pl->desc.epi_slope);
+    if (!rs && epi_supported(pl->fprop, pl->desc.n) && pl->fprop.slab3)
+      return run_slab_epi(pl->fprop, pl->vx, pl->vy, x, packed, y, nullptr, false, as_stream(stream));
     return rs ? rs : run_slab(pl->fprop, as_stream(stream));
   }
   int32_t rc = bind_side(pl->fprop, pl->vx, pl->vy, x, packed, y, bias, pl->desc.epi_act, pl->desc.epi_slope);
@@ -1292,6 +1374,8 @@ int32_t petsyn_conv_dgrad(petsyn_conv_plan* pl, const void* dy, const void* pack
   PETSYN_REQUIRE(pl && dy && packed && dx, "null argument");
   if (pl->dgrad.slab) {
     int32_t rs = bind_slab(pl->dgrad, pl->vdy, pl->vdx, dy, packed, dx, nullptr, PETSYN_ACT_NONE, 0.f);
+    if (!rs && epi_supported(pl->dgrad, pl->desc.n) && pl->dgrad.slab3)
+      return run_slab_epi(pl->dgrad, pl->vdy, pl->vdx, dy, packed, dx, nullptr, true, as_stream(stream));
     return rs ? rs : run_slab(pl->dgrad, as_stream(stream));
   }
   int32_t rc = bind_side(pl->dgrad, pl->vdy, pl->vdx, dy, packed, dx, nullptr, PETSYN_ACT_NONE, 0.f);
@@ -1299,12 +1383,35 @@ int32_t petsyn_conv_dgrad(petsyn_conv_plan* pl, const void* dy, const void* pack
   return run_side(pl->dgrad, pl->vdx, dx, nullptr, PETSYN_ACT_NONE, 0.f, pl->desc.n, as_stream(stream));
 }
 
+int32_t petsyn_conv_epilogue_supported(const petsyn_conv_plan* pl, int32_t pass) {
+  if (!pl || pass < 0 || pass > 1) return 0;
+  return epi_supported(pass == 0 ? pl->fprop : pl->dgrad, pl->desc.n) ? 1 : 0;
+}
+
+int32_t petsyn_conv_fprop_epi(petsyn_conv_plan* pl, const void* x, const void* packed, const float* bias, void* y,
+                              const petsyn_conv_epilogue* epi, void* stream) {
+  PETSYN_REQUIRE(pl && x && packed && y && epi, "null argument");
+  PETSYN_REQUIRE(epi_supported(pl->fprop, pl->desc.n), "this plan's forward pass has no fused epilogue");
+  int32_t rs = bind_slab(pl->fprop, pl->vx, pl->vy, x, packed, y, bias, pl->desc.epi_act, pl->desc.epi_slope);
+  return rs ? rs : run_slab_epi(pl->fprop, pl->vx, pl->vy, x, packed, y, epi, false, as_stream(stream));
+}
+
+int32_t petsyn_conv_dgrad_epi(petsyn_conv_plan* pl, const void* dy, const void* packed, void* dx,
+                              const petsyn_conv_epilogue* epi, void* stream) {
+  PETSYN_REQUIRE(pl && dy && packed && dx && epi, "null argument");
+  PETSYN_REQUIRE(epi_supported(pl->dgrad, pl->desc.n), "this plan's data-gradient pass has no fused epilogue");
+  int32_t rs = bind_slab(pl->dgrad, pl->vdy, pl->vdx, dy, packed, dx, nullptr, PETSYN_ACT_NONE, 0.f);
+  return rs ? rs : run_slab_epi(pl->dgrad, pl->vdy, pl->vdx, dy, packed, dx, epi, true, as_stream(stream));
+}
+
 int32_t petsyn_conv_dgrad_accumulate(petsyn_conv_plan* pl, const void* dy, const void* packed, void* dx, void* stream) {
   PETSYN_REQUIRE(pl && dy && packed && dx, "null argument");
   pl->dgrad.accumulate = true;
   if (pl->dgrad.slab) {
     int32_t rs = bind_slab(pl->dgrad, pl->vdy, pl->vdx, dy, packed, dx, nullptr, PETSYN_ACT_NONE, 0.f);
-    if (!rs) rs = run_slab(pl->dgrad, as_stream(stream));
+    if (!rs) rs = (epi_supported(pl->dgrad, pl->desc.n) && pl->dgrad.slab3)
+                      ? run_slab_epi(pl->dgrad, pl->vdy, pl->vdx, dy, packed, dx, nullptr, true, as_stream(stream))
+                      : run_slab(pl->dgrad, as_stream(stream));
     pl->dgrad.accumulate = false;
     return rs;
   }

@@ -816,12 +816,16 @@ int32_t petsyn_normact_bwd(const petsyn_normact_desc* desc, void* stream) {
   dim3 grid((unsigned)row_blocks(d.rows, d.C, desc->nsamples), (unsigned)desc->nsamples);
   if (d.mean != nullptr) {
     const int nst = d.per_sample ? desc->nsamples : 1;
+    PETSYN_REQUIRE(!desc->sums_precomputed || (desc->sums_prezeroed && d.per_sample && d.t2 == nullptr && d.dslope == nullptr),
+                   "precomputed backward sums need a pre-zeroed per-sample workspace and one gradient source");
     if (!desc->sums_prezeroed) PETSYN_CHECK_CUDA(cudaMemsetAsync(d.sums, 0, (size_t)nst * 2 * d.C * sizeof(double), st));
     const int rpp = 256 / (d.C / 8);
     const size_t smem = PfRing::bytes(d.t2 ? 3 : 2) + (size_t)rpp * 2 * d.C * sizeof(float);
-    PETSYN_NX_DISPATCH(bwd_reduce_kernel, grid, smem, st, d);
-    rc = check_launch("normact bwd_reduce_kernel");
-    if (rc) return rc;
+    if (!desc->sums_precomputed) {     // else: filled by the producing data-gradient convolution's epilogue
+      PETSYN_NX_DISPATCH(bwd_reduce_kernel, grid, smem, st, d);
+      rc = check_launch("normact bwd_reduce_kernel");
+      if (rc) return rc;
+    }
     const int gs = desc->group_size > 1 ? desc->group_size : 1;
     if (d.per_sample && (gs > 1 || d.gamma != nullptr) && !desc->separate_group_combine) {
       d.gc_gs = gs; d.gc_ns = nst; d.gc_acc = desc->affine_accumulate;      // combined inside bwd_apply_kernel's prologue

@@ -594,7 +594,7 @@ __device__ __forceinline__ void bulk_store(float* gdst, const void* ssrc, uint32
 }
 
 // grid: x = persistent CTAs, y = co atom, z = input-channel group (atoms * 16 channels each)
-__global__ void __launch_bounds__(192) slab_wgrad_kernel(const __grid_constant__ SlabWgradParams p) {
+static __global__ void __launch_bounds__(192) slab_wgrad_kernel(const __grid_constant__ SlabWgradParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int hh = p.halo;
@@ -777,7 +777,7 @@ __global__ void __launch_bounds__(192) slab_wgrad_kernel(const __grid_constant__
 //   -> dw[co][ci][kd][kh][kw]            (k3 = 27; for 1x1x1 convs k3 = 1, nacc = 1 and the only tap sits in row block 0)
 // One thread per element of ONE image (coalesced over the image's own layout); the `nimages` per-CTA images are added in CTA
 // order, so the weight gradient is reproducible from run to run (no atomics, no memset of the scratch).
-__global__ void __launch_bounds__(256) slab_wgrad_unpack_kernel(const float* __restrict__ scratch, float* __restrict__ dw,
+static __global__ void __launch_bounds__(256) slab_wgrad_unpack_kernel(const float* __restrict__ scratch, float* __restrict__ dw,
                                                                 int cout, int cin, int apg, int k3, int accumulate,
                                                                 int nimages, int64_t image_floats,
                                                                 const double* __restrict__ dbias_acc,

@@ -99,8 +99,11 @@ class ConvOp(Op):
                  pad: int, op: int = ops.OP_CONV, act: int = ops.ACT_NONE, slope: float = 0.2, y_fp32: bool = False,
                  use_bias: bool = True, need_dx: bool = True, need_dw: bool = True, name: str = "",
                  out: Optional["Sl"] = None, dy_from: Optional["Sl"] = None, cout_pad: Optional[int] = None,
-                 out_index: Optional[Sequence[int]] = None, in_index: Optional[Sequence[int]] = None):
-        """``out_index`` / ``in_index`` (with ``cout_pad``): position of every true output / input channel of the weight inside
+                 out_index: Optional[Sequence[int]] = None, in_index: Optional[Sequence[int]] = None,
+                 res: Optional["Sl"] = None):
+        """``res``: a slice ADDED to the output by the kernel's epilogue (the residual sum of a ResnetBlock; needs
+        ``plan.epi_ok[0]``; it may be the output slice itself, then an earlier op left the addend there).
+        ``out_index`` / ``in_index`` (with ``cout_pad``): position of every true output / input channel of the weight inside
         the (wider, otherwise zero) channel range the kernels see -- attention heads of 8 or 16 channels padded to the
         kernel's 32-channel head: Conv3d / Linear layouts only."""
         self.x, self.weight, self.bias = x, weight, bias
@@ -184,6 +187,14 @@ class ConvOp(Op):
         self.grad_w: Optional[torch.Tensor] = None     # set by the owner: where dW / dbias go
         self.grad_b: Optional[torch.Tensor] = None
         self.flops = self.plan.flops_algorithmic
+        # fused epilogues (Tape.finalize decides): statistics of the output for up to two consuming GroupNorms; the reduction
+        # pass of the backward of the normalisation in front of this conv, done by the data-gradient kernel
+        self.res = res
+        if res is not None:
+            assert self.plan.epi_ok[0] and res.c == self.cout and not y_fp32, "residual epilogue not available for this conv"
+        self.stats_for: List[List[Tuple["NormActOp", int]]] = [[]]
+        self.epi_norm: Optional["NormActOp"] = None
+        self.absorbed = False    # the output is an addend that a later conv's epilogue folds into the same slice (`res`)
 
     # -------------------------------------------------------------------------------------------------
     # batched packing (Tape.repack): staleness check, operand allocation, staging of zero-padded weights
@@ -210,8 +221,8 @@ class ConvOp(Op):
                 self.w_stage[self._oidx[:, None], self._iidx[None, :]] = w.reshape(self.cout_w, self.cin_w, k, k, k)
             elif self.opcode == ops.OP_CONVT:
                 self.w_stage[:self.cin_w, :self.cout_w].copy_(w)
-            else:
-                self.w_stage[:self.cout_w, :self.cin_w].copy_(w)
+            else:                                     # (an nn.Linear weight is 2-D: its kernel volume is 1)
+                self.w_stage[:self.cout_w, :self.cin_w].copy_(w.reshape(self.cout_w, self.cin_w, *self.w_stage.shape[2:]))
         if self.bias_stage is not None:
             if self._oidx is not None:
                 self.bias_stage[self._oidx] = self.bias.detach()
@@ -262,16 +273,43 @@ class ConvOp(Op):
             return self.out_sl.buf.g
         return self.zg if self.y_fp32 else self.z.g
 
+    def out_slice(self) -> Optional["Sl"]:
+        """Where the forward output lives, as a slice (None for the fp32 heads)."""
+        if self.out_sl is not None:
+            return self.out_sl
+        return None if self.y_fp32 else self.z.sl()
+
     def fwd(self, training: bool) -> None:
         bias = None
         if self.use_bias:
             bias = self.bias_stage if self.bias_stage is not None else self.bias.detach()
+        tgts = self.stats_for[0]
+        if self.res is not None or tgts:
+            e = _cabi.ConvEpilogue()
+            if self.res is not None:
+                e.side, e.side_cstride, e.side_coff, e.add_side = ptr(self.res.buf.t), self.res.buf.c, self.res.off, 1
+            for i, (q, off) in enumerate(tgts):
+                if i == 0:
+                    e.stats1, e.stats1_c, e.stats1_coff = ptr(q.sums), q.c, off
+                else:
+                    e.stats2, e.stats2_c, e.stats2_coff = ptr(q.sums), q.c, off
+            self.plan.fprop_epi(self.x.buf.t, self.out(), bias, e)
+            return
         self.plan.fprop(self.x.buf.t, self.out(), bias)
 
     def grad_writes(self):
         return [("dx", self.x)] if self.need_dx else []
 
     def _bwd_dx(self, dz: torch.Tensor) -> None:
+        q = self.epi_norm
+        if q is not None:
+            assert not self.acc_dx
+            e = _cabi.ConvEpilogue()
+            e.side, e.side_cstride, e.side_coff = ptr(q.z.t), q.z.c, q.zs.off
+            e.norm_scale, e.norm_shift, e.norm_mean, e.norm_rstd = ptr(q.scale), ptr(q.shift), ptr(q.mean), ptr(q.rstd)
+            e.norm_act, e.norm_slope, e.bsums = q.act, q.slope, ptr(q.bsums)
+            self.plan.dgrad_epi(dz, self.x.buf.g, e)
+            return
         if self.acc_dx:
             check(lib.petsyn_conv_dgrad_accumulate(self.plan._h, ptr(dz), ptr(self.plan.w_dgrad), ptr(self.x.buf.g),
                                                    stream_ptr()), "conv_dgrad_accumulate")
@@ -374,6 +412,7 @@ class NormActOp(Op):
         self.colsum_conv: Optional["ConvOp"] = None   # conv that produced z: its bias gradient is a by-product of bwd
         # statistics as a by-product: a "none" op may sum what it writes for the norm that consumes the destination ...
         self.stats_from_producers = False              # ... and that norm then skips its own statistics pass
+        self.reduce_from_producer = False              # backward: (sum g, sum g zhat) come from the producing dgrad's epilogue
         self.tape_zeroes_sums = False                  # Tape.finalize moved `sums` into its per-step zero arena
         self.tape_zeroes_bsums = False                 # ... and `bsums` into its per-backward zero arena
         self.slope_param = slope_param          # nn.PReLU weight (one element): slope read from device memory
@@ -424,6 +463,7 @@ class NormActOp(Op):
                 d.mean, d.rstd = ptr(self.mean), ptr(self.rstd)
                 d.sums = ptr(self.bsums)
                 d.sums_prezeroed = 1 if self.tape_zeroes_bsums else 0
+                d.sums_precomputed = 1 if self.reduce_from_producer else 0
                 if self.bn is not None and self.bn.weight is not None:
                     d.gamma = ptr(self.bn.weight)
         if not backward and any(self.stats_for):
@@ -768,10 +808,14 @@ class Tape:
                     else:
                         other(sl)
             elif isinstance(op, ConvOp):
-                if op.out_sl is not None:
-                    other(op.out_sl)
-                elif op.z is not None:
-                    other(op.z.sl())
+                osl = op.out_slice()
+                if osl is None or op.absorbed:
+                    continue                           # fp32 head / an addend that a later conv's epilogue overwrites in place
+                if op.plan.epi_ok[0] and not os.environ.get("PETSYN_NO_EPI_STATS"):
+                    op.stats_for = [[]]
+                    produced.setdefault(id(osl.buf), []).append((op, 0, osl))   # its epilogue can sum what it stores
+                else:
+                    other(osl)
             elif isinstance(op, ResampleOp):
                 other(op.dst)                          # src / dst_grad are only read
             else:
@@ -833,6 +877,30 @@ class Tape:
                 op.tape_zeroes_bsums = True
                 bwd_pairs.append((op, "bsums"))
         self._bwd_arena = arena(bwd_pairs)
+        # backward reduction as a by-product: the data gradient of the conv that consumes a = act(norm(z)) is the ONLY writer of
+        # a's gradient; its epilogue (petsyn_conv_dgrad_epi) reads z beside the tile it stores and accumulates (sum g, sum g zhat)
+        # into the normalisation's backward sums, which then runs its apply pass only
+        for op in self.ops:
+            if isinstance(op, ConvOp):
+                op.epi_norm = None
+        # Measured (tools/conv_layer_bench.py --pass epi, B200): the sigmoid per element makes the epilogue warps the bottleneck of
+        # the shared-memory-bound slab kernel -- 115 us fused against 56 us (data gradient) + 33 us (reduction pass) on the
+        # full-resolution 16 -> 16 layer -- so this fusion is opt-in (PETSYN_EPI_BWD=1); the forward fusions are free and on
+        if use and os.environ.get("PETSYN_EPI_BWD"):
+            for q in normed:
+                q.reduce_from_producer = False
+                if not (q.kind in ("instance", "group") and len(q.dsts) == 1 and not q.no_bwd and q.slope_param is None
+                        and q.ns == q.z.n):
+                    continue
+                a = q.dsts[0]
+                ws = [(op, key, sl) for op, key, sl in writes if sl.buf is a.buf and sl.off < a.off + a.c and a.off < sl.off + sl.c]
+                if len(ws) != 1:
+                    continue
+                op, key, sl = ws[0]
+                if (isinstance(op, ConvOp) and key == "dx" and sl.off == a.off and sl.c == a.c and op.cin == q.c
+                        and op.plan.epi_ok[1] and not op.acc_dx and op.epi_norm is None):
+                    op.epi_norm = q
+                    q.reduce_from_producer = True
         # the weight-gradient kernels write per-CTA / per-split partial images into a scratch that the unpack kernel sums in a
         # fixed order; all weight gradients of a tape run on its main stream one after the other, so they share ONE scratch
         convs = [op for op in self.ops if isinstance(op, ConvOp) and op.need_dw]

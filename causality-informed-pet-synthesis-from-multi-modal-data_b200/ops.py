@@ -46,6 +46,8 @@ class ConvPlan:
         self.flops_algorithmic, self.flops_executed = fa.value, fe.value
         # kernel family per pass (0 gather-form igemm, 1 slab, 2 small-channel wgrad): reporting only
         self.kernel_path = tuple(lib.petsyn_conv_kernel_path(self._h, i) for i in range(3))
+        # fused epilogues (petsyn_conv_{fprop,dgrad}_epi): available per pass (fprop, dgrad)
+        self.epi_ok = tuple(bool(lib.petsyn_conv_epilogue_supported(self._h, i)) for i in range(2))
         self.packed_fprop_bytes = lib.petsyn_conv_packed_fprop_bytes(self._h)
         self.packed_dgrad_bytes = lib.petsyn_conv_packed_dgrad_bytes(self._h)
         self.wgrad_scratch_bytes = lib.petsyn_conv_wgrad_scratch_bytes(self._h)
@@ -82,6 +84,18 @@ class ConvPlan:
 
     def dgrad(self, dy: torch.Tensor, dx: torch.Tensor) -> torch.Tensor:
         check(lib.petsyn_conv_dgrad(self._h, ptr(dy), ptr(self.w_dgrad), ptr(dx), stream_ptr()), "conv_dgrad")
+        return dx
+
+    def fprop_epi(self, x: torch.Tensor, y: torch.Tensor, bias: Optional[torch.Tensor], epi: "_cabi.ConvEpilogue") -> torch.Tensor:
+        """fprop with a fused epilogue (residual add and / or the statistics of the consuming GroupNorm)."""
+        check(lib.petsyn_conv_fprop_epi(self._h, ptr(x), ptr(self.w_fprop), ptr(bias), ptr(y), C.byref(epi), stream_ptr()),
+              "conv_fprop_epi")
+        return y
+
+    def dgrad_epi(self, dy: torch.Tensor, dx: torch.Tensor, epi: "_cabi.ConvEpilogue") -> torch.Tensor:
+        """dgrad whose epilogue also does the reduction pass of the backward of the normalisation in front of this conv."""
+        check(lib.petsyn_conv_dgrad_epi(self._h, ptr(dy), ptr(self.w_dgrad), ptr(dx), C.byref(epi), stream_ptr()),
+              "conv_dgrad_epi")
         return dx
 
     def wgrad(self, x: torch.Tensor, dy: torch.Tensor, dw: torch.Tensor, accumulate: bool = False,

@@ -132,6 +132,37 @@ int32_t petsyn_conv_dgrad(petsyn_conv_plan* plan, const void* dy, const void* pa
  * residual sums in bmgan_model.py:12-23).  The tile epilogue add-reduces through the TMA unit (bf16). */
 int32_t petsyn_conv_dgrad_accumulate(petsyn_conv_plan* plan, const void* dy, const void* packed_dgrad, void* dx,
                                      void* stream);
+/* Fused epilogues of the small-channel 3x3x3 convolutions (the full- and half-resolution ResnetBlock convs of AttenUNet,
+ * atten_unet_model.py:641-662): passes over the convolution's OUTPUT that would otherwise be HBM-bound kernels of their own are
+ * done on the tile while it is in registers.
+ *   side          fprop: added to the output -- the residual sum `conv2(...) + skip_connection(x)` (:662);
+ *                 dgrad: z, the input of the normalisation in front of this convolution (a = act(norm(z)), :644-645)
+ *   stats1/2      fprop: [sample][2][stats_c] double accumulators += (sum y, sum y^2) of the stored bf16 output at channel offset
+ *                 stats_coff -- the statistics of the GroupNorm that reads the output (norm2 after conv1, norm1 of the next block)
+ *   norm_*, bsums dgrad: the reduction pass of that normalisation's backward, bsums[sample][2][cin] += (sum g, sum g * zhat) with
+ *                 g = dx * act'(z * scale + shift); petsyn_normact_bwd then runs with `sums_precomputed` = 1 (apply pass only)
+ * Available when petsyn_conv_epilogue_supported() says so (depth-folded slab kernel, 16 or 32 output channels of the pass);
+ * the plain entry points stay valid for every plan. */
+typedef struct petsyn_conv_epilogue {
+  const void* side;              /* bf16 NDHWC, spatial dims of the pass's output */
+  int32_t side_cstride, side_coff;
+  int32_t add_side;              /* fprop: y += side */
+  double* stats1; int32_t stats1_c, stats1_coff;
+  double* stats2; int32_t stats2_c, stats2_coff;
+  const float* norm_scale;       /* dgrad: [sample][cin] each */
+  const float* norm_shift;
+  const float* norm_mean;
+  const float* norm_rstd;
+  int32_t norm_act;
+  float norm_slope;
+  double* bsums;
+} petsyn_conv_epilogue;
+/* pass: 0 = fprop, 1 = dgrad.  1 if petsyn_conv_{fprop,dgrad}_epi can run this plan's pass, else 0. */
+int32_t petsyn_conv_epilogue_supported(const petsyn_conv_plan* plan, int32_t pass);
+int32_t petsyn_conv_fprop_epi(petsyn_conv_plan* plan, const void* x, const void* packed_fprop, const float* bias, void* y,
+                              const petsyn_conv_epilogue* epi, void* stream);
+int32_t petsyn_conv_dgrad_epi(petsyn_conv_plan* plan, const void* dy, const void* packed_dgrad, void* dx,
+                              const petsyn_conv_epilogue* epi, void* stream);
 /* dw (fp32, PyTorch layout) = conv_backward_weight(x, dy); optional dbias (fp32 [cout]) = sum(dy).
  * `scratch` must hold petsyn_conv_wgrad_scratch_bytes(); it is zeroed and reduced into by the kernel.
  * accumulate != 0 adds into dw instead of overwriting (autograd .grad accumulation). */
@@ -282,6 +313,9 @@ typedef struct petsyn_normact_desc {
   int32_t extra_cstride, extra_coff;
   int32_t dz_colsum_coff, dz_colsum_c; /* dz_colsum covers channels [dz_colsum_coff, +dz_colsum_c) of dz only (the convolution
                               * wrote a channel slice of a wider concat buffer); dz_colsum_c == 0: all c channels */
+  int32_t sums_precomputed;  /* bwd: `sums` already holds (sum g, sum g * zhat) per (sample, channel) -- filled by the fused
+                              * epilogue of the data-gradient convolution that produced the incoming gradient
+                              * (petsyn_conv_dgrad_epi) -- so the reduction pass is skipped and only the apply pass runs */
 } petsyn_normact_desc;
 
 /* sums[sample][0:c] += sum z, sums[sample][c:2c] += sum z^2 (double accumulators, caller-zeroed). */

@@ -41,7 +41,8 @@ LAYERS = {
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--layer", default="up1", choices=sorted(LAYERS))
-    ap.add_argument("--pass", dest="which", default="all", choices=["fprop", "dgrad", "wgrad", "all"])
+    ap.add_argument("--pass", dest="which", default="all",
+                    choices=["fprop", "dgrad", "wgrad", "all", "epi"])   # epi: the fused-epilogue variants beside the plain passes
     ap.add_argument("--iters", type=int, default=20)
     ap.add_argument("--batch", type=int, default=0)
     ap.add_argument("--once", action="store_true")
@@ -62,7 +63,31 @@ def main():
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
     passes = {"fprop": lambda: plan.fprop(x, y), "dgrad": lambda: plan.dgrad(dy, dx),
               "wgrad": lambda: plan.wgrad(x, dy, dw)}
-    todo = list(passes) if args.which == "all" else [args.which]
+    if args.which == "epi":
+        from petsyn_b200._cabi import ConvEpilogue, check, lib, ptr, stream_ptr
+        assert plan.epi_ok[0], "no fused epilogue for this layer's forward pass"
+        res = torch.randn(n, od, oh, ow, cout, generator=g).to(dev).to(torch.bfloat16)
+        st = torch.zeros(n, 2, cout, dtype=torch.float64, device=dev)
+        e_st, e_rs, e_r = ConvEpilogue(), ConvEpilogue(), ConvEpilogue()
+        e_st.stats1, e_st.stats1_c = ptr(st), cout
+        e_rs.side, e_rs.side_cstride, e_rs.add_side, e_rs.stats1, e_rs.stats1_c = ptr(res), cout, 1, ptr(st), cout
+        e_r.side, e_r.side_cstride, e_r.add_side = ptr(res), cout, 1
+        passes = {"fprop": passes["fprop"], "fprop+stats": lambda: plan.fprop_epi(x, y, None, e_st),
+                  "fprop+res": lambda: plan.fprop_epi(x, y, None, e_r),
+                  "fprop+res+stats": lambda: plan.fprop_epi(x, y, None, e_rs),
+                  "stats_pass": lambda: check(lib.petsyn_norm_stats(ptr(y), ptr(st), od * oh * ow, cout, n, stream_ptr())),
+                  "dgrad": passes["dgrad"]}
+        if plan.epi_ok[1]:
+            z = torch.randn(n, d, h, w, cin, generator=g).to(dev).to(torch.bfloat16)
+            f = lambda: torch.rand(n, cin, generator=g).to(dev) + 0.5
+            sc, sh, mu, rs = f(), f(), f(), f()
+            bs = torch.zeros(n, 2, cin, dtype=torch.float64, device=dev)
+            e_n = ConvEpilogue()
+            e_n.side, e_n.side_cstride = ptr(z), cin
+            e_n.norm_scale, e_n.norm_shift, e_n.norm_mean, e_n.norm_rstd = ptr(sc), ptr(sh), ptr(mu), ptr(rs)
+            e_n.norm_act, e_n.bsums = ops.ACT_SILU, ptr(bs)
+            passes["dgrad+normreduce"] = lambda: plan.dgrad_epi(dy, dx, e_n)
+    todo = list(passes) if args.which in ("all", "epi") else [args.which]
     out = {"layer": args.layer, "batch": n, "flops_algorithmic": plan.flops_algorithmic,
            "flops_executed": plan.flops_executed}
     for name in todo:
