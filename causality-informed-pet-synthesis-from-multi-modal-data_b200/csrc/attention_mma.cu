@@ -107,6 +107,7 @@ __device__ __forceinline__ void gemm_p_tile(float (&o)[4][4], const uint32_t (&p
 // ------------------------------------------------------------------------------------------------ forward
 __global__ void __launch_bounds__(128) attn_fwd_mma_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out,
                                                            float* __restrict__ lse, int L, int H, float scale) {
+  pdl_sync();
   __shared__ __align__(16) __nv_bfloat16 sK[2][kT * kPitch], sV[2][kT * kPitch];
   const int n = blockIdx.z, h = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
@@ -209,6 +210,7 @@ __global__ void __launch_bounds__(128) attn_bwd_dq_mma_kernel(const __nv_bfloat1
                                                               const __nv_bfloat16* __restrict__ dout,
                                                               const float* __restrict__ lse, const float* __restrict__ delta,
                                                               __nv_bfloat16* __restrict__ dqkv, int L, int H, float scale) {
+  pdl_sync();
   __shared__ __align__(16) __nv_bfloat16 sK[2][kT * kPitch], sV[2][kT * kPitch];
   const int n = blockIdx.z, h = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
@@ -290,6 +292,7 @@ __global__ void __launch_bounds__(128) attn_bwd_dkv_mma_kernel(const __nv_bfloat
                                                                const __nv_bfloat16* __restrict__ dout,
                                                                const float* __restrict__ lse, const float* __restrict__ delta,
                                                                __nv_bfloat16* __restrict__ dqkv, int L, int H, float scale) {
+  pdl_sync();
   __shared__ __align__(16) __nv_bfloat16 sQ[2][kT * kPitch], sG[2][kT * kPitch];
   __shared__ float sL[2][kT], sD[2][kT];
   const int n = blockIdx.z, h = blockIdx.y;
@@ -374,6 +377,7 @@ __global__ void __launch_bounds__(128) attn_bwd_dkv_mma_kernel(const __nv_bfloat
 __global__ void __launch_bounds__(256) attn_delta_kernel(const __nv_bfloat16* __restrict__ o,
                                                          const __nv_bfloat16* __restrict__ dout,
                                                          float* __restrict__ delta, int N, int L, int H) {
+  pdl_sync();
   const int64_t total = (int64_t)N * L * H;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int h = (int)(i % H);
@@ -409,8 +413,8 @@ int32_t petsyn_attention_fwd(const void* qkv, void* out, float* lse, int32_t n, 
   PETSYN_REQUIRE(qkv && out && lse && n > 0 && l > 0 && heads > 0, "bad argument");
   PETSYN_REQUIRE(head_dim == fa::kD, "attention kernels are specialised for head_dim 32 (num_head_channels=32)");
   dim3 grid((unsigned)((l + fa::kT - 1) / fa::kT), (unsigned)heads, (unsigned)n);
-  fa::attn_fwd_mma_kernel<<<grid, 128, 0, as_stream(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(qkv),
-                                                               reinterpret_cast<__nv_bfloat16*>(out), lse, l, heads, scale);
+  PETSYN_CHECK_CUDA(launch_pdl(fa::attn_fwd_mma_kernel, dim3(grid), dim3(128), 0, as_stream(stream), reinterpret_cast<const __nv_bfloat16*>(qkv),
+                                                               reinterpret_cast<__nv_bfloat16*>(out), lse, l, heads, scale));
   return check_launch("attn_fwd_mma_kernel");
 }
 
@@ -424,14 +428,14 @@ int32_t petsyn_attention_bwd(const void* qkv, const void* out, const void* dout,
   const auto* gp = reinterpret_cast<const __nv_bfloat16*>(dout);
   const int64_t total = (int64_t)n * heads * l;
   const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>((total + 255) / 256, 148 * 16));
-  fa::attn_delta_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(out), gp, delta, n, l, heads);
+  PETSYN_CHECK_CUDA(launch_pdl(fa::attn_delta_kernel, dim3(blocks), dim3(256), 0, st, reinterpret_cast<const __nv_bfloat16*>(out), gp, delta, n, l, heads));
   int32_t rc = check_launch("attn_delta_kernel");
   if (rc) return rc;
   dim3 grid((unsigned)((l + fa::kT - 1) / fa::kT), (unsigned)heads, (unsigned)n);
-  fa::attn_bwd_dq_mma_kernel<<<grid, 128, 0, st>>>(qp, gp, lse, delta, reinterpret_cast<__nv_bfloat16*>(dqkv), l, heads, scale);
+  PETSYN_CHECK_CUDA(launch_pdl(fa::attn_bwd_dq_mma_kernel, dim3(grid), dim3(128), 0, st, qp, gp, lse, delta, reinterpret_cast<__nv_bfloat16*>(dqkv), l, heads, scale));
   rc = check_launch("attn_bwd_dq_mma_kernel");
   if (rc) return rc;
-  fa::attn_bwd_dkv_mma_kernel<<<grid, 128, 0, st>>>(qp, gp, lse, delta, reinterpret_cast<__nv_bfloat16*>(dqkv), l, heads, scale);
+  PETSYN_CHECK_CUDA(launch_pdl(fa::attn_bwd_dkv_mma_kernel, dim3(grid), dim3(128), 0, st, qp, gp, lse, delta, reinterpret_cast<__nv_bfloat16*>(dqkv), l, heads, scale));
   return check_launch("attn_bwd_dkv_mma_kernel");
 }
 

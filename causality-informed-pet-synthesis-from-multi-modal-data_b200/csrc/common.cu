@@ -13,6 +13,15 @@ static std::atomic<uint64_t> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 uint64_t launch_count() { return g_launches.load(std::memory_order_relaxed); }
 
+bool pdl_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("PETSYN_PDL");
+    on = (e != nullptr && e[0] != '\0' && e[0] != '0') ? 1 : 0;
+  }
+  return on == 1;
+}
+
 char* last_error_buf() {
   static thread_local char buf[512] = {0};
   return buf;

@@ -217,6 +217,7 @@ struct PackJob {
 
 template <int K3, bool TRANSPOSED, int NS>
 __global__ void __launch_bounds__(256) pack_weights_multi_kernel(const PackJob* __restrict__ jobs, int njobs) {
+  pdl_sync();
   int lo = 0, hi = njobs - 1;
   const int b = blockIdx.x;
   while (lo < hi) {
@@ -235,6 +236,7 @@ __global__ void __launch_bounds__(256) unpack_wgrad_kernel(const float* __restri
                                                            int max_taps, int rows, int kc_pad, int accumulate,
                                                            int nsplit, const double* __restrict__ dbias_acc,
                                                            float* __restrict__ dbias, int nbias) {
+  pdl_sync();
   if (dbias != nullptr && blockIdx.x == 0 && blockIdx.y == 0)       // bias gradient: double accumulator -> fp32 slot
     for (int i = threadIdx.x; i < nbias; i += 256) dbias[i] = accumulate ? dbias[i] + (float)dbias_acc[i] : (float)dbias_acc[i];
   constexpr int TA = TRANSPOSED ? 64 : 4, TB = TRANSPOSED ? 4 : 64;
@@ -305,6 +307,7 @@ __global__ void __launch_bounds__(256) unpack_wgrad_small_kernel(const float* __
                                                                  int nsplit, int64_t image,
                                                                  const double* __restrict__ dbias_acc,
                                                                  float* __restrict__ dbias, int nbias) {
+  pdl_sync();
   if (dbias != nullptr && blockIdx.x == 0)
     for (int i = threadIdx.x; i < nbias; i += 256) dbias[i] = accumulate ? dbias[i] + (float)dbias_acc[i] : (float)dbias_acc[i];
   const int total = Cout * Cin * k3;
@@ -330,6 +333,7 @@ __global__ void __launch_bounds__(256) splitk_finish_kernel(const float* __restr
                                                             __nv_bfloat16* __restrict__ dst, int64_t rows, int C,
                                                             int cstride, int coff, const float* __restrict__ bias, int act,
                                                             float slope, int accumulate) {
+  pdl_sync();
   const int cpt = C / 8;
   const int64_t total = rows * cpt;
   const int64_t slot = rows * C;
@@ -372,6 +376,7 @@ __global__ void __launch_bounds__(256) splitk_finish_kernel(const float* __restr
 // lane order by lane 0, which overwrites image 0.
 __global__ void __launch_bounds__(256) reduce_images_kernel(float* __restrict__ scratch, int nimages, int64_t image_floats,
                                                             int lanes) {
+  pdl_sync();
   __shared__ float4 part[256];
   const int gpb = 256 / lanes;
   const int64_t ng = image_floats >> 2;
@@ -404,7 +409,7 @@ static int32_t reduce_images(float* scratch, int nimages, int64_t image_floats, 
   while (lanes < 32 && lanes * 4 <= nimages) lanes *= 2;
   const int gpb = 256 / lanes;
   const int64_t ng = image_floats >> 2;
-  reduce_images_kernel<<<(unsigned)((ng + gpb - 1) / gpb), 256, 0, st>>>(scratch, nimages, image_floats, lanes);
+  PETSYN_CHECK_CUDA(launch_pdl(reduce_images_kernel, dim3((unsigned)((ng + gpb - 1) / gpb)), dim3(256), 0, st, scratch, nimages, image_floats, lanes));
   return check_launch("reduce_images_kernel");
 }
 
@@ -675,7 +680,7 @@ static int32_t launch_slab3(const GemmSide& g, cudaStream_t st) {
     PETSYN_CHECK_CUDA(cudaFuncSetAttribute(slab_conv3_kernel<ATOMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
     attr_set = true;
   }
-  slab_conv3_kernel<ATOMS><<<g.slab_grid, 192, g.slab_smem, st>>>(g.sparams);
+  PETSYN_CHECK_CUDA(launch_pdl(slab_conv3_kernel<ATOMS>, dim3(g.slab_grid), dim3(192), g.slab_smem, st, g.sparams));
   return check_launch("slab_conv3_kernel");
 }
 
@@ -686,7 +691,7 @@ static int32_t launch_slab(const GemmSide& g, cudaStream_t st) {
     PETSYN_CHECK_CUDA(cudaFuncSetAttribute(slab_conv_kernel<ATOMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
     attr_set = true;
   }
-  slab_conv_kernel<ATOMS><<<g.slab_grid, 192, g.slab_smem, st>>>(g.sparams);
+  PETSYN_CHECK_CUDA(launch_pdl(slab_conv_kernel<ATOMS>, dim3(g.slab_grid), dim3(192), g.slab_smem, st, g.sparams));
   return check_launch("slab_conv_kernel");
 }
 
@@ -807,7 +812,7 @@ static int32_t launch_igemm_bn(const GemmSide& g, dim3 grid, cudaStream_t st) {
     PETSYN_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     attr_set = true;
   }
-  kern<<<grid, 128, Cfg::kSmemBytes, st>>>(g.params);
+  PETSYN_CHECK_CUDA(launch_pdl(kern, grid, dim3(128), Cfg::kSmemBytes, st, g.params));
   return check_launch("igemm_kernel");
 }
 
@@ -868,9 +873,9 @@ static int32_t run_side(GemmSide& g, const ViewSpec& vc, void* c, const float* b
     if (rc) return rc;
     const int64_t total = g.out_rows_full * (g.R / 8);
     const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>((total + 255) / 256, 148 * 8));
-    splitk_finish_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const float*>(g.workspace), g.ksplit,
+    PETSYN_CHECK_CUDA(launch_pdl(splitk_finish_kernel, dim3(blocks), dim3(256), 0, st, reinterpret_cast<const float*>(g.workspace), g.ksplit,
                                                  reinterpret_cast<__nv_bfloat16*>(c), g.out_rows_full, g.R, vc.cstride,
-                                                 vc.coff, bias, act, slope, g.accumulate ? 1 : 0);
+                                                 vc.coff, bias, act, slope, g.accumulate ? 1 : 0));
     return check_launch("splitk_finish_kernel");
   }
   return launch_igemm(g, batch, st);
@@ -1011,7 +1016,7 @@ static int32_t launch_pack_multi_t(const PackJob* jobs, int njobs, int tiles, cu
                                            (int)smem));
     attr = true;
   }
-  pack_weights_multi_kernel<K3, T, NS><<<tiles, 256, smem, st>>>(jobs, njobs);
+  PETSYN_CHECK_CUDA(launch_pdl(pack_weights_multi_kernel<K3, T, NS>, dim3(tiles), dim3(256), smem, st, jobs, njobs));
   return check_launch("pack_weights_multi_kernel");
 }
 
@@ -1045,8 +1050,8 @@ static int32_t launch_unpack_t(const float* scratch, float* dw, const InvEntryDe
     smem_set = smem;
   }
   dim3 grid((unsigned)((A + TA - 1) / TA), (unsigned)((B + TB - 1) / TB));
-  unpack_wgrad_kernel<K3, T, NS><<<grid, 256, smem, st>>>(scratch, dw, inv, A, B, (int)f.subs.size(), f.prog.max_taps,
-                                                          f.R, f.kc_pad, accumulate, nsplit, bc.acc, bc.out, bc.n);
+  PETSYN_CHECK_CUDA(launch_pdl(unpack_wgrad_kernel<K3, T, NS>, dim3(grid), dim3(256), smem, st, scratch, dw, inv, A, B, (int)f.subs.size(), f.prog.max_taps,
+                                                          f.R, f.kc_pad, accumulate, nsplit, bc.acc, bc.out, bc.n));
   return check_launch("unpack_wgrad_kernel");
 }
 
@@ -1481,14 +1486,14 @@ int32_t petsyn_conv_wgrad_bias(petsyn_conv_plan* pl, const void* x, const void* 
       pl->wg_key_x = x; pl->wg_key_g = dy; pl->wg_key_s = scratch;
     }
     dim3 grid((unsigned)pl->wg_slab_grid, (unsigned)co_atoms, (unsigned)groups);
-    slab_wgrad_kernel<<<grid, 192, pl->wg_slab_smem, st>>>(q);
+    PETSYN_CHECK_CUDA(launch_pdl(slab_wgrad_kernel, grid, dim3(192), pl->wg_slab_smem, st, q));
     int32_t rc = check_launch("slab_wgrad_kernel");
     if (rc) return rc;
     rc = reduce_images(reinterpret_cast<float*>(scratch), pl->wg_slab_grid, q.image_floats, st);
     if (rc) return rc;
-    slab_wgrad_unpack_kernel<<<(unsigned)std::min<int64_t>((q.image_floats + 255) / 256, 148 * 8), 256, 0, st>>>(
-        reinterpret_cast<const float*>(scratch), dw, pl->desc.cout, pl->desc.cin, atoms, pl->k3, accumulate, 1,
-        q.image_floats, bc.acc, bc.out, bc.n);
+    PETSYN_CHECK_CUDA(launch_pdl(slab_wgrad_unpack_kernel, dim3((unsigned)std::min<int64_t>((q.image_floats + 255) / 256, 148 * 8)), dim3(256), 0, st,
+                                 reinterpret_cast<const float*>(scratch), dw, pl->desc.cout, pl->desc.cin, atoms, pl->k3, accumulate, 1,
+        q.image_floats, bc.acc, bc.out, bc.n));
     return check_launch("slab_wgrad_unpack_kernel");
   }
   if (pl->wg_small) {
@@ -1535,7 +1540,7 @@ int32_t petsyn_conv_wgrad_bias(petsyn_conv_plan* pl, const void* x, const void* 
       attr_set = true;
     }
     dim3 grid((unsigned)pl->wg_mtiles, (unsigned)pl->wg_ksplit, (unsigned)f.subs.size());
-    kern<<<grid, 128, smem, st>>>(q);
+    PETSYN_CHECK_CUDA(launch_pdl(kern, grid, dim3(128), smem, st, q));
     int32_t rc = check_launch("wgrad_small_kernel");
     if (rc) return rc;
     const int total = pl->desc.cout * pl->desc.cin * pl->k3;
@@ -1546,9 +1551,9 @@ int32_t petsyn_conv_wgrad_bias(petsyn_conv_plan* pl, const void* x, const void* 
       rc = reduce_images(reinterpret_cast<float*>(scratch), pl->wg_ksplit, image, st);
       if (rc) return rc;
     }
-    unpack_wgrad_small_kernel<<<std::min((total + 255) / 256, 148 * 8), 256, 0, st>>>(
+    PETSYN_CHECK_CUDA(launch_pdl(unpack_wgrad_small_kernel, dim3(std::min((total + 255) / 256, 148 * 8)), dim3(256), 0, st, 
         reinterpret_cast<const float*>(scratch), dw, pl->d_inv, pl->desc.cout, pl->desc.cin, pl->k3, pl->wg_npad, pl->wg_tpm,
-        pl->wg_mtiles, accumulate, inline_split, image, bc.acc, bc.out, bc.n);
+        pl->wg_mtiles, accumulate, inline_split, image, bc.acc, bc.out, bc.n));
     return check_launch("unpack_wgrad_small_kernel");
   }
   WgradParams& p = pl->wg_params;
@@ -1597,7 +1602,7 @@ int32_t petsyn_conv_wgrad_bias(petsyn_conv_plan* pl, const void* x, const void* 
       PETSYN_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
       attr_set = true;
     }
-    kern<<<grid, 128, smem, st>>>(p);
+    PETSYN_CHECK_CUDA(launch_pdl(kern, grid, dim3(128), smem, st, p));
   } else {
     constexpr int STAGES = 4;
     constexpr int smem = STAGES * (16384 + 8192) + 1024 + 256;
@@ -1607,7 +1612,7 @@ int32_t petsyn_conv_wgrad_bias(petsyn_conv_plan* pl, const void* x, const void* 
       PETSYN_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
       attr_set = true;
     }
-    kern<<<grid, 128, smem, st>>>(p);
+    PETSYN_CHECK_CUDA(launch_pdl(kern, grid, dim3(128), smem, st, p));
   }
   int32_t rc = check_launch("wgrad_kernel");
   if (rc) return rc;

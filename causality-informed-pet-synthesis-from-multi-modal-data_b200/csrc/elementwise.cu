@@ -326,6 +326,7 @@ __device__ __forceinline__ float block_sum(float v, float* smem) {
 __global__ void __launch_bounds__(256) l1_loss_kernel(const float* __restrict__ y, const float* __restrict__ t,
                                                       float* __restrict__ loss, float* __restrict__ dy, int64_t n,
                                                       float inv_n, float gscale, const DetWs ws) {
+  pdl_sync();
   __shared__ float red[8];
   float acc = 0.f;
   const int64_t n4 = n / 4;
@@ -354,6 +355,7 @@ __global__ void __launch_bounds__(256) l1_loss_kernel(const float* __restrict__ 
 __global__ void __launch_bounds__(256) mse_const_kernel(const float* __restrict__ x, float target,
                                                         float* __restrict__ loss, float* __restrict__ dx, int64_t n,
                                                         float inv_n, float gscale, const DetWs ws) {
+  pdl_sync();
   __shared__ float red[8];
   float acc = 0.f;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
@@ -371,6 +373,7 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
                                                    float* __restrict__ m, float* __restrict__ v, int64_t n, float lr,
                                                    float b1, float b2, float eps, int step,
                                                    const int32_t* __restrict__ step_dev) {
+  pdl_sync();
   const float t = (float)(step_dev ? *step_dev : step);
   const float bc1 = 1.f - powf(b1, t);
   const float bc2_sqrt = sqrtf(1.f - powf(b2, t));
@@ -515,8 +518,8 @@ int32_t petsyn_l1_loss_fwd_bwd(const float* y, const float* t, float* loss, floa
     int32_t rcw = det_workspace(&ws);
     if (rcw) return rcw;
   }
-  l1_loss_kernel<<<blocks, 256, 0, as_stream(stream)>>>(y, t, loss, dy, numel, 1.f / (float)numel,
-                                                        grad_scale / (float)numel, ws);
+  PETSYN_CHECK_CUDA(launch_pdl(l1_loss_kernel, dim3(blocks), dim3(256), 0, as_stream(stream), y, t, loss, dy, numel, 1.f / (float)numel,
+                                                        grad_scale / (float)numel, ws));
   return check_launch("l1_loss_kernel");
 }
 
@@ -530,8 +533,8 @@ int32_t petsyn_mse_const_fwd_bwd(const float* x, float target, float* loss, floa
     int32_t rcw = det_workspace(&ws);
     if (rcw) return rcw;
   }
-  mse_const_kernel<<<blocks, 256, 0, as_stream(stream)>>>(x, target, loss, dx, numel, 1.f / (float)numel,
-                                                          grad_scale / (float)numel, ws);
+  PETSYN_CHECK_CUDA(launch_pdl(mse_const_kernel, dim3(blocks), dim3(256), 0, as_stream(stream), x, target, loss, dx, numel, 1.f / (float)numel,
+                                                          grad_scale / (float)numel, ws));
   return check_launch("mse_const_kernel");
 }
 
@@ -549,7 +552,7 @@ int32_t petsyn_adam_step(float* p, const float* g, float* m, float* v, int64_t n
   PETSYN_REQUIRE((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
                   reinterpret_cast<uintptr_t>(v)) % 16 == 0, "Adam arenas must be 16-byte aligned");
   const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>((numel / 4 + 255) / 256, 148 * 16));
-  adam_kernel<<<blocks, 256, 0, as_stream(stream)>>>(p, g, m, v, numel, lr, beta1, beta2, eps, step, step_dev);
+  PETSYN_CHECK_CUDA(launch_pdl(adam_kernel, dim3(blocks), dim3(256), 0, as_stream(stream), p, g, m, v, numel, lr, beta1, beta2, eps, step, step_dev));
   return check_launch("adam_kernel");
 }
 

@@ -144,6 +144,7 @@ __global__ void __launch_bounds__(128) igemm_kernel(const __grid_constant__ Igem
   __syncthreads();
   ptx::tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
+  ptx::pdl_sync();       // everything above is on-chip set-up: it overlaps the tail of the previous kernel
 
   if (warp == 0) {
     if (ptx::elect_one()) {
@@ -329,6 +330,7 @@ __global__ void __launch_bounds__(128) wgrad_kernel(const __grid_constant__ Wgra
   __syncthreads();
   ptx::tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
+  ptx::pdl_sync();       // everything above is on-chip set-up: it overlaps the tail of the previous kernel
 
   if (warp == 0) {
     if (ptx::elect_one()) {
@@ -486,6 +488,7 @@ __global__ void __launch_bounds__(128) wgrad_small_kernel(const __grid_constant_
   __syncthreads();
   ptx::tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
+  ptx::pdl_sync();       // everything above is on-chip set-up: it overlaps the tail of the previous kernel
 
   if (warp == 0) {
     if (ptx::elect_one()) {

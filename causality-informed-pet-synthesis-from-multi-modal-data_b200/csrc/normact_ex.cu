@@ -166,6 +166,7 @@ __device__ __forceinline__ void block_reduce_channels(const RowIter& it, float (
 // sums[sample][0:C] += sum z, sums[sample][C:2C] += sum z^2
 __global__ void __launch_bounds__(256) stats_kernel(const __nv_bfloat16* __restrict__ z, double* __restrict__ sums,
                                                     int64_t rows, int C, int zcs, int zco) {
+  pdl_sync();
   extern __shared__ __align__(16) uint8_t smem_raw[];
   float* smem_f = reinterpret_cast<float*>(smem_raw + PfRing::bytes(1));
   RowIter it(C);
@@ -274,6 +275,7 @@ struct Dev {   // device copy of petsyn_normact_desc with typed pointers
 // known at compile time (the common case), so the inner loop carries no switch.
 template <int ACT>
 __global__ void __launch_bounds__(256, 3) fwd_kernel(const Dev d) {
+  pdl_sync();
   extern __shared__ __align__(16) uint8_t smem_raw[];
   RowIter it(d.C);
   const bool has_res = d.res != nullptr;
@@ -376,6 +378,7 @@ __global__ void __launch_bounds__(256, 3) fwd_kernel(const Dev d) {
 
 template <int ACT>
 __global__ void __launch_bounds__(256, 2) bwd_reduce_kernel(const Dev d) {
+  pdl_sync();
   extern __shared__ __align__(16) uint8_t smem_raw[];
   const bool has_t2 = d.t2 != nullptr;
   const int nt = has_t2 ? 3 : 2;
@@ -441,6 +444,7 @@ __global__ void __launch_bounds__(256, 2) bwd_reduce_kernel(const Dev d) {
 
 template <int ACT>
 __global__ void __launch_bounds__(256, 2) bwd_apply_kernel(const Dev d) {
+  pdl_sync();
   extern __shared__ __align__(16) uint8_t smem_raw[];
   const int nt_ring = (d.t2 != nullptr ? 3 : 2) + (d.ex != nullptr ? 1 : 0);
   float* smem_f = reinterpret_cast<float*>(smem_raw + PfRing::bytes(nt_ring));
@@ -668,6 +672,7 @@ __global__ void __launch_bounds__(256) add_slice_kernel(const __nv_bfloat16* __r
 // out[c] = sum_r x[r, coff + c]  (bias gradient), fp32, caller-zeroed
 __global__ void __launch_bounds__(256) colsum_kernel(const __nv_bfloat16* __restrict__ x, int cs, int co,
                                                      double* __restrict__ out, int64_t rows, int C) {
+  pdl_sync();
   extern __shared__ float smem_f[];
   RowIter it(C);
   float acc[1][8];
@@ -745,7 +750,7 @@ using namespace petsyn::nx;
       PETSYN_CHECK_CUDA(cudaFuncSetAttribute(KERNEL<A>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024)); \
       attr_ = true;                                                                                          \
     }                                                                                                        \
-    KERNEL<A><<<GRID, 256, SMEM, ST>>>(D);                                                                   \
+    PETSYN_CHECK_CUDA(launch_pdl(KERNEL<A>, GRID, dim3(256), SMEM, ST, D));                                  \
   }                                                                                                          \
   break;
 #define PETSYN_NX_DISPATCH(KERNEL, GRID, SMEM, ST, D)                                         \
@@ -774,8 +779,8 @@ int32_t petsyn_norm_stats_slice(const void* z, int32_t cstride, int32_t coff, do
   const int rpp = 256 / (c / 8);
   const size_t smem = PfRing::bytes(1) + (size_t)rpp * 2 * c * sizeof(float);
   dim3 grid((unsigned)row_blocks(rows, c, nsamples), (unsigned)nsamples);
-  stats_kernel<<<grid, 256, smem, as_stream(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(z), sums, rows, c, cstride,
-                                                       coff);
+  PETSYN_CHECK_CUDA(launch_pdl(stats_kernel, grid, dim3(256), smem, as_stream(stream),
+                               reinterpret_cast<const __nv_bfloat16*>(z), sums, rows, c, cstride, coff));
   return check_launch("stats_kernel");
 }
 
@@ -868,8 +873,8 @@ int32_t petsyn_colsum(const void* x, int32_t cstride, int32_t coff, double* out,
   cudaStream_t st = as_stream(stream);
   PETSYN_CHECK_CUDA(cudaMemsetAsync(out, 0, (size_t)c * sizeof(double), st));
   const int rpp = 256 / (c / 8);
-  colsum_kernel<<<row_blocks(rows, c, 1), 256, (size_t)rpp * c * sizeof(float), st>>>(
-      reinterpret_cast<const __nv_bfloat16*>(x), cstride, coff, out, rows, c);
+  PETSYN_CHECK_CUDA(launch_pdl(colsum_kernel, dim3(row_blocks(rows, c, 1)), dim3(256), (size_t)rpp * c * sizeof(float), st,
+                               reinterpret_cast<const __nv_bfloat16*>(x), cstride, coff, out, rows, c));
   return check_launch("colsum_kernel");
 }
 

@@ -34,7 +34,7 @@ int32_t launch_of(const SlabParams& p, const SlabEpi& e, int grid, int smem, cud
     PETSYN_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
     attr_set = true;
   }
-  kern<<<grid, 192, smem, st>>>(p, e);
+  PETSYN_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(192), smem, st, p, e));
   return check_launch("slab_conv3_epi_kernel");
 }
 

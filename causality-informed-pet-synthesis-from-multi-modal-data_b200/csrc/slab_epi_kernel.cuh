@@ -131,6 +131,7 @@ __global__ void __launch_bounds__(192, (NB == 1 && ATOMS == 1) ? 3 : (NB * ATOMS
     ptx::tmem_alloc(tmem_slot, tmem_cols);
     ptx::tmem_relinquish();
   }
+  ptx::pdl_sync();         // everything above is on-chip set-up: it overlaps the tail of the previous kernel
   if (kNorm && warp >= 2) {
     // normalisation constants of every sample -> shared memory (read as broadcast 16-byte loads by the epilogue)
     const int cnt = p.batch * N;

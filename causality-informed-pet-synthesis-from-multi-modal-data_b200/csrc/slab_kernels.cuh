@@ -136,6 +136,7 @@ __global__ void __launch_bounds__(192) slab_conv_kernel(const __grid_constant__ 
   __syncthreads();
   ptx::tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
+  ptx::pdl_sync();       // everything above is on-chip set-up: it overlaps the tail of the previous kernel
 
   const int G = gridDim.x;
   if (warp == 0) {
@@ -374,6 +375,7 @@ __global__ void __launch_bounds__(192) slab_conv3_kernel(const __grid_constant__
   __syncthreads();
   ptx::tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
+  ptx::pdl_sync();       // everything above is on-chip set-up: it overlaps the tail of the previous kernel
 
   const int G = gridDim.x;
   if (warp == 0) {
@@ -636,6 +638,7 @@ static __global__ void __launch_bounds__(192) slab_wgrad_kernel(const __grid_con
   __syncthreads();
   ptx::tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
+  ptx::pdl_sync();       // everything above is on-chip set-up: it overlaps the tail of the previous kernel
 
   if (warp == 0) {
     if (ptx::elect_one() && has_work) {
@@ -782,6 +785,7 @@ static __global__ void __launch_bounds__(256) slab_wgrad_unpack_kernel(const flo
                                                                 int nimages, int64_t image_floats,
                                                                 const double* __restrict__ dbias_acc,
                                                                 float* __restrict__ dbias, int nbias) {
+  ptx::pdl_sync();
   if (dbias != nullptr && blockIdx.x == 0)                 // bias gradient: double accumulator -> fp32 gradient slot
     for (int i = threadIdx.x; i < nbias; i += 256) dbias[i] = accumulate ? dbias[i] + (float)dbias_acc[i] : (float)dbias_acc[i];
   const int nacc = k3 == 27 ? 3 : 1;

@@ -20,6 +20,7 @@ __device__ __forceinline__ float bf(const __nv_bfloat16 v) { return __bfloat162f
 __global__ void __launch_bounds__(256) resample_down_kernel(const __nv_bfloat16* __restrict__ src, int css, int cos,
                                                             __nv_bfloat16* __restrict__ dst, int csd, int cod, int N,
                                                             int OD, int OH, int OW, int C, float scale, int accumulate) {
+  pdl_sync();
   const int cpt = C / 8;
   const int64_t total = (int64_t)N * OD * OH * OW * cpt;
   const int ID = 2 * OD, IH = 2 * OH, IW = 2 * OW;
@@ -72,6 +73,7 @@ __global__ void __launch_bounds__(256) resample_down_kernel(const __nv_bfloat16*
 __global__ void __launch_bounds__(256) resample_up_kernel(const __nv_bfloat16* __restrict__ src, int css, int cos,
                                                           __nv_bfloat16* __restrict__ dst, int csd, int cod, int N,
                                                           int OD, int OH, int OW, int C, float scale, int accumulate) {
+  pdl_sync();
   const int cpt = C / 8;
   const int64_t total = (int64_t)N * OD * OH * OW * cpt;
   const int ID = OD / 2, IH = OH / 2, IW = OW / 2;
@@ -121,6 +123,7 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const __nv_bfloat16*
                                                             const float* __restrict__ beta,
                                                             __nv_bfloat16* __restrict__ y, float* __restrict__ mean,
                                                             float* __restrict__ rstd, int64_t rows, int C, float eps) {
+  pdl_sync();
   const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
   const int per = (C + 31) / 32;
   for (int64_t r = (int64_t)blockIdx.x * wpb + (threadIdx.x >> 5); r < rows; r += (int64_t)gridDim.x * wpb) {
@@ -154,6 +157,7 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const __nv_bfloat16*
                                                             __nv_bfloat16* __restrict__ dx, float* __restrict__ dgamma,
                                                             float* __restrict__ dbeta, int64_t rows, int C,
                                                             int accumulate, const DetWs ws) {
+  pdl_sync();
   extern __shared__ __align__(16) float sm[];   // [warps][2][C] per-warp partials of dgamma / dbeta (>= 1024 floats)
   const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
   const int per = (C + 31) / 32;
@@ -219,6 +223,7 @@ __device__ __forceinline__ float gelu_grad(float x) {
 // h: [rows, 2F] = (x | gate); out [rows, F] = x * gelu(gate)     (MONAI MLPBlock act="GEGLU")
 __global__ void __launch_bounds__(256) geglu_fwd_kernel(const __nv_bfloat16* __restrict__ h,
                                                         __nv_bfloat16* __restrict__ out, int64_t rows, int F) {
+  pdl_sync();
   const int64_t total = rows * F;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t r = i / F;
@@ -229,6 +234,7 @@ __global__ void __launch_bounds__(256) geglu_fwd_kernel(const __nv_bfloat16* __r
 __global__ void __launch_bounds__(256) geglu_bwd_kernel(const __nv_bfloat16* __restrict__ h,
                                                         const __nv_bfloat16* __restrict__ dout,
                                                         __nv_bfloat16* __restrict__ dh, int64_t rows, int F) {
+  pdl_sync();
   const int64_t total = rows * F;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t r = i / F;
@@ -246,6 +252,7 @@ __global__ void __launch_bounds__(128) covariate_bias_kernel(const float* __rest
                                                              const float* __restrict__ wo, const float* __restrict__ bo,
                                                              float* __restrict__ vbuf, float* __restrict__ bias, int N,
                                                              int Cctx, int C) {
+  pdl_sync();
   extern __shared__ float sv[];   // [C]
   const int n = blockIdx.x;
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
@@ -263,6 +270,7 @@ __global__ void __launch_bounds__(128) covariate_bias_kernel(const float* __rest
 }
 __global__ void __launch_bounds__(256) add_sample_bias_kernel(__nv_bfloat16* __restrict__ t, const float* __restrict__ bias,
                                                               int64_t rows_per_sample, int64_t rows, int C) {
+  pdl_sync();
   const int64_t total = rows * C;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t r = i / C;
@@ -273,6 +281,7 @@ __global__ void __launch_bounds__(256) add_sample_bias_kernel(__nv_bfloat16* __r
 // dbias[n, c] = sum over the sample's rows of dt[., c]
 __global__ void __launch_bounds__(256) sample_colsum_kernel(const __nv_bfloat16* __restrict__ dt, float* __restrict__ out,
                                                             int64_t rows_per_sample, int C, const DetWs ws) {
+  pdl_sync();
   __shared__ __align__(16) float part[1024];
   const int n = blockIdx.y;
   const int c = threadIdx.x % C;
@@ -300,6 +309,7 @@ __global__ void __launch_bounds__(128) covariate_bias_bwd_kernel(const float* __
                                                                  const float* __restrict__ dbias, float* __restrict__ dwv,
                                                                  float* __restrict__ dwo, float* __restrict__ dbo, int N,
                                                                  int Cctx, int C) {
+  pdl_sync();
   // one block per channel c: row c of dWo, dbo[c], dv[:, c] and row c of dWv -- no dependency between blocks
   extern __shared__ float sdv[];  // [N]: dv[n, c] = sum_c' Wo[c', c] * dbias[n, c']
   const int c = blockIdx.x;
@@ -352,13 +362,13 @@ int32_t petsyn_resample2(const void* src, int32_t src_cstride, int32_t src_coff,
   PETSYN_REQUIRE(!up || ((od | oh | ow) & 1) == 0, "upsampled dims must be even");
   const int64_t total = (int64_t)n * od * oh * ow * (c / 8);
   if (up)
-    resample_up_kernel<<<blocks_for(total), 256, 0, as_stream(stream)>>>(CBFP(src), src_cstride, src_coff, BFP(dst),
+    PETSYN_CHECK_CUDA(launch_pdl(resample_up_kernel, dim3(blocks_for(total)), dim3(256), 0, as_stream(stream), CBFP(src), src_cstride, src_coff, BFP(dst),
                                                                          dst_cstride, dst_coff, n, od, oh, ow, c, scale,
-                                                                         accumulate);
+                                                                         accumulate));
   else
-    resample_down_kernel<<<blocks_for(total), 256, 0, as_stream(stream)>>>(CBFP(src), src_cstride, src_coff, BFP(dst),
+    PETSYN_CHECK_CUDA(launch_pdl(resample_down_kernel, dim3(blocks_for(total)), dim3(256), 0, as_stream(stream), CBFP(src), src_cstride, src_coff, BFP(dst),
                                                                            dst_cstride, dst_coff, n, od, oh, ow, c, scale,
-                                                                           accumulate);
+                                                                           accumulate));
   return check_launch("resample kernel");
 }
 
@@ -366,8 +376,8 @@ int32_t petsyn_layernorm_fwd(const void* x, const float* gamma, const float* bet
                              int64_t rows, int32_t c, float eps, void* stream) {
   PETSYN_REQUIRE(x && gamma && beta && y && mean && rstd && rows > 0, "bad argument");
   PETSYN_REQUIRE(c % 8 == 0 && c >= 8 && c <= 1024, "LayerNorm width must be a multiple of 8, at most 1024");
-  layernorm_fwd_kernel<<<blocks_for(rows, 8), 256, 0, as_stream(stream)>>>(CBFP(x), gamma, beta, BFP(y), mean, rstd, rows,
-                                                                           c, eps);
+  PETSYN_CHECK_CUDA(launch_pdl(layernorm_fwd_kernel, dim3(blocks_for(rows, 8)), dim3(256), 0, as_stream(stream), CBFP(x), gamma, beta, BFP(y), mean, rstd, rows,
+                                                                           c, eps));
   return check_launch("layernorm_fwd_kernel");
 }
 
@@ -387,20 +397,20 @@ int32_t petsyn_layernorm_bwd(const void* x, const void* dy, const float* gamma, 
   const size_t ln_smem = std::max<size_t>((size_t)8 * 2 * c, 1024) * sizeof(float);
   if (ln_smem > 48 * 1024)
     PETSYN_CHECK_CUDA(cudaFuncSetAttribute(layernorm_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ln_smem));
-  layernorm_bwd_kernel<<<blocks_for(rows, 8, 148 * 4), 256, ln_smem, st>>>(
-      CBFP(x), CBFP(dy), gamma, mean, rstd, BFP(dx), dgamma, dbeta, rows, c, accumulate_dx, ws);
+  PETSYN_CHECK_CUDA(launch_pdl(layernorm_bwd_kernel, dim3(blocks_for(rows, 8, 148 * 4)), dim3(256), ln_smem, st, 
+      CBFP(x), CBFP(dy), gamma, mean, rstd, BFP(dx), dgamma, dbeta, rows, c, accumulate_dx, ws));
   return check_launch("layernorm_bwd_kernel");
 }
 
 int32_t petsyn_geglu_fwd(const void* h, void* out, int64_t rows, int32_t f, void* stream) {
   PETSYN_REQUIRE(h && out && rows > 0 && f > 0, "bad argument");
-  geglu_fwd_kernel<<<blocks_for(rows * f), 256, 0, as_stream(stream)>>>(CBFP(h), BFP(out), rows, f);
+  PETSYN_CHECK_CUDA(launch_pdl(geglu_fwd_kernel, dim3(blocks_for(rows * f)), dim3(256), 0, as_stream(stream), CBFP(h), BFP(out), rows, f));
   return check_launch("geglu_fwd_kernel");
 }
 
 int32_t petsyn_geglu_bwd(const void* h, const void* dout, void* dh, int64_t rows, int32_t f, void* stream) {
   PETSYN_REQUIRE(h && dout && dh && rows > 0 && f > 0, "bad argument");
-  geglu_bwd_kernel<<<blocks_for(rows * f), 256, 0, as_stream(stream)>>>(CBFP(h), CBFP(dout), BFP(dh), rows, f);
+  PETSYN_CHECK_CUDA(launch_pdl(geglu_bwd_kernel, dim3(blocks_for(rows * f)), dim3(256), 0, as_stream(stream), CBFP(h), CBFP(dout), BFP(dh), rows, f));
   return check_launch("geglu_bwd_kernel");
 }
 
@@ -409,11 +419,11 @@ int32_t petsyn_covariate_bias_fwd(const float* ctx, const float* wv, const float
                                   int64_t rows_per_sample, void* stream) {
   PETSYN_REQUIRE(ctx && wv && wo && bo && vbuf && bias && tokens && n > 0 && cctx > 0 && c > 0, "bad argument");
   cudaStream_t st = as_stream(stream);
-  covariate_bias_kernel<<<n, 128, c * sizeof(float), st>>>(ctx, wv, wo, bo, vbuf, bias, n, cctx, c);
+  PETSYN_CHECK_CUDA(launch_pdl(covariate_bias_kernel, dim3(n), dim3(128), c * sizeof(float), st, ctx, wv, wo, bo, vbuf, bias, n, cctx, c));
   int32_t rc = check_launch("covariate_bias_kernel");
   if (rc) return rc;
-  add_sample_bias_kernel<<<blocks_for(rows_per_sample * n * c), 256, 0, st>>>(BFP(tokens), bias, rows_per_sample,
-                                                                            rows_per_sample * n, c);
+  PETSYN_CHECK_CUDA(launch_pdl(add_sample_bias_kernel, dim3(blocks_for(rows_per_sample * n * c)), dim3(256), 0, st, BFP(tokens), bias, rows_per_sample,
+                                                                            rows_per_sample * n, c));
   return check_launch("add_sample_bias_kernel");
 }
 
@@ -430,10 +440,10 @@ int32_t petsyn_covariate_bias_bwd(const float* ctx, const float* wo, const float
     int32_t rcw = det_workspace(&ws);
     if (rcw) return rcw;
   }
-  sample_colsum_kernel<<<grid, 256, 0, st>>>(CBFP(dtokens), dbias, rows_per_sample, c, ws);
+  PETSYN_CHECK_CUDA(launch_pdl(sample_colsum_kernel, dim3(grid), dim3(256), 0, st, CBFP(dtokens), dbias, rows_per_sample, c, ws));
   int32_t rc = check_launch("sample_colsum_kernel");
   if (rc) return rc;
-  covariate_bias_bwd_kernel<<<c, 128, (size_t)n * sizeof(float), st>>>(ctx, wo, vbuf, dbias, dwv, dwo, dbo, n, cctx, c);
+  PETSYN_CHECK_CUDA(launch_pdl(covariate_bias_bwd_kernel, dim3(c), dim3(128), (size_t)n * sizeof(float), st, ctx, wo, vbuf, dbias, dwv, dwo, dbo, n, cctx, c));
   return check_launch("covariate_bias_bwd_kernel");
 }
 
