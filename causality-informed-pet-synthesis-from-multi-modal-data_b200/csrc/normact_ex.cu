@@ -131,7 +131,26 @@ __device__ __forceinline__ void block_reduce_channels_to(const RowIter& it, floa
                                                          int pitch1, int off1, double* out2, int pitch2, int off2, int C,
                                                          float extra = 0.f, double* extra_out = nullptr) {
   __shared__ float s_extra[8];
-  if (it.active) {
+  // Rows of one channel octet sit in lanes tx, tx + cpt, tx + 2 cpt, ... of every warp (cpt a power of two <= 32): a warp
+  // butterfly folds them first, so the serial tail below adds 8 per-warp partials instead of `rpp` (up to 128) per-row ones
+  const bool fold = (it.cpt & (it.cpt - 1)) == 0 && it.cpt <= 32;
+  int nparts = it.rpp;
+  if (fold) {
+    for (int off = it.cpt; off < 32; off <<= 1) {
+#pragma unroll
+      for (int v = 0; v < NV; ++v)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[v][i] += __shfl_xor_sync(0xffffffffu, acc[v][i], off);
+    }
+    nparts = (int)(blockDim.x >> 5);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (lane < it.cpt) {
+#pragma unroll
+      for (int v = 0; v < NV; ++v)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) smem[(w * NV + v) * C + lane * 8 + i] = acc[v][i];
+    }
+  } else if (it.active) {
 #pragma unroll
     for (int v = 0; v < NV; ++v)
 #pragma unroll
@@ -145,7 +164,7 @@ __device__ __forceinline__ void block_reduce_channels_to(const RowIter& it, floa
   const int nc = NV * C;
   for (int e = threadIdx.x; e < nc; e += blockDim.x) {
     float s = 0.f;
-    for (int r = 0; r < it.rpp; ++r) s += smem[r * nc + e];
+    for (int r = 0; r < nparts; ++r) s += smem[r * nc + e];
     const int v = e / C, c = e - v * C;
     if (out1) atomicAdd(out1 + v * pitch1 + off1 + c, (double)s);
     if (out2) atomicAdd(out2 + v * pitch2 + off2 + c, (double)s);
@@ -605,14 +624,28 @@ __global__ void __launch_bounds__(256, 2) bwd_apply_kernel(const Dev d) {
   // the bias gradient sums over the samples as well: one reduction over the whole grid
   if (d.dz_colsum != nullptr) {
     // column sums of the final dz over the rows of this CTA -> double accumulator, channels [cs_off, cs_off + cs_n) only
-    if (it.active) {
+    // (warp butterfly over the rows of a channel octet first, as in block_reduce_channels_to)
+    const bool fold = (it.cpt & (it.cpt - 1)) == 0 && it.cpt <= 32;
+    int nparts = it.rpp;
+    if (fold) {
+      for (int off = it.cpt; off < 32; off <<= 1) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) csum[0][i] += __shfl_xor_sync(0xffffffffu, csum[0][i], off);
+      }
+      nparts = (int)(blockDim.x >> 5);
+      const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+      if (lane < it.cpt) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) smem_f[w * d.C + lane * 8 + i] = csum[0][i];
+      }
+    } else if (it.active) {
 #pragma unroll
       for (int i = 0; i < 8; ++i) smem_f[it.ty * d.C + it.tx * 8 + i] = csum[0][i];
     }
     __syncthreads();
     for (int e = threadIdx.x; e < d.cs_n; e += blockDim.x) {
       float s = 0.f;
-      for (int r = 0; r < it.rpp; ++r) s += smem_f[r * d.C + d.cs_off + e];
+      for (int r = 0; r < nparts; ++r) s += smem_f[r * d.C + d.cs_off + e];
       atomicAdd(d.dz_colsum + e, (double)s);
     }
   }
