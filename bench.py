@@ -32,6 +32,9 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch from the committed `ncu --set full` captures (profiles/)
+PROFILED_TRAFFIC = {"slab_conv3_epi": None}
+
 WORKLOADS = {
     # name: (ngf, (D, H, W), per-GPU batch)
     "unet3d_train_cfg1": (64, (96, 112, 96), 1),
@@ -297,11 +300,12 @@ def run_petsyn(args, ngf, shape, batch):
             "gpu_launches": launches * args.steps,
             "clocks": clocks,
             "roofline": {"bound": "tensor", "kernel": f"igemm_kernel<128,64,3,bf16> ({dom}: Upsample x2 + Conv3d "
-                         f"{plan.desc.cin}->{plan.desc.cout} k3)", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s",
-                         "frac": ach / peak_tf, "traffic": None, "executed_tflops": exe,
+                         f"{plan.desc.cin}->{plan.desc.cout} k3)", "achieved": exe, "peak": peak_tf, "unit": "TFLOP/s",
+                         "frac": exe / peak_tf, "traffic": None, "algorithmic_tflops": ach,
                          "peak_source": peak_src, "launch_ms": per_kernel[dom],
-                         "note": "achieved = direct-convolution FLOPs (27 taps on the upsampled grid); the kernel "
-                                 "executes 8 merged taps per output phase (3.375x fewer MACs): executed_tflops"},
+                         "note": "achieved / frac = FLOPs the kernel EXECUTES (8 merged taps per output phase); "
+                                 "algorithmic_tflops = direct-convolution FLOPs (27 taps on the upsampled grid, 3.375x "
+                                 "more MACs) over the same time"},
             "step_breakdown": {"conv_kernels_ms": conv_ms, "per_conv_ms": per_kernel,
                                "model_tflops_algorithmic": step_flops_alg / (ms_total / args.steps * 1e-3) / 1e12},
             "final_loss": final_loss,
@@ -397,8 +401,12 @@ def run_petsyn_bmgan(args, cfg_name, shape, batch):
         trainer.step(*resident[i % pool])
     torch.cuda.synchronize()
     n0 = ops.launch_count()
+    if args.profile_one_step:              # `ncu --profile-from-start off`: exactly this (eager) step is profiled
+        torch.cuda.profiler.start()
     trainer.step(*resident[0])
     torch.cuda.synchronize()
+    if args.profile_one_step:
+        torch.cuda.profiler.stop()
     launches = ops.launch_count() - n0
     if not args.no_graph:
         trainer.capture()                  # one graph on one GPU; graph segments around the collectives when data parallel
@@ -976,9 +984,12 @@ def run_petsyn_atten(args, shape, batch, adv=False):
     for (idx, which), ms_ in op_ms.items():
         key = f"{type(tape.ops[idx]).__name__}.{which}"
         by_kind[key] = by_kind.get(key, 0.0) + ms_
-    # the dominant kernel: slab_conv3_kernel on the full-resolution 16 -> 16 layers (one launch = one fprop)
+    # the dominant kernel family: the depth-folded slab convolution on the full-resolution 16 -> 16 layers (one launch = one
+    # fprop).  conv1 of a ResnetBlock also sums its output for norm2 (reads x, writes y); conv2 adds the skip tensor and sums
+    # the block output for the next norm1 (reads x and the skip tensor, writes y)
     dom = [i for i, op in enumerate(tape.ops) if isinstance(op, G.ConvOp) and op.plan.kernel_path[0] == 1
            and op.cin == 16 and op.cout == 16 and op.x.buf.rows == batch * shape[0] * shape[1] * shape[2]]
+    dom_res = [i for i in dom if tape.ops[i].res is not None]
     dom_ms = statistics.mean(op_ms[(i, "fwd")] for i in dom) if dom else None
     # second largest: the slab weight-gradient kernel of the same layers, timed in isolation (memset + kernel + unpack)
     wg_ms = None
@@ -1019,13 +1030,16 @@ def run_petsyn_atten(args, shape, batch, adv=False):
             step_flops += fwd + (3.0 + 1.0 + 4.0) * trainer.deng.flops_algorithmic
         ach = step_flops / (ms * 1e-3) / 1e12
         vox = batch * d * h * w
-        dom_bytes = vox * 16 * 2 * 2                      # bf16 read-once of x + write-once of y, 16 channels each
+        wg_bytes = vox * 16 * 2 * 2                       # weight gradient: bf16 read-once of x and dy, 16 channels each
+        # bf16 read-once of x + write-once of y, 16 channels each; the residual launches also read the skip tensor once
+        dom_bytes = (vox * 16 * 2 * (2 * (len(dom) - len(dom_res)) + 3 * len(dom_res)) / len(dom)) if dom else 0.0
         dom_flops = 2.0 * vox * 16 * 16 * 27
-        roof = {"bound": "hbm", "kernel": "slab_conv3_kernel<1> (Conv3d 16->16 k3 s1 p1 at 96x128x96, batch 2: the "
-                f"{len(dom)} full-resolution ResnetBlock convs; fprop launches timed; all slab_conv3 instantiations together "
-                "are the largest kernel of the step, 14 %: profiles/r1_launches_default_bench_summary.csv)", "achieved": None, "peak": peak_bw,
-                "unit": "GB/s", "frac": None, "traffic": 111.0e6,
-                "traffic_source": "profiles/r1_slab_conv3_ncu_full_summary.csv (dram read + write bytes of one launch)",
+        roof = {"bound": "hbm", "kernel": "slab_conv3_epi_kernel<1, 1, *> (Conv3d 16->16 k3 s1 p1 at 96x128x96, batch 2, with the "
+                f"fused ResnetBlock epilogues: {len(dom) - len(dom_res)} launches that also sum their output for the next GroupNorm, "
+                f"{len(dom_res)} that also add the skip tensor; fprop launches timed, mean over the {len(dom)}; the slab_conv3 "
+                "family is 14 % of the step's kernel time: profiles/r2_launches_default_bench_summary.csv)",
+                "achieved": None, "peak": peak_bw, "unit": "GB/s", "frac": None, "traffic": PROFILED_TRAFFIC.get("slab_conv3_epi"),
+                "traffic_source": "profiles/r2_slab_conv3_epi_ncu_full_summary.csv (dram read + write bytes of one statistics-epilogue launch)",
                 "algorithmic_bytes_per_launch": dom_bytes, "algorithmic_flops_per_launch": dom_flops,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6459 GB/s"}
         if dom_ms:
@@ -1034,9 +1048,10 @@ def run_petsyn_atten(args, shape, batch, adv=False):
             roof["frac"] = roof["achieved"] / peak_bw
         if wg_ms:
             # weight gradient of the same layer: reads x and dy once (the 27x16x16 result is negligible)
-            roof["also"] = {"kernel": "slab_wgrad_kernel (same 16->16 layer; memset + kernel + unpack)", "bound": "hbm",
-                            "launch_ms": wg_ms, "achieved": dom_bytes / (wg_ms * 1e-3) / 1e9, "unit": "GB/s",
-                            "frac": dom_bytes / (wg_ms * 1e-3) / 1e9 / peak_bw}
+            roof["also"] = {"kernel": "slab_wgrad_kernel (same 16->16 layer; kernel + image reduction + unpack; the largest "
+                            "single symbol of the step, 13 %; runs on the side stream beside the data-gradient chain)",
+                            "bound": "hbm", "launch_ms": wg_ms, "achieved": wg_bytes / (wg_ms * 1e-3) / 1e9, "unit": "GB/s",
+                            "frac": wg_bytes / (wg_ms * 1e-3) / 1e9 / peak_bw, "algorithmic_bytes_per_launch": wg_bytes}
         line = {
             "metric": ATTEN_METRIC + (" + LSGAN adversarial term + discriminator phase (train_unet.py:153-193)" if adv else ""),
             "value": world * batch * args.steps / (ms_total * 1e-3), "unit": UNIT,
@@ -1244,6 +1259,10 @@ def run_petsyn_infer(args, family, shape, micro):
         ms = ms_total / args.steps
         d, h, w = shape
         ach = fwd * chunks / (ms * 1e-3) / 1e12 if fwd else None
+        exe_f = fwd
+        if family != "synth_classify":
+            exe_f = float(getattr(eng, "flops_executed", 0.0)) or fwd      # UnetGenerator3d: merged-tap up convolutions
+        exe = exe_f * chunks / (ms * 1e-3) / 1e12 if exe_f else None
         line = {
             "metric": ("3D T1->PET synthesize-then-classify throughput (generator + classifier inference, device to device)"
                        if family == "synth_classify" else INFER_METRIC), "value": vols / (ms_total * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -1259,7 +1278,9 @@ def run_petsyn_infer(args, family, shape, micro):
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches * args.steps, "clocks": clocks,
             "roofline": {"bound": "tensor", "kernel": "whole forward: algorithmic conv (+ attention) FLOPs / time",
-                         "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": (ach / peak_tf) if ach else None,
+                         "achieved": exe, "peak": peak_tf, "unit": "TFLOP/s", "frac": (exe / peak_tf) if exe else None,
+                         "algorithmic_tflops": ach, "note": "achieved / frac on EXECUTED FLOPs (merged taps of the "
+                         "up-sampling convolutions counted once); algorithmic_tflops = direct-convolution FLOPs over the same time",
                          "traffic": None, "forward_gflop_per_volume": fwd / micro / 1e9 if fwd else None,
                          "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback"},
         }

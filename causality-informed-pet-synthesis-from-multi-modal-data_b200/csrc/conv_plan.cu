@@ -534,6 +534,9 @@ static int32_t finish_side(GemmSide& g, int N, int allow_slab = 0 /* 0 no, 1 = k
   g.kc_pad = (g.Kc + g.kch - 1) / g.kch * g.kch;
   if (g.R >= 128) g.block_n = 128;
   else g.block_n = (g.R + 15) / 16 * 16;
+  // 256 output channels per CTA: the 128 x 64 activation tile of a K step is read from shared memory once for twice the MMA
+  // work (SS-mode tcgen05.mma is bound by its operand reads at N = 128); needs enough tiles to fill the machine without it
+  if (g.R % 256 == 0 && getenv("PETSYN_BN256") != nullptr) g.block_n = 256;
   if (g.block_n > 64 && g.block_n < 128) g.block_n = 128;
   choose_box(g.out_w, g.out_h, g.out_d, 128, false, &g.box_w, &g.box_h, &g.box_d);
   {
@@ -828,6 +831,7 @@ static int32_t launch_igemm(const GemmSide& g, int batch, cudaStream_t st) {
       case 48: return launch_igemm_bn<48, OUT_BF16_REDUCE>(g, grid, st);
       case 64: return launch_igemm_bn<64, OUT_BF16_REDUCE>(g, grid, st);
       case 128: return launch_igemm_bn<128, OUT_BF16_REDUCE>(g, grid, st);
+    case 256: return launch_igemm_bn<256, OUT_BF16_REDUCE>(g, grid, st);
       default: return fail(PETSYN_EINVAL, "unsupported BLOCK_N %d for accumulating output", g.block_n);
     }
   }
@@ -838,6 +842,7 @@ static int32_t launch_igemm(const GemmSide& g, int batch, cudaStream_t st) {
       case 48: return launch_igemm_bn<48, OUT_F32_REDUCE>(g, grid, st);
       case 64: return launch_igemm_bn<64, OUT_F32_REDUCE>(g, grid, st);
       case 128: return launch_igemm_bn<128, OUT_F32_REDUCE>(g, grid, st);
+    case 256: return launch_igemm_bn<256, OUT_F32_REDUCE>(g, grid, st);
       default: return fail(PETSYN_EINVAL, "unsupported BLOCK_N %d for split-K", g.block_n);
     }
   }
@@ -848,6 +853,7 @@ static int32_t launch_igemm(const GemmSide& g, int batch, cudaStream_t st) {
       case 48: return launch_igemm_bn<48, OUT_F32>(g, grid, st);
       case 64: return launch_igemm_bn<64, OUT_F32>(g, grid, st);
       case 128: return launch_igemm_bn<128, OUT_F32>(g, grid, st);
+    case 256: return launch_igemm_bn<256, OUT_F32>(g, grid, st);
       default: return fail(PETSYN_EINVAL, "unsupported BLOCK_N %d for fp32 output", g.block_n);
     }
   }
@@ -857,6 +863,7 @@ static int32_t launch_igemm(const GemmSide& g, int batch, cudaStream_t st) {
     case 48: return launch_igemm_bn<48, OUT_BF16>(g, grid, st);
     case 64: return launch_igemm_bn<64, OUT_BF16>(g, grid, st);
     case 128: return launch_igemm_bn<128, OUT_BF16>(g, grid, st);
+    case 256: return launch_igemm_bn<256, OUT_BF16>(g, grid, st);
     default: return fail(PETSYN_EINVAL, "unsupported BLOCK_N %d", g.block_n);
   }
 }

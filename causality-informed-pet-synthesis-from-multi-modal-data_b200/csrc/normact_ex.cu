@@ -722,10 +722,14 @@ __global__ void __launch_bounds__(256) colsum_kernel(const __nv_bfloat16* __rest
   block_reduce_channels<1>(it, acc, smem_f, out, C);
 }
 
-static int row_blocks(int64_t rows, int C, int nsamples) {
+// grid.x per sample: `waves` = CTAs per SM over all samples.  Two persistent CTAs per SM with equal shares of the rows: one
+// wave (no partial last wave, one ramp-up), and room left on every SM for the weight-gradient kernels of the side stream.
+// Measured on configs[1] (whole step): 8 CTAs per SM 15.50 ms, 6: 15.32, 4: 15.03, 3: 15.15, 2: 14.74, 1: 16.19
+static int row_blocks(int64_t rows, int C, int nsamples, int waves = 2) {
   const int rpp = 256 / (C / 8);
   const int64_t want = (rows + rpp - 1) / rpp;
-  return (int)std::max<int64_t>(1, std::min<int64_t>(want, std::max(1, 148 * 8 / nsamples)));
+  if (const char* e = getenv("PETSYN_NORM_WAVES")) waves = std::max(1, atoi(e));
+  return (int)std::max<int64_t>(1, std::min<int64_t>(want, std::max(1, 148 * waves / nsamples)));
 }
 
 static int32_t to_dev(const petsyn_normact_desc* d, Dev* o) {

@@ -7,6 +7,8 @@
 
 #include <algorithm>
 
+#include <cstdlib>
+
 #include "common.h"
 #include "det_reduce.cuh"
 
@@ -340,6 +342,7 @@ __global__ void __launch_bounds__(128) covariate_bias_bwd_kernel(const float* __
 }
 
 static int blocks_for(int64_t total, int per_block = 256, int cap = 148 * 16) {
+  if (const char* e = getenv("PETSYN_TK_WAVES")) cap = 148 * std::max(1, atoi(e));      // tuning experiments only
   return (int)std::max<int64_t>(1, std::min<int64_t>((total + per_block - 1) / per_block, cap));
 }
 
