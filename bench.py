@@ -33,7 +33,7 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch from the committed `ncu --set full` captures (profiles/)
-PROFILED_TRAFFIC = {"slab_conv3_epi": None}
+PROFILED_TRAFFIC = {"slab_conv3_epi": 113.1e6}    # 75.6 MB read + 37.5 MB written (statistics-epilogue launch)
 
 WORKLOADS = {
     # name: (ngf, (D, H, W), per-GPU batch)

@@ -1484,7 +1484,8 @@ int32_t petsyn_conv_wgrad_bias(petsyn_conv_plan* pl, const void* x, const void* 
       const int cap = (q.tmem_cols <= 256 ? 110 : 200) * 1024;
       q.xring = slab_wgrad_smem_bytes(q.xslab_bytes, q.gslab_bytes, ncols, 8, q.gring) <= cap ? 8 : 4;
       pl->wg_slab_smem = slab_wgrad_smem_bytes(q.xslab_bytes, q.gslab_bytes, ncols, q.xring, q.gring);
-      const int occ = q.tmem_cols <= 256 ? std::max(1, std::min(2, (227 * 1024) / (pl->wg_slab_smem + 1024))) : 1;
+      int occ = q.tmem_cols <= 256 ? std::max(1, std::min(2, (227 * 1024) / (pl->wg_slab_smem + 1024))) : 1;
+      if (const char* e = getenv("PETSYN_WGRAD_OCC")) occ = std::max(1, std::min(occ, atoi(e)));       // tuning experiments only
       const int ctas = std::max(1, 148 * occ / (co_atoms * groups));
       slab_split(q.W, q.H, q.D, q.batch, kWgW, kWgH, ctas, &q.dchunk, &q.nchunks, &q.items);
       pl->wg_slab_grid = std::min(std::min(ctas, q.items), std::max(1, 296 / (co_atoms * groups)));
