@@ -547,7 +547,7 @@ static int32_t finish_side(GemmSide& g, int N, int allow_slab = 0 /* 0 no, 1 = k
     int min_steps = 1 << 30;
     for (auto& sp : g.prog.subs) min_steps = std::min<int>(min_steps, (int)sp.size() * (g.kc_pad / g.kch));
     int ks = (int)(296 / std::max<int64_t>(tiles, 1));
-    ks = std::min(ks, std::max(1, min_steps / 8));
+    ks = std::min(ks, std::max(1, min_steps / 8));        // (<= min_steps: no split of any sub-problem is ever empty)
     g.ksplit = (ks >= 2 && !g.out_fp32) ? ks : 1;
   }
   std::vector<IgemmTap> taps;
@@ -875,7 +875,7 @@ static int32_t run_side(GemmSide& g, const ViewSpec& vc, void* c, const float* b
     const size_t bytes = (size_t)g.out_rows_full * g.R * sizeof(float) * g.ksplit;     // one partial image per K split
     if (g.workspace == nullptr || g.workspace_bytes < bytes)
       return fail(PETSYN_ENOMEM, "split-K needs a %zu-byte workspace (petsyn_conv_set_workspace)", bytes);
-    PETSYN_CHECK_CUDA(cudaMemsetAsync(g.workspace, 0, bytes, st));
+    // (no clearing: every split of every sub-problem owns at least one K step, so each partial image is stored in full)
     int32_t rc = launch_igemm(g, batch, st);
     if (rc) return rc;
     const int64_t total = g.out_rows_full * (g.R / 8);

@@ -118,11 +118,12 @@ __global__ void __launch_bounds__(128) igemm_kernel(const __grid_constant__ Igem
   const int w0 = tw * p.box_w, h0 = th * p.box_h, d0 = td * p.box_d;
   const int n0 = blockIdx.y * BLOCK_N;
   const int total_steps = sub.tap_count * p.kc_chunks;
-  const int per_split = (total_steps + p.ksplit - 1) / p.ksplit;
-  const int s_begin = split * per_split;
-  const int s_end = min(total_steps, s_begin + per_split);
+  // balanced partition of the K steps: no split is empty as long as ksplit <= total_steps (the plan guarantees it), so every
+  // partial image of the split-K workspace is written in full and needs no clearing
+  const int s_begin = (int)(((int64_t)split * total_steps) / p.ksplit);
+  const int s_end = (int)(((int64_t)(split + 1) * total_steps) / p.ksplit);
   const int nsteps = s_end - s_begin;
-  if (nsteps <= 0) return;   // uniform across the CTA; nothing to add to the split-K sum
+  if (nsteps <= 0) return;   // uniform across the CTA (cannot happen for a planned split)
 
   for (int i = tid; i < sub.tap_count; i += 128) s_taps[i] = p.taps[sub.tap_begin + i];
 

@@ -65,6 +65,7 @@ CASES = [
     ("conv", 1, 24, 40, 40, 64, 48, 3, 1, 1),      # two groups of 2 atoms; slab fprop with 4 atoms
     ("conv", 2, 12, 32, 48, 80, 16, 3, 1, 1),      # 5 atoms: the second group's last atom is zero-filled by TMA
     ("conv", 2, 16, 32, 48, 48, 16, 1, 1, 0),      # 1x1x1 skip connection on the slab kernels (no halo, one tap)
+    ("conv", 2, 16, 32, 48, 64, 64, 3, 1, 1),      # 64 -> 64 with many voxels: gather-form kernel (weights do not fit the slab kernels)
     ("conv", 1, 24, 40, 40, 32, 32, 1, 1, 0),      # ... ragged tiles
     ("conv", 2, 12, 32, 48, 96, 32, 1, 1, 0),      # ... wgrad over two channel groups; fprop / dgrad stay gather-form
 ]

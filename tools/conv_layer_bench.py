@@ -35,6 +35,9 @@ LAYERS = {
     "h32_32": (ops.OP_CONV, 2, 48, 64, 48, 32, 32, 3, 1, 1),
     "h64_32": (ops.OP_CONV, 2, 48, 64, 48, 64, 32, 3, 1, 1),
     "h64_64": (ops.OP_CONV, 2, 48, 64, 48, 64, 64, 3, 1, 1),
+    "q64_64": (ops.OP_CONV, 2, 24, 32, 24, 64, 64, 3, 1, 1),        # quarter resolution (level 2)
+    "q128_64": (ops.OP_CONV, 2, 24, 32, 24, 128, 64, 3, 1, 1),
+    "e128_128": (ops.OP_CONV, 2, 12, 16, 12, 128, 128, 3, 1, 1),    # eighth resolution (level 3): split-K + finish
 }
 
 
