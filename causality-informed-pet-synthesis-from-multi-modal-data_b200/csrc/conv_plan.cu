@@ -664,6 +664,7 @@ static int32_t bind_slab(GemmSide& g, const ViewSpec& va, const ViewSpec& vc, co
                             : slab_smem_bytes(p.ntaps, atoms, g.R, p.slab_bytes, 0, g.out_fp32 ? 4 : 2);
   int ring = (fixed + 8 * p.slab_bytes <= 110 * 1024) ? 8 : 4;
   if (g.slab3) ring = 4;                                  // the depth-folded kernel keeps one slab live + prefetch
+  if (g.slab3 && getenv("PETSYN_SLAB3_RING")) ring = atoi(getenv("PETSYN_SLAB3_RING")) == 2 ? 2 : 4;   // tuning experiments only
   if (const char* e = getenv("PETSYN_SLAB_RING")) ring = atoi(e) == 4 ? 4 : 8;       // tuning experiments only
   p.ring = ring;
   g.slab_smem = fixed + ring * p.slab_bytes;

@@ -24,6 +24,9 @@
 namespace petsyn {
 
 enum { kEpiSide = 1, kEpiStats = 2, kEpiNormReduce = 4 };
+#ifndef PETSYN_EPI_MINB
+#define PETSYN_EPI_MINB 3       // resident CTAs per SM the 16 -> 16 variants are compiled for
+#endif
 constexpr int kEpiMaxBatch = 8;                        // samples whose normalisation constants fit the shared-memory table
 
 struct alignas(64) SlabEpi {
@@ -70,7 +73,7 @@ __device__ __forceinline__ float warp_transpose_sum32(float (&a)[32], int lane) 
 
 // FLAGS (compile time) = the epilogue's work: kEpiStats | [kEpiSide]  or  kEpiSide  or  kEpiNormReduce
 template <int ATOMS, int NB, int FLAGS>
-__global__ void __launch_bounds__(192, (NB == 1 && ATOMS == 1) ? 3 : (NB * ATOMS <= 2 ? 2 : 1))
+__global__ void __launch_bounds__(192, (NB == 1 && ATOMS == 1) ? PETSYN_EPI_MINB : (NB * ATOMS <= 2 ? 2 : 1))
     slab_conv3_epi_kernel(const __grid_constant__ SlabParams p, const __grid_constant__ SlabEpi e) {
   constexpr int N = NB * 16;
   constexpr bool kSide = (FLAGS & kEpiSide) != 0, kStats = (FLAGS & kEpiStats) != 0, kNorm = (FLAGS & kEpiNormReduce) != 0;
@@ -200,7 +203,7 @@ __global__ void __launch_bounds__(192, (NB == 1 && ATOMS == 1) ? 3 : (NB * ATOMS
       const uint32_t w_lo = b_lo0 + (ptx::smem_u32(s_w) >> 4);
       const uint32_t slab16 = uint32_t(p.slab_bytes) >> 4;
       constexpr uint32_t blk16 = uint32_t(N) * 2;
-      const uint32_t rshift = (R == 8) ? 3 : 2;
+      const uint32_t rshift = (R == 8) ? 3 : (R == 4 ? 2 : 1);
       ptx::mbar_wait(w_bar, 0);
       for (int b = 0; b < 3; ++b) ptx::mbar_wait(&acc_free[b], 0);
       ptx::tc_fence_after_sync();

@@ -420,7 +420,7 @@ __global__ void __launch_bounds__(192) slab_conv3_kernel(const __grid_constant__
       const uint32_t w_lo = b_lo0 + (ptx::smem_u32(s_w) >> 4);
       const uint32_t slab16 = uint32_t(p.slab_bytes) >> 4;
       const uint32_t blk16 = uint32_t(N) * 2;                  // one weight block (N rows x 32 B) in 16-byte units
-      const uint32_t rshift = (R == 8) ? 3 : 2;
+      const uint32_t rshift = (R == 8) ? 3 : (R == 4 ? 2 : 1);
       ptx::mbar_wait(w_bar, 0);
       for (int b = 0; b < 3; ++b) ptx::mbar_wait(&acc_free[b], 0);      // the epilogue warps zeroed the three blocks
       ptx::tc_fence_after_sync();
