@@ -7,9 +7,11 @@ Kept identical to the reference: the constructor signature and its ``ValueError`
 ``MLPBlock``'s ``linear1/linear2``) and therefore every ``state_dict`` key and shape (416 tensors for
 ``unet/config/training.json``), the ``zero_module`` initialisation, ``forward(x, context)`` on fp32 NCDHW tensors, autograd.
 
-Implemented configuration family: ``resblock_updown=True``, ``with_conditioning=True`` (attention levels use
-cross-attention transformer blocks), one transformer layer, 32 channels per head -- i.e. ``training.json``.  Other
-combinations raise ``NotImplementedError`` (class embeddings are broken in the reference itself).
+Implemented configuration families: ``resblock_updown`` True (``training.json``) or False (conv-form resampling, the
+reference's own smoke block); ``with_conditioning=True`` (attention levels use cross-attention transformer blocks with one
+transformer layer; heads of 8, 16 or 32 channels) or False (``AttentionBlock`` with 32-channel heads, no context); any
+number of levels / ResnetBlocks per level.  Class embeddings (broken in the reference itself), several
+transformer layers and attention dropout raise ``NotImplementedError``.
 
 Execution: a static op tape (``graph.py``).  GroupNorm+SiLU, residual sums and skip concatenation are fused
 bandwidth kernels over channels-last bf16 buffers; every Conv3d (3^3, 1^3, the nearest-x2 + 3^3 of the up-sampling
@@ -134,12 +136,38 @@ class SpatialTransformer(_Container):
         self.proj_out = zero_module(_Convolution(inner, in_channels, 1))
 
 
+class AttentionBlock(_Container):
+    """``AttentionBlock`` (atten_unet_model.py:346-461), the attention of the ``with_conditioning=False`` family: GroupNorm,
+    ``to_q`` / ``to_k`` / ``to_v`` with bias, multi-head self-attention, residual.  ``proj_attn`` is constructed (:383) but the
+    reference's forward never applies it: it keeps its place in the state dict and receives zero gradients."""
+
+    def __init__(self, channels: int, head_channels: Optional[int], norm_num_groups: int, norm_eps: float):
+        super().__init__()
+        self.num_channels = channels
+        self.num_heads = channels // head_channels if head_channels is not None else 1
+        self.norm = nn.GroupNorm(norm_num_groups, channels, eps=norm_eps, affine=True)
+        self.to_q, self.to_k, self.to_v = nn.Linear(channels, channels), nn.Linear(channels, channels), nn.Linear(channels, channels)
+        self.proj_attn = nn.Linear(channels, channels)
+
+
+def _attention_module(c: int, attn: dict) -> nn.Module:
+    if attn.get("block"):                                 # with_conditioning=False
+        return AttentionBlock(c, attn["head_channels"], attn["norm_num_groups"], attn["norm_eps"])
+    return SpatialTransformer(c, **attn)
+
+
 class _DownBlock(_Container):
     def __init__(self, cin, cout, nres, groups, eps, add_downsample, attn: Optional[dict], resblock_updown: bool = True):
         super().__init__()
-        resnets = [ResnetBlock(cin if i == 0 else cout, cout, norm_num_groups=groups, norm_eps=eps) for i in range(nres)]
-        if attn is not None:      # the reference's CrossAttn blocks register `attentions` before `resnets`
-            self.attentions = nn.ModuleList([SpatialTransformer(cout, **attn) for _ in range(nres)])
+        # construction order = the reference's (a resnet, then its attention: :790-810, :893-926), so a seeded default
+        # initialisation draws the same numbers; registration order: `attentions` before `resnets` (:812-813, :929-930)
+        resnets, attentions = [], []
+        for i in range(nres):
+            resnets.append(ResnetBlock(cin if i == 0 else cout, cout, norm_num_groups=groups, norm_eps=eps))
+            if attn is not None:
+                attentions.append(_attention_module(cout, attn))
+        if attn is not None:
+            self.attentions = nn.ModuleList(attentions)
         self.resnets = nn.ModuleList(resnets)
         self.downsampler = None
         if add_downsample:        # atten_unet_model.py:712-730: a down-sampling ResnetBlock, or Downsample(use_conv=True)
@@ -151,21 +179,25 @@ class _MidBlock(_Container):
     def __init__(self, c, groups, eps, attn: dict):
         super().__init__()
         self.resnet_1 = ResnetBlock(c, c, norm_num_groups=groups, norm_eps=eps)
-        self.attention = SpatialTransformer(c, **attn)
+        self.attention = _attention_module(c, attn)
         self.resnet_2 = ResnetBlock(c, c, norm_num_groups=groups, norm_eps=eps)
 
 
 class _UpBlock(_Container):
     def __init__(self, cin, prev, cout, nres, groups, eps, add_upsample, attn: Optional[dict], resblock_updown: bool = True):
         super().__init__()
-        resnets = []
+        resnets, attentions = [], []
         for i in range(nres):
             skip_c = cin if i == nres - 1 else cout
             in_c = prev if i == 0 else cout
             resnets.append(ResnetBlock(in_c + skip_c, cout, norm_num_groups=groups, norm_eps=eps))
-        if attn is not None:
-            self.attentions = nn.ModuleList([SpatialTransformer(cout, **attn) for _ in range(nres)])
+            if attn is not None:
+                attentions.append(_attention_module(cout, attn))
+        if attn is not None and not attn.get("block"):    # CrossAttnUpBlock: attentions first (:1371-1372)
+            self.attentions = nn.ModuleList(attentions)
         self.resnets = nn.ModuleList(resnets)
+        if attn is not None and attn.get("block"):        # AttnUpBlock: resnets first (:1253-1254)
+            self.attentions = nn.ModuleList(attentions)
         self.upsampler = None
         if add_upsample:          # atten_unet_model.py:1148-1165
             self.upsampler = (ResnetBlock(cout, cout, up=True, norm_num_groups=groups, norm_eps=eps)
@@ -210,10 +242,8 @@ class AttenUNet(nn.Module):
                              "as `num_channels`.")
         if spatial_dims != 3 or in_channels != 1 or out_channels != 1:
             raise NotImplementedError("petsyn AttenUNet implements the reference use: 3-D, one channel in, one out")
-        if not with_conditioning or transformer_num_layers != 1 or num_class_embeds is not None or dropout_cattn != 0.0:
-            raise NotImplementedError("petsyn AttenUNet implements with_conditioning=True (cross-attention transformer blocks; "
-                                      "the unconditioned AttentionBlock family is not built), transformer_num_layers=1, no class "
-                                      "embeddings / dropout")
+        if transformer_num_layers != 1 or num_class_embeds is not None or dropout_cattn != 0.0:
+            raise NotImplementedError("petsyn AttenUNet implements transformer_num_layers=1, no class embeddings / dropout")
         for lvl, a in enumerate(list(attention_levels) + [True]):          # the middle block always attends
             hc = num_head_channels[min(lvl, n - 1)]
             if a and hc not in (8, 16, 32):
@@ -233,6 +263,8 @@ class AttenUNet(nn.Module):
         def attn_kw(lvl):
             if not attention_levels[lvl]:
                 return None
+            if not with_conditioning:                     # Attn{Down,Mid,Up}Block: AttentionBlock, no context
+                return dict(block=True, head_channels=num_head_channels[lvl], norm_num_groups=g, norm_eps=e)
             return dict(heads=ch[lvl] // num_head_channels[lvl], head_channels=num_head_channels[lvl],
                         num_layers=transformer_num_layers, norm_num_groups=g, norm_eps=e,
                         cross_attention_dim=cross_attention_dim)
@@ -243,9 +275,12 @@ class AttenUNet(nn.Module):
         for i in range(n):
             in_c, out_c = out_c, ch[i]
             self.down_blocks.append(_DownBlock(in_c, out_c, num_res_blocks[i], g, e, i != n - 1, attn_kw(i), resblock_updown))
-        mid_attn = dict(heads=ch[-1] // num_head_channels[-1], head_channels=num_head_channels[-1],
-                        num_layers=transformer_num_layers, norm_num_groups=g, norm_eps=e,
-                        cross_attention_dim=cross_attention_dim)
+        if with_conditioning:
+            mid_attn = dict(heads=ch[-1] // num_head_channels[-1], head_channels=num_head_channels[-1],
+                            num_layers=transformer_num_layers, norm_num_groups=g, norm_eps=e,
+                            cross_attention_dim=cross_attention_dim)
+        else:
+            mid_attn = dict(block=True, head_channels=num_head_channels[-1], norm_num_groups=g, norm_eps=e)
         self.middle_block = _MidBlock(ch[-1], g, e, mid_attn)
         self.up_blocks = nn.ModuleList([])
         rch = list(reversed(ch))
@@ -273,17 +308,22 @@ class AttenUNet(nn.Module):
         if class_labels is not None or down_block_additional_residuals is not None \
                 or mid_block_additional_residual is not None:
             raise NotImplementedError("class labels / additional residuals are not used by the reference scripts")
-        if context is None:
+        if context is not None and self.with_conditioning is False:       # atten_unet_model.py:1822-1823
+            raise ValueError("model should have with_conditioning = True if context is provided")
+        if context is None and self.with_conditioning:
             raise ValueError("AttenUNet(with_conditioning=True) needs the covariate context tensor")
         if not x.is_cuda:
             raise RuntimeError("petsyn AttenUNet runs on CUDA (sm_100a) only; there is no CPU path")
         if x.dim() != 5 or x.shape[1] != 1:
             raise ValueError(f"expected x of shape [N, 1, D, H, W], got {tuple(x.shape)}")
         x = x.contiguous().float()
-        ctx = context.reshape(x.shape[0], -1).contiguous().float()        # [N, 1, C] or [N, C] (:110-112) -> [N, C]
-        if ctx.shape[1] != self.cfg["cross_attention_dim"]:
-            raise ValueError(f"context has {ctx.shape[1]} covariates, expected {self.cfg['cross_attention_dim']} "
-                             "(context length must be 1)")
+        if self.with_conditioning:
+            ctx = context.reshape(x.shape[0], -1).contiguous().float()    # [N, 1, C] or [N, C] (:110-112) -> [N, C]
+            if ctx.shape[1] != self.cfg["cross_attention_dim"]:
+                raise ValueError(f"context has {ctx.shape[1]} covariates, expected {self.cfg['cross_attention_dim']} "
+                                 "(context length must be 1)")
+        else:
+            ctx = x.new_zeros(x.shape[0], 1)                              # placeholder: no op of the tape reads it
         eng = self.engine_for(x)
         if torch.is_grad_enabled() and any(p.requires_grad for p in eng.params):
             return _AttenFn.apply(eng, x, ctx, *eng.params)
@@ -509,8 +549,34 @@ class _AttenEngine(_EngineBase):
     def _linear(self, x: Sl, lin: nn.Linear, name: str, out: Optional[Sl] = None, **kw) -> ConvOp:
         return self._conv(x, lin, ksize=1, stride=1, pad=0, name=name, out=out, **kw)
 
-    def _transformer(self, st: SpatialTransformer, x: Sl, lvl: int, dst: Optional[Sl], name: str) -> Sl:
+    def _attention_block(self, ab: AttentionBlock, x: Sl, dst: Optional[Sl], name: str) -> Sl:
+        """AttentionBlock.forward (atten_unet_model.py:421-461): out = attention(to_q/k/v(GroupNorm(x))) + x."""
+        t, dev, n = self.tape, self.dev, self.n
+        c, xb = x.c, x.buf
+        L = xb.d * xb.h * xb.w
+        heads = ab.num_heads
+        hd = c // heads
+        if hd != 32:
+            raise NotImplementedError("AttentionBlock heads must be 32 channels wide, the attention kernel's head size (there is "
+                                      "no output projection that could absorb zero-padded heads; num_head_channels=None means "
+                                      f"one head of {c} channels)")
+        T = lambda ch_, nm: Buf(n, xb.d, xb.h, xb.w, ch_, dev, f"{name}.{nm}")
+        g = T(c, "gn")
+        self._gn_act(x, ab.norm, ops.ACT_NONE, g)
+        qkv = T(3 * c, "qkv")
+        for idx, lin in enumerate((ab.to_q, ab.to_k, ab.to_v)):
+            self._linear(g.sl(), lin, f"{name}.qkv{idx}", out=qkv.sl(idx * c, c))
+        o = T(c, "o")
+        t.add(AttentionOp(qkv, o, heads, L))
+        out = dst if dst is not None else T(c, "out").sl()
+        t.add(NormActOp(o, "none", ops.ACT_NONE, [out], res=x))
+        self._zero_params += [ab.proj_attn.weight, ab.proj_attn.bias]       # constructed, never applied (:383, :421-461)
+        return out
+
+    def _transformer(self, st, x: Sl, lvl: int, dst: Optional[Sl], name: str) -> Sl:
         """SpatialTransformer.forward (atten_unet_model.py:315-343) with one BasicTransformerBlock (:225-235)."""
+        if isinstance(st, AttentionBlock):
+            return self._attention_block(st, x, dst, name)
         t, dev, n = self.tape, self.dev, self.n
         c = x.c
         xb = x.buf

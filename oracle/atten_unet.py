@@ -30,6 +30,13 @@ TRAINING_JSON = dict(  # unet/config/training.json:8-38 (atten_unet_def) + cross
     use_flash_attention=False, cross_attention_dim=5)
 
 
+# with_conditioning = False: the Attn{Down,Mid,Up}Block family (:751-852, :970-1029, :1190-1293) -- AttentionBlock (:346-461) instead
+# of the SpatialTransformer, no context
+ATTN_ONLY_CFG = dict(spatial_dims=3, in_channels=1, out_channels=1, num_res_blocks=1, num_channels=(32, 32, 64),
+                     attention_levels=(False, True, True), norm_num_groups=16, norm_eps=1e-6, resblock_updown=True,
+                     num_head_channels=32, with_conditioning=False, cross_attention_dim=None)
+
+
 def randomize_(named_tensors, seed: int = 0) -> None:
     """Deterministic, construction-order-independent re-draw of every parameter (by NAME), so that the reference, the
     oracle and the CUDA modules can be given identical weights -- and so that the reference's ``zero_module`` tensors
@@ -90,6 +97,25 @@ def cross_attention(sd, pre, x, ctx, heads):
     return F.linear(o, sd[pre + "to_out.0.weight"], sd[pre + "to_out.0.bias"])
 
 
+def attention_block(sd, pre, x, groups, eps, heads):
+    """AttentionBlock.forward (:421-461): GroupNorm -> to_q / to_k / to_v (with bias) -> multi-head attention -> + x.
+    ``proj_attn`` is constructed (:383) but never applied by the reference's forward: its parameters get no gradient."""
+    n, c, d, h, w = x.shape
+    t = _gn(sd, pre + "norm.", x, groups, eps).view(n, c, d * h * w).transpose(1, 2)
+    q, k, v = (F.linear(t, sd[pre + nm + ".weight"], sd[pre + nm + ".bias"]) for nm in ("to_q", "to_k", "to_v"))
+
+    def split(u):
+        b, l, dim = u.shape
+        return u.reshape(b, l, heads, dim // heads).permute(0, 2, 1, 3).reshape(b * heads, l, dim // heads)
+
+    q, k, v = split(q), split(k), split(v)
+    scale = 1.0 / ((c / heads) ** 0.5)
+    o = torch.bmm((torch.bmm(q, k.transpose(1, 2)) * scale).softmax(-1), v)
+    bh, l, dh = o.shape
+    o = o.reshape(bh // heads, heads, l, dh).permute(0, 2, 1, 3).reshape(bh // heads, l, dh * heads)
+    return o.transpose(-1, -2).reshape(n, c, d, h, w) + x
+
+
 def transformer(sd, pre, x, ctx, groups, eps, heads):
     """SpatialTransformer.forward (:315-343) with one BasicTransformerBlock (:225-235)."""
     n, c, d, h, w = x.shape
@@ -117,10 +143,15 @@ def forward(x: torch.Tensor, context: torch.Tensor, sd: Dict[str, torch.Tensor],
     hc = [hc] * len(ch) if isinstance(hc, int) else list(hc)
     groups, eps = cfg["norm_num_groups"], cfg.get("norm_eps", 1e-6)
     updown = cfg.get("resblock_updown", False)
-    assert cfg["with_conditioning"]
-    if context.dim() < 3:
+    cond = cfg["with_conditioning"]
+    if cond and context.dim() < 3:
         context = context.unsqueeze(1)                                            # :110-112
+    assert cond or context is None                                                # :1822-1823
     heads = lambda lvl: ch[lvl] // hc[lvl]
+    if not cond:                                                                  # AttentionBlock instead of SpatialTransformer
+        transformer = lambda sd_, pre, x_, ctx_, g_, e_, nh: attention_block(sd_, pre, x_, g_, e_, nh)   # noqa: F811
+    else:
+        transformer = globals()["transformer"]
     h = _conv(sd, "conv_in.", x, 1)
     skips: List[torch.Tensor] = [h]
     for i in range(len(ch)):
@@ -204,6 +235,12 @@ def param_shapes(cfg=TRAINING_JSON) -> Dict[str, tuple]:
             norm(b + nm, c)
         conv(pre + "proj_out.", c, c, 1)
 
+    if not cfg["with_conditioning"]:
+        def transformer(pre, c):                          # AttentionBlock (:377-383)  # noqa: F811
+            norm(pre + "norm.", c)
+            for nm in ("to_q.", "to_k.", "to_v.", "proj_attn."):
+                out[pre + nm + "weight"], out[pre + nm + "bias"] = (c, c), (c,)
+
     conv("conv_in.", 1, ch[0], 3)
     oc = ch[0]
     for i in range(n):
@@ -230,13 +267,16 @@ def param_shapes(cfg=TRAINING_JSON) -> Dict[str, tuple]:
         lvl = n - 1 - i
         pre = f"up_blocks.{i}."
         nr = nres[lvl] + 1
-        if att[lvl]:
+        if att[lvl] and cfg["with_conditioning"]:         # CrossAttnUpBlock: attentions first (:1371-1372)
             for j in range(nr):
                 transformer(pre + f"attentions.{j}.", oc)
         for j in range(nr):
             skip_c = ic if j == nr - 1 else oc
             in_c = prev if j == 0 else oc
             resnet(pre + f"resnets.{j}.", in_c + skip_c, oc)
+        if att[lvl] and not cfg["with_conditioning"]:     # AttnUpBlock: resnets first (:1253-1254)
+            for j in range(nr):
+                transformer(pre + f"attentions.{j}.", oc)
         if i != n - 1:
             if updown:
                 resnet(pre + "upsampler.", oc, oc)

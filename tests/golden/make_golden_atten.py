@@ -42,16 +42,20 @@ def main():
              ("atten_unet_2x96x128x96", (2, 96, 128, 96), 777, 3, cfg),
              # the reference's own smoke configuration (atten_unet_model.py:2034-2051: conv-form resampling, 8-channel heads,
              # 2-D context) on a volume whose coarsest grid is odd (11 x 16 x 11)
-             ("atten_unet_smoke_1x44x64x44", (1, 44, 64, 44), 777, 2, OA.SMOKE_CFG))
+             ("atten_unet_smoke_1x44x64x44", (1, 44, 64, 44), 777, 2, OA.SMOKE_CFG),
+             # with_conditioning=False: Attn{Down,Mid,Up}Block / AttentionBlock instead of the SpatialTransformer, no context
+             ("atten_unet_attnonly_1x32x48x32", (1, 32, 48, 32), 777, 1, OA.ATTN_ONLY_CFG))
     only = sys.argv[1:]
     for name, shape, seed, stride, case_cfg in cases:
         if only and name not in only:
             continue
         model = AttenUNet(**case_cfg).train()
         OA.randomize_(model.named_parameters(), seed=seed)
-        x, ctx, tgt = synth(shape, seed, case_cfg["cross_attention_dim"])
+        x, ctx, tgt = synth(shape, seed, case_cfg["cross_attention_dim"] or 1)
         if case_cfg is OA.SMOKE_CFG:
             ctx = ctx[:, 0]                       # [N, C]: the x.dim() < 3 -> unsqueeze branch (:110-112)
+        if not case_cfg["with_conditioning"]:
+            ctx = None
         y = model(x, ctx)
         loss = torch.nn.L1Loss()(y, tgt)
         loss.backward()

@@ -274,6 +274,53 @@ def test_reference_smoke_config_matches_golden(petsyn):
     assert img2.shape == img.shape and torch.isfinite(img2).all() and all(torch.isfinite(p).all() for p in m.parameters())
 
 
+def test_attention_block_family_matches_golden(petsyn):
+    """``with_conditioning=False``: Attn{Down,Mid,Up}Block with ``AttentionBlock`` (atten_unet_model.py:346-461, 751-852, 970-1029,
+    1190-1293) and no context -- against the fixture generated from the reference class.  ``proj_attn`` is constructed but never
+    applied by the reference's forward: same state-dict keys, exactly zero gradients."""
+    gold = np.load(os.path.join(GOLD, "atten_unet_attnonly_1x32x48x32.npz"))
+    shape, seed = tuple(int(v) for v in gold["shape"]), int(gold["seed"])
+    cfg = OA.ATTN_ONLY_CFG
+    model = petsyn.AttenUNet(**cfg).train()
+    assert list(model.state_dict()) == list(OA.param_shapes(cfg))
+    OA.randomize_(model.named_parameters(), seed=seed)
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    g = torch.Generator().manual_seed(seed)
+    n, d, h, w = shape
+    x, _, tgt = torch.rand(n, 1, d, h, w, generator=g), torch.rand(n, 1, 1, generator=g), torch.rand(n, 1, d, h, w, generator=g)
+    y_gold = torch.from_numpy(gold["output"])
+    pp = {k: v.detach().clone().cuda().requires_grad_(True) for k, v in sd.items()}
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        y_p = OA.forward(x.cuda(), None, pp, cfg)
+    (y_p.float() - tgt.cuda()).abs().mean().backward()
+    peer_err = (y_p.detach().float().cpu() - y_gold).abs()
+    model = model.cuda()
+    with pytest.raises(ValueError):                                    # :1822-1823
+        model(x.cuda(), torch.rand(n, 1, 5, device="cuda"))
+    y = model(x.cuda())
+    loss = torch.nn.functional.l1_loss(y, tgt.cuda())
+    loss.backward()
+    torch.cuda.synchronize()
+    err = (y.detach().cpu() - y_gold).abs()
+    print("attention-block family: out err ours max/mean", err.max().item(), err.mean().item(), "peer", peer_err.max().item(),
+          peer_err.mean().item(), "loss", loss.item(), float(gold["loss"]))
+    assert err.max().item() <= 2.0 * peer_err.max().item() + 5e-3
+    assert err.mean().item() <= 2.0 * peer_err.mean().item() + 5e-4
+    assert abs(loss.item() - float(gold["loss"])) <= 2e-3
+    gtot = float(gold["grad_norm_total"])
+    tot = tot_p = 0.0
+    for k, p in model.named_parameters():
+        gn, ref = p.grad.double().norm().item(), float(gold["gradnorm/" + k])
+        pn = 0.0 if pp[k].grad is None else pp[k].grad.double().norm().item()
+        tot += gn * gn
+        tot_p += pn * pn
+        if ".proj_attn." in k:
+            assert gn == 0.0 and ref == 0.0, k
+        elif ref > 2e-2 * gtot:
+            assert abs(gn - ref) / ref <= max(2.0 * abs(pn - ref) / ref, 0.05), (k, gn, ref, pn)
+    assert abs(tot ** 0.5 - gtot) <= max(2.0 * abs(tot_p ** 0.5 - gtot), 2e-2 * gtot), (tot ** 0.5, gtot, tot_p ** 0.5)
+
+
 def test_contracts(petsyn):
     cfg = dict(OA.TRAINING_JSON)
     with pytest.raises(ValueError):

@@ -99,7 +99,8 @@ def _atten_inputs(shape, seed, cdim):
     return (torch.rand(n, 1, d, h, w, generator=g), torch.rand(n, 1, cdim, generator=g), torch.rand(n, 1, d, h, w, generator=g))
 
 
-@pytest.mark.parametrize("name,cfg_name", [("atten_unet_2x32x48x32", "TRAINING_JSON"), ("atten_unet_smoke_1x44x64x44", "SMOKE_CFG")])
+@pytest.mark.parametrize("name,cfg_name", [("atten_unet_2x32x48x32", "TRAINING_JSON"), ("atten_unet_smoke_1x44x64x44", "SMOKE_CFG"),
+                                           ("atten_unet_attnonly_1x32x48x32", "ATTN_ONLY_CFG")])
 def test_atten_unet_oracle_matches_golden(name, cfg_name):
     from oracle import atten_unet as OA
     cfg = getattr(OA, cfg_name)
@@ -110,9 +111,11 @@ def test_atten_unet_oracle_matches_golden(name, cfg_name):
     for k, v in sd.items():
         ref = float(gold["wsum/" + k])
         assert abs(float(v.double().abs().sum()) - ref) <= 1e-6 * max(1.0, ref), k
-    x, ctx, tgt = _atten_inputs(shape, seed, cfg["cross_attention_dim"])
+    x, ctx, tgt = _atten_inputs(shape, seed, cfg["cross_attention_dim"] or 1)
     if cfg_name == "SMOKE_CFG":
         ctx = ctx[:, 0]                                            # 2-D context (atten_unet_model.py:110-112)
+    if not cfg["with_conditioning"]:
+        ctx = None                                                 # AttentionBlock family: no context (:1822-1823)
     loss, y, grads = OA.train_step(x, ctx, tgt, sd, cfg)
     assert abs(float(loss) - float(gold["loss"])) < 1e-6
     assert np.abs(y.numpy()[:, :, ::st, ::st, ::st] - gold["output"]).max() < 1e-5
@@ -160,7 +163,7 @@ def test_bmgan_oracle_matches_golden():
 
 @pytest.mark.reference
 @pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "unet", "utils")), reason="reference checkout not mounted")
-@pytest.mark.parametrize("cfg_name", ["TRAINING_JSON", "SMOKE_CFG"])
+@pytest.mark.parametrize("cfg_name", ["TRAINING_JSON", "SMOKE_CFG", "ATTN_ONLY_CFG"])
 def test_atten_unet_oracle_matches_live_reference(cfg_name):
     from oracle import atten_unet as OA
     from oracle import monai_stub
@@ -172,7 +175,10 @@ def test_atten_unet_oracle_matches_live_reference(cfg_name):
     model = AttenUNet(**cfg).train()
     OA.randomize_(model.named_parameters(), seed=3)
     assert {k: tuple(v.shape) for k, v in model.state_dict().items()} == OA.param_shapes(cfg)
-    x, ctx, tgt = _atten_inputs((1, 16, 32, 24), 4, cfg["cross_attention_dim"])
+    assert list(model.state_dict()) == list(OA.param_shapes(cfg))                 # registration order too
+    x, ctx, tgt = _atten_inputs((1, 16, 32, 24), 4, cfg["cross_attention_dim"] or 1)
+    if not cfg["with_conditioning"]:
+        ctx = None
     y = model(x, ctx)
     loss = (y - tgt).abs().mean()
     loss.backward()
