@@ -214,6 +214,12 @@ def run_petsyn(args, ngf, shape, batch):
     # ---- warm-up (eager), CUDA-graph capture of the step, warm-up (replay) ----
     for i in range(2):
         trainer.step(*resident[i % pool])
+    if args.profile_one_step:              # `ncu --profile-from-start off`: exactly one (eager) step is profiled
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        trainer.step(*resident[0])
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
     if not args.no_graph:
         trainer.capture()
     for i in range(max(args.warmup, 3)):
