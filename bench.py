@@ -396,7 +396,8 @@ def run_petsyn_bmgan(args, cfg_name, shape, batch):
     host = [bmgan_batch(shape, 777 + 1000 * rank + i, batch) for i in range(pool)]
     pinned = [tuple(t.pin_memory() for t in b) for b in host]
     resident = [tuple(t.to(dev) for t in b) for b in host]
-    trainer = BmganTrainer(gen, disc, lr=2e-4, example_input=resident[0][0], enc=enc)
+    comm_dtype = torch.bfloat16 if os.environ.get("PETSYN_BF16_GRAD_COMM") else torch.float32
+    trainer = BmganTrainer(gen, disc, lr=2e-4, example_input=resident[0][0], enc=enc, grad_comm_dtype=comm_dtype)
 
     def barrier():
         if world > 1:
@@ -788,7 +789,19 @@ def extra_workloads(args, rank, world, dev):
                            "n_gpus": world, "steps": steps, "ms_per_step": ms, "per_gpu_batch": 1, "global_batch": world,
                            "scaling": "weak", "cuda_graph": "segments" if world > 1 else True, "replicas_in_sync": sync,
                            "grad_bytes_allreduced_per_step": 4 * (trainer.garena.numel + trainer.earena.numel),
-                           "algorithmic_tflops_per_gpu": flops / (ms * 1e-3) / 1e12}
+                           "algorithmic_tflops_per_gpu": flops / (ms * 1e-3) / 1e12,
+                           "grad_allreduce_dtype": "fp32 (the reference's DistributedDataParallel)"}
+        if world > 1:
+            # the same step with the gradient buckets averaged in bf16 (GradBucketer(comm_dtype=torch.bfloat16): half the NVLink
+            # bytes, NOT the reference's arithmetic -- reported beside the fp32 number, never instead of it)
+            b = trainer.bucketer
+            b.comm_buf = torch.empty(b.arena.g.numel(), dtype=torch.bfloat16, device=dev)
+            for i in range(2):
+                trainer.step(*batches[i % 3])
+            ms16 = timed(lambda i: trainer.step(*batches[i % 3]), steps)
+            out["bmgan_dp"]["bf16_grad_allreduce"] = {
+                "ms_per_step": ms16, "value": world * 1 / (ms16 * 1e-3), "unit": UNIT,
+                "replicas_in_sync": replicas_in_sync([trainer.garena.p], world, dev)}
     else:
         out["bmgan_dp"] = {"error": err or "another rank failed to build the workload"}
     del trainer

@@ -49,9 +49,14 @@ class GradBucketer:
     """Bucketed gradient all-reduce over a FlatArena, launched as buckets complete (device-agnostic: NCCL on CUDA
     with a side stream, gloo on CPU for the host-logic tests)."""
 
-    def __init__(self, arena: FlatArena, bucket_mb: float = 32.0, process_group=None):
+    def __init__(self, arena: FlatArena, bucket_mb: float = 32.0, process_group=None, comm_dtype=torch.float32):
+        """``comm_dtype``: torch.float32 -- the reference's DistributedDataParallel (fp32 all-reduce of fp32 gradients) -- or
+        torch.bfloat16: every bucket is cast to bf16 on the communication stream, averaged, and cast back into the fp32 arena
+        (half the NVLink bytes; the average of bf16-rounded gradients instead of the fp32 average: an explicit opt-in)."""
         self.arena = arena
         self.pg = process_group
+        self.comm_dtype = comm_dtype
+        self.comm_buf = None
         self.world = dist.get_world_size(process_group) if (dist.is_available() and dist.is_initialized()) else 1
         self.buckets: List[tuple] = []          # (start, end, id(last param))
         limit = max(1, int(bucket_mb * (1 << 20) / 4))
@@ -65,6 +70,8 @@ class GradBucketer:
         self._bucket_of_last = {b[2]: i for i, b in enumerate(self.buckets)}
         self.cuda = arena.g.is_cuda
         self.comm_stream = torch.cuda.Stream(device=arena.g.device) if (self.cuda and self.world > 1) else None
+        if comm_dtype != torch.float32 and self.cuda and self.world > 1:
+            self.comm_buf = torch.empty(arena.g.numel(), dtype=comm_dtype, device=arena.g.device)
         self._pending: List = []
         self._avg = self.cuda          # NCCL supports ReduceOp.AVG; gloo does not
 
@@ -83,13 +90,26 @@ class GradBucketer:
             ev.record()                                # compute stream: bucket i is complete after this point
             self.comm_stream.wait_event(ev)
             with torch.cuda.stream(self.comm_stream):
+                if self.comm_buf is not None:
+                    cb = self.comm_buf[start:end]
+                    cb.copy_(view)                     # fp32 -> bf16 on the communication stream
+                    work = dist.all_reduce(cb, op=op, group=self.pg, async_op=True)
+                    work.wait()                        # the communication stream waits for the collective ...
+                    view.copy_(cb)                     # ... and casts the average back into the fp32 gradient arena
+                    done = torch.cuda.Event()
+                    done.record(self.comm_stream)
+                    self._pending.append((None, view, done))
+                    return
                 work = dist.all_reduce(view, op=op, group=self.pg, async_op=True)
         else:
             work = dist.all_reduce(view, op=op, group=self.pg, async_op=True)
-        self._pending.append((work, view))
+        self._pending.append((work, view, None))
 
     def wait_all(self) -> None:
-        for work, view in self._pending:
+        for work, view, done in self._pending:
+            if done is not None:
+                torch.cuda.current_stream().wait_event(done)
+                continue
             work.wait()                                # CUDA: the current stream waits for the collective
             if not self._avg:
                 view.div_(self.world)
@@ -387,7 +407,7 @@ class BmganTrainer:
 
     def __init__(self, gen, disc, lr: float = 2e-4, betas=(0.9, 0.999), eps: float = 1e-8, lamda_l1: float = 20.0,
                  bucket_mb: float = 64.0, process_group=None, example_input: Optional[torch.Tensor] = None,
-                 step_discriminator: bool = False, enc=None):
+                 step_discriminator: bool = False, enc=None, grad_comm_dtype=torch.float32):
         if example_input is None:
             raise ValueError("example_input (a tensor of the training shape) is required to lay out the arenas")
         self.gen, self.disc = gen, disc
@@ -416,7 +436,7 @@ class BmganTrainer:
         self.loss_adv, self.loss_l1, self.loss_d_fake, self.loss_d_real = f(), f(), f(), f()
         self.dy = torch.zeros(example_input.shape, dtype=torch.float32, device=dev)
         self.dlogits = torch.zeros_like(self.deng.logits)
-        self.bucketer = GradBucketer(self.garena, bucket_mb, process_group)
+        self.bucketer = GradBucketer(self.garena, bucket_mb, process_group, comm_dtype=grad_comm_dtype)
         self.graph = None
         self._cap: Optional[GraphSegments] = None      # set while capture() records the step
         self.static = None
