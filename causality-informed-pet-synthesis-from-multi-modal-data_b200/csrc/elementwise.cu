@@ -6,6 +6,8 @@
 
 #include <algorithm>
 
+#include <cstdlib>
+
 #include "common.h"
 #include "det_reduce.cuh"
 
@@ -432,7 +434,12 @@ __global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g,
 
 static int row_blocks(int64_t rows, int C) {
   const int rpp = 256 / (C / 8);
-  return (int)std::max<int64_t>(1, std::min<int64_t>((rows + rpp - 1) / rpp, 148 * 8));
+  static int waves = 0;                       // persistent CTAs per SM (PETSYN_BN_WAVES: tuning experiments)
+  if (waves == 0) {
+    const char* e = getenv("PETSYN_BN_WAVES");
+    waves = e != nullptr ? std::max(1, atoi(e)) : 2;        // measured on configs[0]: 8 -> 2.69 ms per step, 4 -> 2.63, 2 -> 2.60, 1 -> 2.83
+  }
+  return (int)std::max<int64_t>(1, std::min<int64_t>((rows + rpp - 1) / rpp, 148 * waves));
 }
 
 }  // namespace petsyn
