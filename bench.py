@@ -771,7 +771,8 @@ def extra_workloads(args, rank, world, dev):
         disc = petsyn.patch_discriminator().to(dev).train()
         enc = petsyn.ResNet_encoder().to(dev).train()
         batches = [tuple(t.to(dev) for t in bmgan_batch(shape, 777 + 1000 * rank + i, 1)) for i in range(3)]
-        trainer = BmganTrainer(gen, disc, lr=2e-4, example_input=batches[0][0], enc=enc)
+        trainer = BmganTrainer(gen, disc, lr=2e-4, example_input=batches[0][0], enc=enc,
+                               bucket_mb=float(os.environ.get("PETSYN_BMGAN_BUCKET_MB", "256")))   # 4 graph segments
     except Exception as e:  # pragma: no cover
         err = f"{type(e).__name__}: {e}"
     if agreed(err is None):

@@ -406,7 +406,7 @@ class BmganTrainer:
     """
 
     def __init__(self, gen, disc, lr: float = 2e-4, betas=(0.9, 0.999), eps: float = 1e-8, lamda_l1: float = 20.0,
-                 bucket_mb: float = 64.0, process_group=None, example_input: Optional[torch.Tensor] = None,
+                 bucket_mb: float = 256.0, process_group=None, example_input: Optional[torch.Tensor] = None,
                  step_discriminator: bool = False, enc=None, grad_comm_dtype=torch.float32):
         if example_input is None:
             raise ValueError("example_input (a tensor of the training shape) is required to lay out the arenas")
