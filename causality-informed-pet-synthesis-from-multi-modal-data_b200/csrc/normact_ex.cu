@@ -378,14 +378,20 @@ __global__ void __launch_bounds__(256, 3) fwd_kernel(const Dev d) {
       PfRing::wait();
       const int64_t r = base + q;
       const F8 x = unpack8(pf.get(k % kPf, 0));
-      F8 rs = splat(0.f);
-      if (has_res) rs = unpack8(pf.get(k % kPf, 1));
       F8 o1, o2;
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const float b = x.v[i] * sc.v[i] + sh.v[i];
-        o1.v[i] = act_fwd(b, a1, slope) + rs.v[i];
-        o2.v[i] = (ACT >= 0) ? o1.v[i] : act_fwd(b, a2, slope) + rs.v[i];
+        o1.v[i] = act_fwd(b, a1, slope);
+        o2.v[i] = (ACT >= 0) ? o1.v[i] : act_fwd(b, a2, slope);
+      }
+      if (has_res) {
+        const F8 rs = unpack8(pf.get(k % kPf, 1));
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          o1.v[i] += rs.v[i];
+          o2.v[i] += rs.v[i];
+        }
       }
       store8(d.t1 + r * d.cs1 + d.co1 + it.tx * 8, o1);
       if (d.t2) store8(d.t2 + r * d.cs2 + d.co2 + it.tx * 8, o2);
@@ -448,22 +454,30 @@ __global__ void __launch_bounds__(256, 2) bwd_reduce_kernel(const Dev d) {
     for (int64_t r = r0; r < d.rows; r += stride, ++k) {
       issue(k + kPf - 1);
       PfRing::wait();
-      const F8 x = unpack8(pf.get(k % kPf, 0)), av = unpack8(pf.get(k % kPf, 1));
+      const F8 x = unpack8(pf.get(k % kPf, 0));
+      F8 av = unpack8(pf.get(k % kPf, 1));
       F8 bv = splat(0.f);
-      if (has_t2) bv = unpack8(pf.get(k % kPf, 2));
+      if (has_t2) {
+        bv = unpack8(pf.get(k % kPf, 2));
+        if (ACT >= 0) {                    // one activation for both destinations: their gradients simply add
+#pragma unroll
+          for (int i = 0; i < 8; ++i) av.v[i] += bv.v[i];
+        }
+      }
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const float b = x.v[i] * sc.v[i] + sh.v[i];
         float g;
         if (ACT >= 0) {
-          g = (av.v[i] + bv.v[i]) * act_grad(b, a1, slope);
+          g = av.v[i] * act_grad(b, a1, slope);
         } else {
           g = av.v[i] * act_grad(b, a1, slope);
           if (has_t2) g += bv.v[i] * act_grad(b, a2, slope);
         }
         acc[0][i] += g;
         acc[1][i] += g * x.v[i];
-        if (d.dslope != nullptr && b < 0.f) dsl += (av.v[i] + bv.v[i]) * b;   // d PReLU / d slope = min(b, 0)
+        if (d.dslope != nullptr && b < 0.f)                                     // d PReLU / d slope = min(b, 0)
+          dsl += (ACT >= 0 ? av.v[i] : av.v[i] + bv.v[i]) * b;
       }
     }
     const F8 mu = load8f(d.mean + so + it.tx * 8), rs = load8f(d.rstd + so + it.tx * 8);
@@ -591,22 +605,30 @@ __global__ void __launch_bounds__(256, 2) bwd_apply_kernel(const Dev d) {
     issue(k + kPf - 1);
     PfRing::wait();
     const int64_t r = base + q;
-    const F8 x = unpack8(pf.get(k % kPf, 0)), av = unpack8(pf.get(k % kPf, 1));
+    const F8 x = unpack8(pf.get(k % kPf, 0));
+    F8 av = unpack8(pf.get(k % kPf, 1));
     F8 bv = splat(0.f);
-    if (has_t2) bv = unpack8(pf.get(k % kPf, 2));
+    if (has_t2) {
+      bv = unpack8(pf.get(k % kPf, 2));
+      if (ACT >= 0) {                      // one activation for both destinations: their gradients simply add
+#pragma unroll
+        for (int i = 0; i < 8; ++i) av.v[i] += bv.v[i];
+      }
+    }
     F8 o, dr;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const float b = x.v[i] * sc.v[i] + sh.v[i];
       float g;
       if (ACT >= 0) {
-        g = (av.v[i] + bv.v[i]) * act_grad(b, a1, slope);
+        g = av.v[i] * act_grad(b, a1, slope);
+        dr.v[i] = av.v[i];
       } else {
         g = av.v[i] * act_grad(b, a1, slope);
         if (has_t2) g += bv.v[i] * act_grad(b, a2, slope);
+        dr.v[i] = av.v[i] + bv.v[i];
       }
       o.v[i] = k0.v[i] * g - kA.v[i] - x.v[i] * kB.v[i];
-      dr.v[i] = av.v[i] + bv.v[i];
     }
     if (has_ex) {                       // d(out)/d(x) = identity of a skip connection: its gradient joins dz here
       const F8 e = unpack8(pf.get(k % kPf, nt_ring - 1));
@@ -619,8 +641,10 @@ __global__ void __launch_bounds__(256, 2) bwd_apply_kernel(const Dev d) {
 #pragma unroll
       for (int i = 0; i < 8; ++i) o.v[i] += old.v[i];
     }
+    if (d.dz_colsum != nullptr) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) csum[0][i] += o.v[i];     // column sums of the FINAL gradient (after extra / accumulation)
+      for (int i = 0; i < 8; ++i) csum[0][i] += o.v[i];   // column sums of the FINAL gradient (after extra / accumulation)
+    }
     store8(dzp, o);
     if (d.res) {
       __nv_bfloat16* p = d.res + r * d.csr + d.cor + it.tx * 8;
