@@ -188,9 +188,9 @@ def read_adam_state_dict(sd: dict, exp_avg: List[torch.Tensor], exp_avg_sq: List
 
 class _CheckpointMixin:
     """The reference's checkpoint dictionary (train_unet.py:85-109 resume, :297-302 save):
-    ``{'unet', 'discriminator', 'epoch', 'g_optimizer', 'eval_loss'}`` with ``state_dict()`` s as values, so a checkpoint
-    written here resumes in the reference script and vice versa (under DDP the keys carry a ``module.`` prefix there;
-    ``load_checkpoint`` strips it)."""
+    ``{'unet', 'discriminator', 'epoch', 'g_optimizer', 'eval_loss'}`` with ``state_dict()`` s as values.  Under DDP the
+    reference's keys carry a ``module.`` prefix: ``load_checkpoint`` accepts both forms, ``checkpoint(ddp_prefix=...)`` writes
+    either (default: prefixed when this trainer is data parallel), so checkpoints move in both directions."""
 
     def _moments(self):
         off = {id(p): o for p, o in zip(self.arena.params, self.arena.offsets)}
@@ -213,15 +213,26 @@ class _CheckpointMixin:
         self.step_dev.fill_(read_adam_state_dict(sd, m, v))
         self.lr, self.betas, self.eps = hyper
 
-    def checkpoint(self, epoch: int, eval_loss: float = float("nan"), discriminator=None, model_key: str = "unet") -> dict:
-        out = {model_key: self.model.state_dict(), "epoch": epoch, "g_optimizer": self.optimizer_state_dict(),
+    def checkpoint(self, epoch: int, eval_loss: float = float("nan"), discriminator=None, model_key: str = "unet",
+                   ddp_prefix: Optional[bool] = None) -> dict:
+        """``ddp_prefix``: write the state-dict keys as ``module.<key>`` -- what the reference saves and strictly re-loads when its
+        networks are wrapped in DistributedDataParallel (train_unet.py:72-74,85-88).  Default: on when this trainer runs data
+        parallel.  The reference's resume also indexes ``ckpt['discriminator']`` unconditionally: pass the discriminator
+        (this trainer's own when it was built with one) for a checkpoint the reference script can resume from."""
+        if ddp_prefix is None:
+            ddp_prefix = getattr(self, "world", 1) > 1
+        pre = (lambda sd: {"module." + k: v for k, v in sd.items()}) if ddp_prefix else (lambda sd: dict(sd))
+        out = {model_key: pre(self.model.state_dict()), "epoch": epoch, "g_optimizer": self.optimizer_state_dict(),
                "eval_loss": eval_loss}
+        if discriminator is None:
+            discriminator = getattr(self, "disc", None)
         if discriminator is not None:
-            out["discriminator"] = discriminator.state_dict()
+            out["discriminator"] = pre(discriminator.state_dict())
         return out
 
-    def save_checkpoint(self, path: str, epoch: int, eval_loss: float = float("nan"), discriminator=None) -> None:
-        torch.save(self.checkpoint(epoch, eval_loss, discriminator), path)
+    def save_checkpoint(self, path: str, epoch: int, eval_loss: float = float("nan"), discriminator=None,
+                        ddp_prefix: Optional[bool] = None) -> None:
+        torch.save(self.checkpoint(epoch, eval_loss, discriminator, ddp_prefix=ddp_prefix), path)
 
     def load_checkpoint(self, ckpt, discriminator=None, model_key: str = "unet") -> int:
         """``ckpt``: a path or an already loaded dictionary.  Returns the epoch to resume from (train_unet.py:89)."""

@@ -128,8 +128,10 @@ def test_checkpoint_round_trip_in_the_reference_format(petsyn):
     opt.load_state_dict(ck["g_optimizer"])
     assert opt.param_groups[0]["lr"] == lr and len(opt.state) == len(list(m1.parameters()))
     assert all(float(s["step"]) == 2.0 for s in opt.state.values())
-    # a DDP-saved checkpoint carries the 'module.' prefix
-    ck["unet"] = {"module." + k: v for k, v in ck["unet"].items()}
+    # a DDP-saved checkpoint carries the 'module.' prefix (train_unet.py:72-74): written on request, accepted on load
+    ck_ddp = t1.checkpoint(epoch=6, eval_loss=0.125, ddp_prefix=True)
+    assert list(ck_ddp["unet"]) == ["module." + k for k in m1.state_dict()]
+    ck["unet"] = ck_ddp["unet"]
     m2, t2 = fresh(2)
     assert t2.load_checkpoint(ck) == 7
     for (k, a), b in zip(m1.state_dict().items(), m2.state_dict().values()):
