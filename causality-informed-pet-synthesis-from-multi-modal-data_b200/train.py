@@ -221,6 +221,8 @@ class _CheckpointMixin:
         (this trainer's own when it was built with one) for a checkpoint the reference script can resume from."""
         if ddp_prefix is None:
             ddp_prefix = getattr(self, "world", 1) > 1
+        if hasattr(self, "sync_buffers"):
+            self.sync_buffers()                     # what is saved is what rank 0 holds (DDP's broadcast_buffers)
         pre = (lambda sd: {"module." + k: v for k, v in sd.items()}) if ddp_prefix else (lambda sd: dict(sd))
         out = {model_key: pre(self.model.state_dict()), "epoch": epoch, "g_optimizer": self.optimizer_state_dict(),
                "eval_loss": eval_loss}
@@ -288,12 +290,21 @@ class Unet3dTrainer(_CheckpointMixin):
         self.eng.mark_weights_dirty()
 
     def sync_buffers(self) -> None:
-        """DDP ``broadcast_buffers=True``: BatchNorm running statistics follow rank 0 (train_unet.py:72)."""
+        """DDP ``broadcast_buffers=True`` (train_unet.py:72): BatchNorm running statistics follow rank 0.  DDP re-broadcasts
+        them before every forward; in training mode nothing reads them, and rank 0's own copy evolves from rank 0's batches
+        alone either way, so broadcasting when they are about to be READ -- before evaluation, before a checkpoint
+        (``checkpoint()`` does it) -- leaves every rank with exactly the statistics DDP would have left there."""
         if self.world == 1:
             return
-        for b in self.model.buffers():
-            if b.dtype.is_floating_point:
-                dist.broadcast(b, src=0, group=self.pg)
+        bufs = [b for b in self.model.buffers() if b.dtype.is_floating_point]
+        if not bufs:
+            return
+        flat = torch.cat([b.reshape(-1) for b in bufs])            # one collective instead of one per buffer
+        dist.broadcast(flat, src=0, group=self.pg)
+        off = 0
+        for b in bufs:
+            b.copy_(flat[off:off + b.numel()].view_as(b))
+            off += b.numel()
 
     # ------------------------------------------------------------------------------------------------ step
     def _forward_and_loss(self, x: torch.Tensor, target: torch.Tensor, timers=None) -> None:
