@@ -221,8 +221,6 @@ class _CheckpointMixin:
         (this trainer's own when it was built with one) for a checkpoint the reference script can resume from."""
         if ddp_prefix is None:
             ddp_prefix = getattr(self, "world", 1) > 1
-        if hasattr(self, "sync_buffers"):
-            self.sync_buffers()                     # what is saved is what rank 0 holds (DDP's broadcast_buffers)
         pre = (lambda sd: {"module." + k: v for k, v in sd.items()}) if ddp_prefix else (lambda sd: dict(sd))
         out = {model_key: pre(self.model.state_dict()), "epoch": epoch, "g_optimizer": self.optimizer_state_dict(),
                "eval_loss": eval_loss}
@@ -292,8 +290,9 @@ class Unet3dTrainer(_CheckpointMixin):
     def sync_buffers(self) -> None:
         """DDP ``broadcast_buffers=True`` (train_unet.py:72): BatchNorm running statistics follow rank 0.  DDP re-broadcasts
         them before every forward; in training mode nothing reads them, and rank 0's own copy evolves from rank 0's batches
-        alone either way, so broadcasting when they are about to be READ -- before evaluation, before a checkpoint
-        (``checkpoint()`` does it) -- leaves every rank with exactly the statistics DDP would have left there."""
+        alone either way, so broadcasting when they are about to be READ -- before evaluation on every rank -- leaves every rank
+        with exactly the statistics DDP would have left there.  A collective: call it on ALL ranks (rank 0's own checkpoint,
+        written by rank 0 alone as in train_unet.py:296-302, already holds the authoritative statistics)."""
         if self.world == 1:
             return
         bufs = [b for b in self.model.buffers() if b.dtype.is_floating_point]
