@@ -172,13 +172,12 @@ __device__ __forceinline__ void pack_tile(const float* __restrict__ w, int A, in
   }
   for (int i = tid; i < TA * ROWP; i += 256) tile[i] = 0.f;
   __syncthreads();
-  for (int al = warp; al < TA; al += 8) {
+  // all 256 threads stream the tile: for every a the TB * K3 weights of b0 .. b0 + TB - 1 are one contiguous run
+  for (int e = tid; e < TA * TB * K3; e += 256) {
+    const int al = e / (TB * K3), idx = e - al * (TB * K3);
+    const int bl = idx / K3, k = idx - bl * K3;
     const int a = a0 + al;
-    const float* src = w + ((int64_t)a * B + b0) * K3;
-    for (int idx = lane; idx < TB * K3; idx += 32) {
-      const int bl = idx / K3, k = idx - bl * K3;
-      if (a < A && b0 + bl < B) tile[al * ROWP + bl * K3P + k] = __ldg(src + idx);
-    }
+    if (a < A && b0 + bl < B) tile[al * ROWP + bl * K3P + k] = __ldg(w + ((int64_t)a * B + b0) * K3 + idx);
   }
   __syncthreads();
   // thread <-> one (row, col) of the tile; col is the fast index (64 consecutive columns per row)
