@@ -13,6 +13,7 @@
 #include <cuda_bf16.h>
 
 #include <algorithm>
+#include <cstdlib>
 
 #include "common.h"
 
@@ -55,7 +56,7 @@ __device__ __forceinline__ uint32_t pack2(float lo, float hi) {
 
 // Stage a [64 rows x 32 dims] tile (rows r0 .. r0+63 of a [L, ld] matrix starting at `src`) into smem; rows >= L are zero.
 __device__ __forceinline__ void load_tile(__nv_bfloat16* dst, const __nv_bfloat16* src, int64_t ld, int r0, int L) {
-  for (int e = threadIdx.x; e < kT * 4; e += 128) {
+  for (int e = threadIdx.x & 127; e < kT * 4; e += 128) {
     const int r = e >> 2, c = e & 3;
     const bool ok = r0 + r < L;
     cp_async16(dst + r * kPitch + c * 8, src + (int64_t)(ok ? r0 + r : 0) * ld + c * 8, ok);
@@ -104,13 +105,25 @@ __device__ __forceinline__ void gemm_p_tile(float (&o)[4][4], const uint32_t (&p
   }
 }
 
+// A CTA is G independent groups of four warps that share the same 64 rows and split the streamed tiles between them
+// (group g takes tiles g, g + G, ...): with one group a CTA has four warps and an SM two CTAs' worth of work -- every
+// mma / exp2 / shuffle of the online softmax waits for the one before it; G groups put G times as many warps on the SM.
+// Each group has its own double-buffered tiles and its own named barrier; partial results are merged through shared memory.
+constexpr int kTileBytes = kT * kPitch * 2;                       // one staged [64 x 32] tile
+constexpr int kGroupBytes = 2 * 2 * kTileBytes + 2 * 2 * kT * 4;   // two buffers x two tiles (+ two buffers x two fp32 rows)
+__device__ __forceinline__ void group_sync(int grp) { asm volatile("bar.sync %0, 128;" ::"r"(grp + 1) : "memory"); }
+
 // ------------------------------------------------------------------------------------------------ forward
-__global__ void __launch_bounds__(128) attn_fwd_mma_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out,
+template <int G>
+__global__ void __launch_bounds__(128 * G) attn_fwd_mma_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out,
                                                            float* __restrict__ lse, int L, int H, float scale) {
   pdl_sync();
-  __shared__ __align__(16) __nv_bfloat16 sK[2][kT * kPitch], sV[2][kT * kPitch];
+  extern __shared__ __align__(16) uint8_t fa_smem[];
+  const int grp = threadIdx.x >> 7, ltid = threadIdx.x & 127;
+  __nv_bfloat16(*sK)[kT * kPitch] = reinterpret_cast<__nv_bfloat16(*)[kT * kPitch]>(fa_smem + grp * kGroupBytes);
+  __nv_bfloat16(*sV)[kT * kPitch] = sK + 2;
   const int n = blockIdx.z, h = blockIdx.y;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int warp = ltid >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const int64_t ld = 3 * H * kD;
   const __nv_bfloat16* q = qkv + (int64_t)n * L * ld + h * kD;
   const __nv_bfloat16* k = q + H * kD;
@@ -127,18 +140,20 @@ __global__ void __launch_bounds__(128) attn_fwd_mma_kernel(const __nv_bfloat16* 
     for (int j = 0; j < 4; ++j) o[i][j] = 0.f;
 
   const int ntiles = (L + kT - 1) / kT;
-  load_tile(sK[0], k, ld, 0, L);
-  load_tile(sV[0], v, ld, 0, L);
+  if (grp < ntiles) {
+    load_tile(sK[0], k, ld, grp * kT, L);
+    load_tile(sV[0], v, ld, grp * kT, L);
+  }
   cp_async_commit();
-  for (int it = 0; it < ntiles; ++it) {
-    const int buf = it & 1;
-    if (it + 1 < ntiles) {
-      load_tile(sK[buf ^ 1], k, ld, (it + 1) * kT, L);
-      load_tile(sV[buf ^ 1], v, ld, (it + 1) * kT, L);
+  for (int it = grp, li = 0; it < ntiles; it += G, ++li) {
+    const int buf = li & 1;
+    if (it + G < ntiles) {
+      load_tile(sK[buf ^ 1], k, ld, (it + G) * kT, L);
+      load_tile(sV[buf ^ 1], v, ld, (it + G) * kT, L);
     }
     cp_async_commit();
     cp_async_wait<1>();
-    __syncthreads();
+    group_sync(grp);
     float s[8][4];
 #pragma unroll
     for (int j = 0; j < 8; ++j)
@@ -184,12 +199,44 @@ __global__ void __launch_bounds__(128) attn_fwd_mma_kernel(const __nv_bfloat16* 
       pa[j >> 1][(j & 1) * 2 + 1] = pack2(p2, p3);
     }
     gemm_p_tile(o, pa, sV[buf]);
-    __syncthreads();
+    group_sync(grp);
   }
 #pragma unroll
   for (int r = 0; r < 2; ++r) {
     l[r] += __shfl_xor_sync(0xffffffffu, l[r], 1);
     l[r] += __shfl_xor_sync(0xffffffffu, l[r], 2);
+  }
+  if (G > 1) {
+    // merge the groups' online-softmax states (m, l, o) in group order: groups 1 .. G-1 leave theirs in their own tile
+    // buffers (laid out [value][thread]), group 0 rescales to the common maximum and adds
+    float* mine = reinterpret_cast<float*>(fa_smem + grp * kGroupBytes);
+    if (grp > 0) {
+      mine[0 * 128 + ltid] = m[0]; mine[1 * 128 + ltid] = m[1];
+      mine[2 * 128 + ltid] = l[0]; mine[3 * 128 + ltid] = l[1];
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) mine[(4 + nt * 4 + i) * 128 + ltid] = o[nt][i];
+    }
+    __syncthreads();
+    if (grp > 0) return;
+    for (int og = 1; og < G; ++og) {
+      const float* oth = reinterpret_cast<const float*>(fa_smem + og * kGroupBytes);
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const float m2 = oth[r * 128 + ltid], l2 = oth[(2 + r) * 128 + ltid];
+        const float mn = fmaxf(m[r], m2);
+        const float a1 = m[r] == -INFINITY ? 0.f : exp2f((m[r] - mn) * c);
+        const float a2 = m2 == -INFINITY ? 0.f : exp2f((m2 - mn) * c);
+        m[r] = mn;
+        l[r] = l[r] * a1 + l2 * a2;
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+          o[nt][r * 2] = o[nt][r * 2] * a1 + oth[(4 + nt * 4 + r * 2) * 128 + ltid] * a2;
+          o[nt][r * 2 + 1] = o[nt][r * 2 + 1] * a1 + oth[(4 + nt * 4 + r * 2 + 1) * 128 + ltid] * a2;
+        }
+      }
+    }
   }
 #pragma unroll
   for (int r = 0; r < 2; ++r) {
@@ -206,14 +253,18 @@ __global__ void __launch_bounds__(128) attn_fwd_mma_kernel(const __nv_bfloat16* 
 
 // ------------------------------------------------------------------------------------------------ backward: dQ
 // dS = P * (dP - delta), dP = dO V^T, dQ = scale * dS K
-__global__ void __launch_bounds__(128) attn_bwd_dq_mma_kernel(const __nv_bfloat16* __restrict__ qkv,
+template <int G>
+__global__ void __launch_bounds__(128 * G) attn_bwd_dq_mma_kernel(const __nv_bfloat16* __restrict__ qkv,
                                                               const __nv_bfloat16* __restrict__ dout,
                                                               const float* __restrict__ lse, const float* __restrict__ delta,
                                                               __nv_bfloat16* __restrict__ dqkv, int L, int H, float scale) {
   pdl_sync();
-  __shared__ __align__(16) __nv_bfloat16 sK[2][kT * kPitch], sV[2][kT * kPitch];
+  extern __shared__ __align__(16) uint8_t fa_smem[];
+  const int grp = threadIdx.x >> 7, ltid = threadIdx.x & 127;
+  __nv_bfloat16(*sK)[kT * kPitch] = reinterpret_cast<__nv_bfloat16(*)[kT * kPitch]>(fa_smem + grp * kGroupBytes);
+  __nv_bfloat16(*sV)[kT * kPitch] = sK + 2;
   const int n = blockIdx.z, h = blockIdx.y;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int warp = ltid >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const int64_t ld = 3 * H * kD;
   const __nv_bfloat16* q = qkv + (int64_t)n * L * ld + h * kD;
   const __nv_bfloat16* k = q + H * kD;
@@ -238,18 +289,20 @@ __global__ void __launch_bounds__(128) attn_bwd_dq_mma_kernel(const __nv_bfloat1
     for (int j = 0; j < 4; ++j) dq[i][j] = 0.f;
 
   const int ntiles = (L + kT - 1) / kT;
-  load_tile(sK[0], k, ld, 0, L);
-  load_tile(sV[0], v, ld, 0, L);
+  if (grp < ntiles) {
+    load_tile(sK[0], k, ld, grp * kT, L);
+    load_tile(sV[0], v, ld, grp * kT, L);
+  }
   cp_async_commit();
-  for (int it = 0; it < ntiles; ++it) {
-    const int buf = it & 1;
-    if (it + 1 < ntiles) {
-      load_tile(sK[buf ^ 1], k, ld, (it + 1) * kT, L);
-      load_tile(sV[buf ^ 1], v, ld, (it + 1) * kT, L);
+  for (int it = grp, li = 0; it < ntiles; it += G, ++li) {
+    const int buf = li & 1;
+    if (it + G < ntiles) {
+      load_tile(sK[buf ^ 1], k, ld, (it + G) * kT, L);
+      load_tile(sV[buf ^ 1], v, ld, (it + G) * kT, L);
     }
     cp_async_commit();
     cp_async_wait<1>();
-    __syncthreads();
+    group_sync(grp);
     float s[8][4], dp[8][4];
 #pragma unroll
     for (int j = 0; j < 8; ++j)
@@ -272,7 +325,25 @@ __global__ void __launch_bounds__(128) attn_bwd_dq_mma_kernel(const __nv_bfloat1
       da[j >> 1][(j & 1) * 2 + 1] = pack2(ds[2], ds[3]);
     }
     gemm_p_tile(dq, da, sK[buf]);
+    group_sync(grp);
+  }
+  if (G > 1) {                         // add the groups' partial dQ in group order
+    float* mine = reinterpret_cast<float*>(fa_smem + grp * kGroupBytes);
+    if (grp > 0) {
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) mine[(nt * 4 + i) * 128 + ltid] = dq[nt][i];
+    }
     __syncthreads();
+    if (grp > 0) return;
+    for (int og = 1; og < G; ++og) {
+      const float* oth = reinterpret_cast<const float*>(fa_smem + og * kGroupBytes);
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) dq[nt][i] += oth[(nt * 4 + i) * 128 + ltid];
+    }
   }
 #pragma unroll
   for (int r = 0; r < 2; ++r) {
@@ -288,15 +359,20 @@ __global__ void __launch_bounds__(128) attn_bwd_dq_mma_kernel(const __nv_bfloat1
 // ------------------------------------------------------------------------------------------------ backward: dK, dV
 // One CTA = 64 keys.  S^T = K Q^T, P^T = exp(scale S^T - lse[q]), dV = P^T dO, dP^T = V dO^T,
 // dS^T = P^T * (dP^T - delta[q]), dK = scale * dS^T Q
-__global__ void __launch_bounds__(128) attn_bwd_dkv_mma_kernel(const __nv_bfloat16* __restrict__ qkv,
+template <int G>
+__global__ void __launch_bounds__(128 * G) attn_bwd_dkv_mma_kernel(const __nv_bfloat16* __restrict__ qkv,
                                                                const __nv_bfloat16* __restrict__ dout,
                                                                const float* __restrict__ lse, const float* __restrict__ delta,
                                                                __nv_bfloat16* __restrict__ dqkv, int L, int H, float scale) {
   pdl_sync();
-  __shared__ __align__(16) __nv_bfloat16 sQ[2][kT * kPitch], sG[2][kT * kPitch];
-  __shared__ float sL[2][kT], sD[2][kT];
+  extern __shared__ __align__(16) uint8_t fa_smem[];
+  const int grp = threadIdx.x >> 7, ltid = threadIdx.x & 127;
+  __nv_bfloat16(*sQ)[kT * kPitch] = reinterpret_cast<__nv_bfloat16(*)[kT * kPitch]>(fa_smem + grp * kGroupBytes);
+  __nv_bfloat16(*sG)[kT * kPitch] = sQ + 2;
+  float(*sL)[kT] = reinterpret_cast<float(*)[kT]>(fa_smem + grp * kGroupBytes + 4 * kTileBytes);
+  float(*sD)[kT] = sL + 2;
   const int n = blockIdx.z, h = blockIdx.y;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int warp = ltid >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const int64_t ld = 3 * H * kD;
   const __nv_bfloat16* q = qkv + (int64_t)n * L * ld + h * kD;
   const __nv_bfloat16* k = q + H * kD;
@@ -319,20 +395,20 @@ __global__ void __launch_bounds__(128) attn_bwd_dkv_mma_kernel(const __nv_bfloat
   auto stage = [&](int buf, int q0) {
     load_tile(sQ[buf], q, ld, q0, L);
     load_tile(sG[buf], go, H * kD, q0, L);
-    if (threadIdx.x < kT) {
-      const bool ok = q0 + (int)threadIdx.x < L;
-      sL[buf][threadIdx.x] = ok ? lrow[q0 + threadIdx.x] * kLog2e : INFINITY;   // +inf -> P = 0 for padded queries
-      sD[buf][threadIdx.x] = ok ? drow[q0 + threadIdx.x] : 0.f;
+    if (ltid < kT) {
+      const bool ok = q0 + ltid < L;
+      sL[buf][ltid] = ok ? lrow[q0 + ltid] * kLog2e : INFINITY;   // +inf -> P = 0 for padded queries
+      sD[buf][ltid] = ok ? drow[q0 + ltid] : 0.f;
     }
   };
-  stage(0, 0);
+  if (grp < ntiles) stage(0, grp * kT);
   cp_async_commit();
-  for (int it = 0; it < ntiles; ++it) {
-    const int buf = it & 1;
-    if (it + 1 < ntiles) stage(buf ^ 1, (it + 1) * kT);
+  for (int it = grp, li = 0; it < ntiles; it += G, ++li) {
+    const int buf = li & 1;
+    if (it + G < ntiles) stage(buf ^ 1, (it + G) * kT);
     cp_async_commit();
     cp_async_wait<1>();
-    __syncthreads();
+    group_sync(grp);
     float s[8][4], dp[8][4];
 #pragma unroll
     for (int j = 0; j < 8; ++j)
@@ -357,7 +433,31 @@ __global__ void __launch_bounds__(128) attn_bwd_dkv_mma_kernel(const __nv_bfloat
     }
     gemm_p_tile(dv, pa, sG[buf]);
     gemm_p_tile(dk, da, sQ[buf]);
+    group_sync(grp);
+  }
+  if (G > 1) {                         // add the groups' partial dK / dV in group order
+    float* mine = reinterpret_cast<float*>(fa_smem + grp * kGroupBytes);
+    if (grp > 0) {
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          mine[(nt * 4 + i) * 128 + ltid] = dk[nt][i];
+          mine[(16 + nt * 4 + i) * 128 + ltid] = dv[nt][i];
+        }
+    }
     __syncthreads();
+    if (grp > 0) return;
+    for (int og = 1; og < G; ++og) {
+      const float* oth = reinterpret_cast<const float*>(fa_smem + og * kGroupBytes);
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          dk[nt][i] += oth[(nt * 4 + i) * 128 + ltid];
+          dv[nt][i] += oth[(16 + nt * 4 + i) * 128 + ltid];
+        }
+    }
   }
 #pragma unroll
   for (int r = 0; r < 2; ++r) {
@@ -406,6 +506,33 @@ __global__ void __launch_bounds__(256) attn_delta_kernel(const __nv_bfloat16* __
 
 using namespace petsyn;
 
+// groups of four warps per CTA (PETSYN_ATTN_GROUPS = 1, 2 or 4; default 2): see the note above attn_fwd_mma_kernel
+static int fa_groups() {
+  static int g = 0;
+  if (g == 0) {
+    const char* e = getenv("PETSYN_ATTN_GROUPS");
+    g = e != nullptr ? atoi(e) : 2;
+    if (g != 1 && g != 2 && g != 4) g = 2;
+  }
+  return g;
+}
+#define PETSYN_FA_LAUNCH_G(KERNEL, G, GRID, ST, ...)                                                                  \
+  {                                                                                                                   \
+    static bool attr_ = false;                                                                                        \
+    if (!attr_) {                                                                                                     \
+      PETSYN_CHECK_CUDA(cudaFuncSetAttribute(KERNEL<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * fa::kGroupBytes)); \
+      attr_ = true;                                                                                                   \
+    }                                                                                                                 \
+    PETSYN_CHECK_CUDA(launch_pdl(KERNEL<G>, dim3(GRID), dim3(128 * G), (size_t)(G * fa::kGroupBytes), ST, __VA_ARGS__)); \
+  }
+#define PETSYN_FA_LAUNCH(KERNEL, GRID, ST, ...)                                       \
+  do {                                                                                \
+    const int g_ = fa_groups();                                                       \
+    if (g_ == 1) PETSYN_FA_LAUNCH_G(KERNEL, 1, GRID, ST, __VA_ARGS__)                  \
+    else if (g_ == 2) PETSYN_FA_LAUNCH_G(KERNEL, 2, GRID, ST, __VA_ARGS__)             \
+    else PETSYN_FA_LAUNCH_G(KERNEL, 4, GRID, ST, __VA_ARGS__)                          \
+  } while (0)
+
 extern "C" {
 
 int32_t petsyn_attention_fwd(const void* qkv, void* out, float* lse, int32_t n, int32_t l, int32_t heads,
@@ -413,8 +540,9 @@ int32_t petsyn_attention_fwd(const void* qkv, void* out, float* lse, int32_t n, 
   PETSYN_REQUIRE(qkv && out && lse && n > 0 && l > 0 && heads > 0, "bad argument");
   PETSYN_REQUIRE(head_dim == fa::kD, "attention kernels are specialised for head_dim 32 (num_head_channels=32)");
   dim3 grid((unsigned)((l + fa::kT - 1) / fa::kT), (unsigned)heads, (unsigned)n);
-  PETSYN_CHECK_CUDA(launch_pdl(fa::attn_fwd_mma_kernel, dim3(grid), dim3(128), 0, as_stream(stream), reinterpret_cast<const __nv_bfloat16*>(qkv),
-                                                               reinterpret_cast<__nv_bfloat16*>(out), lse, l, heads, scale));
+  const auto* qp = reinterpret_cast<const __nv_bfloat16*>(qkv);
+  auto* op = reinterpret_cast<__nv_bfloat16*>(out);
+  PETSYN_FA_LAUNCH(fa::attn_fwd_mma_kernel, grid, as_stream(stream), qp, op, lse, l, heads, scale);
   return check_launch("attn_fwd_mma_kernel");
 }
 
@@ -432,10 +560,11 @@ int32_t petsyn_attention_bwd(const void* qkv, const void* out, const void* dout,
   int32_t rc = check_launch("attn_delta_kernel");
   if (rc) return rc;
   dim3 grid((unsigned)((l + fa::kT - 1) / fa::kT), (unsigned)heads, (unsigned)n);
-  PETSYN_CHECK_CUDA(launch_pdl(fa::attn_bwd_dq_mma_kernel, dim3(grid), dim3(128), 0, st, qp, gp, lse, delta, reinterpret_cast<__nv_bfloat16*>(dqkv), l, heads, scale));
+  auto* dq = reinterpret_cast<__nv_bfloat16*>(dqkv);
+  PETSYN_FA_LAUNCH(fa::attn_bwd_dq_mma_kernel, grid, st, qp, gp, lse, delta, dq, l, heads, scale);
   rc = check_launch("attn_bwd_dq_mma_kernel");
   if (rc) return rc;
-  PETSYN_CHECK_CUDA(launch_pdl(fa::attn_bwd_dkv_mma_kernel, dim3(grid), dim3(128), 0, st, qp, gp, lse, delta, reinterpret_cast<__nv_bfloat16*>(dqkv), l, heads, scale));
+  PETSYN_FA_LAUNCH(fa::attn_bwd_dkv_mma_kernel, grid, st, qp, gp, lse, delta, dq, l, heads, scale);
   return check_launch("attn_bwd_dkv_mma_kernel");
 }
 
