@@ -223,34 +223,69 @@ __device__ __forceinline__ float gelu_grad(float x) {
   return 0.5f * (1.f + erff(x * 0.70710678118654752f)) + x * 0.3989422804014327f * __expf(-0.5f * x * x);
 }
 // h: [rows, 2F] = (x | gate); out [rows, F] = x * gelu(gate)     (MONAI MLPBlock act="GEGLU")
+// One thread = 8 consecutive channels (16-byte accesses); F must be a multiple of 8.
+__device__ __forceinline__ void unpack8bf(const uint4& raw, float (&f)[8]) {
+  const __nv_bfloat162* b2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 v = __bfloat1622float2(b2[i]);
+    f[2 * i] = v.x;
+    f[2 * i + 1] = v.y;
+  }
+}
+__device__ __forceinline__ uint4 pack8bf(const float (&f)[8]) {
+  uint4 o;
+  __nv_bfloat162 b0 = __floats2bfloat162_rn(f[0], f[1]), b1 = __floats2bfloat162_rn(f[2], f[3]);
+  __nv_bfloat162 b2 = __floats2bfloat162_rn(f[4], f[5]), b3 = __floats2bfloat162_rn(f[6], f[7]);
+  o.x = *reinterpret_cast<uint32_t*>(&b0); o.y = *reinterpret_cast<uint32_t*>(&b1);
+  o.z = *reinterpret_cast<uint32_t*>(&b2); o.w = *reinterpret_cast<uint32_t*>(&b3);
+  return o;
+}
 __global__ void __launch_bounds__(256) geglu_fwd_kernel(const __nv_bfloat16* __restrict__ h,
                                                         __nv_bfloat16* __restrict__ out, int64_t rows, int F) {
   pdl_sync();
-  const int64_t total = rows * F;
+  const int f8 = F / 8;
+  const int64_t total = rows * f8;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t r = i / F;
-    const int c = (int)(i - r * F);
-    out[i] = __float2bfloat16(bf(h[r * 2 * F + c]) * gelu_f(bf(h[r * 2 * F + F + c])));
+    const int64_t r = i / f8;
+    const int c = (int)(i - r * f8) * 8;
+    float x[8], g[8], o[8];
+    unpack8bf(*reinterpret_cast<const uint4*>(h + r * 2 * F + c), x);
+    unpack8bf(*reinterpret_cast<const uint4*>(h + r * 2 * F + F + c), g);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) o[q] = x[q] * gelu_f(g[q]);
+    *reinterpret_cast<uint4*>(out + r * F + c) = pack8bf(o);
   }
 }
 __global__ void __launch_bounds__(256) geglu_bwd_kernel(const __nv_bfloat16* __restrict__ h,
                                                         const __nv_bfloat16* __restrict__ dout,
                                                         __nv_bfloat16* __restrict__ dh, int64_t rows, int F) {
   pdl_sync();
-  const int64_t total = rows * F;
+  const int f8 = F / 8;
+  const int64_t total = rows * f8;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t r = i / F;
-    const int c = (int)(i - r * F);
-    const float x = bf(h[r * 2 * F + c]), g = bf(h[r * 2 * F + F + c]), d = bf(dout[i]);
-    dh[r * 2 * F + c] = __float2bfloat16(d * gelu_f(g));
-    dh[r * 2 * F + F + c] = __float2bfloat16(d * x * gelu_grad(g));
+    const int64_t r = i / f8;
+    const int c = (int)(i - r * f8) * 8;
+    float x[8], g[8], d[8], dx[8], dg[8];
+    unpack8bf(*reinterpret_cast<const uint4*>(h + r * 2 * F + c), x);
+    unpack8bf(*reinterpret_cast<const uint4*>(h + r * 2 * F + F + c), g);
+    unpack8bf(*reinterpret_cast<const uint4*>(dout + r * F + c), d);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      dx[q] = d[q] * gelu_f(g[q]);
+      dg[q] = d[q] * x[q] * gelu_grad(g[q]);
+    }
+    *reinterpret_cast<uint4*>(dh + r * 2 * F + c) = pack8bf(dx);
+    *reinterpret_cast<uint4*>(dh + r * 2 * F + F + c) = pack8bf(dg);
   }
 }
 
 // ------------------------------------------------------------------------------------------------ covariate injection
 // Cross-attention over a length-1 context: softmax over one key == 1, so attn2(x, ctx) = to_out(to_v(ctx)) for every
 // token (atten_unet_model.py:156-175).  bias[n, :] = Wo (Wv ctx[n]) + bo, then t[n, l, :] += bias[n, :].
-__global__ void __launch_bounds__(128) covariate_bias_kernel(const float* __restrict__ ctx, const float* __restrict__ wv,
+// grid (sample, groups of 8 output channels), 256 threads: every CTA recomputes v = Wv ctx[n] (C x Cctx products), then a warp
+// per output channel strides its lanes over the row of Wo (coalesced) and folds them with a butterfly
+__global__ void __launch_bounds__(256) covariate_bias_kernel(const float* __restrict__ ctx, const float* __restrict__ wv,
                                                              const float* __restrict__ wo, const float* __restrict__ bo,
                                                              float* __restrict__ vbuf, float* __restrict__ bias, int N,
                                                              int Cctx, int C) {
@@ -261,13 +296,16 @@ __global__ void __launch_bounds__(128) covariate_bias_kernel(const float* __rest
     float s = 0.f;
     for (int j = 0; j < Cctx; ++j) s += wv[c * Cctx + j] * ctx[n * Cctx + j];
     sv[c] = s;
-    vbuf[n * C + c] = s;
+    if (blockIdx.y == 0) vbuf[n * C + c] = s;
   }
   __syncthreads();
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    float s = bo[c];
-    for (int j = 0; j < C; ++j) s += wo[c * C + j] * sv[j];
-    bias[n * C + c] = s;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c = blockIdx.y * 8 + warp;
+  if (c < C) {
+    float s = 0.f;
+    for (int j = lane; j < C; j += 32) s += wo[c * C + j] * sv[j];
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) bias[n * C + c] = s + bo[c];
   }
 }
 __global__ void __launch_bounds__(256) add_sample_bias_kernel(__nv_bfloat16* __restrict__ t, const float* __restrict__ bias,
@@ -400,20 +438,20 @@ int32_t petsyn_layernorm_bwd(const void* x, const void* dy, const float* gamma, 
   const size_t ln_smem = std::max<size_t>((size_t)8 * 2 * c, 1024) * sizeof(float);
   if (ln_smem > 48 * 1024)
     PETSYN_CHECK_CUDA(cudaFuncSetAttribute(layernorm_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ln_smem));
-  PETSYN_CHECK_CUDA(launch_pdl(layernorm_bwd_kernel, dim3(blocks_for(rows, 8, 148 * 4)), dim3(256), ln_smem, st, 
+  PETSYN_CHECK_CUDA(launch_pdl(layernorm_bwd_kernel, dim3(blocks_for(rows, 8, 148)), dim3(256), ln_smem, st, 
       CBFP(x), CBFP(dy), gamma, mean, rstd, BFP(dx), dgamma, dbeta, rows, c, accumulate_dx, ws));
   return check_launch("layernorm_bwd_kernel");
 }
 
 int32_t petsyn_geglu_fwd(const void* h, void* out, int64_t rows, int32_t f, void* stream) {
-  PETSYN_REQUIRE(h && out && rows > 0 && f > 0, "bad argument");
-  PETSYN_CHECK_CUDA(launch_pdl(geglu_fwd_kernel, dim3(blocks_for(rows * f)), dim3(256), 0, as_stream(stream), CBFP(h), BFP(out), rows, f));
+  PETSYN_REQUIRE(h && out && rows > 0 && f > 0 && f % 8 == 0, "bad argument (the gated width must be a multiple of 8)");
+  PETSYN_CHECK_CUDA(launch_pdl(geglu_fwd_kernel, dim3(blocks_for(rows * (f / 8))), dim3(256), 0, as_stream(stream), CBFP(h), BFP(out), rows, f));
   return check_launch("geglu_fwd_kernel");
 }
 
 int32_t petsyn_geglu_bwd(const void* h, const void* dout, void* dh, int64_t rows, int32_t f, void* stream) {
-  PETSYN_REQUIRE(h && dout && dh && rows > 0 && f > 0, "bad argument");
-  PETSYN_CHECK_CUDA(launch_pdl(geglu_bwd_kernel, dim3(blocks_for(rows * f)), dim3(256), 0, as_stream(stream), CBFP(h), CBFP(dout), BFP(dh), rows, f));
+  PETSYN_REQUIRE(h && dout && dh && rows > 0 && f > 0 && f % 8 == 0, "bad argument (the gated width must be a multiple of 8)");
+  PETSYN_CHECK_CUDA(launch_pdl(geglu_bwd_kernel, dim3(blocks_for(rows * (f / 8))), dim3(256), 0, as_stream(stream), CBFP(h), CBFP(dout), BFP(dh), rows, f));
   return check_launch("geglu_bwd_kernel");
 }
 
@@ -422,7 +460,7 @@ int32_t petsyn_covariate_bias_fwd(const float* ctx, const float* wv, const float
                                   int64_t rows_per_sample, void* stream) {
   PETSYN_REQUIRE(ctx && wv && wo && bo && vbuf && bias && tokens && n > 0 && cctx > 0 && c > 0, "bad argument");
   cudaStream_t st = as_stream(stream);
-  PETSYN_CHECK_CUDA(launch_pdl(covariate_bias_kernel, dim3(n), dim3(128), c * sizeof(float), st, ctx, wv, wo, bo, vbuf, bias, n, cctx, c));
+  PETSYN_CHECK_CUDA(launch_pdl(covariate_bias_kernel, dim3(n, (c + 7) / 8), dim3(256), c * sizeof(float), st, ctx, wv, wo, bo, vbuf, bias, n, cctx, c));
   int32_t rc = check_launch("covariate_bias_kernel");
   if (rc) return rc;
   PETSYN_CHECK_CUDA(launch_pdl(add_sample_bias_kernel, dim3(blocks_for(rows_per_sample * n * c)), dim3(256), 0, st, BFP(tokens), bias, rows_per_sample,
