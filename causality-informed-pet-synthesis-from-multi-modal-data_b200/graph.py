@@ -180,6 +180,7 @@ class ConvOp(Op):
         self.fork_mode = os.environ.get("PETSYN_FORK_MODE", "wgrad")
         self.acc_dx = False
         self.colsum_done = False  # set by the NormActOp consuming z when it already summed dz over the rows (bias gradient)
+        self.colsum_from: Optional["ConvOp"] = None   # another conv with the SAME output-gradient slice: its column sums are ours
         self.acc_dw = False      # add into grad_w / grad_b instead of overwriting (several backward calls per step)
         self._ver = None
         self._zero_b = None      # data_ptr of the bias-gradient slot that was cleared (biases with identically zero gradient)
@@ -323,14 +324,20 @@ class ConvOp(Op):
         bkw = {}
         if self.bias is not None:
             if self.use_bias:
-                if self.colsum_done:
+                src = self.colsum_from
+                if (src is not None and not self.padded and not src.padded and self.grad_b.is_contiguous()
+                        and src.dbias_stage is not None):
+                    # a ResnetBlock's conv2 and its 1x1 skip convolution read the same output gradient: one pass sums it
+                    self.colsum_done = False
+                    bkw = dict(dbias_acc=src.dbias_stage, dbias=self.grad_b)
+                elif self.colsum_done:
                     self.colsum_done = False
                 else:
                     dsl = self.dy_slice()
                     cs, co = (dsl.buf.c, dsl.off) if dsl is not None else (self.cout, 0)
                     check(lib.petsyn_colsum(ptr(dz), cs, co, ptr(self.dbias_stage), dz.shape[0], self.cout,
                                             stream_ptr()), "colsum")
-                if self.grad_b.is_contiguous() and not self.padded:
+                if not bkw and self.grad_b.is_contiguous() and not self.padded:
                     bkw = dict(dbias_acc=self.dbias_stage, dbias=self.grad_b)
             elif not self.acc_dw and self._zero_b != self.grad_b.data_ptr():
                 # a bias in front of a non-affine InstanceNorm has exactly zero gradient and nothing ever writes its
@@ -791,6 +798,26 @@ class Tape:
             if isinstance(op, NormActOp) and key == "dz" and sl.off <= lo and hi <= sl.off + sl.c and op.colsum_conv is None:
                 op.colsum_conv = cv                    # the conv's channels may be a sub-range of the op's dz
                 op.colsum_range = (lo - sl.off, region.c)
+        # convs that read the SAME output-gradient slice (conv2 and the 1x1 skip convolution of a ResnetBlock) share one
+        # column-sum pass: the owner is the conv whose sums are a normalisation's by-product, else the one that runs first in
+        # backward (all weight gradients of a tape are serialised in backward order)
+        same: Dict[Tuple[int, int, int], List[ConvOp]] = {}
+        for cv in self.ops:
+            if isinstance(cv, ConvOp):
+                cv.colsum_from = None
+                if cv.use_bias and cv.need_dw and cv.bias is not None and cv.dy_slice() is not None:
+                    r = cv.dy_slice()
+                    same.setdefault((id(r.buf), r.off, r.c), []).append(cv)
+        if not os.environ.get("PETSYN_NO_COLSUM_SHARING"):
+            fed = {id(op.colsum_conv) for op in self.ops if isinstance(op, NormActOp) and op.colsum_conv is not None}
+            for lst in same.values():
+                if len(lst) < 2:
+                    continue
+                by = [cv for cv in lst if id(cv) in fed]
+                owner = by[0] if by else lst[-1]          # lst is in tape order: the last one runs first in backward
+                for cv in lst:
+                    if cv is not owner:
+                        cv.colsum_from = owner
         # statistics as a by-product: a GroupNorm whose input (a buffer or a channel slice of one) is written, channel range
         # by channel range, only by un-normalised NormActOps (residual sums, copies into concat buffers) takes its sums from
         # those producers; a destination may serve two consuming normalisations
