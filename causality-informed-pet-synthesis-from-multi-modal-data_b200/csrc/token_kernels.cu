@@ -217,6 +217,101 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const __nv_bfloat16*
       });
 }
 
+// The same for C = NCH * 128: lane l owns channels [4 l, 4 l + 4) of every 128-channel chunk -- 8-byte accesses, everything
+// in registers (the transformer width of the reference's configs is 128)
+template <int NCH>
+__global__ void __launch_bounds__(256) layernorm_bwd_vec_kernel(const __nv_bfloat16* __restrict__ x,
+                                                                const __nv_bfloat16* __restrict__ dy,
+                                                                const float* __restrict__ gamma,
+                                                                const float* __restrict__ mean,
+                                                                const float* __restrict__ rstd,
+                                                                __nv_bfloat16* __restrict__ dx, float* __restrict__ dgamma,
+                                                                float* __restrict__ dbeta, int64_t rows, int accumulate,
+                                                                const DetWs ws) {
+  pdl_sync();
+  constexpr int C = NCH * 128;
+  extern __shared__ __align__(16) float sm[];   // [warps][2][C]
+  const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  float ga[NCH][4], pg[NCH][4], pb[NCH][4];
+#pragma unroll
+  for (int k = 0; k < NCH; ++k) {
+    const float4 g4 = *reinterpret_cast<const float4*>(gamma + k * 128 + lane * 4);
+    ga[k][0] = g4.x; ga[k][1] = g4.y; ga[k][2] = g4.z; ga[k][3] = g4.w;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) pg[k][i] = pb[k][i] = 0.f;
+  }
+  auto ld4 = [](const __nv_bfloat16* p, float (&f)[4]) {
+    const uint2 raw = *reinterpret_cast<const uint2*>(p);
+    const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.x));
+    const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.y));
+    f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y;
+  };
+  for (int64_t r = (int64_t)blockIdx.x * wpb + (threadIdx.x >> 5); r < rows; r += (int64_t)gridDim.x * wpb) {
+    const float mu = mean[r], rs = rstd[r];
+    float xh[NCH][4], gg[NCH][4];
+    float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+    for (int k = 0; k < NCH; ++k) {
+      float xv[4], gv[4];
+      ld4(x + r * C + k * 128 + lane * 4, xv);
+      ld4(dy + r * C + k * 128 + lane * 4, gv);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        xh[k][i] = (xv[i] - mu) * rs;
+        gg[k][i] = gv[i] * ga[k][i];
+        s0 += gg[k][i];
+        s1 += gg[k][i] * xh[k][i];
+        pg[k][i] += gv[i] * xh[k][i];
+        pb[k][i] += gv[i];
+      }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+      s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+      s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+    }
+    s0 *= 1.f / (float)C; s1 *= 1.f / (float)C;
+#pragma unroll
+    for (int k = 0; k < NCH; ++k) {
+      float v[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) v[i] = rs * (gg[k][i] - s0 - xh[k][i] * s1);
+      __nv_bfloat16* p = dx + r * C + k * 128 + lane * 4;
+      if (accumulate) {
+        float old[4];
+        ld4(p, old);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) v[i] += old[i];
+      }
+      uint2 o;
+      __nv_bfloat162 b0 = __floats2bfloat162_rn(v[0], v[1]), b1 = __floats2bfloat162_rn(v[2], v[3]);
+      o.x = *reinterpret_cast<uint32_t*>(&b0); o.y = *reinterpret_cast<uint32_t*>(&b1);
+      *reinterpret_cast<uint2*>(p) = o;
+    }
+  }
+  {
+    float* mine = sm + (threadIdx.x >> 5) * 2 * C;
+#pragma unroll
+    for (int k = 0; k < NCH; ++k)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        mine[k * 128 + lane * 4 + i] = pg[k][i];
+        mine[C + k * 128 + lane * 4 + i] = pb[k][i];
+      }
+  }
+  __syncthreads();
+  det_cta_reduce(
+      ws, 2 * C, sm,
+      [&](int e) {
+        float s = 0.f;
+        for (int w = 0; w < wpb; ++w) s += sm[w * 2 * C + e];
+        return s;
+      },
+      [&](int e, float t, bool atomic) {
+        float* p = e < C ? dgamma + e : dbeta + (e - C);
+        if (atomic) atomicAdd(p, t); else *p += t;
+      });
+}
+
 // ------------------------------------------------------------------------------------------------ GEGLU
 __device__ __forceinline__ float gelu_f(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752f)); }
 __device__ __forceinline__ float gelu_grad(float x) {
@@ -438,8 +533,16 @@ int32_t petsyn_layernorm_bwd(const void* x, const void* dy, const float* gamma, 
   const size_t ln_smem = std::max<size_t>((size_t)8 * 2 * c, 1024) * sizeof(float);
   if (ln_smem > 48 * 1024)
     PETSYN_CHECK_CUDA(cudaFuncSetAttribute(layernorm_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ln_smem));
-  PETSYN_CHECK_CUDA(launch_pdl(layernorm_bwd_kernel, dim3(blocks_for(rows, 8, 148)), dim3(256), ln_smem, st, 
+  if (c == 128) {
+    PETSYN_CHECK_CUDA(launch_pdl(layernorm_bwd_vec_kernel<1>, dim3(blocks_for(rows, 8, 148)), dim3(256), ln_smem, st, CBFP(x), CBFP(dy),
+                                 gamma, mean, rstd, BFP(dx), dgamma, dbeta, rows, accumulate_dx, ws));
+  } else if (c == 256) {
+    PETSYN_CHECK_CUDA(launch_pdl(layernorm_bwd_vec_kernel<2>, dim3(blocks_for(rows, 8, 148)), dim3(256), ln_smem, st, CBFP(x), CBFP(dy),
+                                 gamma, mean, rstd, BFP(dx), dgamma, dbeta, rows, accumulate_dx, ws));
+  } else {
+    PETSYN_CHECK_CUDA(launch_pdl(layernorm_bwd_kernel, dim3(blocks_for(rows, 8, 148)), dim3(256), ln_smem, st, 
       CBFP(x), CBFP(dy), gamma, mean, rstd, BFP(dx), dgamma, dbeta, rows, c, accumulate_dx, ws));
+  }
   return check_launch("layernorm_bwd_kernel");
 }
 
