@@ -97,11 +97,11 @@ def test_generator_step_matches_oracle_and_golden(petsyn):
             assert gn < 1e-4, (k, gn)                              # biases in front of InstanceNorm: exactly zero grad
     print("global grad-norm ours/oracle/peer", tot ** 0.5, tot_ref ** 0.5, tot_peer ** 0.5, "worst per-tensor rel", worst,
           "peer", worst_peer)
-    # The fp32 add-reductions of the CUDA path (statistics / weight-gradient / split-K partials) complete in a run-dependent
-    # order; this randomly initialised generator amplifies those last-bit differences through its 12-voxel InstanceNorm
-    # bottleneck.  Measured over 14 runs of this very test: ours 7002 .. 7801 (oracle 7968, the deterministic cuDNN peer
-    # 7555 +- 5), i.e. 2 .. 12 % below the oracle against the peer's 5.2 %.  Bound: 3x the peer's deviation or 15 %.
-    assert abs(tot ** 0.5 - tot_ref ** 0.5) <= max(3.0 * abs(tot_peer ** 0.5 - tot_ref ** 0.5), 0.15 * tot_ref ** 0.5)
+    # Round 1's fp32 add-reductions completed in a run-dependent order and this randomly initialised generator amplified the
+    # last-bit differences through its 12-voxel InstanceNorm bottleneck (7002 .. 7801 over 14 runs against the oracle's 7968).
+    # The reductions are order-independent now (double accumulators, fixed-order split-K / weight-gradient sums): the norm is
+    # the same in every run (7479; the cuDNN bf16 peer: 7559) and the bound is the usual 2x the peer's own deviation.
+    assert abs(tot ** 0.5 - tot_ref ** 0.5) <= max(2.0 * abs(tot_peer ** 0.5 - tot_ref ** 0.5), 2e-2 * tot_ref ** 0.5)
     # gradient direction on the largest tensors
     og_grads, pg_grads = dict(og.named_parameters()), dict(pg.named_parameters())
     for k in sorted(ref_norms, key=ref_norms.get, reverse=True)[:6]:
