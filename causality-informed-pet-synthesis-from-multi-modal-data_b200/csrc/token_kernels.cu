@@ -158,7 +158,7 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const __nv_bfloat16*
                                                             const float* __restrict__ rstd,
                                                             __nv_bfloat16* __restrict__ dx, float* __restrict__ dgamma,
                                                             float* __restrict__ dbeta, int64_t rows, int C,
-                                                            int accumulate, const DetWs ws) {
+                                                            int accumulate, const DetWs ws, int overwrite) {
   pdl_sync();
   extern __shared__ __align__(16) float sm[];   // [warps][2][C] per-warp partials of dgamma / dbeta (>= 1024 floats)
   const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
@@ -213,7 +213,7 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const __nv_bfloat16*
       },
       [&](int e, float t, bool atomic) {
         float* p = e < C ? dgamma + e : dbeta + (e - C);
-        if (atomic) atomicAdd(p, t); else *p += t;
+        if (atomic) atomicAdd(p, t); else if (overwrite) *p = t; else *p += t;
       });
 }
 
@@ -227,7 +227,7 @@ __global__ void __launch_bounds__(256) layernorm_bwd_vec_kernel(const __nv_bfloa
                                                                 const float* __restrict__ rstd,
                                                                 __nv_bfloat16* __restrict__ dx, float* __restrict__ dgamma,
                                                                 float* __restrict__ dbeta, int64_t rows, int accumulate,
-                                                                const DetWs ws) {
+                                                                const DetWs ws, int overwrite) {
   pdl_sync();
   constexpr int C = NCH * 128;
   extern __shared__ __align__(16) float sm[];   // [warps][2][C]
@@ -308,7 +308,7 @@ __global__ void __launch_bounds__(256) layernorm_bwd_vec_kernel(const __nv_bfloa
       },
       [&](int e, float t, bool atomic) {
         float* p = e < C ? dgamma + e : dbeta + (e - C);
-        if (atomic) atomicAdd(p, t); else *p += t;
+        if (atomic) atomicAdd(p, t); else if (overwrite) *p = t; else *p += t;
       });
 }
 
@@ -523,25 +523,29 @@ int32_t petsyn_layernorm_bwd(const void* x, const void* dy, const float* gamma, 
   PETSYN_REQUIRE(x && dy && gamma && mean && rstd && dx && dgamma && dbeta && rows > 0, "bad argument");
   PETSYN_REQUIRE(c % 8 == 0 && c >= 8 && c <= 1024, "LayerNorm width must be a multiple of 8, at most 1024");
   cudaStream_t st = as_stream(stream);
-  PETSYN_CHECK_CUDA(cudaMemsetAsync(dgamma, 0, c * sizeof(float), st));
-  PETSYN_CHECK_CUDA(cudaMemsetAsync(dbeta, 0, c * sizeof(float), st));
   DetWs ws;
   {
     int32_t rcw = det_workspace(&ws);
     if (rcw) return rcw;
+  }
+  // reproducible mode: the last CTA of the reduction writes the totals (no clearing needed); float-atomic mode adds into zeros
+  const int overwrite = ws.acc != nullptr ? 1 : 0;
+  if (!overwrite) {
+    PETSYN_CHECK_CUDA(cudaMemsetAsync(dgamma, 0, c * sizeof(float), st));
+    PETSYN_CHECK_CUDA(cudaMemsetAsync(dbeta, 0, c * sizeof(float), st));
   }
   const size_t ln_smem = std::max<size_t>((size_t)8 * 2 * c, 1024) * sizeof(float);
   if (ln_smem > 48 * 1024)
     PETSYN_CHECK_CUDA(cudaFuncSetAttribute(layernorm_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ln_smem));
   if (c == 128) {
     PETSYN_CHECK_CUDA(launch_pdl(layernorm_bwd_vec_kernel<1>, dim3(blocks_for(rows, 8, 148)), dim3(256), ln_smem, st, CBFP(x), CBFP(dy),
-                                 gamma, mean, rstd, BFP(dx), dgamma, dbeta, rows, accumulate_dx, ws));
+                                 gamma, mean, rstd, BFP(dx), dgamma, dbeta, rows, accumulate_dx, ws, overwrite));
   } else if (c == 256) {
     PETSYN_CHECK_CUDA(launch_pdl(layernorm_bwd_vec_kernel<2>, dim3(blocks_for(rows, 8, 148)), dim3(256), ln_smem, st, CBFP(x), CBFP(dy),
-                                 gamma, mean, rstd, BFP(dx), dgamma, dbeta, rows, accumulate_dx, ws));
+                                 gamma, mean, rstd, BFP(dx), dgamma, dbeta, rows, accumulate_dx, ws, overwrite));
   } else {
     PETSYN_CHECK_CUDA(launch_pdl(layernorm_bwd_kernel, dim3(blocks_for(rows, 8, 148)), dim3(256), ln_smem, st, 
-      CBFP(x), CBFP(dy), gamma, mean, rstd, BFP(dx), dgamma, dbeta, rows, c, accumulate_dx, ws));
+      CBFP(x), CBFP(dy), gamma, mean, rstd, BFP(dx), dgamma, dbeta, rows, c, accumulate_dx, ws, overwrite));
   }
   return check_launch("layernorm_bwd_kernel");
 }
