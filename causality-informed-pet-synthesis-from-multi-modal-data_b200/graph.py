@@ -404,14 +404,16 @@ class NormActOp(Op):
     def __init__(self, z, kind: str, act: int, dsts: Sequence[Sl], res: Optional[Sl] = None, slope: float = 0.2,
                  bn: Optional[torch.nn.BatchNorm3d] = None, eps: float = 1e-5, name: str = "",
                  slope_param: Optional[torch.nn.Parameter] = None, gn: Optional[torch.nn.GroupNorm] = None,
-                 extra: Optional[Sl] = None, no_bwd: bool = False):
-        """``z``: a whole buffer or a channel slice (Sl) of one.  ``extra`` (backward): a gradient slice ADDED to dz -- the
+                 extra: Optional[Sl] = None, no_bwd: bool = False, act2: Optional[int] = None):
+        """``z``: a whole buffer or a channel slice (Sl) of one.  ``act2``: activation of the second destination when it differs
+        from the first's (UnetSkipConnectionBlock3d: LeakyReLU into the next convolution, ReLU into the skip half of a concat).  ``extra`` (backward): a gradient slice ADDED to dz -- the
         gradient reaching z through an identity skip connection.  ``no_bwd``: this op is a residual sum whose consumers'
         gradients have been redirected (ConvOp.dy_from, ``extra``, ResampleOp.dst_grad): nothing to do in backward."""
         assert kind in ("instance", "batch", "group", "none") and 1 <= len(dsts) <= 2
         self.zs: Sl = z if isinstance(z, Sl) else z.sl()
         z = self.zs.buf                         # the underlying buffer; self.zs.off / .c select the channels
         self.extra, self.no_bwd = extra, no_bwd
+        self.act2 = act if act2 is None else act2
         self.gn = gn                            # nn.GroupNorm (kind == "group"): affine, num_groups, eps
         self.acc_dz = False
         self.fwd_batch_stats = True             # kind == "batch": the last forward normalised with batch statistics
@@ -490,7 +492,7 @@ class NormActOp(Op):
         d.t1, d.t1_cstride, d.t1_coff, d.act1 = ptr(src(s1)), s1.buf.c, s1.off, self.act
         if len(self.dsts) > 1:
             s2 = self.dsts[1]
-            d.t2, d.t2_cstride, d.t2_coff, d.act2 = ptr(src(s2)), s2.buf.c, s2.off, self.act
+            d.t2, d.t2_cstride, d.t2_coff, d.act2 = ptr(src(s2)), s2.buf.c, s2.off, self.act2
         d.slope = self.slope
         if self.slope_param is not None:
             d.slope_dev = ptr(self.slope_param)
@@ -723,21 +725,31 @@ class DropoutOp(Op):
     atten_unet_model.py:1987).  The mask comes from torch's device generator (one rand launch on a [N, 512] tensor); identity
     in eval mode or with p == 0."""
 
-    def __init__(self, x: Buf, module: torch.nn.Dropout):
-        self.x, self.module = x, module
+    def __init__(self, x, module: torch.nn.Dropout):
+        """``x``: a buffer or a channel slice of one (UnetSkipConnectionBlock3d's Dropout(0.5) acts on the up half of a
+        concat buffer, unet_model.py:88)."""
+        self.xs: Sl = x if isinstance(x, Sl) else x.sl()
+        self.x, self.module = self.xs.buf, module
         self.mask: Optional[torch.Tensor] = None
+
+    def _view(self, t: torch.Tensor) -> torch.Tensor:
+        return t[:, self.xs.off:self.xs.off + self.xs.c]
 
     def fwd(self, training: bool) -> None:
         p = float(self.module.p)
         if not training or p == 0.0:
             self.mask = None
             return
-        self.mask = (torch.rand(self.x.t.shape, device=self.x.t.device) >= p).to(torch.bfloat16) / (1.0 - p)
-        self.x.t.mul_(self.mask)
+        v = self._view(self.x.t)
+        if p >= 1.0:
+            self.mask = torch.zeros(v.shape, dtype=torch.bfloat16, device=v.device)
+        else:
+            self.mask = (torch.rand(v.shape, device=v.device) >= p).to(torch.bfloat16) / (1.0 - p)
+        v.mul_(self.mask)
 
     def bwd(self) -> None:
         if self.mask is not None:
-            self.x.g.mul_(self.mask)
+            self._view(self.x.g).mul_(self.mask)
 
 
 class Tape:

@@ -261,6 +261,10 @@ class Unet3dTrainer(_CheckpointMixin):
         self.dev = dev
         if example_input is None:
             raise ValueError("example_input (a tensor of the training shape) is required to lay out the arenas")
+        if not model.default_family():
+            raise NotImplementedError("the fused train_unet step covers the reference configuration (norm_layer=nn.BatchNorm3d, "
+                                      "no dropout layer, unet/train_unet.py:59); other UnetGenerator3d families train through "
+                                      "module.forward / loss.backward() and any torch optimiser")
         eng = model.engine_for(example_input)
         self.eng = eng
         order = eng.grad_order()

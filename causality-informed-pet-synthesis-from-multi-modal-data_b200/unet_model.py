@@ -10,6 +10,11 @@ What is kept identical to the reference (the drop-in boundary):
     running-statistics updates, and the reference's in-place-activation aliasing (the skip half of every concat is
     ``LeakyReLU(x)``, ReLU'd again by the parent).
 
+Constructor families: the reference configuration (``norm_layer=nn.BatchNorm3d``, no dropout layer; train_unet.py:59) runs on
+the tuned engine ``_Engine``; ``norm_layer=nn.InstanceNorm3d`` (biased convolutions, unet_model.py:42-45), a
+``functools.partial`` of either norm (e.g. ``affine=True``) and ``use_dropout=True`` with more than five levels
+(unet_model.py:17, 87-88) run on the op tape (``_TapeEngine``).  Other norm classes raise ``NotImplementedError``.
+
 What differs: nothing is computed by the container modules.  ``UnetGenerator3d.forward`` hands the whole nest to an
 engine that runs fused CUDA kernels over channels-last bf16 activations (fp32 accumulation, fp32 master weights).
 """
@@ -38,31 +43,38 @@ class UnetSkipConnectionBlock3d(nn.Module):
         self.innermost = innermost
         self.outer_nc, self.inner_nc = outer_nc, inner_nc
         norm_cls = norm_layer.func if isinstance(norm_layer, functools.partial) else norm_layer
-        use_bias = norm_cls == nn.InstanceNorm3d
-        if use_bias or norm_cls != nn.BatchNorm3d:
-            raise NotImplementedError("petsyn UnetGenerator3d implements the reference's default norm_layer=nn.BatchNorm3d")
-        if use_dropout and not (outermost or innermost):
-            raise NotImplementedError("use_dropout=True is not implemented (unused by the reference configs)")
+        use_bias = norm_cls == nn.InstanceNorm3d                      # unet_model.py:42-45
+        if norm_cls not in (nn.BatchNorm3d, nn.InstanceNorm3d):
+            raise NotImplementedError("petsyn UnetGenerator3d implements norm_layer = nn.BatchNorm3d / nn.InstanceNorm3d "
+                                      "(or a functools.partial of either)")
+        self.use_bias = use_bias
+        # the default family (bias-free convolutions, plain BatchNorm3d, no dropout layer) runs on the tuned engine below;
+        # every other constructor family on the op tape (_TapeEngine)
+        self.default_family = norm_layer is nn.BatchNorm3d and not (use_dropout and not (outermost or innermost))
 
         # creation order == the reference's (downconv, downnorm, upnorm, up conv) so seeded inits coincide
-        downconv = nn.Conv3d(outer_nc, inner_nc, kernel_size=4, stride=2, padding=1, bias=False)
+        downconv = nn.Conv3d(outer_nc, inner_nc, kernel_size=4, stride=2, padding=1, bias=use_bias)
         downrelu = nn.LeakyReLU(LRELU_SLOPE, True)
         downnorm = norm_layer(inner_nc)
         uprelu = nn.ReLU(True)
         upnorm = norm_layer(outer_nc)
         upsample = nn.Upsample(scale_factor=2)
         up_in = inner_nc if innermost else inner_nc * 2
-        conv = nn.Conv3d(up_in, outer_nc, kernel_size=3, stride=1, padding=1, bias=False)
+        conv = nn.Conv3d(up_in, outer_nc, kernel_size=3, stride=1, padding=1, bias=use_bias)
+        dropout = None
         if outermost:
             layers = [downconv, submodule, uprelu, upsample, conv, nn.Tanh()]
         elif innermost:
             layers = [downrelu, downconv, uprelu, upsample, conv, upnorm]
         else:
             layers = [downrelu, downconv, downnorm, submodule, uprelu, upsample, conv, upnorm]
+            if use_dropout:                                           # unet_model.py:87-88
+                dropout = nn.Dropout(0.5)
+                layers.append(dropout)
         self.model = nn.Sequential(*layers)
         # handles for the engine (not registered twice: these are the same module objects)
         self._refs = dict(downconv=downconv, downnorm=None if (outermost or innermost) else downnorm, upconv=conv,
-                          upnorm=None if outermost else upnorm, submodule=submodule)
+                          upnorm=None if outermost else upnorm, submodule=submodule, dropout=dropout)
 
     def forward(self, x):
         raise RuntimeError("petsyn blocks are parameter containers; call UnetGenerator3d.forward on the whole generator")
@@ -97,11 +109,14 @@ class UnetGenerator3d(nn.Module):
             b = b._refs["submodule"]
         return out
 
-    def engine_for(self, x: torch.Tensor) -> "_Engine":
+    def default_family(self) -> bool:
+        return all(b.default_family for b in self.levels())
+
+    def engine_for(self, x: torch.Tensor):
         key = (tuple(x.shape), x.device.index)
         eng = self._engines.get(key)
         if eng is None:
-            eng = _Engine(self, tuple(x.shape), x.device)
+            eng = (_Engine if self.default_family() else _TapeEngine)(self, tuple(x.shape), x.device)
             self._engines[key] = eng
         return eng
 
@@ -112,6 +127,10 @@ class UnetGenerator3d(nn.Module):
             raise ValueError(f"expected input of shape [N, 1, D, H, W], got {tuple(input.shape)}")
         x = input.contiguous().float()
         eng = self.engine_for(x)
+        if isinstance(eng, _TapeEngine):
+            if torch.is_grad_enabled() and any(p.requires_grad for p in eng.params):
+                return _TapeUnetFn.apply(eng, x, *eng.params)
+            return eng.forward(x).clone()
         params = eng.param_list()
         if torch.is_grad_enabled() and any(p.requires_grad for p in params):
             return _UnetFn.apply(x, eng, *params)
@@ -420,6 +439,122 @@ class _Engine:
                 yield prev.bn.bias
         self.stem.wgrad(self.dz[0], gw(lv[0]._refs["downconv"]))
         yield lv[0]._refs["downconv"].weight
+
+
+# ======================================================================================================================
+# The other constructor families -- norm_layer = nn.InstanceNorm3d (convolutions then carry biases, unet_model.py:42-45)
+# or a functools.partial of either norm, and use_dropout=True with more than five levels (Dropout(0.5) after the up
+# normalisation of the 8*ngf blocks, unet_model.py:17, 87-88) -- are built on the op tape shared with the BMGAN and
+# AttenUNet mirrors (graph.py).  Same schedule as _Engine: the activated block input goes to two places in one launch
+# (LeakyReLU for the next down convolution, ReLU into the skip half of the parent's concat buffer: the reference's in-place
+# LeakyReLU followed by the parent's in-place ReLU, ReLU(LeakyReLU(x)) = ReLU(x)), torch.cat never runs, nn.Upsample is
+# folded into the 3x3x3 convolution's gather.  Dropout commutes with the parent's ReLU (its mask is >= 0).
+# ======================================================================================================================
+from types import SimpleNamespace
+
+from . import graph                                              # noqa: E402
+from ._cabi import check, lib, ptr, stream_ptr                  # noqa: E402
+from .bmgan_model import _EngineBase                             # noqa: E402
+from .graph import Buf, NormActOp, DropoutOp                     # noqa: E402
+
+
+class _TapeUnetFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, eng, x, *params):
+        y = eng.forward(x).clone()
+        eng.stamp(ctx, (x,))
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        ctx.eng.restore(ctx)
+        grads = ctx.eng.backward(dy.contiguous().float())
+        return (None, None, *grads)
+
+
+class _TapeEngine(_EngineBase):
+    CPAD = 16
+
+    def __init__(self, gen: UnetGenerator3d, shape, dev):
+        super().__init__(gen, dev)
+        n, _, D, H, W = shape
+        lv = gen.levels()
+        L = len(lv)
+        if D % (1 << L) or H % (1 << L) or W % (1 << L):
+            raise ValueError(f"spatial dims {D}x{H}x{W} must be divisible by {1 << L} (one halving per level)")
+        outer, inner = [b.outer_nc for b in lv], [b.inner_nc for b in lv]
+        for c in outer[1:] + inner:
+            if c % 8:
+                raise ValueError(f"channel widths must be multiples of 8 (got {c}); use ngf % 4 == 0")
+        self.shape, self.gen = shape, gen
+        t = self.tape
+        B = lambda i, c, name: Buf(n, D >> i, H >> i, W >> i, c, dev, name)
+        self.inp = B(0, self.CPAD, "input")
+        cat = [None] + [B(i, 2 * outer[i], f"cat{i}") for i in range(1, L)]        # [ReLU(up_i) | ReLU(x_i)]
+        # ---- down path ----
+        z = self._conv(self.inp.sl(), lv[0]._refs["downconv"], ksize=4, stride=2, pad=1, need_dx=False, name="down0").z
+        for i in range(1, L):
+            c = outer[i]
+            a = B(i, c, f"a{i}")
+            self._norm(z, lv[i - 1]._refs["downnorm"], ops.ACT_LRELU, [a.sl(), cat[i].sl(c, c)], act2=ops.ACT_RELU,
+                       name=f"down{i - 1}.norm")
+            z = self._conv(a.sl(), lv[i]._refs["downconv"], ksize=4, stride=2, pad=1, name=f"down{i}").z
+        r = B(L, inner[L - 1], "r")
+        t.add(NormActOp(z, "none", ops.ACT_RELU, [r.sl()], name="inner.relu"))
+        # ---- up path ----
+        src = r.sl()
+        for i in range(L - 1, 0, -1):
+            c = outer[i]
+            zu = self._conv(src, lv[i]._refs["upconv"], ksize=3, stride=1, pad=1, op=ops.OP_UPCONV, name=f"up{i}").z
+            self._norm(zu, lv[i]._refs["upnorm"], ops.ACT_RELU, [cat[i].sl(0, c)], name=f"up{i}.norm")
+            if lv[i]._refs["dropout"] is not None:
+                t.add(DropoutOp(cat[i].sl(0, c), lv[i]._refs["dropout"]))
+            src = cat[i].sl()
+        self.head = self._conv(src, lv[0]._refs["upconv"], ksize=3, stride=1, pad=1, op=ops.OP_UPCONV, act=ops.ACT_TANH,
+                               y_fp32=True, name="up0")
+        self.y = torch.zeros(n, 1, D, H, W, dtype=torch.float32, device=dev)
+        self._finish()
+        self.flops_executed = self.flops_algorithmic
+
+    def _norm(self, z, norm: Optional[nn.Module], act: int, dsts, act2: Optional[int] = None, name: str = "") -> None:
+        if norm is None:                                          # outermost / innermost down convolutions
+            self.tape.add(NormActOp(z, "none", act, dsts, act2=act2, slope=LRELU_SLOPE, name=name))
+            return
+        if isinstance(norm, nn.BatchNorm3d):
+            if norm.weight is None or norm.running_mean is None:
+                raise NotImplementedError("BatchNorm3d(affine=False) / (track_running_stats=False) are not implemented")
+            op = NormActOp(z, "batch", act, dsts, act2=act2, slope=LRELU_SLOPE, bn=norm, name=name)
+            self._bind += [(op, "grad_gamma", norm.weight), (op, "grad_beta", norm.bias)]
+        else:
+            if norm.track_running_stats:
+                raise NotImplementedError("InstanceNorm3d(track_running_stats=True) is not implemented")
+            if norm.affine:                                       # per-channel groups of one: GroupNorm(C, C) arithmetic
+                shim = SimpleNamespace(weight=norm.weight, bias=norm.bias, num_groups=norm.num_features, eps=norm.eps)
+                op = NormActOp(z, "group", act, dsts, act2=act2, slope=LRELU_SLOPE, gn=shim, name=name)
+                self._bind += [(op, "grad_gamma", norm.weight), (op, "grad_beta", norm.bias)]
+            else:
+                op = NormActOp(z, "instance", act, dsts, act2=act2, slope=LRELU_SLOPE, eps=norm.eps, name=name)
+        self.tape.add(op)
+
+    def param_list(self) -> List[torch.Tensor]:
+        return self.params
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        n, _, D, H, W = self.shape
+        self.generation += 1
+        check(lib.petsyn_concat_latent(ptr(x), ptr(x), ptr(self.inp.t), D * H * W, n, 0, self.CPAD, stream_ptr()),
+              "concat_latent")
+        self.tape.forward(self.training())
+        check(lib.petsyn_take_channel0(ptr(self.head.zf), ptr(self.y), self.y.numel(), self.head.cout, stream_ptr()),
+              "take_channel0")
+        return self.y
+
+    def backward(self, dy: torch.Tensor, out: Optional[Dict[int, torch.Tensor]] = None, on_ready=None):
+        grads = self.grad_slots(out)
+        check(lib.petsyn_put_channel0_grad(ptr(self.y), ptr(dy), ptr(self.head.zg), dy.numel(), self.head.cout, 1,
+                                           stream_ptr()), "put_channel0_grad")
+        self.run_backward(on_ready)
+        return [g.clone() for g in grads] if out is None else []
 
 
 class _timed:

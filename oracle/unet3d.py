@@ -162,16 +162,38 @@ def _batchnorm(x, sd, prefix, training, new_buffers):
     return (x - mean.view(shape)) * torch.rsqrt(var.view(shape) + BN_EPS) * w.view(shape) + b.view(shape)
 
 
+def _instancenorm(x, sd, prefix, eps=1e-5):
+    """nn.InstanceNorm3d forward (track_running_stats=False: the same in train and eval): per (sample, channel) statistics
+    over the volume, biased variance; affine only when the state dict carries weight / bias for it."""
+    mean = x.mean((2, 3, 4), keepdim=True)
+    var = x.var((2, 3, 4), unbiased=False, keepdim=True)
+    y = (x - mean) * torch.rsqrt(var + eps)
+    if prefix + "weight" in sd:
+        shape = (1, -1, 1, 1, 1)
+        y = y * sd[prefix + "weight"].view(shape) + sd[prefix + "bias"].view(shape)
+    return y
+
+
 def forward(x: torch.Tensor, sd: Dict[str, torch.Tensor], input_nc: int = 1, output_nc: int = 1,
             num_downs: int = 4, ngf: int = 64, training: bool = True,
-            new_buffers: Optional[Dict[str, torch.Tensor]] = None) -> torch.Tensor:
+            new_buffers: Optional[Dict[str, torch.Tensor]] = None, norm: str = "batch",
+            dropout_masks: Optional[Dict[int, torch.Tensor]] = None) -> torch.Tensor:
     """y = UnetGenerator3d(x) (unet_model.py:27-32, 93-99), out of place.
 
     The reference's in-place LeakyReLU/ReLU (unet_model.py:49,51) make the skip half of every
     concat ``LeakyReLU(x)`` rather than ``x``; that is reproduced here explicitly
     (``skip = a`` below), without mutating the caller's tensor.
+
+    ``norm="instance"``: norm_layer=nn.InstanceNorm3d, whose convolutions carry biases (unet_model.py:42-45; read from the
+    state dict when present).  ``dropout_masks``: {level index (0 = outermost): mask already scaled by 1 / (1 - p)} applied
+    where ``use_dropout=True`` puts nn.Dropout(0.5), after the up normalisation (unet_model.py:87-88); None = eval mode.
     """
     levels = level_specs(input_nc, output_nc, num_downs, ngf)
+
+    def _norm(t, prefix):
+        if norm == "instance":
+            return _instancenorm(t, sd, prefix)
+        return _batchnorm(t, sd, prefix, training, new_buffers)
 
     def block(i: int, xin: torch.Tensor) -> torch.Tensor:
         lv = levels[i]
@@ -180,16 +202,20 @@ def forward(x: torch.Tensor, sd: Dict[str, torch.Tensor], input_nc: int = 1, out
             a = xin                                                    # no downrelu (:62)
         else:
             a = F.leaky_relu(xin, LRELU_SLOPE)                         # downrelu (:49), in place in the reference
-        d = F.conv3d(a, sd[f"{lv.prefix}{sl['downconv']}.weight"], None, stride=2, padding=1)   # :47
+        d = F.conv3d(a, sd[f"{lv.prefix}{sl['downconv']}.weight"], sd.get(f"{lv.prefix}{sl['downconv']}.bias"), stride=2,
+                     padding=1)                                                                 # :47
         if sl["downnorm"] is not None:
-            d = _batchnorm(d, sd, f"{lv.prefix}{sl['downnorm']}.", training, new_buffers)      # :50
+            d = _norm(d, f"{lv.prefix}{sl['downnorm']}.")                                      # :50
         inner = d if lv.innermost else block(i + 1, d)
         r = F.relu(inner)                                              # uprelu (:51)
         u = F.interpolate(r, scale_factor=2, mode="nearest")           # nn.Upsample(scale_factor=2) (:59)
-        u = F.conv3d(u, sd[f"{lv.prefix}{sl['upconv']}.weight"], None, stride=1, padding=1)     # :60
+        u = F.conv3d(u, sd[f"{lv.prefix}{sl['upconv']}.weight"], sd.get(f"{lv.prefix}{sl['upconv']}.bias"), stride=1,
+                     padding=1)                                                                 # :60
         if lv.outermost:
             return torch.tanh(u)                                       # :64
-        u = _batchnorm(u, sd, f"{lv.prefix}{sl['upnorm']}.", training, new_buffers)            # :52
+        u = _norm(u, f"{lv.prefix}{sl['upnorm']}.")                                            # :52
+        if dropout_masks is not None and i in dropout_masks:
+            u = u * dropout_masks[i]                                   # nn.Dropout(0.5) (:88)
         return torch.cat([u, a], 1)                                    # :99 (skip is the activated input)
 
     return block(0, x)
@@ -222,3 +248,25 @@ def conv_flops(shape, num_downs: int = 4, ngf: int = 64, nc: int = 1) -> float:
         up_in = lv.inner_nc if lv.innermost else 2 * lv.inner_nc
         total += 2.0 * n * (vox // 8 ** i) * lv.outer_nc * up_in * 27         # k3 conv on the upsampled grid
     return total
+
+
+def randomize_(sd: Dict[str, torch.Tensor], seed: int) -> Dict[str, torch.Tensor]:
+    """Fill a state dict in place with values drawn BY KEY (one generator per key, seeded from the key's position), so
+    that the live reference (tests/golden/make_golden.py) and the module under test get the same parameters whatever
+    their constructors drew -- used for the constructor families whose default initialisation the oracle does not restate
+    (biased convolutions of the InstanceNorm3d family).  Convolution weights ~ N(0, 1/fan_in), biases and affine shifts
+    ~ 0.1 N(0, 1), affine scales ~ 1 + 0.1 N(0, 1); buffers are left alone."""
+    for i, (k, v) in enumerate(sd.items()):
+        if not v.dtype.is_floating_point or k.endswith("running_mean") or k.endswith("running_var"):
+            continue
+        g = torch.Generator().manual_seed(seed * 1000 + i)
+        r = torch.randn(v.shape, generator=g)
+        if v.dim() == 5:
+            r = r / math.sqrt(v[0].numel())
+        elif k.endswith(".weight"):
+            r = 1.0 + 0.1 * r
+        else:
+            r = 0.1 * r
+        with torch.no_grad():
+            v.copy_(r)
+    return sd

@@ -81,5 +81,49 @@ def main():
         print(f"{name}: loss={out['loss']:.6f} gradnorm={out['grad_norm_total']:.5f} -> {os.path.getsize(path)/1e3:.0f} kB")
 
 
+# Other constructor families (unet_model.py:42-45 biased convolutions under InstanceNorm3d, :17 / :87-88 Dropout(0.5) with more
+# than five levels).  Parameters are drawn by key (oracle.unet3d.randomize_), so the fixture does not depend on constructor
+# RNG order; eval() mode where a Dropout layer exists (its mask is not reproducible across implementations; InstanceNorm3d
+# without running statistics behaves the same in both modes).
+FAMILIES = {
+    # name: (norm, affine, use_dropout, num_downs, ngf, shape, seed, train_mode)
+    "unet3d_instnorm_drop_nd6_1x64x64x64": ("instance", False, True, 6, 8, (1, 64, 64, 64), 31, False),
+    "unet3d_instaffine_nd5_2x32x32x32": ("instance", True, False, 5, 8, (2, 32, 32, 32), 32, True),
+    "unet3d_batchnorm_drop_nd6_1x64x64x64": ("batch", True, True, 6, 8, (1, 64, 64, 64), 33, False),
+}
+
+
+def families():
+    import functools
+    sys.path.insert(0, REF)
+    sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+    from unet.utils.unet_model import UnetGenerator3d  # the reference, unmodified
+    from oracle import unet3d as O
+    torch.set_num_threads(os.cpu_count() or 1)
+    for name, (norm, affine, drop, nd, ngf, shape, seed, train) in FAMILIES.items():
+        if norm == "instance":
+            layer = functools.partial(torch.nn.InstanceNorm3d, affine=True) if affine else torch.nn.InstanceNorm3d
+        else:
+            layer = torch.nn.BatchNorm3d
+        model = UnetGenerator3d(1, 1, num_downs=nd, ngf=ngf, norm_layer=layer, use_dropout=drop)
+        O.randomize_(model.state_dict(), seed)
+        model.train(train)
+        t1, pet = synth_pair(shape, seed)
+        y = model(t1.clone())
+        loss = torch.nn.L1Loss()(y, pet)
+        loss.backward()
+        out = {"loss": np.float64(loss.item()), "shape": np.array(shape), "ngf": np.int64(ngf), "seed": np.int64(seed),
+               "num_downs": np.int64(nd), "keys": np.array(list(model.state_dict().keys()))}
+        for k, p in model.named_parameters():
+            out["gradnorm/" + k] = np.float64(p.grad.double().norm().item())
+        out["output_sample"] = y.detach().numpy()[:, :, ::2, ::2, ::2].copy()
+        path = os.path.join(HERE, name + ".npz")
+        np.savez_compressed(path, **out)
+        print(f"{name}: loss={out['loss']:.6f} -> {os.path.getsize(path)/1e3:.0f} kB")
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "families":
+        families()
+    else:
+        main()

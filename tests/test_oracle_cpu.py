@@ -29,7 +29,7 @@ def test_oracle_matches_golden(name):
             assert abs(float(v.double().abs().sum()) - float(gold["wsum/" + k])) <= 1e-6 * max(1.0, float(gold["wsum/" + k])), k
     t1, pet = synth_pair(shape, seed)
     loss, y, grads, bufs = O.train_step(t1, pet, sd, num_downs=4, ngf=ngf)
-    assert abs(float(loss) - float(gold["loss"])) < 1e-6
+    assert abs(loss.item() - float(gold["loss"])) < 1e-6
     assert np.abs(y.numpy() - gold["output"]).max() < 1e-5
     for k, g in grads.items():
         ref = float(gold["gradnorm/" + k])
@@ -117,7 +117,7 @@ def test_atten_unet_oracle_matches_golden(name, cfg_name):
     if not cfg["with_conditioning"]:
         ctx = None                                                 # AttentionBlock family: no context (:1822-1823)
     loss, y, grads = OA.train_step(x, ctx, tgt, sd, cfg)
-    assert abs(float(loss) - float(gold["loss"])) < 1e-6
+    assert abs(loss.item() - float(gold["loss"])) < 1e-6
     assert np.abs(y.numpy()[:, :, ::st, ::st, ::st] - gold["output"]).max() < 1e-5
     tot = 0.0
     for k, g in grads.items():
@@ -214,3 +214,57 @@ def test_bmgan_oracle_matches_live_reference():
     vol = torch.rand(1, 1, 128, 128, 128, generator=g)
     (mr, lr_), (mo, lo) = re_(vol), oe(vol)
     assert (mr - mo).abs().max().item() < 1e-5 and (lr_ - lo).abs().max().item() < 1e-5
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# UnetGenerator3d's other constructor families: the oracle's norm="instance" / biased convolutions / dropout-mask arguments
+# against the fixtures generated from the live reference class (tests/golden/make_golden.py families).
+# ---------------------------------------------------------------------------------------------------------------------
+UNET_FAMILIES = {
+    "unet3d_instnorm_drop_nd6_1x64x64x64": ("instance", False, True),
+    "unet3d_instaffine_nd5_2x32x32x32": ("instance", True, False),
+    "unet3d_batchnorm_drop_nd6_1x64x64x64": ("batch", True, True),
+}
+
+
+def unet_family_state_dict(keys, nd, ngf, seed):
+    """Zero tensors of the right shapes under the reference's keys (shapes follow from the key), filled by key."""
+    levels = O.level_specs(1, 1, nd, ngf)
+    sd = {}
+    for k in keys:
+        lv = max((l for l in levels if k.startswith(l.prefix)), key=lambda l: len(l.prefix))
+        slot, leaf = k[len(lv.prefix):].split(".", 1)
+        sl = O._slots(lv)
+        if int(slot) == sl["downconv"]:
+            shape = (lv.inner_nc, lv.outer_nc, 4, 4, 4) if leaf == "weight" else (lv.inner_nc,)
+        elif int(slot) == sl["upconv"]:
+            shape = (lv.outer_nc, lv.inner_nc * (1 if lv.innermost else 2), 3, 3, 3) if leaf == "weight" else (lv.outer_nc,)
+        else:
+            c = lv.inner_nc if int(slot) == sl["downnorm"] else lv.outer_nc
+            shape = () if leaf == "num_batches_tracked" else (c,)
+        if leaf == "num_batches_tracked":
+            sd[k] = torch.zeros((), dtype=torch.long)
+        else:
+            sd[k] = torch.ones(shape) if leaf == "running_var" else torch.zeros(shape)
+    return O.randomize_(sd, seed)
+
+
+@pytest.mark.parametrize("name", sorted(UNET_FAMILIES))
+def test_unet_family_oracle_matches_golden(name):
+    norm, affine, drop = UNET_FAMILIES[name]
+    gold = np.load(os.path.join(GOLD, name + ".npz"))
+    shape, seed, nd, ngf = tuple(int(v) for v in gold["shape"]), int(gold["seed"]), int(gold["num_downs"]), int(gold["ngf"])
+    sd = unet_family_state_dict([str(k) for k in gold["keys"]], nd, ngf, seed)
+    t1, pet = synth_pair(shape, seed)
+    params = {k: v.requires_grad_(True) for k, v in sd.items()
+              if v.dtype.is_floating_point and "running_" not in k}
+    full = dict(sd); full.update(params)
+    train = name == "unet3d_instaffine_nd5_2x32x32x32"
+    y = O.forward(t1, full, num_downs=nd, ngf=ngf, training=train, norm=norm)
+    loss = (y - pet).abs().mean()
+    loss.backward()
+    assert abs(loss.item() - float(gold["loss"])) < 1e-6
+    assert np.abs(y.detach().numpy()[:, :, ::2, ::2, ::2] - gold["output_sample"]).max() < 1e-5
+    for k, p in params.items():
+        ref = float(gold["gradnorm/" + k])
+        assert abs(p.grad.double().norm().item() - ref) <= 1e-4 * ref + 1e-7, k

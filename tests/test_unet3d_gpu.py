@@ -192,3 +192,128 @@ def test_trainer_eager_and_graph_match_autograd_adam(petsyn):
         assert (se[k] - ref).abs().max().item() <= tol, k
         assert (sg[k] - se[k]).abs().max().item() <= tol, k
     assert int(sg["model.model.1.model.2.num_batches_tracked"]) == steps   # capture() restored the BN counters
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# The other constructor families (unet_model.py:42-45 InstanceNorm3d => biased convolutions; :17, :87-88 Dropout(0.5) with
+# more than five levels) against fixtures from the live reference class and, with the dropout masks the CUDA path drew,
+# against the oracle in training mode.
+# ---------------------------------------------------------------------------------------------------------------------
+def _family_model(petsyn, norm, affine, drop, nd, ngf, seed):
+    import functools
+    if norm == "instance":
+        layer = functools.partial(torch.nn.InstanceNorm3d, affine=True) if affine else torch.nn.InstanceNorm3d
+    else:
+        layer = torch.nn.BatchNorm3d
+    m = petsyn.UnetGenerator3d(1, 1, num_downs=nd, ngf=ngf, norm_layer=layer, use_dropout=drop)
+    O.randomize_(m.state_dict(), seed)
+    return m
+
+
+FAMILIES = {
+    "unet3d_instnorm_drop_nd6_1x64x64x64": ("instance", False, True, False),
+    "unet3d_instaffine_nd5_2x32x32x32": ("instance", True, False, True),
+    "unet3d_batchnorm_drop_nd6_1x64x64x64": ("batch", True, True, False),
+}
+
+
+def _check_grads(model, grads_ref, gradnorm_ref=None):
+    tot = tot_ref = 0.0
+    for k, p in model.named_parameters():
+        assert p.grad is not None, k
+        gn = p.grad.double().norm().item()
+        ref = grads_ref[k].double().norm().item() if gradnorm_ref is None else float(gradnorm_ref["gradnorm/" + k])
+        tot += gn ** 2
+        tot_ref += ref ** 2
+        # a convolution bias in front of a normalisation has a mathematically zero gradient (the norm removes the mean):
+        # both sides hold rounding noise there
+        if ref > 1e-3 * max(1.0, tot_ref ** 0.5):
+            assert abs(gn - ref) <= 8e-2 * ref + 1e-5, (k, gn, ref)
+            if grads_ref is not None:
+                go = grads_ref[k].double().flatten()
+                cos = torch.dot(p.grad.double().cpu().flatten(), go) / (gn * go.norm().item() + 1e-30)
+                assert cos.item() > 0.97, (k, cos.item())
+    assert abs(tot ** 0.5 - tot_ref ** 0.5) <= 3e-2 * tot_ref ** 0.5, (tot ** 0.5, tot_ref ** 0.5)
+
+
+@pytest.mark.parametrize("name", sorted(FAMILIES))
+def test_constructor_families_match_golden(name, petsyn):
+    norm, affine, drop, train = FAMILIES[name]
+    gold = np.load(os.path.join(GOLD, name + ".npz"))
+    shape, seed, nd, ngf = tuple(int(v) for v in gold["shape"]), int(gold["seed"]), int(gold["num_downs"]), int(gold["ngf"])
+    model = _family_model(petsyn, norm, affine, drop, nd, ngf, seed)
+    assert list(model.state_dict().keys()) == [str(k) for k in gold["keys"]]       # the reference's keys, in its order
+    assert not model.default_family()
+    t1, pet = synth_pair(shape, seed)
+    model = model.cuda().train(train)
+    if norm == "batch" and not train:
+        # eval() BatchNorm is inference only (the backward kernels implement batch statistics): forward against the fixture
+        with torch.no_grad():
+            y = model(t1.cuda())
+        assert np.abs(y.cpu().numpy()[:, :, ::2, ::2, ::2] - gold["output_sample"]).max() <= 5e-2
+        with pytest.raises(NotImplementedError):
+            torch.nn.functional.l1_loss(model(t1.cuda()), pet.cuda()).backward()
+        return
+    y = model(t1.cuda())
+    loss = torch.nn.functional.l1_loss(y, pet.cuda())
+    loss.backward()
+    torch.cuda.synchronize()
+    err = np.abs(y.detach().cpu().numpy()[:, :, ::2, ::2, ::2] - gold["output_sample"])
+    # the coarsest normalisations of these small cases see 8 voxels per (sample, channel): bf16 rounding of the conv output is
+    # amplified by the division by a tiny standard deviation, hence a mean bound twice the default family's
+    assert err.max() <= 5e-2 and err.mean() <= 6e-3, (err.max(), err.mean())
+    assert abs(loss.item() - float(gold["loss"])) <= LOSS_ABS
+    sd_cpu = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}
+    params = {k: v.requires_grad_(True) for k, v in sd_cpu.items() if v.dtype.is_floating_point and "running_" not in k}
+    full = dict(sd_cpu); full.update(params)
+    yo = O.forward(t1, full, num_downs=nd, ngf=ngf, training=train, norm=norm)
+    (yo - pet).abs().mean().backward()
+    _check_grads(model, {k: p.grad for k, p in params.items()}, gold)
+
+
+@pytest.mark.parametrize("norm", ["instance", "batch"])
+def test_dropout_training_step_matches_oracle_with_the_same_masks(norm, petsyn):
+    nd, ngf, shape, seed = 6, 8, (2, 64, 64, 64), 41
+    model = _family_model(petsyn, norm, True, True, nd, ngf, seed).cuda().train()
+    t1, pet = synth_pair(shape, seed)
+    y = model(t1.cuda())
+    loss = torch.nn.functional.mse_loss(y, pet.cuda())
+    loss.backward()
+    torch.cuda.synchronize()
+    eng = model.engine_for(t1.cuda())
+    from petsyn_b200.graph import DropoutOp
+    drops = [op for op in eng.tape.ops if isinstance(op, DropoutOp)]
+    assert len(drops) == nd - 5 and all(op.mask is not None for op in drops)
+    masks = {}
+    for op in drops:                      # the op acts on the up half of cat_i: level i = log2(D / buffer depth)
+        b = op.x
+        lvl = int(np.log2(shape[1] // b.d))
+        m = op.mask.float().view(b.n, b.d, b.h, b.w, -1).permute(0, 4, 1, 2, 3).cpu()
+        frac = (m == 0).float().mean().item()
+        assert 0.4 < frac < 0.6 and set(m.unique().tolist()) <= {0.0, 2.0}
+        masks[lvl] = m
+    sd_cpu = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}
+    if norm == "batch":                   # the forward above already moved the running statistics: oracle starts from the initial ones
+        for k in sd_cpu:
+            if k.endswith("running_mean"): sd_cpu[k].zero_()
+            if k.endswith("running_var"): sd_cpu[k].fill_(1.0)
+    params = {k: v.requires_grad_(True) for k, v in sd_cpu.items() if v.dtype.is_floating_point and "running_" not in k}
+    full = dict(sd_cpu); full.update(params)
+    bufs = {}
+    yo = O.forward(t1, full, num_downs=nd, ngf=ngf, training=True, norm=norm, dropout_masks=masks, new_buffers=bufs)
+    lo = torch.nn.functional.mse_loss(yo, pet)
+    lo.backward()
+    err = (y.detach().cpu() - yo.detach()).abs()
+    assert err.max().item() <= 5e-2 and err.mean().item() <= 6e-3, (err.max().item(), err.mean().item())
+    assert abs(loss.item() - lo.item()) <= LOSS_ABS
+    _check_grads(model, {k: p.grad for k, p in params.items()})
+    if norm == "batch":
+        sd = model.state_dict()
+        for k, v in bufs.items():
+            if "running" in k:
+                assert (sd[k].cpu() - v).abs().max().item() <= 2e-2 * (v.abs().max().item() + 1e-3), k
+    # eval(): the Dropout layers are the identity
+    model.eval()
+    with torch.no_grad():
+        model(t1.cuda())
+    assert all(op.mask is None for op in drops)
