@@ -547,6 +547,70 @@ class BmganTrainer:
                 if hasattr(op, "_ver"):
                     op._ver = None
 
+    # ------------------------------------------------------------------------------------------------ checkpoints
+    def _nets(self):
+        """(checkpoint key, optimizer key, module, engine, arena, m, v, optimiser steps taken) per network (train_bmgan.py:296-302)."""
+        steps = int(self.step_dev.item())
+        out = [("generator", "g_optimizer", self.gen, self.geng, self.garena, self.gm, self.gv, steps),
+               ("discriminator", "d_optimizer", self.disc, self.deng, self.darena, self.dm, self.dv,
+                steps if self.step_discriminator else 0)]
+        if self.enc is not None:
+            out.append(("encoder", "e_optimizer", self.enc, self.eeng, self.earena, self.em, self.ev, steps))
+        return out
+
+    @staticmethod
+    def _moment_views(module, arena, m, v):
+        off = {id(p): o for p, o in zip(arena.params, arena.offsets)}
+        ps = list(module.parameters())
+        return ps, [m[off[id(p)]:off[id(p)] + p.numel()].view_as(p) for p in ps], \
+            [v[off[id(p)]:off[id(p)] + p.numel()].view_as(p) for p in ps]
+
+    def checkpoint(self, epoch: int, ddp_prefix: Optional[bool] = None) -> dict:
+        """The dictionary train_bmgan.py:296-302 saves every ``save_every`` epochs and :96-108 resumes from: ``{'generator',
+        'discriminator', 'encoder', 'epoch', 'g_optimizer', 'd_optimizer', 'e_optimizer'}``, the optimizer entries being
+        ``torch.optim.Adam.state_dict()`` s over ``module.parameters()``.  The reference never steps ``d_optimizer``
+        (SURVEY 9 Q4), so its state is empty unless ``step_discriminator`` is set.  ``ddp_prefix`` as in
+        ``Unet3dTrainer.checkpoint`` (train_bmgan.py:72-75 wraps the three networks in DistributedDataParallel)."""
+        if ddp_prefix is None:
+            ddp_prefix = self.world > 1
+        pre = (lambda sd: {"module." + k: v for k, v in sd.items()}) if ddp_prefix else (lambda sd: dict(sd))
+        out = {"epoch": epoch}
+        for key, okey, module, _, arena, m, v, steps in self._nets():
+            out[key] = pre(module.state_dict())
+            ps, mv, vv = self._moment_views(module, arena, m, v)
+            out[okey] = adam_state_dict(ps, mv, vv, steps, self.lr, self.betas, self.eps)
+        return out
+
+    def save_checkpoint(self, path: str, epoch: int, ddp_prefix: Optional[bool] = None) -> None:
+        torch.save(self.checkpoint(epoch, ddp_prefix=ddp_prefix), path)
+
+    def load_checkpoint(self, ckpt) -> int:
+        """``ckpt``: a path or a loaded dictionary in the layout above (either key form; ``best.ckpt``, train_bmgan.py:282-288,
+        carries no optimizer entries: the moments are then left as they are).  Returns the epoch to resume from (:100)."""
+        if isinstance(ckpt, (str, bytes)) or hasattr(ckpt, "__fspath__"):
+            ckpt = torch.load(ckpt, map_location=self.dev, weights_only=False)
+        strip = lambda sd: {(k[7:] if k.startswith("module.") else k): v for k, v in sd.items()}
+        steps = None
+        for key, okey, module, eng, arena, m, v, _ in self._nets():
+            module.load_state_dict(strip(ckpt[key]))                 # parameters are views of the arena: copied in place
+            if okey in ckpt:
+                g = ckpt[okey]["param_groups"][0]
+                hyper = (float(g["lr"]), tuple(g["betas"]), float(g["eps"]))
+                if self.graph is not None and hyper != (self.lr, tuple(self.betas), self.eps):
+                    raise RuntimeError("lr / betas / eps are baked into the captured step: load the checkpoint before capture()")
+                _, mv, vv = self._moment_views(module, arena, m, v)
+                n = read_adam_state_dict(ckpt[okey], mv, vv)
+                if okey == "g_optimizer":
+                    steps = n
+                    self.lr, self.betas, self.eps = hyper
+        if steps is not None:
+            self.step_dev.fill_(steps)
+            self.step_count = steps
+        self._dirty()
+        for eng in (self.deng,) + ((self.eeng,) if self.enc is not None else ()):
+            eng.mark_weights_dirty()
+        return int(ckpt["epoch"]) + 1
+
     def step(self, t1: torch.Tensor, pet: torch.Tensor, z: torch.Tensor):
         """Returns the device tensors (adv, l1, d_fake, d_real) of this rank's micro-batch."""
         self.step_count += 1

@@ -346,3 +346,52 @@ def test_bmgan_trainer_step(petsyn):
                 assert abs(x - y) <= 2e-2, (results[0], results[1])
             else:
                 assert abs(x - y) <= 1.0 * max(abs(x), abs(y)) + 5e-2, (results[0], results[1])
+
+
+def test_bmgan_checkpoint_round_trip_in_the_reference_format(petsyn):
+    """train_bmgan.py:296-302 (save) / :96-108 (resume): {'generator', 'discriminator', 'encoder', 'epoch', 'g_optimizer',
+    'd_optimizer', 'e_optimizer'}; the optimizer entries load into torch.optim.Adam over module.parameters() as they are."""
+    import io
+    from petsyn_b200.train import BmganTrainer
+    shape, seed = (1, 96, 96, 96), 7              # the encoder must reduce it to 2x2x2 (nn.Linear(128*8, 8), bmgan_model.py:124)
+    t1, pet, z = (t.cuda() for t in synth(shape, seed))
+
+    def make(s):
+        torch.manual_seed(s)
+        gen, disc = petsyn.dense_unet_generator(**SMALL).cuda().train(), petsyn.patch_discriminator().cuda().train()
+        enc = petsyn.ResNet_encoder().cuda().train()
+        return gen, disc, enc, BmganTrainer(gen, disc, enc=enc, example_input=t1)
+
+    g1, d1, e1, tr1 = make(seed)
+    for _ in range(2):
+        tr1.step(t1, pet, z)
+    buf = io.BytesIO()
+    torch.save(tr1.checkpoint(epoch=4), buf)
+    ck = torch.load(io.BytesIO(buf.getvalue()), map_location="cuda", weights_only=False)
+    assert set(ck) == {"generator", "discriminator", "encoder", "epoch", "g_optimizer", "d_optimizer", "e_optimizer"}
+    for key, mod in (("generator", g1), ("discriminator", d1), ("encoder", e1)):
+        assert list(ck[key]) == list(mod.state_dict())
+    for okey, mod, stepped in (("g_optimizer", g1, True), ("d_optimizer", d1, False), ("e_optimizer", e1, True)):
+        opt = torch.optim.Adam(mod.parameters(), lr=1.0)
+        opt.load_state_dict(ck[okey])
+        assert opt.param_groups[0]["lr"] == 2e-4
+        if stepped:
+            assert len(opt.state) == len(list(mod.parameters())) and all(float(s["step"]) == 2.0 for s in opt.state.values())
+        else:
+            assert len(opt.state) == 0                     # the reference never steps d_optimizer (SURVEY 9 Q4)
+    ck_ddp = tr1.checkpoint(epoch=4, ddp_prefix=True)
+    assert list(ck_ddp["generator"]) == ["module." + k for k in g1.state_dict()]
+    ck["generator"] = ck_ddp["generator"]
+    g2, d2, e2, tr2 = make(seed + 1)
+    assert tr2.load_checkpoint(ck) == 5
+    for a, b in ((g1, g2), (d1, d2), (e1, e2)):
+        for (k, va), vb in zip(a.state_dict().items(), b.state_dict().values()):
+            assert torch.equal(va, vb), k
+    assert torch.equal(tr1.gm, tr2.gm) and torch.equal(tr1.gv, tr2.gv) and torch.equal(tr1.em, tr2.em)
+    assert int(tr2.step_dev.item()) == 2 and tr2.step_count == 2
+    la, lb = [v.item() for v in tr1.step(t1, pet, z)], [v.item() for v in tr2.step(t1, pet, z)]
+    assert abs(la[1] - lb[1]) <= 2e-2                     # L1 term: same trajectory (the LSGAN terms are noise-dominated, see above)
+    # best.ckpt (train_bmgan.py:282-288) has no optimizer entries
+    best = {k: v for k, v in ck.items() if not k.endswith("_optimizer")}
+    best["l1_loss"] = 0.5
+    assert tr2.load_checkpoint(best) == 5
