@@ -9,9 +9,9 @@ Kept identical to the reference: the constructor signature and its ``ValueError`
 
 Implemented configuration families: ``resblock_updown`` True (``training.json``) or False (conv-form resampling, the
 reference's own smoke block); ``with_conditioning=True`` (attention levels use cross-attention transformer blocks with one
-transformer layer; heads of 8, 16 or 32 channels) or False (``AttentionBlock`` with 32-channel heads, no context); any
-number of levels / ResnetBlocks per level.  Class embeddings (broken in the reference itself), several
-transformer layers and attention dropout raise ``NotImplementedError``.
+or more transformer layers; heads of 8, 16 or 32 channels) or False (``AttentionBlock`` with 32-channel heads, no context); any
+number of levels / ResnetBlocks per level.  Class embeddings (broken in the reference itself) and
+attention dropout raise ``NotImplementedError``.
 
 Execution: a static op tape (``graph.py``).  GroupNorm+SiLU, residual sums and skip concatenation are fused
 bandwidth kernels over channels-last bf16 buffers; every Conv3d (3^3, 1^3, the nearest-x2 + 3^3 of the up-sampling
@@ -242,8 +242,8 @@ class AttenUNet(nn.Module):
                              "as `num_channels`.")
         if spatial_dims != 3 or in_channels != 1 or out_channels != 1:
             raise NotImplementedError("petsyn AttenUNet implements the reference use: 3-D, one channel in, one out")
-        if transformer_num_layers != 1 or num_class_embeds is not None or dropout_cattn != 0.0:
-            raise NotImplementedError("petsyn AttenUNet implements transformer_num_layers=1, no class embeddings / dropout")
+        if transformer_num_layers < 1 or num_class_embeds is not None or dropout_cattn != 0.0:
+            raise NotImplementedError("petsyn AttenUNet implements no class embeddings / attention dropout")
         for lvl, a in enumerate(list(attention_levels) + [True]):          # the middle block always attends
             hc = num_head_channels[min(lvl, n - 1)]
             if a and hc not in (8, 16, 32):
@@ -577,19 +577,30 @@ class _AttenEngine(_EngineBase):
         return out
 
     def _transformer(self, st, x: Sl, lvl: int, dst: Optional[Sl], name: str) -> Sl:
-        """SpatialTransformer.forward (atten_unet_model.py:315-343) with one BasicTransformerBlock (:225-235)."""
+        """SpatialTransformer.forward (atten_unet_model.py:315-343): GroupNorm, proj_in, the BasicTransformerBlocks, proj_out, + x."""
         if isinstance(st, AttentionBlock):
             return self._attention_block(st, x, dst, name)
         t, dev, n = self.tape, self.dev, self.n
         c = x.c
         xb = x.buf
         L = xb.d * xb.h * xb.w
-        blk: BasicTransformerBlock = st.transformer_blocks[0]
-        heads = blk.attn1.num_heads
+        heads = st.transformer_blocks[0].attn1.num_heads
         T = lambda ch_, nm: Buf(n, xb.d, xb.h, xb.w, ch_, dev, f"{name}.{nm}")
         g = T(c, "gn")
         self._gn_act(x, st.norm, ops.ACT_NONE, g)
         t0 = self._conv(g.sl(), st.proj_in.conv, ksize=1, stride=1, pad=0, name=name + ".proj_in").z
+        for li, blk in enumerate(st.transformer_blocks):           # in sequence (:336-337)
+            t0 = self._transformer_layer(blk, t0, heads, L, T, name if li == 0 else f"{name}.l{li}", "" if li == 0 else f"l{li}.")
+        t3 = t0
+        po = self._conv(t3.sl(), st.proj_out.conv, ksize=1, stride=1, pad=0, name=name + ".proj_out").z
+        out = dst if dst is not None else T(c, "out").sl()
+        t.add(NormActOp(po, "none", ops.ACT_NONE, [out], res=x))
+        return out
+
+    def _transformer_layer(self, blk: BasicTransformerBlock, t0: Buf, heads: int, L: int, T0, name: str, tag: str) -> Buf:
+        """One BasicTransformerBlock (:225-235) on the token buffer ``t0``; returns the buffer holding its output."""
+        t = self.tape
+        T = lambda ch_, nm: T0(ch_, tag + nm)
         inner = t0.c
         n1 = T(inner, "n1")
         ln1 = LayerNormOp(t0, n1, blk.norm1)
@@ -632,10 +643,7 @@ class _AttenEngine(_EngineBase):
         f2 = self._linear(gg.sl(), blk.ff.linear2, name + ".ff2").z
         t3 = T(inner, "t3")
         t.add(NormActOp(f2, "none", ops.ACT_NONE, [t3.sl()], res=t1.sl()))
-        po = self._conv(t3.sl(), st.proj_out.conv, ksize=1, stride=1, pad=0, name=name + ".proj_out").z
-        out = dst if dst is not None else T(c, "out").sl()
-        t.add(NormActOp(po, "none", ops.ACT_NONE, [out], res=x))
-        return out
+        return t3
 
     # ------------------------------------------------------------------------------------------------ run
     def grad_slots(self, out=None):

@@ -32,6 +32,10 @@ TRAINING_JSON = dict(  # unet/config/training.json:8-38 (atten_unet_def) + cross
 
 # with_conditioning = False: the Attn{Down,Mid,Up}Block family (:751-852, :970-1029, :1190-1293) -- AttentionBlock (:346-461) instead
 # of the SpatialTransformer, no context
+# transformer_num_layers = 2: two BasicTransformerBlocks chained inside every SpatialTransformer (:300-301, :336-337)
+TWO_LAYER_CFG = dict(spatial_dims=3, in_channels=1, out_channels=1, num_res_blocks=1, num_channels=(32, 32, 64),
+                     attention_levels=(False, True, True), norm_num_groups=16, norm_eps=1e-6, resblock_updown=True,
+                     num_head_channels=(0, 32, 32), with_conditioning=True, transformer_num_layers=2, cross_attention_dim=5)
 ATTN_ONLY_CFG = dict(spatial_dims=3, in_channels=1, out_channels=1, num_res_blocks=1, num_channels=(32, 32, 64),
                      attention_levels=(False, True, True), norm_num_groups=16, norm_eps=1e-6, resblock_updown=True,
                      num_head_channels=32, with_conditioning=False, cross_attention_dim=None)
@@ -117,18 +121,22 @@ def attention_block(sd, pre, x, groups, eps, heads):
 
 
 def transformer(sd, pre, x, ctx, groups, eps, heads):
-    """SpatialTransformer.forward (:315-343) with one BasicTransformerBlock (:225-235)."""
+    """SpatialTransformer.forward (:315-343): the BasicTransformerBlocks (:225-235) in sequence (:336-337), as many as the
+    state dict holds (transformer_num_layers)."""
     n, c, d, h, w = x.shape
     res = x
     t = _conv(sd, pre + "proj_in.", _gn(sd, pre + "norm.", x, groups, eps), 0)
     t = t.permute(0, 2, 3, 4, 1).reshape(n, d * h * w, -1)
-    b = pre + "transformer_blocks.0."
-    ln = lambda name, v: F.layer_norm(v, (v.shape[-1],), sd[b + name + ".weight"], sd[b + name + ".bias"])
-    t = cross_attention(sd, b + "attn1.", ln("norm1", t), ln("norm1", t), heads) + t
-    t = cross_attention(sd, b + "attn2.", ln("norm2", t), ctx, heads) + t
-    y = F.linear(ln("norm3", t), sd[b + "ff.linear1.weight"], sd[b + "ff.linear1.bias"])
-    a, gate = y.chunk(2, dim=-1)
-    t = F.linear(a * F.gelu(gate), sd[b + "ff.linear2.weight"], sd[b + "ff.linear2.bias"]) + t
+    layer = 0
+    while pre + f"transformer_blocks.{layer}.norm1.weight" in sd:
+        b = pre + f"transformer_blocks.{layer}."
+        ln = lambda name, v: F.layer_norm(v, (v.shape[-1],), sd[b + name + ".weight"], sd[b + name + ".bias"])
+        t = cross_attention(sd, b + "attn1.", ln("norm1", t), ln("norm1", t), heads) + t
+        t = cross_attention(sd, b + "attn2.", ln("norm2", t), ctx, heads) + t
+        y = F.linear(ln("norm3", t), sd[b + "ff.linear1.weight"], sd[b + "ff.linear1.bias"])
+        a, gate = y.chunk(2, dim=-1)
+        t = F.linear(a * F.gelu(gate), sd[b + "ff.linear2.weight"], sd[b + "ff.linear2.bias"]) + t
+        layer += 1
     t = t.reshape(n, d, h, w, -1).permute(0, 4, 1, 2, 3).contiguous()
     return _conv(sd, pre + "proj_out.", t, 0) + res
 
@@ -224,15 +232,16 @@ def param_shapes(cfg=TRAINING_JSON) -> Dict[str, tuple]:
     def transformer(pre, c):
         norm(pre + "norm.", c)
         conv(pre + "proj_in.", c, c, 1)
-        b = pre + "transformer_blocks.0."
-        for a, kv in (("attn1.", c), ("attn2.", cdim)):
-            out[b + a + "to_q.weight"], out[b + a + "to_k.weight"], out[b + a + "to_v.weight"] = (c, c), (c, kv), (c, kv)
-            out[b + a + "to_out.0.weight"], out[b + a + "to_out.0.bias"] = (c, c), (c,)
-            if a == "attn1.":
-                out[b + "ff.linear1.weight"], out[b + "ff.linear1.bias"] = (8 * c, c), (8 * c,)
-                out[b + "ff.linear2.weight"], out[b + "ff.linear2.bias"] = (c, 4 * c), (c,)
-        for nm in ("norm1.", "norm2.", "norm3."):
-            norm(b + nm, c)
+        for layer in range(cfg.get("transformer_num_layers", 1)):
+            b = pre + f"transformer_blocks.{layer}."
+            for a, kv in (("attn1.", c), ("attn2.", cdim)):
+                out[b + a + "to_q.weight"], out[b + a + "to_k.weight"], out[b + a + "to_v.weight"] = (c, c), (c, kv), (c, kv)
+                out[b + a + "to_out.0.weight"], out[b + a + "to_out.0.bias"] = (c, c), (c,)
+                if a == "attn1.":
+                    out[b + "ff.linear1.weight"], out[b + "ff.linear1.bias"] = (8 * c, c), (8 * c,)
+                    out[b + "ff.linear2.weight"], out[b + "ff.linear2.bias"] = (c, 4 * c), (c,)
+            for nm in ("norm1.", "norm2.", "norm3."):
+                norm(b + nm, c)
         conv(pre + "proj_out.", c, c, 1)
 
     if not cfg["with_conditioning"]:

@@ -44,7 +44,9 @@ def main():
              # 2-D context) on a volume whose coarsest grid is odd (11 x 16 x 11)
              ("atten_unet_smoke_1x44x64x44", (1, 44, 64, 44), 777, 2, OA.SMOKE_CFG),
              # with_conditioning=False: Attn{Down,Mid,Up}Block / AttentionBlock instead of the SpatialTransformer, no context
-             ("atten_unet_attnonly_1x32x48x32", (1, 32, 48, 32), 777, 1, OA.ATTN_ONLY_CFG))
+             ("atten_unet_attnonly_1x32x48x32", (1, 32, 48, 32), 777, 1, OA.ATTN_ONLY_CFG),
+             # transformer_num_layers = 2: two BasicTransformerBlocks per SpatialTransformer
+             ("atten_unet_twolayer_1x32x48x32", (1, 32, 48, 32), 777, 1, OA.TWO_LAYER_CFG))
     only = sys.argv[1:]
     for name, shape, seed, stride, case_cfg in cases:
         if only and name not in only:

@@ -321,6 +321,51 @@ def test_attention_block_family_matches_golden(petsyn):
     assert abs(tot ** 0.5 - gtot) <= max(2.0 * abs(tot_p ** 0.5 - gtot), 2e-2 * gtot), (tot ** 0.5, gtot, tot_p ** 0.5)
 
 
+def test_two_transformer_layers_match_golden(petsyn):
+    """``transformer_num_layers=2``: two BasicTransformerBlocks chained inside every SpatialTransformer (atten_unet_model.py:300-301,
+    336-337) -- against the fixture generated from the reference class, calibrated by the cuDNN bf16 peer like the tests above."""
+    gold = np.load(os.path.join(GOLD, "atten_unet_twolayer_1x32x48x32.npz"))
+    shape, seed = tuple(int(v) for v in gold["shape"]), int(gold["seed"])
+    cfg = OA.TWO_LAYER_CFG
+    model = petsyn.AttenUNet(**cfg).train()
+    assert list(model.state_dict()) == list(OA.param_shapes(cfg))
+    assert any(".transformer_blocks.1." in k for k in model.state_dict())
+    OA.randomize_(model.named_parameters(), seed=seed)
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    g = torch.Generator().manual_seed(seed)
+    n, d, h, w = shape
+    x, ctx, tgt = torch.rand(n, 1, d, h, w, generator=g), torch.rand(n, 1, 5, generator=g), torch.rand(n, 1, d, h, w, generator=g)
+    y_gold = torch.from_numpy(gold["output"])
+    pp = {k: v.detach().clone().cuda().requires_grad_(True) for k, v in sd.items()}
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        y_p = OA.forward(x.cuda(), ctx.cuda(), pp, cfg)
+    (y_p.float() - tgt.cuda()).abs().mean().backward()
+    peer_err = (y_p.detach().float().cpu() - y_gold).abs()
+    model = model.cuda()
+    y = model(x.cuda(), ctx.cuda())
+    loss = torch.nn.functional.l1_loss(y, tgt.cuda())
+    loss.backward()
+    torch.cuda.synchronize()
+    err = (y.detach().cpu() - y_gold).abs()
+    print("two transformer layers: out err ours max/mean", err.max().item(), err.mean().item(), "peer", peer_err.max().item(),
+          peer_err.mean().item(), "loss", loss.item(), float(gold["loss"]))
+    assert err.max().item() <= 2.0 * peer_err.max().item() + 5e-3
+    assert err.mean().item() <= 2.0 * peer_err.mean().item() + 5e-4
+    assert abs(loss.item() - float(gold["loss"])) <= 2e-3
+    gtot = float(gold["grad_norm_total"])
+    tot = tot_p = 0.0
+    for k, p in model.named_parameters():
+        gn, ref = p.grad.double().norm().item(), float(gold["gradnorm/" + k])
+        pn = 0.0 if pp[k].grad is None else pp[k].grad.double().norm().item()
+        tot += gn * gn
+        tot_p += pn * pn
+        if ref == 0.0:                  # attn2's to_q / to_k / norm2: a softmax over ONE context token ignores them
+            assert gn == 0.0, k
+        elif ref > 2e-2 * gtot:
+            assert abs(gn - ref) / ref <= max(2.0 * abs(pn - ref) / ref, 0.05), (k, gn, ref, pn)
+    assert abs(tot ** 0.5 - gtot) <= max(2.0 * abs(tot_p ** 0.5 - gtot), 2e-2 * gtot), (tot ** 0.5, gtot, tot_p ** 0.5)
+
+
 def test_contracts(petsyn):
     cfg = dict(OA.TRAINING_JSON)
     with pytest.raises(ValueError):

@@ -100,7 +100,8 @@ def _atten_inputs(shape, seed, cdim):
 
 
 @pytest.mark.parametrize("name,cfg_name", [("atten_unet_2x32x48x32", "TRAINING_JSON"), ("atten_unet_smoke_1x44x64x44", "SMOKE_CFG"),
-                                           ("atten_unet_attnonly_1x32x48x32", "ATTN_ONLY_CFG")])
+                                           ("atten_unet_attnonly_1x32x48x32", "ATTN_ONLY_CFG"),
+                                           ("atten_unet_twolayer_1x32x48x32", "TWO_LAYER_CFG")])
 def test_atten_unet_oracle_matches_golden(name, cfg_name):
     from oracle import atten_unet as OA
     cfg = getattr(OA, cfg_name)
