@@ -293,7 +293,7 @@ class AttenUNet(nn.Module):
                                            resblock_updown))
         self.out = nn.Sequential(nn.GroupNorm(g, ch[0], eps=e, affine=True), nn.SiLU(),
                                  zero_module(_Convolution(ch[0], out_channels, 3)))
-        self._engines: Dict[Tuple, "_AttenEngine"] = {}
+        self._engines: Dict[Tuple, "_AttenEngine"] = ops.EngineCache()
 
     def engine_for(self, x: torch.Tensor) -> "_AttenEngine":
         key = (tuple(x.shape), x.device.index)
@@ -746,7 +746,7 @@ class DiffusionModelEncoder(nn.Module):
             self.down_blocks.append(_DownBlock(in_c, out_c, num_res_blocks[i], g, e, True, attn))
         self.out = nn.Sequential(nn.Linear(head_in_features, 512), nn.ReLU(), nn.Dropout(0.1),
                                  nn.Linear(512, out_channels))
-        self._engines: Dict[Tuple, "_ClsEngine"] = {}
+        self._engines: Dict[Tuple, "_ClsEngine"] = ops.EngineCache()
 
     def forward(self, x: torch.Tensor, timesteps: torch.Tensor | None = None, context: torch.Tensor | None = None,
                 class_labels: torch.Tensor | None = None) -> torch.Tensor:

@@ -113,7 +113,7 @@ class dense_unet_generator(nn.Module):
                 nn.LeakyReLU(LRELU_SLOPE)])))
             cur = c
         self.output_layer = nn.Sequential(*(_cnl(cur, oc) + _cnl(oc, oc) + [nn.Conv3d(oc, 1, 3, padding=1), nn.Tanh()]))
-        self._engines: Dict[Tuple, "_GenEngine"] = {}
+        self._engines: Dict[Tuple, "_GenEngine"] = ops.EngineCache()
 
     def engine_for(self, x: torch.Tensor) -> "_GenEngine":
         key = (tuple(x.shape), x.device.index)
@@ -460,7 +460,7 @@ class PatchDiscriminator(_PatchDiscriminatorNet):
             raise NotImplementedError("petsyn PatchDiscriminator implements the reference's use: 3-D, one channel in / out, "
                                       "kernel 4, LeakyReLU(0.2), BatchNorm, no conv bias, padding 1, no dropout")
         super().__init__(num_channels, in_channels, num_layers_d)
-        self._engines: Dict[Tuple, "_DiscEngine"] = {}
+        self._engines: Dict[Tuple, "_DiscEngine"] = ops.EngineCache()
 
     def engine_for(self, x: torch.Tensor) -> "_DiscEngine":
         key = (tuple(x.shape), x.device.index)
@@ -491,7 +491,7 @@ class patch_discriminator(nn.Module):
     def __init__(self):
         super().__init__()
         self.patch_d = _PatchDiscriminatorNet(32, 1, 4)
-        self._engines: Dict[Tuple, "_DiscEngine"] = {}
+        self._engines: Dict[Tuple, "_DiscEngine"] = ops.EngineCache()
 
     def engine_for(self, x: torch.Tensor) -> "_DiscEngine":
         key = (tuple(x.shape), x.device.index)
@@ -658,7 +658,7 @@ class ResNet_encoder(nn.Module):
             cur = c
         self.linear1 = nn.Linear(128 * 8, 8)
         self.linear2 = nn.Linear(128 * 8, 8)
-        self._engines: Dict[Tuple, "_EncEngine"] = {}
+        self._engines: Dict[Tuple, "_EncEngine"] = ops.EngineCache()
 
     def engine_for(self, x: torch.Tensor) -> "_EncEngine":
         key = (tuple(x.shape), x.device.index)

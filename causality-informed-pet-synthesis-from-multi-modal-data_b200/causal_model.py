@@ -145,7 +145,7 @@ class Decoder(_DecoderBase):
         blocks.append(nn.GroupNorm(norm_num_groups, cin, eps=norm_eps, affine=True))
         blocks.append(_Convolution(cin, out_channels, 3))
         self.blocks = nn.ModuleList(blocks)
-        self._engines = {}
+        self._engines = ops.EngineCache()
 
     def plan(self):
         """(conv_in, [stage, ...], final norm, SiLU before the last conv?, out conv); a stage is ('res', block, None) or
@@ -210,7 +210,7 @@ class DiffusionModelDecoder(_DecoderBase):
             self.up_blocks.append(_UpStage(prev, ch[i], num_res_blocks[i], g, e, attn))
             prev = ch[i]
         self.out = nn.Sequential(nn.GroupNorm(g, ch[-1], eps=e, affine=True), nn.SiLU(), _Convolution(ch[-1], out_channels, 3))
-        self._engines = {}
+        self._engines = ops.EngineCache()
 
     def plan(self):
         stages = []

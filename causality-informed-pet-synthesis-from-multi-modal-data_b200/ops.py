@@ -9,6 +9,9 @@ from __future__ import annotations
 import ctypes as C
 from typing import Optional, Tuple
 
+import os
+from collections import OrderedDict
+
 import torch
 
 from . import _cabi
@@ -313,3 +316,22 @@ def launch_count() -> int:
 
 def sumsq(g: torch.Tensor, out: torch.Tensor) -> None:
     check(lib.petsyn_sumsq(ptr(g), ptr(out), g.numel(), stream_ptr()), "sumsq")
+
+
+class EngineCache(OrderedDict):
+    """Per-module cache of engines keyed by (input shape, device): least recently used entries are dropped beyond
+    ``PETSYN_MAX_ENGINES`` (default 4) so that inference over many volume shapes does not keep every shape's activation
+    buffers alive.  An evicted engine still referenced by a pending autograd node or a trainer lives until they let go."""
+
+    def get(self, key, default=None):
+        if key in self:
+            self.move_to_end(key)
+            return self[key]
+        return default
+
+    def __setitem__(self, key, value):
+        super().__setitem__(key, value)
+        self.move_to_end(key)
+        limit = max(1, int(os.environ.get("PETSYN_MAX_ENGINES", "4")))
+        while len(self) > limit:
+            self.popitem(last=False)

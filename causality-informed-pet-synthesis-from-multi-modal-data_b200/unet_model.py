@@ -99,7 +99,7 @@ class UnetGenerator3d(nn.Module):
         else:
             blk = UnetSkipConnectionBlock3d(output_nc, ngf * 2, blk, outermost=True, norm_layer=norm_layer)
         self.model = blk
-        self._engines: Dict[Tuple, "_Engine"] = {}
+        self._engines: Dict[Tuple, "_Engine"] = ops.EngineCache()
 
     # ------------------------------------------------------------------------------------------------
     def levels(self) -> List[UnetSkipConnectionBlock3d]:

@@ -91,3 +91,16 @@ def test_block_output_living_in_a_concat_slot(petsyn):
     d = nxt._desc(True)
     assert (d.z_cstride, d.z_coff, d.dz_cstride, d.dz_coff) == (32, 16, 32, 16) and d.c == 16
     assert d.extra == cat.g.data_ptr() and (d.extra_cstride, d.extra_coff) == (32, 16) and d.dz_accumulate == 1
+
+
+def test_engine_cache_is_least_recently_used(monkeypatch):
+    """Drop-in modules keep one engine (all activation buffers of a shape) per input shape: bounded, least recently used out."""
+    import petsyn
+    monkeypatch.setenv("PETSYN_MAX_ENGINES", "2")
+    c = petsyn.ops.EngineCache()
+    c["a"], c["b"] = 1, 2
+    assert c.get("a") == 1                     # refreshes "a"
+    c["c"] = 3
+    assert list(c) == ["a", "c"] and c.get("b") is None
+    m = petsyn.UnetGenerator3d(1, 1, 4, ngf=8)
+    assert isinstance(m._engines, petsyn.ops.EngineCache)
