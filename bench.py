@@ -913,7 +913,7 @@ def run_petsyn_atten(args, shape, batch, adv=False):
         torch.manual_seed(778)
         disc = petsyn.PatchDiscriminator(**DISC_CFG).to(dev).train()
     trainer = AttenUNetTrainer(model, lr=5e-4, example_input=resident[0][0], discriminator=disc, adv_weight=0.1 if adv else 0.0,
-                               disc_lr=1e-4)
+                               disc_lr=1e-4, bucket_mb=float(os.environ.get("PETSYN_ATTEN_BUCKET_MB", "32")))
 
     def barrier():
         if world > 1:
