@@ -20,15 +20,18 @@ engine that runs fused CUDA kernels over channels-last bf16 activations (fp32 ac
 """
 from __future__ import annotations
 
-import os
-
 import functools
+import os
+from types import SimpleNamespace
 from typing import Dict, List, Optional, Tuple
 
 import torch
 import torch.nn as nn
 
 from . import ops
+from ._cabi import check, lib, ptr, stream_ptr
+from .bmgan_model import _EngineBase
+from .graph import Buf, DropoutOp, NormActOp
 
 LRELU_SLOPE = 0.2   # unet_model.py:49
 
@@ -450,14 +453,6 @@ class _Engine:
 # LeakyReLU followed by the parent's in-place ReLU, ReLU(LeakyReLU(x)) = ReLU(x)), torch.cat never runs, nn.Upsample is
 # folded into the 3x3x3 convolution's gather.  Dropout commutes with the parent's ReLU (its mask is >= 0).
 # ======================================================================================================================
-from types import SimpleNamespace
-
-from . import graph                                              # noqa: E402
-from ._cabi import check, lib, ptr, stream_ptr                  # noqa: E402
-from .bmgan_model import _EngineBase                             # noqa: E402
-from .graph import Buf, NormActOp, DropoutOp                     # noqa: E402
-
-
 class _TapeUnetFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, eng, x, *params):
