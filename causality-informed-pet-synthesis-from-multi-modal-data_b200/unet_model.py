@@ -509,7 +509,7 @@ class _TapeEngine(_EngineBase):
                                y_fp32=True, name="up0")
         self.y = torch.zeros(n, 1, D, H, W, dtype=torch.float32, device=dev)
         self._finish()
-        self.flops_executed = self.flops_algorithmic
+        self.flops_executed = sum(op.plan.flops_executed for op in self.tape.ops if hasattr(op, "plan"))   # incl. channel padding
 
     def _norm(self, z, norm: Optional[nn.Module], act: int, dsts, act2: Optional[int] = None, name: str = "") -> None:
         if norm is None:                                          # outermost / innermost down convolutions
