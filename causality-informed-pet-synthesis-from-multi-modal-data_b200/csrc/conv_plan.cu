@@ -805,11 +805,11 @@ static int32_t view_map(CUtensorMap* out, const void* base, const ViewSpec& v, b
   return encode_tmap(out, dt, 5, b, dims, strides, box, swizzle);
 }
 
-template <int BN, int OUT_MODE>
+template <int BN, int OUT_MODE, bool STATS = false>
 static int32_t launch_igemm_bn(const GemmSide& g, dim3 grid, cudaStream_t st) {
   constexpr int STAGES = (BN <= 128) ? 3 : 4;
   using Cfg = IgemmCfg<BN, 64, STAGES, OUT_MODE>;
-  auto kern = igemm_kernel<BN, 64, STAGES, OUT_MODE>;
+  auto kern = igemm_kernel<BN, 64, STAGES, OUT_MODE, STATS>;
   static bool attr_set = false;   // per instantiation
   if (!attr_set) {
     PETSYN_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
@@ -865,6 +865,27 @@ static int32_t launch_igemm(const GemmSide& g, int batch, cudaStream_t st) {
     case 128: return launch_igemm_bn<128, OUT_BF16>(g, grid, st);
     case 256: return launch_igemm_bn<256, OUT_BF16>(g, grid, st);
     default: return fail(PETSYN_EINVAL, "unsupported BLOCK_N %d", g.block_n);
+  }
+}
+
+// Output statistics in the gather-form kernel's epilogue (petsyn_conv_fprop_epi with statistics targets only): a plain
+// bf16 store of one un-phased output view, no split-K, 32 / 64 / 128 channels per tile
+static bool igemm_stats_supported(const GemmSide& g) {
+  return !g.slab && g.ksplit == 1 && !g.out_fp32 && !g.accumulate && g.subs.size() == 1 && !g.prog.out_phased &&
+         (g.block_n == 32 || g.block_n == 64 || g.block_n == 128) && getenv("PETSYN_NO_EPI") == nullptr &&
+         getenv("PETSYN_NO_IGEMM_STATS") == nullptr;
+}
+
+static int32_t launch_igemm_stats(const GemmSide& g, int batch, cudaStream_t st) {
+  dim3 grid;
+  grid.x = (unsigned)(g.params.tiles_w * g.params.tiles_h * g.params.tiles_d * batch);
+  grid.y = (unsigned)((g.R + g.block_n - 1) / g.block_n);
+  grid.z = 1;
+  switch (g.block_n) {
+    case 32: return launch_igemm_bn<32, OUT_BF16, true>(g, grid, st);
+    case 64: return launch_igemm_bn<64, OUT_BF16, true>(g, grid, st);
+    case 128: return launch_igemm_bn<128, OUT_BF16, true>(g, grid, st);
+    default: return fail(PETSYN_EINVAL, "unsupported BLOCK_N %d for output statistics", g.block_n);
   }
 }
 
@@ -1397,12 +1418,28 @@ int32_t petsyn_conv_dgrad(petsyn_conv_plan* pl, const void* dy, const void* pack
 
 int32_t petsyn_conv_epilogue_supported(const petsyn_conv_plan* pl, int32_t pass) {
   if (!pl || pass < 0 || pass > 1) return 0;
-  return epi_supported(pass == 0 ? pl->fprop : pl->dgrad, pl->desc.n) ? 1 : 0;
+  if (epi_supported(pass == 0 ? pl->fprop : pl->dgrad, pl->desc.n)) return 1;
+  return (pass == 0 && igemm_stats_supported(pl->fprop)) ? 2 : 0;   // 2: statistics targets only
 }
 
 int32_t petsyn_conv_fprop_epi(petsyn_conv_plan* pl, const void* x, const void* packed, const float* bias, void* y,
                               const petsyn_conv_epilogue* epi, void* stream) {
   PETSYN_REQUIRE(pl && x && packed && y && epi, "null argument");
+  if (!pl->fprop.slab && igemm_stats_supported(pl->fprop)) {
+    PETSYN_REQUIRE(epi->side == nullptr && epi->bsums == nullptr && (epi->stats1 != nullptr || epi->stats2 != nullptr),
+                   "the gather-form kernel's epilogue takes statistics targets only");
+    int32_t rc = bind_side(pl->fprop, pl->vx, pl->vy, x, packed, y, bias, pl->desc.epi_act, pl->desc.epi_slope);
+    if (rc) return rc;
+    IgemmParams& p = pl->fprop.params;
+    p.st1 = epi->stats1; p.st1_c = epi->stats1_c; p.st1_off = epi->stats1_coff;
+    p.st2 = epi->stats2; p.st2_c = epi->stats2_c; p.st2_off = epi->stats2_coff;
+    p.ext_w = pl->vy.W; p.ext_h = pl->vy.H; p.ext_d = pl->vy.D;
+    PETSYN_REQUIRE((p.st1 == nullptr || p.st1_off + pl->fprop.R <= p.st1_c) && (p.st2 == nullptr || p.st2_off + pl->fprop.R <= p.st2_c),
+                   "statistics target narrower than the output channels");
+    rc = launch_igemm_stats(pl->fprop, pl->desc.n, as_stream(stream));
+    p.st1 = p.st2 = nullptr;
+    return rc;
+  }
   PETSYN_REQUIRE(epi_supported(pl->fprop, pl->desc.n), "this plan's forward pass has no fused epilogue");
   int32_t rs = bind_slab(pl->fprop, pl->vx, pl->vy, x, packed, y, bias, pl->desc.epi_act, pl->desc.epi_slope);
   return rs ? rs : run_slab_epi(pl->fprop, pl->vx, pl->vy, x, packed, y, epi, false, as_stream(stream));

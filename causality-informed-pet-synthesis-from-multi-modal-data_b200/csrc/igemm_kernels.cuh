@@ -52,6 +52,12 @@ struct alignas(64) IgemmParams {
   int32_t epi_act;
   float epi_slope;
   int32_t ksplit;         // CTAs sharing one output tile's K loop (split-K; >1 only with OUT_F32_REDUCE)
+  // STATS variant: per (sample, channel) sum and sum of squares of the STORED (bf16) outputs, added to up to two
+  // [sample][2][st_c] double accumulators (the GroupNorm / InstanceNorm that consumes the output skips its statistics pass)
+  double* st1;
+  double* st2;
+  int32_t st1_c, st1_off, st2_c, st2_off;
+  int32_t ext_w, ext_h, ext_d;   // extent of the output view: rows of a tile beyond it are clipped by the store and not summed
 };
 
 enum { OUT_BF16 = 0, OUT_F32 = 1, OUT_F32_REDUCE = 2, OUT_BF16_REDUCE = 3 };
@@ -92,8 +98,10 @@ struct IgemmCfg {
   static constexpr uint32_t kTmemCols = BLOCK_N <= 32 ? 32 : (BLOCK_N <= 64 ? 64 : (BLOCK_N <= 128 ? 128 : 256));
 };
 
-template <int BLOCK_N, int KCH, int STAGES, int OUT_MODE>
+template <int BLOCK_N, int KCH, int STAGES, int OUT_MODE, bool STATS = false>
 __global__ void __launch_bounds__(128) igemm_kernel(const __grid_constant__ IgemmParams p) {
+  static_assert(!STATS || (OUT_MODE == OUT_BF16 && (BLOCK_N == 32 || BLOCK_N == 64 || BLOCK_N == 128)),
+                "output statistics: bf16 stores, 32 / 64 / 128 channels per tile");
   using Cfg = IgemmCfg<BLOCK_N, KCH, STAGES, OUT_MODE>;
   using Sw = SwizzleOf<KCH>;
   extern __shared__ uint8_t smem_raw[];
@@ -239,6 +247,15 @@ __global__ void __launch_bounds__(128) igemm_kernel(const __grid_constant__ Igem
       }
     }
   }
+  // STATS scratch sits behind the staging tile, in pipeline stages no MMA reads any more (accum_bar has completed)
+  uint8_t* s_valid = smem + Cfg::kStagingBytes;                              // [128] row inside the output extent?
+  float* s_part = reinterpret_cast<float*>(smem + Cfg::kStagingBytes + 128); // [row groups][BLOCK_N][2]
+  if constexpr (STATS) {
+    static_assert(Cfg::kStagingBytes + 128 + (256 / BLOCK_N) * BLOCK_N * 2 * 4 <= Cfg::kMainBytes, "no room for the statistics scratch");
+    const int bw = row % p.box_w, bh = (row / p.box_w) % p.box_h, bd = row / (p.box_w * p.box_h);
+    // (a box may hold fewer than 128 voxels: the accumulator rows behind it are computed from stale shared memory)
+    s_valid[row] = (bd < p.box_d && w0 + bw < p.ext_w && h0 + bh < p.ext_h && d0 + bd < p.ext_d) ? 1 : 0;
+  }
   ptx::tc_fence_before_sync();
   ptx::fence_proxy_async_smem();
   __syncthreads();
@@ -258,7 +275,46 @@ __global__ void __launch_bounds__(128) igemm_kernel(const __grid_constant__ Igem
         ptx::tma_store_5d(cmap, src, ch, w0, h0, d0, nb);
     }
     ptx::tma_store_commit();
-    ptx::tma_store_wait_all();
+    if constexpr (!STATS) ptx::tma_store_wait_all();
+  }
+  if constexpr (STATS) {
+    // column sums of the staged tile (what the TMA store is writing): thread = (channel pair, group of rows)
+    constexpr int kPairs = BLOCK_N / 2, kGroups = 128 / kPairs, kRowsPer = 128 / kGroups;
+    const int pair = tid % kPairs, grp = tid / kPairs;
+    const int c = 2 * pair;
+    const uint8_t* colp = smem + (c / Cfg::kChunkC) * (128 * Cfg::kRowPitch);
+    const int cin = c % Cfg::kChunkC;
+    float s0 = 0.f, q0 = 0.f, s1 = 0.f, q1 = 0.f;
+#pragma unroll 4
+    for (int r = grp * kRowsPer; r < (grp + 1) * kRowsPer; ++r) {
+      const int j = (cin * 2) >> 4;
+      const int js = Cfg::kSwz ? (j ^ (r & 7)) : j;
+      const uint32_t w = *reinterpret_cast<const uint32_t*>(colp + r * Cfg::kRowPitch + (js << 4) + ((cin * 2) & 15));
+      const bool ok = s_valid[r] != 0;              // a select, not a product: a clipped row may hold NaN
+      const float a = ok ? __uint_as_float(w << 16) : 0.f, b = ok ? __uint_as_float(w & 0xffff0000u) : 0.f;
+      s0 += a; q0 += a * a;
+      s1 += b; q1 += b * b;
+    }
+    float* pp = s_part + (grp * BLOCK_N + c) * 2;
+    pp[0] = s0; pp[1] = q0; pp[2] = s1; pp[3] = q1;
+    __syncthreads();
+    if (tid < BLOCK_N && n0 + tid < p.rows) {
+      float ts = 0.f, tq = 0.f;
+#pragma unroll
+      for (int g = 0; g < kGroups; ++g) { ts += s_part[(g * BLOCK_N + tid) * 2]; tq += s_part[(g * BLOCK_N + tid) * 2 + 1]; }
+      const int ch = n0 + tid;
+      if (p.st1 != nullptr) {
+        double* d = p.st1 + (int64_t)nb * 2 * p.st1_c + p.st1_off + ch;
+        atomicAdd(d, (double)ts);
+        atomicAdd(d + p.st1_c, (double)tq);
+      }
+      if (p.st2 != nullptr) {
+        double* d = p.st2 + (int64_t)nb * 2 * p.st2_c + p.st2_off + ch;
+        atomicAdd(d, (double)ts);
+        atomicAdd(d + p.st2_c, (double)tq);
+      }
+    }
+    if (tid == 0) ptx::tma_store_wait_all();
   }
 }
 

@@ -522,9 +522,10 @@ class NormActOp(Op):
         stats = lambda ns, rows: check(lib.petsyn_norm_stats_slice(ptr(z.t), z.c, self.zs.off, ptr(self.sums), rows, c, ns,
                                                                    stream_ptr()), "norm_stats")
         if self.kind == "instance":
-            if not self.tape_zeroes_sums:
-                self.sums.zero_()
-            stats(z.n, self.rows)
+            if not self.stats_from_producers:
+                if not self.tape_zeroes_sums:
+                    self.sums.zero_()
+                stats(z.n, self.rows)
             if SEPARATE_FINALIZE:        # default: folded into the apply launch below (fin_* fields of the descriptor)
                 check(lib.petsyn_norm_finalize(ptr(self.sums), None, None, None, None, ptr(self.scale), ptr(self.shift),
                                                ptr(self.mean), ptr(self.rstd), self.rows, c, z.n, 1, self.eps, 0.0, 1,
@@ -850,7 +851,7 @@ class Tape:
                 osl = op.out_slice()
                 if osl is None or op.absorbed:
                     continue                           # fp32 head / an addend that a later conv's epilogue overwrites in place
-                if op.plan.epi_ok[0] and not os.environ.get("PETSYN_NO_EPI_STATS"):
+                if op.plan.epi_stats_ok and not os.environ.get("PETSYN_NO_EPI_STATS"):
                     op.stats_for = [[]]
                     produced.setdefault(id(osl.buf), []).append((op, 0, osl))   # its epilogue can sum what it stores
                 else:
@@ -865,7 +866,7 @@ class Tape:
                         other(v)
         shared = []
         for q in self.ops:
-            if not (isinstance(q, NormActOp) and q.kind == "group" and not os.environ.get("PETSYN_NO_STATS_FUSION")):
+            if not (isinstance(q, NormActOp) and q.kind in ("group", "instance") and not os.environ.get("PETSYN_NO_STATS_FUSION")):
                 continue
             lo, hi = q.zs.off, q.zs.off + q.zs.c
             if any(a < hi and lo < b for a, b in other_writers.get(id(q.z), [])):

@@ -50,7 +50,9 @@ class ConvPlan:
         # kernel family per pass (0 gather-form igemm, 1 slab, 2 small-channel wgrad): reporting only
         self.kernel_path = tuple(lib.petsyn_conv_kernel_path(self._h, i) for i in range(3))
         # fused epilogues (petsyn_conv_{fprop,dgrad}_epi): available per pass (fprop, dgrad)
-        self.epi_ok = tuple(bool(lib.petsyn_conv_epilogue_supported(self._h, i)) for i in range(2))
+        sup = [int(lib.petsyn_conv_epilogue_supported(self._h, i)) for i in range(2)]
+        self.epi_ok = tuple(v == 1 for v in sup)          # any fused epilogue (residual, statistics, norm-backward reduce)
+        self.epi_stats_ok = sup[0] in (1, 2)               # forward pass: at least the statistics epilogue
         self.packed_fprop_bytes = lib.petsyn_conv_packed_fprop_bytes(self._h)
         self.packed_dgrad_bytes = lib.petsyn_conv_packed_dgrad_bytes(self._h)
         self.wgrad_scratch_bytes = lib.petsyn_conv_wgrad_scratch_bytes(self._h)

@@ -157,7 +157,8 @@ typedef struct petsyn_conv_epilogue {
   float norm_slope;
   double* bsums;
 } petsyn_conv_epilogue;
-/* pass: 0 = fprop, 1 = dgrad.  1 if petsyn_conv_{fprop,dgrad}_epi can run this plan's pass, else 0. */
+/* pass: 0 = fprop, 1 = dgrad.  1 if petsyn_conv_{fprop,dgrad}_epi can run this plan's pass with any epilogue, 2 if only with
+ * statistics targets (stats1 / stats2; the gather-form kernel, forward pass), else 0. */
 int32_t petsyn_conv_epilogue_supported(const petsyn_conv_plan* plan, int32_t pass);
 int32_t petsyn_conv_fprop_epi(petsyn_conv_plan* plan, const void* x, const void* packed_fprop, const float* bias, void* y,
                               const petsyn_conv_epilogue* epi, void* stream);

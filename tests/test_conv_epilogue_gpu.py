@@ -143,3 +143,56 @@ def test_dgrad_with_norm_backward_reduction(petsyn, n, d, h, w, cin, cout, act):
     plan.dgrad_epi(dy, dx, e)
     torch.cuda.synchronize()
     assert torch.equal(b2, bsums)                  # reproducible
+
+
+# gather-form (igemm) kernel: statistics targets only.  n, d, h, w, cin, cout, k, stride, pad -- ragged tiles, stride 2,
+# 1x1x1 (the transformer linears' shape), two channel tiles (cout 256 = 2 x 128)
+IGEMM_CASES = [
+    (2, 22, 36, 28, 64, 64, 3, 1, 1),
+    (2, 20, 34, 30, 64, 128, 3, 1, 1),
+    (2, 44, 60, 52, 32, 64, 4, 2, 1),
+    (3, 14, 20, 18, 128, 256, 3, 1, 1),
+    (2, 18, 32, 32, 96, 32, 1, 1, 0),
+]
+
+
+@pytest.mark.parametrize("n,d,h,w,cin,cout,k,s,p", IGEMM_CASES)
+def test_gather_form_statistics_epilogue(petsyn, n, d, h, w, cin, cout, k, s, p):
+    from petsyn_b200._cabi import ConvEpilogue, ptr
+    ops = petsyn.ops
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device="cpu").manual_seed(11 + cin + cout + k)
+    x = torch.randn(n, d, h, w, cin, generator=g).to(dev).to(torch.bfloat16)
+    wt = (torch.randn(cout, cin, k, k, k, generator=g) / (cin * k ** 3) ** 0.5).to(dev)
+    bias = torch.randn(cout, generator=g).to(dev)
+    plan = ops.ConvPlan(ops.OP_CONV, n, d, h, w, cin, cout, k, s, p)
+    assert plan.epi_stats_ok and plan.kernel_path[0] == 0 and not plan.epi_ok[0]
+    plan.pack(wt, need_dgrad=False)
+    od, oh, ow = plan.out_dims
+    y_plain = torch.zeros(n, od, oh, ow, cout, dtype=torch.bfloat16, device=dev)
+    plan.fprop(x, y_plain, bias)
+    y = torch.zeros_like(y_plain)
+    st1 = torch.zeros(n, 2, cout + 8, dtype=torch.float64, device=dev)
+    st2 = torch.zeros(n, 2, cout, dtype=torch.float64, device=dev)
+    e = ConvEpilogue()
+    e.stats1, e.stats1_c, e.stats1_coff = ptr(st1), cout + 8, 8
+    e.stats2, e.stats2_c, e.stats2_coff = ptr(st2), cout, 0
+    plan.fprop_epi(x, y, bias, e)
+    torch.cuda.synchronize()
+    assert torch.equal(y, y_plain)
+    v = y.double().reshape(n, -1, cout)
+    want = torch.stack([v.sum(1), (v * v).sum(1)], 1)
+    tol = 1e-6 * want.abs().max().item()
+    assert torch.allclose(st2, want, rtol=1e-6, atol=tol)
+    assert torch.allclose(st1[:, :, 8:], want, rtol=1e-6, atol=tol) and st1[:, :, :8].abs().max().item() == 0.0
+    st3 = torch.zeros_like(st2)
+    e2 = ConvEpilogue()
+    e2.stats1, e2.stats1_c = ptr(st3), cout
+    plan.fprop_epi(x, y, bias, e2)
+    torch.cuda.synchronize()
+    assert torch.equal(st3, st2)                   # reproducible
+    e3 = ConvEpilogue()
+    e3.stats1, e3.stats1_c = ptr(st3), cout
+    e3.side, e3.side_cstride, e3.add_side = ptr(y_plain), cout, 1
+    with pytest.raises(ValueError):
+        plan.fprop_epi(x, y, bias, e3)             # this kernel takes statistics targets only
