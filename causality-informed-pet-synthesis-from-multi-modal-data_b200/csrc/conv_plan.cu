@@ -369,6 +369,60 @@ __global__ void __launch_bounds__(256) splitk_finish_kernel(const float* __restr
   }
 }
 
+// The same finish pass, also summing what it stores: per (sample, channel) sum and sum of squares of the bf16 output into up
+// to two [sample][2][st_c] double accumulators (the statistics pass of the normalisation that consumes a split-K convolution).
+// grid (x, sample); thread = (8-channel group, row of the pass); C / 8 divides 256.
+__global__ void __launch_bounds__(256) splitk_finish_stats_kernel(const float* __restrict__ src, int nslots,
+                                                                  __nv_bfloat16* __restrict__ dst, int64_t rows_per_sample,
+                                                                  int C, int cstride, int coff, const float* __restrict__ bias,
+                                                                  int act, float slope, double* st1, int st1_c, int st1_off,
+                                                                  double* st2, int st2_c, int st2_off) {
+  pdl_sync();
+  __shared__ float s_red[4096];                      // [rows of a pass][2][C]: (256 / cpt) * 2 * 8 * cpt floats
+  const int cpt = C / 8, rpp = 256 / cpt;
+  const int tx = threadIdx.x % cpt, ty = threadIdx.x / cpt;
+  const int c = tx * 8;
+  const int sample = blockIdx.y;
+  const int64_t slot = rows_per_sample * gridDim.y * C;
+  float a0[8], a1[8], bs[8];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) { a0[q] = a1[q] = 0.f; bs[q] = bias ? __ldg(bias + c + q) : 0.f; }
+  for (int64_t rr = (int64_t)blockIdx.x * rpp + ty; rr < rows_per_sample; rr += (int64_t)gridDim.x * rpp) {
+    const int64_t r = (int64_t)sample * rows_per_sample + rr;
+    float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int k = 0; k < nslots; ++k) {
+      const float* sp = src + k * slot + r * C + c;
+      const float4 v0 = *reinterpret_cast<const float4*>(sp), v1 = *reinterpret_cast<const float4*>(sp + 4);
+      f[0] += v0.x; f[1] += v0.y; f[2] += v0.z; f[3] += v0.w; f[4] += v1.x; f[5] += v1.y; f[6] += v1.z; f[7] += v1.w;
+    }
+#pragma unroll
+    for (int q = 0; q < 8; ++q) f[q] = apply_act(f[q] + bs[q], act, slope);
+    uint4 o;
+    __nv_bfloat162 b[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      b[q] = __floats2bfloat162_rn(f[2 * q], f[2 * q + 1]);
+      const float2 back = __bfloat1622float2(b[q]);            // statistics of the values AS STORED
+      a0[2 * q] += back.x; a1[2 * q] += back.x * back.x;
+      a0[2 * q + 1] += back.y; a1[2 * q + 1] += back.y * back.y;
+    }
+    o.x = *reinterpret_cast<uint32_t*>(&b[0]); o.y = *reinterpret_cast<uint32_t*>(&b[1]);
+    o.z = *reinterpret_cast<uint32_t*>(&b[2]); o.w = *reinterpret_cast<uint32_t*>(&b[3]);
+    *reinterpret_cast<uint4*>(dst + r * cstride + coff + c) = o;
+  }
+  float* mine = s_red + (size_t)ty * 2 * C;
+#pragma unroll
+  for (int q = 0; q < 8; ++q) { mine[c + q] = a0[q]; mine[C + c + q] = a1[q]; }
+  __syncthreads();
+  for (int e = threadIdx.x; e < 2 * C; e += 256) {
+    float t = 0.f;
+    for (int y = 0; y < rpp; ++y) t += s_red[(size_t)y * 2 * C + e];      // fixed order
+    const int which = e / C, ch = e - which * C;
+    if (st1 != nullptr) atomicAdd(st1 + ((int64_t)sample * 2 + which) * st1_c + st1_off + ch, (double)t);
+    if (st2 != nullptr) atomicAdd(st2 + ((int64_t)sample * 2 + which) * st2_c + st2_off + ch, (double)t);
+  }
+}
+
 // Partial images of a weight gradient (one per K split / per persistent CTA) -> image 0, added in image order: the result
 // does not depend on the order the producing CTAs finished in (reproducible weight gradients without atomics).
 // thread = (float4 group g, lane l): lane l adds images l, l + L, ... in ascending order, then the L lane sums are added in
@@ -870,10 +924,16 @@ static int32_t launch_igemm(const GemmSide& g, int batch, cudaStream_t st) {
 
 // Output statistics in the gather-form kernel's epilogue (petsyn_conv_fprop_epi with statistics targets only): a plain
 // bf16 store of one un-phased output view, no split-K, 32 / 64 / 128 channels per tile
-static bool igemm_stats_supported(const GemmSide& g) {
-  return !g.slab && g.ksplit == 1 && !g.out_fp32 && !g.accumulate && g.subs.size() == 1 && !g.prog.out_phased &&
-         (g.block_n == 32 || g.block_n == 64 || g.block_n == 128) && getenv("PETSYN_NO_EPI") == nullptr &&
-         getenv("PETSYN_NO_IGEMM_STATS") == nullptr;
+static bool finish_stats_ok(const GemmSide& g, int batch) {
+  const int cpt = g.R / 8;
+  return g.R % 8 == 0 && cpt >= 1 && cpt <= 256 && 256 % cpt == 0 && !g.accumulate && g.out_rows_full % batch == 0;
+}
+
+static bool igemm_stats_supported(const GemmSide& g, int batch) {
+  if (g.slab || g.out_fp32 || g.accumulate || getenv("PETSYN_NO_EPI") != nullptr || getenv("PETSYN_NO_IGEMM_STATS") != nullptr)
+    return false;
+  if (g.ksplit > 1) return finish_stats_ok(g, batch) && getenv("PETSYN_NO_FINISH_STATS") == nullptr;   // in the finish pass
+  return g.subs.size() == 1 && !g.prog.out_phased && (g.block_n == 32 || g.block_n == 64 || g.block_n == 128);
 }
 
 static int32_t launch_igemm_stats(const GemmSide& g, int batch, cudaStream_t st) {
@@ -891,7 +951,7 @@ static int32_t launch_igemm_stats(const GemmSide& g, int batch, cudaStream_t st)
 
 // run one gather-form GEMM: (split-K: zero the fp32 workspace, reduce into it, convert) or a direct launch
 static int32_t run_side(GemmSide& g, const ViewSpec& vc, void* c, const float* bias, int act, float slope, int batch,
-                        cudaStream_t st) {
+                        cudaStream_t st, const petsyn_conv_epilogue* ep = nullptr) {
   if (g.ksplit > 1) {
     const size_t bytes = (size_t)g.out_rows_full * g.R * sizeof(float) * g.ksplit;     // one partial image per K split
     if (g.workspace == nullptr || g.workspace_bytes < bytes)
@@ -899,6 +959,16 @@ static int32_t run_side(GemmSide& g, const ViewSpec& vc, void* c, const float* b
     // (no clearing: every split of every sub-problem owns at least one K step, so each partial image is stored in full)
     int32_t rc = launch_igemm(g, batch, st);
     if (rc) return rc;
+    if (ep != nullptr) {             // the finish pass also sums what it stores (statistics for the consuming normalisation)
+      const int64_t rps = g.out_rows_full / batch;
+      const int rpp = 256 / (g.R / 8);
+      const int bx = (int)std::max<int64_t>(1, std::min<int64_t>((rps + rpp - 1) / rpp, std::max(1, 148 * 4 / batch)));
+      PETSYN_CHECK_CUDA(launch_pdl(splitk_finish_stats_kernel, dim3(bx, batch), dim3(256), 0, st,
+                                   reinterpret_cast<const float*>(g.workspace), g.ksplit, reinterpret_cast<__nv_bfloat16*>(c), rps,
+                                   g.R, vc.cstride, vc.coff, bias, act, slope, ep->stats1, ep->stats1_c, ep->stats1_coff,
+                                   ep->stats2, ep->stats2_c, ep->stats2_coff));
+      return check_launch("splitk_finish_stats_kernel");
+    }
     const int64_t total = g.out_rows_full * (g.R / 8);
     const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>((total + 255) / 256, 148 * 8));
     PETSYN_CHECK_CUDA(launch_pdl(splitk_finish_kernel, dim3(blocks), dim3(256), 0, st, reinterpret_cast<const float*>(g.workspace), g.ksplit,
@@ -1419,17 +1489,22 @@ int32_t petsyn_conv_dgrad(petsyn_conv_plan* pl, const void* dy, const void* pack
 int32_t petsyn_conv_epilogue_supported(const petsyn_conv_plan* pl, int32_t pass) {
   if (!pl || pass < 0 || pass > 1) return 0;
   if (epi_supported(pass == 0 ? pl->fprop : pl->dgrad, pl->desc.n)) return 1;
-  return (pass == 0 && igemm_stats_supported(pl->fprop)) ? 2 : 0;   // 2: statistics targets only
+  return (pass == 0 && igemm_stats_supported(pl->fprop, pl->desc.n)) ? 2 : 0;   // 2: statistics targets only
 }
 
 int32_t petsyn_conv_fprop_epi(petsyn_conv_plan* pl, const void* x, const void* packed, const float* bias, void* y,
                               const petsyn_conv_epilogue* epi, void* stream) {
   PETSYN_REQUIRE(pl && x && packed && y && epi, "null argument");
-  if (!pl->fprop.slab && igemm_stats_supported(pl->fprop)) {
+  if (!pl->fprop.slab && igemm_stats_supported(pl->fprop, pl->desc.n)) {
     PETSYN_REQUIRE(epi->side == nullptr && epi->bsums == nullptr && (epi->stats1 != nullptr || epi->stats2 != nullptr),
                    "the gather-form kernel's epilogue takes statistics targets only");
     int32_t rc = bind_side(pl->fprop, pl->vx, pl->vy, x, packed, y, bias, pl->desc.epi_act, pl->desc.epi_slope);
     if (rc) return rc;
+    PETSYN_REQUIRE((epi->stats1 == nullptr || epi->stats1_coff + pl->fprop.R <= epi->stats1_c) &&
+                   (epi->stats2 == nullptr || epi->stats2_coff + pl->fprop.R <= epi->stats2_c),
+                   "statistics target narrower than the output channels");
+    if (pl->fprop.ksplit > 1)
+      return run_side(pl->fprop, pl->vy, y, bias, pl->desc.epi_act, pl->desc.epi_slope, pl->desc.n, as_stream(stream), epi);
     IgemmParams& p = pl->fprop.params;
     p.st1 = epi->stats1; p.st1_c = epi->stats1_c; p.st1_off = epi->stats1_coff;
     p.st2 = epi->stats2; p.st2_c = epi->stats2_c; p.st2_off = epi->stats2_coff;

@@ -153,6 +153,11 @@ IGEMM_CASES = [
     (2, 44, 60, 52, 32, 64, 4, 2, 1),
     (3, 14, 20, 18, 128, 256, 3, 1, 1),
     (2, 18, 32, 32, 96, 32, 1, 1, 0),
+    # few voxels: split-K, the statistics come from the finish pass (splitk_finish_stats_kernel)
+    (2, 6, 8, 6, 128, 128, 3, 1, 1),
+    (3, 5, 7, 6, 64, 256, 3, 1, 1),
+    (1, 12, 16, 12, 256, 64, 4, 2, 1),
+    (2, 6, 8, 6, 128, 1024, 1, 1, 0),
 ]
 
 
@@ -167,6 +172,8 @@ def test_gather_form_statistics_epilogue(petsyn, n, d, h, w, cin, cout, k, s, p)
     bias = torch.randn(cout, generator=g).to(dev)
     plan = ops.ConvPlan(ops.OP_CONV, n, d, h, w, cin, cout, k, s, p)
     assert plan.epi_stats_ok and plan.kernel_path[0] == 0 and not plan.epi_ok[0]
+    if n * d * h * w // s ** 3 <= 2048:
+        assert plan.workspace is not None          # the plan splits K
     plan.pack(wt, need_dgrad=False)
     od, oh, ow = plan.out_dims
     y_plain = torch.zeros(n, od, oh, ow, cout, dtype=torch.bfloat16, device=dev)
