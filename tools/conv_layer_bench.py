@@ -38,6 +38,9 @@ LAYERS = {
     "q64_64": (ops.OP_CONV, 2, 24, 32, 24, 64, 64, 3, 1, 1),        # quarter resolution (level 2)
     "q128_64": (ops.OP_CONV, 2, 24, 32, 24, 128, 64, 3, 1, 1),
     "e128_128": (ops.OP_CONV, 2, 12, 16, 12, 128, 128, 3, 1, 1),    # eighth resolution (level 3): split-K + finish
+    # BMGAN dense_unet_generator (configs[2]) at 96x128x96, batch 1: input-layer and first dense-block convolutions
+    "b64_64": (ops.OP_CONV, 1, 96, 128, 96, 64, 64, 3, 1, 1),
+    "b192_128": (ops.OP_CONV, 1, 48, 64, 48, 192, 128, 3, 1, 1),
 }
 
 
@@ -68,18 +71,22 @@ def main():
               "wgrad": lambda: plan.wgrad(x, dy, dw)}
     if args.which == "epi":
         from petsyn_b200._cabi import ConvEpilogue, check, lib, ptr, stream_ptr
-        assert plan.epi_ok[0], "no fused epilogue for this layer's forward pass"
+        assert plan.epi_stats_ok, "no fused epilogue for this layer's forward pass"
         res = torch.randn(n, od, oh, ow, cout, generator=g).to(dev).to(torch.bfloat16)
         st = torch.zeros(n, 2, cout, dtype=torch.float64, device=dev)
         e_st, e_rs, e_r = ConvEpilogue(), ConvEpilogue(), ConvEpilogue()
         e_st.stats1, e_st.stats1_c = ptr(st), cout
         e_rs.side, e_rs.side_cstride, e_rs.add_side, e_rs.stats1, e_rs.stats1_c = ptr(res), cout, 1, ptr(st), cout
         e_r.side, e_r.side_cstride, e_r.add_side = ptr(res), cout, 1
-        passes = {"fprop": passes["fprop"], "fprop+stats": lambda: plan.fprop_epi(x, y, None, e_st),
-                  "fprop+res": lambda: plan.fprop_epi(x, y, None, e_r),
-                  "fprop+res+stats": lambda: plan.fprop_epi(x, y, None, e_rs),
-                  "stats_pass": lambda: check(lib.petsyn_norm_stats(ptr(y), ptr(st), od * oh * ow, cout, n, stream_ptr())),
-                  "dgrad": passes["dgrad"]}
+        if not plan.epi_ok[0]:         # gather-form kernel (or its split-K finish pass): statistics targets only
+            passes = {"fprop": passes["fprop"], "fprop+stats": lambda: plan.fprop_epi(x, y, None, e_st),
+                      "stats_pass": lambda: check(lib.petsyn_norm_stats(ptr(y), ptr(st), od * oh * ow, cout, n, stream_ptr()))}
+        else:
+            passes = {"fprop": passes["fprop"], "fprop+stats": lambda: plan.fprop_epi(x, y, None, e_st),
+                      "fprop+res": lambda: plan.fprop_epi(x, y, None, e_r),
+                      "fprop+res+stats": lambda: plan.fprop_epi(x, y, None, e_rs),
+                      "stats_pass": lambda: check(lib.petsyn_norm_stats(ptr(y), ptr(st), od * oh * ow, cout, n, stream_ptr())),
+                      "dgrad": passes["dgrad"]}
         if plan.epi_ok[1]:
             z = torch.randn(n, d, h, w, cin, generator=g).to(dev).to(torch.bfloat16)
             f = lambda: torch.rand(n, cin, generator=g).to(dev) + 0.5
