@@ -962,7 +962,10 @@ static int32_t run_side(GemmSide& g, const ViewSpec& vc, void* c, const float* b
     if (ep != nullptr) {             // the finish pass also sums what it stores (statistics for the consuming normalisation)
       const int64_t rps = g.out_rows_full / batch;
       const int rpp = 256 / (g.R / 8);
-      const int bx = (int)std::max<int64_t>(1, std::min<int64_t>((rps + rpp - 1) / rpp, std::max(1, 148 * 4 / batch)));
+      // two CTAs per SM: every CTA ends with 2 C double atomics, so more (smaller) CTAs cost more than they spread (512 channels,
+      // 2304 rows: +10 us over the plain finish pass with 592 CTAs, +4 us with 296)
+      static const int waves = getenv("PETSYN_FINISH_WAVES") ? std::max(1, atoi(getenv("PETSYN_FINISH_WAVES"))) : 2;
+      const int bx = (int)std::max<int64_t>(1, std::min<int64_t>((rps + rpp - 1) / rpp, std::max(1, 148 * waves / batch)));
       PETSYN_CHECK_CUDA(launch_pdl(splitk_finish_stats_kernel, dim3(bx, batch), dim3(256), 0, st,
                                    reinterpret_cast<const float*>(g.workspace), g.ksplit, reinterpret_cast<__nv_bfloat16*>(c), rps,
                                    g.R, vc.cstride, vc.coff, bias, act, slope, ep->stats1, ep->stats1_c, ep->stats1_coff,

@@ -41,6 +41,8 @@ LAYERS = {
     # BMGAN dense_unet_generator (configs[2]) at 96x128x96, batch 1: input-layer and first dense-block convolutions
     "b64_64": (ops.OP_CONV, 1, 96, 128, 96, 64, 64, 3, 1, 1),
     "b192_128": (ops.OP_CONV, 1, 48, 64, 48, 192, 128, 3, 1, 1),
+    "b512_512": (ops.OP_CONV, 1, 12, 16, 12, 512, 512, 3, 1, 1),    # split-K + finish
+    "b256_256": (ops.OP_CONV, 1, 24, 32, 24, 256, 256, 3, 1, 1),
 }
 
 
