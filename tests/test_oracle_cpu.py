@@ -269,3 +269,27 @@ def test_unet_family_oracle_matches_golden(name):
     for k, p in params.items():
         ref = float(gold["gradnorm/" + k])
         assert abs(p.grad.double().norm().item() - ref) <= 1e-4 * ref + 1e-7, k
+
+
+@pytest.mark.parametrize("name", sorted(UNET_FAMILIES))
+def test_unet_family_modules_have_the_reference_keys(name):
+    """The drop-in containers of the non-default constructor families register the reference's parameters under the reference's
+    names, in its order (the fixture stores the live class's state-dict keys); construction needs no GPU."""
+    import functools
+    import petsyn
+    norm, affine, drop = UNET_FAMILIES[name]
+    gold = np.load(os.path.join(GOLD, name + ".npz"))
+    nd, ngf, seed = int(gold["num_downs"]), int(gold["ngf"]), int(gold["seed"])
+    if norm == "instance":
+        layer = functools.partial(torch.nn.InstanceNorm3d, affine=True) if affine else torch.nn.InstanceNorm3d
+    else:
+        layer = torch.nn.BatchNorm3d
+    m = petsyn.UnetGenerator3d(1, 1, num_downs=nd, ngf=ngf, norm_layer=layer, use_dropout=drop)
+    assert list(m.state_dict().keys()) == [str(k) for k in gold["keys"]]
+    assert not m.default_family()
+    ref_sd = unet_family_state_dict([str(k) for k in gold["keys"]], nd, ngf, seed)
+    m.load_state_dict(ref_sd)                                   # a reference checkpoint of that family loads unchanged
+    with pytest.raises(RuntimeError):
+        m(torch.zeros(1, 1, 64, 64, 64))                        # no CPU path
+    with pytest.raises(NotImplementedError):
+        petsyn.UnetGenerator3d(1, 1, num_downs=nd, ngf=ngf, norm_layer=torch.nn.GroupNorm)
