@@ -293,3 +293,19 @@ def test_unet_family_modules_have_the_reference_keys(name):
         m(torch.zeros(1, 1, 64, 64, 64))                        # no CPU path
     with pytest.raises(NotImplementedError):
         petsyn.UnetGenerator3d(1, 1, num_downs=nd, ngf=ngf, norm_layer=torch.nn.GroupNorm)
+
+
+@pytest.mark.parametrize("cfg_name", ["TRAINING_JSON", "SMOKE_CFG", "ATTN_ONLY_CFG", "TWO_LAYER_CFG"])
+def test_atten_unet_modules_have_the_reference_keys(cfg_name):
+    """petsyn.AttenUNet registers, for every constructor family with a fixture, exactly the parameters the reference class does
+    (names, order, shapes; the fixtures' ``wsum/<key>`` entries were written from the live class's named_parameters())."""
+    import petsyn
+    from oracle import atten_unet as OA
+    cfg = getattr(OA, cfg_name)
+    m = petsyn.AttenUNet(**cfg)
+    shapes = OA.param_shapes(cfg)
+    assert [(k, tuple(v.shape)) for k, v in m.state_dict().items()] == [(k, tuple(s)) for k, s in shapes.items()]
+    fixture = {"TRAINING_JSON": "atten_unet_2x32x48x32", "SMOKE_CFG": "atten_unet_smoke_1x44x64x44",
+               "ATTN_ONLY_CFG": "atten_unet_attnonly_1x32x48x32", "TWO_LAYER_CFG": "atten_unet_twolayer_1x32x48x32"}[cfg_name]
+    gold = np.load(os.path.join(GOLD, fixture + ".npz"))
+    assert sorted(k[len("wsum/"):] for k in gold.files if k.startswith("wsum/")) == sorted(shapes)
